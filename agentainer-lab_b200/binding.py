@@ -1,0 +1,314 @@
+"""ctypes mirror of include/agentainer_gpu.h.  Test / bench harness only: the reference-facing boundary is the
+C-ABI itself (a Go host binds it with cgo).  Method names follow the ABI one to one."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import constants as K
+from .build import build_native, lib_path
+
+record_dtype = np.dtype([
+    ("request_id", "u1", 16), ("replay_of", "u1", 16), ("agent_id", "S32"), ("seq", "<u8"), ("flags", "<u4"),
+    ("path_len", "<u2"), ("hdr_len", "<u2"), ("body_len", "<u4"), ("status", "u1"), ("retry_count", "u1"),
+    ("max_retries", "u1"), ("error_code", "u1"), ("resp_status", "<u2"), ("reserved0", "<u2"), ("reserved1", "<u4"),
+    ("payload", "u1", 416)])
+outcome_dtype = np.dtype([
+    ("request_id", "u1", 16), ("agent_id", "S32"), ("kind", "u1"), ("reserved0", "u1"), ("http_status", "<u2"),
+    ("reserved1", "<u4"), ("seq", "<u8")])
+verdict_dtype = np.dtype([("code", "u1"), ("flags", "u1"), ("http_status", "<u2"), ("agent_slot", "<u4")])
+dispatch_dtype = np.dtype([("rid", "<u8"), ("agent_slot", "<u4"), ("reserved", "<u4"), ("request_id", "u1", 16)])
+assert record_dtype.itemsize == 512 and outcome_dtype.itemsize == 64
+assert verdict_dtype.itemsize == 8 and dispatch_dtype.itemsize == 32
+
+
+class AgrConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("slab_rows", C.c_uint64), ("table_slots", C.c_uint64),
+                ("max_agents", C.c_uint32), ("max_batch", C.c_uint32), ("log_entries", C.c_uint64),
+                ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class AgrStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "rows_used", "rows_cap", "ingested", "stored", "replay_flagged", "dedupe_hits", "forwarded", "queued",
+        "unavailable", "not_found", "dup_ids", "completions", "completion_misses", "failures", "dead_lettered",
+        "dial_errors", "replay_scans", "replay_dispatched", "completed_log_len", "failed_log_len",
+        "k1_launches", "k2_launches", "k3_launches", "k4_launches")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
+
+
+class AgrSynth(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_agents", C.c_uint32), ("zipf_milli", C.c_uint32),
+                ("dup_permille", C.c_uint32), ("reserved", C.c_uint32), ("agent_nanos0", C.c_uint64)]
+
+
+# every symbol include/agentainer_gpu.h declares (tests/test_abi.py cross-checks this list against the header)
+ABI_SYMBOLS = [
+    "agr_create", "agr_destroy", "agr_abi_version", "agr_last_error", "agr_strerror",
+    "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
+    "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
+    "agr_host_alloc", "agr_host_free", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
+    "agr_stream", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
+    "agr_agent_hash", "agr_agent_shard",
+]
+
+_lib = None
+
+
+class AgrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"agr error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """Load libagentainer_b200.so (building it first if the sources are newer).  Fails loudly: no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or lib_path()
+    if path is None:
+        try:
+            p = build_native()
+        except RuntimeError:
+            if not os.path.exists(p):
+                raise
+    lib = C.CDLL(p)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    sig = {
+        "agr_create": (i32, [C.POINTER(AgrConfig), C.POINTER(vp)]),
+        "agr_destroy": (None, [vp]),
+        "agr_abi_version": (u32, []),
+        "agr_last_error": (C.c_char_p, []),
+        "agr_strerror": (C.c_char_p, [i32]),
+        "agr_set_agent_state": (i32, [vp, C.c_char_p, C.c_uint8]),
+        "agr_drop_agent": (i32, [vp, C.c_char_p]),
+        "agr_agent_slot": (i32, [vp, C.c_char_p]),
+        "agr_ingest": (i32, [vp, vp, u32, vp, C.POINTER(u64)]),
+        "agr_complete": (i32, [vp, vp, u32, vp]),
+        "agr_replay_scan": (i32, [vp, vp, vp, u32, C.POINTER(u32)]),
+        "agr_pending": (i32, [vp, C.c_char_p, vp, u32, C.POINTER(u32)]),
+        "agr_get_record": (i32, [vp, C.c_char_p, vp, vp]),
+        "agr_list": (i32, [vp, C.c_char_p, i32, vp, u32, C.POINTER(u32)]),
+        "agr_stats_get": (i32, [vp, C.POINTER(AgrStats)]),
+        "agr_host_alloc": (vp, [C.c_size_t]),
+        "agr_host_free": (None, [vp]),
+        "agr_reserve_rows": (i32, [vp, u32, C.POINTER(u64)]),
+        "agr_ingest_rows": (i32, [vp, u64, u32, vp]),
+        "agr_ingest_rows_async": (i32, [vp, u64, u32]),
+        "agr_sync": (i32, [vp]),
+        "agr_stream": (vp, [vp]),
+        "agr_slab_ptr": (vp, [vp, u64]),
+        "agr_synth_agent_id": (i32, [C.POINTER(AgrSynth), u32, C.c_char_p]),
+        "agr_synth_fill_host": (i32, [C.POINTER(AgrSynth), u64, u32, vp]),
+        "agr_synth_fill_rows": (i32, [vp, C.POINTER(AgrSynth), u64, u64, u32]),
+        "agr_agent_hash": (u64, [C.c_char_p]),
+        "agr_agent_shard": (u32, [C.c_char_p, u32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.agr_abi_version() != 1:
+        raise RuntimeError("ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, rc: int) -> int:
+    if rc < 0:
+        raise AgrError(rc, (lib.agr_last_error() or b"").decode())
+    return rc
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _synth(seed, n_agents, zipf_milli=0, dup_permille=0, agent_nanos0=0) -> AgrSynth:
+    return AgrSynth(seed, n_agents, zipf_milli, dup_permille, 0, agent_nanos0)
+
+
+def synth_fill_host(first_index: int, n: int, *, seed=1, n_agents=16, zipf_milli=0, dup_permille=0,
+                    agent_nanos0=0, out: Optional[np.ndarray] = None) -> np.ndarray:
+    lib = load_library()
+    if out is None:
+        out = np.zeros(n, dtype=record_dtype)
+    s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0)
+    _check(lib, lib.agr_synth_fill_host(C.byref(s), first_index, n, _ptr(out)))
+    return out
+
+
+def synth_agent_id(k: int, *, agent_nanos0=0) -> str:
+    lib = load_library()
+    buf = C.create_string_buffer(32)
+    s = _synth(0, 1, 0, 0, agent_nanos0)
+    _check(lib, lib.agr_synth_agent_id(C.byref(s), k, buf))
+    return buf.value.decode()
+
+
+def agent_hash(agent_id: str) -> int:
+    return load_library().agr_agent_hash(agent_id.encode())
+
+
+def agent_shard(agent_id: str, n: int) -> int:
+    return load_library().agr_agent_shard(agent_id.encode(), n)
+
+
+class PinnedArray:
+    """numpy view over agr_host_alloc memory (the zero-copy producer path)."""
+
+    def __init__(self, lib, n: int, dtype):
+        self.lib = lib
+        nbytes = max(1, n * np.dtype(dtype).itemsize)
+        self.ptr = lib.agr_host_alloc(nbytes)
+        if not self.ptr:
+            raise AgrError(K.AGR_ENOMEM, "agr_host_alloc failed")
+        buf = (C.c_uint8 * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.agr_host_free(self.ptr)
+            self.ptr = None
+
+
+class Engine:
+    """One shard (one GPU) of the request engine.  Thin wrapper: every method is one C-ABI call."""
+
+    def __init__(self, *, device=-1, slab_rows=1 << 16, max_agents=1024, max_batch=0, flags=0, table_slots=0,
+                 log_entries=0, k1_variant=0):
+        self.lib = load_library()
+        cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
+                        log_entries, k1_variant, 0)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.agr_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.max_batch = cfg.max_batch
+
+    def close(self):
+        if self.h:
+            self.lib.agr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- agent table
+    def set_agent_state(self, agent_id: str, status) -> int:
+        code = K.AGENT_STATUS_CODES[status] if isinstance(status, str) else int(status)
+        return _check(self.lib, self.lib.agr_set_agent_state(self.h, agent_id.encode(), code))
+
+    def drop_agent(self, agent_id: str) -> None:
+        _check(self.lib, self.lib.agr_drop_agent(self.h, agent_id.encode()))
+
+    def agent_slot(self, agent_id: str) -> int:
+        return _check(self.lib, self.lib.agr_agent_slot(self.h, agent_id.encode()))
+
+    # ---- K1
+    def ingest(self, recs: np.ndarray, want_verdicts: bool = True) -> Tuple[Optional[np.ndarray], int]:
+        assert recs.dtype == record_dtype and recs.flags["C_CONTIGUOUS"]
+        n = len(recs)
+        out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
+        first = C.c_uint64()
+        _check(self.lib, self.lib.agr_ingest(self.h, _ptr(recs), n, _ptr(out) if want_verdicts else None, C.byref(first)))
+        return out, first.value
+
+    def reserve_rows(self, n: int) -> int:
+        first = C.c_uint64()
+        _check(self.lib, self.lib.agr_reserve_rows(self.h, n, C.byref(first)))
+        return first.value
+
+    def ingest_rows(self, first_rid: int, n: int, want_verdicts: bool = True) -> Optional[np.ndarray]:
+        out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
+        _check(self.lib, self.lib.agr_ingest_rows(self.h, first_rid, n, _ptr(out) if want_verdicts else None))
+        return out
+
+    def ingest_rows_async(self, first_rid: int, n: int) -> None:
+        _check(self.lib, self.lib.agr_ingest_rows_async(self.h, first_rid, n))
+
+    def sync(self) -> None:
+        _check(self.lib, self.lib.agr_sync(self.h))
+
+    def stream(self) -> int:
+        return self.lib.agr_stream(self.h) or 0
+
+    def slab_ptr(self, rid: int) -> int:
+        return self.lib.agr_slab_ptr(self.h, rid) or 0
+
+    def synth_fill_rows(self, first_index: int, first_rid: int, n: int, *, seed=1, n_agents=16, zipf_milli=0,
+                        dup_permille=0, agent_nanos0=0) -> None:
+        s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0)
+        _check(self.lib, self.lib.agr_synth_fill_rows(self.h, C.byref(s), first_index, first_rid, n))
+
+    def pinned(self, n: int, dtype=record_dtype) -> PinnedArray:
+        return PinnedArray(self.lib, n, dtype)
+
+    # ---- K2
+    def complete(self, outs: np.ndarray, want_results: bool = True) -> Optional[np.ndarray]:
+        assert outs.dtype == outcome_dtype and outs.flags["C_CONTIGUOUS"]
+        n = len(outs)
+        res = np.zeros(n, dtype=np.int32) if want_results else None
+        _check(self.lib, self.lib.agr_complete(self.h, _ptr(outs), n, _ptr(res) if want_results else None))
+        return res
+
+    # ---- K3
+    def replay_scan(self, with_records: bool = True, cap: int = 1 << 16):
+        while True:
+            disp = np.zeros(cap, dtype=dispatch_dtype)
+            recs = np.zeros(cap, dtype=record_dtype) if with_records else None
+            n = C.c_uint32()
+            rc = self.lib.agr_replay_scan(self.h, _ptr(disp), _ptr(recs) if with_records else None, cap, C.byref(n))
+            if rc == K.AGR_ECAP:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc)
+            return disp[: n.value], (recs[: n.value] if with_records else None)
+
+    def pending(self, agent_id: str, cap: int = 1 << 12) -> np.ndarray:
+        while True:
+            out = np.zeros(cap, dtype=record_dtype)
+            n = C.c_uint32()
+            rc = self.lib.agr_pending(self.h, agent_id.encode(), _ptr(out), cap, C.byref(n))
+            if rc == K.AGR_ECAP:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc)
+            return out[: n.value]
+
+    def get_record(self, agent_id: str, request_id: bytes) -> Optional[np.ndarray]:
+        out = np.zeros(1, dtype=record_dtype)
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        rc = self.lib.agr_get_record(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), _ptr(out))
+        if rc == K.AGR_ENOTFOUND:
+            return None
+        _check(self.lib, rc)
+        return out[0]
+
+    def list(self, agent_id: str, which: int, cap: int = 1 << 12) -> np.ndarray:
+        while True:
+            ids = np.zeros((cap, 16), dtype=np.uint8)
+            n = C.c_uint32()
+            rc = self.lib.agr_list(self.h, agent_id.encode(), which, _ptr(ids), cap, C.byref(n))
+            if rc == K.AGR_ECAP:
+                cap = int(n.value)
+                continue
+            _check(self.lib, rc)
+            return ids[: n.value]
+
+    def stats(self) -> dict:
+        s = AgrStats()
+        _check(self.lib, self.lib.agr_stats_get(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in AgrStats._fields_}

@@ -1,0 +1,715 @@
+// agr_engine.cu — host side of the engine and the C-ABI of include/agentainer_gpu.h.
+//
+// One agr_handle == one GPU shard: HBM slab + SoA state + dedupe index + logs + agent-table mirror, one stream.
+// Calls are linearised by the handle mutex; the order in which calls take it is the event order the state
+// machine sees (the reference's serialisation point is the single-threaded Redis server).
+// There is NO CPU fallback: every state transition happens in the kernels of agr_kernels.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/agentainer_gpu.h"
+#include "agr_kernels.cuh"
+
+static_assert(sizeof(agr_record) == 512, "agr_record must be 512 B");
+static_assert(sizeof(agr_outcome) == 64, "agr_outcome must be 64 B");
+static_assert(sizeof(agr_dispatch) == 32, "agr_dispatch must be 32 B");
+static_assert(sizeof(agr_verdict) == 8, "agr_verdict must be 8 B");
+static_assert(sizeof(agr_slot) == 32, "agr_slot must be 32 B");
+static_assert(sizeof(agr_agent_key) == 48, "agr_agent_key must be 48 B");
+static_assert(sizeof(agr_dop) == 32, "agr_dop must be 32 B");
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(AGR_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+struct agr_handle {
+    std::mutex mu;
+    agr_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    agr_dev d{};
+    uint64_t rows_used = 0;
+    uint64_t scan_lo = 0;     // every row below has left its pending list for good
+    // host agent map + mirror
+    std::unordered_map<std::string, uint32_t> slot_of;
+    std::vector<std::string> agent_names;
+    std::vector<uint8_t> agent_status;
+    std::vector<agr_agent_key> akeys_host;
+    // staging
+    uint8_t* bounce[2] = {nullptr, nullptr};   // pinned, for pageable caller buffers
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    uint32_t* h_state = nullptr;               // pinned [max_batch]
+    uint32_t* h_route = nullptr;
+    agr_dop* h_ops = nullptr;                  // pinned [max_batch]
+    int32_t* h_results = nullptr;              // pinned [max_batch]
+    agr_k2_scratch k2{};
+    agr_dop* d_ops = nullptr;
+    // K3
+    uint32_t* d_matrix = nullptr; size_t matrix_entries = 0;
+    uint32_t* d_gtotal = nullptr; uint32_t* d_goff = nullptr;
+    uint32_t* d_out_rid = nullptr; uint32_t* d_out_slot = nullptr; uint32_t out_cap = 0;
+    uint32_t* d_min_inq = nullptr;
+    uint8_t* d_gather = nullptr; size_t gather_bytes = 0;
+    uint8_t* h_gather = nullptr; size_t h_gather_bytes = 0;
+    uint32_t* h_small = nullptr;               // pinned scratch (>= 64 words)
+    unsigned long long* d_cdf = nullptr; uint32_t cdf_n = 0;
+    // launch accounting
+    uint64_t k1_launches = 0, k2_launches = 0, k3_launches = 0, k4_launches = 0;
+    uint64_t replay_scans = 0, replay_dispatched = 0;
+    std::vector<void*> dev_allocs, host_allocs;
+};
+
+template <typename T>
+static int dev_alloc(agr_handle* h, T** p, size_t count, bool zero) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail(AGR_ENOMEM, std::string("cudaMalloc ") + std::to_string(count * sizeof(T)) + " B: " + cudaGetErrorString(e));
+    if (zero) { e = cudaMemsetAsync(q, 0, count * sizeof(T), h->stream); if (e != cudaSuccess) return fail(AGR_ECUDA, cudaGetErrorString(e)); }
+    h->dev_allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+template <typename T>
+static int host_alloc(agr_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaHostAlloc(&q, count * sizeof(T), cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(AGR_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    h->host_allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+#define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
+
+static uint64_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+static void pack_agent_id(const char* id, unsigned long long w[4]) {
+    char buf[AGR_AGENT_ID_BYTES];
+    memset(buf, 0, sizeof buf);
+    strncpy(buf, id, AGR_AGENT_ID_BYTES - 1);
+    memcpy(w, buf, 32);
+}
+
+extern "C" {
+
+uint32_t agr_abi_version(void) { return AGR_ABI_VERSION; }
+const char* agr_last_error(void) { return g_err.c_str(); }
+const char* agr_strerror(int code) {
+    switch (code) {
+        case AGR_OK: return "ok";
+        case AGR_EINVAL: return "invalid argument";
+        case AGR_ENODEV: return "no usable CUDA device";
+        case AGR_ENOMEM: return "out of memory";
+        case AGR_ENOSPC: return "capacity exhausted";
+        case AGR_ENOTFOUND: return "not found";
+        case AGR_ECUDA: return "CUDA error";
+        case AGR_ECAP: return "output array too small";
+        case AGR_ECOMM: return "multi-GPU exchange error";
+        default: return "unknown error";
+    }
+}
+
+void* agr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+void agr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int create_impl(const agr_config* cfg_in, agr_handle* h) {
+    agr_config c{};
+    if (cfg_in) c = *cfg_in;
+    if (c.flags == 0) c.flags = AGR_CFG_PERSISTENCE;
+    if (c.slab_rows == 0) c.slab_rows = 1ull << 20;
+    if (c.slab_rows >= 0x7fffffffull) return fail(AGR_EINVAL, "slab_rows must be < 2^31");
+    if (c.table_slots == 0) c.table_slots = next_pow2(c.slab_rows * 2);
+    if (c.table_slots & (c.table_slots - 1)) return fail(AGR_EINVAL, "table_slots must be a power of two");
+    if (c.table_slots < c.slab_rows + c.slab_rows / 4) return fail(AGR_EINVAL, "table_slots must be >= 1.25 * slab_rows");
+    if (c.table_slots > (1ull << 32)) return fail(AGR_EINVAL, "table_slots must be <= 2^32");
+    if (c.max_agents == 0) c.max_agents = 4096;
+    if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
+    if (c.max_batch == 0) c.max_batch = 1u << 20;
+    if (c.log_entries == 0) c.log_entries = c.slab_rows * 2;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(AGR_ENODEV, "no CUDA device visible (this library has no CPU fallback)"); }
+    int dev = c.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(AGR_ENODEV, "cudaGetDevice failed"); }
+    if (dev >= ndev) return fail(AGR_ENODEV, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(AGR_ENODEV, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only");
+    CK(cudaSetDevice(dev));
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    h->cfg = c;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    agr_dev& d = h->d;
+    TRY(dev_alloc(h, &d.slab, (size_t)c.slab_rows * AGR_REC, false));
+    TRY(dev_alloc(h, &d.state, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.route, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.aux, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.cksum, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.table, c.table_slots, true));
+    d.table_mask = c.table_slots - 1;
+    uint32_t acap = (uint32_t)next_pow2((uint64_t)c.max_agents * 2);
+    TRY(dev_alloc(h, &d.akeys, acap, true));
+    d.amask = acap - 1;
+    h->akeys_host.assign(acap, agr_agent_key{});
+    TRY(dev_alloc(h, &d.astatus, c.max_agents, true));
+    TRY(dev_alloc(h, &d.pend_cnt, c.max_agents, true));
+    TRY(dev_alloc(h, &d.comp_cnt, c.max_agents, true));
+    TRY(dev_alloc(h, &d.fail_cnt, c.max_agents, true));
+    TRY(dev_alloc(h, &d.ctr, (size_t)C_NCTR, true));
+    TRY(dev_alloc(h, &d.completed_log, c.log_entries, false));
+    TRY(dev_alloc(h, &d.failed_log, c.log_entries, false));
+    TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
+    d.log_cap = c.log_entries;
+    TRY(dev_alloc(h, &d.dupfix, (size_t)1, true));
+    d.cfg_flags = c.flags;
+    // staging
+    h->bounce_bytes = std::min<size_t>((size_t)c.max_batch * AGR_REC, (size_t)32 << 20);
+    for (int k = 0; k < 2; ++k) {
+        TRY(host_alloc(h, &h->bounce[k], h->bounce_bytes));
+        CK(cudaEventCreateWithFlags(&h->bounce_ev[k], cudaEventDisableTiming));
+    }
+    TRY(host_alloc(h, &h->h_state, c.max_batch));
+    TRY(host_alloc(h, &h->h_route, c.max_batch));
+    TRY(host_alloc(h, &h->h_ops, c.max_batch));
+    TRY(host_alloc(h, &h->h_results, c.max_batch));
+    TRY(host_alloc(h, &h->h_small, (size_t)64));
+    TRY(dev_alloc(h, &h->d_ops, c.max_batch, false));
+    h->k2.ops = h->d_ops;
+    TRY(dev_alloc(h, &h->k2.nxt, c.max_batch, false));
+    TRY(dev_alloc(h, &h->k2.hrid, c.max_batch, false));
+    TRY(dev_alloc(h, &h->k2.hidx, c.max_batch, false));
+    TRY(dev_alloc(h, &h->k2.eff, c.max_batch, false));
+    TRY(dev_alloc(h, &h->k2.results, c.max_batch, false));
+    TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048, false));
+    TRY(dev_alloc(h, &h->d_gtotal, (size_t)c.max_agents + 1, false));
+    TRY(dev_alloc(h, &h->d_goff, (size_t)c.max_agents + 2, false));
+    TRY(dev_alloc(h, &h->d_min_inq, (size_t)1, false));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_create(const agr_config* cfg, agr_handle** out) {
+    if (!out) return fail(AGR_EINVAL, "out is NULL");
+    *out = nullptr;
+    agr_handle* h = new agr_handle();
+    int r = create_impl(cfg, h);
+    if (r < 0) { std::string keep = g_err; agr_destroy(h); g_err = keep; return r; }
+    *out = h;
+    return 0;
+}
+
+void agr_destroy(agr_handle* h) {
+    if (!h) return;
+    if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    for (void* p : h->dev_allocs) cudaFree(p);
+    for (void* p : h->host_allocs) cudaFreeHost(p);
+    for (int k = 0; k < 2; ++k) if (h->bounce_ev[k]) cudaEventDestroy(h->bounce_ev[k]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------ agent table
+static int agent_find(agr_handle* h, const char* id) {
+    auto it = h->slot_of.find(std::string(id));
+    return it == h->slot_of.end() ? -1 : (int)it->second;
+}
+
+int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
+    if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
+    size_t len = strnlen(agent_id, AGR_AGENT_ID_BYTES);
+    if (len == 0 || len >= AGR_AGENT_ID_BYTES) return fail(AGR_EINVAL, "agent id must be 1..31 bytes");
+    if (status > AGR_AGENT_FAILED) return fail(AGR_EINVAL, "bad agent status");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) {
+        if (h->agent_names.size() >= h->cfg.max_agents) return fail(AGR_ENOSPC, "agent table full");
+        slot = (int)h->agent_names.size();
+        h->agent_names.emplace_back(agent_id);
+        h->agent_status.push_back(status);
+        h->slot_of.emplace(std::string(agent_id), (uint32_t)slot);
+        agr_agent_key key{};
+        pack_agent_id(agent_id, key.w);
+        key.slot = (uint32_t)slot;
+        uint32_t idx = (uint32_t)agr_hash_agent(key.w[0], key.w[1], key.w[2], key.w[3]) & h->d.amask;
+        while (h->akeys_host[idx].w[0] | h->akeys_host[idx].w[1] | h->akeys_host[idx].w[2] | h->akeys_host[idx].w[3])
+            idx = (idx + 1) & h->d.amask;
+        h->akeys_host[idx] = key;
+        // status first, then the key that makes the slot reachable; both are stream-ordered before the next kernel
+        CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d.akeys + idx, &key, sizeof key, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        h->agent_status[slot] = status;
+        CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
+    }
+    return slot;
+}
+
+int agr_agent_slot(agr_handle* h, const char* agent_id) {
+    if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    int s = agent_find(h, agent_id);
+    if (s < 0 || h->agent_status[s] == AG_STATUS_REMOVED) return fail(AGR_ENOTFOUND, "agent not found");
+    return s;
+}
+
+int agr_drop_agent(agr_handle* h, const char* agent_id) {
+    if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return fail(AGR_ENOTFOUND, "agent not found");
+    h->agent_status[slot] = AG_STATUS_REMOVED;
+    uint8_t st = AG_STATUS_REMOVED;
+    CK(cudaMemcpyAsync(h->d.astatus + slot, &st, 1, cudaMemcpyHostToDevice, h->stream));   // DEL agent:{id} (agent.go:344)
+    unsigned long long lens[2];
+    CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    agr_launch_drop_agent(h->d, (uint32_t)slot, h->rows_used, std::max(lens[0], lens[1]), h->stream);
+    h->k3_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    if (h->rows_used + n > h->cfg.slab_rows) return fail(AGR_ENOSPC, "slab full");
+    *first = h->rows_used;
+    h->rows_used += n;
+    return 0;
+}
+
+static void expand_verdicts(const uint32_t* route, uint32_t n, agr_verdict* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t r = route[i];
+        agr_verdict v;
+        v.code = (uint8_t)rt_code(r);
+        v.flags = (uint8_t)rt_flags(r);
+        v.agent_slot = rt_slot(r);
+        switch (v.code) {
+            case AGR_V_QUEUED: v.http_status = 202; break;
+            case AGR_V_UNAVAILABLE: v.http_status = 503; break;
+            case AGR_V_NOT_FOUND: v.http_status = 404; break;
+            default: v.http_status = 0; break;
+        }
+        out[i] = v;
+    }
+}
+
+static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, bool sync) {
+    if (first + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
+    if (n == 0) return 0;
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->sm_count, h->stream);
+    h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
+    CK(cudaGetLastError());
+    if (out) {
+        CK(cudaMemcpyAsync(h->h_route, h->d.route + first, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        expand_verdicts(h->h_route, n, out);
+    } else if (sync) {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int agr_reserve_rows(agr_handle* h, uint32_t n, uint64_t* first_rid) {
+    if (!h || !first_rid) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return reserve_rows_locked(h, n, first_rid);
+}
+int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out) {
+    if (!h) return fail(AGR_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return ingest_rows_locked(h, first_rid, n, out, true);
+}
+int agr_ingest_rows_async(agr_handle* h, uint64_t first_rid, uint32_t n) {
+    if (!h) return fail(AGR_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return ingest_rows_locked(h, first_rid, n, nullptr, false);
+}
+int agr_sync(agr_handle* h) {
+    if (!h) return fail(AGR_EINVAL, "NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+void* agr_stream(agr_handle* h) { return h ? (void*)h->stream : nullptr; }
+void* agr_slab_ptr(agr_handle* h, uint64_t rid) { return (h && rid < h->cfg.slab_rows) ? (void*)(h->d.slab + rid * AGR_REC) : nullptr; }
+
+// host -> slab rows.  Pinned (or registered) caller memory is DMA'd in place; pageable memory goes through two
+// pinned bounce buffers so that the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+static int upload_rows(agr_handle* h, const agr_record* recs, uint64_t first, uint32_t n) {
+    uint8_t* dst = h->d.slab + first * AGR_REC;
+    const size_t bytes = (size_t)n * AGR_REC;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, recs) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    if (pinned) {
+        CK(cudaMemcpyAsync(dst, recs, bytes, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    size_t off = 0; int k = 0;
+    while (off < bytes) {
+        size_t chunk = std::min(h->bounce_bytes, bytes - off);
+        CK(cudaEventSynchronize(h->bounce_ev[k]));
+        memcpy(h->bounce[k], (const uint8_t*)recs + off, chunk);
+        CK(cudaMemcpyAsync(dst + off, h->bounce[k], chunk, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaEventRecord(h->bounce_ev[k], h->stream));
+        off += chunk; k ^= 1;
+    }
+    return 0;
+}
+
+int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid) {
+    if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint64_t first = 0;
+    TRY(reserve_rows_locked(h, n, &first));
+    if (first_rid) *first_rid = first;
+    if (n == 0) return 0;
+    TRY(upload_rows(h, recs, first, n));
+    return ingest_rows_locked(h, first, n, out, true);
+}
+
+// ------------------------------------------------------------------------------------------ K2
+int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
+    if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    if (n == 0) return 0;
+    // resolve agent ids on the host (the Go shim holds the id string, not a slot)
+    std::string last_id; uint32_t last_slot = RT_SLOT_NONE;
+    for (uint32_t j = 0; j < n; ++j) {
+        const agr_outcome& o = outs[j];
+        agr_dop& op = h->h_ops[j];
+        memcpy(&op.id_lo, o.request_id, 8);
+        memcpy(&op.id_hi, o.request_id + 8, 8);
+        size_t len = strnlen(o.agent_id, AGR_AGENT_ID_BYTES);
+        if (len != last_id.size() || memcmp(o.agent_id, last_id.data(), len) != 0) {
+            last_id.assign(o.agent_id, len);
+            auto it = h->slot_of.find(last_id);
+            last_slot = (it == h->slot_of.end()) ? RT_SLOT_NONE : it->second;
+        }
+        op.slot = last_slot;
+        op.http = o.http_status;
+        op.kind = o.kind;
+        op.pad = 0;
+        op.seq = o.seq;
+    }
+    CK(cudaMemcpyAsync(h->d_ops, h->h_ops, (size_t)n * sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    agr_launch_k2(h->d, h->k2, n, h->stream);
+    h->k2_launches += 5;
+    CK(cudaGetLastError());
+    if (results) {
+        CK(cudaMemcpyAsync(h->h_results, h->k2.results, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(results, h->h_results, (size_t)n * 4);
+    } else {
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K3
+static int ensure_out(agr_handle* h, uint32_t cap) {
+    if (cap <= h->out_cap) return 0;
+    uint32_t ncap = std::max<uint32_t>(cap, 1024);
+    TRY(dev_alloc(h, &h->d_out_rid, ncap, false));
+    TRY(dev_alloc(h, &h->d_out_slot, ncap, false));
+    h->out_cap = ncap;
+    return 0;
+}
+static int ensure_gather(agr_handle* h, size_t bytes) {
+    if (bytes > h->gather_bytes) { TRY(dev_alloc(h, &h->d_gather, bytes, false)); h->gather_bytes = bytes; }
+    if (bytes > h->h_gather_bytes) { TRY(host_alloc(h, &h->h_gather, bytes)); h->h_gather_bytes = bytes; }
+    return 0;
+}
+
+// runs the stable partition; returns the number selected in *total (may exceed cap: then only counts are valid)
+static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t* log, uint64_t lo, uint64_t hi,
+                         uint32_t cap, uint32_t* total) {
+    *total = 0;
+    if (hi <= lo) return 0;
+    agr_k3_params p{};
+    p.mode = mode; p.slot = slot; p.log = log; p.lo = lo; p.hi = hi;
+    p.groups = (mode == K3_TICK) ? std::max<uint32_t>(1, (uint32_t)h->agent_names.size()) : 1;
+    uint64_t items = hi - lo;
+    uint64_t max_warps = std::max<uint64_t>(1, (4u << 20) / p.groups);
+    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 32, (items + 1023) / 1024);
+    p.nwarps = (uint32_t)std::max<uint64_t>(1, std::min(want, max_warps));
+    uint64_t per = (items + p.nwarps - 1) / p.nwarps;
+    per = (per + 31) & ~31ull;
+    p.per_warp = (uint32_t)per;
+    p.nwarps = (uint32_t)((items + per - 1) / per);
+    size_t need = (size_t)p.nwarps * p.groups;
+    if (need > h->matrix_entries) { TRY(dev_alloc(h, &h->d_matrix, need, false)); h->matrix_entries = need; }
+    TRY(ensure_out(h, cap));
+    p.matrix = h->d_matrix; p.gtotal = h->d_gtotal; p.goff = h->d_goff;
+    p.out_rid = h->d_out_rid; p.out_slot = h->d_out_slot; p.cap = cap;
+    p.min_inq = (mode == K3_TICK) ? h->d_min_inq : nullptr;
+    if (mode == K3_TICK) CK(cudaMemsetAsync(h->d_min_inq, 0xff, 4, h->stream));
+    agr_launch_k3_select(h->d, p, h->sm_count, h->stream);
+    h->k3_launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_small, h->d_goff + p.groups, 4, cudaMemcpyDeviceToHost, h->stream));
+    if (mode == K3_TICK) CK(cudaMemcpyAsync(h->h_small + 1, h->d_min_inq, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *total = h->h_small[0];
+    if (mode == K3_TICK) {
+        uint32_t m = h->h_small[1];
+        h->scan_lo = (m == AGR_RID_NONE) ? hi : std::max<uint64_t>(h->scan_lo, m);
+    }
+    return 0;
+}
+
+int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t cap, uint32_t* n) {
+    if (!h || !n) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    *n = 0;
+    h->replay_scans++;
+    uint32_t total = 0;
+    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    *n = total;
+    if (total > cap) return fail(AGR_ECAP, "dispatch array too small");
+    h->replay_dispatched += total;
+    if (total == 0 || !out) return 0;
+    size_t bytes = (size_t)total * 32 + (recs ? (size_t)total * AGR_REC : 0);
+    TRY(ensure_gather(h, bytes));
+    uint8_t* d_disp = h->d_gather;
+    uint8_t* d_recs = recs ? h->d_gather + (size_t)total * 32 : nullptr;
+    agr_launch_k3_gather(h->d, h->d_out_rid, h->d_out_slot, total, d_recs, d_disp, nullptr, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_gather, (size_t)total * 32);
+    if (recs) memcpy(recs, h->h_gather + (size_t)total * 32, (size_t)total * AGR_REC);
+    return 0;
+}
+
+int agr_pending(agr_handle* h, const char* agent_id, agr_record* out, uint32_t cap, uint32_t* n) {
+    if (!h || !agent_id || !n) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    *n = 0;
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return 0;     // LRANGE on a missing key is an empty list
+    uint32_t total = 0;
+    TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    *n = total;
+    if (total > cap) return fail(AGR_ECAP, "output array too small");
+    if (total == 0 || !out) return 0;
+    size_t bytes = (size_t)total * AGR_REC;
+    TRY(ensure_gather(h, bytes));
+    agr_launch_k3_gather(h->d, h->d_out_rid, nullptr, total, h->d_gather, nullptr, nullptr, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_gather, bytes);
+    return 0;
+}
+
+int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16], uint32_t cap, uint32_t* n) {
+    if (!h || !agent_id || !n) return fail(AGR_EINVAL, "NULL argument");
+    if (which < AGR_LIST_PENDING || which > AGR_LIST_FAILED) return fail(AGR_EINVAL, "bad list selector");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    *n = 0;
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return 0;
+    uint32_t total = 0;
+    if (which == AGR_LIST_PENDING) {
+        TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    } else {
+        unsigned long long lens[2];
+        CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const uint32_t* log = (which == AGR_LIST_COMPLETED) ? h->d.completed_log : h->d.failed_log;
+        uint64_t len = (which == AGR_LIST_COMPLETED) ? lens[0] : lens[1];
+        TRY(select_locked(h, K3_LOG_AGENT, (uint32_t)slot, log, 0, len, cap, &total));
+    }
+    *n = total;
+    if (total > cap) return fail(AGR_ECAP, "output array too small");
+    if (total == 0 || !ids) return 0;
+    size_t bytes = (size_t)total * 16;
+    TRY(ensure_gather(h, bytes));
+    agr_launch_k3_gather(h->d, h->d_out_rid, nullptr, total, nullptr, nullptr, h->d_gather, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(ids, h->h_gather, bytes);
+    return 0;
+}
+
+// storage.Get("agent:{a}:requests:{r}") (server.go:661-662): read-only resolve in the dedupe index, then a 1-row gather
+int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id[16], agr_record* out) {
+    if (!h || !agent_id || !request_id || !out) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return fail(AGR_ENOTFOUND, "request not found");
+    agr_dop& op = h->h_ops[0];
+    memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
+    op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
+    CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    agr_launch_resolve(h->d, h->k2, 1, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
+    TRY(ensure_gather(h, AGR_REC));
+    agr_launch_k3_gather(h->d, h->k2.hrid, nullptr, 1, h->d_gather, nullptr, nullptr, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, AGR_REC, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->h_gather, AGR_REC);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stats
+int agr_stats_get(agr_handle* h, agr_stats* out) {
+    if (!h || !out) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    unsigned long long c[C_NCTR], lens[2];
+    CK(cudaMemcpyAsync(c, h->d.ctr, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memset(out, 0, sizeof *out);
+    out->rows_used = h->rows_used; out->rows_cap = h->cfg.slab_rows;
+    out->ingested = c[C_INGESTED]; out->stored = c[C_STORED]; out->replay_flagged = c[C_REPLAY];
+    out->dedupe_hits = c[C_DEDUPE_HITS]; out->forwarded = c[C_FORWARDED]; out->queued = c[C_QUEUED];
+    out->unavailable = c[C_UNAVAILABLE]; out->not_found = c[C_NOT_FOUND]; out->dup_ids = c[C_DUP_IDS];
+    out->completions = c[C_COMPLETIONS]; out->completion_misses = c[C_COMPLETION_MISSES];
+    out->failures = c[C_FAILURES]; out->dead_lettered = c[C_DEAD_LETTERED]; out->dial_errors = c[C_DIAL_ERRORS];
+    out->replay_scans = h->replay_scans; out->replay_dispatched = h->replay_dispatched;
+    out->completed_log_len = lens[0]; out->failed_log_len = lens[1];
+    out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
+    out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches;
+    out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ synthetic stream
+static agr_synth_dev synth_params(const agr_synth* s, const unsigned long long* cdf) {
+    agr_synth_dev p;
+    p.seed = s->seed; p.n_agents = s->n_agents; p.dup_permille = s->dup_permille;
+    p.agent_nanos0 = s->agent_nanos0 ? s->agent_nanos0 : 1700000000000000000ULL;
+    p.cdf = cdf;
+    return p;
+}
+// Zipf(s = zipf_milli / 1000) cumulative thresholds in pure integer arithmetic, so the table (and therefore the
+// stream) is bit-identical on every host: weight_k = 2^40 * 2^-(s * log2(k+1)), log2 in 32.32 fixed point by
+// repeated squaring, 2^-f as a product of the constants 2^-(2^-(b+1)) obtained from an integer square-root chain.
+typedef unsigned __int128 u128_t;
+static unsigned long long fx_log2(unsigned long long x) {        // integer x >= 1 -> log2(x) in 32.32
+    unsigned long long ip = 0;
+    for (unsigned long long v = x; v >= 2; v >>= 1) ip++;
+    u128_t m = (u128_t)x << (63 - ip);                           // mantissa in [1,2) as Q1.63
+    unsigned long long frac = 0;
+    for (int b = 31; b >= 0; --b) {
+        m = (m * m) >> 63;                                       // square: value in [1,4)
+        if (m >> 64) { m >>= 1; frac |= (1ULL << b); }           // >= 2: emit a one bit, renormalise
+    }
+    return (ip << 32) | frac;
+}
+static unsigned long long isqrt128(u128_t v) {
+    u128_t lo = 0, hi = (u128_t)1 << 64;
+    while (lo + 1 < hi) { u128_t mid = (lo + hi) >> 1; if (mid * mid <= v) lo = mid; else hi = mid; }
+    return (unsigned long long)lo;
+}
+static void zipf_cdf(uint32_t n, uint32_t zipf_milli, std::vector<unsigned long long>& cdf) {
+    unsigned long long r[32];                                    // r[b] = 2^-(2^-(b+1)) in Q0.64
+    r[0] = isqrt128((u128_t)1 << 127);
+    for (int k = 1; k < 32; ++k) r[k] = isqrt128((u128_t)r[k - 1] << 64);
+    std::vector<unsigned long long> w(n);
+    u128_t total = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const unsigned long long y = (unsigned long long)(((u128_t)fx_log2((unsigned long long)k + 1) * zipf_milli) / 1000);
+        const unsigned long long ip = y >> 32, fr = y & 0xffffffffULL;
+        u128_t a = (u128_t)1 << 64;                              // 1.0 in Q1.64
+        for (int b = 0; b < 32; ++b)
+            if (fr & (1ULL << (31 - b))) a = (a * r[b]) >> 64;
+        unsigned long long wk = ip >= 40 ? 0 : (unsigned long long)(a >> 24) >> ip;   // 2^40 * 2^-y
+        w[k] = wk ? wk : 1;
+        total += w[k];
+    }
+    cdf.resize(n);
+    u128_t run = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        run += w[k];
+        u128_t t = (run << 64) / total;
+        cdf[k] = (k + 1 == n || (t >> 64)) ? ~0ULL : (unsigned long long)t;
+    }
+}
+
+int agr_synth_agent_id(const agr_synth* s, uint32_t k, char out[AGR_AGENT_ID_BYTES]) {
+    if (!s || !out) return fail(AGR_EINVAL, "NULL argument");
+    unsigned long long n0 = s->agent_nanos0 ? s->agent_nanos0 : 1700000000000000000ULL;
+    agr_synth_agent_name(n0 + (unsigned long long)k * 1000003ULL, out);
+    return 0;
+}
+int agr_synth_fill_host(const agr_synth* s, uint64_t first_index, uint32_t n, agr_record* out) {
+    if (!s || (n && !out) || s->n_agents == 0) return fail(AGR_EINVAL, "bad argument");
+    std::vector<unsigned long long> cdf;
+    if (s->zipf_milli) zipf_cdf(s->n_agents, s->zipf_milli, cdf);
+    agr_synth_dev p = synth_params(s, s->zipf_milli ? cdf.data() : nullptr);
+    for (uint32_t i = 0; i < n; ++i) agr_synth_record(p, first_index + i, (unsigned char*)&out[i]);
+    return 0;
+}
+int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index, uint64_t first_rid, uint32_t n) {
+    if (!h || !s || s->n_agents == 0) return fail(AGR_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (first_rid + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
+    const unsigned long long* dcdf = nullptr;
+    if (s->zipf_milli) {
+        std::vector<unsigned long long> cdf;
+        zipf_cdf(s->n_agents, s->zipf_milli, cdf);
+        if (h->cdf_n < s->n_agents) { TRY(dev_alloc(h, &h->d_cdf, s->n_agents, false)); h->cdf_n = s->n_agents; }
+        CK(cudaMemcpyAsync(h->d_cdf, cdf.data(), (size_t)s->n_agents * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        dcdf = h->d_cdf;
+    }
+    agr_launch_synth(h->d.slab + first_rid * AGR_REC, synth_params(s, dcdf), first_index, n, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+uint64_t agr_agent_hash(const char* agent_id) { return agent_id ? agr_fnv1a64(agent_id, AGR_AGENT_ID_BYTES) : 0; }
+uint32_t agr_agent_shard(const char* agent_id, uint32_t n_shards) {
+    return n_shards ? (uint32_t)(agr_agent_hash(agent_id) % n_shards) : 0;
+}
+
+}  // extern "C"

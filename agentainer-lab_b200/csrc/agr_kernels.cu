@@ -1,0 +1,659 @@
+// agr_kernels.cu — sm_100a kernels of the request path.
+//
+//   K1  k1_ingest_*  + k1_post   ingest + dedupe + route        (requests.go:64-117, server.go:493-557)
+//   K2  k2_link / k2_apply / k2_offsets / k2_append              (requests.go:120-194,228-275, server.go:583-615)
+//   K3  k3_count / k3_scan_groups / k3_scan_total / k3_scatter / k3_gather
+//                                                                 (replay_worker.go:58-117, requests.go:197-225)
+//
+// All arithmetic is integer / byte work bounded by HBM bandwidth; there is no tensor-core work on this path.
+#include "agr_kernels.cuh"
+#include "../../include/agentainer_gpu.h"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_v4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+struct u128 { unsigned long long lo, hi; };
+__device__ __forceinline__ u128 cas128(void* addr, u128 cmp, u128 val) {
+    u128 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\t"
+                 "mov.b128 c, {%2, %3};\n\t"
+                 "mov.b128 v, {%4, %5};\n\t"
+                 "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\t"
+                 "mov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi)
+                 : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// agent id -> (slot, status).  Table is tiny (48 B per entry) and read-only inside a kernel: L1 / L2 resident.
+__device__ __forceinline__ uint32_t agent_lookup(const agr_dev& d, unsigned long long w0, unsigned long long w1,
+                                                 unsigned long long w2, unsigned long long w3) {
+    if ((w0 | w1 | w2 | w3) == 0ULL) return RT_SLOT_NONE;
+    uint32_t idx = (uint32_t)agr_hash_agent(w0, w1, w2, w3) & d.amask;
+    for (uint32_t probe = 0; probe <= d.amask; ++probe) {
+        const agr_agent_key* e = d.akeys + idx;
+        uint4 a = ldg_v4(&e->w[0]);
+        uint4 b = ldg_v4(&e->w[2]);
+        unsigned long long e0 = pack64(a.x, a.y), e1 = pack64(a.z, a.w), e2 = pack64(b.x, b.y), e3 = pack64(b.z, b.w);
+        if ((e0 | e1 | e2 | e3) == 0ULL) return RT_SLOT_NONE;
+        if (e0 == w0 && e1 == w1 && e2 == w2 && e3 == w3) return __ldg(&e->slot);
+        idx = (idx + 1) & d.amask;
+    }
+    return RT_SLOT_NONE;
+}
+
+// dedupe-index lookup: returns slot index or ~0ULL
+__device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsigned long long lo, unsigned long long hi) {
+    unsigned long long idx = agr_hash_id(lo, hi) & d.table_mask;
+    for (unsigned long long probe = 0; probe <= d.table_mask; ++probe) {
+        const agr_slot* s = d.table + idx;
+        const uint4 k = __ldcg(reinterpret_cast<const uint4*>(s));
+        unsigned long long klo = pack64(k.x, k.y), khi = pack64(k.z, k.w);
+        if ((klo | khi) == 0ULL) return ~0ULL;
+        if (klo == lo && khi == hi) return idx;
+        idx = (idx + 1) & d.table_mask;
+    }
+    return ~0ULL;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// Decision + persistence for ONE record whose 96 B header is in registers.  Sequential semantics of
+// proxyToAgentHandler (server.go:498-541) with StoreRequest (requests.go:64-117) inlined.
+struct k1_result { uint32_t state, route; };
+
+__device__ __forceinline__ k1_result k1_decide(const agr_dev& d, uint32_t rid, uint4 h0, uint4 h1, uint4 h2, uint4 h3,
+                                               uint4 h4, uint4 h5, uint32_t* lc /*local counters*/) {
+    k1_result out{0u, 0u};
+    const unsigned long long id_lo = pack64(h0.x, h0.y), id_hi = pack64(h0.z, h0.w);
+    const uint32_t flags_in = h4.z;
+    const bool replay = (flags_in & AGR_F_REPLAY) != 0;                                   // server.go:506
+    const bool persistence = (d.cfg_flags & AGR_CFG_PERSISTENCE) != 0;
+    // GetAgent (server.go:498, agent.go:372-390)
+    uint32_t slot = agent_lookup(d, pack64(h2.x, h2.y), pack64(h2.z, h2.w), pack64(h3.x, h3.y), pack64(h3.z, h3.w));
+    uint32_t astatus = AG_STATUS_REMOVED;
+    if (slot != RT_SLOT_NONE) astatus = d.astatus[slot];
+    lc[C_INGESTED]++;
+    if (slot == RT_SLOT_NONE || astatus == AG_STATUS_REMOVED) {                           // server.go:499-502
+        lc[C_NOT_FOUND]++;
+        out.route = RT_SLOT_NONE | (AGR_V_NOT_FOUND << RT_CODE_SHIFT);
+        return out;
+    }
+    uint32_t vflags = 0;
+    bool tracked = false;
+    if (persistence && !replay) {                                                         // server.go:508
+        // StoreRequest: SET rec (the row itself, already in the slab) + index insert + RPUSH pending (INQ bit)
+        bool ok = (id_lo | id_hi) != 0ULL;
+        if (ok) {
+            unsigned long long idx = agr_hash_id(id_lo, id_hi) & d.table_mask;
+            const u128 zero{0ULL, 0ULL}, key{id_lo, id_hi};
+            for (;;) {
+                u128 old = cas128(&d.table[idx], zero, key);
+                if ((old.lo | old.hi) == 0ULL || (old.lo == id_lo && old.hi == id_hi)) break;
+                idx = (idx + 1) & d.table_mask;
+            }
+            const uint32_t inv = ~rid;
+            uint32_t prev = atomicMax(&d.table[idx].inv_rid, inv);
+            if (prev > inv) ok = false;                       // an EARLIER row owns this id: duplicate
+            else if (prev != 0u) atomicAdd(d.dupfix, 1u);     // a LATER row raced ahead: k1_post demotes it
+        }
+        if (ok) {
+            uint32_t maxr = (h5.y >> 16) & 0xffu;
+            if (maxr == 0) maxr = 3;                                                      // requests.go:95
+            out.state = AGR_ST_PENDING | ST_INQ | ST_STORED | (maxr << ST_MAX_SHIFT);     // requests.go:93-95,111
+            vflags |= AGR_VF_STORED | AGR_VF_TRACKED;
+            tracked = true;
+            lc[C_STORED]++;
+        } else {
+            vflags |= AGR_VF_DUP_ID;                                                      // server.go:511-514 path
+            lc[C_DUP_IDS]++;
+        }
+    } else if (replay) {                                                                  // server.go:519-522
+        vflags |= AGR_VF_REPLAY;
+        lc[C_REPLAY]++;
+        tracked = (pack64(h1.x, h1.y) | pack64(h1.z, h1.w)) != 0ULL;
+        if (tracked) vflags |= AGR_VF_TRACKED;
+    }
+    uint32_t code;
+    if (astatus != AGR_AGENT_RUNNING) {                                                   // server.go:525
+        if (persistence && tracked) { code = AGR_V_QUEUED; lc[C_QUEUED]++; }              // :526-536
+        else { code = AGR_V_UNAVAILABLE; lc[C_UNAVAILABLE]++; }                           // :539-540
+    } else {
+        code = AGR_V_FORWARD; lc[C_FORWARDED]++;                                          // :546-572
+        if (out.state) out.state |= ST_INFLIGHT;
+    }
+    out.route = slot | (code << RT_CODE_SHIFT) | (vflags << RT_FLAG_SHIFT);
+    return out;
+}
+
+#define K1_NLC 9   // counters C_INGESTED .. C_DUP_IDS are contiguous from 0
+
+__device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc, uint32_t* s_ctr) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < K1_NLC; ++c) {
+        uint32_t v = __reduce_add_sync(FULL, lc[c]);
+        if (lane == 0 && v) atomicAdd(&s_ctr[c], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < K1_NLC && s_ctr[threadIdx.x]) atomicAdd(&d.ctr[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+}
+
+// v0: each warp owns 32 consecutive records.  Pass 1: lane i loads the 96 B header of record i (six 16 B loads,
+// every fetched sector fully used) and runs the decision chain thread-per-record, so 32 index inserts are in
+// flight per warp.  Pass 2: the warp streams the 416 B payloads coalesced (lane l = 16 B chunk l) for the record
+// checksum, REDUX-reducing per record.  Every byte of the record is read exactly once.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, const uint32_t first_rid, const uint32_t n) {
+    __shared__ uint32_t s_ctr[K1_NLC];
+    if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t lc[K1_NLC];
+#pragma unroll
+    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    const uint32_t tiles = (n + 31u) >> 5;
+    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < tiles; tile += gridDim.x * WARPS) {
+        const uint32_t i = tile * 32u + lane;
+        const bool valid = i < n;
+        const uint32_t rid = first_rid + i;
+        const uint8_t* tile_base = d.slab + (size_t)(first_rid + tile * 32u) * AGR_REC;
+        uint4 h0, h1, h2, h3, h4, h5;
+        h0 = h1 = h2 = h3 = h4 = h5 = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            const uint8_t* rec = tile_base + (size_t)lane * AGR_REC;
+            h0 = ldg_nc_v4(rec);      h1 = ldg_nc_v4(rec + 16); h2 = ldg_nc_v4(rec + 32);
+            h3 = ldg_nc_v4(rec + 48); h4 = ldg_nc_v4(rec + 64); h5 = ldg_nc_v4(rec + 80);
+        }
+        // ---- pass 2 first (pure streaming, independent of the decision chain): payload checksum
+        uint32_t c0 = 0, c1 = 0;
+        {
+            const uint32_t hw[24] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w,
+                                     h3.x, h3.y, h3.z, h3.w, h4.x, h4.y, h4.z, h4.w, h5.x, h5.y, h5.z, h5.w};
+#pragma unroll
+            for (int k = 0; k < 24; ++k) { c0 += hw[k]; c1 += (uint32_t)(k + 1) * hw[k]; }
+        }
+        const uint32_t in_tile = min(32u, n - tile * 32u);
+        const uint32_t wbase = 4u * lane + 1u;
+#pragma unroll 1
+        for (uint32_t r0 = 0; r0 < in_tile; r0 += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (lane >= 6 && r0 + u < in_tile) v[u] = ldg_nc_v4(tile_base + (size_t)(r0 + u) * AGR_REC + lane * 16);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint32_t p0 = v[u].x + v[u].y + v[u].z + v[u].w;
+                uint32_t p1 = wbase * v[u].x + (wbase + 1) * v[u].y + (wbase + 2) * v[u].z + (wbase + 3) * v[u].w;
+                p0 = __reduce_add_sync(FULL, p0);
+                p1 = __reduce_add_sync(FULL, p1);
+                if ((uint32_t)lane == r0 + u) { c0 += p0; c1 += p1; }
+            }
+        }
+        // ---- pass 1: decision chain, one record per lane
+        if (valid) {
+            k1_result r = k1_decide(d, rid, h0, h1, h2, h3, h4, h5, lc);
+            d.state[rid] = r.state;
+            d.route[rid] = r.route;
+            d.cksum[rid] = agr_cksum_pack(c0, c1);
+        }
+    }
+    k1_flush_counters(d, lc, s_ctr);
+}
+
+// Post pass over the batch's route words (4 B / record, the records themselves are not re-read except for the
+// rare rows that need it):
+//   (a) LLEN pending bookkeeping: one atomicAdd per (warp, agent) via match_any;
+//   (b) replay-flagged rows: resolve replay_of in the dedupe index -> KNOWN (dedupe hit).  Done here, after ALL
+//       inserts of the batch, and compared by rid so that "known" means "stored EARLIER in arrival order";
+//   (c) only if an in-batch duplicate-id race was seen (dupfix != 0, never with minted UUIDs): every stored row
+//       re-checks that it still owns its id; the later row is demoted to a persistence failure.
+__global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    const uint32_t rid = first_rid + i;
+    uint32_t r = valid ? d.route[rid] : 0u;
+    uint32_t vf = rt_flags(r);
+    const uint32_t dupfix = *reinterpret_cast<volatile uint32_t*>(d.dupfix);
+    uint32_t hits = 0, demoted = 0, q2u = 0;
+    if (valid && (vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
+        uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + AGR_OFF_REPLAY_OF);
+        unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
+        if (idx != ~0ULL) {
+            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
+            uint32_t orid = ~inv;
+            if (inv != 0u && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
+                r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
+                d.route[rid] = r;
+                hits = 1;
+            }
+        }
+    }
+    if (dupfix != 0u && valid && (vf & AGR_VF_STORED)) {
+        uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+        unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
+        uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : ~(__ldcg(&d.table[idx].inv_rid));
+        if (owner != rid) {   // demote: behave like a failed StoreRequest (server.go:511-514)
+            demoted = 1;
+            uint32_t code = rt_code(r);
+            if (code == AGR_V_QUEUED) { code = AGR_V_UNAVAILABLE; q2u = 1; }
+            vf = (vf & ~(AGR_VF_STORED | AGR_VF_TRACKED)) | AGR_VF_DUP_ID;
+            r = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
+            d.route[rid] = r;
+            d.state[rid] = 0;
+        }
+    }
+    // (a) pending-list length per agent
+    const bool stored = valid && (vf & AGR_VF_STORED);
+    const uint32_t key = stored ? rt_slot(r) : (0x80000000u | (uint32_t)lane);
+    const uint32_t peers = __match_any_sync(FULL, key);
+    if (stored && lane == (__ffs(peers) - 1)) atomicAdd(&d.pend_cnt[rt_slot(r)], (uint32_t)__popc(peers));
+    hits = __reduce_add_sync(FULL, hits);
+    demoted = __reduce_add_sync(FULL, demoted);
+    q2u = __reduce_add_sync(FULL, q2u);
+    if (lane == 0) {
+        if (hits) atomicAdd(&d.ctr[C_DEDUPE_HITS], (unsigned long long)hits);
+        if (demoted) {
+            atomicAdd(&d.ctr[C_DUP_IDS], (unsigned long long)demoted);
+            atomicAdd(&d.ctr[C_STORED], (unsigned long long)(0ULL - demoted));
+            if (q2u) {
+                atomicAdd(&d.ctr[C_QUEUED], (unsigned long long)(0ULL - q2u));
+                atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)q2u);
+            }
+        }
+    }
+}
+
+int agr_k1_launches_per_batch(uint32_t) { return 2; }
+
+void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    (void)variant;
+    cudaMemsetAsync(d.dupfix, 0, sizeof(uint32_t), st);
+    constexpr int WARPS = 8;
+    const uint32_t tiles = (n + 31u) / 32u;
+    uint32_t blocks = (tiles + WARPS - 1) / WARPS;
+    const uint32_t maxb = (uint32_t)sm_count * 8u;
+    if (blocks > maxb) blocks = maxb;
+    k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
+    k1_post<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// Outcomes must be applied in array order per record (MarkRequestFailed then StoreResponse is not the same as the
+// reverse, KAT-H).  k2_link resolves each outcome to its row and threads all outcomes of one row onto a chain
+// rooted in the index slot; k2_apply lets the chain root replay that row's outcomes in ascending op index on a
+// private copy of the state word (so Q24's lost updates cannot happen); k2_offsets + k2_append push the
+// completed / failed list entries in op order (RPUSH order == call order).
+__global__ void __launch_bounds__(256) k2_link(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const agr_dop op = s.ops[j];
+    s.eff[j] = 0;
+    s.nxt[j] = 0;
+    uint32_t rid = AGR_RID_NONE;
+    int32_t res = 0;
+    const bool ext = (d.cfg_flags & AGR_CFG_SKIP_INFLIGHT) != 0;
+    if ((op.id_lo | op.id_hi) != 0ULL && (op.kind == AGR_OUT_RESPONSE || op.kind == AGR_OUT_ERROR ||
+                                            (op.kind == AGR_OUT_DIAL_ERR && ext))) {
+        unsigned long long idx = table_find(d, op.id_lo, op.id_hi);
+        if (idx != ~0ULL) {
+            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
+            uint32_t cand = ~inv;
+            // the Redis key is agent:{a}:requests:{r}: the agent is part of the key (requests.go:150,229)
+            if (inv != 0u && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) {
+                rid = cand;
+                s.hidx[j] = (uint32_t)idx;
+                s.nxt[j] = atomicExch(&d.table[idx].head, j + 1u);
+            }
+        }
+        if (rid == AGR_RID_NONE && op.kind != AGR_OUT_DIAL_ERR) {
+            res = AGR_ENOTFOUND;                                   // requests.go:153-156 / 232-235
+            atomicAdd(&d.ctr[C_COMPLETION_MISSES], 1ULL);
+        }
+    }
+    if (op.kind == AGR_OUT_DIAL_ERR) atomicAdd(&d.ctr[C_DIAL_ERRORS], 1ULL);    // server.go:600-605: stays pending
+    s.hrid[j] = rid;
+    if (s.results) s.results[j] = res;
+}
+
+// read-only resolve of (agent slot, request id) -> rid, used by agr_get_record
+__global__ void __launch_bounds__(256) k_resolve(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const agr_dop op = s.ops[j];
+    uint32_t rid = AGR_RID_NONE;
+    if ((op.id_lo | op.id_hi) != 0ULL) {
+        unsigned long long idx = table_find(d, op.id_lo, op.id_hi);
+        if (idx != ~0ULL) {
+            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
+            uint32_t cand = ~inv;
+            if (inv != 0u && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) rid = cand;
+        }
+    }
+    s.hrid[j] = rid;
+}
+void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
+    if (n) k_resolve<<<(n + 255u) / 256u, 256, 0, st>>>(d, s, n);
+}
+
+__global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t rid = s.hrid[j];
+    if (rid == AGR_RID_NONE) return;
+    const uint32_t idx = s.hidx[j];
+    if (__ldcg(&d.table[idx].head) != j + 1u) return;   // not the chain root
+    uint32_t st = d.state[rid], aux = d.aux[rid];
+    const uint32_t slot = rt_slot(d.route[rid]);
+    uint32_t dpend = 0, ncomp = 0, nfail = 0, nerr = 0;
+    long long last = -1;
+    for (;;) {
+        // next op of this row in ascending op index
+        uint32_t best = 0xffffffffu;
+        for (uint32_t cur = j + 1u; cur != 0u; cur = s.nxt[cur - 1u]) {
+            uint32_t o = cur - 1u;
+            if ((long long)o > last && o < best) best = o;
+        }
+        if (best == 0xffffffffu) break;
+        last = best;
+        const agr_dop op = s.ops[best];
+        uint8_t eff = 0;
+        if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
+            st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED;  // :166
+            aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
+            if (st & ST_INQ) { st &= ~ST_INQ; dpend++; }                     // :180-184 LREM pending 1 id
+            eff |= 1; ncomp++;                                               // :187-191 RPUSH completed
+        } else if (op.kind == AGR_OUT_ERROR) {                               // MarkRequestFailed, requests.go:243-262
+            uint32_t retry = st_retry(st);
+            if (retry < 255u) retry++;                                       // :245
+            st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT)) | (retry << ST_RETRY_SHIFT);
+            aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
+            nerr++;
+            if (retry < st_max(st)) {
+                st |= AGR_ST_PENDING;                                        // :248-249, keeps queue position (Q11)
+            } else {
+                st |= AGR_ST_FAILED;                                         // :243
+                eff |= 2; nfail++;                                           // :252-255 RPUSH failed
+                if (st & ST_INQ) { st &= ~ST_INQ; dpend++; }                 // :258-261 LREM pending 1 id
+            }
+        } else {                                                             // dial error, extension bookkeeping only
+            st &= ~ST_INFLIGHT;
+        }
+        s.eff[best] = eff;
+    }
+    d.state[rid] = st;
+    d.aux[rid] = aux;
+    d.table[idx].head = 0;
+    if (dpend) atomicSub(&d.pend_cnt[slot], dpend);
+    if (ncomp) { atomicAdd(&d.comp_cnt[slot], ncomp); atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)ncomp); }
+    if (nerr) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)nerr);
+    if (nfail) { atomicAdd(&d.fail_cnt[slot], nfail); atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)nfail); }
+}
+
+// one CTA: per-chunk counts of push flags -> exclusive bases; reserves log space
+__global__ void __launch_bounds__(1024) k2_offsets(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
+    __shared__ uint32_t sc[1024], sf[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t nchunks = (n + csize - 1) / csize;
+    uint32_t cc = 0, cf = 0;
+    if (t < nchunks) {
+        const uint32_t b = t * csize, e = min(n, b + csize);
+        for (uint32_t k = b; k < e; ++k) { uint8_t f = s.eff[k]; cc += f & 1u; cf += (f >> 1) & 1u; }
+    }
+    sc[t] = cc; sf[t] = cf;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {      // Hillis-Steele inclusive scan
+        uint32_t ac = 0, af = 0;
+        if (t >= off) { ac = sc[t - off]; af = sf[t - off]; }
+        __syncthreads();
+        sc[t] += ac; sf[t] += af;
+        __syncthreads();
+    }
+    const unsigned long long base_c = d.log_len[0], base_f = d.log_len[1];
+    // chunk bases are offsets from the current log tail; the tail itself is read again in k2_append
+    s.chunk_base[t] = sc[t] - cc;
+    s.chunk_base[1024 + t] = sf[t] - cf;
+    if (t == 1023) {
+        unsigned long long tc = sc[1023], tf = sf[1023];
+        if (base_c + tc > d.log_cap || base_f + tf > d.log_cap) atomicAdd(&d.ctr[C_LOG_OVERFLOW], 1ULL);
+    }
+}
+
+// warp per chunk: order-preserving append; the last warp to finish nothing special — tails advanced by k2_tail
+__global__ void __launch_bounds__(256) k2_append(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
+    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nchunks = (n + csize - 1) / csize;
+    if (chunk >= nchunks) return;
+    unsigned long long pc = d.log_len[0] + s.chunk_base[chunk];
+    unsigned long long pf = d.log_len[1] + s.chunk_base[1024 + chunk];
+    const uint32_t b = chunk * csize, e = min(n, b + csize);
+    for (uint32_t k0 = b; k0 < e; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        uint8_t f = (k < e) ? s.eff[k] : 0;
+        const uint32_t rid = (k < e) ? s.hrid[k] : AGR_RID_NONE;
+        uint32_t mc = __ballot_sync(FULL, f & 1u), mf = __ballot_sync(FULL, f & 2u);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (f & 1u) { unsigned long long p = pc + __popc(mc & lt); if (p < d.log_cap) d.completed_log[p] = rid; }
+        if (f & 2u) { unsigned long long p = pf + __popc(mf & lt); if (p < d.log_cap) d.failed_log[p] = rid; }
+        pc += __popc(mc); pf += __popc(mf);
+    }
+}
+
+__global__ void k2_tail(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
+    // total pushes = base of the last chunk + its count; recompute the last chunk's count
+    const uint32_t nchunks = (n + csize - 1) / csize;
+    const uint32_t last = nchunks - 1;
+    uint32_t cc = 0, cf = 0;
+    for (uint32_t k = last * csize; k < n; ++k) { uint8_t f = s.eff[k]; cc += f & 1u; cf += (f >> 1) & 1u; }
+    unsigned long long tc = d.log_len[0] + s.chunk_base[last] + cc;
+    unsigned long long tf = d.log_len[1] + s.chunk_base[1024 + last] + cf;
+    d.log_len[0] = tc < d.log_cap ? tc : d.log_cap;
+    d.log_len[1] = tf < d.log_cap ? tf : d.log_cap;
+}
+
+void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
+    if (n == 0) return;
+    const uint32_t blocks = (n + 255u) / 256u;
+    k2_link<<<blocks, 256, 0, st>>>(d, s, n);
+    k2_apply<<<blocks, 256, 0, st>>>(d, s, n);
+    uint32_t csize = (n + 1023u) / 1024u;
+    csize = (csize + 31u) & ~31u;
+    if (csize < 32u) csize = 32u;
+    const uint32_t nchunks = (n + csize - 1) / csize;
+    k2_offsets<<<1, 1024, 0, st>>>(d, s, n, csize);
+    k2_append<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(d, s, n, csize);
+    k2_tail<<<1, 1, 0, st>>>(d, s, n, csize);
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// Stable agent-major partition of the selected items: output order = (agent slot ascending, item order ascending).
+// Each warp owns a contiguous run of items; matrix[w][g] first holds the warp's per-group count, then (after the
+// column scan) the position where warp w's first item of group g goes.  Inside a 32-item step match_any + popc
+// give the stable rank — the warp-ballot agent-id partition.
+struct k3_item { bool sel; uint32_t rid; uint32_t slot; bool inq; };
+
+__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it) {
+    k3_item o{false, AGR_RID_NONE, RT_SLOT_NONE, false};
+    if (it >= p.hi) return o;
+    if (p.mode == K3_LOG_AGENT) {
+        const uint32_t rid = p.log[it];
+        if (rid == AGR_RID_NONE) return o;
+        o.rid = rid; o.slot = rt_slot(d.route[rid]);
+        o.sel = (o.slot == p.slot);
+        return o;
+    }
+    const uint32_t rid = (uint32_t)it;
+    const uint32_t st = d.state[rid];
+    if (!(st & ST_INQ)) return o;                       // not in agent:{a}:requests:pending
+    o.inq = true;
+    o.rid = rid; o.slot = rt_slot(d.route[rid]);
+    if (p.mode == K3_AGENT_PENDING) { o.sel = (o.slot == p.slot); return o; }   // GetPendingRequests, requests.go:197-225
+    // K3_TICK: isAgentRunning (replay_worker.go:76-81,166-189) + the skip rule of :101
+    if (d.astatus[o.slot] != AGR_AGENT_RUNNING) return o;
+    if (st_status(st) == AGR_ST_PROCESSING || st_retry(st) >= st_max(st)) return o;
+    if ((d.cfg_flags & AGR_CFG_SKIP_INFLIGHT) && (st & ST_INFLIGHT)) return o;  // extension, off in parity mode
+    o.sel = true;
+    return o;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_params p) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= p.nwarps) return;
+    uint32_t* row = p.matrix + (size_t)w * p.groups;
+    const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
+    unsigned long long e = b + p.per_warp;
+    if (e > p.hi) e = p.hi;
+    uint32_t mininq = AGR_RID_NONE;
+    for (unsigned long long k0 = b; k0 < e; k0 += 32) {
+        k3_item it = k3_eval(d, p, k0 + lane);
+        if (it.inq && it.rid < mininq) mininq = it.rid;
+        const uint32_t g = (p.groups == 1) ? 0u : it.slot;
+        const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
+        const uint32_t peers = __match_any_sync(FULL, key);
+        if (it.sel) {
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            const bool leader = (rank == 0);
+            volatile uint32_t* cell = row + g;
+            const uint32_t base = *cell;
+            if (SCATTER) {
+                const uint32_t pos = p.goff[g] + base + rank;
+                if (pos < p.cap) { p.out_rid[pos] = it.rid; p.out_slot[pos] = it.slot; }
+            }
+            __syncwarp(peers);
+            if (leader) *cell = base + __popc(peers);
+        }
+        __syncwarp();
+    }
+    if (!SCATTER && p.min_inq && p.mode == K3_TICK) {
+        mininq = __reduce_min_sync(FULL, mininq);
+        if (lane == 0 && mininq != AGR_RID_NONE) atomicMin(p.min_inq, mininq);
+    }
+}
+
+// column scan: thread per group walks the warps (coalesced across groups)
+__global__ void __launch_bounds__(256) k3_scan_groups(const agr_k3_params p) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.groups) return;
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < p.nwarps; ++w) {
+        uint32_t* cell = p.matrix + (size_t)w * p.groups + g;
+        uint32_t c = *cell; *cell = run; run += c;
+    }
+    p.gtotal[g] = run;
+}
+// exclusive scan over groups (one CTA, loops for groups > 1024); goff[groups] = total
+__global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < p.groups; b += 1024) {
+        uint32_t v = (b + t < p.groups) ? p.gtotal[b + t] : 0u;
+        sh[t] = v;
+        __syncthreads();
+        for (uint32_t off = 1; off < 1024; off <<= 1) {
+            uint32_t a = (t >= off) ? sh[t - off] : 0u;
+            __syncthreads();
+            sh[t] += a;
+            __syncthreads();
+        }
+        if (b + t < p.groups) p.goff[b + t] = carry + sh[t] - v;
+        __syncthreads();
+        if (t == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (t == 0) p.goff[p.groups] = carry;
+}
+
+void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStream_t st) {
+    cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
+    const uint32_t blocks = (p.nwarps * 32u + 255u) / 256u;
+    k3_pass<false><<<blocks, 256, 0, st>>>(d, p);
+    k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
+    k3_scan_total<<<1, 1024, 0, st>>>(p);
+    k3_pass<true><<<blocks, 256, 0, st>>>(d, p);
+}
+
+// warp per selected row: copy the record out with the live state patched into the header, and/or emit the
+// dispatch entry / the bare id
+__global__ void __launch_bounds__(256) k3_gather(const agr_dev d, const uint32_t* rids, const uint32_t* slots, const uint32_t n,
+                                                 uint8_t* out_recs, uint8_t* out_dispatch, uint8_t* out_ids) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t rid = rids[w];
+    const uint8_t* src = d.slab + (size_t)rid * AGR_REC;
+    uint4 v = ldg_nc_v4(src + lane * 16);
+    if (out_recs) {
+        if (lane == 5) {   // bytes 80..95: body_len | status,retry,max,err | resp_status
+            const uint32_t st = d.state[rid], aux = d.aux[rid];
+            v.y = st_status(st) | (st_retry(st) << 8) | (st_max(st) << 16) | (((aux >> AUX_ERR_SHIFT) & 0xffu) << 24);
+            v.z = (v.z & 0xffff0000u) | (aux & 0xffffu);
+        }
+        *reinterpret_cast<uint4*>(out_recs + (size_t)w * AGR_REC + lane * 16) = v;
+    }
+    uint4 id;
+    id.x = __shfl_sync(FULL, v.x, 0); id.y = __shfl_sync(FULL, v.y, 0);
+    id.z = __shfl_sync(FULL, v.z, 0); id.w = __shfl_sync(FULL, v.w, 0);
+    if (out_dispatch && lane == 0) {
+        uint4 head = make_uint4(rid, 0u, slots ? slots[w] : rt_slot(d.route[rid]), 0u);
+        *reinterpret_cast<uint4*>(out_dispatch + (size_t)w * 32) = head;
+        *reinterpret_cast<uint4*>(out_dispatch + (size_t)w * 32 + 16) = id;
+    }
+    if (out_ids && lane == 0) *reinterpret_cast<uint4*>(out_ids + (size_t)w * 16) = id;
+}
+
+void agr_launch_k3_gather(const agr_dev& d, const uint32_t* rids, const uint32_t* slots, uint32_t n, uint8_t* out_recs,
+                          uint8_t* out_dispatch, uint8_t* out_ids, cudaStream_t st) {
+    if (n == 0) return;
+    k3_gather<<<(n * 32u + 255u) / 256u, 256, 0, st>>>(d, rids, slots, n, out_recs, out_dispatch, out_ids);
+}
+
+// agent.Manager.Remove queue cleanup (agent.go:349-359): DEL the three lists of one agent
+__global__ void __launch_bounds__(256) k_drop_rows(const agr_dev d, const uint32_t slot, const unsigned long long rows) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const uint32_t st = d.state[r];
+    if ((st & ST_INQ) && rt_slot(d.route[r]) == slot) d.state[r] = st & ~ST_INQ;
+}
+__global__ void __launch_bounds__(256) k_drop_logs(const agr_dev d, const uint32_t slot) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d.log_len[0]) { uint32_t rid = d.completed_log[k]; if (rid != AGR_RID_NONE && rt_slot(d.route[rid]) == slot) d.completed_log[k] = AGR_RID_NONE; }
+    if (k < d.log_len[1]) { uint32_t rid = d.failed_log[k]; if (rid != AGR_RID_NONE && rt_slot(d.route[rid]) == slot) d.failed_log[k] = AGR_RID_NONE; }
+    if (k == 0) { d.pend_cnt[slot] = 0; d.comp_cnt[slot] = 0; d.fail_cnt[slot] = 0; }
+}
+void agr_launch_drop_agent(const agr_dev& d, uint32_t slot, unsigned long long rows, unsigned long long max_log_len,
+                           cudaStream_t st) {
+    if (rows) k_drop_rows<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, slot, rows);
+    if (max_log_len == 0) max_log_len = 1;   // k == 0 also resets the per-agent list lengths
+    k_drop_logs<<<(unsigned)((max_log_len + 255) / 256), 256, 0, st>>>(d, slot);
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic stream
+__global__ void __launch_bounds__(128) k_synth(uint8_t* dst, const agr_synth_dev s, const unsigned long long first_index, const uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    agr_synth_record(s, first_index + i, dst + (size_t)i * AGR_REC);
+}
+void agr_launch_synth(uint8_t* dst, agr_synth_dev s, unsigned long long first_index, uint32_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_synth<<<(n + 127u) / 128u, 128, 0, st>>>(dst, s, first_index, n);
+}

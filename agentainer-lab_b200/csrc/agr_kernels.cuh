@@ -1,0 +1,87 @@
+// agr_kernels.cuh — device-side view of the engine state and the launch entry points of the K1..K3 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "agr_common.h"
+#include "agr_synth.h"
+
+// global counters (device u64 array), mirrored into agr_stats
+enum {
+    C_INGESTED = 0, C_STORED, C_REPLAY, C_DEDUPE_HITS, C_FORWARDED, C_QUEUED, C_UNAVAILABLE, C_NOT_FOUND, C_DUP_IDS,
+    C_COMPLETIONS, C_COMPLETION_MISSES, C_FAILURES, C_DEAD_LETTERED, C_DIAL_ERRORS,
+    C_REPLAY_DISPATCHED, C_LOG_OVERFLOW, C_NCTR = 24
+};
+
+struct agr_dev {
+    uint8_t* slab;
+    uint32_t* state;
+    uint32_t* route;
+    uint32_t* aux;
+    unsigned long long* cksum;
+    agr_slot* table;
+    unsigned long long table_mask;
+    agr_agent_key* akeys;
+    uint32_t amask;
+    uint8_t* astatus;          // [max_agents]
+    uint32_t* pend_cnt;        // per agent: LLEN pending / completed / failed
+    uint32_t* comp_cnt;
+    uint32_t* fail_cnt;
+    unsigned long long* ctr;   // C_NCTR
+    uint32_t* completed_log;
+    uint32_t* failed_log;
+    unsigned long long* log_len;   // [0] completed, [1] failed
+    unsigned long long log_cap;
+    uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
+    uint32_t cfg_flags;
+};
+
+// K2 device descriptor (host resolves agent_id -> slot)
+struct __attribute__((aligned(16))) agr_dop {
+    unsigned long long id_lo, id_hi;
+    uint32_t slot;
+    uint16_t http;
+    uint8_t kind;
+    uint8_t pad;
+    unsigned long long seq;
+};
+
+struct agr_k2_scratch {
+    const agr_dop* ops;
+    uint32_t* nxt;      // chain link (op index + 1, 0 = end)
+    uint32_t* hrid;     // resolved rid or AGR_RID_NONE
+    uint32_t* hidx;     // table slot index
+    uint8_t* eff;       // bit0 push completed, bit1 push failed
+    int32_t* results;   // 0 / AGR_ENOTFOUND
+    uint32_t* chunk_base;  // [2][1024]
+};
+
+// K3 select modes
+enum { K3_TICK = 0, K3_AGENT_PENDING = 1, K3_LOG_AGENT = 2 };
+struct agr_k3_params {
+    int mode;
+    uint32_t slot;             // agent for the single-agent modes
+    const uint32_t* log;       // K3_LOG_AGENT: source log
+    unsigned long long lo, hi; // item range [lo, hi): rids or log positions
+    uint32_t groups;           // matrix columns: max agent slot + 1 (TICK) or 1
+    uint32_t nwarps;           // matrix rows
+    uint32_t per_warp;         // items per warp chunk (multiple of 32)
+    uint32_t* matrix;          // [nwarps][groups]
+    uint32_t* gtotal;          // [groups]
+    uint32_t* goff;            // [groups + 1]
+    uint32_t* out_rid;         // [cap]
+    uint32_t* out_slot;        // [cap]
+    uint32_t cap;
+    uint32_t* min_inq;         // TICK: lowest rid still in a pending list (low-water mark for the next scan)
+};
+
+void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, int sm_count, cudaStream_t st);
+void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
+void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
+void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int sm_count, cudaStream_t st);
+void agr_launch_k3_gather(const agr_dev& d, const uint32_t* rids, const uint32_t* slots, uint32_t n,
+                          uint8_t* out_recs /*nullable*/, uint8_t* out_dispatch /*nullable, 32 B each*/,
+                          uint8_t* out_ids /*nullable, 16 B each*/, cudaStream_t st);
+void agr_launch_drop_agent(const agr_dev& d, uint32_t slot, unsigned long long rows, unsigned long long max_log_len,
+                           cudaStream_t st);
+void agr_launch_synth(uint8_t* dst, agr_synth_dev s, unsigned long long first_index, uint32_t n, cudaStream_t st);
+int  agr_k1_launches_per_batch(uint32_t variant);

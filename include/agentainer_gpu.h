@@ -1,0 +1,258 @@
+/*
+ * agentainer_gpu.h — C-ABI of the B200-native request queue / replay / route engine.
+ *
+ * This is the drop-in boundary for ONE path of oso95/Agentainer-lab: the
+ * internal/requests persistence + replay queue and the decision part of the
+ * internal/api reverse proxy.  The reference has no FFI of its own (it is pure
+ * Go talking to Redis); the seam is the Go method set of requests.Manager and
+ * requests.ReplayWorker plus the decision code in proxyToAgentHandler.  Every
+ * entry point below names the reference interface it replaces (file:line,
+ * relative to the reference tree).  The cgo binding a maintainer adds is in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types in any signature;
+ *   - the caller owns every input buffer until the call returns; the library
+ *     never retains a caller pointer (cgo pointer-passing rules);
+ *   - outputs go to caller-allocated arrays with (cap, *n);
+ *   - return 0 on success, a negative AGR_E* code otherwise; never aborts;
+ *     agr_last_error() gives a thread-local message for the last failure;
+ *   - every entry point is thread-safe (calls on one handle are linearised in
+ *     the order they acquire the handle; that order IS the event order the
+ *     state machine sees, like commands arriving at a single Redis server);
+ *   - there is no CPU fallback: without a usable sm_100 device agr_create fails.
+ */
+#ifndef AGENTAINER_GPU_H
+#define AGENTAINER_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGR_ABI_VERSION 1u
+
+/* ------------------------------------------------------------------ errors */
+#define AGR_OK          0
+#define AGR_EINVAL     -1   /* bad argument */
+#define AGR_ENODEV     -2   /* no usable CUDA device (sm_100) */
+#define AGR_ENOMEM     -3   /* host or device allocation failed */
+#define AGR_ENOSPC     -4   /* slab / log / agent table capacity exhausted */
+#define AGR_ENOTFOUND  -5   /* key miss: "failed to get request" (requests.go:153-156,232-235), unknown agent */
+#define AGR_ECUDA      -6   /* CUDA runtime error (message in agr_last_error) */
+#define AGR_ECAP       -7   /* caller's output array too small; *n holds the needed count */
+#define AGR_ECOMM      -8   /* multi-GPU exchange (NCCL) error */
+
+/* ---------------------------------------------------------- record layout */
+/*
+ * Fixed-stride binary form of requests.Request (requests.go:27-41).  512 B,
+ * little-endian, naturally aligned.  IDs and time are supplied by the caller:
+ * the reference mints uuid.New() / time.Now() inside StoreRequest
+ * (requests.go:87,96); the Go shim mints them before the call so that the
+ * state machine is a pure function of its input stream.
+ */
+#define AGR_RECORD_BYTES   512u
+#define AGR_HEADER_BYTES    96u
+#define AGR_PAYLOAD_BYTES  (AGR_RECORD_BYTES - AGR_HEADER_BYTES)   /* 416 */
+#define AGR_AGENT_ID_BYTES  32u   /* "agent-<unixnano>" (agent.go:594-596) NUL padded, <=31 chars */
+
+/* flags */
+#define AGR_F_REPLAY        0x00000001u  /* X-Agentainer-Replay: true (server.go:506) */
+#define AGR_F_METHOD_SHIFT  8            /* bits 8..15: method code */
+#define AGR_F_METHOD_MASK   0x0000ff00u
+enum { AGR_M_GET = 1, AGR_M_POST = 2, AGR_M_PUT = 3, AGR_M_DELETE = 4, AGR_M_PATCH = 5, AGR_M_HEAD = 6, AGR_M_OPTIONS = 7 };
+
+/* RequestStatus (requests.go:19-24) */
+enum { AGR_ST_NONE = 0, AGR_ST_PENDING = 1, AGR_ST_PROCESSING = 2, AGR_ST_COMPLETED = 3, AGR_ST_FAILED = 4 };
+
+typedef struct agr_record {
+    uint8_t  request_id[16];   /* raw UUID bytes of Request.ID (fresh records: minted by the caller, must be unique and non-zero) */
+    uint8_t  replay_of[16];    /* X-Agentainer-Request-ID of a replay-flagged request (server.go:519-522); all-zero = header absent */
+    char     agent_id[AGR_AGENT_ID_BYTES];
+    uint64_t seq;              /* logical created_at (requests.go:96): caller's arrival counter */
+    uint32_t flags;            /* AGR_F_* */
+    uint16_t path_len;         /* Request.Path, stored WITH the /agent/{id} prefix (Q3) and without the query (Q4) */
+    uint16_t hdr_len;          /* flattened first-value headers "Key: Value\n" sorted by key (Q5) */
+    uint32_t body_len;
+    uint8_t  status;           /* AGR_ST_*; on input ignored; on output (agr_pending / agr_get_record) the live value */
+    uint8_t  retry_count;      /* same */
+    uint8_t  max_retries;      /* requests.go:95: 3; 0 on input means 3 */
+    uint8_t  error_code;       /* output only: AGR_OUT_* kind that last failed it (Request.Error is a string in the reference) */
+    uint16_t resp_status;      /* output only: Response.StatusCode of the stored response, 0 if none */
+    uint16_t reserved0;
+    uint32_t reserved1;
+    uint8_t  payload[AGR_PAYLOAD_BYTES];  /* path | headers | body, zero padded; path_len+hdr_len+body_len <= 416 */
+} agr_record;
+
+/* ------------------------------------------------------------------ config */
+#define AGR_CFG_PERSISTENCE   0x1u  /* features.request_persistence (config.go:70); default on */
+#define AGR_CFG_SKIP_INFLIGHT 0x2u  /* EXTENSION, off in parity mode: replay scan skips records whose forward is still in flight (fixes Q16) */
+
+typedef struct agr_config {
+    int32_t  device;         /* CUDA ordinal; -1 = current */
+    uint32_t flags;          /* AGR_CFG_*; 0 = AGR_CFG_PERSISTENCE */
+    uint64_t slab_rows;      /* record capacity (rows of 512 B); 0 = 1<<20 */
+    uint64_t table_slots;    /* dedupe-index slots, power of two >= 2*slab_rows; 0 = auto */
+    uint32_t max_agents;     /* agent-table capacity; 0 = 4096 */
+    uint32_t max_batch;      /* largest n accepted by one agr_ingest / agr_complete; 0 = 1<<20 */
+    uint64_t log_entries;    /* capacity of the completed and failed logs; 0 = 2*slab_rows */
+    uint32_t k1_variant;     /* 0 = default kernel; others select alternates for A/B measurement */
+    uint32_t reserved;
+} agr_config;
+
+typedef struct agr_handle agr_handle;
+
+/* --------------------------------------------------------------- lifecycle */
+/* replaces requests.NewManager (requests.go:57) + NewReplayWorker (replay_worker.go:24): ONE process-wide
+ * handle instead of the two stateless Managers the reference creates (server.go:62, main.go:335). */
+int  agr_create(const agr_config* cfg, agr_handle** out);
+void agr_destroy(agr_handle* h);
+uint32_t agr_abi_version(void);
+const char* agr_last_error(void);
+const char* agr_strerror(int code);
+
+/* ------------------------------------------------------------- agent table */
+/* Agent status mirror.  Replaces the per-request GET agent:{id} + Unmarshal of agent.Manager.GetAgent
+ * (agent.go:372-390) read at server.go:498 and replay_worker.go:166-189.  Called from wherever the host
+ * writes Agent.Status (saveAgent agent.go:510-530, state sync).  Registers the agent on first use; slots are
+ * handed out in registration order.  Returns the slot (>= 0) or a negative error. */
+enum { AGR_AGENT_CREATED = 0, AGR_AGENT_RUNNING = 1, AGR_AGENT_STOPPED = 2, AGR_AGENT_PAUSED = 3, AGR_AGENT_FAILED = 4 };  /* agent.go:23-29 */
+int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status);
+/* replaces the queue cleanup of agent.Manager.Remove (agent.go:343-359): DEL agent:{id} and the three lists.
+ * Records are left orphaned exactly like the reference (Q17). */
+int agr_drop_agent(agr_handle* h, const char* agent_id);
+int agr_agent_slot(agr_handle* h, const char* agent_id);   /* slot or AGR_ENOTFOUND */
+
+/* ------------------------------------------------------- K1 ingest + route */
+/* verdict codes = the HTTP decision of proxyToAgentHandler (server.go:493-557) */
+enum {
+    AGR_V_FORWARD     = 1,   /* agent running: reverse-proxy to http://{id}:8000 (server.go:546-572) */
+    AGR_V_QUEUED      = 2,   /* 202, "Request queued for replay" (server.go:526-536) */
+    AGR_V_UNAVAILABLE = 3,   /* 503 (server.go:539-540) */
+    AGR_V_NOT_FOUND   = 4    /* 404 agent not found (server.go:499-502) */
+};
+#define AGR_VF_STORED   0x01u  /* StoreRequest ran: record persisted + RPUSH pending (requests.go:100-114) */
+#define AGR_VF_TRACKED  0x02u  /* requestID != "" : completion will be recorded (server.go:588,597) */
+#define AGR_VF_REPLAY   0x04u  /* replay-flagged: not stored again (server.go:508,519) */
+#define AGR_VF_KNOWN    0x08u  /* replay-flagged and replay_of names a record stored earlier (dedupe hit) */
+#define AGR_VF_DUP_ID   0x10u  /* fresh record whose request_id already exists: contract violation, handled as a
+                                  persistence failure (server.go:511-514): not stored, untracked */
+
+typedef struct agr_verdict {
+    uint8_t  code;        /* AGR_V_* */
+    uint8_t  flags;       /* AGR_VF_* */
+    uint16_t http_status; /* 0 (forward), 202, 503, 404 */
+    uint32_t agent_slot;  /* valid unless NOT_FOUND */
+} agr_verdict;
+
+/* Batch form of the per-request sequence
+ *   GetAgent -> isReplay -> StoreRequest -> status gate            (server.go:498-541, requests.go:64-117)
+ * applied to recs[0..n) in array order.  n == 1 is the single-request call.  first_rid (nullable) receives
+ * the slab row of recs[0]; record i lives in row first_rid + i.  recs may be pageable or pinned host memory. */
+int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid);
+
+/* ------------------------------------------------------- K2 complete / fail */
+enum {
+    AGR_OUT_RESPONSE  = 1,  /* a response came back (ANY status code, Q6): Manager.StoreResponse (requests.go:120-194),
+                               reached from interceptTransport.RoundTrip (server.go:588-594), the worker
+                               (replay_worker.go:158) and the manual replay handler (server.go:739) */
+    AGR_OUT_DIAL_ERR  = 2,  /* "connection refused" | "no such host" | "dial tcp": stays pending (server.go:600-605) */
+    AGR_OUT_ERROR     = 3   /* any other error: Manager.MarkRequestFailed (requests.go:228-275), reached from
+                               server.go:606-611, replay_worker.go:109-112, server.go:728-733 */
+};
+typedef struct agr_outcome {
+    uint8_t  request_id[16];
+    char     agent_id[AGR_AGENT_ID_BYTES];
+    uint8_t  kind;          /* AGR_OUT_* */
+    uint8_t  reserved0;
+    uint16_t http_status;   /* Response.StatusCode for AGR_OUT_RESPONSE */
+    uint32_t reserved1;
+    uint64_t seq;           /* logical processed_at / received_at (requests.go:146,164) */
+} agr_outcome;              /* 64 B */
+
+/* Applies outs[0..n) in array order.  results (nullable) receives per outcome 0 or AGR_ENOTFOUND (the
+ * "failed to get request" error the callers only log, Q20).  An all-zero request_id is a no-op
+ * (t.requestID == "", server.go:588,597). */
+int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results);
+
+/* ------------------------------------------------------------ K3 replay scan */
+typedef struct agr_dispatch {
+    uint64_t rid;           /* slab row */
+    uint32_t agent_slot;
+    uint32_t reserved;
+    uint8_t  request_id[16];
+} agr_dispatch;             /* 32 B */
+
+/* One tick of ReplayWorker.processAgents (replay_worker.go:58-87) up to, not including, the HTTP call:
+ * agents with a non-empty pending list (KEYS agent:*:requests:pending) that are running (isAgentRunning,
+ * :166-189), their pending lists in FIFO order (GetPendingRequests, requests.go:197-225), minus entries with
+ * status == processing or retry_count >= max_retries (:101).  Output is grouped by agent in ascending slot
+ * order (Redis leaves the KEYS order undefined, Q9), FIFO inside each agent.  The host performs
+ * replayRequest (:120-163) for each entry and reports back through agr_ingest (replay-flagged) and
+ * agr_complete.  If recs != NULL the stored records are gathered into recs[0..*n) in the same order. */
+int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t cap, uint32_t* n);
+
+/* Manager.GetPendingRequests (requests.go:197-225) for one agent: FIFO, live status / retry patched in. */
+int agr_pending(agr_handle* h, const char* agent_id, agr_record* out, uint32_t cap, uint32_t* n);
+
+/* storage.Get("agent:{a}:requests:{r}") as used by server.go:661-662,687-688 (Q22). */
+int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id[16], agr_record* out);
+
+/* LRANGE agent:{a}:requests:{pending|completed|failed} 0 -1 — the ID sequences parity is defined on
+ * (completed keeps the Q7 duplicates). */
+enum { AGR_LIST_PENDING = 0, AGR_LIST_COMPLETED = 1, AGR_LIST_FAILED = 2 };
+int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16], uint32_t cap, uint32_t* n);
+
+/* ------------------------------------------------------------------- stats */
+typedef struct agr_stats {
+    uint64_t rows_used, rows_cap;
+    uint64_t ingested, stored, replay_flagged, dedupe_hits, forwarded, queued, unavailable, not_found, dup_ids;
+    uint64_t completions, completion_misses, failures, dead_lettered, dial_errors;
+    uint64_t replay_scans, replay_dispatched;
+    uint64_t completed_log_len, failed_log_len;
+    uint64_t k1_launches, k2_launches, k3_launches, k4_launches;   /* kernels of this library launched so far */
+    uint32_t agents, device;
+} agr_stats;
+int agr_stats_get(agr_handle* h, agr_stats* out);
+
+/* ----------------------------------------------- pinned-host / resident path */
+/* internal/storage moves to pinned host + HBM slabs: the zero-copy producer path.  The Go side fills records
+ * directly into pinned memory obtained here and passes that pointer to agr_ingest (DMA without a bounce). */
+void* agr_host_alloc(size_t bytes);
+void  agr_host_free(void* p);
+
+/* Split form of agr_ingest for callers that keep the batch resident on the device (bench "value" leg, and the
+ * receive side of the multi-GPU exchange): reserve rows, fill them (agr_synth_fill_rows or a DMA of the caller's
+ * own), then run K1 over them.  verdicts may be NULL (they stay on the device). */
+int agr_reserve_rows(agr_handle* h, uint32_t n, uint64_t* first_rid);
+int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out);
+/* launch-only variants: enqueue on the handle's stream and return without synchronising */
+int agr_ingest_rows_async(agr_handle* h, uint64_t first_rid, uint32_t n);
+int agr_sync(agr_handle* h);
+void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run on (for CUDA-event timing) */
+void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
+
+/* -------------------------------------------------- synthetic stream (bench) */
+/* Counter-based generator of BASELINE.json's synthetic streams; integer-only, identical on host and device. */
+typedef struct agr_synth {
+    uint64_t seed;
+    uint32_t n_agents;        /* 16 / 256 */
+    uint32_t zipf_milli;      /* 0 = uniform; 1200 = Zipf s=1.2 by rank */
+    uint32_t dup_permille;    /* replay-flagged duplicates per 1000 records (C3: 100) */
+    uint32_t reserved;
+    uint64_t agent_nanos0;    /* agent k has id "agent-<agent_nanos0 + k*1000003>" */
+} agr_synth;
+int agr_synth_agent_id(const agr_synth* s, uint32_t k, char out[AGR_AGENT_ID_BYTES]);
+int agr_synth_fill_host(const agr_synth* s, uint64_t first_index, uint32_t n, agr_record* out);
+int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index, uint64_t first_rid, uint32_t n);
+
+/* shard owner of an agent: FNV-1a 64 of the id bytes, mod n_shards.  Go: hash/fnv New64a. */
+uint64_t agr_agent_hash(const char* agent_id);
+uint32_t agr_agent_shard(const char* agent_id, uint32_t n_shards);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGENTAINER_GPU_H */

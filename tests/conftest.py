@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from agentainer_lab_b200 import load_library
+    return load_library()

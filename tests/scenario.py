@@ -1,0 +1,346 @@
+"""Event-stream scenarios and their two interpreters.
+
+A scenario is a list of events in a total order (the order commands would reach the single Redis server):
+
+  ("agent",  agent_id, status)                 saveAgent / state sync writes Agent.Status
+  ("remove", agent_id)                         agent.Manager.Remove
+  ("req",    Req, backend)                     one HTTP call to /agent/{id}/...; backend = what the agent side does
+                                               if the proxy forwards it: ("response", code) | ("dial",) | ("error",)
+  ("tick",   backends, flip)                   one ReplayWorker tick; backends maps request-id hex -> backend for
+                                               that replay (default ("response", 200), also ("client",)); flip =
+                                               None or (k, agent_id, status): status write right after the k-th
+                                               replay of the tick (only for the agent being replayed, see below)
+
+run_oracle() executes the literal restatement of the Go code (oracle/model.py).  run_engine() does what the Go
+glue does with the C-ABI: batch consecutive requests into agr_ingest, report outcomes through agr_complete, and on
+a tick call agr_replay_scan, re-inject each dispatched record replay-flagged, and report the server-side and
+worker-side completions (replay_worker.go:120-163) in the order the reference performs them.
+
+Tick linearisation: the reference checks isAgentRunning and snapshots the pending list per agent when its turn
+comes; the engine snapshots all agents at the scan.  The two agree whenever no OTHER agent's status changes in the
+middle of a tick, which is what these scenarios guarantee (a flip only ever targets the agent being replayed —
+KAT-F / Q8).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import model as M  # noqa: E402
+
+ZERO16 = bytes(16)
+
+
+@dataclass
+class Req:
+    agent_id: str
+    rid: bytes                     # the id StoreRequest would mint (uuid.New) — 16 raw bytes
+    seq: int
+    replay: bool = False           # X-Agentainer-Replay: true
+    replay_of: bytes = ZERO16      # X-Agentainer-Request-ID
+    method: str = "POST"
+    subpath: str = "/chat"
+    body: bytes = b'{"message":"hi"}'
+    headers: Dict[str, str] = field(default_factory=lambda: {"Content-Type": "application/json"})
+
+    @property
+    def path(self) -> str:
+        return f"/agent/{self.agent_id}{self.subpath}"
+
+
+@dataclass
+class Observed:
+    verdicts: List[Tuple] = field(default_factory=list)        # per "req": (code, http, stored, tracked)
+    ticks: List[List[Tuple[str, str]]] = field(default_factory=list)   # per tick: [(agent_id, id hex)] dispatch order
+    lists: Dict[str, Dict[str, List[str]]] = field(default_factory=dict)   # agent -> pending/completed/failed id hex
+    records: Dict[Tuple[str, str], Tuple] = field(default_factory=dict)   # (agent, id hex) -> (status, retry, resp)
+
+    def per_agent_ticks(self):
+        out = []
+        for t in self.ticks:
+            d: Dict[str, List[str]] = {}
+            for a, r in t:
+                d.setdefault(a, []).append(r)
+            out.append(d)
+        return out
+
+
+def all_agents(events) -> List[str]:
+    seen: List[str] = []
+    for e in events:
+        a = e[1].agent_id if e[0] == "req" else (e[1] if e[0] in ("agent", "remove") else None)
+        if a is not None and a not in seen:
+            seen.append(a)
+    return seen
+
+
+def all_fresh(events) -> List[Tuple[str, bytes]]:
+    return [(e[1].agent_id, e[1].rid) for e in events if e[0] == "req" and not e[1].replay]
+
+
+# ----------------------------------------------------------------------------------------------- oracle side
+def run_oracle(events, persistence: bool = True) -> Observed:
+    ref = M.ReferencePath(persistence)
+    obs = Observed()
+    for e in events:
+        if e[0] == "agent":
+            ref.set_agent(e[1], e[2])
+        elif e[0] == "remove":
+            ref.remove_agent(e[1])
+        elif e[0] == "req":
+            r: Req = e[1]
+            headers = dict(r.headers)
+            if r.replay:
+                headers["X-Agentainer-Replay"] = "true"
+                if r.replay_of != ZERO16:
+                    headers["X-Agentainer-Request-ID"] = r.replay_of.hex()
+            req = M.HttpRequest(r.method, r.path, headers, r.body, new_id=r.rid.hex(), now=r.seq)
+            v, _ = ref.request(r.agent_id, req, e[2])
+            obs.verdicts.append((v.code, v.http_status, v.stored, v.request_id != ""))
+        elif e[0] == "tick":
+            backends, flip = e[1], e[2]
+
+            def backend_for(agent_id, req, _b=backends):
+                return _b.get(req["id"], ("response", 200))
+
+            def on_replay(agent_id, request_id, k, _f=flip):
+                if _f is not None and k == _f[0]:
+                    ref.set_agent(_f[1], _f[2])
+
+            obs.ticks.append(ref.tick(backend_for, now=0, on_replay=on_replay))
+        else:
+            raise ValueError(e[0])
+    for a in all_agents(events):
+        obs.lists[a] = ref.lists(a)
+    for a, rid in all_fresh(events):
+        st = ref.record_state(a, rid.hex())
+        if st is not None:
+            obs.records[(a, rid.hex())] = st
+    return obs
+
+
+# ----------------------------------------------------------------------------------------------- engine side
+def make_records(reqs: List[Req]) -> np.ndarray:
+    from agentainer_lab_b200 import record_dtype, constants as K
+    recs = np.zeros(len(reqs), dtype=record_dtype)
+    for i, r in enumerate(reqs):
+        recs[i]["request_id"] = np.frombuffer(r.rid, dtype=np.uint8)
+        recs[i]["replay_of"] = np.frombuffer(r.replay_of if r.replay else ZERO16, dtype=np.uint8)
+        recs[i]["agent_id"] = r.agent_id.encode()
+        recs[i]["seq"] = r.seq
+        recs[i]["flags"] = (K.AGR_F_REPLAY if r.replay else 0) | (K.METHOD_CODES[r.method] << K.AGR_F_METHOD_SHIFT)
+        path = r.path.encode()
+        hdrs = "".join(f"{k}: {v}\n" for k, v in sorted(r.headers.items())).encode()
+        blob = path + hdrs + r.body
+        assert len(blob) <= 416
+        recs[i]["path_len"], recs[i]["hdr_len"], recs[i]["body_len"] = len(path), len(hdrs), len(r.body)
+        recs[i]["status"], recs[i]["max_retries"] = K.AGR_ST_PENDING, 3
+        recs[i]["payload"][: len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+    return recs
+
+
+def _outcome(outs: list, rid: bytes, agent_id: str, kind: int, http: int = 0, seq: int = 0):
+    outs.append((rid, agent_id, kind, http, seq))
+
+
+def _outcomes_array(outs: list) -> np.ndarray:
+    from agentainer_lab_b200 import outcome_dtype
+    arr = np.zeros(len(outs), dtype=outcome_dtype)
+    for j, (rid, agent_id, kind, http, seq) in enumerate(outs):
+        arr[j]["request_id"] = np.frombuffer(rid, dtype=np.uint8)
+        arr[j]["agent_id"] = agent_id.encode()
+        arr[j]["kind"], arr[j]["http_status"], arr[j]["seq"] = kind, http, seq
+    return arr
+
+
+def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
+    """Drive the C-ABI like the Go glue.  max_batch / rng vary how consecutive requests are batched (results must
+    not depend on it)."""
+    from agentainer_lab_b200 import constants as K
+    obs = Observed()
+    slot_name: Dict[int, str] = {}
+    pend_reqs: List[Tuple[Req, Tuple]] = []
+
+    def flush():
+        nonlocal pend_reqs
+        while pend_reqs:
+            take = len(pend_reqs) if rng is None else int(rng.integers(1, len(pend_reqs) + 1))
+            take = min(take, max_batch)
+            chunk, pend_reqs = pend_reqs[:take], pend_reqs[take:]
+            recs = make_records([r for r, _ in chunk])
+            verdicts, _ = eng.ingest(recs)
+            outs: list = []
+            for (r, backend), v in zip(chunk, verdicts):
+                code, flags = int(v["code"]), int(v["flags"])
+                tracked = bool(flags & K.AGR_VF_TRACKED)
+                obs.verdicts.append((code, int(v["http_status"]), bool(flags & K.AGR_VF_STORED), tracked))
+                if code != K.AGR_V_FORWARD or not tracked:
+                    continue                                 # interceptTransport: requestID == "" records nothing
+                rid = r.replay_of if r.replay else r.rid
+                if backend[0] == "response":
+                    _outcome(outs, rid, r.agent_id, K.AGR_OUT_RESPONSE, backend[1], r.seq)
+                elif backend[0] == "dial":
+                    _outcome(outs, rid, r.agent_id, K.AGR_OUT_DIAL_ERR, 0, r.seq)
+                else:
+                    _outcome(outs, rid, r.agent_id, K.AGR_OUT_ERROR, 0, r.seq)
+            if outs:
+                eng.complete(_outcomes_array(outs))
+
+    for e in events:
+        if e[0] == "req":
+            pend_reqs.append((e[1], e[2]))
+            continue
+        flush()
+        if e[0] == "agent":
+            slot_name[eng.set_agent_state(e[1], e[2])] = e[1]
+        elif e[0] == "remove":
+            eng.drop_agent(e[1])
+        elif e[0] == "tick":
+            backends, flip = e[1], e[2]
+            disp, recs = eng.replay_scan(with_records=True)
+            order = [(slot_name[int(d["agent_slot"])], bytes(d["request_id"]).hex()) for d in disp]
+            obs.ticks.append(order)
+            # replayRequest (replay_worker.go:120-163): same record, replay-flagged, ID in the tracking header
+            recs = recs.copy()
+            recs["flags"] |= K.AGR_F_REPLAY
+            recs["replay_of"] = recs["request_id"]
+            cuts = [0, len(recs)]
+            if flip is not None and 0 < flip[0] < len(recs):
+                cuts = [0, flip[0], len(recs)]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if a > 0 and flip is not None:
+                    eng.set_agent_state(flip[1], flip[2])
+                seg = np.ascontiguousarray(recs[a:b])
+                if len(seg) == 0:
+                    continue
+                verdicts, _ = eng.ingest(seg)
+                outs = []
+                for rec, v, (agent_id, rid_hex) in zip(seg, verdicts, order[a:b]):
+                    rid = bytes(rec["request_id"])
+                    code = int(v["code"])
+                    backend = backends.get(rid_hex, ("response", 200))
+                    if code == K.AGR_V_FORWARD:
+                        if backend[0] == "response":        # server side (server.go:588-594) then worker (:158)
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, backend[1])
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, backend[1])
+                        elif backend[0] == "dial":          # server: stays pending; proxy answers 502 -> worker completes
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_DIAL_ERR)
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, 502)
+                        elif backend[0] == "error":         # server: MarkRequestFailed; 502 -> worker completes (KAT-H)
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_ERROR)
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, 502)
+                        else:                               # worker's own client failed (replay_worker.go:109-112)
+                            _outcome(outs, rid, agent_id, K.AGR_OUT_ERROR)
+                    else:                                   # proxy answered itself (202 / 503 / 404): worker stores it (Q8)
+                        _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, int(v["http_status"]))
+                if outs:
+                    eng.complete(_outcomes_array(outs))
+            if flip is not None and flip[0] >= len(recs):
+                eng.set_agent_state(flip[1], flip[2])
+        else:
+            raise ValueError(e[0])
+    flush()
+    names = {0: "pending", 1: "completed", 2: "failed"}
+    for a in all_agents(events):
+        obs.lists[a] = {names[w]: [bytes(x).hex() for x in eng.list(a, w)] for w in (0, 1, 2)}
+    for a, rid in all_fresh(events):
+        rec = eng.get_record(a, rid)
+        if rec is not None:
+            obs.records[(a, rid.hex())] = (K.STATUS_NAMES[int(rec["status"])], int(rec["retry_count"]), int(rec["resp_status"]))
+    return obs
+
+
+def assert_same(o: Observed, g: Observed) -> None:
+    assert o.verdicts == g.verdicts, _first_diff(o.verdicts, g.verdicts, "verdict")
+    assert o.per_agent_ticks() == g.per_agent_ticks(), "replay dispatch order differs"
+    assert o.ticks == g.ticks, "cross-agent dispatch order differs from the canonical (registration) order"
+    assert o.lists == g.lists, _lists_diff(o.lists, g.lists)
+    assert o.records == g.records, _first_diff(sorted(o.records.items()), sorted(g.records.items()), "record")
+
+
+def _first_diff(a, b, what):
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            return f"{what} {i}: oracle {x} != engine {y}"
+    return f"{what} count: oracle {len(a)} != engine {len(b)}"
+
+
+def _lists_diff(a, b):
+    for ag in a:
+        for q in a[ag]:
+            if a[ag][q] != b.get(ag, {}).get(q):
+                return f"list {ag}/{q}: oracle {a[ag][q][:6]}.. (n={len(a[ag][q])}) != engine {b.get(ag, {}).get(q, [])[:6]}.. (n={len(b.get(ag, {}).get(q, []))})"
+    return "lists differ"
+
+
+# ----------------------------------------------------------------------------------------------- generators
+def rid_of(i: int) -> bytes:
+    """Deterministic UUIDv4-shaped id for scenario record i."""
+    import hashlib
+    b = bytearray(hashlib.sha256(b"agr-scenario-%d" % i).digest()[:16])
+    b[6] = (b[6] & 0x0F) | 0x40
+    b[8] = (b[8] & 0x3F) | 0x80
+    return bytes(b)
+
+
+def random_scenario(seed: int, n_events: int = 300, n_agents: int = 5, p_replay: float = 0.1) -> list:
+    """Mixed stream: status flips, fresh requests with all backend kinds, client-sent replay-flagged duplicates,
+    ticks with mixed replay outcomes and KAT-F style mid-tick flips."""
+    rng = np.random.default_rng(seed)
+    agents = [f"agent-{1700000000000000000 + 1000003 * k}" for k in range(n_agents)]
+    events: list = []
+    status = {}
+    for a in agents:
+        status[a] = "running" if rng.random() < 0.6 else "stopped"
+        events.append(("agent", a, status[a]))
+    fresh: Dict[str, List[bytes]] = {a: [] for a in agents}
+    ctr = 0
+    for _ in range(n_events):
+        u = rng.random()
+        if u < 0.07:
+            a = agents[int(rng.integers(n_agents))]
+            status[a] = str(rng.choice(["running", "stopped", "paused", "failed", "created"], p=[0.5, 0.3, 0.1, 0.05, 0.05]))
+            events.append(("agent", a, status[a]))
+        elif u < 0.12:
+            backends = {}
+            for a in agents:
+                for rid in fresh[a]:
+                    v = rng.random()
+                    if v < 0.12:
+                        backends[rid.hex()] = ("dial",)
+                    elif v < 0.24:
+                        backends[rid.hex()] = ("error",)
+                    elif v < 0.30:
+                        backends[rid.hex()] = ("client",)
+                    elif v < 0.40:
+                        backends[rid.hex()] = ("response", int(rng.choice([404, 500, 503])))
+            events.append(("tick", backends, None))
+        else:
+            ctr += 1
+            a = agents[int(rng.integers(n_agents))] if rng.random() > 0.03 else "agent-unknown"
+            v = rng.random()
+            backend = ("response", 200) if v < 0.7 else (("dial",) if v < 0.8 else (("error",) if v < 0.92 else ("response", 500)))
+            if a != "agent-unknown" and fresh[a] and rng.random() < p_replay:
+                w = rng.random()
+                if w < 0.8:
+                    target = fresh[a][int(rng.integers(len(fresh[a])))]
+                elif w < 0.9:
+                    target = rid_of(10_000_000 + ctr)          # unknown id
+                else:
+                    target = ZERO16                             # header absent
+                events.append(("req", Req(a, rid_of(ctr), ctr, replay=True, replay_of=target), backend))
+            else:
+                r = Req(a, rid_of(ctr), ctr, body=b'{"message":"m%d"}' % ctr)
+                if a != "agent-unknown":
+                    fresh[a].append(r.rid)
+                events.append(("req", r, backend))
+    events.append(("tick", {}, None))
+    return events

@@ -1,0 +1,63 @@
+"""The oracle against the hand-derived known-answer traces.  CPU only."""
+import pytest
+
+from kats import SCENARIOS, load_golden, AGENT_A
+from scenario import run_oracle, rid_of, Req
+from oracle import model as M
+
+GOLD, RAW = load_golden()
+
+
+@pytest.mark.parametrize("kat", sorted(SCENARIOS))
+def test_oracle_matches_golden(kat):
+    obs = run_oracle(SCENARIOS[kat])
+    exp = GOLD[kat]
+    assert obs.verdicts == exp["verdicts"]
+    assert obs.ticks == exp["ticks"]
+    for a, qs in exp["lists"].items():
+        assert obs.lists[a] == qs, (kat, a)
+    assert obs.records == exp["records"]
+
+
+def test_kat_a_redis_command_order():
+    """KAT-A also pins the ORDER of the seven Redis commands of one proxied request."""
+    ref = M.ReferencePath()
+    ref.set_agent("A", "running")
+    ref.redis.trace = True
+    r1 = rid_of(1).hex()
+    ref.request("A", M.HttpRequest("POST", "/agent/A/chat", {}, b"{}", new_id=r1, now=1), ("response", 200))
+    ops = [" ".join(op[:1] + tuple(x.replace(f"agent:A:requests:{r1}", "rec").replace("agent:A:requests:", "").replace(r1, "r1")
+                                   for x in op[1:])) for op in ref.redis.ops]
+    assert ops == RAW["redis_ops_KAT-A"]
+
+
+def test_lrem_removes_first_match_only():
+    r = M.MiniRedis()
+    for v in ["a", "b", "a", "c"]:
+        r.rpush("k", v)
+    assert r.lrem("k", 1, "a") == 1
+    assert r.lrange_all("k") == ["b", "a", "c"]
+    assert r.lrem("k", 1, "zz") == 0
+    for v in ["b", "a", "c"]:
+        r.lrem("k", 1, v)
+    assert r.keys("k*") == []          # empty list does not exist as a key
+
+
+def test_replay_path_strip():
+    """replayRequest strips /agent/{id} and maps "" to "/" (replay_worker.go:123-130)."""
+    ref = M.ReferencePath()
+    ref.set_agent(AGENT_A, "stopped")
+    seen = []
+    orig = ref.proxy.handle
+
+    def spy(agent_id, req, backend):
+        seen.append(req.path)
+        return orig(agent_id, req, backend)
+
+    ref.proxy.handle = spy
+    for i, sub in enumerate(["/chat", "", "/"]):
+        r = Req(AGENT_A, rid_of(i + 1), i + 1, subpath=sub)
+        orig(AGENT_A, M.HttpRequest("POST", r.path, {}, b"", new_id=r.rid.hex(), now=i), ("response", 200))
+    ref.set_agent(AGENT_A, "running")
+    ref.tick(lambda a, r: ("response", 200), now=9)
+    assert seen == [f"/agent/{AGENT_A}/chat", f"/agent/{AGENT_A}/", f"/agent/{AGENT_A}/"]

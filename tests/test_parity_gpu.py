@@ -1,0 +1,142 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the golden KATs.  GPU only.
+Integer / byte work: the bar is bit-exact on verdicts, per-record (status, retry, response), per-agent
+pending / completed / failed id sequences (with the Q7 duplicates) and per-tick replay dispatch order."""
+import numpy as np
+import pytest
+
+import agentainer_lab_b200 as A
+from agentainer_lab_b200 import constants as K
+from kats import SCENARIOS, load_golden
+from scenario import run_oracle, run_engine, assert_same, random_scenario, Req, rid_of, make_records
+
+pytestmark = pytest.mark.gpu
+GOLD, _ = load_golden()
+
+
+def engine(**kw):
+    kw.setdefault("slab_rows", 1 << 15)
+    kw.setdefault("max_agents", 256)
+    return A.Engine(**kw)
+
+
+@pytest.mark.parametrize("kat", sorted(SCENARIOS))
+def test_kat_against_golden_and_oracle(kat):
+    with engine() as eng:
+        got = run_engine(eng, SCENARIOS[kat])
+    exp = GOLD[kat]
+    assert got.verdicts == exp["verdicts"]
+    assert got.ticks == exp["ticks"]
+    for a, qs in exp["lists"].items():
+        assert got.lists[a] == qs, (kat, a)
+    assert got.records == exp["records"]
+    assert_same(run_oracle(SCENARIOS[kat]), got)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_streams_match_oracle(seed):
+    ev = random_scenario(seed, n_events=400, n_agents=2 + seed % 6)
+    with engine() as eng:
+        assert_same(run_oracle(ev), run_engine(eng, ev))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_result_does_not_depend_on_batching(seed):
+    """Same stream, requests batched 1-by-1, in random-size batches, or all at once: identical observables."""
+    ev = random_scenario(100 + seed, n_events=250, n_agents=4, p_replay=0.25)
+    ref = run_oracle(ev)
+    with engine() as eng:
+        assert_same(ref, run_engine(eng, ev, max_batch=1))
+    with engine() as eng:
+        assert_same(ref, run_engine(eng, ev, rng=np.random.default_rng(seed)))
+
+
+def test_persistence_disabled():
+    ev = [("agent", "agent-1", "running"), ("agent", "agent-2", "stopped"),
+          ("req", Req("agent-1", rid_of(1), 1), ("response", 200)), ("req", Req("agent-2", rid_of(2), 2), ("response", 200))]
+    with engine(flags=0x80000000) as eng:      # any non-zero flags word without AGR_CFG_PERSISTENCE
+        got = run_engine(eng, ev)
+    assert_same(run_oracle(ev, persistence=False), got)
+    assert got.verdicts == [(1, 0, False, False), (3, 503, False, False)]
+
+
+def test_duplicate_fresh_id_is_a_persistence_failure():
+    """ABI contract (not reachable in the reference, whose ids come from uuid.New): a fresh record whose id is already
+    stored — in an earlier batch or EARLIER IN THE SAME BATCH — is not stored and goes on untracked."""
+    with engine() as eng:
+        eng.set_agent_state("agent-1", "running")
+        eng.set_agent_state("agent-2", "stopped")
+        reqs = [Req("agent-1", rid_of(1), 1), Req("agent-2", rid_of(2), 2), Req("agent-1", rid_of(1), 3),
+                Req("agent-2", rid_of(2), 4), Req("agent-2", rid_of(1), 5)]
+        v, _ = eng.ingest(make_records(reqs))
+        assert [int(x) for x in v["code"]] == [1, 2, 1, 3, 3]
+        assert [int(x) & K.AGR_VF_STORED for x in v["flags"]] == [1, 1, 0, 0, 0]
+        assert [bool(int(x) & K.AGR_VF_DUP_ID) for x in v["flags"]] == [False, False, True, True, True]
+        v2, _ = eng.ingest(make_records([Req("agent-1", rid_of(2), 6), Req("agent-1", rid_of(7), 7)]))
+        assert [bool(int(x) & K.AGR_VF_DUP_ID) for x in v2["flags"]] == [True, False]
+        assert [bytes(x).hex() for x in eng.list("agent-2", 0)] == [rid_of(2).hex()]
+        s = eng.stats()
+        assert s["dup_ids"] == 4 and s["stored"] == 3
+
+
+def test_large_batch_duplicate_race_is_resolved_by_arrival_order():
+    """Many duplicates inside one big batch: whichever thread wins the insert race, the LOWEST row keeps the id."""
+    n = 1 << 14
+    reqs = A.synth_fill_host(0, n, seed=21, n_agents=8)
+    reqs2 = reqs.copy()
+    dup_src = np.arange(0, n // 2, 7)
+    dup_dst = n - 1 - np.arange(len(dup_src))
+    reqs2["request_id"][dup_dst] = reqs2["request_id"][dup_src]
+    with engine(slab_rows=1 << 16) as eng:
+        for k in range(8):
+            eng.set_agent_state(A.synth_agent_id(k), "running")
+        v, _ = eng.ingest(reqs2)
+        dup = (v["flags"] & K.AGR_VF_DUP_ID) != 0
+        assert set(np.nonzero(dup)[0]) == set(dup_dst)
+        assert ((v["flags"][~dup] & K.AGR_VF_STORED) != 0).all()
+
+
+def test_known_flag_means_stored_earlier():
+    with engine() as eng:
+        eng.set_agent_state("agent-1", "running")
+        reqs = [Req("agent-1", rid_of(1), 1, replay=True, replay_of=rid_of(2)),   # names a LATER row of the same batch
+                Req("agent-1", rid_of(2), 2),
+                Req("agent-1", rid_of(3), 3, replay=True, replay_of=rid_of(2))]
+        v, _ = eng.ingest(make_records(reqs))
+        assert [bool(int(x) & K.AGR_VF_KNOWN) for x in v["flags"]] == [False, False, True]
+        assert eng.stats()["dedupe_hits"] == 1
+
+
+def test_pending_and_get_record_views():
+    ev = [("agent", "agent-1", "stopped")] + [("req", Req("agent-1", rid_of(i), i, body=b"x" * i), ("response", 200)) for i in range(1, 40)]
+    with engine() as eng:
+        run_engine(eng, ev)
+        pend = eng.pending("agent-1")
+        assert [bytes(r["request_id"]) for r in pend] == [rid_of(i) for i in range(1, 40)]
+        assert (pend["status"] == K.AGR_ST_PENDING).all() and (pend["body_len"] == np.arange(1, 40)).all()
+        rec = eng.get_record("agent-1", rid_of(7))
+        assert int(rec["seq"]) == 7 and bytes(rec["payload"][rec["path_len"] + rec["hdr_len"]:][:7]) == b"x" * 7
+        assert eng.get_record("agent-1", rid_of(99)) is None
+        assert eng.get_record("agent-2", rid_of(7)) is None
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 2 at full size (1 M records, 256 agents, all running): size-independent properties."""
+    n, na = 1 << 20, 256
+    with A.Engine(slab_rows=n, max_agents=512, max_batch=n) as eng:
+        for k in range(na):
+            eng.set_agent_state(A.synth_agent_id(k), "running")
+        first = eng.reserve_rows(n)
+        eng.synth_fill_rows(0, first, n, seed=2, n_agents=na)
+        v = eng.ingest_rows(first, n)
+        assert (v["code"] == K.AGR_V_FORWARD).all() and ((v["flags"] & K.AGR_VF_STORED) != 0).all()
+        s = eng.stats()
+        assert s["ingested"] == n and s["stored"] == n and s["forwarded"] == n and s["dup_ids"] == 0
+        host = A.synth_fill_host(0, 4096, seed=2, n_agents=na)
+        slots = {A.synth_agent_id(k).encode(): k for k in range(na)}
+        assert [slots[x] for x in host["agent_id"]] == list(v["agent_slot"][:4096])
+        # every record pending, per-agent FIFO == arrival order
+        a0 = A.synth_agent_id(3)
+        ids = eng.list(a0, K.AGR_LIST_PENDING, cap=1 << 14)
+        mask = host["agent_id"] == a0.encode()
+        assert [bytes(x) for x in ids[: mask.sum()]] == [bytes(x) for x in host["request_id"][mask]]
+        assert sum(len(eng.list(A.synth_agent_id(k), 0, cap=1 << 14)) for k in range(0, na, 37)) > 0
