@@ -55,7 +55,7 @@ AGR_HD uint32_t agr_synth_agent_name(unsigned long long nanos, char* out /*32*/)
 }
 
 #define AGR_SYNTH_HDRS "Content-Type: application/json\nUser-Agent: agr-synth/1\n"
-#define AGR_SYNTH_HDRS_LEN 56u
+#define AGR_SYNTH_HDRS_LEN 55u
 
 // Writes record i (512 B) to out.  out must be 8-byte aligned.
 AGR_HD void agr_synth_record(const agr_synth_dev& s, unsigned long long i, unsigned char* out) {
