@@ -72,7 +72,10 @@ struct agr_handle {
     uint64_t k1_launches = 0, k2_launches = 0, k3_launches = 0, k4_launches = 0;
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
+    // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
+    std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
 };
+#define AGR_TIMING_RING 1024
 
 template <typename T>
 static int dev_alloc(agr_handle* h, T** p, size_t count, bool zero) {
@@ -222,6 +225,7 @@ void agr_destroy(agr_handle* h) {
     for (void* p : h->dev_allocs) cudaFree(p);
     for (void* p : h->host_allocs) cudaFreeHost(p);
     for (int k = 0; k < 2; ++k) if (h->bounce_ev[k]) cudaEventDestroy(h->bounce_ev[k]);
+    for (auto e : h->tev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -319,7 +323,16 @@ static void expand_verdicts(const uint32_t* route, uint32_t n, agr_verdict* out)
 static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, bool sync) {
     if (first + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
     if (n == 0) return 0;
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->sm_count, h->stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->cfg.flags & AGR_CFG_TIMING) {
+        if (h->tev.empty()) {
+            h->tev.resize(2 * AGR_TIMING_RING);
+            for (auto& e : h->tev) CK(cudaEventCreate(&e));
+        }
+        const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
+        e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
+    }
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->sm_count, h->stream, e0, e1);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
     if (out) {
@@ -617,6 +630,24 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
     out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches;
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
+    return 0;
+}
+
+int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches) {
+    if (!h || !sum_ms || !launches) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    *sum_ms = 0; *launches = 0;
+    uint64_t from = h->tev_read;
+    if (h->tev_next - from > AGR_TIMING_RING) from = h->tev_next - AGR_TIMING_RING;
+    for (uint64_t i = from; i < h->tev_next; ++i) {
+        float ms = 0;
+        const uint64_t k = i % AGR_TIMING_RING;
+        CK(cudaEventElapsedTime(&ms, h->tev[2 * k], h->tev[2 * k + 1]));
+        *sum_ms += ms; (*launches)++;
+    }
+    h->tev_read = h->tev_next;
     return 0;
 }
 

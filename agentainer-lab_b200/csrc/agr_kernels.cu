@@ -279,16 +279,19 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
 
 int agr_k1_launches_per_batch(uint32_t) { return 2; }
 
-void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, int sm_count, cudaStream_t st) {
+void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, int sm_count, cudaStream_t st,
+                   cudaEvent_t ev0, cudaEvent_t ev1) {
     if (n == 0) return;
     (void)variant;
     cudaMemsetAsync(d.dupfix, 0, sizeof(uint32_t), st);
+    if (ev0) cudaEventRecord(ev0, st);
     constexpr int WARPS = 8;
     const uint32_t tiles = (n + 31u) / 32u;
     uint32_t blocks = (tiles + WARPS - 1) / WARPS;
     const uint32_t maxb = (uint32_t)sm_count * 8u;
     if (blocks > maxb) blocks = maxb;
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
+    if (ev1) cudaEventRecord(ev1, st);
     k1_post<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
 }
 

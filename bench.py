@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json): agent requests/sec through
+ingest + dedupe + route on 512 B records.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+A "step" is ONE pass of the hot path (K1: ingest + dedupe + route) over ONE batch of the workload's records
+(c2 = BASELINE configs[1]: 1 M synthetic 512 B records, 256 agent ids, uniform, all agents running).
+  value     whole-job records/s, records already resident in the HBM slab when the timed region starts
+            (CUDA events on the engine's stream, barrier + synchronize on both sides, max over ranks);
+  e2e       the same metric through the C-ABI call a host makes (agr_ingest) with PINNED HOST buffers: the
+            host->device copy of the step's records and the device->host read of its verdicts are inside the
+            timed region;
+  roofline  dominant kernel (k1_ingest): algorithmic bytes (520 B/record) / its device time measured
+            live with CUDA events on the launching stream, against MEASURED_PEAKS.json hbm_gbs;
+  cpu_baseline  the C restatement of the reference's Go+Redis path (oracle/cpu_ref.c, kind "port": the reference
+            itself cannot be built in this image) timed on ONE host core over a bounded sample.
+  --impl reference  times that CPU restatement on all host threads (agents sharded across threads) on the same
+            workload/metric — the reference arm the driver compares against.
+Under torchrun (N > 1) every rank owns one GPU and one shard of the agents; no data-path collective is needed
+for c2/c3 (records are steered to the owner shard before the copy), so scaling is "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent_requests_per_sec_ingest_dedupe_route_512B"
+ALG_BYTES_PER_RECORD = 520          # 512 B record read + 4 B queue/state entry + 4 B verdict
+WORKLOADS = {
+    "c2": dict(name="C2: 1M synthetic 512B POST /agent/<id>/chat records per step, 256 agent ids, uniform, all agents running, no crash-replay",
+               records=1 << 20, agents=256, zipf_milli=0, dup_permille=0),
+    "c3": dict(name="C3: 10M records (10 steps of 1M), 256 agent ids Zipf s=1.2, 10% replay-flagged duplicates",
+               records=1 << 20, agents=256, zipf_milli=1200, dup_permille=100),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        hi = sorted(sm)[len(sm) // 2:]          # the upper half of the samples = the ones taken under load
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16):
+    n = len(out)
+    per = (n + threads - 1) // threads
+    ts = []
+    for t in range(threads):
+        a, b = t * per, min(n, (t + 1) * per)
+        if a >= b:
+            break
+        th = threading.Thread(target=A.synth_fill_host, args=(first_index + a, b - a),
+                              kwargs=dict(seed=seed, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"],
+                                          dup_permille=wl["dup_permille"], agent_nanos0=nanos0, out=out[a:b]))
+        th.start(); ts.append(th)
+    for th in ts:
+        th.join()
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_single(A, wl, budget_s=12.0, max_records=3_000_000):
+    """oracle/cpu_ref.c (restatement of the Go+Redis path) on ONE core over a bounded sample of the workload."""
+    from oracle.cpu_ref import CRef
+    chunk = 1 << 16
+    c = CRef()
+    for k in range(wl["agents"]):
+        c.set_agent_state(A.synth_agent_id(k), "running")
+    done, spent = 0, 0.0
+    while spent < budget_s and done < max_records:
+        recs = A.synth_fill_host(done, chunk, seed=2, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"], dup_permille=wl["dup_permille"])
+        t = time.perf_counter()
+        c.ingest(recs)
+        spent += time.perf_counter() - t
+        done += chunk
+    c.close()
+    return {"value": done / spent, "unit": "requests/s", "cores": 1, "kind": "port",
+            "sample": f"first {done} records of the workload stream, ingest+dedupe+route only (GetAgent + StoreRequest + status gate with JSON/base64 marshal, no RESP/TCP), {spent:.1f} s"}
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the CPU restatement with all host threads (agents sharded over threads; the real
+    reference serialises on one Redis thread, so this flatters it)."""
+    import agentainer_lab_b200 as A
+    from oracle.cpu_ref import CRef
+    if rank != 0:
+        return
+    threads = max(1, min(os.cpu_count() or 1, wl["agents"], 64))
+    per_step = wl["records"] if threads >= 16 else wl["records"] // 8
+    agents = [A.synth_agent_id(k).encode() for k in range(wl["agents"])]
+    owner = {a: i % threads for i, a in enumerate(agents)}
+    shards = [CRef() for _ in range(threads)]
+    for i, a in enumerate(agents):
+        shards[i % threads].set_agent_state(a.decode(), "running")
+    times = []
+    buf = np.zeros(per_step, dtype=A.record_dtype)
+    for step in range(args.warmup + args.steps):
+        parallel_fill(A, buf, step * per_step, wl, 2, 0, threads=min(32, os.cpu_count() or 1))
+        # steer each record to the thread that owns its agent (the Go host does this when it parses the path)
+        idx = np.searchsorted(np.array(sorted(agents)), buf["agent_id"])
+        rank_of = np.array([owner[a] for a in sorted(agents)], dtype=np.int32)[idx]
+        parts = [np.ascontiguousarray(buf[rank_of == t]) for t in range(threads)]
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=shards[t].ingest, args=(parts[t],)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = per_step * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "requests/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["name"], "records_per_step": per_step, "agents": wl["agents"]},
+            "cpu_baseline": {"value": val, "unit": "requests/s", "cores": threads, "kind": "port",
+                             "sample": f"{per_step} records per step, agents sharded over {threads} threads of oracle/cpu_ref.c (reference Go+Redis cannot be built here: no go, no redis-server)"},
+            "e2e": {"value": val, "unit": "requests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import agentainer_lab_b200 as A
+    from agentainer_lab_b200 import constants as K
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    B, W, S = wl["records"], args.warmup, args.steps
+    e_steps, e_warm = min(S, args.e2e_steps), 1
+    rows = (W + S) * B + (e_warm + e_steps) * B
+    eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant,
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING)
+    nanos0 = 1700000000000000000 + rank * 10_000_000_000        # each rank (shard) owns its own agent ids
+    for k in range(wl["agents"]):
+        eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
+    synth = dict(seed=2 + rank, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"], dup_permille=wl["dup_permille"], agent_nanos0=nanos0)
+    first = eng.reserve_rows((W + S) * B)
+    for s in range(W + S):                                       # records resident in HBM before the timed region
+        eng.synth_fill_rows(s * B, first + s * B, B, **synth)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for s in range(W):
+        eng.ingest_rows_async(first + s * B, B)
+    eng.sync()
+    eng.kernel_time()                                            # drop warm-up launches from the kernel timer
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for s in range(W, W + S):
+        eng.ingest_rows_async(first + s * B, B)
+    ev1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    if dist:
+        dist.barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    k_ms, k_n = eng.kernel_time()
+    clocks = sampler.stop()
+    st = eng.stats()
+    assert st["ingested"] == (W + S) * B, st
+    # ---- e2e through the public C-ABI call with pinned host buffers (H2D + kernels + D2H verdicts timed)
+    pin = eng.pinned(B)
+    e_times = []
+    launches_before = st["k1_launches"]
+    for s in range(e_warm + e_steps):
+        parallel_fill(A, pin.array, (W + S + s) * B, wl, synth["seed"], nanos0)
+        if dist:
+            dist.barrier()
+        t = time.perf_counter()
+        verdicts, _ = eng.ingest(pin.array)
+        dt = time.perf_counter() - t
+        if s >= e_warm:
+            e_times.append(dt)
+    assert (verdicts["code"] != 0).all()
+    pin.free()
+    e_ms = 1e3 * sum(e_times) / len(e_times)
+    if dist:
+        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dev_ms, e_ms, k_avg = [float(x) for x in t_all.tolist()]
+    else:
+        k_avg = k_ms / max(1, k_n)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = ALG_BYTES_PER_RECORD * B / (k_avg * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(f"variant{args.variant}", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = cpu_port_single(A, wl) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": METRIC, "value": world * B * S / (dev_ms * 1e-3), "unit": "requests/s", "n_gpus": world, "steps": S, "warmup": W,
+            "ms_per_step": dev_ms / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "records_per_step_per_gpu": B, "agents_per_gpu": wl["agents"], "record_bytes": 512,
+                       "parallelism": f"shard{world}" if world > 1 else "single",
+                       "l2": "each step reads a fresh 512 MiB batch (> 126 MB L2); no explicit flush",
+                       "k1_variant": args.variant},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k1_ingest", "kernel_ms": k_avg, "launches_timed": k_n, "algorithmic_bytes_per_record": ALG_BYTES_PER_RECORD,
+                         "peak_source": peak_src},
+            "e2e": {"value": world * B / (e_ms * 1e-3), "unit": "requests/s", "h2d_bytes_per_step": B * 512, "d2h_bytes_per_step": B * 4,
+                    "steps": len(e_times), "ms_per_step": e_ms, "api": "agr_ingest (pinned host records in, verdicts out)"},
+            "gpu_launches": S * 2, "wall_ms_timed_region": wall_ms, "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

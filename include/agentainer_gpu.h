@@ -88,6 +88,7 @@ typedef struct agr_record {
 
 /* ------------------------------------------------------------------ config */
 #define AGR_CFG_PERSISTENCE   0x1u  /* features.request_persistence (config.go:70); default on */
+#define AGR_CFG_TIMING        0x4u  /* record CUDA-event pairs around the dominant K1 kernel (agr_kernel_time) */
 #define AGR_CFG_SKIP_INFLIGHT 0x2u  /* EXTENSION, off in parity mode: replay scan skips records whose forward is still in flight (fixes Q16) */
 
 typedef struct agr_config {
@@ -232,6 +233,9 @@ int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* 
 int agr_ingest_rows_async(agr_handle* h, uint64_t first_rid, uint32_t n);
 int agr_sync(agr_handle* h);
 void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run on (for CUDA-event timing) */
+/* With AGR_CFG_TIMING: device time of the dominant K1 kernel (k1_ingest) summed over the launches since the last
+ * call (at most the latest 1024), from CUDA events recorded on the launching stream.  Synchronises. */
+int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches);
 void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
 
 /* -------------------------------------------------- synthetic stream (bench) */
