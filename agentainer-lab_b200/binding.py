@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
     "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
-    "agr_stream", "agr_kernel_time", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
+    "agr_stream", "agr_kernel_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
     "agr_agent_hash", "agr_agent_shard",
 ]
 
@@ -101,6 +101,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_sync": (i32, [vp]),
         "agr_stream": (vp, [vp]),
         "agr_slab_ptr": (vp, [vp, u64]),
+        "agr_debug_read": (i32, [vp, i32, u64, u32, vp]),
         "agr_kernel_time": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "agr_synth_agent_id": (i32, [C.POINTER(AgrSynth), u32, C.c_char_p]),
         "agr_synth_fill_host": (i32, [C.POINTER(AgrSynth), u64, u32, vp]),
@@ -250,6 +251,12 @@ class Engine:
         ms, n = C.c_double(), C.c_uint64()
         _check(self.lib, self.lib.agr_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def debug_read(self, which: str, first_rid: int, n: int) -> np.ndarray:
+        sel = {"state": 0, "route": 1, "aux": 2, "cksum": 3}[which]
+        out = np.zeros(n, dtype=np.uint64 if sel == 3 else np.uint32)
+        _check(self.lib, self.lib.agr_debug_read(self.h, sel, first_rid, n, _ptr(out)))
+        return out
 
     def slab_ptr(self, rid: int) -> int:
         return self.lib.agr_slab_ptr(self.h, rid) or 0

@@ -72,6 +72,7 @@ struct agr_handle {
     uint64_t k1_launches = 0, k2_launches = 0, k3_launches = 0, k4_launches = 0;
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
+    alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
     // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
     std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
 };
@@ -181,7 +182,9 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.failed_log, c.log_entries, false));
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
-    TRY(dev_alloc(h, &d.dupfix, (size_t)1, true));
+    TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
+    if (c.k1_variant != 0 && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
+        return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags;
     // staging
     h->bounce_bytes = std::min<size_t>((size_t)c.max_batch * AGR_REC, (size_t)32 << 20);
@@ -296,7 +299,6 @@ int agr_drop_agent(agr_handle* h, const char* agent_id) {
 
 // ------------------------------------------------------------------------------------------ K1
 static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
-    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     if (h->rows_used + n > h->cfg.slab_rows) return fail(AGR_ENOSPC, "slab full");
     *first = h->rows_used;
     h->rows_used += n;
@@ -322,6 +324,7 @@ static void expand_verdicts(const uint32_t* route, uint32_t n, agr_verdict* out)
 
 static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, bool sync) {
     if (first + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     if (n == 0) return 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
@@ -332,7 +335,7 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
         const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->sm_count, h->stream, e0, e1);
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->cfg.k1_variant ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
     if (out) {
@@ -630,6 +633,24 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
     out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches;
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
+    return 0;
+}
+
+int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, void* out) {
+    if (!h || (n && !out)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (first_rid + n > h->cfg.slab_rows) return fail(AGR_EINVAL, "row range out of bounds");
+    const void* src = nullptr; size_t w = 4;
+    switch (which) {
+        case AGR_DBG_STATE: src = h->d.state + first_rid; break;
+        case AGR_DBG_ROUTE: src = h->d.route + first_rid; break;
+        case AGR_DBG_AUX: src = h->d.aux + first_rid; break;
+        case AGR_DBG_CKSUM: src = h->d.cksum + first_rid; w = 8; break;
+        default: return fail(AGR_EINVAL, "bad array selector");
+    }
+    CK(cudaMemcpyAsync(out, src, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -74,8 +74,11 @@ struct agr_k3_params {
     uint32_t* min_inq;         // TICK: lowest rid still in a pending list (low-water mark for the next scan)
 };
 
-void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, int sm_count, cudaStream_t st,
-                   cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);   // events bracket the main (dominant) kernel
+// variant 0 = LSU kernel (k1_ingest_v0); 1..4 = TMA kernel shapes (agr_k1_tma.cu), tmap = its CUtensorMap (128 B).
+// The optional events bracket the main (dominant) kernel.
+void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
+                   cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
 void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
 void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
 void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int sm_count, cudaStream_t st);

@@ -196,7 +196,9 @@ def run_ours(args, wl, rank, world, local_rank):
     for k in range(wl["agents"]):
         eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
     synth = dict(seed=2 + rank, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"], dup_permille=wl["dup_permille"], agent_nanos0=nanos0)
-    first = eng.reserve_rows((W + S) * B)
+    first = eng.reserve_rows(B)
+    for s in range(1, W + S):
+        eng.reserve_rows(B)
     for s in range(W + S):                                       # records resident in HBM before the timed region
         eng.synth_fill_rows(s * B, first + s * B, B, **synth)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))

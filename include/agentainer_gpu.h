@@ -238,6 +238,11 @@ void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run
 int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches);
 void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
 
+/* Diagnostic read-back of the per-row SoA words (tests, snapshot tooling): which = 0 state (u32), 1 route (u32),
+ * 2 aux (u32), 3 checksum (u64).  out must hold n elements of that width. */
+enum { AGR_DBG_STATE = 0, AGR_DBG_ROUTE = 1, AGR_DBG_AUX = 2, AGR_DBG_CKSUM = 3 };
+int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, void* out);
+
 /* -------------------------------------------------- synthetic stream (bench) */
 /* Counter-based generator of BASELINE.json's synthetic streams; integer-only, identical on host and device. */
 typedef struct agr_synth {

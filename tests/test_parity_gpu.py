@@ -50,6 +50,49 @@ def test_result_does_not_depend_on_batching(seed):
         assert_same(ref, run_engine(eng, ev, rng=np.random.default_rng(seed)))
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_tma_variants_match_oracle(variant):
+    """Every K1 kernel shape (LSU v0 is the default elsewhere; 1..4 are the TMA pipelines) gives identical results."""
+    for seed in (3, 8):
+        ev = random_scenario(seed, n_events=400, n_agents=5)
+        with engine(k1_variant=variant) as eng:
+            assert_same(run_oracle(ev), run_engine(eng, ev))
+    # ragged batch sizes around the 32-record tile and a batch that is not at row 0
+    recs = A.synth_fill_host(0, 5000, seed=9, n_agents=8, dup_permille=100)
+    with engine(k1_variant=0) as e0, engine(k1_variant=variant) as e1:
+        for e in (e0, e1):
+            for k in range(8):
+                e.set_agent_state(A.synth_agent_id(k), "running" if k % 3 else "stopped")
+        off = 0
+        for n in (1, 31, 32, 33, 63, 64, 65, 1000, 2049, 700):
+            chunk = np.ascontiguousarray(recs[off:off + n]); off += n
+            v0, _ = e0.ingest(chunk); v1, _ = e1.ingest(chunk)
+            assert v0.tobytes() == v1.tobytes()
+        s0, s1 = e0.stats(), e1.stats()
+        for k in ("ingested", "stored", "replay_flagged", "dedupe_hits", "forwarded", "queued", "unavailable", "dup_ids"):
+            assert s0[k] == s1[k], k
+        for k in range(8):
+            a = A.synth_agent_id(k)
+            assert e0.list(a, 0).tobytes() == e1.list(a, 0).tobytes()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_checksum_matches_numpy(variant):
+    """cksum[rid] = (sum (k+1) w_k) << 32 | sum w_k over the 128 LE words — checked through a device read-back."""
+    import ctypes as C
+    n = 777
+    recs = A.synth_fill_host(0, n, seed=4, n_agents=4)
+    w = recs.view(np.uint32).reshape(n, 128).astype(np.uint64)
+    c0 = w.sum(axis=1) & 0xFFFFFFFF
+    c1 = (w * np.arange(1, 129, dtype=np.uint64)).sum(axis=1) & 0xFFFFFFFF
+    with engine(k1_variant=variant) as eng:
+        for k in range(4):
+            eng.set_agent_state(A.synth_agent_id(k), "running")
+        eng.ingest(recs)
+        got = eng.debug_read("cksum", 0, n)
+    assert (got == ((c1 << np.uint64(32)) | c0)).all()
+
+
 def test_persistence_disabled():
     ev = [("agent", "agent-1", "running"), ("agent", "agent-2", "stopped"),
           ("req", Req("agent-1", rid_of(1), 1), ("response", 200)), ("req", Req("agent-2", rid_of(2), 2), ("response", 200))]
