@@ -76,7 +76,8 @@ struct __attribute__((aligned(32))) agr_slot {
 struct __attribute__((aligned(16))) agr_agent_key {
     unsigned long long w[4];  // 32 B id, NUL padded; all-zero = empty
     uint32_t slot;
-    uint32_t pad[3];
+    uint32_t status;          // AGR_AGENT_* or AG_STATUS_REMOVED (mirrors astatus[slot]; read together with the key)
+    uint32_t pad[2];
 };
 #define AG_STATUS_REMOVED 0xffu
 

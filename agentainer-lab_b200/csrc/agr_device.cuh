@@ -31,23 +31,6 @@ __device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
     return ((unsigned long long)hi << 32) | lo;
 }
 
-// agent id -> (slot, status).  Table is tiny (48 B per entry) and read-only inside a kernel: L1 / L2 resident.
-__device__ __forceinline__ uint32_t agent_lookup(const agr_dev& d, unsigned long long w0, unsigned long long w1,
-                                                 unsigned long long w2, unsigned long long w3) {
-    if ((w0 | w1 | w2 | w3) == 0ULL) return RT_SLOT_NONE;
-    uint32_t idx = (uint32_t)agr_hash_agent(w0, w1, w2, w3) & d.amask;
-    for (uint32_t probe = 0; probe <= d.amask; ++probe) {
-        const agr_agent_key* e = d.akeys + idx;
-        uint4 a = ldg_v4(&e->w[0]);
-        uint4 b = ldg_v4(&e->w[2]);
-        unsigned long long e0 = pack64(a.x, a.y), e1 = pack64(a.z, a.w), e2 = pack64(b.x, b.y), e3 = pack64(b.z, b.w);
-        if ((e0 | e1 | e2 | e3) == 0ULL) return RT_SLOT_NONE;
-        if (e0 == w0 && e1 == w1 && e2 == w2 && e3 == w3) return __ldg(&e->slot);
-        idx = (idx + 1) & d.amask;
-    }
-    return RT_SLOT_NONE;
-}
-
 // dedupe-index lookup: returns slot index or ~0ULL
 __device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsigned long long lo, unsigned long long hi) {
     unsigned long long idx = agr_hash_id(lo, hi) & d.table_mask;
@@ -63,44 +46,87 @@ __device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsig
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-// Decision + persistence for ONE record whose 96 B header is in registers.  Sequential semantics of
-// proxyToAgentHandler (server.go:498-541) with StoreRequest (requests.go:64-117) inlined.
+// Decision + persistence for ONE record whose 96 B header is in registers: the sequential semantics of
+// proxyToAgentHandler (server.go:498-541) with StoreRequest (requests.go:64-117) inlined, split in stages so a
+// kernel can put independent work (the record checksum) between the long-latency global operations:
+//   k1_agent_issue   -> loads of the first agent-table probe                      (GetAgent, server.go:498)
+//   k1_begin         -> resolves the agent, classifies, issues the FIRST index CAS (StoreRequest's SET)
+//   k1_finish        -> finishes probing, publishes the row id, forms verdict + state word
+// The index insert is ONE returning atomic (CAS.128 on the id) plus a fire-and-forget RED.max of ~rid.  Who owns
+// an id is therefore decided by the final value of inv_rid (lowest row wins = arrival order); a row that found its
+// id already present is provisionally a duplicate and bumps dupfix, and only then does k1_post re-check owners.
 struct k1_result { uint32_t state, route; };
+struct ag_probe { uint4 a, b, t; uint32_t idx; };
+struct k1_ctx {
+    unsigned long long id_lo, id_hi, tidx;
+    u128 old;
+    uint32_t slot, astatus;
+    bool replay, want_store, cas_issued;
+};
 
-__device__ __forceinline__ k1_result k1_decide(const agr_dev& d, uint32_t rid, uint4 h0, uint4 h1, uint4 h2, uint4 h3,
-                                               uint4 h4, uint4 h5, uint32_t* lc /*local counters*/) {
+__device__ __forceinline__ ag_probe agent_probe_load(const agr_dev& d, uint32_t idx) {
+    ag_probe p;
+    const agr_agent_key* e = d.akeys + idx;
+    p.a = ldg_v4(&e->w[0]); p.b = ldg_v4(&e->w[2]); p.t = ldg_v4(&e->slot); p.idx = idx;
+    return p;
+}
+__device__ __forceinline__ ag_probe k1_agent_issue(const agr_dev& d, const uint4& h2, const uint4& h3) {
+    return agent_probe_load(d, (uint32_t)agr_hash_agent(pack64(h2.x, h2.y), pack64(h2.z, h2.w), pack64(h3.x, h3.y), pack64(h3.z, h3.w)) & d.amask);
+}
+// resolves (slot, status) from the first probe, continuing the linear probe if needed
+__device__ __forceinline__ void agent_resolve(const agr_dev& d, ag_probe p, const uint4& h2, const uint4& h3, uint32_t& slot, uint32_t& status) {
+    slot = RT_SLOT_NONE; status = AG_STATUS_REMOVED;
+    if ((h2.x | h2.y | h2.z | h2.w | h3.x | h3.y | h3.z | h3.w) == 0u) return;
+    for (uint32_t probe = 0; probe <= d.amask; ++probe) {
+        if ((p.a.x | p.a.y | p.a.z | p.a.w | p.b.x | p.b.y | p.b.z | p.b.w) == 0u) return;          // empty: miss
+        if (p.a.x == h2.x && p.a.y == h2.y && p.a.z == h2.z && p.a.w == h2.w && p.b.x == h3.x && p.b.y == h3.y &&
+            p.b.z == h3.z && p.b.w == h3.w) { slot = p.t.x; status = p.t.y & 0xffu; return; }
+        p = agent_probe_load(d, (p.idx + 1) & d.amask);
+    }
+}
+
+__device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, const uint4& h0, const uint4& h2, const uint4& h3,
+                                         const uint4& h4, k1_ctx& c) {
+    c.id_lo = pack64(h0.x, h0.y); c.id_hi = pack64(h0.z, h0.w);
+    c.replay = (h4.z & AGR_F_REPLAY) != 0;                                                // server.go:506
+    agent_resolve(d, ap, h2, h3, c.slot, c.astatus);                                      // server.go:498
+    const bool found = c.slot != RT_SLOT_NONE && c.astatus != AG_STATUS_REMOVED;
+    c.want_store = found && (d.cfg_flags & AGR_CFG_PERSISTENCE) && !c.replay;             // server.go:508
+    c.cas_issued = c.want_store && (c.id_lo | c.id_hi) != 0ULL;
+    c.old = u128{0ULL, 0ULL};
+    c.tidx = 0;
+    if (c.cas_issued) {
+        c.tidx = agr_hash_id(c.id_lo, c.id_hi) & d.table_mask;
+        c.old = cas128(&d.table[c.tidx], u128{0ULL, 0ULL}, u128{c.id_lo, c.id_hi});
+    }
+}
+
+__device__ __forceinline__ k1_result k1_finish(const agr_dev& d, uint32_t rid, const uint4& h1, const uint4& h5, k1_ctx& c,
+                                               uint32_t* lc /*local counters*/) {
     k1_result out{0u, 0u};
-    const unsigned long long id_lo = pack64(h0.x, h0.y), id_hi = pack64(h0.z, h0.w);
-    const uint32_t flags_in = h4.z;
-    const bool replay = (flags_in & AGR_F_REPLAY) != 0;                                   // server.go:506
-    const bool persistence = (d.cfg_flags & AGR_CFG_PERSISTENCE) != 0;
-    // GetAgent (server.go:498, agent.go:372-390)
-    uint32_t slot = agent_lookup(d, pack64(h2.x, h2.y), pack64(h2.z, h2.w), pack64(h3.x, h3.y), pack64(h3.z, h3.w));
-    uint32_t astatus = AG_STATUS_REMOVED;
-    if (slot != RT_SLOT_NONE) astatus = d.astatus[slot];
     lc[C_INGESTED]++;
-    if (slot == RT_SLOT_NONE || astatus == AG_STATUS_REMOVED) {                           // server.go:499-502
+    if (c.slot == RT_SLOT_NONE || c.astatus == AG_STATUS_REMOVED) {                       // server.go:499-502
         lc[C_NOT_FOUND]++;
         out.route = RT_SLOT_NONE | (AGR_V_NOT_FOUND << RT_CODE_SHIFT);
         return out;
     }
     uint32_t vflags = 0;
     bool tracked = false;
-    if (persistence && !replay) {                                                         // server.go:508
+    if (c.want_store) {
         // StoreRequest: SET rec (the row itself, already in the slab) + index insert + RPUSH pending (INQ bit)
-        bool ok = (id_lo | id_hi) != 0ULL;
+        bool ok = c.cas_issued;
         if (ok) {
-            unsigned long long idx = agr_hash_id(id_lo, id_hi) & d.table_mask;
-            const u128 zero{0ULL, 0ULL}, key{id_lo, id_hi};
             for (;;) {
-                u128 old = cas128(&d.table[idx], zero, key);
-                if ((old.lo | old.hi) == 0ULL || (old.lo == id_lo && old.hi == id_hi)) break;
-                idx = (idx + 1) & d.table_mask;
+                if ((c.old.lo | c.old.hi) == 0ULL) break;                                 // claimed an empty slot
+                if (c.old.lo == c.id_lo && c.old.hi == c.id_hi) {                         // id already present
+                    ok = false;
+                    atomicAdd(d.dupfix, 1u);
+                    break;
+                }
+                c.tidx = (c.tidx + 1) & d.table_mask;
+                c.old = cas128(&d.table[c.tidx], u128{0ULL, 0ULL}, u128{c.id_lo, c.id_hi});
             }
-            const uint32_t inv = ~rid;
-            uint32_t prev = atomicMax(&d.table[idx].inv_rid, inv);
-            if (prev > inv) ok = false;                       // an EARLIER row owns this id: duplicate
-            else if (prev != 0u) atomicAdd(d.dupfix, 1u);     // a LATER row raced ahead: k1_post demotes it
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[c.tidx].inv_rid), "r"(~rid) : "memory");
         }
         if (ok) {
             uint32_t maxr = (h5.y >> 16) & 0xffu;
@@ -113,21 +139,21 @@ __device__ __forceinline__ k1_result k1_decide(const agr_dev& d, uint32_t rid, u
             vflags |= AGR_VF_DUP_ID;                                                      // server.go:511-514 path
             lc[C_DUP_IDS]++;
         }
-    } else if (replay) {                                                                  // server.go:519-522
+    } else if (c.replay) {                                                                // server.go:519-522
         vflags |= AGR_VF_REPLAY;
         lc[C_REPLAY]++;
-        tracked = (pack64(h1.x, h1.y) | pack64(h1.z, h1.w)) != 0ULL;
+        tracked = (h1.x | h1.y | h1.z | h1.w) != 0u;
         if (tracked) vflags |= AGR_VF_TRACKED;
     }
     uint32_t code;
-    if (astatus != AGR_AGENT_RUNNING) {                                                   // server.go:525
-        if (persistence && tracked) { code = AGR_V_QUEUED; lc[C_QUEUED]++; }              // :526-536
+    if (c.astatus != AGR_AGENT_RUNNING) {                                                 // server.go:525
+        if ((d.cfg_flags & AGR_CFG_PERSISTENCE) && tracked) { code = AGR_V_QUEUED; lc[C_QUEUED]++; }   // :526-536
         else { code = AGR_V_UNAVAILABLE; lc[C_UNAVAILABLE]++; }                           // :539-540
     } else {
         code = AGR_V_FORWARD; lc[C_FORWARDED]++;                                          // :546-572
         if (out.state) out.state |= ST_INFLIGHT;
     }
-    out.route = slot | (code << RT_CODE_SHIFT) | (vflags << RT_FLAG_SHIFT);
+    out.route = c.slot | (code << RT_CODE_SHIFT) | (vflags << RT_FLAG_SHIFT);
     return out;
 }
 

@@ -49,6 +49,7 @@ struct agr_handle {
     std::vector<std::string> agent_names;
     std::vector<uint8_t> agent_status;
     std::vector<agr_agent_key> akeys_host;
+    std::vector<uint32_t> akey_index;          // slot -> index of its entry in the open-addressing key table
     // staging
     uint8_t* bounce[2] = {nullptr, nullptr};   // pinned, for pageable caller buffers
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
@@ -174,9 +175,6 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     d.amask = acap - 1;
     h->akeys_host.assign(acap, agr_agent_key{});
     TRY(dev_alloc(h, &d.astatus, c.max_agents, true));
-    TRY(dev_alloc(h, &d.pend_cnt, c.max_agents, true));
-    TRY(dev_alloc(h, &d.comp_cnt, c.max_agents, true));
-    TRY(dev_alloc(h, &d.fail_cnt, c.max_agents, true));
     TRY(dev_alloc(h, &d.ctr, (size_t)C_NCTR, true));
     TRY(dev_alloc(h, &d.completed_log, c.log_entries, false));
     TRY(dev_alloc(h, &d.failed_log, c.log_entries, false));
@@ -239,6 +237,16 @@ static int agent_find(agr_handle* h, const char* id) {
     return it == h->slot_of.end() ? -1 : (int)it->second;
 }
 
+// status lives in two places on the device: astatus[slot] (K3 reads it by slot) and the key entry (K1 reads it with
+// the key in one access); both copies are stream-ordered before the next kernel
+static int push_agent_status(agr_handle* h, uint32_t slot, uint8_t status) {
+    const uint32_t idx = h->akey_index[slot];
+    h->akeys_host[idx].status = status;
+    CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(&h->d.akeys[idx].status, &h->akeys_host[idx].status, 4, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
 int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
     if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
     size_t len = strnlen(agent_id, AGR_AGENT_ID_BYTES);
@@ -256,16 +264,18 @@ int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
         agr_agent_key key{};
         pack_agent_id(agent_id, key.w);
         key.slot = (uint32_t)slot;
+        key.status = status;
         uint32_t idx = (uint32_t)agr_hash_agent(key.w[0], key.w[1], key.w[2], key.w[3]) & h->d.amask;
         while (h->akeys_host[idx].w[0] | h->akeys_host[idx].w[1] | h->akeys_host[idx].w[2] | h->akeys_host[idx].w[3])
             idx = (idx + 1) & h->d.amask;
         h->akeys_host[idx] = key;
+        h->akey_index.push_back(idx);
         // status first, then the key that makes the slot reachable; both are stream-ordered before the next kernel
         CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d.akeys + idx, &key, sizeof key, cudaMemcpyHostToDevice, h->stream));
     } else {
         h->agent_status[slot] = status;
-        CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
+        TRY(push_agent_status(h, (uint32_t)slot, status));
     }
     return slot;
 }
@@ -285,8 +295,7 @@ int agr_drop_agent(agr_handle* h, const char* agent_id) {
     int slot = agent_find(h, agent_id);
     if (slot < 0) return fail(AGR_ENOTFOUND, "agent not found");
     h->agent_status[slot] = AG_STATUS_REMOVED;
-    uint8_t st = AG_STATUS_REMOVED;
-    CK(cudaMemcpyAsync(h->d.astatus + slot, &st, 1, cudaMemcpyHostToDevice, h->stream));   // DEL agent:{id} (agent.go:344)
+    TRY(push_agent_status(h, (uint32_t)slot, AG_STATUS_REMOVED));                          // DEL agent:{id} (agent.go:344)
     unsigned long long lens[2];
     CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -101,36 +101,44 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         // header: chunks 0..5 of this lane's record
         const uint4 h0 = lds128(base + ((0u << 4) ^ sw)), h1 = lds128(base + ((1u << 4) ^ sw)), h2 = lds128(base + ((2u << 4) ^ sw));
         const uint4 h3 = lds128(base + ((3u << 4) ^ sw)), h4 = lds128(base + ((4u << 4) ^ sw)), h5 = lds128(base + ((5u << 4) ^ sw));
-        // start the dedupe-index line on its way to L2 while the checksum runs
+        // long-latency work first: agent-table probe, index-line prefetch, and the claim of the NEXT tile
+        const ag_probe ap = k1_agent_issue(d, h2, h3);
         if (valid && !(h4.z & AGR_F_REPLAY))
             prefetch_l2(&d.table[agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask]);
-        // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words)
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(tile_counter, 1u);
+        // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words), first half
         uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
+        for (int k = 0; k < 16; ++k) {
+            const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
+            c0 += v.x + v.y + v.z + v.w;
+            c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
+        }
+        // agent resolved (its loads had half a checksum to land): classify and put the index CAS in flight
+        k1_ctx cx;
+        if (valid) k1_begin(d, ap, h0, h2, h3, h4, cx);
+#pragma unroll
+        for (int k = 16; k < 32; ++k) {
             const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
             c0 += v.x + v.y + v.z + v.w;
             c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
         }
         __syncwarp();      // every lane has consumed the stage: it may be refilled
         {
-            uint32_t t = 0;
-            if (lane == 0) {
-                t = atomicAdd(tile_counter, 1u);
-                if (t < tiles) {
-                    const uint32_t dst = my_smem + s * TILE_BYTES;
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async refill
-                    mbar_expect_tx(bar, TILE_BYTES);
+            if (lane == 0 && next_tile < tiles) {
+                const uint32_t dst = my_smem + s * TILE_BYTES;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async refill
+                mbar_expect_tx(bar, TILE_BYTES);
 #pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + t * TILE_RECS));
-                }
+                for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + next_tile * TILE_RECS));
             }
-            t = __shfl_sync(FULL, t, 0);
+            next_tile = __shfl_sync(FULL, next_tile, 0);
 #pragma unroll
-            for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = t;
+            for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
         }
         if (valid) {
-            const k1_result r = k1_decide(d, rid, h0, h1, h2, h3, h4, h5, lc);
+            const k1_result r = k1_finish(d, rid, h1, h5, cx, lc);
             d.state[rid] = r.state;
             d.route[rid] = r.route;
             d.cksum[rid] = agr_cksum_pack(c0, c1);

@@ -34,7 +34,11 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
             h0 = ldg_nc_v4(rec);      h1 = ldg_nc_v4(rec + 16); h2 = ldg_nc_v4(rec + 32);
             h3 = ldg_nc_v4(rec + 48); h4 = ldg_nc_v4(rec + 64); h5 = ldg_nc_v4(rec + 80);
         }
-        // ---- pass 2 first (pure streaming, independent of the decision chain): payload checksum
+        // ---- long-latency chain first: agent probe -> classification -> first index CAS in flight
+        const ag_probe ap = k1_agent_issue(d, h2, h3);
+        k1_ctx cx;
+        if (valid) k1_begin(d, ap, h0, h2, h3, h4, cx);
+        // ---- pass 2 (pure streaming, independent of the decision chain): payload checksum
         uint32_t c0 = 0, c1 = 0;
         {
             const uint32_t hw[24] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w,
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
         }
         // ---- pass 1: decision chain, one record per lane
         if (valid) {
-            k1_result r = k1_decide(d, rid, h0, h1, h2, h3, h4, h5, lc);
+            k1_result r = k1_finish(d, rid, h1, h5, cx, lc);
             d.state[rid] = r.state;
             d.route[rid] = r.route;
             d.cksum[rid] = agr_cksum_pack(c0, c1);
@@ -72,71 +76,85 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
     k1_flush_counters(d, lc, s_ctr);
 }
 
-// Post pass over the batch's route words (4 B / record, the records themselves are not re-read except for the
-// rare rows that need it):
-//   (a) LLEN pending bookkeeping: one atomicAdd per (warp, agent) via match_any;
-//   (b) replay-flagged rows: resolve replay_of in the dedupe index -> KNOWN (dedupe hit).  Done here, after ALL
-//       inserts of the batch, and compared by rid so that "known" means "stored EARLIER in arrival order";
-//   (c) only if an in-batch duplicate-id race was seen (dupfix != 0, never with minted UUIDs): every stored row
-//       re-checks that it still owns its id; the later row is demoted to a persistence failure.
+// Post pass over the batch's route words (4 B / record; the records themselves are re-read only for the rare rows
+// that need it).  Runs after ALL inserts of the batch:
+//   (a) replay-flagged rows: resolve replay_of in the dedupe index -> KNOWN (dedupe hit), compared by row id so that
+//       "known" means "stored EARLIER in arrival order";
+//   (b) only if some row found its id already present (dupfix != 0 — never with minted UUIDs): owner of an id = the
+//       LOWEST row that carried it (final inv_rid).  A provisionally stored row that is not the owner is demoted to a
+//       persistence failure (server.go:511-514); a provisional duplicate that IS the owner (it lost the CAS race to a
+//       later row of the same batch) is promoted to stored.
 __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t dupfix = __ldcg(d.dupfix);
+    const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    const bool valid = i < n;
-    const uint32_t rid = first_rid + i;
-    uint32_t r = valid ? d.route[rid] : 0u;
-    uint32_t vf = rt_flags(r);
-    const uint32_t dupfix = *reinterpret_cast<volatile uint32_t*>(d.dupfix);
-    uint32_t hits = 0, demoted = 0, q2u = 0;
-    if (valid && (vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
-        uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + AGR_OFF_REPLAY_OF);
-        unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
-        if (idx != ~0ULL) {
-            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
-            uint32_t orid = ~inv;
-            if (inv != 0u && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
-                r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
-                d.route[rid] = r;
-                hits = 1;
+    uint32_t hits = 0;
+    int stored_delta = 0, q_delta = 0;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
+        const uint32_t i = i0 + threadIdx.x;
+        if (i >= n) continue;
+        const uint32_t rid = first_rid + i;
+        uint32_t r = d.route[rid];
+        uint32_t vf = rt_flags(r);
+        if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
+            uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + AGR_OFF_REPLAY_OF);
+            unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
+            if (idx != ~0ULL) {
+                const uint32_t inv = __ldcg(&d.table[idx].inv_rid);
+                const uint32_t orid = ~inv;
+                if (inv != 0u && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
+                    r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
+                    d.route[rid] = r;
+                    hits++;
+                }
             }
         }
-    }
-    if (dupfix != 0u && valid && (vf & AGR_VF_STORED)) {
-        uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
-        unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
-        uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : ~(__ldcg(&d.table[idx].inv_rid));
-        if (owner != rid) {   // demote: behave like a failed StoreRequest (server.go:511-514)
-            demoted = 1;
+        if (dupfix != 0u && (vf & (AGR_VF_STORED | AGR_VF_DUP_ID))) {
+            const uint4 h0 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+            const unsigned long long idx = table_find(d, pack64(h0.x, h0.y), pack64(h0.z, h0.w));
+            const uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : ~__ldcg(&d.table[idx].inv_rid);
             uint32_t code = rt_code(r);
-            if (code == AGR_V_QUEUED) { code = AGR_V_UNAVAILABLE; q2u = 1; }
-            vf = (vf & ~(AGR_VF_STORED | AGR_VF_TRACKED)) | AGR_VF_DUP_ID;
-            r = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
-            d.route[rid] = r;
-            d.state[rid] = 0;
+            const bool running = d.astatus[rt_slot(r)] == AGR_AGENT_RUNNING;
+            if ((vf & AGR_VF_STORED) && owner != rid) {                 // demote
+                if (code == AGR_V_QUEUED) { code = AGR_V_UNAVAILABLE; q_delta--; }
+                vf = (vf & ~(AGR_VF_STORED | AGR_VF_TRACKED)) | AGR_VF_DUP_ID;
+                d.state[rid] = 0;
+                stored_delta--;
+            } else if ((vf & AGR_VF_DUP_ID) && owner == rid && (pack64(h0.x, h0.y) | pack64(h0.z, h0.w)) != 0ULL) {   // promote
+                const uint4 h5 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + 80);
+                uint32_t maxr = (h5.y >> 16) & 0xffu;
+                if (maxr == 0) maxr = 3;
+                uint32_t st = AGR_ST_PENDING | ST_INQ | ST_STORED | (maxr << ST_MAX_SHIFT);
+                if (running) st |= ST_INFLIGHT;
+                else if (code == AGR_V_UNAVAILABLE) { code = AGR_V_QUEUED; q_delta++; }
+                vf = (vf & ~AGR_VF_DUP_ID) | AGR_VF_STORED | AGR_VF_TRACKED;
+                d.state[rid] = st;
+                stored_delta++;
+            }
+            d.route[rid] = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
         }
     }
-    // (a) pending-list length per agent
-    const bool stored = valid && (vf & AGR_VF_STORED);
-    const uint32_t key = stored ? rt_slot(r) : (0x80000000u | (uint32_t)lane);
-    const uint32_t peers = __match_any_sync(FULL, key);
-    if (stored && lane == (__ffs(peers) - 1)) atomicAdd(&d.pend_cnt[rt_slot(r)], (uint32_t)__popc(peers));
     hits = __reduce_add_sync(FULL, hits);
-    demoted = __reduce_add_sync(FULL, demoted);
-    q2u = __reduce_add_sync(FULL, q2u);
+    stored_delta = __reduce_add_sync(FULL, stored_delta);
+    q_delta = __reduce_add_sync(FULL, q_delta);
     if (lane == 0) {
         if (hits) atomicAdd(&d.ctr[C_DEDUPE_HITS], (unsigned long long)hits);
-        if (demoted) {
-            atomicAdd(&d.ctr[C_DUP_IDS], (unsigned long long)demoted);
-            atomicAdd(&d.ctr[C_STORED], (unsigned long long)(0ULL - demoted));
-            if (q2u) {
-                atomicAdd(&d.ctr[C_QUEUED], (unsigned long long)(0ULL - q2u));
-                atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)q2u);
-            }
+        if (stored_delta) {
+            atomicAdd(&d.ctr[C_STORED], (unsigned long long)(long long)stored_delta);
+            atomicAdd(&d.ctr[C_DUP_IDS], (unsigned long long)(long long)(-stored_delta));
+        }
+        if (q_delta) {
+            atomicAdd(&d.ctr[C_QUEUED], (unsigned long long)(long long)q_delta);
+            atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)(long long)(-q_delta));
         }
     }
 }
 
 int agr_k1_launches_per_batch(uint32_t) { return 2; }
+static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
+    uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 8u;
+    return b < cap ? b : cap;
+}
 
 cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t* counter,
                               int sm_count, cudaStream_t st);
@@ -149,7 +167,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (variant != 0 && tmap != nullptr) {
         agr_launch_k1_tma(variant, tmap, d, first_rid, n, d.dupfix + 1, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
-        k1_post<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
+        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
         return;
     }
     constexpr int WARPS = 8;
@@ -159,7 +177,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (blocks > maxb) blocks = maxb;
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
-    k1_post<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
+    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -222,56 +240,66 @@ void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, c
 
 __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t rid = s.hrid[j];
-    if (rid == AGR_RID_NONE) return;
-    const uint32_t idx = s.hidx[j];
-    if (__ldcg(&d.table[idx].head) != j + 1u) return;   // not the chain root
-    uint32_t st = d.state[rid], aux = d.aux[rid];
-    const uint32_t slot = rt_slot(d.route[rid]);
-    uint32_t dpend = 0, ncomp = 0, nfail = 0, nerr = 0;
-    long long last = -1;
-    for (;;) {
-        // next op of this row in ascending op index
-        uint32_t best = 0xffffffffu;
-        for (uint32_t cur = j + 1u; cur != 0u; cur = s.nxt[cur - 1u]) {
-            uint32_t o = cur - 1u;
-            if ((long long)o > last && o < best) best = o;
+    const int lane = threadIdx.x & 31;
+    uint32_t ncomp = 0, nfail = 0, nerr = 0;
+    uint32_t rid = AGR_RID_NONE, idx = 0;
+    bool root = false;
+    if (j < n) {
+        rid = s.hrid[j];
+        if (rid != AGR_RID_NONE) {
+            idx = s.hidx[j];
+            root = (__ldcg(&d.table[idx].head) == j + 1u);          // chain root = last op linked onto this row
         }
-        if (best == 0xffffffffu) break;
-        last = best;
-        const agr_dop op = s.ops[best];
-        uint8_t eff = 0;
-        if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
-            st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED;  // :166
-            aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
-            if (st & ST_INQ) { st &= ~ST_INQ; dpend++; }                     // :180-184 LREM pending 1 id
-            eff |= 1; ncomp++;                                               // :187-191 RPUSH completed
-        } else if (op.kind == AGR_OUT_ERROR) {                               // MarkRequestFailed, requests.go:243-262
-            uint32_t retry = st_retry(st);
-            if (retry < 255u) retry++;                                       // :245
-            st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT)) | (retry << ST_RETRY_SHIFT);
-            aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
-            nerr++;
-            if (retry < st_max(st)) {
-                st |= AGR_ST_PENDING;                                        // :248-249, keeps queue position (Q11)
-            } else {
-                st |= AGR_ST_FAILED;                                         // :243
-                eff |= 2; nfail++;                                           // :252-255 RPUSH failed
-                if (st & ST_INQ) { st &= ~ST_INQ; dpend++; }                 // :258-261 LREM pending 1 id
-            }
-        } else {                                                             // dial error, extension bookkeeping only
-            st &= ~ST_INFLIGHT;
-        }
-        s.eff[best] = eff;
     }
-    d.state[rid] = st;
-    d.aux[rid] = aux;
-    d.table[idx].head = 0;
-    if (dpend) atomicSub(&d.pend_cnt[slot], dpend);
-    if (ncomp) { atomicAdd(&d.comp_cnt[slot], ncomp); atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)ncomp); }
-    if (nerr) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)nerr);
-    if (nfail) { atomicAdd(&d.fail_cnt[slot], nfail); atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)nfail); }
+    if (root) {
+        uint32_t st = d.state[rid], aux = d.aux[rid];
+        long long last = -1;
+        for (;;) {
+            // next op of this row in ascending op index
+            uint32_t best = 0xffffffffu;
+            for (uint32_t cur = j + 1u; cur != 0u; cur = s.nxt[cur - 1u]) {
+                uint32_t o = cur - 1u;
+                if ((long long)o > last && o < best) best = o;
+            }
+            if (best == 0xffffffffu) break;
+            last = best;
+            const agr_dop op = s.ops[best];
+            uint8_t eff = 0;
+            if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
+                st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED;  // :166
+                aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
+                st &= ~ST_INQ;                                                   // :180-184 LREM pending 1 id
+                eff |= 1; ncomp++;                                               // :187-191 RPUSH completed
+            } else if (op.kind == AGR_OUT_ERROR) {                               // MarkRequestFailed, requests.go:243-262
+                uint32_t retry = st_retry(st);
+                if (retry < 255u) retry++;                                       // :245
+                st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT)) | (retry << ST_RETRY_SHIFT);
+                aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
+                nerr++;
+                if (retry < st_max(st)) {
+                    st |= AGR_ST_PENDING;                                        // :248-249, keeps queue position (Q11)
+                } else {
+                    st |= AGR_ST_FAILED;                                         // :243
+                    eff |= 2; nfail++;                                           // :252-255 RPUSH failed
+                    st &= ~ST_INQ;                                               // :258-261 LREM pending 1 id
+                }
+            } else {                                                             // dial error, extension bookkeeping only
+                st &= ~ST_INFLIGHT;
+            }
+            s.eff[best] = eff;
+        }
+        d.state[rid] = st;
+        d.aux[rid] = aux;
+        d.table[idx].head = 0;
+    }
+    ncomp = __reduce_add_sync(FULL, ncomp);
+    nerr = __reduce_add_sync(FULL, nerr);
+    nfail = __reduce_add_sync(FULL, nfail);
+    if (lane == 0) {
+        if (ncomp) atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)ncomp);
+        if (nerr) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)nerr);
+        if (nfail) atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)nfail);
+    }
 }
 
 // one CTA: per-chunk counts of push flags -> exclusive bases; reserves log space
@@ -508,13 +536,11 @@ __global__ void __launch_bounds__(256) k_drop_logs(const agr_dev d, const uint32
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < d.log_len[0]) { uint32_t rid = d.completed_log[k]; if (rid != AGR_RID_NONE && rt_slot(d.route[rid]) == slot) d.completed_log[k] = AGR_RID_NONE; }
     if (k < d.log_len[1]) { uint32_t rid = d.failed_log[k]; if (rid != AGR_RID_NONE && rt_slot(d.route[rid]) == slot) d.failed_log[k] = AGR_RID_NONE; }
-    if (k == 0) { d.pend_cnt[slot] = 0; d.comp_cnt[slot] = 0; d.fail_cnt[slot] = 0; }
 }
 void agr_launch_drop_agent(const agr_dev& d, uint32_t slot, unsigned long long rows, unsigned long long max_log_len,
                            cudaStream_t st) {
     if (rows) k_drop_rows<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, slot, rows);
-    if (max_log_len == 0) max_log_len = 1;   // k == 0 also resets the per-agent list lengths
-    k_drop_logs<<<(unsigned)((max_log_len + 255) / 256), 256, 0, st>>>(d, slot);
+    if (max_log_len) k_drop_logs<<<(unsigned)((max_log_len + 255) / 256), 256, 0, st>>>(d, slot);
 }
 
 // ------------------------------------------------------------------------------------------------ synthetic stream

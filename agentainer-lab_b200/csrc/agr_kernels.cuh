@@ -23,9 +23,6 @@ struct agr_dev {
     agr_agent_key* akeys;
     uint32_t amask;
     uint8_t* astatus;          // [max_agents]
-    uint32_t* pend_cnt;        // per agent: LLEN pending / completed / failed
-    uint32_t* comp_cnt;
-    uint32_t* fail_cnt;
     unsigned long long* ctr;   // C_NCTR
     uint32_t* completed_log;
     uint32_t* failed_log;

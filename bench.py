@@ -54,46 +54,44 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / clock-event reasons sampled through NVML every ~2 ms during the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.stop_flag, self.t, self.max_mhz = index, [], 0, False, None, None
+
+    def _run(self):
+        import pynvml as N
+        try:
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                self.reasons |= int(get_reasons(h))
+                time.sleep(0.002)
+        except Exception as e:      # no NVML: report that rather than invent numbers
+            self.error = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def mark(self):
+        """samples taken from now on belong to the timed region"""
+        self.mark_at = len(self.samples)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        hi = sorted(sm)[len(sm) // 2:]          # the upper half of the samples = the ones taken under load
-        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=2)
+        timed = self.samples[getattr(self, "mark_at", 0):] or self.samples
+        if not timed:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "error": getattr(self, "error", None)}
+        return {"sm_mhz": float(np.median(timed)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if self.reasons & k), "samples": len(timed)}
 
 
 def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16):
@@ -212,6 +210,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     t0 = time.perf_counter()
     ev0.record(stream)
     for s in range(W, W + S):
