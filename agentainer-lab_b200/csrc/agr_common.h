@@ -62,6 +62,7 @@ AGR_HD uint32_t rt_flags(uint32_t r) { return r >> RT_FLAG_SHIFT; }
 #define AUX_ERR_SHIFT 16
 
 #define AGR_RID_NONE 0xffffffffu
+#define AGR_CFGI_SPLIT_INDEX 0x10000u   // internal cfg_flags bit: K1 runs as stream kernel + k1_index kernel
 
 // ---- dedupe-index slot.  key == 0 means empty (a UUIDv4 is never all-zero); inv_rid = ~rid so that a zeroed
 // slot is "no rid yet" and atomicMax keeps the LOWEST rid (arrival order wins among duplicate ids).

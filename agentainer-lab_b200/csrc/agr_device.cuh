@@ -15,16 +15,13 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 __device__ __forceinline__ uint4 ldg_v4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-struct u128 { unsigned long long lo, hi; };
+// 128-bit compare-and-swap on a dedupe-index slot's id.  The result stays an opaque 128-bit value (no unpacking
+// at the issue point), so nothing depends on the atomic's return until the caller actually inspects it.
+typedef unsigned __int128 u128;
+__device__ __forceinline__ u128 make_u128(unsigned long long lo, unsigned long long hi) { return ((u128)hi << 64) | lo; }
 __device__ __forceinline__ u128 cas128(void* addr, u128 cmp, u128 val) {
     u128 old;
-    asm volatile("{\n\t.reg .b128 c, v, o;\n\t"
-                 "mov.b128 c, {%2, %3};\n\t"
-                 "mov.b128 v, {%4, %5};\n\t"
-                 "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\t"
-                 "mov.b128 {%0, %1}, o;\n\t}"
-                 : "=l"(old.lo), "=l"(old.hi)
-                 : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+    asm volatile("atom.relaxed.gpu.global.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(cmp), "q"(val) : "memory");
     return old;
 }
 __device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
@@ -61,7 +58,7 @@ struct k1_ctx {
     unsigned long long id_lo, id_hi, tidx;
     u128 old;
     uint32_t slot, astatus;
-    bool replay, want_store, cas_issued;
+    bool replay, want_store, cas_issued, deferred;
 };
 
 __device__ __forceinline__ ag_probe agent_probe_load(const agr_dev& d, uint32_t idx) {
@@ -92,12 +89,14 @@ __device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, c
     agent_resolve(d, ap, h2, h3, c.slot, c.astatus);                                      // server.go:498
     const bool found = c.slot != RT_SLOT_NONE && c.astatus != AG_STATUS_REMOVED;
     c.want_store = found && (d.cfg_flags & AGR_CFG_PERSISTENCE) && !c.replay;             // server.go:508
-    c.cas_issued = c.want_store && (c.id_lo | c.id_hi) != 0ULL;
-    c.old = u128{0ULL, 0ULL};
+    // split mode: the insert is done by k1_index after the stream kernel; the row is provisionally "stored"
+    c.deferred = c.want_store && (c.id_lo | c.id_hi) != 0ULL && (d.cfg_flags & AGR_CFGI_SPLIT_INDEX);
+    c.cas_issued = c.want_store && (c.id_lo | c.id_hi) != 0ULL && !c.deferred && !(d.cfg_flags & AGR_CFG_DIAG_NO_INDEX);
+    c.old = 0;
     c.tidx = 0;
     if (c.cas_issued) {
         c.tidx = agr_hash_id(c.id_lo, c.id_hi) & d.table_mask;
-        c.old = cas128(&d.table[c.tidx], u128{0ULL, 0ULL}, u128{c.id_lo, c.id_hi});
+        c.old = cas128(&d.table[c.tidx], 0, make_u128(c.id_lo, c.id_hi));
     }
 }
 
@@ -114,17 +113,18 @@ __device__ __forceinline__ k1_result k1_finish(const agr_dev& d, uint32_t rid, c
     bool tracked = false;
     if (c.want_store) {
         // StoreRequest: SET rec (the row itself, already in the slab) + index insert + RPUSH pending (INQ bit)
-        bool ok = c.cas_issued;
-        if (ok) {
+        bool ok = c.cas_issued || c.deferred;
+        if (c.cas_issued) {
+            const u128 key = make_u128(c.id_lo, c.id_hi);
             for (;;) {
-                if ((c.old.lo | c.old.hi) == 0ULL) break;                                 // claimed an empty slot
-                if (c.old.lo == c.id_lo && c.old.hi == c.id_hi) {                         // id already present
+                if (c.old == 0) break;                                                    // claimed an empty slot
+                if (c.old == key) {                                                       // id already present
                     ok = false;
-                    atomicAdd(d.dupfix, 1u);
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(d.dupfix) : "memory");
                     break;
                 }
                 c.tidx = (c.tidx + 1) & d.table_mask;
-                c.old = cas128(&d.table[c.tidx], u128{0ULL, 0ULL}, u128{c.id_lo, c.id_hi});
+                c.old = cas128(&d.table[c.tidx], 0, key);
             }
             asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[c.tidx].inv_rid), "r"(~rid) : "memory");
         }

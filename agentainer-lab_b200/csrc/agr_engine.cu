@@ -181,9 +181,10 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
     TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
-    if (c.k1_variant != 0 && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
+    if ((c.k1_variant & 0xfu) != 0 && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
-    d.cfg_flags = c.flags;
+    d.cfg_flags = c.flags & 0xffffu;
+    if (c.k1_variant & 0x10u) d.cfg_flags |= AGR_CFGI_SPLIT_INDEX;
     // staging
     h->bounce_bytes = std::min<size_t>((size_t)c.max_batch * AGR_REC, (size_t)32 << 20);
     for (int k = 0; k < 2; ++k) {
@@ -344,7 +345,7 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
         const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, h->cfg.k1_variant ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
     if (out) {

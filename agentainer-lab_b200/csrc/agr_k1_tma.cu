@@ -68,9 +68,8 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     // prologue: claim and issue STAGES tiles
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1u);
-        t = __shfl_sync(FULL, t, 0);
+        // static schedule: tile = warp's global index + k * total warps (no atomics on the refill path)
+        const uint32_t t = (blockIdx.x * WARPS + warp) + (uint32_t)s * (gridDim.x * WARPS);
         tile_of[s] = t;
         if (lane == 0 && t < tiles) {
             const uint32_t bar = my_bar + s * 8, dst = my_smem + s * TILE_BYTES;
@@ -83,6 +82,9 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     const uint32_t rowoff = (uint32_t)lane * 128u;
     const uint32_t sw = ((uint32_t)lane & 7u) << 4;
     uint32_t phase = 0;
+    // software pipeline across tiles: the index CAS of tile t is issued in the middle of tile t and consumed in the
+    // middle of tile t+1 (k1_finish), so its whole round trip hides behind a tile of checksum work
+    k1_ctx pcx; uint4 ph1 = make_uint4(0, 0, 0, 0); uint32_t ph5y = 0, prid = 0; bool pvalid = false;
     for (uint32_t it = 0;; ++it) {
         const int s = (STAGES == 1) ? 0 : (int)(it % STAGES);
         uint32_t tile;
@@ -105,45 +107,55 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         const ag_probe ap = k1_agent_issue(d, h2, h3);
         if (valid && !(h4.z & AGR_F_REPLAY))
             prefetch_l2(&d.table[agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask]);
-        uint32_t next_tile = 0;
-        if (lane == 0) next_tile = atomicAdd(tile_counter, 1u);
+        const uint32_t next_tile = tile + (uint32_t)STAGES * (gridDim.x * WARPS);
         // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words), first half
         uint32_t c0 = 0, c1 = 0;
+        const bool do_ck = !(d.cfg_flags & AGR_CFG_DIAG_NO_CKSUM);
+        if (do_ck) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
             c0 += v.x + v.y + v.z + v.w;
             c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
         }
-        // agent resolved (its loads had half a checksum to land): classify and put the index CAS in flight
-        k1_ctx cx;
-        if (valid) k1_begin(d, ap, h0, h2, h3, h4, cx);
+        }
+        // previous tile: its CAS has had a full tile to come back
+        if (pvalid) {
+            const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
+            const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
+            d.state[prid] = r.state;
+            d.route[prid] = r.route;
+        }
+        // this tile: agent resolved (its loads had half a checksum to land): classify, put the index CAS in flight.
+        // pcx is dead here (just consumed), so the CAS writes straight into the loop-carried registers.
+        if (valid) k1_begin(d, ap, h0, h2, h3, h4, pcx);
+        ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid;
+        if (do_ck) {
 #pragma unroll
         for (int k = 16; k < 32; ++k) {
             const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
             c0 += v.x + v.y + v.z + v.w;
             c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
         }
+        }
+        if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
         __syncwarp();      // every lane has consumed the stage: it may be refilled
-        {
-            if (lane == 0 && next_tile < tiles) {
-                const uint32_t dst = my_smem + s * TILE_BYTES;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async refill
-                mbar_expect_tx(bar, TILE_BYTES);
+        if (lane == 0 && next_tile < tiles) {
+            const uint32_t dst = my_smem + s * TILE_BYTES;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async refill
+            mbar_expect_tx(bar, TILE_BYTES);
 #pragma unroll
-                for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + next_tile * TILE_RECS));
-            }
-            next_tile = __shfl_sync(FULL, next_tile, 0);
+            for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + next_tile * TILE_RECS));
+        }
 #pragma unroll
-            for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
-        }
-        if (valid) {
-            const k1_result r = k1_finish(d, rid, h1, h5, cx, lc);
-            d.state[rid] = r.state;
-            d.route[rid] = r.route;
-            d.cksum[rid] = agr_cksum_pack(c0, c1);
-        }
+        for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
         if (s == STAGES - 1) phase ^= 1u;
+    }
+    if (pvalid) {
+        const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
+        const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
+        d.state[prid] = r.state;
+        d.route[prid] = r.route;
     }
     k1_flush_counters(d, lc, s_ctr);
 }

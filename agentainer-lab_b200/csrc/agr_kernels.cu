@@ -150,7 +150,53 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
     }
 }
 
-int agr_k1_launches_per_batch(uint32_t) { return 2; }
+// K1b (split mode): the dedupe-index insert of every provisionally stored row, one thread per record at full
+// occupancy — the random-access round trips are hidden by ~2 K resident threads per SM instead of by the streaming
+// warps' software pipeline.  A row whose id is already present becomes a provisional duplicate (k1_post decides).
+__global__ void __launch_bounds__(256) k1_index(const agr_dev d, const uint32_t first_rid, const uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int dups = 0, q2u = 0;
+    if (i < n) {
+        const uint32_t rid = first_rid + i;
+        uint32_t r = d.route[rid];
+        uint32_t vf = rt_flags(r);
+        if (vf & AGR_VF_STORED) {
+            const uint4 h0 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+            const u128 key = make_u128(pack64(h0.x, h0.y), pack64(h0.z, h0.w));
+            unsigned long long idx = agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask;
+            bool dup = false;
+            for (;;) {
+                const u128 old = cas128(&d.table[idx], 0, key);
+                if (old == 0) break;
+                if (old == key) { dup = true; break; }
+                idx = (idx + 1) & d.table_mask;
+            }
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(~rid) : "memory");
+            if (dup) {
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(d.dupfix) : "memory");
+                uint32_t code = rt_code(r);
+                if (code == AGR_V_QUEUED) { code = AGR_V_UNAVAILABLE; q2u = 1; }
+                vf = (vf & ~(AGR_VF_STORED | AGR_VF_TRACKED)) | AGR_VF_DUP_ID;
+                d.route[rid] = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
+                d.state[rid] = 0;
+                dups = 1;
+            }
+        }
+    }
+    dups = __reduce_add_sync(FULL, dups);
+    q2u = __reduce_add_sync(FULL, q2u);
+    if (lane == 0 && dups) {
+        atomicAdd(&d.ctr[C_STORED], (unsigned long long)(long long)(-dups));
+        atomicAdd(&d.ctr[C_DUP_IDS], (unsigned long long)dups);
+        if (q2u) {
+            atomicAdd(&d.ctr[C_QUEUED], (unsigned long long)(long long)(-q2u));
+            atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)q2u);
+        }
+    }
+}
+
+int agr_k1_launches_per_batch(uint32_t variant) { return (variant & 0x10u) ? 3 : 2; }
 static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
     uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 8u;
     return b < cap ? b : cap;
@@ -164,9 +210,10 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (n == 0) return;
     cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
-    if (variant != 0 && tmap != nullptr) {
-        agr_launch_k1_tma(variant, tmap, d, first_rid, n, d.dupfix + 1, sm_count, st);
+    if ((variant & 0xfu) != 0 && tmap != nullptr) {
+        agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, d.dupfix + 1, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
+        if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
         k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
         return;
     }
@@ -177,6 +224,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (blocks > maxb) blocks = maxb;
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
+    if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
     k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
 }
 

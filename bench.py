@@ -187,9 +187,9 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     B, W, S = wl["records"], args.warmup, args.steps
     e_steps, e_warm = min(S, args.e2e_steps), 1
-    rows = (W + S) * B + (e_warm + e_steps) * B
+    rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B)
     eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant,
-                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING)
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | args.diag_flags)
     nanos0 = 1700000000000000000 + rank * 10_000_000_000        # each rank (shard) owns its own agent ids
     for k in range(wl["agents"]):
         eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
@@ -226,6 +226,8 @@ def run_ours(args, wl, rank, world, local_rank):
     clocks = sampler.stop()
     st = eng.stats()
     assert st["ingested"] == (W + S) * B, st
+    if args.diag_flags:
+        print("WARNING: diagnostic flags set; numbers below are for attribution only", file=sys.stderr)
     # ---- e2e through the public C-ABI call with pinned host buffers (H2D + kernels + D2H verdicts timed)
     pin = eng.pinned(B)
     e_times = []
@@ -292,6 +294,8 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")
+    ap.add_argument("--rows", type=int, default=0, help="override slab rows (table size follows)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

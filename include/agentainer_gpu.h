@@ -89,6 +89,8 @@ typedef struct agr_record {
 /* ------------------------------------------------------------------ config */
 #define AGR_CFG_PERSISTENCE   0x1u  /* features.request_persistence (config.go:70); default on */
 #define AGR_CFG_TIMING        0x4u  /* record CUDA-event pairs around the dominant K1 kernel (agr_kernel_time) */
+#define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
+#define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */
 #define AGR_CFG_SKIP_INFLIGHT 0x2u  /* EXTENSION, off in parity mode: replay scan skips records whose forward is still in flight (fixes Q16) */
 
 typedef struct agr_config {

@@ -50,7 +50,7 @@ def test_result_does_not_depend_on_batching(seed):
         assert_same(ref, run_engine(eng, ev, rng=np.random.default_rng(seed)))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 0x10, 0x11, 0x14])
 def test_tma_variants_match_oracle(variant):
     """Every K1 kernel shape (LSU v0 is the default elsewhere; 1..4 are the TMA pipelines) gives identical results."""
     for seed in (3, 8):
@@ -121,7 +121,8 @@ def test_duplicate_fresh_id_is_a_persistence_failure():
         assert s["dup_ids"] == 4 and s["stored"] == 3
 
 
-def test_large_batch_duplicate_race_is_resolved_by_arrival_order():
+@pytest.mark.parametrize("variant", [0, 1, 0x14])
+def test_large_batch_duplicate_race_is_resolved_by_arrival_order(variant):
     """Many duplicates inside one big batch: whichever thread wins the insert race, the LOWEST row keeps the id."""
     n = 1 << 14
     reqs = A.synth_fill_host(0, n, seed=21, n_agents=8)
@@ -129,13 +130,18 @@ def test_large_batch_duplicate_race_is_resolved_by_arrival_order():
     dup_src = np.arange(0, n // 2, 7)
     dup_dst = n - 1 - np.arange(len(dup_src))
     reqs2["request_id"][dup_dst] = reqs2["request_id"][dup_src]
-    with engine(slab_rows=1 << 16) as eng:
+    with engine(slab_rows=1 << 16, k1_variant=variant) as eng:
         for k in range(8):
-            eng.set_agent_state(A.synth_agent_id(k), "running")
+            eng.set_agent_state(A.synth_agent_id(k), "running" if k % 2 else "stopped")
         v, _ = eng.ingest(reqs2)
         dup = (v["flags"] & K.AGR_VF_DUP_ID) != 0
         assert set(np.nonzero(dup)[0]) == set(dup_dst)
         assert ((v["flags"][~dup] & K.AGR_VF_STORED) != 0).all()
+        assert set(v["code"][dup]) <= {K.AGR_V_FORWARD, K.AGR_V_UNAVAILABLE}
+        assert set(v["code"][~dup]) <= {K.AGR_V_FORWARD, K.AGR_V_QUEUED}
+        s = eng.stats()
+        assert s["stored"] == n - len(dup_dst) and s["dup_ids"] == len(dup_dst)
+        assert s["queued"] == int((v["code"] == K.AGR_V_QUEUED).sum()) and s["unavailable"] == int((v["code"] == K.AGR_V_UNAVAILABLE).sum())
 
 
 def test_known_flag_means_stored_earlier():
