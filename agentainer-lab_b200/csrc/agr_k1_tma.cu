@@ -108,38 +108,18 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         if (valid && !(h4.z & AGR_F_REPLAY))
             prefetch_l2(&d.table[agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask]);
         const uint32_t next_tile = tile + (uint32_t)STAGES * (gridDim.x * WARPS);
-        // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words), first half
+        // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words).  Only shared
+        // memory is touched between the wait and the refill, so the stage is held for the checksum alone.
         uint32_t c0 = 0, c1 = 0;
-        const bool do_ck = !(d.cfg_flags & AGR_CFG_DIAG_NO_CKSUM);
-        if (do_ck) {
+        if (!(d.cfg_flags & AGR_CFG_DIAG_NO_CKSUM)) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
-            c0 += v.x + v.y + v.z + v.w;
-            c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
+            for (int k = 0; k < 32; ++k) {
+                const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
+                c0 += v.x + v.y + v.z + v.w;
+                c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
+            }
         }
-        }
-        // previous tile: its CAS has had a full tile to come back
-        if (pvalid) {
-            const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
-            const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
-            d.state[prid] = r.state;
-            d.route[prid] = r.route;
-        }
-        // this tile: agent resolved (its loads had half a checksum to land): classify, put the index CAS in flight.
-        // pcx is dead here (just consumed), so the CAS writes straight into the loop-carried registers.
-        if (valid) k1_begin(d, ap, h0, h2, h3, h4, pcx);
-        ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid;
-        if (do_ck) {
-#pragma unroll
-        for (int k = 16; k < 32; ++k) {
-            const uint4 v = lds128(base + (uint32_t)(k >> 3) * 4096u + ((((uint32_t)k & 7u) << 4) ^ sw));
-            c0 += v.x + v.y + v.z + v.w;
-            c1 += (uint32_t)(4 * k + 1) * v.x + (uint32_t)(4 * k + 2) * v.y + (uint32_t)(4 * k + 3) * v.z + (uint32_t)(4 * k + 4) * v.w;
-        }
-        }
-        if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
-        __syncwarp();      // every lane has consumed the stage: it may be refilled
+        __syncwarp();      // every lane has consumed the stage: refill it right away
         if (lane == 0 && next_tile < tiles) {
             const uint32_t dst = my_smem + s * TILE_BYTES;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async refill
@@ -149,6 +129,18 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         }
 #pragma unroll
         for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
+        if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
+        // previous tile: its CAS has had a full tile to come back
+        if (pvalid) {
+            const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
+            const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
+            d.state[prid] = r.state;
+            d.route[prid] = r.route;
+        }
+        // this tile: agent loads have landed by now; classify and put the index CAS in flight.  pcx is dead here
+        // (just consumed), so the CAS writes straight into the loop-carried registers.
+        if (valid) k1_begin(d, ap, h0, h2, h3, h4, pcx);
+        ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid;
         if (s == STAGES - 1) phase ^= 1u;
     }
     if (pvalid) {
