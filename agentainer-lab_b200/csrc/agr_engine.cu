@@ -149,6 +149,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
     if (c.max_batch == 0) c.max_batch = 1u << 20;
     if (c.log_entries == 0) c.log_entries = c.slab_rows * 2;
+    if ((c.k1_variant & 0xfu) == 0) c.k1_variant |= 4u;      // default K1 shape: TMA, 14 warps x 1 stage, fused index
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(AGR_ENODEV, "no CUDA device visible (this library has no CPU fallback)"); }
     int dev = c.device;
@@ -181,7 +182,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
     TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
-    if ((c.k1_variant & 0xfu) != 0 && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
+    if ((c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags & 0xffffu;
     if (c.k1_variant & 0x10u) d.cfg_flags |= AGR_CFGI_SPLIT_INDEX;
@@ -345,7 +346,7 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
         const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
     if (out) {

@@ -210,7 +210,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (n == 0) return;
     cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
-    if ((variant & 0xfu) != 0 && tmap != nullptr) {
+    if ((variant & 0xfu) != AGR_K1_LSU && tmap != nullptr) {
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, d.dupfix + 1, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);

@@ -71,7 +71,10 @@ struct agr_k3_params {
     uint32_t* min_inq;         // TICK: lowest rid still in a pending list (low-water mark for the next scan)
 };
 
-// variant 0 = LSU kernel (k1_ingest_v0); 1..4 = TMA kernel shapes (agr_k1_tma.cu), tmap = its CUtensorMap (128 B).
+// K1 variants (agr_config.k1_variant low nibble): 0 = default (= 4); 1..4 = TMA kernel shapes (agr_k1_tma.cu:
+// 1 = 7 warps x 2 stages, 2 = 6 x 2, 3 = 4 x 3, 4 = 14 x 1), tmap = the slab's CUtensorMap (128 B);
+// 5 = LSU kernel (k1_ingest_v0, no TMA).  Bit 0x10 = split mode: stream kernel + k1_index kernel.
+#define AGR_K1_LSU 5u
 // The optional events bracket the main (dominant) kernel.
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);

@@ -101,7 +101,8 @@ typedef struct agr_config {
     uint32_t max_agents;     /* agent-table capacity; 0 = 4096 */
     uint32_t max_batch;      /* largest n accepted by one agr_ingest / agr_complete; 0 = 1<<20 */
     uint64_t log_entries;    /* capacity of the completed and failed logs; 0 = 2*slab_rows */
-    uint32_t k1_variant;     /* 0 = default kernel; others select alternates for A/B measurement */
+    uint32_t k1_variant;     /* 0 = default K1 kernel (TMA, 14 warps x 1 stage, fused index); 1..4 TMA shapes, 5 = LSU kernel,
+                                | 0x10 = split stream / index kernels — alternates kept for A/B measurement */
     uint32_t reserved;
 } agr_config;
 
