@@ -4,7 +4,7 @@ this Python package is only the thin ctypes mirror used by tests and bench.py, p
 
 There is no CPU fallback: importing works anywhere (so the ABI can be checked without a GPU), but creating an
 Engine without an sm_100 device raises."""
-from .build import build_native, lib_path          # noqa: F401
+from .build import build_native, build_host, lib_path   # noqa: F401
 from .binding import (                              # noqa: F401
     Engine, AgrError, load_library, record_dtype, outcome_dtype, verdict_dtype, dispatch_dtype,
     synth_fill_host, synth_agent_id, agent_hash, agent_shard, ABI_SYMBOLS,

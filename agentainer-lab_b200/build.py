@@ -43,3 +43,24 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     return lib_path()
+
+
+HOST = os.path.join(_HERE, "host")
+
+
+def build_host(force: bool = False) -> str:
+    """Compile the C++ mirror of requests.Manager / ReplayWorker and its threaded driver (host/test_host)."""
+    out = os.path.join(HOST, "test_host")
+    srcs = [os.path.join(HOST, f) for f in ("requests.cpp", "test_host.cpp")]
+    deps = srcs + [os.path.join(HOST, "requests.hpp"), lib_path()]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
+        return out
+    gxx = shutil.which("g++")
+    if not gxx:
+        raise RuntimeError("g++ not found")
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(_HERE, "..", "include")] + srcs + [
+        "-o", out, "-L" + LIBDIR, "-lagentainer_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return out

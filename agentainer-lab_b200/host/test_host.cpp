@@ -1,0 +1,92 @@
+// test_host.cpp — drives the C++ mirror of requests.Manager / ReplayWorker exactly as the Go server would:
+// KAT-A, KAT-B, KAT-C through the mirrored method names, then 8 threads calling Decide/StoreResponse concurrently
+// (one goroutine per HTTP request in the reference).  Exit code 0 == all checks passed.  Needs a B200.
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "requests.hpp"
+using namespace agentainer::requests;
+
+#define CHECK(c) do { if (!(c)) { printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+static std::vector<std::string> list_ids(agr_handle* h, const char* agent, int which) {
+    uint8_t ids[4096][16]; uint32_t n = 0;
+    if (agr_list(h, agent, which, ids, 4096, &n) < 0) return {};
+    std::vector<std::string> out;
+    for (uint32_t i = 0; i < n; ++i) out.push_back(FormatUUID(ids[i]));
+    return out;
+}
+
+int main() {
+    agr_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = 0; cfg.slab_rows = 1 << 16; cfg.max_agents = 64; cfg.max_batch = 4096;
+    agr_handle* h = nullptr;
+    if (agr_create(&cfg, &h) < 0) { printf("agr_create: %s\n", agr_last_error()); return 2; }
+    Manager mgr(h);
+    const char* A = "agent-1700000000000000001";
+    HttpRequest post; post.Method = "POST"; post.Path = std::string("/agent/") + A + "/chat";
+    post.Header["Content-Type"] = "application/json"; post.Body = {'{', '}'};
+
+    // KAT-A: running agent, 200 OK
+    CHECK(agr_set_agent_state(h, A, AGR_AGENT_RUNNING) == 0);
+    Verdict v; CHECK(mgr.Decide(A, post, &v).empty());
+    CHECK(v.Code == AGR_V_FORWARD && v.Stored && !v.RequestID.empty());
+    Response ok; ok.StatusCode = 200;
+    CHECK(mgr.StoreResponse(A, v.RequestID, ok).empty());
+    CHECK(list_ids(h, A, AGR_LIST_PENDING).empty());
+    CHECK(list_ids(h, A, AGR_LIST_COMPLETED) == std::vector<std::string>{v.RequestID});
+    CHECK(!mgr.StoreResponse(A, "00000000-0000-4000-8000-000000000001", ok).empty());   // "failed to get request"
+
+    // KAT-B / KAT-C: stopped agent queues three, start + one tick replays FIFO, completed holds every id twice (Q7)
+    const char* B = "agent-1700000000000000002";
+    CHECK(agr_set_agent_state(h, B, AGR_AGENT_STOPPED) == 1);
+    std::vector<std::string> ids;
+    for (int i = 0; i < 3; ++i) {
+        HttpRequest r = post; r.Path = std::string("/agent/") + B + "/chat"; r.Body.push_back((uint8_t)('0' + i));
+        CHECK(mgr.Decide(B, r, &v).empty());
+        CHECK(v.Code == AGR_V_QUEUED && v.HTTPStatus == 202);
+        ids.push_back(v.RequestID);
+    }
+    std::vector<Request> pend; CHECK(mgr.GetPendingRequests(B, &pend).empty());
+    CHECK(pend.size() == 3 && pend[0].ID == ids[0] && pend[2].ID == ids[2] && pend[1].Body.back() == '1');
+    CHECK(pend[0].Path == std::string("/agent/") + B + "/chat" && pend[0].Headers.at("Content-Type") == "application/json");
+    CHECK(agr_set_agent_state(h, B, AGR_AGENT_RUNNING) == 1);
+    std::vector<std::string> seen;
+    ReplayWorker worker(&mgr, [&](const std::string& agent, const Request& req) {
+        seen.push_back(req.ID);
+        HttpRequest rr; rr.Method = req.Method; rr.Path = req.Path; rr.Header = req.Headers; rr.Body = req.Body;
+        rr.Header["X-Agentainer-Request-ID"] = req.ID; rr.Header["X-Agentainer-Replay"] = "true";   // replay_worker.go:147-148
+        Verdict pv; mgr.Decide(agent, rr, &pv);                              // loops back through the proxy
+        if (pv.Code != AGR_V_FORWARD) return pv.HTTPStatus;
+        Response r200; r200.StatusCode = 200;
+        mgr.StoreResponse(agent, pv.RequestID, r200);                        // interceptTransport (server.go:588-594)
+        return 200;
+    });
+    CHECK(worker.ProcessAgents() == 3);
+    CHECK(seen == ids);
+    CHECK(list_ids(h, B, AGR_LIST_PENDING).empty());
+    CHECK((list_ids(h, B, AGR_LIST_COMPLETED) == std::vector<std::string>{ids[0], ids[0], ids[1], ids[1], ids[2], ids[2]}));
+
+    // concurrency: 8 threads x 500 requests against a running agent, each completed by its own thread
+    const char* C = "agent-1700000000000000003";
+    CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 2);
+    std::vector<std::thread> ths; std::atomic<int> bad{0};
+    for (int t = 0; t < 8; ++t) ths.emplace_back([&, t] {
+        for (int i = 0; i < 500; ++i) {
+            HttpRequest r = post; r.Path = std::string("/agent/") + C + "/chat";
+            Verdict tv; Response r200; r200.StatusCode = 200;
+            if (!mgr.Decide(C, r, &tv).empty() || tv.Code != AGR_V_FORWARD) { bad++; continue; }
+            if (!mgr.StoreResponse(C, tv.RequestID, r200).empty()) bad++;
+        }
+        (void)t;
+    });
+    for (auto& th : ths) th.join();
+    CHECK(bad == 0);
+    CHECK(list_ids(h, C, AGR_LIST_PENDING).empty());
+    agr_stats st; CHECK(agr_stats_get(h, &st) == 0);
+    CHECK(st.completions == 1 + 6 + 4000 && st.completion_misses == 1);
+    agr_destroy(h);
+    printf("host mirror OK: KAT-A/B/C + 4000 concurrent requests\n");
+    return 0;
+}
