@@ -35,6 +35,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of a box: starts the DRAM fetch without occupying shared memory (latency hiding beyond the smem ring)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -45,7 +49,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int WARPS, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const uint32_t first_rid, const uint32_t n,
-              uint32_t* __restrict__ tile_counter) {
+              const uint32_t pf_dist) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[WARPS * STAGES];
     __shared__ uint32_t s_ctr[K1_NLC];
@@ -76,6 +80,14 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
             mbar_expect_tx(bar, TILE_BYTES);
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + t * TILE_RECS));
+        }
+    }
+    const uint32_t tstride = gridDim.x * WARPS;
+    // L2 prefetch window: the pf_dist tiles this warp will load after the ones already in flight
+    if (lane < 4) {
+        for (uint32_t k = 0; k < pf_dist; ++k) {
+            const uint32_t t = (blockIdx.x * WARPS + warp) + (STAGES + k) * tstride;
+            if (t < tiles) tma_prefetch_2d(&tmap, lane * 128, (int32_t)(first_rid + t * TILE_RECS));
         }
     }
     // per-lane swizzled chunk offsets inside a [32][128 B] box: row * 128 + ((c ^ (row & 7)) << 4)
@@ -127,6 +139,10 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) tma_load_2d(dst + cb * 4096, &tmap, bar, cb * 128, (int32_t)(first_rid + next_tile * TILE_RECS));
         }
+        if (pf_dist && lane < 4) {
+            const uint32_t t = next_tile + pf_dist * tstride;
+            if (t < tiles) tma_prefetch_2d(&tmap, lane * 128, (int32_t)(first_rid + t * TILE_RECS));
+        }
 #pragma unroll
         for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
         if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
@@ -176,7 +192,7 @@ int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128
 }
 
 template <int WARPS, int STAGES>
-static cudaError_t launch_tma(const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t* counter, int sm_count,
+static cudaError_t launch_tma(const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t pf_dist, int sm_count,
                               cudaStream_t st) {
     const size_t smem = (size_t)WARPS * STAGES * TILE_BYTES + 1024;
     static bool attr_done = false;
@@ -189,17 +205,17 @@ static cudaError_t launch_tma(const void* map, const agr_dev& d, uint32_t first_
     uint32_t blocks = (uint32_t)sm_count;
     const uint32_t need = (tiles + WARPS - 1) / WARPS;
     if (blocks > need) blocks = need;
-    k1_ingest_tma<WARPS, STAGES><<<blocks, WARPS * 32, smem, st>>>(*(const CUtensorMap*)map, d, first_rid, n, counter);
+    k1_ingest_tma<WARPS, STAGES><<<blocks, WARPS * 32, smem, st>>>(*(const CUtensorMap*)map, d, first_rid, n, pf_dist);
     return cudaGetLastError();
 }
 
 // variant 1 (default TMA): 7 warps x 2 stages; 2: 6 x 2; 3: 4 x 3; 4: 14 x 1 (all: one persistent CTA per SM)
-cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t* counter,
+cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t pf_dist,
                               int sm_count, cudaStream_t st) {
     switch (variant) {
-        case 2: return launch_tma<6, 2>(map, d, first_rid, n, counter, sm_count, st);
-        case 3: return launch_tma<4, 3>(map, d, first_rid, n, counter, sm_count, st);
-        case 4: return launch_tma<14, 1>(map, d, first_rid, n, counter, sm_count, st);
-        default: return launch_tma<7, 2>(map, d, first_rid, n, counter, sm_count, st);
+        case 2: return launch_tma<6, 2>(map, d, first_rid, n, pf_dist, sm_count, st);
+        case 3: return launch_tma<4, 3>(map, d, first_rid, n, pf_dist, sm_count, st);
+        case 4: return launch_tma<14, 1>(map, d, first_rid, n, pf_dist, sm_count, st);
+        default: return launch_tma<7, 2>(map, d, first_rid, n, pf_dist, sm_count, st);
     }
 }

@@ -202,7 +202,7 @@ static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
     return b < cap ? b : cap;
 }
 
-cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t* counter,
+cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t pf_dist,
                               int sm_count, cudaStream_t st);
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
@@ -211,7 +211,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
     if ((variant & 0xfu) != AGR_K1_LSU && tmap != nullptr) {
-        agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, d.dupfix + 1, sm_count, st);
+        agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
         k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
