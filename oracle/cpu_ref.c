@@ -36,21 +36,34 @@ enum { T_STRING = 1, T_LIST = 2 };
 typedef struct { char id[37]; } lid;           /* uuid text */
 typedef struct {
     char* key; uint32_t klen; uint64_t hash; int type;
-    char* val; uint32_t vlen;                  /* T_STRING */
+    char* val; uint32_t vlen, vcap;            /* T_STRING (val lives in the arena: never freed, reused in place) */
     lid* items; uint32_t n, cap;               /* T_LIST */
 } kent;
-typedef struct { kent* e; uint64_t cap, used, tomb; } keyspace;
+/* bump arena per keyspace: one Redis instance = one allocator, so shards on different threads never contend */
+typedef struct achunk { struct achunk* next; size_t used, cap; } achunk;
+typedef struct { kent* e; uint64_t cap, used, tomb; achunk* arena; } keyspace;
+static char* arena_alloc(keyspace* k, size_t n) {
+    n = (n + 15) & ~(size_t)15;
+    if (!k->arena || k->arena->used + n > k->arena->cap) {
+        size_t cap = n > ((size_t)8 << 20) ? n : ((size_t)8 << 20);
+        achunk* c = (achunk*)malloc(sizeof(achunk) + cap);
+        c->next = k->arena; c->used = 0; c->cap = cap; k->arena = c;
+    }
+    char* p = (char*)(k->arena + 1) + k->arena->used;
+    k->arena->used += n;
+    return p;
+}
 
 static uint64_t fnv(const char* s, uint32_t n) { uint64_t h = 0xcbf29ce484222325ULL; for (uint32_t i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 0x100000001b3ULL; } return h; }
-static void ks_init(keyspace* k, uint64_t cap) { k->cap = cap; k->used = k->tomb = 0; k->e = (kent*)calloc(cap, sizeof(kent)); }
+static void ks_init(keyspace* k, uint64_t cap) { k->cap = cap; k->used = k->tomb = 0; k->arena = NULL; k->e = (kent*)calloc(cap, sizeof(kent)); }
 static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create);
 static void ks_grow(keyspace* k) {
-    keyspace n; ks_init(&n, k->cap * 2);
+    keyspace n; ks_init(&n, k->cap * 2); n.arena = k->arena;
     for (uint64_t i = 0; i < k->cap; ++i) if (k->e[i].key && k->e[i].type) {
         uint64_t j = k->e[i].hash & (n.cap - 1);
         while (n.e[j].key) j = (j + 1) & (n.cap - 1);
         n.e[j] = k->e[i]; n.used++;
-    } else if (k->e[i].key) free(k->e[i].key);
+    }
     free(k->e); *k = n;
 }
 static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create) {
@@ -61,9 +74,9 @@ static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create) {
         kent* e = &k->e[j];
         if (!e->key) {
             if (!create) return NULL;
-            if (firsttomb) { e = firsttomb; free(e->key); k->tomb--; }
-            e->key = (char*)malloc(klen + 1); memcpy(e->key, key, klen); e->key[klen] = 0;
-            e->klen = klen; e->hash = h; e->type = 0; e->val = NULL; e->vlen = 0; e->items = NULL; e->n = e->cap = 0;
+            if (firsttomb) { e = firsttomb; k->tomb--; }
+            e->key = arena_alloc(k, klen + 1); memcpy(e->key, key, klen); e->key[klen] = 0;
+            e->klen = klen; e->hash = h; e->type = 0; e->val = NULL; e->vlen = e->vcap = 0; e->items = NULL; e->n = e->cap = 0;
             k->used++;
             return e;
         }
@@ -74,20 +87,22 @@ static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create) {
 }
 static void ks_del_entry(keyspace* k, kent* e) {          /* DEL */
     if (!e || !e->type) return;
-    free(e->val); free(e->items); e->val = NULL; e->items = NULL; e->n = e->cap = 0; e->vlen = 0;
+    free(e->items); e->val = NULL; e->items = NULL; e->n = e->cap = 0; e->vlen = e->vcap = 0;
     e->type = 0; k->used--; k->tomb++;
 }
 static void r_set(keyspace* k, const char* key, uint32_t klen, const char* v, uint32_t vlen) {   /* SET key val EX 24h */
     kent* e = ks_find(k, key, klen, 1);
-    if (e->type == T_LIST) { free(e->items); e->items = NULL; }
-    if (e->type == 0 && e->val == NULL) { /* fresh or tombstone reuse */ }
-    char* nv = (char*)malloc(vlen + 1); memcpy(nv, v, vlen); nv[vlen] = 0;
-    free(e->val); e->val = nv; e->vlen = vlen; e->type = T_STRING;
+    if (e->type == T_LIST) { free(e->items); e->items = NULL; e->val = NULL; e->vcap = 0; }
+    if (e->val == NULL || vlen + 1 > e->vcap) {              /* room for the response that StoreResponse adds later */
+        e->vcap = vlen + vlen / 2 + 128;
+        e->val = arena_alloc(k, e->vcap);
+    }
+    memcpy(e->val, v, vlen); e->val[vlen] = 0; e->vlen = vlen; e->type = T_STRING;
 }
 static kent* r_get(keyspace* k, const char* key, uint32_t klen) { kent* e = ks_find(k, key, klen, 0); return (e && e->type == T_STRING) ? e : NULL; }
 static void r_rpush(keyspace* k, const char* key, uint32_t klen, const char* id) {
     kent* e = ks_find(k, key, klen, 1);
-    if (e->type != T_LIST) { free(e->val); e->val = NULL; e->type = T_LIST; e->n = 0; }
+    if (e->type != T_LIST) { e->val = NULL; e->vcap = 0; e->type = T_LIST; e->n = 0; }
     if (e->n == e->cap) { e->cap = e->cap ? e->cap * 2 : 8; e->items = (lid*)realloc(e->items, e->cap * sizeof(lid)); }
     memcpy(e->items[e->n].id, id, 36); e->items[e->n].id[36] = 0; e->n++;
 }
@@ -277,7 +292,8 @@ cref* cref_create(uint32_t flags) {
 }
 void cref_destroy(cref* c) {
     if (!c) return;
-    for (uint64_t i = 0; i < c->ks.cap; ++i) { free(c->ks.e[i].key); free(c->ks.e[i].val); free(c->ks.e[i].items); }
+    for (uint64_t i = 0; i < c->ks.cap; ++i) free(c->ks.e[i].items);
+    for (achunk* a = c->ks.arena; a;) { achunk* nx = a->next; free(a); a = nx; }
     free(c->ks.e); free(c->scratch.p); free(c->agents); free(c);
 }
 static const char* agent_status_name(uint8_t s) { static const char* n[] = {"created", "running", "stopped", "paused", "failed"}; return s < 5 ? n[s] : "unknown"; }
