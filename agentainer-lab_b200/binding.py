@@ -220,10 +220,14 @@ class Engine:
         return _check(self.lib, self.lib.agr_agent_slot(self.h, agent_id.encode()))
 
     # ---- K1
-    def ingest(self, recs: np.ndarray, want_verdicts: bool = True) -> Tuple[Optional[np.ndarray], int]:
+    def ingest(self, recs: np.ndarray, want_verdicts: bool = True, out: Optional[np.ndarray] = None) -> Tuple[Optional[np.ndarray], int]:
         assert recs.dtype == record_dtype and recs.flags["C_CONTIGUOUS"]
         n = len(recs)
-        out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
+        if out is not None:
+            assert out.dtype == verdict_dtype and len(out) >= n
+            want_verdicts = True
+        else:
+            out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
         first = C.c_uint64()
         _check(self.lib, self.lib.agr_ingest(self.h, _ptr(recs), n, _ptr(out) if want_verdicts else None, C.byref(first)))
         return out, first.value

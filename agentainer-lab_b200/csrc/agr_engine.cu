@@ -41,6 +41,10 @@ struct agr_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;        // H2D of chunk k+1 overlaps K1 of chunk k (agr_ingest pipeline)
+    std::vector<cudaEvent_t> chunk_ev;
+    agr_verdict* d_verdicts = nullptr;         // [max_batch], written by k1_post
+    agr_verdict* h_verdicts = nullptr;         // pinned [max_batch]
     agr_dev d{};
     uint64_t rows_used = 0;
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
@@ -54,8 +58,6 @@ struct agr_handle {
     uint8_t* bounce[2] = {nullptr, nullptr};   // pinned, for pageable caller buffers
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
-    uint32_t* h_state = nullptr;               // pinned [max_batch]
-    uint32_t* h_route = nullptr;
     agr_dop* h_ops = nullptr;                  // pinned [max_batch]
     int32_t* h_results = nullptr;              // pinned [max_batch]
     agr_k2_scratch k2{};
@@ -163,6 +165,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     h->sm_count = prop.multiProcessorCount;
     h->cfg = c;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     agr_dev& d = h->d;
     TRY(dev_alloc(h, &d.slab, (size_t)c.slab_rows * AGR_REC, false));
     TRY(dev_alloc(h, &d.state, c.slab_rows, true));
@@ -192,8 +195,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
         TRY(host_alloc(h, &h->bounce[k], h->bounce_bytes));
         CK(cudaEventCreateWithFlags(&h->bounce_ev[k], cudaEventDisableTiming));
     }
-    TRY(host_alloc(h, &h->h_state, c.max_batch));
-    TRY(host_alloc(h, &h->h_route, c.max_batch));
+    TRY(host_alloc(h, &h->h_verdicts, c.max_batch));
+    TRY(dev_alloc(h, &h->d_verdicts, c.max_batch, false));
     TRY(host_alloc(h, &h->h_ops, c.max_batch));
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
@@ -229,6 +232,8 @@ void agr_destroy(agr_handle* h) {
     for (void* p : h->host_allocs) cudaFreeHost(p);
     for (int k = 0; k < 2; ++k) if (h->bounce_ev[k]) cudaEventDestroy(h->bounce_ev[k]);
     for (auto e : h->tev) cudaEventDestroy(e);
+    for (auto e : h->chunk_ev) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -316,27 +321,7 @@ static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
     return 0;
 }
 
-static void expand_verdicts(const uint32_t* route, uint32_t n, agr_verdict* out) {
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t r = route[i];
-        agr_verdict v;
-        v.code = (uint8_t)rt_code(r);
-        v.flags = (uint8_t)rt_flags(r);
-        v.agent_slot = rt_slot(r);
-        switch (v.code) {
-            case AGR_V_QUEUED: v.http_status = 202; break;
-            case AGR_V_UNAVAILABLE: v.http_status = 503; break;
-            case AGR_V_NOT_FOUND: v.http_status = 404; break;
-            default: v.http_status = 0; break;
-        }
-        out[i] = v;
-    }
-}
-
-static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, bool sync) {
-    if (first + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
-    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
-    if (n == 0) return 0;
+static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
         if (h->tev.empty()) {
@@ -346,13 +331,22 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
         const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr, h->sm_count, h->stream, e0, e1);
+    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr,
+                  h->sm_count, h->stream, e0, e1, d_out);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
+    return 0;
+}
+
+static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, bool sync) {
+    if (first + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    if (n == 0) return 0;
+    TRY(launch_k1_locked(h, first, n, out ? h->d_verdicts : nullptr));
     if (out) {
-        CK(cudaMemcpyAsync(h->h_route, h->d.route + first, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        expand_verdicts(h->h_route, n, out);
+        memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
     } else if (sync) {
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -385,41 +379,66 @@ int agr_sync(agr_handle* h) {
 void* agr_stream(agr_handle* h) { return h ? (void*)h->stream : nullptr; }
 void* agr_slab_ptr(agr_handle* h, uint64_t rid) { return (h && rid < h->cfg.slab_rows) ? (void*)(h->d.slab + rid * AGR_REC) : nullptr; }
 
-// host -> slab rows.  Pinned (or registered) caller memory is DMA'd in place; pageable memory goes through two
-// pinned bounce buffers so that the CPU copy of chunk k+1 overlaps the DMA of chunk k.
-static int upload_rows(agr_handle* h, const agr_record* recs, uint64_t first, uint32_t n) {
-    uint8_t* dst = h->d.slab + first * AGR_REC;
-    const size_t bytes = (size_t)n * AGR_REC;
+// host -> slab rows -> K1 -> verdicts, pipelined in chunks: the H2D copy of chunk k+1 (copy stream) overlaps K1 and the
+// verdict D2H of chunk k (compute stream).  Chunks are consecutive sub-batches in arrival order, so the result is
+// identical to one big batch (tests/test_parity_gpu.py::test_result_does_not_depend_on_batching).
+// Pinned (or registered) caller memory is DMA'd in place; pageable memory goes through two pinned bounce buffers.
+#define AGR_INGEST_CHUNK (1u << 17)   // 128 Ki records = 64 MiB per H2D chunk
+static bool is_pinned(const void* p) {
     cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, recs) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
-    else cudaGetLastError();
-    if (pinned) {
-        CK(cudaMemcpyAsync(dst, recs, bytes, cudaMemcpyHostToDevice, h->stream));
-        return 0;
-    }
-    size_t off = 0; int k = 0;
-    while (off < bytes) {
-        size_t chunk = std::min(h->bounce_bytes, bytes - off);
-        CK(cudaEventSynchronize(h->bounce_ev[k]));
-        memcpy(h->bounce[k], (const uint8_t*)recs + off, chunk);
-        CK(cudaMemcpyAsync(dst + off, h->bounce[k], chunk, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaEventRecord(h->bounce_ev[k], h->stream));
-        off += chunk; k ^= 1;
-    }
-    return 0;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return false;
 }
 
 int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     uint64_t first = 0;
     TRY(reserve_rows_locked(h, n, &first));
     if (first_rid) *first_rid = first;
     if (n == 0) return 0;
-    TRY(upload_rows(h, recs, first, n));
-    return ingest_rows_locked(h, first, n, out, true);
+    const bool src_pinned = is_pinned(recs);
+    const bool out_pinned = out && is_pinned(out);
+    const uint32_t nchunks = (n + AGR_INGEST_CHUNK - 1) / AGR_INGEST_CHUNK;
+    while (h->chunk_ev.size() < nchunks + 1) {
+        cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunk_ev.push_back(e);
+    }
+    // the copy stream must not overwrite rows before earlier work on the compute stream is done with the slab
+    CK(cudaEventRecord(h->chunk_ev[nchunks], h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[nchunks], 0));
+    int bk = 0;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t off = c * AGR_INGEST_CHUNK, cn = std::min(AGR_INGEST_CHUNK, n - off);
+        uint8_t* dst = h->d.slab + (first + off) * AGR_REC;
+        const uint8_t* src = (const uint8_t*)(recs + off);
+        size_t bytes = (size_t)cn * AGR_REC;
+        if (src_pinned) {
+            CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        } else {
+            for (size_t o = 0; o < bytes;) {
+                size_t piece = std::min(h->bounce_bytes, bytes - o);
+                CK(cudaEventSynchronize(h->bounce_ev[bk]));
+                memcpy(h->bounce[bk], src + o, piece);
+                CK(cudaMemcpyAsync(dst + o, h->bounce[bk], piece, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->bounce_ev[bk], h->copy_stream));
+                o += piece; bk ^= 1;
+            }
+        }
+        CK(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
+        TRY(launch_k1_locked(h, first + off, cn, out ? h->d_verdicts + off : nullptr));
+        if (out) {
+            agr_verdict* hdst = out_pinned ? out + off : h->h_verdicts + off;
+            CK(cudaMemcpyAsync(hdst, h->d_verdicts + off, (size_t)cn * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (out && !out_pinned) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------ K2

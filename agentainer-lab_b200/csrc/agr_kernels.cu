@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 //       LOWEST row that carried it (final inv_rid).  A provisionally stored row that is not the owner is demoted to a
 //       persistence failure (server.go:511-514); a provisional duplicate that IS the owner (it lost the CAS race to a
 //       later row of the same batch) is promoted to stored.
-__global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n) {
+__global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts) {
     const uint32_t dupfix = __ldcg(d.dupfix);
     const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -131,7 +131,13 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
                 d.state[rid] = st;
                 stored_delta++;
             }
-            d.route[rid] = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
+            r = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
+            d.route[rid] = r;
+        }
+        if (verdicts) {   // agr_verdict {u8 code, u8 flags, u16 http_status, u32 agent_slot}, written for the D2H copy
+            const uint32_t code = rt_code(r);
+            const uint32_t http = code == AGR_V_QUEUED ? 202u : code == AGR_V_UNAVAILABLE ? 503u : code == AGR_V_NOT_FOUND ? 404u : 0u;
+            verdicts[i] = make_uint2(code | (rt_flags(r) << 8) | (http << 16), rt_slot(r));
         }
     }
     hits = __reduce_add_sync(FULL, hits);
@@ -206,7 +212,7 @@ cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& 
                               int sm_count, cudaStream_t st);
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
-                   cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+                   cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, void* verdicts) {
     if (n == 0) return;
     cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
@@ -214,7 +220,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
+        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
         return;
     }
     constexpr int WARPS = 8;
@@ -225,7 +231,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
     if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n);
+    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

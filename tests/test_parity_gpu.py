@@ -94,6 +94,35 @@ def test_checksum_matches_numpy(variant):
     assert (got == ((c1 << np.uint64(32)) | c0)).all()
 
 
+def test_chunked_pipelined_ingest_equals_one_launch():
+    """agr_ingest pipelines H2D chunks (128 Ki records) against K1 on a second stream: same verdicts, state and lists as
+    ONE K1 launch over the same rows, from pageable and from pinned host memory."""
+    n, na = 300_000, 32
+    recs = A.synth_fill_host(0, n, seed=31, n_agents=na, dup_permille=100)
+
+    def setup(e):
+        for k in range(na):
+            e.set_agent_state(A.synth_agent_id(k), "running" if k % 4 else "stopped")
+    with engine(slab_rows=n, max_batch=n) as e0, engine(slab_rows=n, max_batch=n) as e1, engine(slab_rows=n, max_batch=n) as e2:
+        for e in (e0, e1, e2):
+            setup(e)
+        first = e0.reserve_rows(n)
+        e0.synth_fill_rows(0, first, n, seed=31, n_agents=na, dup_permille=100)
+        v0 = e0.ingest_rows(first, n)
+        v1, _ = e1.ingest(recs)                                    # pageable -> bounce buffers, 3 chunks
+        pin, pv = e2.pinned(n), e2.pinned(n, A.verdict_dtype)
+        pin.array[:] = recs
+        v2, _ = e2.ingest(pin.array, out=pv.array)                 # pinned in, pinned out
+        assert v0.tobytes() == v1.tobytes() == v2[:n].tobytes()
+        for k in ("state", "route", "cksum"):
+            assert e0.debug_read(k, 0, n).tobytes() == e1.debug_read(k, 0, n).tobytes() == e2.debug_read(k, 0, n).tobytes()
+        s0, s1, s2 = e0.stats(), e1.stats(), e2.stats()
+        for k in ("stored", "replay_flagged", "dedupe_hits", "forwarded", "queued", "unavailable", "dup_ids"):
+            assert s0[k] == s1[k] == s2[k], k
+        del v2
+        pin.free(); pv.free()
+
+
 def test_persistence_disabled():
     ev = [("agent", "agent-1", "running"), ("agent", "agent-2", "stopped"),
           ("req", Req("agent-1", rid_of(1), 1), ("response", 200)), ("req", Req("agent-2", rid_of(2), 2), ("response", 200))]
