@@ -39,6 +39,12 @@ class AgrStats(C.Structure):
         "k1_launches", "k2_launches", "k3_launches", "k4_launches")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
 
 
+class AgrExchangeInfo(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("n_local", C.c_uint32), ("n_sent", C.c_uint32),
+                ("n_received", C.c_uint32), ("sent_to", C.c_uint32 * 32), ("received_from", C.c_uint32 * 32),
+                ("first_rid", C.c_uint64)]
+
+
 class AgrSynth(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_agents", C.c_uint32), ("zipf_milli", C.c_uint32),
                 ("dup_permille", C.c_uint32), ("reserved", C.c_uint32), ("agent_nanos0", C.c_uint64)]
@@ -51,7 +57,7 @@ ABI_SYMBOLS = [
     "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
-    "agr_agent_hash", "agr_agent_shard",
+    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
 ]
 
 _lib = None
@@ -108,6 +114,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_synth_fill_rows": (i32, [vp, C.POINTER(AgrSynth), u64, u64, u32]),
         "agr_agent_hash": (u64, [C.c_char_p]),
         "agr_agent_shard": (u32, [C.c_char_p, u32]),
+        "agr_comm_unique_id": (i32, [vp]),
+        "agr_comm_init": (i32, [vp, vp, i32, i32]),
+        "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -149,6 +158,13 @@ def synth_agent_id(k: int, *, agent_nanos0=0) -> str:
     s = _synth(0, 1, 0, 0, agent_nanos0)
     _check(lib, lib.agr_synth_agent_id(C.byref(s), k, buf))
     return buf.value.decode()
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    _check(lib, lib.agr_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
 
 
 def agent_hash(agent_id: str) -> int:
@@ -272,6 +288,19 @@ class Engine:
 
     def pinned(self, n: int, dtype=record_dtype) -> PinnedArray:
         return PinnedArray(self.lib, n, dtype)
+
+    # ---- K4 (multi-GPU exchange)
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.lib, self.lib.agr_comm_init(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+    def ingest_sharded(self, recs: np.ndarray, want_verdicts: bool = True):
+        assert recs.dtype == record_dtype and recs.flags["C_CONTIGUOUS"]
+        n = len(recs)
+        out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
+        info = AgrExchangeInfo()
+        _check(self.lib, self.lib.agr_ingest_sharded(self.h, _ptr(recs) if n else None, n, _ptr(out) if (want_verdicts and n) else None, C.byref(info)))
+        return out, info
 
     # ---- K2
     def complete(self, outs: np.ndarray, want_results: bool = True) -> Optional[np.ndarray]:

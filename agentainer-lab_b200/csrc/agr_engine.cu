@@ -5,6 +5,8 @@
 // machine sees (the reference's serialisation point is the single-threaded Redis server).
 // There is NO CPU fallback: every state transition happens in the kernels of agr_kernels.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: every NCCL symbol is resolved with dlopen/dlsym at run time
 #include <stdint.h>
 #include <string.h>
 
@@ -76,6 +78,16 @@ struct agr_handle {
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
     alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
+    // multi-GPU exchange (K4)
+    ncclComm_t comm = nullptr; int rank = 0, world = 1;
+    uint8_t* d_stage = nullptr;                // incoming batch before binning [max_batch * 512]
+    uint8_t* d_send = nullptr;                 // owner-major send buffer [max_batch * 512]
+    uint8_t* d_owner = nullptr; uint32_t* d_perm = nullptr;
+    uint32_t* d_k4matrix = nullptr; uint32_t k4_nwarps = 0;
+    uint32_t* d_k4cnt = nullptr;               // [4][32]: gtotal, goff(33 → second row pair), recv counts
+    agr_verdict* d_xverd = nullptr;            // verdicts of local + received rows [2 * max_batch]
+    agr_verdict* d_vback = nullptr;            // verdicts returned by owners, owner-major [max_batch]
+    agr_verdict* d_vout = nullptr;             // caller-order verdicts [max_batch]
     // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
     std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
 };
@@ -102,6 +114,18 @@ static int host_alloc(agr_handle* h, T** p, size_t count) {
 }
 #define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
 
+struct nccl_api {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static nccl_api g_nccl;
 static uint64_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 static void pack_agent_id(const char* id, unsigned long long w[4]) {
@@ -234,6 +258,7 @@ void agr_destroy(agr_handle* h) {
     for (auto e : h->tev) cudaEventDestroy(e);
     for (auto e : h->chunk_ev) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -663,6 +688,130 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
     out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches;
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ K4 exchange
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(AGR_ECOMM, std::string("dlopen libnccl.so.2: ") + dlerror());
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) return fail(AGR_ECOMM, "libnccl.so.2 lacks " name)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(AGR_ECOMM, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+
+int agr_comm_unique_id(uint8_t out[128]) {
+    if (!out) return fail(AGR_EINVAL, "NULL argument");
+    TRY(nccl_load());
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return 0;
+}
+
+int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
+    if (!h || !id) return fail(AGR_EINVAL, "NULL argument");
+    if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(AGR_EINVAL, "bad rank / world (1..32 shards)");
+    TRY(nccl_load());
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId uid; memcpy(uid.internal, id, 128);
+    NK(g_nccl.CommInitRank(&h->comm, world, uid, rank));
+    h->rank = rank; h->world = world;
+    const size_t mb = h->cfg.max_batch;
+    TRY(dev_alloc(h, &h->d_stage, mb * AGR_REC, false));
+    TRY(dev_alloc(h, &h->d_send, mb * AGR_REC, false));
+    TRY(dev_alloc(h, &h->d_owner, mb, false));
+    TRY(dev_alloc(h, &h->d_perm, mb, false));
+    h->k4_nwarps = (uint32_t)std::min<size_t>((size_t)h->sm_count * 32, std::max<size_t>(1, (mb + 1023) / 1024));
+    TRY(dev_alloc(h, &h->d_k4matrix, (size_t)h->k4_nwarps * 32, false));
+    TRY(dev_alloc(h, &h->d_k4cnt, (size_t)4 * 40, true));
+    TRY(dev_alloc(h, &h->d_xverd, 2 * mb, false));
+    TRY(dev_alloc(h, &h->d_vback, mb, false));
+    TRY(dev_alloc(h, &h->d_vout, mb, false));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
+    if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    const uint32_t G = (uint32_t)h->world, me = (uint32_t)h->rank;
+    cudaStream_t st = h->stream;
+    uint32_t* d_gtotal = h->d_k4cnt; uint32_t* d_goff = h->d_k4cnt + 40; uint32_t* d_rcnt = h->d_k4cnt + 80;
+    // 1. batch -> staging, owners + per-owner counts (K4 count + scan)
+    if (n) CK(cudaMemcpyAsync(h->d_stage, recs, (size_t)n * AGR_REC, cudaMemcpyHostToDevice, st));
+    agr_k4_params p{};
+    p.items = h->d_stage; p.item_bytes = AGR_REC; p.agent_off = AGR_OFF_AGENT_ID; p.n = n; p.G = G; p.me = me;
+    uint32_t per = (n + h->k4_nwarps - 1) / std::max<uint32_t>(1, h->k4_nwarps);
+    per = std::max<uint32_t>(32, (per + 31) & ~31u);
+    p.per_warp = per; p.nwarps = std::max<uint32_t>(1, (n + per - 1) / per);
+    p.matrix = h->d_k4matrix; p.gtotal = d_gtotal; p.goff = d_goff; p.owner = h->d_owner; p.perm = h->d_perm;
+    agr_launch_k4_count(p, st);
+    h->k4_launches += 2;
+    CK(cudaGetLastError());
+    // 2. counts all-to-all (one int per peer), then both count vectors to the host
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        NK(g_nccl.Send(d_gtotal + q, 1, ncclUint32, (int)q, h->comm, st));
+        NK(g_nccl.Recv(d_rcnt + q, 1, ncclUint32, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    uint32_t* hc = h->h_small;                       // [0..31] send counts, [32..63] recv counts
+    CK(cudaMemcpyAsync(hc, d_gtotal, G * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc + 32, d_rcnt, G * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t scnt[32], rcnt[32], soff[33], roff[33];
+    soff[0] = 0; roff[0] = 0;
+    for (uint32_t q = 0; q < G; ++q) { scnt[q] = hc[q]; rcnt[q] = (q == me) ? 0 : hc[32 + q]; soff[q + 1] = soff[q] + scnt[q]; roff[q + 1] = roff[q] + rcnt[q]; }
+    const uint32_t n_local = scnt[me], n_recv = roff[G], total = n_local + n_recv;
+    if (total > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more records than 2 * max_batch");
+    uint64_t first = 0;
+    TRY(reserve_rows_locked(h, total, &first));
+    // 3. stable pack: own records straight into their slab rows, peer segments into the send buffer
+    p.local_dst = h->d.slab + first * AGR_REC; p.send_dst = h->d_send;
+    if (n) { agr_launch_k4_scatter(p, st); h->k4_launches += 1; CK(cudaGetLastError()); }
+    // 4. the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
+    uint8_t* recv_base = h->d.slab + (first + n_local) * AGR_REC;
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        if (q == me) continue;
+        if (scnt[q]) NK(g_nccl.Send(h->d_send + (size_t)soff[q] * AGR_REC, (size_t)scnt[q] * AGR_REC, ncclUint8, (int)q, h->comm, st));
+        if (rcnt[q]) NK(g_nccl.Recv(recv_base + (size_t)roff[q] * AGR_REC, (size_t)rcnt[q] * AGR_REC, ncclUint8, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    // 5. K1 at the owner over local + received rows (received rows were unpacked by the receive itself)
+    if (total) TRY(launch_k1_locked(h, first, total, h->d_xverd));
+    // 6. verdicts back to where the records came from, then restored to the caller's order
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        if (q == me) continue;
+        if (rcnt[q]) NK(g_nccl.Send(h->d_xverd + n_local + roff[q], (size_t)rcnt[q] * sizeof(agr_verdict), ncclUint8, (int)q, h->comm, st));
+        if (scnt[q]) NK(g_nccl.Recv(h->d_vback + soff[q], (size_t)scnt[q] * sizeof(agr_verdict), ncclUint8, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    if (n) {
+        agr_launch_k4_unpermute(p, h->d_xverd, h->d_vback, h->d_vout, sizeof(agr_verdict), st);
+        h->k4_launches += 1;
+        CK(cudaGetLastError());
+        if (out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_vout, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (n && out) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->world = G; info->rank = me; info->n_local = n_local; info->n_sent = n - n_local; info->n_received = n_recv; info->first_rid = first;
+        for (uint32_t q = 0; q < G; ++q) { info->sent_to[q] = (q == me) ? 0 : scnt[q]; info->received_from[q] = rcnt[q]; }
+    }
     return 0;
 }
 

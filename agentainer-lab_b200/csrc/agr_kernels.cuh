@@ -76,6 +76,24 @@ struct agr_k3_params {
 // 5 = LSU kernel (k1_ingest_v0, no TMA).  Bit 0x10 = split mode: stream kernel + k1_index kernel.
 #define AGR_K1_LSU 5u
 // The optional events bracket the main (dominant) kernel.
+// K4: shard binning / stable pack for the multi-GPU exchange
+struct agr_k4_params {
+    const uint8_t* items;      // n items of item_bytes each (records: 512, outcome descriptors: 32)
+    uint32_t item_bytes, agent_off, n, G, me;
+    uint32_t nwarps, per_warp;
+    uint32_t* matrix;          // [nwarps][G]
+    uint32_t* gtotal;          // [G]   items per owner
+    uint32_t* goff;            // [G+1] owner-major offsets
+    uint8_t* owner;            // [n]
+    uint32_t* perm;            // [n]   position of item i in owner-major order
+    uint8_t* local_dst;        // where this shard's own items go (final slab rows / local op array)
+    uint8_t* send_dst;         // owner-major send buffer (peer segments are shipped as they lie)
+};
+void agr_launch_k4_count(const agr_k4_params& p, cudaStream_t st);
+void agr_launch_k4_scatter(const agr_k4_params& p, cudaStream_t st);
+void agr_launch_k4_unpermute(const agr_k4_params& p, const void* local_res, const void* remote_res, void* out, uint32_t res_bytes,
+                             cudaStream_t st);
+
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */);

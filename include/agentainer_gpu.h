@@ -241,6 +241,25 @@ void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run
 int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches);
 void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
 
+/* ------------------------------------------------------------ multi-GPU exchange (K4) */
+/* One handle per GPU; shard owner of an agent = agr_agent_shard(id, world).  Fresh traffic is steered to the owner by
+ * the host when it parses /agent/{id} (server.go:494-495) and needs no collective.  Records that reach a non-owner shard
+ * (BASELINE config 4: replay-flagged requests re-injected through another shard's proxy) are routed here:
+ * K4 bins the batch by owner and packs it (local records go straight into their slab rows), ONE grouped
+ * ncclSend/ncclRecv all-to-all over NVLink ships every peer segment to its owner, K1 runs at the owner over
+ * local + received rows, and the verdicts travel back the same way and are restored to the caller's order.
+ * NCCL is loaded at run time (libnccl.so.2); without it agr_comm_init fails with AGR_ECOMM.  Collective: every rank of
+ * the communicator must call agr_ingest_sharded the same number of times (n may be 0). */
+int agr_comm_unique_id(uint8_t out[128]);                                          /* rank 0; ship to the other ranks */
+int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world);
+typedef struct agr_exchange_info {
+    uint32_t world, rank;
+    uint32_t n_local, n_sent, n_received;      /* records of the batch owned here / shipped / received from peers */
+    uint32_t sent_to[32], received_from[32];
+    uint64_t first_rid;                        /* rows: [first_rid, +n_local) local, then received, grouped by source rank */
+} agr_exchange_info;
+int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info);
+
 /* Diagnostic read-back of the per-row SoA words (tests, snapshot tooling): which = 0 state (u32), 1 route (u32),
  * 2 aux (u32), 3 checksum (u64).  out must hold n elements of that width. */
 enum { AGR_DBG_STATE = 0, AGR_DBG_ROUTE = 1, AGR_DBG_AUX = 2, AGR_DBG_CKSUM = 3 };

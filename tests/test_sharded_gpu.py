@@ -1,0 +1,82 @@
+"""K4 + NCCL exchange on two GPUs: agr_ingest_sharded routes records that reached a non-owner shard to their owner,
+runs K1 there and brings the verdicts back in the caller's order.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    import torch.distributed as dist
+    import agentainer_lab_b200 as A
+    from agentainer_lab_b200 import constants as K
+    from oracle.cpu_ref import CRef
+    from sharding import owned_agents, make_rank_batch
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    uid = [A.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    own = owned_agents(world, 8)
+    status = lambda a: "running" if int(a[-1]) % 3 else "stopped"
+    eng = A.Engine(device=rank, slab_rows=1 << 16, max_agents=64, max_batch=1 << 14)
+    eng.comm_init(uid[0], rank, world)
+    ref = CRef()
+    for a in own[rank]:
+        eng.set_agent_state(a, status(a)); ref.set_agent_state(a, status(a))
+    ok = True
+    for step, n in enumerate([3000, 1, 0, 5000]):
+        n_here = n if (step != 1 or rank == 0) else 0          # ragged: one rank sends a single record, the other nothing
+        batch = make_rank_batch(rank, world, own, n_here, seed=11 + step, p_cross_replay=0.05, p_missteer=0.05, first_index=step * 10000) \\
+            if n_here else np.zeros(0, dtype=A.record_dtype)
+        v, info = eng.ingest_sharded(batch)
+        allb = [None] * world
+        dist.all_gather_object(allb, batch.tobytes())
+        batches = [np.frombuffer(b, dtype=A.record_dtype) for b in allb]
+        # expected at this owner: own host's records first, then the other ranks' in rank order
+        order = [rank] + [p for p in range(world) if p != rank]
+        mine = [b[np.array([A.agent_shard(a.decode(), world) == rank for a in b["agent_id"]], dtype=bool)] if len(b) else b for b in (batches[p] for p in order)]
+        mine = np.ascontiguousarray(np.concatenate(mine)) if sum(len(m) for m in mine) else np.zeros(0, dtype=A.record_dtype)
+        ev, _ = ref.ingest(mine) if len(mine) else (np.zeros(0, dtype=A.verdict_dtype), 0)
+        assert info.n_local + info.n_sent == n_here and info.n_received == len(mine) - info.n_local
+        # verdicts of MY batch, wherever each record was decided: gather every owner's expected verdict by request id
+        exp = {}
+        alle = [None] * world
+        dist.all_gather_object(alle, (mine["request_id"].tobytes(), ev["code"].tobytes(), (ev["flags"] & 0x7).tobytes()))
+        for ids, codes, flags in alle:
+            ids = np.frombuffer(ids, dtype=np.uint8).reshape(-1, 16)
+            for i, c, f in zip(ids, np.frombuffer(codes, dtype=np.uint8), np.frombuffer(flags, dtype=np.uint8)):
+                exp[bytes(i)] = (int(c), int(f))
+        for rec, got in zip(batch, v if v is not None else []):
+            e = exp[bytes(rec["request_id"])]
+            ok &= (int(got["code"]), int(got["flags"]) & 0x7) == e
+    for a in own[rank]:
+        ok &= [bytes(x).hex() for x in eng.list(a, 0)] == [bytes(x).hex() for x in ref.list(a, 0)]
+    s = eng.stats()
+    q.put((rank, bool(ok), s["k4_launches"], s["stored"]))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_ingest_two_gpus():
+    import torch.multiprocessing as mp
+    world, port = 2, 29544
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, k4, stored in res:
+        assert ok, f"rank {rank}: sharded ingest differs from the oracle"
+        assert k4 > 0 and stored > 0
