@@ -32,8 +32,9 @@ def _worker(rank, world, port, q):
     ok = True
     for step, n in enumerate([3000, 1, 0, 5000]):
         n_here = n if (step != 1 or rank == 0) else 0          # ragged: one rank sends a single record, the other nothing
-        batch = make_rank_batch(rank, world, own, n_here, seed=11 + step, p_cross_replay=0.05, p_missteer=0.05, first_index=step * 10000) \\
-            if n_here else np.zeros(0, dtype=A.record_dtype)
+        batch = np.zeros(0, dtype=A.record_dtype)
+        if n_here:
+            batch = make_rank_batch(rank, world, own, n_here, seed=11 + step, p_cross_replay=0.05, p_missteer=0.05, first_index=step * 10000)
         v, info = eng.ingest_sharded(batch)
         allb = [None] * world
         dist.all_gather_object(allb, batch.tobytes())
