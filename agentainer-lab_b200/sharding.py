@@ -1,8 +1,9 @@
-"""Shared helpers for the sharded (multi-GPU) tests: who owns an agent, and how a host builds per-rank batches."""
+"""Harness helpers for the sharded (multi-GPU) tests and bench: who owns an agent, and how a host builds the batch
+that arrives at one shard (BASELINE config 4).  Not a product surface."""
 import numpy as np
 
-import agentainer_lab_b200 as A
-from agentainer_lab_b200 import constants as K
+from . import binding as A
+from . import constants as K
 
 
 def owned_agents(world: int, per_rank: int, nanos0: int = 1700000000000000000):

@@ -201,7 +201,7 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     B, W, S = wl["records"], args.warmup, args.steps
     e_steps, e_warm = min(S, args.e2e_steps), 1
-    rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B)
+    rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B + (B if world > 1 else 0) * 2)
     eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant,
                    flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | args.diag_flags)
     nanos0 = 1700000000000000000 + rank * 10_000_000_000        # each rank (shard) owns its own agent ids
@@ -260,6 +260,36 @@ def run_ours(args, wl, rank, world, local_rank):
     del verdicts
     pin.free(); pin_v.free()
     e_ms = 1e3 * sum(e_times) / len(e_times)
+    # ---- N > 1: the exchange path (BASELINE config 4): 5 % of every rank's batch are replay-flagged records whose agent
+    # lives on another shard -> K4 bin/pack, NCCL all-to-all to the owners, K1 there, verdicts back.  Host buffers in,
+    # verdicts out, wall clock with a barrier on both sides (max over ranks by construction of the barrier).
+    exchange = None
+    if dist and not args.no_exchange:
+        from agentainer_lab_b200.sharding import owned_agents, make_rank_batch
+        uid = [A.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
+        own = owned_agents(world, 64, nanos0=1800000000000000000)
+        for a in own[rank]:
+            eng.set_agent_state(a, "running")
+        xn, x_times, sent, recvd = B // 4, [], 0, 0
+        for s in range(1 + args.x_steps):
+            xb = make_rank_batch(rank, world, own, xn, seed=50 + s, p_cross_replay=0.05, first_index=s * xn)
+            dist.barrier()
+            t = time.perf_counter()
+            xv, info = eng.ingest_sharded(xb)
+            dist.barrier()
+            dt = time.perf_counter() - t
+            if s >= 1:
+                x_times.append(dt); sent += info.n_sent; recvd += info.n_received
+        assert (xv["code"] == K.AGR_V_FORWARD).all()
+        x_ms = 1e3 * sum(x_times) / len(x_times)
+        cnt = torch.tensor([sent, recvd], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt)
+        exchange = {"value": world * xn / (x_ms * 1e-3), "unit": "requests/s", "records_per_step_per_gpu": xn,
+                    "cross_shard_fraction": float(cnt[0]) / (world * xn * len(x_times)), "ms_per_step": x_ms,
+                    "nvlink_bytes_per_step": float(cnt[0]) * (512 + 8) / len(x_times),
+                    "api": "agr_ingest_sharded (pageable host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
     if dist:
         t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -282,7 +312,7 @@ def run_ours(args, wl, rank, world, local_rank):
             "ms_per_step": dev_ms / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": wl["name"], "records_per_step_per_gpu": B, "agents_per_gpu": wl["agents"], "record_bytes": 512,
-                       "parallelism": f"shard{world}" if world > 1 else "single",
+                       "parallelism": f"shard{world} by FNV-1a64(agent_id) mod {world}; fresh traffic steered to the owner (no collective); the exchange path is measured separately under \"exchange\"" if world > 1 else "single",
                        "l2": "each step reads a fresh 512 MiB batch (> 126 MB L2); no explicit flush",
                        "k1_variant": args.variant},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -294,6 +324,8 @@ def run_ours(args, wl, rank, world, local_rank):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if exchange:
+            line["exchange"] = exchange
         print(json.dumps(line))
     eng.close()
     if dist:
@@ -310,6 +342,8 @@ def main():
     ap.add_argument("--variant", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true")
+    ap.add_argument("--x-steps", type=int, default=3)
     ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")
     ap.add_argument("--rows", type=int, default=0, help="override slab rows (table size follows)")
     args = ap.parse_args()

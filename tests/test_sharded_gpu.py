@@ -17,7 +17,7 @@ def _worker(rank, world, port, q):
     import agentainer_lab_b200 as A
     from agentainer_lab_b200 import constants as K
     from oracle.cpu_ref import CRef
-    from sharding import owned_agents, make_rank_batch
+    from agentainer_lab_b200.sharding import owned_agents, make_rank_batch
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     uid = [A.comm_unique_id() if rank == 0 else None]

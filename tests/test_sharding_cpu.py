@@ -15,7 +15,7 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
     import agentainer_lab_b200 as A
     from oracle.cpu_ref import CRef
-    from sharding import owned_agents, make_rank_batch
+    from agentainer_lab_b200.sharding import owned_agents, make_rank_batch
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     own = owned_agents(world, 6)
@@ -47,7 +47,7 @@ def _worker(rank, world, port, q):
 def test_sharded_results_equal_single_shard_oracle():
     import agentainer_lab_b200 as A
     from oracle.cpu_ref import CRef
-    from sharding import owned_agents
+    from agentainer_lab_b200.sharding import owned_agents
     world, port = 2, 29533
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
