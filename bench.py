@@ -266,30 +266,39 @@ def run_ours(args, wl, rank, world, local_rank):
     exchange = None
     if dist and not args.no_exchange:
         from agentainer_lab_b200.sharding import owned_agents, make_rank_batch
-        uid = [A.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(uid[0], rank, world)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)                     # NCCL prints its version banner to stdout on communicator creation
+        try:
+            uid = [A.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            eng.comm_init(uid[0], rank, world)
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
         own = owned_agents(world, 64, nanos0=1800000000000000000)
         for a in own[rank]:
             eng.set_agent_state(a, "running")
         xn, x_times, sent, recvd = B // 4, [], 0, 0
+        xpin = eng.pinned(xn)
         for s in range(1 + args.x_steps):
-            xb = make_rank_batch(rank, world, own, xn, seed=50 + s, p_cross_replay=0.05, first_index=s * xn)
+            xpin.array[:] = make_rank_batch(rank, world, own, xn, seed=50 + s, p_cross_replay=0.05, first_index=s * xn)
             dist.barrier()
             t = time.perf_counter()
-            xv, info = eng.ingest_sharded(xb)
+            xv, info = eng.ingest_sharded(xpin.array)
             dist.barrier()
             dt = time.perf_counter() - t
             if s >= 1:
                 x_times.append(dt); sent += info.n_sent; recvd += info.n_received
         assert (xv["code"] == K.AGR_V_FORWARD).all()
+        xpin.free()
         x_ms = 1e3 * sum(x_times) / len(x_times)
         cnt = torch.tensor([sent, recvd], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt)
         exchange = {"value": world * xn / (x_ms * 1e-3), "unit": "requests/s", "records_per_step_per_gpu": xn,
                     "cross_shard_fraction": float(cnt[0]) / (world * xn * len(x_times)), "ms_per_step": x_ms,
                     "nvlink_bytes_per_step": float(cnt[0]) * (512 + 8) / len(x_times),
-                    "api": "agr_ingest_sharded (pageable host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
+                    "api": "agr_ingest_sharded (pinned host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
     if dist:
         t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
