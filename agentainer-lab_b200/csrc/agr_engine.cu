@@ -60,7 +60,9 @@ struct agr_handle {
     uint8_t* bounce[2] = {nullptr, nullptr};   // pinned, for pageable caller buffers
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
-    agr_dop* h_ops = nullptr;                  // pinned [max_batch]
+    agr_dop* h_ops = nullptr;                  // pinned [16] (single-key lookups)
+    agr_outcome* h_outs = nullptr;             // pinned [max_batch]
+    agr_outcome* d_outs = nullptr;             // [max_batch]
     int32_t* h_results = nullptr;              // pinned [max_batch]
     agr_k2_scratch k2{};
     agr_dop* d_ops = nullptr;
@@ -126,6 +128,13 @@ struct nccl_api {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static nccl_api g_nccl;
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return false;
+}
+
 static uint64_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
 
 static void pack_agent_id(const char* id, unsigned long long w[4]) {
@@ -221,7 +230,9 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     }
     TRY(host_alloc(h, &h->h_verdicts, c.max_batch));
     TRY(dev_alloc(h, &h->d_verdicts, c.max_batch, false));
-    TRY(host_alloc(h, &h->h_ops, c.max_batch));
+    TRY(host_alloc(h, &h->h_ops, (size_t)16));
+    TRY(host_alloc(h, &h->h_outs, c.max_batch));
+    TRY(dev_alloc(h, &h->d_outs, c.max_batch, false));
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
     TRY(dev_alloc(h, &h->d_ops, c.max_batch, false));
@@ -409,13 +420,6 @@ void* agr_slab_ptr(agr_handle* h, uint64_t rid) { return (h && rid < h->cfg.slab
 // identical to one big batch (tests/test_parity_gpu.py::test_result_does_not_depend_on_batching).
 // Pinned (or registered) caller memory is DMA'd in place; pageable memory goes through two pinned bounce buffers.
 #define AGR_INGEST_CHUNK (1u << 17)   // 128 Ki records = 64 MiB per H2D chunk
-static bool is_pinned(const void* p) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    return false;
-}
-
 int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -473,28 +477,16 @@ int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* re
     CK(cudaSetDevice(h->device));
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     if (n == 0) return 0;
-    // resolve agent ids on the host (the Go shim holds the id string, not a slot)
-    std::string last_id; uint32_t last_slot = RT_SLOT_NONE;
-    for (uint32_t j = 0; j < n; ++j) {
-        const agr_outcome& o = outs[j];
-        agr_dop& op = h->h_ops[j];
-        memcpy(&op.id_lo, o.request_id, 8);
-        memcpy(&op.id_hi, o.request_id + 8, 8);
-        size_t len = strnlen(o.agent_id, AGR_AGENT_ID_BYTES);
-        if (len != last_id.size() || memcmp(o.agent_id, last_id.data(), len) != 0) {
-            last_id.assign(o.agent_id, len);
-            auto it = h->slot_of.find(last_id);
-            last_slot = (it == h->slot_of.end()) ? RT_SLOT_NONE : it->second;
-        }
-        op.slot = last_slot;
-        op.http = o.http_status;
-        op.kind = o.kind;
-        op.pad = 0;
-        op.seq = o.seq;
+    // outcomes go to the device as they are; k2_prepare resolves the agent ids in the device agent table
+    if (is_pinned(outs)) {
+        CK(cudaMemcpyAsync(h->d_outs, outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        memcpy(h->h_outs, outs, (size_t)n * sizeof(agr_outcome));
+        CK(cudaMemcpyAsync(h->d_outs, h->h_outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
     }
-    CK(cudaMemcpyAsync(h->d_ops, h->h_ops, (size_t)n * sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, n, h->stream);
     agr_launch_k2(h->d, h->k2, n, h->stream);
-    h->k2_launches += 5;
+    h->k2_launches += 6;
     CK(cudaGetLastError());
     if (results) {
         CK(cudaMemcpyAsync(h->h_results, h->k2.results, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));

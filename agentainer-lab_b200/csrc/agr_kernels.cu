@@ -240,6 +240,26 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
 // rooted in the index slot; k2_apply lets the chain root replay that row's outcomes in ascending op index on a
 // private copy of the state word (so Q24's lost updates cannot happen); k2_offsets + k2_append push the
 // completed / failed list entries in op order (RPUSH order == call order).
+// agr_outcome (64 B, caller's form: request id + agent id string) -> agr_dop (32 B: id + agent slot).  The agent id is
+// resolved in the DEVICE agent table (same probe as K1), so agr_complete has no per-outcome host work.
+__global__ void __launch_bounds__(256) k2_prepare(const agr_dev d, const uint8_t* __restrict__ outs, agr_dop* __restrict__ ops, const uint32_t n) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint8_t* o = outs + (size_t)j * 64;
+    const uint4 id = ldg_nc_v4(o), a0 = ldg_nc_v4(o + 16), a1 = ldg_nc_v4(o + 32), t = ldg_nc_v4(o + 48);
+    uint32_t slot, status;
+    agent_resolve(d, k1_agent_issue(d, a0, a1), a0, a1, slot, status);
+    agr_dop op;
+    op.id_lo = pack64(id.x, id.y); op.id_hi = pack64(id.z, id.w);
+    op.slot = slot;                              // RT_SLOT_NONE for an unknown agent: the key cannot exist
+    op.kind = (uint8_t)(t.x & 0xffu); op.pad = 0; op.http = (uint16_t)(t.x >> 16);
+    op.seq = pack64(t.z, t.w);
+    ops[j] = op;
+}
+void agr_launch_k2_prepare(const agr_dev& d, const void* outs, agr_dop* ops, uint32_t n, cudaStream_t st) {
+    if (n) k2_prepare<<<(n + 255u) / 256u, 256, 0, st>>>(d, (const uint8_t*)outs, ops, n);
+}
+
 __global__ void __launch_bounds__(256) k2_link(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;

@@ -98,6 +98,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */);
 int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
+void agr_launch_k2_prepare(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, agr_dop* ops, uint32_t n, cudaStream_t st);
 void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
 void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
 void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int sm_count, cudaStream_t st);

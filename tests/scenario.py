@@ -344,3 +344,27 @@ def random_scenario(seed: int, n_events: int = 300, n_agents: int = 5, p_replay:
                 events.append(("req", r, backend))
     events.append(("tick", {}, None))
     return events
+
+
+def synth_to_req(r) -> Req:
+    """A synthetic-stream record (agr_synth) as a scenario request (byte-identical when packed again)."""
+    rep = bool(r["flags"] & 1)
+    o = int(r["path_len"]) + int(r["hdr_len"])
+    return Req(r["agent_id"].decode(), bytes(r["request_id"]), int(r["seq"]), replay=rep, replay_of=bytes(r["replay_of"]),
+               body=bytes(r["payload"][o:o + int(r["body_len"])]),
+               headers={"Content-Type": "application/json", "User-Agent": "agr-synth/1"})
+
+
+def config1_events(n=10_000, na=16, seed=1, dup_permille=50):
+    """BASELINE config 1: 10 k synthetic 512 B POST /agent/<id>/chat records, 16 agent ids; half the agents are stopped for
+    the first half of the stream, then started; one tick (dedupe + replay order)."""
+    import agentainer_lab_b200 as A
+    recs = A.synth_fill_host(0, n, seed=seed, n_agents=na, dup_permille=dup_permille)
+    agents = [A.synth_agent_id(k) for k in range(na)]
+    ev = [("agent", a, "stopped" if k % 2 else "running") for k, a in enumerate(agents)]
+    for i in range(n):
+        if i == n // 2:
+            ev += [("agent", a, "running") for a in agents]
+        ev.append(("req", synth_to_req(recs[i]), ("response", 200)))
+    ev.append(("tick", {}, None))
+    return ev, recs

@@ -48,26 +48,12 @@ def test_json_round_trip_preserves_the_record():
 def test_config1_stream_c_port_equals_python_oracle():
     """BASELINE config 1: 10 k synthetic 512 B POST /agent/<id>/chat records, 16 agent ids, half the agents stopped for
     the first 5 000 records then started, one tick: dedupe + replay order.  C port == Python oracle."""
-    n, na = 10_000, 16
-    recs = A.synth_fill_host(0, n, seed=1, n_agents=na, dup_permille=50)
-    agents = [A.synth_agent_id(k) for k in range(na)]
-    ev = [("agent", a, "stopped" if k % 2 else "running") for k, a in enumerate(agents)]
-
-    def to_req(r):
-        rep = bool(r["flags"] & 1)
-        body = bytes(r["payload"][r["path_len"] + r["hdr_len"]: r["path_len"] + r["hdr_len"] + r["body_len"]])
-        return Req(r["agent_id"].decode(), bytes(r["request_id"]), int(r["seq"]), replay=rep,
-                   replay_of=bytes(r["replay_of"]), body=body,
-                   headers={"Content-Type": "application/json", "User-Agent": "agr-synth/1"})
-    for i in range(n):
-        if i == n // 2:
-            ev += [("agent", a, "running") for a in agents]
-        ev.append(("req", to_req(recs[i]), ("response", 200)))
-    ev.append(("tick", {}, None))
+    from scenario import config1_events, synth_to_req
+    ev, recs = config1_events()
     ref = run_oracle(ev)
     assert sum(len(t) for t in ref.ticks) > 1000
     with CRef() as c:
         got = run_engine(c, ev, max_batch=4096)
     assert_same(ref, got)
     # the scenario's records are byte-identical to the synthetic stream's
-    assert make_records([to_req(recs[7])]).tobytes() == recs[7:8].tobytes()
+    assert make_records([synth_to_req(recs[7])]).tobytes() == recs[7:8].tobytes()

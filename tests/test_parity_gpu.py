@@ -123,6 +123,54 @@ def test_chunked_pipelined_ingest_equals_one_launch():
         pin.free(); pv.free()
 
 
+def test_config1_stream_on_gpu():
+    """BASELINE config 1 (10 k records / 16 agents / stop-start / one tick) through the CUDA path == Python oracle."""
+    from scenario import config1_events
+    ev, _ = config1_events()
+    with engine() as eng:
+        assert_same(run_oracle(ev), run_engine(eng, ev, max_batch=4096))
+
+
+def test_config3_shape_against_c_port():
+    """BASELINE config 3's shape (Zipf s = 1.2 over 256 ids, 10 % replay-flagged duplicates) at 200 k records, with a
+    mixed agent population, completions, a stop/start and a tick: CUDA path == C restatement on every verdict, every
+    per-agent list and the replay dispatch order."""
+    from oracle.cpu_ref import CRef
+    n, na = 200_000, 256
+    recs = A.synth_fill_host(0, n, seed=3, n_agents=na, zipf_milli=1200, dup_permille=100)
+    agents = [A.synth_agent_id(k) for k in range(na)]
+    outs = np.zeros(n, dtype=A.outcome_dtype)
+    with A.Engine(slab_rows=1 << 19, max_agents=512, max_batch=1 << 18) as eng, CRef() as ref:
+        for e in (eng, ref):
+            for k, a in enumerate(agents):
+                e.set_agent_state(a, "stopped" if k % 5 == 1 else "running")      # incl. the rank-1 hot agent
+        results = []
+        for e in (eng, ref):
+            v, _ = e.ingest(recs)
+            fwd = (v["code"] == K.AGR_V_FORWARD) & ((v["flags"] & K.AGR_VF_TRACKED) != 0)
+            m = int(fwd.sum())
+            outs[:m]["request_id"] = np.where(((recs["flags"][fwd] & 1) != 0)[:, None], recs["replay_of"][fwd], recs["request_id"][fwd])
+            outs[:m]["agent_id"] = recs["agent_id"][fwd]
+            kinds = np.array([K.AGR_OUT_RESPONSE, K.AGR_OUT_RESPONSE, K.AGR_OUT_RESPONSE, K.AGR_OUT_ERROR, K.AGR_OUT_DIAL_ERR], dtype=np.uint8)
+            outs[:m]["kind"] = kinds[np.arange(m) % 5]
+            outs[:m]["http_status"] = 200
+            res = e.complete(np.ascontiguousarray(outs[:m]))
+            for k, a in enumerate(agents):
+                if k % 5 == 1:
+                    e.set_agent_state(a, "running")
+            disp, _ = e.replay_scan(with_records=False) if e is eng else e.replay_scan()
+            results.append((v, res, disp))
+        (v0, r0, d0), (v1, r1, d1) = results
+        assert (v0["code"] == v1["code"]).all() and ((v0["flags"] & 0x7) == (v1["flags"] & 0x7)).all()
+        assert (v0["agent_slot"] == v1["agent_slot"]).all()
+        assert (r0 == r1).all()
+        assert len(d0) == len(d1) > 10_000
+        assert (d0["agent_slot"] == d1["agent_slot"]).all() and d0["request_id"].tobytes() == d1["request_id"].tobytes()
+        for a in agents[:12] + agents[100:104]:
+            for w in (0, 1, 2):
+                assert eng.list(a, w, cap=1 << 16).tobytes() == ref.list(a, w, cap=1 << 16).tobytes(), (a, w)
+
+
 def test_persistence_disabled():
     ev = [("agent", "agent-1", "running"), ("agent", "agent-2", "stopped"),
           ("req", Req("agent-1", rid_of(1), 1), ("response", 200)), ("req", Req("agent-2", rid_of(2), 2), ("response", 200))]
