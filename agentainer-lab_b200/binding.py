@@ -56,7 +56,7 @@ ABI_SYMBOLS = [
     "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
     "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
-    "agr_stream", "agr_kernel_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
+    "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
 ]
 
@@ -108,6 +108,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_stream": (vp, [vp]),
         "agr_slab_ptr": (vp, [vp, u64]),
         "agr_debug_read": (i32, [vp, i32, u64, u32, vp]),
+        "agr_op_time": (i32, [vp, i32, C.POINTER(C.c_double)]),
         "agr_kernel_time": (i32, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "agr_synth_agent_id": (i32, [C.POINTER(AgrSynth), u32, C.c_char_p]),
         "agr_synth_fill_host": (i32, [C.POINTER(AgrSynth), u64, u32, vp]),
@@ -271,6 +272,11 @@ class Engine:
         ms, n = C.c_double(), C.c_uint64()
         _check(self.lib, self.lib.agr_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def op_time(self, which: int) -> float:
+        ms = C.c_double()
+        _check(self.lib, self.lib.agr_op_time(self.h, which, C.byref(ms)))
+        return ms.value
 
     def debug_read(self, which: str, first_rid: int, n: int) -> np.ndarray:
         sel = {"state": 0, "route": 1, "aux": 2, "cksum": 3}[which]

@@ -92,6 +92,8 @@ struct agr_handle {
     agr_verdict* d_vout = nullptr;             // caller-order verdicts [max_batch]
     // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
     std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
+    cudaEvent_t op_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] last K2 group, [2,3] last K3 select group
+    bool op_timed[2] = {false, false};
 };
 #define AGR_TIMING_RING 1024
 
@@ -267,6 +269,7 @@ void agr_destroy(agr_handle* h) {
     for (void* p : h->host_allocs) cudaFreeHost(p);
     for (int k = 0; k < 2; ++k) if (h->bounce_ev[k]) cudaEventDestroy(h->bounce_ev[k]);
     for (auto e : h->tev) cudaEventDestroy(e);
+    for (auto e : h->op_ev) if (e) cudaEventDestroy(e);
     for (auto e : h->chunk_ev) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -484,10 +487,16 @@ int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* re
         memcpy(h->h_outs, outs, (size_t)n * sizeof(agr_outcome));
         CK(cudaMemcpyAsync(h->d_outs, h->h_outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
     }
+    const bool timing = (h->cfg.flags & AGR_CFG_TIMING) != 0;
+    if (timing) {
+        for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(h->op_ev[0], h->stream));
+    }
     agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, n, h->stream);
     agr_launch_k2(h->d, h->k2, n, h->stream);
     h->k2_launches += 6;
     CK(cudaGetLastError());
+    if (timing) { CK(cudaEventRecord(h->op_ev[1], h->stream)); h->op_timed[0] = true; }
     if (results) {
         CK(cudaMemcpyAsync(h->h_results, h->k2.results, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -536,9 +545,15 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.out_rid = h->d_out_rid; p.out_slot = h->d_out_slot; p.cap = cap;
     p.min_inq = (mode == K3_TICK) ? h->d_min_inq : nullptr;
     if (mode == K3_TICK) CK(cudaMemsetAsync(h->d_min_inq, 0xff, 4, h->stream));
+    const bool timing = (h->cfg.flags & AGR_CFG_TIMING) != 0;
+    if (timing) {
+        for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(h->op_ev[2], h->stream));
+    }
     agr_launch_k3_select(h->d, p, h->sm_count, h->stream);
     h->k3_launches += 4;
     CK(cudaGetLastError());
+    if (timing) { CK(cudaEventRecord(h->op_ev[3], h->stream)); h->op_timed[1] = true; }
     CK(cudaMemcpyAsync(h->h_small, h->d_goff + p.groups, 4, cudaMemcpyDeviceToHost, h->stream));
     if (mode == K3_TICK) CK(cudaMemcpyAsync(h->h_small + 1, h->d_min_inq, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -822,6 +837,18 @@ int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, voi
     }
     CK(cudaMemcpyAsync(out, src, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_op_time(agr_handle* h, int which, double* ms) {
+    if (!h || !ms || which < 0 || which > 1) return fail(AGR_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (!h->op_timed[which]) return fail(AGR_ENOTFOUND, "no timed launch of that group yet (needs AGR_CFG_TIMING)");
+    CK(cudaStreamSynchronize(h->stream));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, h->op_ev[2 * which], h->op_ev[2 * which + 1]));
+    *ms = f;
     return 0;
 }
 

@@ -260,6 +260,33 @@ def run_ours(args, wl, rank, world, local_rank):
     del verdicts
     pin.free(); pin_v.free()
     e_ms = 1e3 * sum(e_times) / len(e_times)
+    # ---- secondary kernels: K2 over one batch of outcomes, K3 replay scan over the slab (device time)
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        host = A.synth_fill_host(W * B, B, **synth)                        # the first timed batch: all stored, all forwarded
+        outs = eng.pinned(B, A.outcome_dtype)
+        outs.array["request_id"] = host["request_id"]; outs.array["agent_id"] = host["agent_id"]
+        outs.array["kind"] = K.AGR_OUT_RESPONSE; outs.array["http_status"] = 200
+        if wl["dup_permille"]:
+            rep = (host["flags"] & 1) != 0
+            outs.array["request_id"][rep] = host["replay_of"][rep]
+        eng.complete(outs.array, want_results=False)
+        k2_ms = eng.op_time(0)
+        outs.free()
+        # a tick where 1/16 of the agents are running with a backlog (every un-completed row is still pending)
+        for k in range(wl["agents"]):
+            if k % 16:
+                eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "stopped")
+        disp, _ = eng.replay_scan(with_records=False, cap=1 << 22)
+        k3_ms = eng.op_time(1)
+        for k in range(wl["agents"]):
+            eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
+        scanned = eng.stats()["rows_used"]
+        secondary = {"k2_complete": {"outcomes": B, "ms": k2_ms, "outcomes_per_s": B / (k2_ms * 1e-3), "algorithmic_bytes_per_outcome": 72,
+                                     "GBps": 72 * B / (k2_ms * 1e-3) / 1e9},
+                     "k3_replay_scan": {"rows_scanned": scanned, "dispatched": int(len(disp)), "ms": k3_ms,
+                                        "rows_per_s": scanned / (k3_ms * 1e-3), "algorithmic_bytes_per_row": 8,
+                                        "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9}}
     # ---- N > 1: the exchange path (BASELINE config 4): 5 % of every rank's batch are replay-flagged records whose agent
     # lives on another shard -> K4 bin/pack, NCCL all-to-all to the owners, K1 there, verdicts back.  Host buffers in,
     # verdicts out, wall clock with a barrier on both sides (max over ranks by construction of the barrier).
@@ -335,6 +362,8 @@ def run_ours(args, wl, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         if exchange:
             line["exchange"] = exchange
+        if secondary:
+            line["secondary_kernels"] = secondary
         print(json.dumps(line))
     eng.close()
     if dist:
@@ -352,6 +381,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exchange", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--x-steps", type=int, default=3)
     ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")
     ap.add_argument("--rows", type=int, default=0, help="override slab rows (table size follows)")

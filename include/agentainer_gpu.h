@@ -239,6 +239,9 @@ void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run
 /* With AGR_CFG_TIMING: device time of the dominant K1 kernel (k1_ingest) summed over the launches since the last
  * call (at most the latest 1024), from CUDA events recorded on the launching stream.  Synchronises. */
 int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches);
+/* With AGR_CFG_TIMING: device time (CUDA events on the launching stream) of the most recent kernel group:
+ * which = 0 the K2 kernels of the last agr_complete, 1 the K3 select kernels of the last scan / pending / list. */
+int agr_op_time(agr_handle* h, int which, double* ms);
 void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
 
 /* ------------------------------------------------------------ multi-GPU exchange (K4) */
