@@ -28,7 +28,7 @@ assert verdict_dtype.itemsize == 8 and dispatch_dtype.itemsize == 32
 class AgrConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("slab_rows", C.c_uint64), ("table_slots", C.c_uint64),
                 ("max_agents", C.c_uint32), ("max_batch", C.c_uint32), ("log_entries", C.c_uint64),
-                ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
+                ("id_secret", C.c_uint64), ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AgrStats(C.Structure):
@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "agr_create", "agr_destroy", "agr_abi_version", "agr_last_error", "agr_strerror",
     "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
     "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
-    "agr_host_alloc", "agr_host_free", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
+    "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
 ]
@@ -101,6 +101,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_stats_get": (i32, [vp, C.POINTER(AgrStats)]),
         "agr_host_alloc": (vp, [C.c_size_t]),
         "agr_host_free": (None, [vp]),
+        "agr_mint_ids": (i32, [vp, u64, u32, vp]),
         "agr_reserve_rows": (i32, [vp, u32, C.POINTER(u64)]),
         "agr_ingest_rows": (i32, [vp, u64, u32, vp]),
         "agr_ingest_rows_async": (i32, [vp, u64, u32]),
@@ -199,10 +200,11 @@ class Engine:
     """One shard (one GPU) of the request engine.  Thin wrapper: every method is one C-ABI call."""
 
     def __init__(self, *, device=-1, slab_rows=1 << 16, max_agents=1024, max_batch=0, flags=0, table_slots=0,
-                 log_entries=0, k1_variant=0):
+                 log_entries=0, k1_variant=0, id_secret=0):
         self.lib = load_library()
         cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
-                        log_entries, k1_variant, 0)
+                        log_entries, id_secret, k1_variant, 0)
+        self.mint = bool(flags & K.AGR_CFG_MINT_IDS)
         h = C.c_void_p()
         _check(self.lib, self.lib.agr_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -248,6 +250,11 @@ class Engine:
         first = C.c_uint64()
         _check(self.lib, self.lib.agr_ingest(self.h, _ptr(recs), n, _ptr(out) if want_verdicts else None, C.byref(first)))
         return out, first.value
+
+    def mint_ids(self, first_rid: int, n: int) -> np.ndarray:
+        ids = np.zeros((n, 16), dtype=np.uint8)
+        _check(self.lib, self.lib.agr_mint_ids(self.h, first_rid, n, _ptr(ids)))
+        return ids
 
     def reserve_rows(self, n: int) -> int:
         first = C.c_uint64()

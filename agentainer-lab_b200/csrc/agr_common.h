@@ -106,6 +106,52 @@ AGR_HD unsigned long long agr_fnv1a64(const char* s, uint32_t maxlen) {
     return h;
 }
 
+// ---- engine-minted request ids (AGR_CFG_MINT_IDS).  The reference mints uuid.New() INSIDE StoreRequest
+// (internal/requests/requests.go:87); in this mode the engine does the same, and the id is an exact invertible
+// function of where the record lives: lo = a keyed 60-bit permutation of (row | shard << 40 | generation << 48) laid
+// around the UUIDv4 version nibble, hi = a keyed hash of the same value with the RFC 4122 variant bits.  A lookup
+// decodes the row from lo and accepts only if mint(row) equals ALL 128 presented bits — an exact membership test with
+// no table, no atomics and no random DRAM traffic on the ingest path.
+#define AGR_MINT_M60 ((1ULL << 60) - 1)
+#define AGR_MINT_C1 0x9e3779b97f4a7c15ULL
+#define AGR_MINT_C2 0xbf58476d1ce4e5b9ULL
+AGR_HD unsigned long long agr_inv_odd(unsigned long long c) {           // inverse mod 2^64 (Newton), masked by callers
+    unsigned long long x = c;
+    for (int k = 0; k < 6; ++k) x *= 2 - c * x;
+    return x;
+}
+AGR_HD unsigned long long agr_perm60(unsigned long long x) {
+    x &= AGR_MINT_M60;
+    x = (x * AGR_MINT_C1) & AGR_MINT_M60; x ^= x >> 29;
+    x = (x * AGR_MINT_C2) & AGR_MINT_M60; x ^= x >> 31;
+    return x;
+}
+AGR_HD unsigned long long agr_perm60_inv(unsigned long long y) {
+    y &= AGR_MINT_M60;
+    y ^= y >> 31;                                                          // 2 * 31 >= 60: self-inverse
+    y = (y * agr_inv_odd(AGR_MINT_C2)) & AGR_MINT_M60;
+    y ^= y >> 29; y ^= y >> 58;                                            // inverse of y ^= y >> 29 on 60 bits
+    y = (y * agr_inv_odd(AGR_MINT_C1)) & AGR_MINT_M60;
+    return y;
+}
+AGR_HD void agr_mint_id(unsigned long long rid, uint32_t shard, uint32_t gen, unsigned long long secret,
+                        unsigned long long& lo, unsigned long long& hi) {
+    const unsigned long long x = (rid & 0xffffffffffULL) | ((unsigned long long)(shard & 0xffu) << 40) | ((unsigned long long)(gen & 0xfffu) << 48);
+    const unsigned long long y = agr_perm60(x ^ (secret & AGR_MINT_M60));
+    lo = (y & ((1ULL << 52) - 1)) | (0x4ULL << 52) | ((y >> 52) << 56);
+    hi = agr_fmix64((x + 0x632be59bd9b4e019ULL) * 0x9e3779b97f4a7c15ULL ^ (secret >> 7));
+    hi = (hi & ~0xc0ULL) | 0x80ULL;
+}
+// decodes (rid, shard, gen) from lo; returns false if lo cannot be a minted id.  Callers must still compare
+// agr_mint_id(rid, shard, gen) with the presented (lo, hi).
+AGR_HD bool agr_unmint_id(unsigned long long lo, unsigned long long secret, unsigned long long& rid, uint32_t& shard, uint32_t& gen) {
+    if (((lo >> 52) & 0xfULL) != 0x4ULL) return false;
+    const unsigned long long y = (lo & ((1ULL << 52) - 1)) | ((lo >> 56) << 52);
+    const unsigned long long x = agr_perm60_inv(y) ^ (secret & AGR_MINT_M60);
+    rid = x & 0xffffffffffULL; shard = (uint32_t)((x >> 40) & 0xffu); gen = (uint32_t)((x >> 48) & 0xfffu);
+    return true;
+}
+
 // ---- record checksum: c0 = sum w_k, c1 = sum (k+1) w_k over the 128 little-endian u32 words, mod 2^32
 // (Fletcher-style; detects any single-word change and any swap of two unequal words).
 AGR_HD unsigned long long agr_cksum_pack(uint32_t c0, uint32_t c1) {

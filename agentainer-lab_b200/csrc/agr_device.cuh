@@ -42,6 +42,24 @@ __device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsig
     return ~0ULL;
 }
 
+// (agent slot is checked by the callers) request id -> row holding the record stored under it, or AGR_RID_NONE.
+// Hash mode: probe the dedupe index.  Mint mode: decode the row from the id and accept only an exact 128-bit match.
+__device__ __forceinline__ uint32_t lookup_rid(const agr_dev& d, unsigned long long lo, unsigned long long hi) {
+    if ((lo | hi) == 0ULL) return AGR_RID_NONE;
+    if (d.cfg_flags & AGR_CFG_MINT_IDS) {
+        unsigned long long rid; uint32_t shard, gen;
+        if (!agr_unmint_id(lo, d.id_secret, rid, shard, gen)) return AGR_RID_NONE;
+        if (rid >= d.rows_hi || shard != d.shard_id || gen != d.id_gen) return AGR_RID_NONE;
+        unsigned long long mlo, mhi;
+        agr_mint_id(rid, shard, gen, d.id_secret, mlo, mhi);
+        return (mlo == lo && mhi == hi) ? (uint32_t)rid : AGR_RID_NONE;
+    }
+    const unsigned long long idx = table_find(d, lo, hi);
+    if (idx == ~0ULL) return AGR_RID_NONE;
+    const uint32_t inv = __ldcg(&d.table[idx].inv_rid);
+    return inv ? ~inv : AGR_RID_NONE;
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // Decision + persistence for ONE record whose 96 B header is in registers: the sequential semantics of
 // proxyToAgentHandler (server.go:498-541) with StoreRequest (requests.go:64-117) inlined, split in stages so a
@@ -90,7 +108,8 @@ __device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, c
     const bool found = c.slot != RT_SLOT_NONE && c.astatus != AG_STATUS_REMOVED;
     c.want_store = found && (d.cfg_flags & AGR_CFG_PERSISTENCE) && !c.replay;             // server.go:508
     // split mode: the insert is done by k1_index after the stream kernel; the row is provisionally "stored"
-    c.deferred = c.want_store && (c.id_lo | c.id_hi) != 0ULL && (d.cfg_flags & AGR_CFGI_SPLIT_INDEX);
+    // mint mode: the id is a function of the row, nothing to insert; the caller's request_id is ignored
+    c.deferred = c.want_store && ((d.cfg_flags & AGR_CFG_MINT_IDS) || ((c.id_lo | c.id_hi) != 0ULL && (d.cfg_flags & AGR_CFGI_SPLIT_INDEX)));
     c.cas_issued = c.want_store && (c.id_lo | c.id_hi) != 0ULL && !c.deferred && !(d.cfg_flags & AGR_CFG_DIAG_NO_INDEX);
     c.old = 0;
     c.tidx = 0;

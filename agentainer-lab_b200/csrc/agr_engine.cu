@@ -178,9 +178,11 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (c.flags == 0) c.flags = AGR_CFG_PERSISTENCE;
     if (c.slab_rows == 0) c.slab_rows = 1ull << 20;
     if (c.slab_rows >= 0x7fffffffull) return fail(AGR_EINVAL, "slab_rows must be < 2^31");
+    const bool mint = (c.flags & AGR_CFG_MINT_IDS) != 0;
+    if (mint) c.table_slots = 64;                               // no dedupe index in this mode (a stub keeps pointers valid)
     if (c.table_slots == 0) c.table_slots = next_pow2(c.slab_rows * 2);
     if (c.table_slots & (c.table_slots - 1)) return fail(AGR_EINVAL, "table_slots must be a power of two");
-    if (c.table_slots < c.slab_rows + c.slab_rows / 4) return fail(AGR_EINVAL, "table_slots must be >= 1.25 * slab_rows");
+    if (!mint && c.table_slots < c.slab_rows + c.slab_rows / 4) return fail(AGR_EINVAL, "table_slots must be >= 1.25 * slab_rows");
     if (c.table_slots > (1ull << 32)) return fail(AGR_EINVAL, "table_slots must be <= 2^32");
     if (c.max_agents == 0) c.max_agents = 4096;
     if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
@@ -220,6 +222,9 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
     TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
+    TRY(dev_alloc(h, &d.head, c.slab_rows, true));
+    d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
+    d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
     if ((c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags & 0xffffu;
@@ -241,7 +246,6 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     h->k2.ops = h->d_ops;
     TRY(dev_alloc(h, &h->k2.nxt, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.hrid, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.hidx, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.eff, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.results, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048, false));
@@ -361,6 +365,7 @@ static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
 }
 
 static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out) {
+    h->d.rows_hi = (uint32_t)h->rows_used;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
         if (h->tev.empty()) {
@@ -388,6 +393,17 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
         memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
     } else if (sync) {
         CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int agr_mint_ids(agr_handle* h, uint64_t first_rid, uint32_t n, uint8_t (*ids)[16]) {
+    if (!h || (n && !ids)) return fail(AGR_EINVAL, "NULL argument");
+    if (!(h->cfg.flags & AGR_CFG_MINT_IDS)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_MINT_IDS");
+    for (uint32_t i = 0; i < n; ++i) {
+        unsigned long long lo, hi;
+        agr_mint_id(first_rid + i, h->d.shard_id, h->d.id_gen, h->d.id_secret, lo, hi);
+        memcpy(ids[i], &lo, 8); memcpy(ids[i] + 8, &hi, 8);
     }
     return 0;
 }
@@ -487,6 +503,7 @@ int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* re
         memcpy(h->h_outs, outs, (size_t)n * sizeof(agr_outcome));
         CK(cudaMemcpyAsync(h->d_outs, h->h_outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
     }
+    h->d.rows_hi = (uint32_t)h->rows_used;
     const bool timing = (h->cfg.flags & AGR_CFG_TIMING) != 0;
     if (timing) {
         for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
@@ -658,6 +675,7 @@ int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id
     memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    h->d.rows_hi = (uint32_t)h->rows_used;
     agr_launch_resolve(h->d, h->k2, 1, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
@@ -731,6 +749,7 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     ncclUniqueId uid; memcpy(uid.internal, id, 128);
     NK(g_nccl.CommInitRank(&h->comm, world, uid, rank));
     h->rank = rank; h->world = world;
+    h->d.shard_id = (uint32_t)rank;
     const size_t mb = h->cfg.max_batch;
     TRY(dev_alloc(h, &h->d_stage, mb * AGR_REC, false));
     TRY(dev_alloc(h, &h->d_send, mb * AGR_REC, false));

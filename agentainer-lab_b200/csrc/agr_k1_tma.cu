@@ -117,7 +117,7 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         const uint4 h3 = lds128(base + ((3u << 4) ^ sw)), h4 = lds128(base + ((4u << 4) ^ sw)), h5 = lds128(base + ((5u << 4) ^ sw));
         // long-latency work first: agent-table probe, index-line prefetch, and the claim of the NEXT tile
         const ag_probe ap = k1_agent_issue(d, h2, h3);
-        if (valid && !(h4.z & AGR_F_REPLAY))
+        if (valid && !(h4.z & AGR_F_REPLAY) && !(d.cfg_flags & AGR_CFG_MINT_IDS))
             prefetch_l2(&d.table[agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask]);
         const uint32_t next_tile = tile + (uint32_t)STAGES * (gridDim.x * WARPS);
         // position-weighted checksum over the 32 chunks of the record (weights k+1 over the 128 words).  Only shared

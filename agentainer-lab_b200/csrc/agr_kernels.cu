@@ -98,15 +98,11 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
         uint32_t vf = rt_flags(r);
         if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
             uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + AGR_OFF_REPLAY_OF);
-            unsigned long long idx = table_find(d, pack64(t.x, t.y), pack64(t.z, t.w));
-            if (idx != ~0ULL) {
-                const uint32_t inv = __ldcg(&d.table[idx].inv_rid);
-                const uint32_t orid = ~inv;
-                if (inv != 0u && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
-                    r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
-                    d.route[rid] = r;
-                    hits++;
-                }
+            const uint32_t orid = lookup_rid(d, pack64(t.x, t.y), pack64(t.z, t.w));
+            if (orid != AGR_RID_NONE && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
+                r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
+                d.route[rid] = r;
+                hits++;
             }
         }
         if (dupfix != 0u && (vf & (AGR_VF_STORED | AGR_VF_DUP_ID))) {
@@ -219,7 +215,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if ((variant & 0xfu) != AGR_K1_LSU && tmap != nullptr) {
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
-        if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
+        if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
         k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
         return;
     }
@@ -230,7 +226,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     if (blocks > maxb) blocks = maxb;
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
-    if (d.cfg_flags & AGR_CFGI_SPLIT_INDEX) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
+    if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
     k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
 }
 
@@ -271,16 +267,11 @@ __global__ void __launch_bounds__(256) k2_link(const agr_dev d, const agr_k2_scr
     const bool ext = (d.cfg_flags & AGR_CFG_SKIP_INFLIGHT) != 0;
     if ((op.id_lo | op.id_hi) != 0ULL && (op.kind == AGR_OUT_RESPONSE || op.kind == AGR_OUT_ERROR ||
                                             (op.kind == AGR_OUT_DIAL_ERR && ext))) {
-        unsigned long long idx = table_find(d, op.id_lo, op.id_hi);
-        if (idx != ~0ULL) {
-            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
-            uint32_t cand = ~inv;
-            // the Redis key is agent:{a}:requests:{r}: the agent is part of the key (requests.go:150,229)
-            if (inv != 0u && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) {
-                rid = cand;
-                s.hidx[j] = (uint32_t)idx;
-                s.nxt[j] = atomicExch(&d.table[idx].head, j + 1u);
-            }
+        const uint32_t cand = lookup_rid(d, op.id_lo, op.id_hi);
+        // the Redis key is agent:{a}:requests:{r}: the agent is part of the key (requests.go:150,229)
+        if (cand != AGR_RID_NONE && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) {
+            rid = cand;
+            s.nxt[j] = atomicExch(&d.head[rid], j + 1u);
         }
         if (rid == AGR_RID_NONE && op.kind != AGR_OUT_DIAL_ERR) {
             res = AGR_ENOTFOUND;                                   // requests.go:153-156 / 232-235
@@ -298,14 +289,8 @@ __global__ void __launch_bounds__(256) k_resolve(const agr_dev d, const agr_k2_s
     if (j >= n) return;
     const agr_dop op = s.ops[j];
     uint32_t rid = AGR_RID_NONE;
-    if ((op.id_lo | op.id_hi) != 0ULL) {
-        unsigned long long idx = table_find(d, op.id_lo, op.id_hi);
-        if (idx != ~0ULL) {
-            uint32_t inv = __ldcg(&d.table[idx].inv_rid);
-            uint32_t cand = ~inv;
-            if (inv != 0u && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) rid = cand;
-        }
-    }
+    const uint32_t cand = lookup_rid(d, op.id_lo, op.id_hi);
+    if (cand != AGR_RID_NONE && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) rid = cand;
     s.hrid[j] = rid;
 }
 void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
@@ -316,14 +301,11 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     uint32_t ncomp = 0, nfail = 0, nerr = 0;
-    uint32_t rid = AGR_RID_NONE, idx = 0;
+    uint32_t rid = AGR_RID_NONE;
     bool root = false;
     if (j < n) {
         rid = s.hrid[j];
-        if (rid != AGR_RID_NONE) {
-            idx = s.hidx[j];
-            root = (__ldcg(&d.table[idx].head) == j + 1u);          // chain root = last op linked onto this row
-        }
+        if (rid != AGR_RID_NONE) root = (__ldcg(&d.head[rid]) == j + 1u);   // chain root = last op linked onto this row
     }
     if (root) {
         uint32_t st = d.state[rid], aux = d.aux[rid];
@@ -364,7 +346,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
         }
         d.state[rid] = st;
         d.aux[rid] = aux;
-        d.table[idx].head = 0;
+        d.head[rid] = 0;
     }
     ncomp = __reduce_add_sync(FULL, ncomp);
     nerr = __reduce_add_sync(FULL, nerr);
@@ -574,6 +556,11 @@ __global__ void __launch_bounds__(256) k3_gather(const agr_dev d, const uint32_t
     const uint32_t rid = rids[w];
     const uint8_t* src = d.slab + (size_t)rid * AGR_REC;
     uint4 v = ldg_nc_v4(src + lane * 16);
+    if (lane == 0 && (d.cfg_flags & AGR_CFG_MINT_IDS)) {          // Request.ID = what the engine minted for this row
+        unsigned long long lo, hi;
+        agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+        v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
     if (out_recs) {
         if (lane == 5) {   // bytes 80..95: body_len | status,retry,max,err | resp_status
             const uint32_t st = d.state[rid], aux = d.aux[rid];

@@ -29,6 +29,10 @@ struct agr_dev {
     unsigned long long* log_len;   // [0] completed, [1] failed
     unsigned long long log_cap;
     uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
+    uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
+    unsigned long long id_secret;   // AGR_CFG_MINT_IDS
+    uint32_t shard_id, id_gen;
+    uint32_t rows_hi;          // rows handed out so far (bound for decoded row ids)
     uint32_t cfg_flags;
 };
 
@@ -46,7 +50,6 @@ struct agr_k2_scratch {
     const agr_dop* ops;
     uint32_t* nxt;      // chain link (op index + 1, 0 = end)
     uint32_t* hrid;     // resolved rid or AGR_RID_NONE
-    uint32_t* hidx;     // table slot index
     uint8_t* eff;       // bit0 push completed, bit1 push failed
     int32_t* results;   // 0 / AGR_ENOTFOUND
     uint32_t* chunk_base;  // [2][1024]

@@ -89,6 +89,10 @@ typedef struct agr_record {
 /* ------------------------------------------------------------------ config */
 #define AGR_CFG_PERSISTENCE   0x1u  /* features.request_persistence (config.go:70); default on */
 #define AGR_CFG_TIMING        0x4u  /* record CUDA-event pairs around the dominant K1 kernel (agr_kernel_time) */
+#define AGR_CFG_MINT_IDS      0x8u  /* the engine mints Request.ID itself, like StoreRequest does (requests.go:87): the id is an
+                                       exact invertible function of the record's row, agr_record.request_id of fresh records is
+                                       ignored on input, callers read the ids with agr_mint_ids.  No dedupe-index table exists in
+                                       this mode (lookups decode the row and verify all 128 bits). */
 #define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
 #define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */
 #define AGR_CFG_SKIP_INFLIGHT 0x2u  /* EXTENSION, off in parity mode: replay scan skips records whose forward is still in flight (fixes Q16) */
@@ -101,6 +105,7 @@ typedef struct agr_config {
     uint32_t max_agents;     /* agent-table capacity; 0 = 4096 */
     uint32_t max_batch;      /* largest n accepted by one agr_ingest / agr_complete; 0 = 1<<20 */
     uint64_t log_entries;    /* capacity of the completed and failed logs; 0 = 2*slab_rows */
+    uint64_t id_secret;      /* AGR_CFG_MINT_IDS: key of the id permutation; 0 = a fixed default */
     uint32_t k1_variant;     /* 0 = default K1 kernel (TMA, 14 warps x 1 stage, fused index); 1..4 TMA shapes, 5 = LSU kernel,
                                 | 0x10 = split stream / index kernels — alternates kept for A/B measurement */
     uint32_t reserved;
@@ -226,6 +231,10 @@ int agr_stats_get(agr_handle* h, agr_stats* out);
  * directly into pinned memory obtained here and passes that pointer to agr_ingest (DMA without a bounce). */
 void* agr_host_alloc(size_t bytes);
 void  agr_host_free(void* p);
+
+/* AGR_CFG_MINT_IDS: the ids the engine minted for rows [first_rid, first_rid + n) (pure host computation).  Record i of
+ * an agr_ingest batch lives in row first_rid + i. */
+int agr_mint_ids(agr_handle* h, uint64_t first_rid, uint32_t n, uint8_t (*ids)[16]);
 
 /* Split form of agr_ingest for callers that keep the batch resident on the device (bench "value" leg, and the
  * receive side of the multi-GPU exchange): reserve rows, fill them (agr_synth_fill_rows or a DMA of the caller's

@@ -168,6 +168,17 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
     obs = Observed()
     slot_name: Dict[int, str] = {}
     pend_reqs: List[Tuple[Req, Tuple]] = []
+    # AGR_CFG_MINT_IDS: the engine mints the ids (like StoreRequest does); the scenario's symbolic ids are mapped to
+    # them so that the oracle (which takes its ids from the stream) and the engine can be compared id for id
+    mint = bool(getattr(eng, "mint", False))
+    s2e: Dict[bytes, bytes] = {}
+    e2s: Dict[bytes, bytes] = {}
+
+    def tin(b: bytes) -> bytes:
+        return s2e.get(b, b)
+
+    def tout(b: bytes) -> bytes:
+        return e2s.get(b, b)
 
     def flush():
         nonlocal pend_reqs
@@ -176,7 +187,16 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
             take = min(take, max_batch)
             chunk, pend_reqs = pend_reqs[:take], pend_reqs[take:]
             recs = make_records([r for r, _ in chunk])
-            verdicts, _ = eng.ingest(recs)
+            if mint:
+                for i, (r, _) in enumerate(chunk):
+                    if r.replay:
+                        recs[i]["replay_of"] = np.frombuffer(tin(r.replay_of), dtype=np.uint8)
+            verdicts, first_rid = eng.ingest(recs)
+            if mint:
+                ids = eng.mint_ids(first_rid, len(chunk))
+                for i, ((r, _), v) in enumerate(zip(chunk, verdicts)):
+                    if int(v["flags"]) & K.AGR_VF_STORED:
+                        s2e[r.rid] = bytes(ids[i]); e2s[bytes(ids[i])] = r.rid
             outs: list = []
             for (r, backend), v in zip(chunk, verdicts):
                 code, flags = int(v["code"]), int(v["flags"])
@@ -184,7 +204,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
                 obs.verdicts.append((code, int(v["http_status"]), bool(flags & K.AGR_VF_STORED), tracked))
                 if code != K.AGR_V_FORWARD or not tracked:
                     continue                                 # interceptTransport: requestID == "" records nothing
-                rid = r.replay_of if r.replay else r.rid
+                rid = tin(r.replay_of if r.replay else r.rid)
                 if backend[0] == "response":
                     _outcome(outs, rid, r.agent_id, K.AGR_OUT_RESPONSE, backend[1], r.seq)
                 elif backend[0] == "dial":
@@ -206,7 +226,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
         elif e[0] == "tick":
             backends, flip = e[1], e[2]
             disp, recs = eng.replay_scan(with_records=True)
-            order = [(slot_name[int(d["agent_slot"])], bytes(d["request_id"]).hex()) for d in disp]
+            order = [(slot_name[int(d["agent_slot"])], tout(bytes(d["request_id"])).hex()) for d in disp]
             obs.ticks.append(order)
             # replayRequest (replay_worker.go:120-163): same record, replay-flagged, ID in the tracking header
             recs = recs.copy()
@@ -250,9 +270,9 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
     flush()
     names = {0: "pending", 1: "completed", 2: "failed"}
     for a in all_agents(events):
-        obs.lists[a] = {names[w]: [bytes(x).hex() for x in eng.list(a, w)] for w in (0, 1, 2)}
+        obs.lists[a] = {names[w]: [tout(bytes(x)).hex() for x in eng.list(a, w)] for w in (0, 1, 2)}
     for a, rid in all_fresh(events):
-        rec = eng.get_record(a, rid)
+        rec = eng.get_record(a, tin(rid)) if (not mint or rid in s2e) else None
         if rec is not None:
             obs.records[(a, rid.hex())] = (K.STATUS_NAMES[int(rec["status"])], int(rec["retry_count"]), int(rec["resp_status"]))
     return obs

@@ -19,6 +19,53 @@ def engine(**kw):
     return A.Engine(**kw)
 
 
+MINT = K.AGR_CFG_PERSISTENCE | K.AGR_CFG_MINT_IDS
+
+
+@pytest.mark.parametrize("kat", sorted(SCENARIOS))
+def test_kats_with_engine_minted_ids(kat):
+    """AGR_CFG_MINT_IDS: the engine mints Request.ID (as StoreRequest does, requests.go:87); every KAT still holds."""
+    with engine(flags=MINT) as eng:
+        got = run_engine(eng, SCENARIOS[kat])
+    exp = GOLD[kat]
+    assert got.verdicts == exp["verdicts"] and got.ticks == exp["ticks"] and got.records == exp["records"]
+    for a, qs in exp["lists"].items():
+        assert got.lists[a] == qs, (kat, a)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_streams_with_engine_minted_ids(seed):
+    ev = random_scenario(200 + seed, n_events=400, n_agents=2 + seed % 6, p_replay=0.2)
+    ref = run_oracle(ev)
+    with engine(flags=MINT) as eng:
+        assert_same(ref, run_engine(eng, ev))
+    with engine(flags=MINT, k1_variant=5) as eng:
+        assert_same(ref, run_engine(eng, ev, rng=np.random.default_rng(seed)))
+
+
+def test_minted_ids_are_uuid4_unique_and_verified_exactly():
+    with engine(flags=MINT, id_secret=0xfeedface12345678) as eng:
+        eng.set_agent_state("agent-1", "stopped")
+        reqs = [Req("agent-1", rid_of(i), i) for i in range(1, 2001)]
+        v, first = eng.ingest(make_records(reqs))
+        ids = eng.mint_ids(first, 2000)
+        assert len({bytes(x) for x in ids}) == 2000
+        assert (ids[:, 6] >> 4 == 4).all() and (ids[:, 8] >> 6 == 2).all()
+        assert [bytes(x) for x in eng.list("agent-1", 0)] == [bytes(x) for x in ids]          # pending list speaks minted ids
+        rec = eng.get_record("agent-1", bytes(ids[7]))
+        assert bytes(rec["request_id"]) == bytes(ids[7]) and int(rec["seq"]) == 8
+        # one flipped bit anywhere in the id is a miss (exact 128-bit check, not a tag compare)
+        for bit in (0, 37, 63, 64, 100, 127):
+            bad = bytearray(bytes(ids[7])); bad[bit // 8] ^= 1 << (bit % 8)
+            assert eng.get_record("agent-1", bytes(bad)) is None
+        assert eng.get_record("agent-1", rid_of(8)) is None                                  # the caller's own id is not a key
+        outs = np.zeros(2, dtype=A.outcome_dtype)
+        outs["agent_id"] = b"agent-1"; outs["kind"] = K.AGR_OUT_RESPONSE; outs["http_status"] = 200
+        outs[0]["request_id"] = ids[3]; outs[1]["request_id"] = np.frombuffer(rid_of(4), dtype=np.uint8)
+        assert list(eng.complete(outs)) == [0, K.AGR_ENOTFOUND]
+
+
+
 @pytest.mark.parametrize("kat", sorted(SCENARIOS))
 def test_kat_against_golden_and_oracle(kat):
     with engine() as eng:
