@@ -189,6 +189,41 @@ def run_reference(args, wl, rank, world):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def measure_resident(A, K, torch, dist, args, wl, rank, local_rank, extra_flags, steps, warmup):
+    """Device-resident K1 measurement on a fresh engine: records pre-generated in the slab, `steps` timed launches."""
+    B = wl["records"]
+    eng = A.Engine(device=local_rank, slab_rows=(warmup + steps) * B, max_agents=1024, max_batch=B, k1_variant=args.variant,
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | extra_flags)
+    nanos0 = 1700000000000000000 + rank * 10_000_000_000
+    for k in range(wl["agents"]):
+        eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
+    synth = dict(seed=2 + rank, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"], dup_permille=wl["dup_permille"], agent_nanos0=nanos0)
+    first = eng.reserve_rows(B)
+    for s in range(1, warmup + steps):
+        eng.reserve_rows(B)
+    for s in range(warmup + steps):
+        eng.synth_fill_rows(s * B, first + s * B, B, **synth)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    for s in range(warmup):
+        eng.ingest_rows_async(first + s * B, B)
+    eng.sync(); eng.kernel_time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for s in range(warmup, warmup + steps):
+        eng.ingest_rows_async(first + s * B, B)
+    ev1.record(stream)
+    eng.sync(); torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    k_ms, k_n = eng.kernel_time()
+    st = eng.stats()
+    assert st["stored"] + st["replay_flagged"] == (warmup + steps) * B, st
+    eng.close()
+    return dev_ms, k_ms / max(1, k_n)
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch
     import agentainer_lab_b200 as A
@@ -287,6 +322,12 @@ def run_ours(args, wl, rank, world, local_rank):
                      "k3_replay_scan": {"rows_scanned": scanned, "dispatched": int(len(disp)), "ms": k3_ms,
                                         "rows_per_s": scanned / (k3_ms * 1e-3), "algorithmic_bytes_per_row": 8,
                                         "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9}}
+    # ---- the same workload with engine-minted ids (AGR_CFG_MINT_IDS): StoreRequest mints the id itself in the reference
+    # (requests.go:87); with ids that are a function of the row there is no dedupe-index insert on the ingest path
+    mint = None
+    if not args.no_mint and not wl["dup_permille"]:
+        m_dev_ms, m_k = measure_resident(A, K, torch, dist, args, wl, rank, local_rank, K.AGR_CFG_MINT_IDS, min(S, 10), W)
+        mint = (m_dev_ms / min(S, 10), m_k)
     # ---- N > 1: the exchange path (BASELINE config 4): 5 % of every rank's batch are replay-flagged records whose agent
     # lives on another shard -> K4 bin/pack, NCCL all-to-all to the owners, K1 there, verdicts back.  Host buffers in,
     # verdicts out, wall clock with a barrier on both sides (max over ranks by construction of the barrier).
@@ -327,9 +368,11 @@ def run_ours(args, wl, rank, world, local_rank):
                     "nvlink_bytes_per_step": float(cnt[0]) * (512 + 8) / len(x_times),
                     "api": "agr_ingest_sharded (pinned host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
     if dist:
-        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)], device="cuda", dtype=torch.float64)
+        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)] + (list(mint) if mint else [0.0, 0.0]), device="cuda", dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dev_ms, e_ms, k_avg = [float(x) for x in t_all.tolist()]
+        dev_ms, e_ms, k_avg = [float(x) for x in t_all.tolist()[:3]]
+        if mint:
+            mint = tuple(float(x) for x in t_all.tolist()[3:5])
     else:
         k_avg = k_ms / max(1, k_n)
     if rank == 0:
@@ -364,6 +407,11 @@ def run_ours(args, wl, rank, world, local_rank):
             line["exchange"] = exchange
         if secondary:
             line["secondary_kernels"] = secondary
+        if mint:
+            m_ach = ALG_BYTES_PER_RECORD * B / (mint[1] * 1e-3) / 1e9
+            line["mint_ids"] = {"value": world * B / (mint[0] * 1e-3), "unit": "requests/s", "ms_per_step": mint[0], "kernel_ms": mint[1],
+                                "roofline_frac": m_ach / peak, "achieved_GBps": m_ach,
+                                "note": "same workload and kernel with AGR_CFG_MINT_IDS: the engine mints Request.ID as a keyed bijection of the row (the reference mints uuid.New() inside StoreRequest), so ingest has no dedupe-index insert"}
         print(json.dumps(line))
     eng.close()
     if dist:
@@ -382,6 +430,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exchange", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-mint", action="store_true")
     ap.add_argument("--x-steps", type=int, default=3)
     ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")
     ap.add_argument("--rows", type=int, default=0, help="override slab rows (table size follows)")
