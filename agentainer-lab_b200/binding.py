@@ -47,16 +47,17 @@ class AgrExchangeInfo(C.Structure):
 
 class AgrSynth(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_agents", C.c_uint32), ("zipf_milli", C.c_uint32),
-                ("dup_permille", C.c_uint32), ("reserved", C.c_uint32), ("agent_nanos0", C.c_uint64)]
+                ("dup_permille", C.c_uint32), ("mint", C.c_uint32), ("agent_nanos0", C.c_uint64),
+                ("mint_base_rid", C.c_uint64), ("mint_secret", C.c_uint64), ("mint_shard", C.c_uint32), ("mint_gen", C.c_uint32)]
 
 
 # every symbol include/agentainer_gpu.h declares (tests/test_abi.py cross-checks this list against the header)
 ABI_SYMBOLS = [
     "agr_create", "agr_destroy", "agr_abi_version", "agr_last_error", "agr_strerror",
     "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
-    "agr_ingest", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
+    "agr_ingest", "agr_ingest_ex", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
-    "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows",
+    "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
 ]
 
@@ -93,6 +94,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_drop_agent": (i32, [vp, C.c_char_p]),
         "agr_agent_slot": (i32, [vp, C.c_char_p]),
         "agr_ingest": (i32, [vp, vp, u32, vp, C.POINTER(u64)]),
+        "agr_ingest_ex": (i32, [vp, vp, u32, vp, vp, C.POINTER(u64)]),
         "agr_complete": (i32, [vp, vp, u32, vp]),
         "agr_replay_scan": (i32, [vp, vp, vp, u32, C.POINTER(u32)]),
         "agr_pending": (i32, [vp, C.c_char_p, vp, u32, C.POINTER(u32)]),
@@ -114,6 +116,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_synth_agent_id": (i32, [C.POINTER(AgrSynth), u32, C.c_char_p]),
         "agr_synth_fill_host": (i32, [C.POINTER(AgrSynth), u64, u32, vp]),
         "agr_synth_fill_rows": (i32, [vp, C.POINTER(AgrSynth), u64, u64, u32]),
+        "agr_synth_bind_mint": (i32, [vp, C.POINTER(AgrSynth), u64]),
         "agr_agent_hash": (u64, [C.c_char_p]),
         "agr_agent_shard": (u32, [C.c_char_p, u32]),
         "agr_comm_unique_id": (i32, [vp]),
@@ -140,16 +143,20 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
 
-def _synth(seed, n_agents, zipf_milli=0, dup_permille=0, agent_nanos0=0) -> AgrSynth:
-    return AgrSynth(seed, n_agents, zipf_milli, dup_permille, 0, agent_nanos0)
+def _synth(seed, n_agents, zipf_milli=0, dup_permille=0, agent_nanos0=0, mint=None) -> AgrSynth:
+    s = AgrSynth(seed, n_agents, zipf_milli, dup_permille, 0, agent_nanos0, 0, 0, 0, 0)
+    if mint is not None:          # (engine, base_rid): duplicates name engine-minted ids
+        eng, base = mint
+        _check(eng.lib, eng.lib.agr_synth_bind_mint(eng.h, C.byref(s), base))
+    return s
 
 
 def synth_fill_host(first_index: int, n: int, *, seed=1, n_agents=16, zipf_milli=0, dup_permille=0,
-                    agent_nanos0=0, out: Optional[np.ndarray] = None) -> np.ndarray:
+                    agent_nanos0=0, mint=None, out: Optional[np.ndarray] = None) -> np.ndarray:
     lib = load_library()
     if out is None:
         out = np.zeros(n, dtype=record_dtype)
-    s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0)
+    s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0, mint)
     _check(lib, lib.agr_synth_fill_host(C.byref(s), first_index, n, _ptr(out)))
     return out
 
@@ -239,6 +246,13 @@ class Engine:
         return _check(self.lib, self.lib.agr_agent_slot(self.h, agent_id.encode()))
 
     # ---- K1
+    def ingest_ex(self, recs: np.ndarray, out: np.ndarray, ids: np.ndarray) -> int:
+        """agr_ingest_ex: verdicts and Request.IDs into caller arrays (pinned or not); returns first_rid."""
+        assert recs.dtype == record_dtype and out.dtype == verdict_dtype and ids.dtype == np.uint8 and ids.shape[1] == 16
+        first = C.c_uint64()
+        _check(self.lib, self.lib.agr_ingest_ex(self.h, _ptr(recs), len(recs), _ptr(out), _ptr(ids), C.byref(first)))
+        return first.value
+
     def ingest(self, recs: np.ndarray, want_verdicts: bool = True, out: Optional[np.ndarray] = None) -> Tuple[Optional[np.ndarray], int]:
         assert recs.dtype == record_dtype and recs.flags["C_CONTIGUOUS"]
         n = len(recs)
@@ -295,8 +309,8 @@ class Engine:
         return self.lib.agr_slab_ptr(self.h, rid) or 0
 
     def synth_fill_rows(self, first_index: int, first_rid: int, n: int, *, seed=1, n_agents=16, zipf_milli=0,
-                        dup_permille=0, agent_nanos0=0) -> None:
-        s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0)
+                        dup_permille=0, agent_nanos0=0, mint_base=None) -> None:
+        s = _synth(seed, n_agents, zipf_milli, dup_permille, agent_nanos0, (self, mint_base) if mint_base is not None else None)
         _check(self.lib, self.lib.agr_synth_fill_rows(self.h, C.byref(s), first_index, first_rid, n))
 
     def pinned(self, n: int, dtype=record_dtype) -> PinnedArray:

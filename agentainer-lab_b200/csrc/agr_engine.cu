@@ -47,6 +47,8 @@ struct agr_handle {
     std::vector<cudaEvent_t> chunk_ev;
     agr_verdict* d_verdicts = nullptr;         // [max_batch], written by k1_post
     agr_verdict* h_verdicts = nullptr;         // pinned [max_batch]
+    uint8_t* d_ids = nullptr;                  // [max_batch][16] Request.ID per record (agr_ingest_ex)
+    uint8_t* h_ids = nullptr;                  // pinned
     agr_dev d{};
     uint64_t rows_used = 0;
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
@@ -237,6 +239,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     }
     TRY(host_alloc(h, &h->h_verdicts, c.max_batch));
     TRY(dev_alloc(h, &h->d_verdicts, c.max_batch, false));
+    TRY(dev_alloc(h, &h->d_ids, (size_t)c.max_batch * 16, false));
+    TRY(host_alloc(h, &h->h_ids, (size_t)c.max_batch * 16));
     TRY(host_alloc(h, &h->h_ops, (size_t)16));
     TRY(host_alloc(h, &h->h_outs, c.max_batch));
     TRY(dev_alloc(h, &h->d_outs, c.max_batch, false));
@@ -364,7 +368,7 @@ static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
     return 0;
 }
 
-static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out) {
+static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out, uint8_t* d_ids = nullptr) {
     h->d.rows_hi = (uint32_t)h->rows_used;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
@@ -376,7 +380,7 @@ static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdi
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
     agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr,
-                  h->sm_count, h->stream, e0, e1, d_out);
+                  h->sm_count, h->stream, e0, e1, d_out, d_ids);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
     return 0;
@@ -440,6 +444,10 @@ void* agr_slab_ptr(agr_handle* h, uint64_t rid) { return (h && rid < h->cfg.slab
 // Pinned (or registered) caller memory is DMA'd in place; pageable memory goes through two pinned bounce buffers.
 #define AGR_INGEST_CHUNK (1u << 17)   // 128 Ki records = 64 MiB per H2D chunk
 int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid) {
+    return agr_ingest_ex(h, recs, n, out, nullptr, first_rid);
+}
+
+int agr_ingest_ex(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
@@ -450,6 +458,7 @@ int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* o
     if (n == 0) return 0;
     const bool src_pinned = is_pinned(recs);
     const bool out_pinned = out && is_pinned(out);
+    const bool ids_pinned = ids && is_pinned(ids);
     const uint32_t nchunks = (n + AGR_INGEST_CHUNK - 1) / AGR_INGEST_CHUNK;
     while (h->chunk_ev.size() < nchunks + 1) {
         cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -478,14 +487,19 @@ int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* o
         }
         CK(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
-        TRY(launch_k1_locked(h, first + off, cn, out ? h->d_verdicts + off : nullptr));
+        TRY(launch_k1_locked(h, first + off, cn, out ? h->d_verdicts + off : nullptr, ids ? h->d_ids + (size_t)off * 16 : nullptr));
         if (out) {
             agr_verdict* hdst = out_pinned ? out + off : h->h_verdicts + off;
             CK(cudaMemcpyAsync(hdst, h->d_verdicts + off, (size_t)cn * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
         }
+        if (ids) {
+            uint8_t* idst = ids_pinned ? (uint8_t*)ids + (size_t)off * 16 : h->h_ids + (size_t)off * 16;
+            CK(cudaMemcpyAsync(idst, h->d_ids + (size_t)off * 16, (size_t)cn * 16, cudaMemcpyDeviceToHost, h->stream));
+        }
     }
     CK(cudaStreamSynchronize(h->stream));
     if (out && !out_pinned) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
+    if (ids && !ids_pinned) memcpy(ids, h->h_ids, (size_t)n * 16);
     return 0;
 }
 
@@ -890,8 +904,17 @@ int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches) {
 }
 
 // ------------------------------------------------------------------------------------------ synthetic stream
+int agr_synth_bind_mint(agr_handle* h, agr_synth* s, uint64_t base_rid) {
+    if (!h || !s) return fail(AGR_EINVAL, "NULL argument");
+    if (!(h->cfg.flags & AGR_CFG_MINT_IDS)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_MINT_IDS");
+    s->mint = 1; s->mint_base_rid = base_rid; s->mint_secret = h->d.id_secret; s->mint_shard = h->d.shard_id; s->mint_gen = h->d.id_gen;
+    return 0;
+}
+
 static agr_synth_dev synth_params(const agr_synth* s, const unsigned long long* cdf) {
     agr_synth_dev p;
+    p.mint = s->mint; p.mint_shard = s->mint_shard; p.mint_gen = s->mint_gen; p.pad = 0;
+    p.mint_base_rid = s->mint_base_rid; p.mint_secret = s->mint_secret;
     p.seed = s->seed; p.n_agents = s->n_agents; p.dup_permille = s->dup_permille;
     p.agent_nanos0 = s->agent_nanos0 ? s->agent_nanos0 : 1700000000000000000ULL;
     p.cdf = cdf;

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 //       LOWEST row that carried it (final inv_rid).  A provisionally stored row that is not the owner is demoted to a
 //       persistence failure (server.go:511-514); a provisional duplicate that IS the owner (it lost the CAS race to a
 //       later row of the same batch) is promoted to stored.
-__global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts) {
+__global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts,
+                                               uint4* __restrict__ ids) {
     const uint32_t dupfix = __ldcg(d.dupfix);
     const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -134,6 +135,15 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
             const uint32_t code = rt_code(r);
             const uint32_t http = code == AGR_V_QUEUED ? 202u : code == AGR_V_UNAVAILABLE ? 503u : code == AGR_V_NOT_FOUND ? 404u : 0u;
             verdicts[i] = make_uint2(code | (rt_flags(r) << 8) | (http << 16), rt_slot(r));
+        }
+        if (ids) {        // Request.ID as the engine knows it
+            if (d.cfg_flags & AGR_CFG_MINT_IDS) {
+                unsigned long long lo, hi;
+                agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+                ids[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+            } else {
+                ids[i] = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+            }
         }
     }
     hits = __reduce_add_sync(FULL, hits);
@@ -208,7 +218,7 @@ cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& 
                               int sm_count, cudaStream_t st);
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
-                   cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, void* verdicts) {
+                   cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, void* verdicts, void* ids) {
     if (n == 0) return;
     cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
@@ -216,7 +226,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
+        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
         return;
     }
     constexpr int WARPS = 8;
@@ -227,7 +237,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
     if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts);
+    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

@@ -15,6 +15,9 @@ struct agr_synth_dev {
     uint32_t dup_permille;
     unsigned long long agent_nanos0;
     const unsigned long long* cdf;   // n_agents cumulative thresholds (pick smallest k with u <= cdf[k]); NULL = uniform
+    // engine-minted ids (AGR_CFG_MINT_IDS): a duplicate names its target by the id the ENGINE minted for the target's row
+    uint32_t mint, mint_shard, mint_gen, pad;
+    unsigned long long mint_base_rid, mint_secret;   // stream index j lives in row mint_base_rid + j
 };
 
 AGR_HD unsigned long long agr_splitmix64(unsigned long long x) {
@@ -75,7 +78,8 @@ AGR_HD void agr_synth_record(const agr_synth_dev& s, unsigned long long i, unsig
     uint32_t agent;
     if (replay) {
         unsigned long long t_lo, t_hi;
-        agr_synth_id(s, target, t_lo, t_hi);
+        if (s.mint) agr_mint_id(s.mint_base_rid + target, s.mint_shard, s.mint_gen, s.mint_secret, t_lo, t_hi);
+        else agr_synth_id(s, target, t_lo, t_hi);
         o64[2] = t_lo; o64[3] = t_hi;
         agent = agr_synth_fresh_agent(s, target);
     } else {

@@ -94,7 +94,7 @@ class ClockSampler:
                 "reasons": sorted(v for k, v in self.REASONS.items() if self.reasons & k), "samples": len(timed)}
 
 
-def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16):
+def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16, mint=None):
     n = len(out)
     per = (n + threads - 1) // threads
     ts = []
@@ -104,7 +104,7 @@ def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16):
             break
         th = threading.Thread(target=A.synth_fill_host, args=(first_index + a, b - a),
                               kwargs=dict(seed=seed, n_agents=wl["agents"], zipf_milli=wl["zipf_milli"],
-                                          dup_permille=wl["dup_permille"], agent_nanos0=nanos0, out=out[a:b]))
+                                          dup_permille=wl["dup_permille"], agent_nanos0=nanos0, mint=mint, out=out[a:b]))
         th.start(); ts.append(th)
     for th in ts:
         th.join()
@@ -201,8 +201,9 @@ def measure_resident(A, K, torch, dist, args, wl, rank, local_rank, extra_flags,
     first = eng.reserve_rows(B)
     for s in range(1, warmup + steps):
         eng.reserve_rows(B)
+    mint_base = first if (extra_flags & K.AGR_CFG_MINT_IDS) else None
     for s in range(warmup + steps):
-        eng.synth_fill_rows(s * B, first + s * B, B, **synth)
+        eng.synth_fill_rows(s * B, first + s * B, B, mint_base=mint_base, **synth)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
     for s in range(warmup):
         eng.ingest_rows_async(first + s * B, B)
@@ -237,8 +238,9 @@ def run_ours(args, wl, rank, world, local_rank):
     B, W, S = wl["records"], args.warmup, args.steps
     e_steps, e_warm = min(S, args.e2e_steps), 1
     rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B + (B if world > 1 else 0) * 2)
+    id_flags = K.AGR_CFG_MINT_IDS if args.id_mode == "mint" else 0
     eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant,
-                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | args.diag_flags)
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | args.diag_flags | id_flags)
     nanos0 = 1700000000000000000 + rank * 10_000_000_000        # each rank (shard) owns its own agent ids
     for k in range(wl["agents"]):
         eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
@@ -246,8 +248,9 @@ def run_ours(args, wl, rank, world, local_rank):
     first = eng.reserve_rows(B)
     for s in range(1, W + S):
         eng.reserve_rows(B)
+    mint_base = first if id_flags else None                      # stream index j -> row first + j
     for s in range(W + S):                                       # records resident in HBM before the timed region
-        eng.synth_fill_rows(s * B, first + s * B, B, **synth)
+        eng.synth_fill_rows(s * B, first + s * B, B, mint_base=mint_base, **synth)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -280,27 +283,33 @@ def run_ours(args, wl, rank, world, local_rank):
     # ---- e2e through the public C-ABI call with pinned host buffers (H2D + kernels + D2H verdicts timed)
     pin = eng.pinned(B)
     pin_v = eng.pinned(B, A.verdict_dtype)
+    pin_ids = eng.pinned(B * 16, np.uint8)
+    ids_view = pin_ids.array.reshape(B, 16)
     e_times = []
     launches_before = st["k1_launches"]
     for s in range(e_warm + e_steps):
-        parallel_fill(A, pin.array, (W + S + s) * B, wl, synth["seed"], nanos0)
+        parallel_fill(A, pin.array, (W + S + s) * B, wl, synth["seed"], nanos0, mint=(eng, first) if id_flags else None)
         if dist:
             dist.barrier()
         t = time.perf_counter()
-        verdicts, _ = eng.ingest(pin.array, out=pin_v.array)
+        eng.ingest_ex(pin.array, pin_v.array, ids_view)          # verdicts AND Request.IDs back on the host
         dt = time.perf_counter() - t
+        verdicts = pin_v.array
         if s >= e_warm:
             e_times.append(dt)
-    assert (verdicts["code"] != 0).all()
-    del verdicts
-    pin.free(); pin_v.free()
+    assert (verdicts["code"] != 0).all() and ids_view.any(axis=1).all()
+    if id_flags:
+        assert (ids_view[:64] == eng.mint_ids(eng.stats()["rows_used"] - B, 64)).all()
+    del verdicts, ids_view
+    pin.free(); pin_v.free(); pin_ids.free()
     e_ms = 1e3 * sum(e_times) / len(e_times)
     # ---- secondary kernels: K2 over one batch of outcomes, K3 replay scan over the slab (device time)
     secondary = None
     if rank == 0 and not args.no_secondary:
-        host = A.synth_fill_host(W * B, B, **synth)                        # the first timed batch: all stored, all forwarded
+        host = A.synth_fill_host(W * B, B, mint=(eng, first) if id_flags else None, **synth)   # the first timed batch
         outs = eng.pinned(B, A.outcome_dtype)
-        outs.array["request_id"] = host["request_id"]; outs.array["agent_id"] = host["agent_id"]
+        outs.array["request_id"] = eng.mint_ids(first + W * B, B) if id_flags else host["request_id"]
+        outs.array["agent_id"] = host["agent_id"]
         outs.array["kind"] = K.AGR_OUT_RESPONSE; outs.array["http_status"] = 200
         if wl["dup_permille"]:
             rep = (host["flags"] & 1) != 0
@@ -322,12 +331,15 @@ def run_ours(args, wl, rank, world, local_rank):
                      "k3_replay_scan": {"rows_scanned": scanned, "dispatched": int(len(disp)), "ms": k3_ms,
                                         "rows_per_s": scanned / (k3_ms * 1e-3), "algorithmic_bytes_per_row": 8,
                                         "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9}}
-    # ---- the same workload with engine-minted ids (AGR_CFG_MINT_IDS): StoreRequest mints the id itself in the reference
-    # (requests.go:87); with ids that are a function of the row there is no dedupe-index insert on the ingest path
-    mint = None
-    if not args.no_mint and not wl["dup_permille"]:
-        m_dev_ms, m_k = measure_resident(A, K, torch, dist, args, wl, rank, local_rank, K.AGR_CFG_MINT_IDS, min(S, 10), W)
-        mint = (m_dev_ms / min(S, 10), m_k)
+    # ---- the same workload and kernel in the OTHER id mode: "mint" = the engine mints
+    # Request.ID like StoreRequest does (requests.go:87) and ids are a keyed bijection of the row; "hash" = caller-supplied
+    # random ids kept in a 32 B/slot dedupe index (one CAS.128 + RED per stored record)
+    other = None
+    if not args.no_other_mode:
+        o_flags = 0 if id_flags else K.AGR_CFG_MINT_IDS
+        o_steps = min(S, 10)
+        o_dev_ms, o_k = measure_resident(A, K, torch, dist, args, wl, rank, local_rank, o_flags, o_steps, W)
+        other = (o_dev_ms / o_steps, o_k)
     # ---- N > 1: the exchange path (BASELINE config 4): 5 % of every rank's batch are replay-flagged records whose agent
     # lives on another shard -> K4 bin/pack, NCCL all-to-all to the owners, K1 there, verdicts back.  Host buffers in,
     # verdicts out, wall clock with a barrier on both sides (max over ranks by construction of the barrier).
@@ -368,11 +380,11 @@ def run_ours(args, wl, rank, world, local_rank):
                     "nvlink_bytes_per_step": float(cnt[0]) * (512 + 8) / len(x_times),
                     "api": "agr_ingest_sharded (pinned host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
     if dist:
-        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)] + (list(mint) if mint else [0.0, 0.0]), device="cuda", dtype=torch.float64)
+        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)] + (list(other) if other else [0.0, 0.0]), device="cuda", dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         dev_ms, e_ms, k_avg = [float(x) for x in t_all.tolist()[:3]]
-        if mint:
-            mint = tuple(float(x) for x in t_all.tolist()[3:5])
+        if other:
+            other = tuple(float(x) for x in t_all.tolist()[3:5])
     else:
         k_avg = k_ms / max(1, k_n)
     if rank == 0:
@@ -382,7 +394,7 @@ def run_ours(args, wl, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(f"variant{args.variant}", {}).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get(f"{args.id_mode}_variant{args.variant}", {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         cpu = cpu_port_single(A, wl) if world == 1 and not args.no_cpu else None
@@ -393,12 +405,14 @@ def run_ours(args, wl, rank, world, local_rank):
             "config": {"workload": wl["name"], "records_per_step_per_gpu": B, "agents_per_gpu": wl["agents"], "record_bytes": 512,
                        "parallelism": f"shard{world} by FNV-1a64(agent_id) mod {world}; fresh traffic steered to the owner (no collective); the exchange path is measured separately under \"exchange\"" if world > 1 else "single",
                        "l2": "each step reads a fresh 512 MiB batch (> 126 MB L2); no explicit flush",
-                       "k1_variant": args.variant},
+                       "k1_variant": args.variant,
+                       "id_mode": args.id_mode + (" (engine-minted Request.ID = keyed bijection of the row, as StoreRequest mints uuid.New(); no dedupe-index table)"
+                                                   if id_flags else " (caller-supplied random ids in a 32 B/slot dedupe index)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k1_ingest", "kernel_ms": k_avg, "launches_timed": k_n, "algorithmic_bytes_per_record": ALG_BYTES_PER_RECORD,
                          "peak_source": peak_src},
-            "e2e": {"value": world * B / (e_ms * 1e-3), "unit": "requests/s", "h2d_bytes_per_step": B * 512, "d2h_bytes_per_step": B * 8,
-                    "steps": len(e_times), "ms_per_step": e_ms, "api": "agr_ingest (pinned host records in, verdicts out)"},
+            "e2e": {"value": world * B / (e_ms * 1e-3), "unit": "requests/s", "h2d_bytes_per_step": B * 512, "d2h_bytes_per_step": B * 24,
+                    "steps": len(e_times), "ms_per_step": e_ms, "api": "agr_ingest_ex (pinned host records in; verdicts + Request.IDs out)"},
             "gpu_launches": S * 2, "wall_ms_timed_region": wall_ms, "clocks": clocks,
         }
         if cpu:
@@ -407,11 +421,10 @@ def run_ours(args, wl, rank, world, local_rank):
             line["exchange"] = exchange
         if secondary:
             line["secondary_kernels"] = secondary
-        if mint:
-            m_ach = ALG_BYTES_PER_RECORD * B / (mint[1] * 1e-3) / 1e9
-            line["mint_ids"] = {"value": world * B / (mint[0] * 1e-3), "unit": "requests/s", "ms_per_step": mint[0], "kernel_ms": mint[1],
-                                "roofline_frac": m_ach / peak, "achieved_GBps": m_ach,
-                                "note": "same workload and kernel with AGR_CFG_MINT_IDS: the engine mints Request.ID as a keyed bijection of the row (the reference mints uuid.New() inside StoreRequest), so ingest has no dedupe-index insert"}
+        if other:
+            o_ach = ALG_BYTES_PER_RECORD * B / (other[1] * 1e-3) / 1e9
+            line["other_id_mode"] = {"id_mode": "hash" if id_flags else "mint", "value": world * B / (other[0] * 1e-3), "unit": "requests/s",
+                                     "ms_per_step": other[0], "kernel_ms": other[1], "roofline_frac": o_ach / peak, "achieved_GBps": o_ach}
         print(json.dumps(line))
     eng.close()
     if dist:
@@ -430,7 +443,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exchange", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--no-mint", action="store_true")
+    ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--id-mode", default="mint", choices=["mint", "hash"])
     ap.add_argument("--x-steps", type=int, default=3)
     ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")
     ap.add_argument("--rows", type=int, default=0, help="override slab rows (table size follows)")

@@ -161,6 +161,9 @@ typedef struct agr_verdict {
  * applied to recs[0..n) in array order.  n == 1 is the single-request call.  first_rid (nullable) receives
  * the slab row of recs[0]; record i lives in row first_rid + i.  recs may be pageable or pinned host memory. */
 int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint64_t* first_rid);
+/* Same, and also returns Request.ID of every record as the engine knows it (nullable): with AGR_CFG_MINT_IDS the ids
+ * the engine minted (what StoreRequest returns in storedReq.ID, server.go:515), otherwise the caller's own ids echoed. */
+int agr_ingest_ex(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid);
 
 /* ------------------------------------------------------- K2 complete / fail */
 enum {
@@ -284,9 +287,15 @@ typedef struct agr_synth {
     uint32_t n_agents;        /* 16 / 256 */
     uint32_t zipf_milli;      /* 0 = uniform; 1200 = Zipf s=1.2 by rank */
     uint32_t dup_permille;    /* replay-flagged duplicates per 1000 records (C3: 100) */
-    uint32_t reserved;
+    uint32_t mint;            /* 1: duplicates name their target by the id the engine mints for it (set by agr_synth_bind_mint) */
     uint64_t agent_nanos0;    /* agent k has id "agent-<agent_nanos0 + k*1000003>" */
+    uint64_t mint_base_rid;   /* row of stream index 0 */
+    uint64_t mint_secret;
+    uint32_t mint_shard, mint_gen;
 } agr_synth;
+/* For engines created with AGR_CFG_MINT_IDS: make the stream's duplicates refer to engine-minted ids, assuming stream
+ * index j will be ingested into row base_rid + j. */
+int agr_synth_bind_mint(agr_handle* h, agr_synth* s, uint64_t base_rid);
 int agr_synth_agent_id(const agr_synth* s, uint32_t k, char out[AGR_AGENT_ID_BYTES]);
 int agr_synth_fill_host(const agr_synth* s, uint64_t first_index, uint32_t n, agr_record* out);
 int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index, uint64_t first_rid, uint32_t n);

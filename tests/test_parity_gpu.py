@@ -178,16 +178,23 @@ def test_config1_stream_on_gpu():
         assert_same(run_oracle(ev), run_engine(eng, ev, max_batch=4096))
 
 
-def test_config3_shape_against_c_port():
+@pytest.mark.parametrize("mode", ["hash", "mint"])
+def test_config3_shape_against_c_port(mode):
     """BASELINE config 3's shape (Zipf s = 1.2 over 256 ids, 10 % replay-flagged duplicates) at 200 k records, with a
     mixed agent population, completions, a stop/start and a tick: CUDA path == C restatement on every verdict, every
     per-agent list and the replay dispatch order."""
     from oracle.cpu_ref import CRef
     n, na = 200_000, 256
-    recs = A.synth_fill_host(0, n, seed=3, n_agents=na, zipf_milli=1200, dup_permille=100)
     agents = [A.synth_agent_id(k) for k in range(na)]
     outs = np.zeros(n, dtype=A.outcome_dtype)
-    with A.Engine(slab_rows=1 << 19, max_agents=512, max_batch=1 << 18) as eng, CRef() as ref:
+    flags = MINT if mode == "mint" else 0
+    with A.Engine(slab_rows=1 << 19, max_agents=512, max_batch=1 << 18, flags=flags) as eng, CRef() as ref:
+        if mode == "mint":
+            # the stream's duplicates name engine-minted ids; the checker is given the same ids the engine will mint
+            recs = A.synth_fill_host(0, n, seed=3, n_agents=na, zipf_milli=1200, dup_permille=100, mint=(eng, 0))
+            recs["request_id"] = eng.mint_ids(0, n)
+        else:
+            recs = A.synth_fill_host(0, n, seed=3, n_agents=na, zipf_milli=1200, dup_permille=100)
         for e in (eng, ref):
             for k, a in enumerate(agents):
                 e.set_agent_state(a, "stopped" if k % 5 == 1 else "running")      # incl. the rank-1 hot agent
@@ -216,6 +223,21 @@ def test_config3_shape_against_c_port():
         for a in agents[:12] + agents[100:104]:
             for w in (0, 1, 2):
                 assert eng.list(a, w, cap=1 << 16).tobytes() == ref.list(a, w, cap=1 << 16).tobytes(), (a, w)
+        assert eng.stats()["dedupe_hits"] > 10_000            # the duplicates really resolved to earlier stored rows
+
+
+def test_ingest_ex_returns_the_ids_the_engine_knows():
+    recs = A.synth_fill_host(0, 3000, seed=5, n_agents=4)
+    for flags in (0, MINT):
+        with engine(flags=flags) as eng:
+            for k in range(4):
+                eng.set_agent_state(A.synth_agent_id(k), "running")
+            eng.ingest(recs[:1000])
+            out, ids = np.zeros(2000, dtype=A.verdict_dtype), np.zeros((2000, 16), dtype=np.uint8)
+            first = eng.ingest_ex(np.ascontiguousarray(recs[1000:]), out, ids)
+            assert first == 1000 and (out["code"] == K.AGR_V_FORWARD).all()
+            exp = eng.mint_ids(first, 2000) if flags else recs["request_id"][1000:]
+            assert (ids == exp).all()
 
 
 def test_persistence_disabled():
