@@ -226,6 +226,60 @@ def test_config3_shape_against_c_port(mode):
         assert eng.stats()["dedupe_hits"] > 10_000            # the duplicates really resolved to earlier stored rows
 
 
+@pytest.mark.parametrize("mode", ["hash", "mint"])
+def test_config5_crash_replay_cycles_against_c_port(mode):
+    """BASELINE config 5's event shape on fixed 512 B records: a sustained stream in batches; every few batches 1 % of
+    the agents 'crash' — status still running, forwards end in dial errors, so their records stay pending with retry
+    untouched (Q12) — then they come back and ONE tick replays each crashed agent's whole pending queue in FIFO order
+    (Q14), each replay completing twice (Q7).  CUDA path == C restatement on verdicts, dispatch order and lists."""
+    from oracle.cpu_ref import CRef
+    na, B, nb = 200, 20_000, 10
+    agents = [A.synth_agent_id(k) for k in range(na)]
+    flags = MINT if mode == "mint" else 0
+    rng = np.random.default_rng(5)
+    with A.Engine(slab_rows=1 << 19, max_agents=512, max_batch=1 << 17, flags=flags) as eng, CRef() as ref:
+        for e in (eng, ref):
+            for a in agents:
+                e.set_agent_state(a, "running")
+        crashed = np.zeros(na, dtype=bool)
+        total_replayed = 0
+        for b in range(nb):
+            recs = A.synth_fill_host(b * B, B, seed=9, n_agents=na, zipf_milli=1200)
+            if mode == "mint":
+                recs["request_id"] = eng.mint_ids(eng.stats()["rows_used"], B)
+            if b % 3 == 1:
+                crashed[rng.choice(na, size=max(1, na // 100 * 2), replace=False)] = True     # ~1-2 % of the agents
+            idx = (np.array([int(x[6:]) for x in recs["agent_id"]]) - 1700000000000000000) // 1000003
+            outs = np.zeros(B, dtype=A.outcome_dtype)
+            outs["request_id"], outs["agent_id"], outs["http_status"] = recs["request_id"], recs["agent_id"], 200
+            outs["kind"] = np.where(crashed[idx], K.AGR_OUT_DIAL_ERR, K.AGR_OUT_RESPONSE)
+            got = []
+            for e in (eng, ref):
+                v, _ = e.ingest(recs)
+                r = e.complete(outs)
+                got.append((v["code"].copy(), r.copy()))
+            assert (got[0][0] == got[1][0]).all() and (got[0][1] == got[1][1]).all()
+            if b % 3 == 2:                      # the crashed agents restart; one tick replays their queues
+                crashed[:] = False
+                d0, r0 = eng.replay_scan(with_records=True)
+                d1, r1 = ref.replay_scan()
+                assert len(d0) == len(d1) and (d0["agent_slot"] == d1["agent_slot"]).all()
+                assert d0["request_id"].tobytes() == d1["request_id"].tobytes()
+                assert r0["payload"].tobytes() == r1["payload"].tobytes()          # the gathered records are the stored ones
+                total_replayed += len(d0)
+                rep = np.zeros(2 * len(d0), dtype=A.outcome_dtype)                  # server-side + worker-side completion (Q7)
+                rep["request_id"] = np.repeat(d0["request_id"], 2, axis=0)
+                rep["agent_id"] = np.repeat(r0["agent_id"], 2)
+                rep["kind"], rep["http_status"] = K.AGR_OUT_RESPONSE, 200
+                for e in (eng, ref):
+                    e.complete(rep)
+        assert total_replayed > 1000
+        for a in agents[:8] + [agents[k] for k in (50, 120, 199)]:
+            for w in (0, 1, 2):
+                assert eng.list(a, w, cap=1 << 16).tobytes() == ref.list(a, w, cap=1 << 16).tobytes(), (a, w)
+        assert sum(len(eng.list(a, 0)) for a in agents) == 0
+
+
 def test_ingest_ex_returns_the_ids_the_engine_knows():
     recs = A.synth_fill_host(0, 3000, seed=5, n_agents=4)
     for flags in (0, MINT):
