@@ -96,8 +96,10 @@ Error Manager::Decide(const std::string& agentID, const HttpRequest& req, Verdic
     if (replay) { auto r = req.Header.find("X-Agentainer-Request-ID"); if (r != req.Header.end()) ParseUUID(r->second, of); }   // :519-522
     agr_record rec; agr_verdict v;
     ToRecord(agentID, req, id, replay, of, ++seq_, &rec);
-    int rc = agr_ingest(h_, &rec, 1, &v, nullptr);
+    uint8_t minted[1][16];
+    int rc = agr_ingest_ex(h_, &rec, 1, &v, minted, nullptr);
     if (rc < 0) return std::string("failed to store request: ") + agr_last_error();
+    if (mint_) memcpy(id, minted[0], 16);                                                // storedReq.ID (server.go:515)
     out->Code = v.code; out->HTTPStatus = v.http_status; out->Stored = (v.flags & AGR_VF_STORED) != 0;
     out->RequestID = !(v.flags & AGR_VF_TRACKED) ? "" : replay ? FormatUUID(of) : FormatUUID(id);
     return "";

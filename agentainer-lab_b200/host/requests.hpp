@@ -59,7 +59,9 @@ bool ParseUUID(const std::string& s, uint8_t id[16]);
 
 class Manager {
   public:
-    explicit Manager(agr_handle* h) : h_(h) {}               // NewManager (requests.go:57)
+    // NewManager (requests.go:57).  engine_mints_ids: the handle was created with AGR_CFG_MINT_IDS, so Request.ID is what
+    // the engine minted (read back through agr_ingest_ex), exactly as StoreRequest returns storedReq.ID (server.go:515).
+    explicit Manager(agr_handle* h, bool engine_mints_ids = false) : h_(h), mint_(engine_mints_ids) {}
     // proxyToAgentHandler's decision (server.go:493-541): agent lookup, replay-flag dedupe, StoreRequest, status gate.
     Error Decide(const std::string& agentID, const HttpRequest& req, Verdict* out);
     // StoreRequest (requests.go:64-117).  Persists and appends to the pending queue regardless of the agent's status.
@@ -80,6 +82,7 @@ class Manager {
   private:
     Error complete(const std::string& agentID, const std::string& requestID, uint8_t kind, int http);
     agr_handle* h_;
+    bool mint_;
     std::atomic<uint64_t> seq_{0};
 };
 

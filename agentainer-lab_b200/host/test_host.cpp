@@ -19,11 +19,12 @@ static std::vector<std::string> list_ids(agr_handle* h, const char* agent, int w
     return out;
 }
 
-int main() {
+static int run(bool mint) {
     agr_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = 0; cfg.slab_rows = 1 << 16; cfg.max_agents = 64; cfg.max_batch = 4096;
+    cfg.flags = AGR_CFG_PERSISTENCE | (mint ? AGR_CFG_MINT_IDS : 0u);
     agr_handle* h = nullptr;
     if (agr_create(&cfg, &h) < 0) { printf("agr_create: %s\n", agr_last_error()); return 2; }
-    Manager mgr(h);
+    Manager mgr(h, mint);
     const char* A = "agent-1700000000000000001";
     HttpRequest post; post.Method = "POST"; post.Path = std::string("/agent/") + A + "/chat";
     post.Header["Content-Type"] = "application/json"; post.Body = {'{', '}'};
@@ -87,6 +88,12 @@ int main() {
     agr_stats st; CHECK(agr_stats_get(h, &st) == 0);
     CHECK(st.completions == 1 + 6 + 4000 && st.completion_misses == 1);
     agr_destroy(h);
-    printf("host mirror OK: KAT-A/B/C + 4000 concurrent requests\n");
+    printf("host mirror OK (%s ids): KAT-A/B/C + 4000 concurrent requests\n", mint ? "engine-minted" : "caller-supplied");
     return 0;
+}
+
+int main() {
+    int rc = run(false);
+    if (rc) return rc;
+    return run(true);
 }
