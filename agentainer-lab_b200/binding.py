@@ -16,6 +16,8 @@ record_dtype = np.dtype([
     ("path_len", "<u2"), ("hdr_len", "<u2"), ("body_len", "<u4"), ("status", "u1"), ("retry_count", "u1"),
     ("max_retries", "u1"), ("error_code", "u1"), ("resp_status", "<u2"), ("reserved0", "<u2"), ("reserved1", "<u4"),
     ("payload", "u1", 416)])
+header_dtype = np.dtype([(n, record_dtype.fields[n][0]) for n in record_dtype.names if n != "payload"])   # the 96 B header
+assert header_dtype.itemsize == 96
 outcome_dtype = np.dtype([
     ("request_id", "u1", 16), ("agent_id", "S32"), ("kind", "u1"), ("reserved0", "u1"), ("http_status", "<u2"),
     ("reserved1", "<u4"), ("seq", "<u8")])
@@ -28,7 +30,7 @@ assert verdict_dtype.itemsize == 8 and dispatch_dtype.itemsize == 32
 class AgrConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("slab_rows", C.c_uint64), ("table_slots", C.c_uint64),
                 ("max_agents", C.c_uint32), ("max_batch", C.c_uint32), ("log_entries", C.c_uint64),
-                ("id_secret", C.c_uint64), ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
+                ("id_secret", C.c_uint64), ("vslab_bytes", C.c_uint64), ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AgrStats(C.Structure):
@@ -55,7 +57,7 @@ class AgrSynth(C.Structure):
 ABI_SYMBOLS = [
     "agr_create", "agr_destroy", "agr_abi_version", "agr_last_error", "agr_strerror",
     "agr_set_agent_state", "agr_drop_agent", "agr_agent_slot",
-    "agr_ingest", "agr_ingest_ex", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
+    "agr_ingest", "agr_ingest_ex", "agr_ingest_var", "agr_replay_scan_var", "agr_get_record_var", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
@@ -95,6 +97,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_agent_slot": (i32, [vp, C.c_char_p]),
         "agr_ingest": (i32, [vp, vp, u32, vp, C.POINTER(u64)]),
         "agr_ingest_ex": (i32, [vp, vp, u32, vp, vp, C.POINTER(u64)]),
+        "agr_ingest_var": (i32, [vp, vp, vp, u32, vp, vp, C.POINTER(u64)]),
+        "agr_replay_scan_var": (i32, [vp, vp, vp, u64, vp, u32, C.POINTER(u32), C.POINTER(u64)]),
+        "agr_get_record_var": (i32, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]),
         "agr_complete": (i32, [vp, vp, u32, vp]),
         "agr_replay_scan": (i32, [vp, vp, vp, u32, C.POINTER(u32)]),
         "agr_pending": (i32, [vp, C.c_char_p, vp, u32, C.POINTER(u32)]),
@@ -207,11 +212,12 @@ class Engine:
     """One shard (one GPU) of the request engine.  Thin wrapper: every method is one C-ABI call."""
 
     def __init__(self, *, device=-1, slab_rows=1 << 16, max_agents=1024, max_batch=0, flags=0, table_slots=0,
-                 log_entries=0, k1_variant=0, id_secret=0):
+                 log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0):
         self.lib = load_library()
         cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
-                        log_entries, id_secret, k1_variant, 0)
+                        log_entries, id_secret, vslab_bytes, k1_variant, 0)
         self.mint = bool(flags & K.AGR_CFG_MINT_IDS)
+        self.varlen = bool(flags & K.AGR_CFG_VARLEN)
         h = C.c_void_p()
         _check(self.lib, self.lib.agr_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -315,6 +321,39 @@ class Engine:
 
     def pinned(self, n: int, dtype=record_dtype) -> PinnedArray:
         return PinnedArray(self.lib, n, dtype)
+
+    # ---- variable-length records (AGR_CFG_VARLEN)
+    def ingest_var(self, blob: np.ndarray, offsets: np.ndarray):
+        assert blob.dtype == np.uint8 and offsets.dtype == np.uint32
+        n = len(offsets) - 1
+        out = np.zeros(n, dtype=verdict_dtype)
+        ids = np.zeros((n, 16), dtype=np.uint8)
+        first = C.c_uint64()
+        _check(self.lib, self.lib.agr_ingest_var(self.h, _ptr(blob), _ptr(offsets), n, _ptr(out), _ptr(ids), C.byref(first)))
+        return out, ids, first.value
+
+    def replay_scan_var(self, cap: int = 1 << 14, blob_cap: int = 1 << 24):
+        while True:
+            disp = np.zeros(cap, dtype=dispatch_dtype)
+            blob = np.zeros(blob_cap, dtype=np.uint8)
+            offs = np.zeros(cap + 1, dtype=np.uint64)
+            n, nb = C.c_uint32(), C.c_uint64()
+            rc = self.lib.agr_replay_scan_var(self.h, _ptr(disp), _ptr(blob), blob_cap, _ptr(offs), cap, C.byref(n), C.byref(nb))
+            if rc == K.AGR_ECAP:
+                cap, blob_cap = max(cap, int(n.value)), max(blob_cap, int(nb.value) + 16)
+                continue
+            _check(self.lib, rc)
+            return disp[: n.value], blob[: nb.value], offs[: n.value + 1]
+
+    def get_record_var(self, agent_id: str, request_id: bytes) -> Optional[np.ndarray]:
+        out = np.zeros(8192, dtype=np.uint8)
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        ln = C.c_uint32()
+        rc = self.lib.agr_get_record_var(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), _ptr(out), 8192, C.byref(ln))
+        if rc == K.AGR_ENOTFOUND:
+            return None
+        _check(self.lib, rc)
+        return out[: ln.value]
 
     # ---- K4 (multi-GPU exchange)
     def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:

@@ -42,6 +42,11 @@ __device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsig
     return ~0ULL;
 }
 
+// address of a row's record: fixed 512 B stride, or the byte offset kept per row in variable-length mode
+__device__ __forceinline__ const uint8_t* rec_ptr(const agr_dev& d, uint32_t rid) {
+    return d.voff ? d.slab + d.voff[rid] : d.slab + (size_t)rid * AGR_REC;
+}
+
 // (agent slot is checked by the callers) request id -> row holding the record stored under it, or AGR_RID_NONE.
 // Hash mode: probe the dedupe index.  Mint mode: decode the row from the id and accept only an exact 128-bit match.
 __device__ __forceinline__ uint32_t lookup_rid(const agr_dev& d, unsigned long long lo, unsigned long long hi) {

@@ -82,6 +82,12 @@ struct agr_handle {
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
     alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
+    // variable-length mode
+    uint64_t vused = 0, vcap = 0;
+    uint32_t* d_voffsets = nullptr; uint32_t* d_tile_first = nullptr;   // per-batch offsets [max_batch+1], tile index
+    uint32_t* h_voffsets = nullptr;
+    uint32_t* d_lens = nullptr; unsigned long long* d_goffs = nullptr;  // gather scratch [out_cap]
+    uint32_t lens_cap = 0;
     // multi-GPU exchange (K4)
     ncclComm_t comm = nullptr; int rank = 0, world = 1;
     uint8_t* d_stage = nullptr;                // incoming batch before binning [max_batch * 512]
@@ -206,7 +212,20 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     agr_dev& d = h->d;
-    TRY(dev_alloc(h, &d.slab, (size_t)c.slab_rows * AGR_REC, false));
+    const bool varlen = (c.flags & AGR_CFG_VARLEN) != 0;
+    if (varlen) {
+        if (c.vslab_bytes == 0) c.vslab_bytes = 1024ull * c.slab_rows;
+        h->cfg = c;
+        h->vcap = c.vslab_bytes;
+        TRY(dev_alloc(h, &d.slab, (size_t)c.vslab_bytes + AGR_VT_MAXREC, false));
+        TRY(dev_alloc(h, &d.voff, c.slab_rows, true));
+        TRY(dev_alloc(h, &d.vlen, c.slab_rows, true));
+        TRY(dev_alloc(h, &h->d_voffsets, (size_t)c.max_batch + 1, false));
+        TRY(host_alloc(h, &h->h_voffsets, (size_t)c.max_batch + 1));
+        TRY(dev_alloc(h, &h->d_tile_first, (size_t)(((size_t)c.max_batch * AGR_VT_MAXREC) / AGR_VT_TILE + 8), false));
+    } else {
+        TRY(dev_alloc(h, &d.slab, (size_t)c.slab_rows * AGR_REC, false));
+    }
     TRY(dev_alloc(h, &d.state, c.slab_rows, true));
     TRY(dev_alloc(h, &d.route, c.slab_rows, true));
     TRY(dev_alloc(h, &d.aux, c.slab_rows, true));
@@ -227,7 +246,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
     d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
     d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
-    if ((c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
+    if (!varlen && (c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags & 0xffffu;
     if (c.k1_variant & 0x10u) d.cfg_flags |= AGR_CFGI_SPLIT_INDEX;
@@ -449,6 +468,7 @@ int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* o
 
 int agr_ingest_ex(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
+    if (h->cfg.flags & AGR_CFG_VARLEN) return fail(AGR_EINVAL, "variable-length engine: use agr_ingest_var");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
@@ -598,6 +618,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
 
 int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t cap, uint32_t* n) {
     if (!h || !n) return fail(AGR_EINVAL, "NULL argument");
+    if ((h->cfg.flags & AGR_CFG_VARLEN) && recs) return fail(AGR_EINVAL, "variable-length engine: use agr_replay_scan_var to gather records");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     *n = 0;
@@ -703,6 +724,138 @@ int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id
     CK(cudaMemcpyAsync(h->h_gather, h->d_gather, AGR_REC, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     memcpy(out, h->h_gather, AGR_REC);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ variable-length records
+int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, uint32_t n, agr_verdict* out, uint8_t (*ids)[16],
+                   uint64_t* first_rid) {
+    if (!h || (n && (!blob || !offsets))) return fail(AGR_EINVAL, "NULL argument");
+    if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    uint64_t first = 0;
+    if (n == 0) { if (first_rid) *first_rid = h->rows_used; return 0; }
+    const uint64_t bytes = offsets[n];
+    if (offsets[0] != 0) return fail(AGR_EINVAL, "offsets[0] must be 0");
+    for (uint32_t i = 0; i < n; ++i) {                           // host-side shape check (lengths are part of the wire format)
+        const uint32_t len = offsets[i + 1] - offsets[i];
+        if (offsets[i + 1] < offsets[i] || (len & 15u) || len < AGR_HEADER_BYTES || len > AGR_VAR_MAX_RECORD)
+            return fail(AGR_EINVAL, "record " + std::to_string(i) + ": length must be a multiple of 16 in [96, 8192]");
+    }
+    if (h->vused + bytes > h->vcap) return fail(AGR_ENOSPC, "byte slab full");
+    TRY(reserve_rows_locked(h, n, &first));
+    if (first_rid) *first_rid = first;
+    const uint64_t base = h->vused;
+    h->vused += bytes;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->d.slab + base, blob, bytes, cudaMemcpyHostToDevice, st));
+    if (is_pinned(offsets)) CK(cudaMemcpyAsync(h->d_voffsets, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    else { memcpy(h->h_voffsets, offsets, ((size_t)n + 1) * 4); CK(cudaMemcpyAsync(h->d_voffsets, h->h_voffsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st)); }
+    h->d.rows_hi = (uint32_t)h->rows_used;
+    CK(cudaMemsetAsync(h->d.dupfix, 0, 8, st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->cfg.flags & AGR_CFG_TIMING) {
+        if (h->tev.empty()) { h->tev.resize(2 * AGR_TIMING_RING); for (auto& e : h->tev) CK(cudaEventCreate(&e)); }
+        const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
+        e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
+        CK(cudaEventRecord(e0, st));
+    }
+    CK(agr_launch_k1_var(h->d, h->d.slab + base, h->d_voffsets, n, bytes, h->d_tile_first, (uint32_t)first, base, h->sm_count, st));
+    if (e1) CK(cudaEventRecord(e1, st));
+    agr_launch_k1_post(h->d, (uint32_t)first, n, h->sm_count, st, out ? h->d_verdicts : nullptr, ids ? h->d_ids : nullptr);
+    h->k1_launches += 3;
+    CK(cudaGetLastError());
+    if (out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, st));
+    if (ids) CK(cudaMemcpyAsync(h->h_ids, h->d_ids, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (out) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
+    if (ids) memcpy(ids, h->h_ids, (size_t)n * 16);
+    return 0;
+}
+
+// packs the variable-length records of rows d_out_rid[0..total) into the caller's blob
+static int gather_var_locked(agr_handle* h, uint32_t total, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint64_t* blob_bytes) {
+    if (total > h->lens_cap) {
+        uint32_t ncap = std::max<uint32_t>(total, 1024);
+        TRY(dev_alloc(h, &h->d_lens, ncap, false));
+        TRY(dev_alloc(h, &h->d_goffs, (size_t)ncap + 1, false));
+        h->lens_cap = ncap;
+    }
+    agr_launch_var_lens(h->d, h->d_out_rid, total, h->d_lens, h->stream);
+    std::vector<uint32_t> lens(total);
+    CK(cudaMemcpyAsync(lens.data(), h->d_lens, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<unsigned long long> offs((size_t)total + 1);
+    offs[0] = 0;
+    for (uint32_t j = 0; j < total; ++j) offs[j + 1] = offs[j] + lens[j];
+    *blob_bytes = offs[total];
+    if (offsets) for (uint32_t j = 0; j <= total; ++j) offsets[j] = offs[j];
+    if (!blob) return 0;
+    if (offs[total] > blob_cap) return fail(AGR_ECAP, "blob too small");
+    TRY(ensure_gather(h, (size_t)offs[total] + 16));
+    CK(cudaMemcpyAsync(h->d_goffs, offs.data(), ((size_t)total + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    agr_launch_var_copy(h->d, h->d_out_rid, total, h->d_goffs, h->d_gather, h->stream);
+    h->k3_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)offs[total], cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(blob, h->h_gather, (size_t)offs[total]);
+    return 0;
+}
+
+int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint32_t cap,
+                        uint32_t* n, uint64_t* blob_bytes) {
+    if (!h || !n || !blob_bytes) return fail(AGR_EINVAL, "NULL argument");
+    if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    *n = 0; *blob_bytes = 0;
+    h->replay_scans++;
+    uint32_t total = 0;
+    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    *n = total;
+    if (total > cap) return fail(AGR_ECAP, "dispatch array too small");
+    h->replay_dispatched += total;
+    if (total == 0) return 0;
+    if (out) {
+        TRY(ensure_gather(h, (size_t)total * 32));
+        agr_launch_k3_gather(h->d, h->d_out_rid, h->d_out_slot, total, nullptr, h->d_gather, nullptr, h->stream);
+        h->k3_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)total * 32, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(out, h->h_gather, (size_t)total * 32);
+    }
+    return gather_var_locked(h, total, blob, blob_cap, offsets, blob_bytes);
+}
+
+int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
+    if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
+    if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return fail(AGR_ENOTFOUND, "request not found");
+    agr_dop& op = h->h_ops[0];
+    memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
+    op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
+    CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    h->d.rows_hi = (uint32_t)h->rows_used;
+    agr_launch_resolve(h->d, h->k2, 1, h->stream);
+    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
+    TRY(ensure_out(h, 1));
+    CK(cudaMemcpyAsync(h->d_out_rid, h->k2.hrid, 4, cudaMemcpyDeviceToDevice, h->stream));
+    uint64_t bytes = 0;
+    std::vector<uint8_t> tmp(AGR_VAR_MAX_RECORD);
+    uint64_t offs[2];
+    TRY(gather_var_locked(h, 1, tmp.data(), tmp.size(), offs, &bytes));
+    *len = (uint32_t)bytes;
+    if (bytes > cap || !out) return out ? fail(AGR_ECAP, "output buffer too small") : 0;
+    memcpy(out, tmp.data(), bytes);
     return 0;
 }
 

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
         uint32_t r = d.route[rid];
         uint32_t vf = rt_flags(r);
         if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
-            uint4 t = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + AGR_OFF_REPLAY_OF);
+            uint4 t = ldg_nc_v4(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF);
             const uint32_t orid = lookup_rid(d, pack64(t.x, t.y), pack64(t.z, t.w));
             if (orid != AGR_RID_NONE && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
                 r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
             }
         }
         if (dupfix != 0u && (vf & (AGR_VF_STORED | AGR_VF_DUP_ID))) {
-            const uint4 h0 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+            const uint4 h0 = ldg_nc_v4(rec_ptr(d, rid));
             const unsigned long long idx = table_find(d, pack64(h0.x, h0.y), pack64(h0.z, h0.w));
             const uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : ~__ldcg(&d.table[idx].inv_rid);
             uint32_t code = rt_code(r);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
                 d.state[rid] = 0;
                 stored_delta--;
             } else if ((vf & AGR_VF_DUP_ID) && owner == rid && (pack64(h0.x, h0.y) | pack64(h0.z, h0.w)) != 0ULL) {   // promote
-                const uint4 h5 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC + 80);
+                const uint4 h5 = ldg_nc_v4(rec_ptr(d, rid) + 80);
                 uint32_t maxr = (h5.y >> 16) & 0xffu;
                 if (maxr == 0) maxr = 3;
                 uint32_t st = AGR_ST_PENDING | ST_INQ | ST_STORED | (maxr << ST_MAX_SHIFT);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
                 agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
                 ids[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
             } else {
-                ids[i] = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+                ids[i] = ldg_nc_v4(rec_ptr(d, rid));
             }
         }
     }
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) k1_index(const agr_dev d, const uint32_t 
         uint32_t r = d.route[rid];
         uint32_t vf = rt_flags(r);
         if (vf & AGR_VF_STORED) {
-            const uint4 h0 = ldg_nc_v4(d.slab + (size_t)rid * AGR_REC);
+            const uint4 h0 = ldg_nc_v4(rec_ptr(d, rid));
             const u128 key = make_u128(pack64(h0.x, h0.y), pack64(h0.z, h0.w));
             unsigned long long idx = agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask;
             bool dup = false;
@@ -216,6 +216,10 @@ static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
 
 cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t pf_dist,
                               int sm_count, cudaStream_t st);
+
+void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids) {
+    if (n) k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
+}
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
                    cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, void* verdicts, void* ids) {
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(256) k3_gather(const agr_dev d, const uint32_t
     const int lane = threadIdx.x & 31;
     if (w >= n) return;
     const uint32_t rid = rids[w];
-    const uint8_t* src = d.slab + (size_t)rid * AGR_REC;
+    const uint8_t* src = rec_ptr(d, rid);      // (variable-length rows: the first 512 B; use the *_var gathers for all of it)
     uint4 v = ldg_nc_v4(src + lane * 16);
     if (lane == 0 && (d.cfg_flags & AGR_CFG_MINT_IDS)) {          // Request.ID = what the engine minted for this row
         unsigned long long lo, hi;

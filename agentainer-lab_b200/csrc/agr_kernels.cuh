@@ -30,6 +30,8 @@ struct agr_dev {
     unsigned long long log_cap;
     uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
+    unsigned long long* voff;  // variable-length mode: byte offset of row's record in the slab (nullptr = fixed 512 B rows)
+    uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
     uint32_t shard_id, id_gen;
     uint32_t rows_hi;          // rows handed out so far (bound for decoded row ids)
@@ -79,6 +81,14 @@ struct agr_k3_params {
 // 5 = LSU kernel (k1_ingest_v0, no TMA).  Bit 0x10 = split mode: stream kernel + k1_index kernel.
 #define AGR_K1_LSU 5u
 // The optional events bracket the main (dominant) kernel.
+// K1 for variable-length records (agr_k1_var.cu) and the matching gathers
+cudaError_t agr_launch_k1_var(const agr_dev& d, const uint8_t* blob, const uint32_t* off, uint32_t n, unsigned long long blob_bytes,
+                              uint32_t* tile_first, uint32_t first_rid, unsigned long long blob_base, int sm_count, cudaStream_t st);
+void agr_launch_var_lens(const agr_dev& d, const uint32_t* rids, uint32_t n, uint32_t* lens, cudaStream_t st);
+void agr_launch_var_copy(const agr_dev& d, const uint32_t* rids, uint32_t n, const unsigned long long* out_off, uint8_t* out, cudaStream_t st);
+#define AGR_VT_TILE 8192u
+#define AGR_VT_MAXREC 8192u
+
 // K4: shard binning / stable pack for the multi-GPU exchange
 struct agr_k4_params {
     const uint8_t* items;      // n items of item_bytes each (records: 512, outcome descriptors: 32)
@@ -101,6 +111,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */,
                    void* ids = nullptr /* device u8[n][16]: Request.ID per record, written by k1_post */);
+void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);
 int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
 void agr_launch_k2_prepare(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, agr_dop* ops, uint32_t n, cudaStream_t st);
 void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);

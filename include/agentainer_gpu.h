@@ -93,6 +93,7 @@ typedef struct agr_record {
                                        exact invertible function of the record's row, agr_record.request_id of fresh records is
                                        ignored on input, callers read the ids with agr_mint_ids.  No dedupe-index table exists in
                                        this mode (lookups decode the row and verify all 128 bits). */
+#define AGR_CFG_VARLEN        0x10u /* variable-length records (BASELINE config 5): byte-addressed slab, agr_ingest_var / *_var reads */
 #define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
 #define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */
 #define AGR_CFG_SKIP_INFLIGHT 0x2u  /* EXTENSION, off in parity mode: replay scan skips records whose forward is still in flight (fixes Q16) */
@@ -106,6 +107,7 @@ typedef struct agr_config {
     uint32_t max_batch;      /* largest n accepted by one agr_ingest / agr_complete; 0 = 1<<20 */
     uint64_t log_entries;    /* capacity of the completed and failed logs; 0 = 2*slab_rows */
     uint64_t id_secret;      /* AGR_CFG_MINT_IDS: key of the id permutation; 0 = a fixed default */
+    uint64_t vslab_bytes;    /* AGR_CFG_VARLEN: capacity of the byte slab; 0 = 1024 * slab_rows */
     uint32_t k1_variant;     /* 0 = default K1 kernel (TMA, 14 warps x 1 stage, fused index); 1..4 TMA shapes, 5 = LSU kernel,
                                 | 0x10 = split stream / index kernels — alternates kept for A/B measurement */
     uint32_t reserved;
@@ -216,6 +218,22 @@ int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id
  * (completed keeps the Q7 duplicates). */
 enum { AGR_LIST_PENDING = 0, AGR_LIST_COMPLETED = 1, AGR_LIST_FAILED = 2 };
 int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16], uint32_t cap, uint32_t* n);
+
+/* ------------------------------------------------ variable-length records (AGR_CFG_VARLEN) */
+/* A variable-length record is the 96-byte header of agr_record (same fields, same offsets) followed by its payload
+ * path | headers | body, zero padded to a multiple of 16 bytes; its stored length is 96 + round16(path_len + hdr_len +
+ * body_len) <= AGR_VAR_MAX_RECORD.  A batch is one contiguous blob of such records plus offsets[0..n] (bytes from the
+ * start of the blob, offsets[n] = blob length; every offset a multiple of 16).  Semantics are those of agr_ingest_ex. */
+#define AGR_VAR_MAX_RECORD 8192u
+int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, uint32_t n, agr_verdict* out,
+                   uint8_t (*ids)[16], uint64_t* first_rid);
+/* agr_replay_scan for variable-length records: dispatch entries as usual; if blob != NULL the stored records are packed
+ * into blob (capacity blob_cap bytes) with offsets[0..*n] (live status / retry / response patched into the headers).
+ * AGR_ECAP if either capacity is too small (*n and *blob_bytes hold what is needed). */
+int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint32_t cap,
+                        uint32_t* n, uint64_t* blob_bytes);
+/* storage.Get for a variable-length record: copies it into out (cap bytes), *len = stored length. */
+int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
 
 /* ------------------------------------------------------------------- stats */
 typedef struct agr_stats {

@@ -147,6 +147,29 @@ def make_records(reqs: List[Req]) -> np.ndarray:
     return recs
 
 
+def make_var_batch(reqs: List[Req]):
+    """Variable-length wire form (AGR_CFG_VARLEN): 96 B header + payload padded to 16 B per record, one blob + offsets."""
+    from agentainer_lab_b200 import header_dtype, constants as K
+    parts, offsets = [], [0]
+    for r in reqs:
+        path = r.path.encode()
+        hdrs = "".join(f"{k}: {v}\n" for k, v in sorted(r.headers.items())).encode()
+        payload = path + hdrs + r.body
+        h = np.zeros(1, dtype=header_dtype)
+        h["request_id"] = np.frombuffer(r.rid, dtype=np.uint8)
+        h["replay_of"] = np.frombuffer(r.replay_of if r.replay else ZERO16, dtype=np.uint8)
+        h["agent_id"] = r.agent_id.encode()
+        h["seq"] = r.seq
+        h["flags"] = (K.AGR_F_REPLAY if r.replay else 0) | (K.METHOD_CODES[r.method] << K.AGR_F_METHOD_SHIFT)
+        h["path_len"], h["hdr_len"], h["body_len"] = len(path), len(hdrs), len(r.body)
+        h["status"], h["max_retries"] = K.AGR_ST_PENDING, 3
+        pad = (-len(payload)) % 16
+        parts.append(h.tobytes() + payload + bytes(pad))
+        offsets.append(offsets[-1] + len(parts[-1]))
+    blob = np.frombuffer(b"".join(parts), dtype=np.uint8).copy() if parts else np.zeros(0, dtype=np.uint8)
+    return blob, np.array(offsets, dtype=np.uint32)
+
+
 def _outcome(outs: list, rid: bytes, agent_id: str, kind: int, http: int = 0, seq: int = 0):
     outs.append((rid, agent_id, kind, http, seq))
 
@@ -171,6 +194,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
     # AGR_CFG_MINT_IDS: the engine mints the ids (like StoreRequest does); the scenario's symbolic ids are mapped to
     # them so that the oracle (which takes its ids from the stream) and the engine can be compared id for id
     mint = bool(getattr(eng, "mint", False))
+    varlen = bool(getattr(eng, "varlen", False))
     s2e: Dict[bytes, bytes] = {}
     e2s: Dict[bytes, bytes] = {}
 
@@ -186,14 +210,21 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
             take = len(pend_reqs) if rng is None else int(rng.integers(1, len(pend_reqs) + 1))
             take = min(take, max_batch)
             chunk, pend_reqs = pend_reqs[:take], pend_reqs[take:]
-            recs = make_records([r for r, _ in chunk])
+            if varlen:
+                import dataclasses
+                reqs = [dataclasses.replace(r, replay_of=tin(r.replay_of)) if (mint and r.replay) else r for r, _ in chunk]
+                blob, offs = make_var_batch(reqs)
+                verdicts, ids, first_rid = eng.ingest_var(blob, offs)
+            else:
+                recs = make_records([r for r, _ in chunk])
+                if mint:
+                    for i, (r, _) in enumerate(chunk):
+                        if r.replay:
+                            recs[i]["replay_of"] = np.frombuffer(tin(r.replay_of), dtype=np.uint8)
+                verdicts, first_rid = eng.ingest(recs)
+                if mint:
+                    ids = eng.mint_ids(first_rid, len(chunk))
             if mint:
-                for i, (r, _) in enumerate(chunk):
-                    if r.replay:
-                        recs[i]["replay_of"] = np.frombuffer(tin(r.replay_of), dtype=np.uint8)
-            verdicts, first_rid = eng.ingest(recs)
-            if mint:
-                ids = eng.mint_ids(first_rid, len(chunk))
                 for i, ((r, _), v) in enumerate(zip(chunk, verdicts)):
                     if int(v["flags"]) & K.AGR_VF_STORED:
                         s2e[r.rid] = bytes(ids[i]); e2s[bytes(ids[i])] = r.rid
@@ -225,13 +256,23 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
             eng.drop_agent(e[1])
         elif e[0] == "tick":
             backends, flip = e[1], e[2]
-            disp, recs = eng.replay_scan(with_records=True)
+            if varlen:
+                from agentainer_lab_b200 import header_dtype
+                disp, vblob, voffs = eng.replay_scan_var()
+                vblob = vblob.copy()
+                for j in range(len(disp)):          # replayRequest: same record, replay-flagged, ID in the tracking header
+                    hv = vblob[int(voffs[j]): int(voffs[j]) + 96].view(header_dtype)
+                    hv["flags"] |= K.AGR_F_REPLAY
+                    hv["replay_of"] = hv["request_id"]
+                recs = disp                          # only its length / request ids are used below
+            else:
+                disp, recs = eng.replay_scan(with_records=True)
+                # replayRequest (replay_worker.go:120-163): same record, replay-flagged, ID in the tracking header
+                recs = recs.copy()
+                recs["flags"] |= K.AGR_F_REPLAY
+                recs["replay_of"] = recs["request_id"]
             order = [(slot_name[int(d["agent_slot"])], tout(bytes(d["request_id"])).hex()) for d in disp]
             obs.ticks.append(order)
-            # replayRequest (replay_worker.go:120-163): same record, replay-flagged, ID in the tracking header
-            recs = recs.copy()
-            recs["flags"] |= K.AGR_F_REPLAY
-            recs["replay_of"] = recs["request_id"]
             cuts = [0, len(recs)]
             if flip is not None and 0 < flip[0] < len(recs):
                 cuts = [0, flip[0], len(recs)]
@@ -241,7 +282,11 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
                 seg = np.ascontiguousarray(recs[a:b])
                 if len(seg) == 0:
                     continue
-                verdicts, _ = eng.ingest(seg)
+                if varlen:
+                    lo = int(voffs[a])
+                    verdicts, _, _ = eng.ingest_var(np.ascontiguousarray(vblob[lo: int(voffs[b])]), (voffs[a: b + 1] - voffs[a]).astype(np.uint32))
+                else:
+                    verdicts, _ = eng.ingest(seg)
                 outs = []
                 for rec, v, (agent_id, rid_hex) in zip(seg, verdicts, order[a:b]):
                     rid = bytes(rec["request_id"])
@@ -272,7 +317,12 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
     for a in all_agents(events):
         obs.lists[a] = {names[w]: [tout(bytes(x)).hex() for x in eng.list(a, w)] for w in (0, 1, 2)}
     for a, rid in all_fresh(events):
-        rec = eng.get_record(a, tin(rid)) if (not mint or rid in s2e) else None
+        if varlen:
+            from agentainer_lab_b200 import header_dtype
+            raw = eng.get_record_var(a, tin(rid)) if (not mint or rid in s2e) else None
+            rec = raw[:96].view(header_dtype)[0] if raw is not None else None
+        else:
+            rec = eng.get_record(a, tin(rid)) if (not mint or rid in s2e) else None
         if rec is not None:
             obs.records[(a, rid.hex())] = (K.STATUS_NAMES[int(rec["status"])], int(rec["retry_count"]), int(rec["resp_status"]))
     return obs
