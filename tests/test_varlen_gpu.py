@@ -91,7 +91,8 @@ def test_stored_bytes_checksum_and_tile_edges():
             assert len(raw) == len(src) and raw[96:].tobytes() == src[96:].tobytes() and raw[:84].tobytes() == src[:84].tobytes()
         eng.set_agent_state("agent-1", "running")
         disp, vblob, voffs = eng.replay_scan_var()
-        exp_idx = [i for i in range(len(reqs)) if i % 3]
+        # agent-1's queued records, then agent-2's forwarded-but-unanswered ones (still pending: Q1 / Q16), FIFO inside each
+        exp_idx = [i for i in range(len(reqs)) if i % 3] + [i for i in range(len(reqs)) if i % 3 == 0]
         assert [bytes(d["request_id"]) for d in disp] == [reqs[i].rid for i in exp_idx]
         for j in (0, 1, len(exp_idx) // 2, len(exp_idx) - 1):
             i = exp_idx[j]
