@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -82,6 +83,15 @@ struct agr_handle {
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
     alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
+    // flat-combining front-end for concurrent small ingests (AGR_CFG_COMBINE)
+    std::mutex cmu; std::condition_variable ccv;
+    agr_record* c_ring = nullptr;              // pinned [AGR_COMBINE_RING]
+    agr_verdict* c_verd = nullptr; uint8_t* c_ids = nullptr; int32_t* c_rc = nullptr; uint64_t* c_rid = nullptr;
+    uint64_t c_head = 0, c_taken = 0, c_done = 0;   // slots assigned / handed to a leader / finished
+    uint64_t c_low = 0;                        // every slot below has been collected by its owner (ring space is [c_low, c_head))
+    std::vector<uint8_t> c_flag;               // [AGR_COMBINE_RING] collected marks for out-of-order owners
+    bool c_leader = false;
+    uint64_t c_batches = 0, c_records = 0;
     // variable-length mode
     uint64_t vused = 0, vcap = 0;
     uint32_t* d_voffsets = nullptr; uint32_t* d_tile_first = nullptr;   // per-batch offsets [max_batch+1], tile index
@@ -104,6 +114,8 @@ struct agr_handle {
     bool op_timed[2] = {false, false};
 };
 #define AGR_TIMING_RING 1024
+#define AGR_COMBINE_RING 16384u
+#define AGR_COMBINE_MAX 32u
 
 template <typename T>
 static int dev_alloc(agr_handle* h, T** p, size_t count, bool zero) {
@@ -265,6 +277,14 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->d_outs, c.max_batch, false));
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
+    if (c.flags & AGR_CFG_COMBINE) {
+        TRY(host_alloc(h, &h->c_ring, (size_t)AGR_COMBINE_RING));
+        TRY(host_alloc(h, &h->c_verd, (size_t)AGR_COMBINE_RING));
+        TRY(host_alloc(h, &h->c_ids, (size_t)AGR_COMBINE_RING * 16));
+        TRY(host_alloc(h, &h->c_rc, (size_t)AGR_COMBINE_RING));
+        TRY(host_alloc(h, &h->c_rid, (size_t)AGR_COMBINE_RING));
+        h->c_flag.assign(AGR_COMBINE_RING, 0);
+    }
     TRY(dev_alloc(h, &h->d_ops, c.max_batch, false));
     h->k2.ops = h->d_ops;
     TRY(dev_alloc(h, &h->k2.nxt, c.max_batch, false));
@@ -466,11 +486,69 @@ int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* o
     return agr_ingest_ex(h, recs, n, out, nullptr, first_rid);
 }
 
+static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid);
+
+// Flat combining: the ring order is the event order.  A caller appends its records; if nobody leads, it becomes the leader:
+// it takes everything queued so far (its own records included), runs it as ONE batch through the normal path, publishes the
+// verdicts, and steps down as soon as its own records are done (another waiter then leads the next batch).
+static int combine_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
+    std::unique_lock<std::mutex> lk(h->cmu);
+    h->ccv.wait(lk, [&] { return h->c_head + n - h->c_low <= AGR_COMBINE_RING; });
+    const uint64_t my = h->c_head;
+    h->c_head += n;
+    for (uint32_t i = 0; i < n; ++i) h->c_ring[(my + i) % AGR_COMBINE_RING] = recs[i];
+    while (h->c_done < my + n) {
+        if (h->c_leader) { h->ccv.wait(lk); continue; }
+        h->c_leader = true;
+        const uint64_t from = h->c_taken, to = h->c_head;
+        h->c_taken = to;
+        lk.unlock();
+        for (uint64_t a = from; a < to;) {                      // at most two contiguous pieces of the ring
+            const uint64_t pos = a % AGR_COMBINE_RING;
+            const uint32_t cn = (uint32_t)std::min<uint64_t>(to - a, AGR_COMBINE_RING - pos);
+            uint64_t first = 0;
+            int rc;
+            {
+                std::lock_guard<std::mutex> hl(h->mu);
+                rc = cudaSetDevice(h->device) == cudaSuccess
+                         ? ingest_ex_locked(h, h->c_ring + pos, cn, h->c_verd + pos, (uint8_t(*)[16])(h->c_ids + pos * 16), &first)
+                         : AGR_ECUDA;
+            }
+            for (uint32_t i = 0; i < cn; ++i) { h->c_rc[pos + i] = rc; h->c_rid[pos + i] = first + i; }
+            a += cn;
+        }
+        lk.lock();
+        h->c_batches++; h->c_records += to - from;
+        h->c_done = to;
+        h->c_leader = false;
+        h->ccv.notify_all();
+    }
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t pos = (my + i) % AGR_COMBINE_RING;
+        if (h->c_rc[pos] < 0) rc = h->c_rc[pos];
+        if (out) out[i] = h->c_verd[pos];
+        if (ids) memcpy(ids[i], h->c_ids + pos * 16, 16);
+    }
+    if (first_rid) *first_rid = h->c_rid[my % AGR_COMBINE_RING];   // rows of one caller are consecutive (appended under the lock)
+    if (rc < 0) g_err = "combined ingest failed";
+    for (uint32_t i = 0; i < n; ++i) h->c_flag[(my + i) % AGR_COMBINE_RING] = 1;
+    while (h->c_low < h->c_done && h->c_flag[h->c_low % AGR_COMBINE_RING]) { h->c_flag[h->c_low % AGR_COMBINE_RING] = 0; h->c_low++; }
+    lk.unlock();
+    h->ccv.notify_all();                                          // ring space was released
+    return rc;
+}
+
 int agr_ingest_ex(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     if (h->cfg.flags & AGR_CFG_VARLEN) return fail(AGR_EINVAL, "variable-length engine: use agr_ingest_var");
+    if ((h->cfg.flags & AGR_CFG_COMBINE) && n >= 1 && n <= AGR_COMBINE_MAX) return combine_ingest(h, recs, n, out, ids, first_rid);
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
+    return ingest_ex_locked(h, recs, n, out, ids, first_rid);
+}
+
+static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     uint64_t first = 0;
     TRY(reserve_rows_locked(h, n, &first));

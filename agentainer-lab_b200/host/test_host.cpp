@@ -1,6 +1,7 @@
 // test_host.cpp — drives the C++ mirror of requests.Manager / ReplayWorker exactly as the Go server would:
 // KAT-A, KAT-B, KAT-C through the mirrored method names, then 8 threads calling Decide/StoreResponse concurrently
 // (one goroutine per HTTP request in the reference).  Exit code 0 == all checks passed.  Needs a B200.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <thread>
@@ -19,9 +20,9 @@ static std::vector<std::string> list_ids(agr_handle* h, const char* agent, int w
     return out;
 }
 
-static int run(bool mint) {
-    agr_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = 0; cfg.slab_rows = 1 << 16; cfg.max_agents = 64; cfg.max_batch = 4096;
-    cfg.flags = AGR_CFG_PERSISTENCE | (mint ? AGR_CFG_MINT_IDS : 0u);
+static int run(bool mint, bool combine) {
+    agr_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = 0; cfg.slab_rows = 1 << 18; cfg.max_agents = 64; cfg.max_batch = 1 << 15;
+    cfg.flags = AGR_CFG_PERSISTENCE | (mint ? AGR_CFG_MINT_IDS : 0u) | (combine ? AGR_CFG_COMBINE : 0u);
     agr_handle* h = nullptr;
     if (agr_create(&cfg, &h) < 0) { printf("agr_create: %s\n", agr_last_error()); return 2; }
     Manager mgr(h, mint);
@@ -69,11 +70,13 @@ static int run(bool mint) {
     CHECK(list_ids(h, B, AGR_LIST_PENDING).empty());
     CHECK((list_ids(h, B, AGR_LIST_COMPLETED) == std::vector<std::string>{ids[0], ids[0], ids[1], ids[1], ids[2], ids[2]}));
 
-    // concurrency: 8 threads x 500 requests against a running agent, each completed by its own thread
+    // concurrency: NT threads x 500 requests against a running agent, each completed by its own thread
     const char* C = "agent-1700000000000000003";
     CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 2);
+    const int NT = combine ? 64 : 8;
     std::vector<std::thread> ths; std::atomic<int> bad{0};
-    for (int t = 0; t < 8; ++t) ths.emplace_back([&, t] {
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < NT; ++t) ths.emplace_back([&, t] {
         for (int i = 0; i < 500; ++i) {
             HttpRequest r = post; r.Path = std::string("/agent/") + C + "/chat";
             Verdict tv; Response r200; r200.StatusCode = 200;
@@ -83,17 +86,22 @@ static int run(bool mint) {
         (void)t;
     });
     for (auto& th : ths) th.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     CHECK(bad == 0);
     CHECK(list_ids(h, C, AGR_LIST_PENDING).empty());
     agr_stats st; CHECK(agr_stats_get(h, &st) == 0);
-    CHECK(st.completions == 1 + 6 + 4000 && st.completion_misses == 1);
+    CHECK(st.completions == (uint64_t)(1 + 6 + NT * 500) && st.completion_misses == 1);
+    printf("host mirror OK (%s ids%s): KAT-A/B/C + %d concurrent single-request Decide+StoreResponse round trips from %d threads, %.0f req/s, %llu K1 launches\n",
+           mint ? "engine-minted" : "caller-supplied", combine ? ", flat-combined ingest" : "", NT * 500, NT, NT * 500 / secs,
+           (unsigned long long)st.k1_launches);
     agr_destroy(h);
-    printf("host mirror OK (%s ids): KAT-A/B/C + 4000 concurrent requests\n", mint ? "engine-minted" : "caller-supplied");
     return 0;
 }
 
 int main() {
-    int rc = run(false);
+    int rc = run(false, false);
     if (rc) return rc;
-    return run(true);
+    rc = run(true, false);
+    if (rc) return rc;
+    return run(true, true);
 }

@@ -93,6 +93,9 @@ typedef struct agr_record {
                                        exact invertible function of the record's row, agr_record.request_id of fresh records is
                                        ignored on input, callers read the ids with agr_mint_ids.  No dedupe-index table exists in
                                        this mode (lookups decode the row and verify all 128 bits). */
+#define AGR_CFG_COMBINE       0x20u /* flat-combine concurrent small agr_ingest / agr_ingest_ex calls (n <= 32) into one K1 launch:
+                                       callers append to a pinned ring, the first one to arrive leads the batch, the others wait
+                                       for their verdicts; the ring order is the event order (SURVEY 8b threading) */
 #define AGR_CFG_VARLEN        0x10u /* variable-length records (BASELINE config 5): byte-addressed slab, agr_ingest_var / *_var reads */
 #define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
 #define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */
