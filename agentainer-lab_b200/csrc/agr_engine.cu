@@ -92,6 +92,12 @@ struct agr_handle {
     std::vector<uint8_t> c_flag;               // [AGR_COMBINE_RING] collected marks for out-of-order owners
     bool c_leader = false;
     uint64_t c_batches = 0, c_records = 0;
+    // the same for agr_complete
+    std::mutex kmu; std::condition_variable kcv;
+    agr_outcome* k_ring = nullptr; int32_t* k_res = nullptr; int32_t* k_rc = nullptr;
+    uint64_t k_head = 0, k_taken = 0, k_done = 0, k_low = 0;
+    std::vector<uint8_t> k_flag;
+    bool k_leader = false;
     // variable-length mode
     uint64_t vused = 0, vcap = 0;
     uint32_t* d_voffsets = nullptr; uint32_t* d_tile_first = nullptr;   // per-batch offsets [max_batch+1], tile index
@@ -284,6 +290,10 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
         TRY(host_alloc(h, &h->c_rc, (size_t)AGR_COMBINE_RING));
         TRY(host_alloc(h, &h->c_rid, (size_t)AGR_COMBINE_RING));
         h->c_flag.assign(AGR_COMBINE_RING, 0);
+        TRY(host_alloc(h, &h->k_ring, (size_t)AGR_COMBINE_RING));
+        TRY(host_alloc(h, &h->k_res, (size_t)AGR_COMBINE_RING));
+        TRY(host_alloc(h, &h->k_rc, (size_t)AGR_COMBINE_RING));
+        h->k_flag.assign(AGR_COMBINE_RING, 0);
     }
     TRY(dev_alloc(h, &h->d_ops, c.max_batch, false));
     h->k2.ops = h->d_ops;
@@ -602,10 +612,60 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
 }
 
 // ------------------------------------------------------------------------------------------ K2
+static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results);
+
+// flat combining of concurrent small agr_complete calls; same protocol as combine_ingest (ring order = event order)
+static int combine_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
+    std::unique_lock<std::mutex> lk(h->kmu);
+    h->kcv.wait(lk, [&] { return h->k_head + n - h->k_low <= AGR_COMBINE_RING; });
+    const uint64_t my = h->k_head;
+    h->k_head += n;
+    for (uint32_t i = 0; i < n; ++i) h->k_ring[(my + i) % AGR_COMBINE_RING] = outs[i];
+    while (h->k_done < my + n) {
+        if (h->k_leader) { h->kcv.wait(lk); continue; }
+        h->k_leader = true;
+        const uint64_t from = h->k_taken, to = h->k_head;
+        h->k_taken = to;
+        lk.unlock();
+        for (uint64_t a = from; a < to;) {
+            const uint64_t pos = a % AGR_COMBINE_RING;
+            const uint32_t cn = (uint32_t)std::min<uint64_t>(to - a, AGR_COMBINE_RING - pos);
+            int rc;
+            {
+                std::lock_guard<std::mutex> hl(h->mu);
+                rc = cudaSetDevice(h->device) == cudaSuccess ? complete_locked(h, h->k_ring + pos, cn, h->k_res + pos) : AGR_ECUDA;
+            }
+            for (uint32_t i = 0; i < cn; ++i) h->k_rc[pos + i] = rc;
+            a += cn;
+        }
+        lk.lock();
+        h->k_done = to;
+        h->k_leader = false;
+        h->kcv.notify_all();
+    }
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t pos = (my + i) % AGR_COMBINE_RING;
+        if (h->k_rc[pos] < 0) rc = h->k_rc[pos];
+        if (results) results[i] = h->k_res[pos];
+        h->k_flag[pos] = 1;
+    }
+    while (h->k_low < h->k_done && h->k_flag[h->k_low % AGR_COMBINE_RING]) { h->k_flag[h->k_low % AGR_COMBINE_RING] = 0; h->k_low++; }
+    if (rc < 0) g_err = "combined complete failed";
+    lk.unlock();
+    h->kcv.notify_all();
+    return rc;
+}
+
 int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
     if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
+    if ((h->cfg.flags & AGR_CFG_COMBINE) && n >= 1 && n <= AGR_COMBINE_MAX) return combine_complete(h, outs, n, results);
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
+    return complete_locked(h, outs, n, results);
+}
+
+static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     if (n == 0) return 0;
     // outcomes go to the device as they are; k2_prepare resolves the agent ids in the device agent table
