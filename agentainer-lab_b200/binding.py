@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "agr_ingest", "agr_ingest_ex", "agr_ingest_var", "agr_replay_scan_var", "agr_get_record_var", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
-    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded",
+    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_snapshot", "agr_restore", "agr_verify",
 ]
 
 _lib = None
@@ -124,6 +124,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_synth_bind_mint": (i32, [vp, C.POINTER(AgrSynth), u64]),
         "agr_agent_hash": (u64, [C.c_char_p]),
         "agr_agent_shard": (u32, [C.c_char_p, u32]),
+        "agr_snapshot": (i32, [vp, C.c_char_p]),
+        "agr_restore": (i32, [C.POINTER(AgrConfig), C.c_char_p, C.POINTER(vp)]),
+        "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
@@ -212,14 +215,17 @@ class Engine:
     """One shard (one GPU) of the request engine.  Thin wrapper: every method is one C-ABI call."""
 
     def __init__(self, *, device=-1, slab_rows=1 << 16, max_agents=1024, max_batch=0, flags=0, table_slots=0,
-                 log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0):
+                 log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0, restore_from=None):
         self.lib = load_library()
         cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
                         log_entries, id_secret, vslab_bytes, k1_variant, 0)
         self.mint = bool(flags & K.AGR_CFG_MINT_IDS)
         self.varlen = bool(flags & K.AGR_CFG_VARLEN)
         h = C.c_void_p()
-        _check(self.lib, self.lib.agr_create(C.byref(cfg), C.byref(h)))
+        if restore_from is not None:
+            _check(self.lib, self.lib.agr_restore(C.byref(cfg), restore_from.encode(), C.byref(h)))
+        else:
+            _check(self.lib, self.lib.agr_create(C.byref(cfg), C.byref(h)))
         self.h = h
         self.max_batch = cfg.max_batch
 
@@ -419,6 +425,14 @@ class Engine:
                 continue
             _check(self.lib, rc)
             return ids[: n.value]
+
+    def snapshot(self, path: str) -> None:
+        _check(self.lib, self.lib.agr_snapshot(self.h, path.encode()))
+
+    def verify(self) -> Tuple[int, int]:
+        rows, bad = C.c_uint64(), C.c_uint64()
+        _check(self.lib, self.lib.agr_verify(self.h, C.byref(rows), C.byref(bad)))
+        return rows.value, bad.value
 
     def stats(self) -> dict:
         s = AgrStats()

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>      // types only: every NCCL symbol is resolved with dlopen/dlsym at run time
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -994,6 +995,144 @@ int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t reques
     *len = (uint32_t)bytes;
     if (bytes > cap || !out) return out ? fail(AGR_ECAP, "output buffer too small") : 0;
     memcpy(out, tmp.data(), bytes);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ durability
+struct snap_header {
+    char magic[8];                 // "AGRSNAP1"
+    uint32_t flags, n_agents, shard, gen;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo;
+};
+static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
+    const size_t chunk = h->bounce_bytes;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t m = std::min(chunk, bytes - o);
+        CK(cudaMemcpyAsync(h->bounce[0], (const uint8_t*)dsrc + o, m, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (fwrite(h->bounce[0], 1, m, f) != m) return fail(AGR_EINVAL, "snapshot: short write");
+    }
+    return 0;
+}
+static int load_dev(agr_handle* h, FILE* f, void* ddst, size_t bytes) {
+    const size_t chunk = h->bounce_bytes;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t m = std::min(chunk, bytes - o);
+        if (fread(h->bounce[0], 1, m, f) != m) return fail(AGR_EINVAL, "restore: short read");
+        CK(cudaMemcpyAsync((uint8_t*)ddst + o, h->bounce[0], m, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int agr_snapshot(agr_handle* h, const char* path) {
+    if (!h || !path) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(AGR_EINVAL, std::string("snapshot: cannot open ") + path);
+    snap_header hd{};
+    memcpy(hd.magic, "AGRSNAP1", 8);
+    hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN);
+    hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
+    hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
+    unsigned long long lens[2];
+    int rc = 0;
+    auto done = [&](int r) { fclose(f); return r; };
+    if (cudaMemcpy(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost) != cudaSuccess) return done(fail(AGR_ECUDA, "snapshot: log_len"));
+    hd.log_len[0] = lens[0]; hd.log_len[1] = lens[1];
+    if (fwrite(&hd, sizeof hd, 1, f) != 1) return done(fail(AGR_EINVAL, "snapshot: short write"));
+    for (uint32_t a = 0; a < hd.n_agents; ++a) {
+        char name[AGR_AGENT_ID_BYTES] = {0};
+        strncpy(name, h->agent_names[a].c_str(), AGR_AGENT_ID_BYTES - 1);
+        fwrite(name, 1, AGR_AGENT_ID_BYTES, f); fwrite(&h->agent_status[a], 1, 1, f);
+    }
+    const size_t R = hd.rows_used;
+    const size_t slab_bytes = (h->cfg.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
+    if ((rc = dump_dev(h, f, h->d.slab, slab_bytes)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.state, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.route, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.aux, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.cksum, R * 8)) < 0) return done(rc);
+    if (h->cfg.flags & AGR_CFG_VARLEN) {
+        if ((rc = dump_dev(h, f, h->d.voff, R * 8)) < 0) return done(rc);
+        if ((rc = dump_dev(h, f, h->d.vlen, R * 4)) < 0) return done(rc);
+    }
+    if ((rc = dump_dev(h, f, h->d.completed_log, (size_t)lens[0] * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.failed_log, (size_t)lens[1] * 4)) < 0) return done(rc);
+    return done(0);
+}
+
+int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
+    if (!cfg || !path || !out) return fail(AGR_EINVAL, "NULL argument");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(AGR_EINVAL, std::string("restore: cannot open ") + path);
+    snap_header hd{};
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "AGRSNAP1", 8) != 0) { fclose(f); return fail(AGR_EINVAL, "restore: not a snapshot"); }
+    agr_config c = *cfg;
+    if (c.flags == 0) c.flags = AGR_CFG_PERSISTENCE;
+    const uint32_t mode_bits = AGR_CFG_MINT_IDS | AGR_CFG_VARLEN;
+    if ((c.flags & mode_bits) != (hd.flags & mode_bits)) { fclose(f); return fail(AGR_EINVAL, "restore: id mode / record form differ from the snapshot"); }
+    if (c.id_secret == 0) c.id_secret = hd.id_secret;
+    if (c.id_secret != hd.id_secret) { fclose(f); return fail(AGR_EINVAL, "restore: id_secret differs from the snapshot"); }
+    agr_handle* h = nullptr;
+    int rc = agr_create(&c, &h);
+    if (rc < 0) { fclose(f); return rc; }
+    auto bail = [&](int r) { std::string keep = g_err; fclose(f); agr_destroy(h); g_err = keep; return r; };
+    if (hd.rows_used > h->cfg.slab_rows || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && hd.vused > h->vcap))
+        return bail(fail(AGR_ENOSPC, "restore: snapshot larger than the configured capacities"));
+    for (uint32_t a = 0; a < hd.n_agents; ++a) {
+        char name[AGR_AGENT_ID_BYTES]; uint8_t st;
+        if (fread(name, 1, AGR_AGENT_ID_BYTES, f) != AGR_AGENT_ID_BYTES || fread(&st, 1, 1, f) != 1) return bail(fail(AGR_EINVAL, "restore: short read"));
+        name[AGR_AGENT_ID_BYTES - 1] = 0;
+        const bool removed = (st == AG_STATUS_REMOVED);
+        if ((rc = agr_set_agent_state(h, name, removed ? (uint8_t)AGR_AGENT_STOPPED : st)) < 0) return bail(rc);
+        if (removed) { std::lock_guard<std::mutex> lk(h->mu); h->agent_status[a] = AG_STATUS_REMOVED; if ((rc = push_agent_status(h, a, AG_STATUS_REMOVED)) < 0) return bail(rc); }
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t R = hd.rows_used;
+    const size_t slab_bytes = (hd.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
+    if ((rc = load_dev(h, f, h->d.slab, slab_bytes)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.state, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.route, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.aux, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.cksum, R * 8)) < 0) return bail(rc);
+    if (hd.flags & AGR_CFG_VARLEN) {
+        if ((rc = load_dev(h, f, h->d.voff, R * 8)) < 0) return bail(rc);
+        if ((rc = load_dev(h, f, h->d.vlen, R * 4)) < 0) return bail(rc);
+    }
+    if ((rc = load_dev(h, f, h->d.completed_log, (size_t)hd.log_len[0] * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.failed_log, (size_t)hd.log_len[1] * 4)) < 0) return bail(rc);
+    unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
+    if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
+    h->rows_used = hd.rows_used; h->vused = hd.vused; h->scan_lo = hd.scan_lo;
+    h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->d.rows_hi = (uint32_t)hd.rows_used;
+    if (!(hd.flags & AGR_CFG_MINT_IDS) && R) {        // hash-id mode: rebuild the dedupe index from the restored rows
+        agr_launch_reindex(h->d, (uint32_t)R, h->stream);
+        h->k1_launches += 1;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: reindex"));
+    }
+    fclose(f);
+    *out = h;
+    return 0;
+}
+
+int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad) {
+    if (!h || !bad) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    unsigned long long* d_bad = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
+    CK(cudaMemsetAsync(d_bad, 0, 8, h->stream));
+    agr_launch_verify(h->d, h->rows_used, d_bad, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, d_bad, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *bad = v;
+    if (rows_checked) *rows_checked = h->rows_used;
     return 0;
 }
 

@@ -208,6 +208,32 @@ __global__ void __launch_bounds__(256) k1_index(const agr_dev d, const uint32_t 
     }
 }
 
+// integrity sweep: warp per row, recompute the position-weighted checksum of the stored bytes and compare
+__global__ void __launch_bounds__(256) k_verify(const agr_dev d, const unsigned long long rows, unsigned long long* __restrict__ bad) {
+    const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= rows) return;
+    const uint32_t rid = (uint32_t)w;
+    const uint8_t* src = rec_ptr(d, rid);
+    const uint32_t chunks = d.voff ? (d.vlen[rid] >> 4) : 32u;
+    uint32_t c0 = 0, c1 = 0;
+    for (uint32_t c = lane; c < chunks; c += 32) {
+        const uint4 v = ldg_nc_v4(src + (size_t)c * 16);
+        c0 += v.x + v.y + v.z + v.w;
+        c1 += (4 * c + 1) * v.x + (4 * c + 2) * v.y + (4 * c + 3) * v.z + (4 * c + 4) * v.w;
+    }
+    c0 = __reduce_add_sync(FULL, c0);
+    c1 = __reduce_add_sync(FULL, c1);
+    if (lane == 0 && agr_cksum_pack(c0, c1) != d.cksum[rid]) atomicAdd(bad, 1ULL);
+}
+void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st) {
+    if (rows) k_verify<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(d, rows, bad);
+}
+// rebuild of the dedupe index from restored rows (hash-id mode): k1_index over every stored row
+void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st) {
+    if (rows) k1_index<<<(rows + 255u) / 256u, 256, 0, st>>>(d, 0u, rows);
+}
+
 int agr_k1_launches_per_batch(uint32_t variant) { return (variant & 0x10u) ? 3 : 2; }
 static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
     uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 8u;

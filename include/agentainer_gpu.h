@@ -238,6 +238,17 @@ int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_
 /* storage.Get for a variable-length record: copies it into out (cap bytes), *len = stored length. */
 int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
 
+/* ------------------------------------------------- durability */
+/* What Redis persistence gave the reference (records and queues survive a server restart, docker-compose.yml:11-12):
+ * agr_snapshot writes the live state (slab rows, per-row state words, completed / failed logs, agent table) to a file;
+ * agr_restore creates a new engine from it (cfg gives the capacities; id mode and record form must match the snapshot).
+ * In hash-id mode the dedupe index is not stored: it is rebuilt on the device from the restored rows. */
+int agr_snapshot(agr_handle* h, const char* path);
+int agr_restore(const agr_config* cfg, const char* path, agr_handle** out);
+/* Integrity sweep: recomputes the checksum of every stored record on the device and compares it with the one K1 took at
+ * ingest.  *bad = number of rows that differ (0 on a healthy slab). */
+int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad);
+
 /* ------------------------------------------------------------------- stats */
 typedef struct agr_stats {
     uint64_t rows_used, rows_cap;
