@@ -302,7 +302,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->k2.hrid, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.eff, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.results, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048, false));
+    TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048 + 8, false));
     TRY(dev_alloc(h, &h->d_gtotal, (size_t)c.max_agents + 1, false));
     TRY(dev_alloc(h, &h->d_goff, (size_t)c.max_agents + 2, false));
     TRY(dev_alloc(h, &h->d_min_inq, (size_t)1, false));

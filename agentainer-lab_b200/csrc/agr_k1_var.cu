@@ -11,9 +11,12 @@
 #include "agr_device.cuh"
 
 #define VT_TILE 8192u                 // bytes of blob per tile
-#define VT_MAXREC 8192u               // longest record (header + payload)
-#define VT_STAGE (VT_TILE + VT_MAXREC)
-#define VT_MAXCNT 88u                 // >= VT_TILE / 96 + 2 records can start in one tile
+#define VT_WARPS 16
+#define VT_MAXREC 8192u               // longest legal record (header + payload)
+#define VT_TAIL 4608u                 // stage room behind the tile for the last owned record (a 4 KB body fits); a record that
+                                      // ends beyond the stage (> 4.5 KiB and badly placed: rare) is read from global memory
+#define VT_STAGE (VT_TILE + VT_TAIL)  // 12800 B = 100 x 128
+#define VT_MAXCNT (VT_TILE / 96u + 2u)   // at most this many records can start in one tile
 
 __device__ __forceinline__ uint32_t v_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint4 v_lds128(uint32_t a) {
@@ -40,7 +43,7 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
               const uint32_t ntiles, const uint32_t first_rid, const unsigned long long blob_base /* byte offset of blob in the slab */) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bars[WARPS];
-    __shared__ uint32_t s_off[WARPS][VT_MAXCNT + 1];
+    __shared__ uint32_t s_off[WARPS][2][VT_MAXCNT + 1];       // record offsets of the current / the next tile
     __shared__ unsigned long long s_ck[WARPS][VT_MAXCNT];
     __shared__ uint32_t s_ctr[K1_NLC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -54,29 +57,55 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
     for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
     const uint32_t stage = smem_base + (uint32_t)warp * VT_STAGE;
     const uint32_t bar = v_smem_u32(&bars[warp]);
-    uint32_t phase = 0;
-    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < ntiles; tile += gridDim.x * WARPS) {
-        const uint32_t a = __ldg(&tile_first[tile]), b = __ldg(&tile_first[tile + 1]);
-        if (a == b) continue;                                   // no record starts in this tile (inside a long record)
-        const uint32_t cnt = b - a;                             // <= VT_MAXCNT by construction (records are >= 96 B)
-        for (uint32_t k = lane; k <= cnt; k += 32) s_off[warp][k] = __ldg(&off[a + k]);
-        __syncwarp();
-        const uint32_t start = s_off[warp][0], bytes = s_off[warp][cnt] - start;
+    const uint32_t tstride = gridDim.x * WARPS;
+
+    // next non-empty tile at or after t: returns its record range and leaves its offsets in s_off[warp][buf]
+    auto fetch_meta = [&](uint32_t t, int buf, uint32_t& a, uint32_t& cnt) -> uint32_t {
+        for (; t < ntiles; t += tstride) {
+            a = __ldg(&tile_first[t]);
+            const uint32_t b = __ldg(&tile_first[t + 1]);
+            if (a != b) {                                       // (a tile inside a long record owns nothing)
+                cnt = b - a;
+                for (uint32_t k = lane; k <= cnt; k += 32) s_off[warp][buf][k] = __ldg(&off[a + k]);
+                __syncwarp();
+                return t;
+            }
+        }
+        cnt = 0;
+        return ntiles;
+    };
+    auto issue = [&](int buf, uint32_t cnt) {
         if (lane == 0) {
+            const uint32_t start = s_off[warp][buf][0];
+            const uint32_t bytes = min(s_off[warp][buf][cnt] - start, VT_STAGE);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(stage), "l"(blob + start), "r"(bytes), "r"(bar) : "memory");
         }
+    };
+
+    int cur = 0;
+    uint32_t a = 0, cnt = 0, phase = 0;
+    uint32_t tile = fetch_meta(blockIdx.x * WARPS + warp, cur, a, cnt);
+    if (tile < ntiles) issue(cur, cnt);
+    while (tile < ntiles) {
+        // the NEXT tile's record range and offsets arrive while this tile's bulk copy is in flight
+        uint32_t na = 0, ncnt = 0;
+        const uint32_t ntile = fetch_meta(tile + tstride, cur ^ 1, na, ncnt);
+        const uint32_t* so = s_off[warp][cur];
+        const uint32_t start = so[0], bytes = min(so[cnt] - start, VT_STAGE);
         asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
                      ::"r"(bar), "r"(phase) : "memory");
         phase ^= 1u;
         // ---- checksum: one record at a time, lanes sweep its 16 B chunks (conflict-free), REDUX per record
         for (uint32_t r = 0; r < cnt; ++r) {
-            const uint32_t lo = s_off[warp][r] - start, chunks = (s_off[warp][r + 1] - s_off[warp][r]) >> 4;
+            const uint32_t lo = so[r] - start, chunks = (so[r + 1] - so[r]) >> 4;
+            const bool in_stage = (so[r + 1] - start) <= bytes;                    // warp-uniform
+            const uint8_t* g = blob + so[r];
             uint32_t c0 = 0, c1 = 0;
             for (uint32_t c = lane; c < chunks; c += 32) {
-                const uint4 v = v_lds128(stage + lo + (c << 4));
+                const uint4 v = in_stage ? v_lds128(stage + lo + (c << 4)) : ldg_nc_v4(g + ((size_t)c << 4));
                 c0 += v.x + v.y + v.z + v.w;
                 c1 += (4 * c + 1) * v.x + (4 * c + 2) * v.y + (4 * c + 3) * v.z + (4 * c + 4) * v.w;
             }
@@ -85,11 +114,18 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
             if (lane == 0) s_ck[warp][r] = agr_cksum_pack(c0, c1);
         }
         __syncwarp();
-        // ---- decisions: one record per lane
-        for (uint32_t r = lane; r < cnt; r += 32) {
-            const uint32_t hb = stage + (s_off[warp][r] - start);
-            const uint4 h0 = v_lds128(hb), h1 = v_lds128(hb + 16), h2 = v_lds128(hb + 32), h3 = v_lds128(hb + 48),
-                        h4 = v_lds128(hb + 64), h5 = v_lds128(hb + 80);
+        // ---- decisions, one record per lane.  Round 0 (records 0..31 of the tile) reads its headers, THEN the stage is
+        // handed back to the TMA unit for the next tile, and only then does the long-latency decision chain run.
+        auto load_header = [&](uint32_t r, uint4& h0, uint4& h1, uint4& h2, uint4& h3, uint4& h4, uint4& h5) {
+            const uint32_t hb = stage + (so[r] - start);
+            if ((so[r] - start) + 96u <= bytes) {
+                h0 = v_lds128(hb); h1 = v_lds128(hb + 16); h2 = v_lds128(hb + 32); h3 = v_lds128(hb + 48); h4 = v_lds128(hb + 64); h5 = v_lds128(hb + 80);
+            } else {
+                const uint8_t* g = blob + so[r];
+                h0 = ldg_nc_v4(g); h1 = ldg_nc_v4(g + 16); h2 = ldg_nc_v4(g + 32); h3 = ldg_nc_v4(g + 48); h4 = ldg_nc_v4(g + 64); h5 = ldg_nc_v4(g + 80);
+            }
+        };
+        auto decide = [&](uint32_t r, const uint4& h0, const uint4& h1, const uint4& h2, const uint4& h3, const uint4& h4, const uint4& h5) {
             const uint32_t rid = first_rid + a + r;
             k1_ctx cx;
             k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, cx);
@@ -97,10 +133,22 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
             d.state[rid] = res.state;
             d.route[rid] = res.route;
             d.cksum[rid] = s_ck[warp][r];
-            d.voff[rid] = blob_base + s_off[warp][r];
-            d.vlen[rid] = s_off[warp][r + 1] - s_off[warp][r];
+            d.voff[rid] = blob_base + so[r];
+            d.vlen[rid] = so[r + 1] - so[r];
+        };
+        for (uint32_t r = 32 + lane; r < cnt; r += 32) {          // rounds 1.. (tiles of many small records) first
+            uint4 h0, h1, h2, h3, h4, h5;
+            load_header(r, h0, h1, h2, h3, h4, h5);
+            decide(r, h0, h1, h2, h3, h4, h5);
         }
+        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0, h2 = h0, h3 = h0, h4 = h0, h5 = h0;
+        const bool mine = (uint32_t)lane < cnt;
+        if (mine) load_header(lane, h0, h1, h2, h3, h4, h5);
+        __syncwarp();                                             // the stage has been consumed
+        if (ntile < ntiles) issue(cur ^ 1, ncnt);
+        if (mine) decide(lane, h0, h1, h2, h3, h4, h5);
         __syncwarp();
+        tile = ntile; a = na; cnt = ncnt; cur ^= 1;
     }
     k1_flush_counters(d, lc, s_ctr);
 }
@@ -137,7 +185,7 @@ __global__ void __launch_bounds__(256) k_var_copy(const agr_dev d, const uint32_
 
 cudaError_t agr_launch_k1_var(const agr_dev& d, const uint8_t* blob, const uint32_t* off, uint32_t n, unsigned long long blob_bytes,
                               uint32_t* tile_first, uint32_t first_rid, unsigned long long blob_base, int sm_count, cudaStream_t st) {
-    constexpr int WARPS = 13;
+    constexpr int WARPS = VT_WARPS;
     const size_t smem = (size_t)WARPS * VT_STAGE + 128;
     static bool attr_done = false;
     if (!attr_done) {

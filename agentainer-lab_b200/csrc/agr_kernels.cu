@@ -422,8 +422,10 @@ __global__ void __launch_bounds__(1024) k2_offsets(const agr_dev d, const agr_k2
     s.chunk_base[t] = sc[t] - cc;
     s.chunk_base[1024 + t] = sf[t] - cf;
     if (t == 1023) {
-        unsigned long long tc = sc[1023], tf = sf[1023];
-        if (base_c + tc > d.log_cap || base_f + tf > d.log_cap) atomicAdd(&d.ctr[C_LOG_OVERFLOW], 1ULL);
+        unsigned long long tc = base_c + sc[1023], tf = base_f + sf[1023];       // new tails, applied by k2_tail after the append
+        if (tc > d.log_cap || tf > d.log_cap) atomicAdd(&d.ctr[C_LOG_OVERFLOW], 1ULL);
+        s.chunk_base[2048] = (uint32_t)min(tc, d.log_cap);       s.chunk_base[2049] = (uint32_t)(min(tc, d.log_cap) >> 32);
+        s.chunk_base[2050] = (uint32_t)min(tf, d.log_cap);       s.chunk_base[2051] = (uint32_t)(min(tf, d.log_cap) >> 32);
     }
 }
 
@@ -448,16 +450,9 @@ __global__ void __launch_bounds__(256) k2_append(const agr_dev d, const agr_k2_s
     }
 }
 
-__global__ void k2_tail(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
-    // total pushes = base of the last chunk + its count; recompute the last chunk's count
-    const uint32_t nchunks = (n + csize - 1) / csize;
-    const uint32_t last = nchunks - 1;
-    uint32_t cc = 0, cf = 0;
-    for (uint32_t k = last * csize; k < n; ++k) { uint8_t f = s.eff[k]; cc += f & 1u; cf += (f >> 1) & 1u; }
-    unsigned long long tc = d.log_len[0] + s.chunk_base[last] + cc;
-    unsigned long long tf = d.log_len[1] + s.chunk_base[1024 + last] + cf;
-    d.log_len[0] = tc < d.log_cap ? tc : d.log_cap;
-    d.log_len[1] = tf < d.log_cap ? tf : d.log_cap;
+__global__ void k2_tail(const agr_dev d, const agr_k2_scratch s) {
+    d.log_len[0] = ((unsigned long long)s.chunk_base[2049] << 32) | s.chunk_base[2048];
+    d.log_len[1] = ((unsigned long long)s.chunk_base[2051] << 32) | s.chunk_base[2050];
 }
 
 void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
@@ -471,7 +466,7 @@ void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaSt
     const uint32_t nchunks = (n + csize - 1) / csize;
     k2_offsets<<<1, 1024, 0, st>>>(d, s, n, csize);
     k2_append<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(d, s, n, csize);
-    k2_tail<<<1, 1, 0, st>>>(d, s, n, csize);
+    k2_tail<<<1, 1, 0, st>>>(d, s);
 }
 
 // ------------------------------------------------------------------------------------------------ K3

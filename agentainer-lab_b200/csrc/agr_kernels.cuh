@@ -86,7 +86,7 @@ cudaError_t agr_launch_k1_var(const agr_dev& d, const uint8_t* blob, const uint3
                               uint32_t* tile_first, uint32_t first_rid, unsigned long long blob_base, int sm_count, cudaStream_t st);
 void agr_launch_var_lens(const agr_dev& d, const uint32_t* rids, uint32_t n, uint32_t* lens, cudaStream_t st);
 void agr_launch_var_copy(const agr_dev& d, const uint32_t* rids, uint32_t n, const unsigned long long* out_off, uint8_t* out, cudaStream_t st);
-#define AGR_VT_TILE 8192u
+#define AGR_VT_TILE 8192u   // lower bound of the tile size used by agr_k1_var.cu (sizes the tile index)
 #define AGR_VT_MAXREC 8192u
 
 // K4: shard binning / stable pack for the multi-GPU exchange
