@@ -476,7 +476,8 @@ void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaSt
 // give the stable rank — the warp-ballot agent-id partition.
 struct k3_item { bool sel; uint32_t rid; uint32_t slot; bool inq; };
 
-__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it) {
+// `st` = the row's state word (row modes; prefetched by the caller) — unused in log mode
+__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it, uint32_t st) {
     k3_item o{false, AGR_RID_NONE, RT_SLOT_NONE, false};
     if (it >= p.hi) return o;
     if (p.mode == K3_LOG_AGENT) {
@@ -487,7 +488,6 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
         return o;
     }
     const uint32_t rid = (uint32_t)it;
-    const uint32_t st = d.state[rid];
     if (!(st & ST_INQ)) return o;                       // not in agent:{a}:requests:pending
     o.inq = true;
     o.rid = rid; o.slot = rt_slot(d.route[rid]);
@@ -500,35 +500,52 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
     return o;
 }
 
-template <bool SCATTER>
+// SMEM: the warp's row of per-group cursors lives in shared memory (groups <= K3_SMEM_GROUPS); otherwise in the global
+// matrix through volatile accesses.
+#define K3_SMEM_GROUPS 1024u
+template <bool SCATTER, bool SMEM>
 __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_params p) {
+    extern __shared__ uint32_t s_rows[];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= p.nwarps) return;
-    uint32_t* row = p.matrix + (size_t)w * p.groups;
+    uint32_t* grow = p.matrix + (size_t)w * p.groups;
+    uint32_t* srow = s_rows + (size_t)(threadIdx.x >> 5) * p.groups;
+    if (SMEM) {
+        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = SCATTER ? grow[g] : 0u;
+        __syncwarp();
+    }
     const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
     unsigned long long e = b + p.per_warp;
     if (e > p.hi) e = p.hi;
     uint32_t mininq = AGR_RID_NONE;
+    const bool rows = (p.mode != K3_LOG_AGENT);
+    uint32_t st_next = (rows && b + lane < e) ? d.state[b + lane] : 0u;
     for (unsigned long long k0 = b; k0 < e; k0 += 32) {
-        k3_item it = k3_eval(d, p, k0 + lane);
+        const uint32_t st = st_next;
+        st_next = (rows && k0 + 32 + lane < e) ? d.state[k0 + 32 + lane] : 0u;      // next step's words are in flight
+        if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;                // nothing pending in these 32 rows
+        k3_item it = k3_eval(d, p, k0 + lane, st);
         if (it.inq && it.rid < mininq) mininq = it.rid;
         const uint32_t g = (p.groups == 1) ? 0u : it.slot;
         const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
         const uint32_t peers = __match_any_sync(FULL, key);
         if (it.sel) {
             const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            const bool leader = (rank == 0);
-            volatile uint32_t* cell = row + g;
+            volatile uint32_t* cell = (SMEM ? srow : grow) + g;
             const uint32_t base = *cell;
             if (SCATTER) {
                 const uint32_t pos = p.goff[g] + base + rank;
                 if (pos < p.cap) { p.out_rid[pos] = it.rid; p.out_slot[pos] = it.slot; }
             }
             __syncwarp(peers);
-            if (leader) *cell = base + __popc(peers);
+            if (rank == 0) *cell = base + __popc(peers);
         }
         __syncwarp();
+    }
+    if (SMEM && !SCATTER) {
+        __syncwarp();
+        for (uint32_t g = lane; g < p.groups; g += 32) grow[g] = srow[g];
     }
     if (!SCATTER && p.min_inq && p.mode == K3_TICK) {
         mininq = __reduce_min_sync(FULL, mininq);
@@ -573,12 +590,20 @@ __global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
 }
 
 void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStream_t st) {
-    cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
     const uint32_t blocks = (p.nwarps * 32u + 255u) / 256u;
-    k3_pass<false><<<blocks, 256, 0, st>>>(d, p);
-    k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
-    k3_scan_total<<<1, 1024, 0, st>>>(p);
-    k3_pass<true><<<blocks, 256, 0, st>>>(d, p);
+    if (p.groups <= K3_SMEM_GROUPS) {
+        const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 32 KiB
+        k3_pass<false, true><<<blocks, 256, smem, st>>>(d, p);
+        k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
+        k3_scan_total<<<1, 1024, 0, st>>>(p);
+        k3_pass<true, true><<<blocks, 256, smem, st>>>(d, p);
+    } else {
+        cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
+        k3_pass<false, false><<<blocks, 256, 0, st>>>(d, p);
+        k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
+        k3_scan_total<<<1, 1024, 0, st>>>(p);
+        k3_pass<true, false><<<blocks, 256, 0, st>>>(d, p);
+    }
 }
 
 // warp per selected row: copy the record out with the live state patched into the header, and/or emit the
