@@ -477,7 +477,7 @@ void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaSt
 struct k3_item { bool sel; uint32_t rid; uint32_t slot; bool inq; };
 
 // `st` = the row's state word (row modes; prefetched by the caller) — unused in log mode
-__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it, uint32_t st) {
+__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it, uint32_t st, uint32_t rt) {
     k3_item o{false, AGR_RID_NONE, RT_SLOT_NONE, false};
     if (it >= p.hi) return o;
     if (p.mode == K3_LOG_AGENT) {
@@ -490,7 +490,7 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
     const uint32_t rid = (uint32_t)it;
     if (!(st & ST_INQ)) return o;                       // not in agent:{a}:requests:pending
     o.inq = true;
-    o.rid = rid; o.slot = rt_slot(d.route[rid]);
+    o.rid = rid; o.slot = rt_slot(rt);
     if (p.mode == K3_AGENT_PENDING) { o.sel = (o.slot == p.slot); return o; }   // GetPendingRequests, requests.go:197-225
     // K3_TICK: isAgentRunning (replay_worker.go:76-81,166-189) + the skip rule of :101
     if (d.astatus[o.slot] != AGR_AGENT_RUNNING) return o;
@@ -521,11 +521,14 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     uint32_t mininq = AGR_RID_NONE;
     const bool rows = (p.mode != K3_LOG_AGENT);
     uint32_t st_next = (rows && b + lane < e) ? d.state[b + lane] : 0u;
+    uint32_t rt_next = (rows && b + lane < e) ? d.route[b + lane] : 0u;
     for (unsigned long long k0 = b; k0 < e; k0 += 32) {
-        const uint32_t st = st_next;
-        st_next = (rows && k0 + 32 + lane < e) ? d.state[k0 + 32 + lane] : 0u;      // next step's words are in flight
+        const uint32_t st = st_next, rt = rt_next;
+        const bool more = rows && k0 + 32 + lane < e;                                // next step's words are in flight
+        st_next = more ? d.state[k0 + 32 + lane] : 0u;
+        rt_next = more ? d.route[k0 + 32 + lane] : 0u;
         if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;                // nothing pending in these 32 rows
-        k3_item it = k3_eval(d, p, k0 + lane, st);
+        k3_item it = k3_eval(d, p, k0 + lane, st, rt);
         if (it.inq && it.rid < mininq) mininq = it.rid;
         const uint32_t g = (p.groups == 1) ? 0u : it.slot;
         const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
