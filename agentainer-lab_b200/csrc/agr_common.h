@@ -7,7 +7,9 @@
 //   route[rid]: u32  agent slot | verdict | verdict flags                        (K1 writes, K2/K3 read)
 //   aux[rid]  : u32  response status | error kind                                (K2 writes)
 //   cksum[rid]: u64  position-weighted checksum of the 512 B record              (K1 writes)
-//   table     : open-addressing dedupe index, 32 B slots {id128, ~rid, chain head}, 128-bit CAS on the id
+//   head[rid] : u32  K2 per-batch chain head of the row
+//   table     : hash-id mode only: open-addressing dedupe index, 32 B slots {id128, ~rid}, 128-bit CAS on the id
+//               (absent with engine-minted ids, where the id is a keyed bijection of rid: agr_mint_id below)
 //   logs      : completed / failed append-only logs of rid (per-agent lists are stable filters of them)
 #pragma once
 #include <stdint.h>
@@ -69,8 +71,7 @@ AGR_HD uint32_t rt_flags(uint32_t r) { return r >> RT_FLAG_SHIFT; }
 struct __attribute__((aligned(32))) agr_slot {
     unsigned long long key_lo, key_hi;
     uint32_t inv_rid;
-    uint32_t head;   // K2 per-batch chain head (op index + 1), 0 when idle
-    uint32_t pad[2];
+    uint32_t pad[3];
 };
 
 // ---- agent table entry (device mirror of the host map): 48 B key+slot, open addressing

@@ -1,8 +1,10 @@
 // agr_kernels.cu — sm_100a kernels of the request path.
 //
-//   K1  k1_ingest_*  + k1_post   ingest + dedupe + route        (requests.go:64-117, server.go:493-557)
-//   K2  k2_link / k2_apply / k2_offsets / k2_append              (requests.go:120-194,228-275, server.go:583-615)
-//   K3  k3_count / k3_scan_groups / k3_scan_total / k3_scatter / k3_gather
+//   K1  k1_ingest_v0 (LSU variant; the default TMA kernel is in agr_k1_tma.cu, the variable-length one in
+//       agr_k1_var.cu), k1_index (split mode), k1_post          (requests.go:64-117, server.go:493-557)
+//   K2  k2_prepare / k2_link / k2_apply / k2_offsets / k2_append / k2_tail
+//                                                                 (requests.go:120-194,228-275, server.go:583-615)
+//   K3  k3_pass<count|scatter> / k3_scan_groups / k3_scan_total / k3_gather, k_resolve, k_verify, k_drop_*
 //                                                                 (replay_worker.go:58-117, requests.go:197-225)
 //
 // All arithmetic is integer / byte work bounded by HBM bandwidth; there is no tensor-core work on this path.
