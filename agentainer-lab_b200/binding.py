@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "agr_ingest", "agr_ingest_ex", "agr_ingest_var", "agr_replay_scan_var", "agr_get_record_var", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
-    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_snapshot", "agr_restore", "agr_verify",
+    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify",
 ]
 
 _lib = None
@@ -130,6 +130,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
+        "agr_complete_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -373,6 +374,14 @@ class Engine:
         info = AgrExchangeInfo()
         _check(self.lib, self.lib.agr_ingest_sharded(self.h, _ptr(recs) if n else None, n, _ptr(out) if (want_verdicts and n) else None, C.byref(info)))
         return out, info
+
+    def complete_sharded(self, outs: np.ndarray):
+        assert outs.dtype == outcome_dtype and outs.flags["C_CONTIGUOUS"]
+        n = len(outs)
+        res = np.zeros(n, dtype=np.int32)
+        info = AgrExchangeInfo()
+        _check(self.lib, self.lib.agr_complete_sharded(self.h, _ptr(outs) if n else None, n, _ptr(res) if n else None, C.byref(info)))
+        return res, info
 
     # ---- K2
     def complete(self, outs: np.ndarray, want_results: bool = True) -> Optional[np.ndarray]:

@@ -1205,7 +1205,94 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     TRY(dev_alloc(h, &h->d_xverd, 2 * mb, false));
     TRY(dev_alloc(h, &h->d_vback, mb, false));
     TRY(dev_alloc(h, &h->d_vout, mb, false));
+    // K2 over local + received outcomes: scratch for 2 * max_batch ops
+    TRY(dev_alloc(h, &h->d_outs, 2 * mb, false));
+    TRY(dev_alloc(h, &h->d_ops, 2 * mb, false));
+    h->k2.ops = h->d_ops;
+    TRY(dev_alloc(h, &h->k2.nxt, 2 * mb, false));
+    TRY(dev_alloc(h, &h->k2.hrid, 2 * mb, false));
+    TRY(dev_alloc(h, &h->k2.eff, 2 * mb, false));
+    TRY(dev_alloc(h, &h->k2.results, 2 * mb, false));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info) {
+    if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    const uint32_t G = (uint32_t)h->world, me = (uint32_t)h->rank;
+    cudaStream_t st = h->stream;
+    uint32_t* d_gtotal = h->d_k4cnt; uint32_t* d_goff = h->d_k4cnt + 40; uint32_t* d_rcnt = h->d_k4cnt + 80;
+    const size_t S = sizeof(agr_outcome);
+    // outcomes -> staging (the record staging buffer is reused), owners + counts
+    if (n) CK(cudaMemcpyAsync(h->d_stage, outs, (size_t)n * S, cudaMemcpyHostToDevice, st));
+    agr_k4_params p{};
+    p.items = h->d_stage; p.item_bytes = (uint32_t)S; p.agent_off = 16; p.n = n; p.G = G; p.me = me;
+    uint32_t per = (n + h->k4_nwarps - 1) / std::max<uint32_t>(1, h->k4_nwarps);
+    per = std::max<uint32_t>(32, (per + 31) & ~31u);
+    p.per_warp = per; p.nwarps = std::max<uint32_t>(1, (n + per - 1) / per);
+    p.matrix = h->d_k4matrix; p.gtotal = d_gtotal; p.goff = d_goff; p.owner = h->d_owner; p.perm = h->d_perm;
+    agr_launch_k4_count(p, st);
+    h->k4_launches += 2;
+    CK(cudaGetLastError());
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        NK(g_nccl.Send(d_gtotal + q, 1, ncclUint32, (int)q, h->comm, st));
+        NK(g_nccl.Recv(d_rcnt + q, 1, ncclUint32, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    uint32_t* hc = h->h_small;
+    CK(cudaMemcpyAsync(hc, d_gtotal, G * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc + 32, d_rcnt, G * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t scnt[32], rcnt[32], soff[33], roff[33];
+    soff[0] = 0; roff[0] = 0;
+    for (uint32_t q = 0; q < G; ++q) { scnt[q] = hc[q]; rcnt[q] = (q == me) ? 0 : hc[32 + q]; soff[q + 1] = soff[q] + scnt[q]; roff[q + 1] = roff[q] + rcnt[q]; }
+    const uint32_t n_local = scnt[me], n_recv = roff[G], total = n_local + n_recv;
+    if (total > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more outcomes than 2 * max_batch");
+    // pack: own outcomes straight into the K2 input array, peer segments into the send buffer
+    p.local_dst = (uint8_t*)h->d_outs; p.send_dst = h->d_send;
+    if (n) { agr_launch_k4_scatter(p, st); h->k4_launches += 1; CK(cudaGetLastError()); }
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        if (q == me) continue;
+        if (scnt[q]) NK(g_nccl.Send(h->d_send + (size_t)soff[q] * S, (size_t)scnt[q] * S, ncclUint8, (int)q, h->comm, st));
+        if (rcnt[q]) NK(g_nccl.Recv((uint8_t*)(h->d_outs + n_local) + (size_t)roff[q] * S, (size_t)rcnt[q] * S, ncclUint8, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    // K2 at the owner over local + received outcomes
+    if (total) {
+        h->d.rows_hi = (uint32_t)h->rows_used;
+        agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, st);
+        agr_launch_k2(h->d, h->k2, total, st);
+        h->k2_launches += 6;
+        CK(cudaGetLastError());
+    }
+    // result codes back to the reporters, restored to the caller's order
+    int32_t* d_rback = (int32_t*)h->d_vback;
+    NK(g_nccl.GroupStart());
+    for (uint32_t q = 0; q < G; ++q) {
+        if (q == me) continue;
+        if (rcnt[q]) NK(g_nccl.Send(h->k2.results + n_local + roff[q], (size_t)rcnt[q] * 4, ncclUint8, (int)q, h->comm, st));
+        if (scnt[q]) NK(g_nccl.Recv(d_rback + soff[q], (size_t)scnt[q] * 4, ncclUint8, (int)q, h->comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    if (n) {
+        agr_launch_k4_unpermute(p, h->k2.results, d_rback, h->d_vout, 4, st);
+        h->k4_launches += 1;
+        CK(cudaGetLastError());
+        if (results) CK(cudaMemcpyAsync(h->h_results, h->d_vout, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (n && results) memcpy(results, h->h_results, (size_t)n * 4);
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->world = G; info->rank = me; info->n_local = n_local; info->n_sent = n - n_local; info->n_received = n_recv;
+        for (uint32_t q = 0; q < G; ++q) { info->sent_to[q] = (q == me) ? 0 : scnt[q]; info->received_from[q] = rcnt[q]; }
+    }
     return 0;
 }
 

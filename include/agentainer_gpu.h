@@ -306,6 +306,10 @@ typedef struct agr_exchange_info {
     uint64_t first_rid;                        /* rows: [first_rid, +n_local) local, then received, grouped by source rank */
 } agr_exchange_info;
 int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info);
+/* The same route for outcomes (cross-shard replay reconciliation): an outcome reported at a shard that does not own the
+ * agent (the worker of shard A replayed through shard B's proxy) is shipped to the owner, applied there by K2 in
+ * (own host first, then peers by rank) order, and its result code comes back.  Collective like agr_ingest_sharded. */
+int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info);
 
 /* Diagnostic read-back of the per-row SoA words (tests, snapshot tooling): which = 0 state (u32), 1 route (u32),
  * 2 aux (u32), 3 checksum (u64).  out must hold n elements of that width. */

@@ -56,8 +56,34 @@ def _worker(rank, world, port, q):
         for rec, got in zip(batch, v if v is not None else []):
             e = exp[bytes(rec["request_id"])]
             ok &= (int(got["code"]), int(got["flags"]) & 0x7) == e
+    # ---- outcomes reported at the WRONG shard travel to the owner (agr_complete_sharded): every rank completes a slice of
+    # EVERY agent's pending records, own or not; the owner applies them (own host first, then peers by rank)
+    pend_all = [None] * world
+    dist.all_gather_object(pend_all, {a: [bytes(x) for x in eng.list(a, 0)] for a in own[rank]})
+    outs = []
+    for r in range(world):
+        for a, ids in sorted(pend_all[r].items()):
+            for j, rid in enumerate(ids[:40]):
+                if j % world == rank:
+                    outs.append((rid, a, K.AGR_OUT_RESPONSE if j % 3 else K.AGR_OUT_ERROR))
+    outs.append((bytes(range(16)), own[(rank + 1) % world][0], K.AGR_OUT_RESPONSE))          # unknown id at a foreign owner
+    arr = np.zeros(len(outs), dtype=A.outcome_dtype)
+    for j, (rid, a, kind) in enumerate(outs):
+        arr[j]["request_id"] = np.frombuffer(rid, dtype=np.uint8); arr[j]["agent_id"] = a.encode(); arr[j]["kind"] = kind; arr[j]["http_status"] = 200
+    res, cinfo = eng.complete_sharded(arr)
+    ok &= list(res[:-1]) == [0] * (len(outs) - 1) and res[-1] == K.AGR_ENOTFOUND
+    ok &= cinfo.n_sent > 0 and cinfo.n_received > 0
+    allo = [None] * world
+    dist.all_gather_object(allo, arr.tobytes())
+    order = [rank] + [p for p in range(world) if p != rank]
+    for src in order:                                  # the owner's merge order
+        o = np.frombuffer(allo[src], dtype=A.outcome_dtype)
+        mine_o = o[np.array([A.agent_shard(a.decode(), world) == rank for a in o["agent_id"]], dtype=bool)]
+        if len(mine_o):
+            ref.complete(np.ascontiguousarray(mine_o))
     for a in own[rank]:
-        ok &= [bytes(x).hex() for x in eng.list(a, 0)] == [bytes(x).hex() for x in ref.list(a, 0)]
+        for w in (0, 1, 2):
+            ok &= [bytes(x).hex() for x in eng.list(a, w)] == [bytes(x).hex() for x in ref.list(a, w)]
     s = eng.stats()
     q.put((rank, bool(ok), s["k4_launches"], s["stored"]))
     dist.barrier()
