@@ -30,7 +30,8 @@ assert verdict_dtype.itemsize == 8 and dispatch_dtype.itemsize == 32
 class AgrConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("slab_rows", C.c_uint64), ("table_slots", C.c_uint64),
                 ("max_agents", C.c_uint32), ("max_batch", C.c_uint32), ("log_entries", C.c_uint64),
-                ("id_secret", C.c_uint64), ("vslab_bytes", C.c_uint64), ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
+                ("id_secret", C.c_uint64), ("vslab_bytes", C.c_uint64), ("resp_bytes", C.c_uint64),
+                ("k1_variant", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AgrStats(C.Structure):
@@ -60,7 +61,7 @@ ABI_SYMBOLS = [
     "agr_ingest", "agr_ingest_ex", "agr_ingest_var", "agr_replay_scan_var", "agr_get_record_var", "agr_complete", "agr_replay_scan", "agr_pending", "agr_get_record", "agr_list", "agr_stats_get",
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
-    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify",
+    "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
 ]
 
 _lib = None
@@ -124,6 +125,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_synth_bind_mint": (i32, [vp, C.POINTER(AgrSynth), u64]),
         "agr_agent_hash": (u64, [C.c_char_p]),
         "agr_agent_shard": (u32, [C.c_char_p, u32]),
+        "agr_store_response_body": (i32, [vp, C.c_char_p, vp, vp, u32]),
+        "agr_get_response_body": (i32, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]),
         "agr_snapshot": (i32, [vp, C.c_char_p]),
         "agr_restore": (i32, [C.POINTER(AgrConfig), C.c_char_p, C.POINTER(vp)]),
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -219,7 +222,7 @@ class Engine:
                  log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0, restore_from=None):
         self.lib = load_library()
         cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
-                        log_entries, id_secret, vslab_bytes, k1_variant, 0)
+                        log_entries, id_secret, vslab_bytes, 0, k1_variant, 0)
         self.mint = bool(flags & K.AGR_CFG_MINT_IDS)
         self.varlen = bool(flags & K.AGR_CFG_VARLEN)
         h = C.c_void_p()
@@ -434,6 +437,25 @@ class Engine:
                 continue
             _check(self.lib, rc)
             return ids[: n.value]
+
+    def store_response_body(self, agent_id: str, request_id: bytes, body: bytes) -> bool:
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        buf = (C.c_uint8 * max(1, len(body))).from_buffer_copy(body or b"\0")
+        rc = self.lib.agr_store_response_body(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), C.cast(buf, C.c_void_p), len(body))
+        if rc == K.AGR_ENOTFOUND:
+            return False
+        _check(self.lib, rc)
+        return True
+
+    def get_response_body(self, agent_id: str, request_id: bytes) -> Optional[bytes]:
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        out = (C.c_uint8 * 65536)()
+        ln = C.c_uint32()
+        rc = self.lib.agr_get_response_body(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), C.cast(out, C.c_void_p), 65536, C.byref(ln))
+        if rc == K.AGR_ENOTFOUND:
+            return None
+        _check(self.lib, rc)
+        return bytes(out[: ln.value])
 
     def snapshot(self, path: str) -> None:
         _check(self.lib, self.lib.agr_snapshot(self.h, path.encode()))

@@ -84,6 +84,9 @@ struct agr_handle {
     uint64_t replay_scans = 0, replay_dispatched = 0;
     std::vector<void*> dev_allocs, host_allocs;
     alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
+    // stored responses: byte slab + per-row (offset, length), written off the hot path
+    uint8_t* d_resp = nullptr; uint64_t resp_used = 0, resp_cap = 0;
+    unsigned long long* d_resp_off = nullptr; uint32_t* d_resp_len = nullptr;
     // flat-combining front-end for concurrent small ingests (AGR_CFG_COMBINE)
     std::mutex cmu; std::condition_variable ccv;
     agr_record* c_ring = nullptr;              // pinned [AGR_COMBINE_RING]
@@ -262,6 +265,11 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
     TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
+    if (c.resp_bytes == 0) c.resp_bytes = 64ull * c.slab_rows;
+    h->cfg.resp_bytes = c.resp_bytes; h->resp_cap = c.resp_bytes;
+    TRY(dev_alloc(h, &h->d_resp, (size_t)c.resp_bytes, false));
+    TRY(dev_alloc(h, &h->d_resp_off, c.slab_rows, true));
+    TRY(dev_alloc(h, &h->d_resp_len, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
     d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
     d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
@@ -998,11 +1006,61 @@ int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t reques
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ stored responses
+static int resolve_one_locked(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint32_t* rid) {
+    int slot = agent_find(h, agent_id);
+    if (slot < 0) return fail(AGR_ENOTFOUND, "request not found");
+    agr_dop& op = h->h_ops[0];
+    memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
+    op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
+    CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
+    h->d.rows_hi = (uint32_t)h->rows_used;
+    agr_launch_resolve(h->d, h->k2, 1, h->stream);
+    h->k3_launches += 1;
+    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
+    *rid = h->h_small[0];
+    return 0;
+}
+
+int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* bytes, uint32_t len) {
+    if (!h || !agent_id || !request_id || (len && !bytes)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint32_t rid = 0;
+    TRY(resolve_one_locked(h, agent_id, request_id, &rid));
+    if (h->resp_used + len > h->resp_cap) return fail(AGR_ENOSPC, "response slab full");
+    const unsigned long long off = h->resp_used;
+    h->resp_used += (len + 15u) & ~15ull;
+    if (len) CK(cudaMemcpyAsync(h->d_resp + off, bytes, len, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_resp_off + rid, &off, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_resp_len + rid, &len, 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
+    if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint32_t rid = 0;
+    TRY(resolve_one_locked(h, agent_id, request_id, &rid));
+    unsigned long long off = 0; uint32_t l = 0;
+    CK(cudaMemcpyAsync(&off, h->d_resp_off + rid, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&l, h->d_resp_len + rid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *len = l;
+    if (l > cap || !out) return (out && l > cap) ? fail(AGR_ECAP, "output buffer too small") : 0;
+    if (l) { CK(cudaMemcpyAsync(out, h->d_resp + off, l, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ durability
 struct snap_header {
     char magic[8];                 // "AGRSNAP1"
     uint32_t flags, n_agents, shard, gen;
-    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used;
 };
 static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
     const size_t chunk = h->bounce_bytes;
@@ -1037,6 +1095,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
+    hd.resp_used = h->resp_used;
     unsigned long long lens[2];
     int rc = 0;
     auto done = [&](int r) { fclose(f); return r; };
@@ -1061,6 +1120,9 @@ int agr_snapshot(agr_handle* h, const char* path) {
     }
     if ((rc = dump_dev(h, f, h->d.completed_log, (size_t)lens[0] * 4)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.failed_log, (size_t)lens[1] * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_resp_off, R * 8)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_resp_len, R * 4)) < 0) return done(rc);
     return done(0);
 }
 
@@ -1081,6 +1143,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     int rc = agr_create(&c, &h);
     if (rc < 0) { fclose(f); return rc; }
     auto bail = [&](int r) { std::string keep = g_err; fclose(f); agr_destroy(h); g_err = keep; return r; };
+    if (hd.resp_used > h->resp_cap) return bail(fail(AGR_ENOSPC, "restore: stored responses larger than resp_bytes"));
     if (hd.rows_used > h->cfg.slab_rows || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && hd.vused > h->vcap))
         return bail(fail(AGR_ENOSPC, "restore: snapshot larger than the configured capacities"));
     for (uint32_t a = 0; a < hd.n_agents; ++a) {
@@ -1105,6 +1168,10 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     }
     if ((rc = load_dev(h, f, h->d.completed_log, (size_t)hd.log_len[0] * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.failed_log, (size_t)hd.log_len[1] * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_resp_off, R * 8)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_resp_len, R * 4)) < 0) return bail(rc);
+    h->resp_used = hd.resp_used;
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->scan_lo = hd.scan_lo;

@@ -111,6 +111,7 @@ typedef struct agr_config {
     uint64_t log_entries;    /* capacity of the completed and failed logs; 0 = 2*slab_rows */
     uint64_t id_secret;      /* AGR_CFG_MINT_IDS: key of the id permutation; 0 = a fixed default */
     uint64_t vslab_bytes;    /* AGR_CFG_VARLEN: capacity of the byte slab; 0 = 1024 * slab_rows */
+    uint64_t resp_bytes;     /* capacity of the stored-response byte slab; 0 = 64 * slab_rows */
     uint32_t k1_variant;     /* 0 = default K1 kernel (TMA, 14 warps x 1 stage, fused index); 1..4 TMA shapes, 5 = LSU kernel,
                                 | 0x10 = split stream / index kernels — alternates kept for A/B measurement */
     uint32_t reserved;
@@ -237,6 +238,14 @@ int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_
                         uint32_t* n, uint64_t* blob_bytes);
 /* storage.Get for a variable-length record: copies it into out (cap bytes), *len = stored length. */
 int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
+
+/* ------------------------------------------------- stored responses (requests.go:142-147,165) */
+/* StoreResponse keeps the whole response in the record (status, first-value headers, body).  agr_complete carries the
+ * status on the hot path; the bytes (flattened "Key: Value\n" headers + body, caller's framing) go here, off the hot
+ * path, and come back for GET /agents/{id}/requests/{reqId} (server.go:655-679).  The latest store wins, like the
+ * reference's SET.  AGR_ENOTFOUND if the record does not exist. */
+int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* bytes, uint32_t len);
+int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
 
 /* ------------------------------------------------- durability */
 /* What Redis persistence gave the reference (records and queues survive a server restart, docker-compose.yml:11-12):

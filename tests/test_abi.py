@@ -43,7 +43,7 @@ def test_struct_sizes():
     assert A.verdict_dtype.itemsize == 8 and A.dispatch_dtype.itemsize == 32
     assert A.record_dtype.fields["payload"][1] == K.AGR_HEADER_BYTES
     assert A.record_dtype.fields["seq"][1] == 64 and A.record_dtype.fields["agent_id"][1] == 32
-    assert C.sizeof(AgrConfig) == 64
+    assert C.sizeof(AgrConfig) == 72
 
 
 def test_abi_version_and_strerror(lib):

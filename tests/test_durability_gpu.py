@@ -86,3 +86,26 @@ def test_restore_rejects_mismatched_mode(tmp_path):
         A.Engine(slab_rows=1 << 10, flags=MODES["hash"], restore_from=p)
     with pytest.raises(A.AgrError):
         A.Engine(slab_rows=1 << 10, flags=MODES["mint"], id_secret=12345, restore_from=p)
+
+
+def test_stored_response_bodies_round_trip_and_survive_a_restart(tmp_path):
+    """StoreResponse keeps the response with the record (requests.go:142-147,165); the bytes travel off the hot path."""
+    from scenario import Req, rid_of, make_records
+    p = str(tmp_path / "r.snap")
+    with A.Engine(slab_rows=1 << 10, max_agents=16, flags=MODES["mint"]) as eng:
+        eng.set_agent_state("agent-1", "running")
+        v, first = eng.ingest(make_records([Req("agent-1", rid_of(i), i) for i in range(1, 6)]))
+        ids = [bytes(x) for x in eng.mint_ids(first, 5)]
+        assert eng.get_response_body("agent-1", ids[0]) == b""
+        assert eng.store_response_body("agent-1", ids[0], b'Content-Type: application/json\n\n{"reply":"hi"}')
+        assert eng.store_response_body("agent-1", ids[3], b"x" * 5000)
+        assert eng.store_response_body("agent-1", ids[0], b"second response wins")            # like the reference's SET
+        assert not eng.store_response_body("agent-1", rid_of(77), b"nope")
+        assert eng.get_response_body("agent-1", ids[0]) == b"second response wins"
+        assert eng.get_response_body("agent-1", ids[3]) == b"x" * 5000
+        assert eng.get_response_body("agent-2", ids[3]) is None
+        eng.snapshot(p)
+    with A.Engine(slab_rows=1 << 10, max_agents=16, flags=MODES["mint"], restore_from=p) as eng2:
+        assert eng2.get_response_body("agent-1", ids[0]) == b"second response wins"
+        assert eng2.get_response_body("agent-1", ids[3]) == b"x" * 5000
+        assert eng2.get_response_body("agent-1", ids[1]) == b""

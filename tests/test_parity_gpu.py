@@ -390,3 +390,47 @@ def test_full_size_properties_1m():
         mask = host["agent_id"] == a0.encode()
         assert [bytes(x) for x in ids[: mask.sum()]] == [bytes(x) for x in host["request_id"][mask]]
         assert sum(len(eng.list(A.synth_agent_id(k), 0, cap=1 << 14)) for k in range(0, na, 37)) > 0
+
+
+def test_flat_combining_of_concurrent_single_request_calls():
+    """AGR_CFG_COMBINE: many threads calling agr_ingest_ex / agr_complete with ONE request each get the same answers as a
+    serial run, in far fewer K1 launches; the ring order is the event order (per-agent FIFO = order of the row ids)."""
+    import threading
+    nt, per = 16, 60
+    agents = ["agent-%d" % k for k in range(4)]
+    with engine(flags=MINT | K.AGR_CFG_COMBINE, slab_rows=1 << 14) as eng:
+        for k, a in enumerate(agents):
+            eng.set_agent_state(a, "stopped" if k % 2 else "running")
+        results = [[] for _ in range(nt)]
+
+        def worker(t):
+            for i in range(per):
+                a = agents[(t + i) % 4]
+                rec = make_records([Req(a, rid_of(1 + t * per + i), 1 + t * per + i)])
+                out, ids = np.zeros(1, dtype=A.verdict_dtype), np.zeros((1, 16), dtype=np.uint8)
+                first = eng.ingest_ex(rec, out, ids)
+                results[t].append((a, int(out[0]["code"]), first, bytes(ids[0])))
+                if int(out[0]["code"]) == K.AGR_V_FORWARD:
+                    o = np.zeros(1, dtype=A.outcome_dtype)
+                    o["request_id"], o["agent_id"], o["kind"], o["http_status"] = ids[0], a.encode(), K.AGR_OUT_RESPONSE, 200
+                    assert list(eng.complete(o)) == [0]
+
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(nt)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        flat = [x for r in results for x in r]
+        assert len({x[2] for x in flat}) == nt * per                       # every request got its own row
+        assert all((code == K.AGR_V_QUEUED) == (agents.index(a) % 2 == 1) for a, code, _, _ in flat)
+        assert all(bytes(eng.mint_ids(first, 1)[0]) == rid for _, _, first, rid in flat)
+        for k, a in enumerate(agents):
+            mine = sorted((first, rid) for aa, _, first, rid in flat if aa == a)
+            pend = [bytes(x) for x in eng.list(a, K.AGR_LIST_PENDING)]
+            comp = [bytes(x) for x in eng.list(a, K.AGR_LIST_COMPLETED)]
+            if k % 2:
+                assert pend == [rid for _, rid in mine] and comp == []     # FIFO == row order == ring order
+            else:
+                assert pend == [] and sorted(comp) == sorted(rid for _, rid in mine)
+        s = eng.stats()
+        assert s["stored"] == nt * per and s["k1_launches"] < 2 * nt * per
