@@ -692,7 +692,7 @@ static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, i
     }
     agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, n, h->stream);
     agr_launch_k2(h->d, h->k2, n, h->stream);
-    h->k2_launches += 6;
+    h->k2_launches += 7;
     CK(cudaGetLastError());
     if (timing) { CK(cudaEventRecord(h->op_ev[1], h->stream)); h->op_timed[0] = true; }
     if (results) {
@@ -1335,7 +1335,7 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
         h->d.rows_hi = (uint32_t)h->rows_used;
         agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, st);
         agr_launch_k2(h->d, h->k2, total, st);
-        h->k2_launches += 6;
+        h->k2_launches += 7;
         CK(cudaGetLastError());
     }
     // result codes back to the reporters, restored to the caller's order

@@ -400,16 +400,28 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
     }
 }
 
-// one CTA: per-chunk counts of push flags -> exclusive bases; reserves log space
+// warp per chunk: counts of completed / failed pushes in the chunk (coalesced bytes, ballot + popc)
+__global__ void __launch_bounds__(256) k2_count(const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
+    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nchunks = (n + csize - 1) / csize;
+    if (chunk >= nchunks) return;
+    const uint32_t b = chunk * csize, e = min(n, b + csize);
+    uint32_t cc = 0, cf = 0;
+    for (uint32_t k0 = b; k0 < e; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const uint8_t f = (k < e) ? s.eff[k] : 0;
+        cc += __popc(__ballot_sync(FULL, f & 1u));
+        cf += __popc(__ballot_sync(FULL, f & 2u));
+    }
+    if (lane == 0) { s.chunk_base[chunk] = cc; s.chunk_base[1024 + chunk] = cf; }
+}
+// one CTA: exclusive scan of the <= 1024 chunk counts -> chunk bases; computes the new log tails
 __global__ void __launch_bounds__(1024) k2_offsets(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
     __shared__ uint32_t sc[1024], sf[1024];
     const uint32_t t = threadIdx.x;
     const uint32_t nchunks = (n + csize - 1) / csize;
-    uint32_t cc = 0, cf = 0;
-    if (t < nchunks) {
-        const uint32_t b = t * csize, e = min(n, b + csize);
-        for (uint32_t k = b; k < e; ++k) { uint8_t f = s.eff[k]; cc += f & 1u; cf += (f >> 1) & 1u; }
-    }
+    const uint32_t cc = (t < nchunks) ? s.chunk_base[t] : 0u, cf = (t < nchunks) ? s.chunk_base[1024 + t] : 0u;
     sc[t] = cc; sf[t] = cf;
     __syncthreads();
     for (uint32_t off = 1; off < 1024; off <<= 1) {      // Hillis-Steele inclusive scan
@@ -466,6 +478,7 @@ void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaSt
     csize = (csize + 31u) & ~31u;
     if (csize < 32u) csize = 32u;
     const uint32_t nchunks = (n + csize - 1) / csize;
+    k2_count<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(s, n, csize);
     k2_offsets<<<1, 1024, 0, st>>>(d, s, n, csize);
     k2_append<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(d, s, n, csize);
     k2_tail<<<1, 1, 0, st>>>(d, s);
@@ -558,16 +571,28 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     }
 }
 
-// column scan: thread per group walks the warps (coalesced across groups)
+// column scan: one CTA per group turns that group's per-warp counts into exclusive prefixes over the warps
 __global__ void __launch_bounds__(256) k3_scan_groups(const agr_k3_params p) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.groups) return;
-    uint32_t run = 0;
-    for (uint32_t w = 0; w < p.nwarps; ++w) {
-        uint32_t* cell = p.matrix + (size_t)w * p.groups + g;
-        uint32_t c = *cell; *cell = run; run += c;
+    __shared__ uint32_t part[256];
+    const uint32_t g = blockIdx.x, t = threadIdx.x;
+    const uint32_t per = (p.nwarps + 255u) / 256u;
+    const uint32_t w0 = t * per, w1 = min(p.nwarps, w0 + per);
+    uint32_t sum = 0;
+    for (uint32_t w = w0; w < w1; ++w) sum += p.matrix[(size_t)w * p.groups + g];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 256; off <<= 1) {
+        uint32_t a = (t >= off) ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += a;
+        __syncthreads();
     }
-    p.gtotal[g] = run;
+    uint32_t run = part[t] - sum;                       // exclusive prefix of this thread's slice
+    for (uint32_t w = w0; w < w1; ++w) {
+        uint32_t* cell = p.matrix + (size_t)w * p.groups + g;
+        const uint32_t c = *cell; *cell = run; run += c;
+    }
+    if (t == 255) p.gtotal[g] = part[255];
 }
 // exclusive scan over groups (one CTA, loops for groups > 1024); goff[groups] = total
 __global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
@@ -599,13 +624,13 @@ void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStr
     if (p.groups <= K3_SMEM_GROUPS) {
         const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 32 KiB
         k3_pass<false, true><<<blocks, 256, smem, st>>>(d, p);
-        k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
+        k3_scan_groups<<<p.groups, 256, 0, st>>>(p);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
         k3_pass<true, true><<<blocks, 256, smem, st>>>(d, p);
     } else {
         cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
         k3_pass<false, false><<<blocks, 256, 0, st>>>(d, p);
-        k3_scan_groups<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p);
+        k3_scan_groups<<<p.groups, 256, 0, st>>>(p);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
         k3_pass<true, false><<<blocks, 256, 0, st>>>(d, p);
     }
