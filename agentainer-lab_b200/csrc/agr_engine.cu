@@ -311,7 +311,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->k2.eff, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.results, c.max_batch, false));
     TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048 + 8, false));
-    TRY(dev_alloc(h, &h->d_gtotal, (size_t)c.max_agents + 1, false));
+    TRY(dev_alloc(h, &h->d_gtotal, ((size_t)c.max_agents + 8) * 66, false));   // gtotal + 64 segment partials per group
     TRY(dev_alloc(h, &h->d_goff, (size_t)c.max_agents + 2, false));
     TRY(dev_alloc(h, &h->d_min_inq, (size_t)1, false));
     CK(cudaStreamSynchronize(h->stream));
@@ -749,7 +749,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
         CK(cudaEventRecord(h->op_ev[2], h->stream));
     }
     agr_launch_k3_select(h->d, p, h->sm_count, h->stream);
-    h->k3_launches += 4;
+    h->k3_launches += 6;
     CK(cudaGetLastError());
     if (timing) { CK(cudaEventRecord(h->op_ev[3], h->stream)); h->op_timed[1] = true; }
     CK(cudaMemcpyAsync(h->h_small, h->d_goff + p.groups, 4, cudaMemcpyDeviceToHost, h->stream));

@@ -571,28 +571,44 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     }
 }
 
-// column scan: one CTA per group turns that group's per-warp counts into exclusive prefixes over the warps
-__global__ void __launch_bounds__(256) k3_scan_groups(const agr_k3_params p) {
-    __shared__ uint32_t part[256];
-    const uint32_t g = blockIdx.x, t = threadIdx.x;
-    const uint32_t per = (p.nwarps + 255u) / 256u;
-    const uint32_t w0 = t * per, w1 = min(p.nwarps, w0 + per);
+// column scan, two levels, every access coalesced across groups: the warp rows are cut into K3_SEGS segments;
+// (1) thread (seg, g) sums its segment of column g, (2) thread g scans the K3_SEGS partial sums, (3) thread (seg, g) rewrites
+// its segment as exclusive prefixes.  Afterwards matrix[w][g] = number of group-g items in warps < w.
+#define K3_SEGS 64u
+__global__ void __launch_bounds__(256) k3_seg_sum(const agr_k3_params p, uint32_t* __restrict__ partial) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
+    if (g >= p.groups) return;
+    const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
     uint32_t sum = 0;
     for (uint32_t w = w0; w < w1; ++w) sum += p.matrix[(size_t)w * p.groups + g];
-    part[t] = sum;
-    __syncthreads();
-    for (uint32_t off = 1; off < 256; off <<= 1) {
-        uint32_t a = (t >= off) ? part[t - off] : 0u;
-        __syncthreads();
-        part[t] += a;
-        __syncthreads();
+    partial[(size_t)seg * p.groups + g] = sum;
+}
+__global__ void __launch_bounds__(256) k3_seg_scan(const agr_k3_params p, uint32_t* __restrict__ partial) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.groups) return;
+    uint32_t run = 0;
+    for (uint32_t seg = 0; seg < K3_SEGS; ++seg) {
+        uint32_t* c = partial + (size_t)seg * p.groups + g;
+        const uint32_t v = *c; *c = run; run += v;
     }
-    uint32_t run = part[t] - sum;                       // exclusive prefix of this thread's slice
+    p.gtotal[g] = run;
+}
+__global__ void __launch_bounds__(256) k3_seg_apply(const agr_k3_params p, const uint32_t* __restrict__ partial) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
+    if (g >= p.groups) return;
+    const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
+    uint32_t run = partial[(size_t)seg * p.groups + g];
     for (uint32_t w = w0; w < w1; ++w) {
         uint32_t* cell = p.matrix + (size_t)w * p.groups + g;
         const uint32_t c = *cell; *cell = run; run += c;
     }
-    if (t == 255) p.gtotal[g] = part[255];
+}
+static void k3_scan_groups_launch(const agr_k3_params& p, cudaStream_t st) {
+    uint32_t* partial = p.gtotal + p.groups + 8;                 // scratch behind gtotal (sized by the engine)
+    const dim3 grid((p.groups + 255u) / 256u, K3_SEGS);
+    k3_seg_sum<<<grid, 256, 0, st>>>(p, partial);
+    k3_seg_scan<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p, partial);
+    k3_seg_apply<<<grid, 256, 0, st>>>(p, partial);
 }
 // exclusive scan over groups (one CTA, loops for groups > 1024); goff[groups] = total
 __global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
@@ -624,13 +640,13 @@ void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStr
     if (p.groups <= K3_SMEM_GROUPS) {
         const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 32 KiB
         k3_pass<false, true><<<blocks, 256, smem, st>>>(d, p);
-        k3_scan_groups<<<p.groups, 256, 0, st>>>(p);
+        k3_scan_groups_launch(p, st);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
         k3_pass<true, true><<<blocks, 256, smem, st>>>(d, p);
     } else {
         cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
         k3_pass<false, false><<<blocks, 256, 0, st>>>(d, p);
-        k3_scan_groups<<<p.groups, 256, 0, st>>>(p);
+        k3_scan_groups_launch(p, st);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
         k3_pass<true, false><<<blocks, 256, 0, st>>>(d, p);
     }

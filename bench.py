@@ -54,24 +54,26 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock / clock-event reasons sampled through NVML every ~2 ms during the timed region."""
+    """SM clock / clock-event reasons sampled through NVML in a spinning thread while the timed region runs (the region is
+    only a few milliseconds long), plus a slower background rate outside it."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.samples, self.reasons, self.stop_flag, self.t, self.max_mhz = index, [], 0, False, None, None
+        self.index, self.samples, self.stop_flag, self.t, self.max_mhz = index, [], False, None, None
+        self.fast, self.error = False, None
 
     def _run(self):
-        import pynvml as N
         try:
+            import pynvml as N
             N.nvmlInit()
             h = N.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
             get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop_flag:
-                self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
-                self.reasons |= int(get_reasons(h))
-                time.sleep(0.002)
+                self.samples.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(get_reasons(h))))
+                if not self.fast:
+                    time.sleep(0.002)
         except Exception as e:      # no NVML: report that rather than invent numbers
             self.error = repr(e)
 
@@ -80,18 +82,29 @@ class ClockSampler:
         self.t.start()
 
     def mark(self):
-        """samples taken from now on belong to the timed region"""
-        self.mark_at = len(self.samples)
+        """the timed region starts now"""
+        self.t0, self.fast = time.perf_counter(), True
+
+    def unmark(self):
+        self.t1, self.fast = time.perf_counter(), False
 
     def stop(self):
         self.stop_flag = True
         if self.t:
             self.t.join(timeout=2)
-        timed = self.samples[getattr(self, "mark_at", 0):] or self.samples
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        timed = [s for s in self.samples if t0 <= s[0] <= t1]
+        scope = "timed region"
+        if not timed:                  # region shorter than one NVML round trip: fall back to the samples around it
+            timed = [s for s in self.samples if t0 - 0.05 <= s[0] <= t1 + 0.05]
+            scope = "timed region +/- 50 ms"
         if not timed:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "error": getattr(self, "error", None)}
-        return {"sm_mhz": float(np.median(timed)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(v for k, v in self.REASONS.items() if self.reasons & k), "samples": len(timed)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "error": self.error}
+        reasons = 0
+        for s in timed:
+            reasons |= s[2]
+        return {"sm_mhz": float(np.median([s[1] for s in timed])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if reasons & k), "samples": len(timed), "scope": scope}
 
 
 def parallel_fill(A, out, first_index, wl, seed, nanos0, threads=16, mint=None):
@@ -271,6 +284,7 @@ def run_ours(args, wl, rank, world, local_rank):
     eng.sync()
     torch.cuda.synchronize()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.unmark()
     if dist:
         dist.barrier()
     dev_ms = ev0.elapsed_time(ev1)
