@@ -53,57 +53,73 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+out = open(sys.argv[2], "w", buffering=1)
+out.write("max %d\\n" % N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+while True:
+    out.write("%.6f %d %d\\n" % (time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), get_reasons(h)))
+    time.sleep(0.0002)
+"""
+
+
 class ClockSampler:
-    """SM clock / clock-event reasons sampled through NVML in a spinning thread while the timed region runs (the region is
-    only a few milliseconds long), plus a slower background rate outside it."""
+    """SM clock / clock-event reasons sampled through NVML by a SEPARATE process (NVML calls made from a process with a
+    busy CUDA context stall for milliseconds), ~5 kHz, wall-clock timestamps; the timed region is a few ms long."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.t, self.max_mhz = index, [], False, None, None
-        self.fast, self.error = False, None
-
-    def _run(self):
-        try:
-            import pynvml as N
-            N.nvmlInit()
-            h = N.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
-            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self.stop_flag:
-                self.samples.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), int(get_reasons(h))))
-                if not self.fast:
-                    time.sleep(0.002)
-        except Exception as e:      # no NVML: report that rather than invent numbers
-            self.error = repr(e)
+        import tempfile
+        self.index, self.proc, self.t0, self.t1 = index, None, 0.0, float("inf")
+        self.path = os.path.join(tempfile.gettempdir(), f"agr_clocks_{os.getpid()}_{index}.txt")
 
     def start(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(self.index), self.path],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
 
     def mark(self):
-        """the timed region starts now"""
-        self.t0, self.fast = time.perf_counter(), True
+        self.t0 = time.time()
 
     def unmark(self):
-        self.t1, self.fast = time.perf_counter(), False
+        self.t1 = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.t:
-            self.t.join(timeout=2)
-        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
-        timed = [s for s in self.samples if t0 <= s[0] <= t1]
-        scope = "timed region"
-        if not timed:                  # region shorter than one NVML round trip: fall back to the samples around it
-            timed = [s for s in self.samples if t0 - 0.05 <= s[0] <= t1 + 0.05]
-            scope = "timed region +/- 50 ms"
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": "sampler did not start"}
+        time.sleep(0.01)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        mx, rows = None, []
+        try:
+            for ln in open(self.path):
+                f = ln.split()
+                if f and f[0] == "max":
+                    mx = float(f[1])
+                elif len(f) == 3:
+                    rows.append((float(f[0]), float(f[1]), int(f[2])))
+            os.remove(self.path)
+        except Exception as e:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0, "error": repr(e)}
+        timed, scope = [r for r in rows if self.t0 <= r[0] <= self.t1], "timed region"
+        if len(timed) < 3:
+            timed, scope = [r for r in rows if self.t0 - 0.02 <= r[0] <= self.t1 + 0.02], "timed region +/- 20 ms"
         if not timed:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "error": self.error}
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0, "error": "no NVML sample near the timed region"}
         reasons = 0
-        for s in timed:
-            reasons |= s[2]
-        return {"sm_mhz": float(np.median([s[1] for s in timed])), "sm_max_mhz": self.max_mhz,
+        for r in timed:
+            reasons |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in timed])), "sm_max_mhz": mx,
                 "reasons": sorted(v for k, v in self.REASONS.items() if reasons & k), "samples": len(timed), "scope": scope}
 
 
