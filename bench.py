@@ -53,16 +53,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-SAMPLER_SRC = r"""
+SAMPLER_SRC = """
 import sys, time
 import pynvml as N
 N.nvmlInit()
 h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
 get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
 out = open(sys.argv[2], "w", buffering=1)
-out.write("max %d\\n" % N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+print("max", N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), file=out)
 while True:
-    out.write("%.6f %d %d\\n" % (time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), get_reasons(h)))
+    print("%.6f" % time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), get_reasons(h), file=out)
     time.sleep(0.0002)
 """
 
