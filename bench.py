@@ -85,6 +85,18 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout=10.0):
+        """block until the sampler process has written its first sample (it needs ~0.5 s to import NVML)"""
+        t = time.time()
+        while time.time() - t < timeout:
+            try:
+                if os.path.getsize(self.path) > 64:
+                    return True
+            except OSError:
+                pass
+            time.sleep(0.01)
+        return False
+
     def mark(self):
         self.t0 = time.time()
 
@@ -264,6 +276,8 @@ def run_ours(args, wl, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     B, W, S = wl["records"], args.warmup, args.steps
     e_steps, e_warm = min(S, args.e2e_steps), 1
     rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B + (B if world > 1 else 0) * 2)
@@ -281,8 +295,7 @@ def run_ours(args, wl, rank, world, local_rank):
     for s in range(W + S):                                       # records resident in HBM before the timed region
         eng.synth_fill_rows(s * B, first + s * B, B, mint_base=mint_base, **synth)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_ready()
     for s in range(W):
         eng.ingest_rows_async(first + s * B, B)
     eng.sync()
