@@ -1284,20 +1284,21 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     return 0;
 }
 
-int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info) {
-    if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
+// Shared first half of the exchanges: stage the caller's items, find every item's owner (K4 count + scan), swap the
+// per-peer counts with one grouped send/recv, and lay out the owner-major send offsets and the source-major receive offsets.
+struct exchange_plan {
+    agr_k4_params p{};
+    uint32_t G = 1, me = 0, scnt[32], rcnt[32], soff[33], roff[33], n_local = 0, n_recv = 0;
+};
+static int exchange_begin(agr_handle* h, const void* items, uint32_t item_bytes, uint32_t agent_off, uint32_t n, exchange_plan& x) {
     if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
-    const uint32_t G = (uint32_t)h->world, me = (uint32_t)h->rank;
+    x.G = (uint32_t)h->world; x.me = (uint32_t)h->rank;
     cudaStream_t st = h->stream;
     uint32_t* d_gtotal = h->d_k4cnt; uint32_t* d_goff = h->d_k4cnt + 40; uint32_t* d_rcnt = h->d_k4cnt + 80;
-    const size_t S = sizeof(agr_outcome);
-    // outcomes -> staging (the record staging buffer is reused), owners + counts
-    if (n) CK(cudaMemcpyAsync(h->d_stage, outs, (size_t)n * S, cudaMemcpyHostToDevice, st));
-    agr_k4_params p{};
-    p.items = h->d_stage; p.item_bytes = (uint32_t)S; p.agent_off = 16; p.n = n; p.G = G; p.me = me;
+    if (n) CK(cudaMemcpyAsync(h->d_stage, items, (size_t)n * item_bytes, cudaMemcpyHostToDevice, st));
+    agr_k4_params& p = x.p;
+    p.items = h->d_stage; p.item_bytes = item_bytes; p.agent_off = agent_off; p.n = n; p.G = x.G; p.me = x.me;
     uint32_t per = (n + h->k4_nwarps - 1) / std::max<uint32_t>(1, h->k4_nwarps);
     per = std::max<uint32_t>(32, (per + 31) & ~31u);
     p.per_warp = per; p.nwarps = std::max<uint32_t>(1, (n + per - 1) / per);
@@ -1306,136 +1307,108 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
     h->k4_launches += 2;
     CK(cudaGetLastError());
     NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
+    for (uint32_t q = 0; q < x.G; ++q) {
         NK(g_nccl.Send(d_gtotal + q, 1, ncclUint32, (int)q, h->comm, st));
         NK(g_nccl.Recv(d_rcnt + q, 1, ncclUint32, (int)q, h->comm, st));
     }
     NK(g_nccl.GroupEnd());
-    uint32_t* hc = h->h_small;
-    CK(cudaMemcpyAsync(hc, d_gtotal, G * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hc + 32, d_rcnt, G * 4, cudaMemcpyDeviceToHost, st));
+    uint32_t* hc = h->h_small;                       // [0..31] send counts, [32..63] receive counts
+    CK(cudaMemcpyAsync(hc, d_gtotal, x.G * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc + 32, d_rcnt, x.G * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    uint32_t scnt[32], rcnt[32], soff[33], roff[33];
-    soff[0] = 0; roff[0] = 0;
-    for (uint32_t q = 0; q < G; ++q) { scnt[q] = hc[q]; rcnt[q] = (q == me) ? 0 : hc[32 + q]; soff[q + 1] = soff[q] + scnt[q]; roff[q + 1] = roff[q] + rcnt[q]; }
-    const uint32_t n_local = scnt[me], n_recv = roff[G], total = n_local + n_recv;
-    if (total > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more outcomes than 2 * max_batch");
-    // pack: own outcomes straight into the K2 input array, peer segments into the send buffer
-    p.local_dst = (uint8_t*)h->d_outs; p.send_dst = h->d_send;
-    if (n) { agr_launch_k4_scatter(p, st); h->k4_launches += 1; CK(cudaGetLastError()); }
+    x.soff[0] = 0; x.roff[0] = 0;
+    for (uint32_t q = 0; q < x.G; ++q) {
+        x.scnt[q] = hc[q]; x.rcnt[q] = (q == x.me) ? 0 : hc[32 + q];
+        x.soff[q + 1] = x.soff[q] + x.scnt[q]; x.roff[q + 1] = x.roff[q] + x.rcnt[q];
+    }
+    x.n_local = x.scnt[x.me]; x.n_recv = x.roff[x.G];
+    if (x.n_local + x.n_recv > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more items than 2 * max_batch");
+    return 0;
+}
+// the all-to-all itself: peer segments of `send` to their owners, landing at recv_base in source-rank order
+static int exchange_payload(agr_handle* h, const exchange_plan& x, const uint8_t* send, uint8_t* recv_base, size_t item_bytes) {
     NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
-        if (q == me) continue;
-        if (scnt[q]) NK(g_nccl.Send(h->d_send + (size_t)soff[q] * S, (size_t)scnt[q] * S, ncclUint8, (int)q, h->comm, st));
-        if (rcnt[q]) NK(g_nccl.Recv((uint8_t*)(h->d_outs + n_local) + (size_t)roff[q] * S, (size_t)rcnt[q] * S, ncclUint8, (int)q, h->comm, st));
+    for (uint32_t q = 0; q < x.G; ++q) {
+        if (q == x.me) continue;
+        if (x.scnt[q]) NK(g_nccl.Send(send + (size_t)x.soff[q] * item_bytes, (size_t)x.scnt[q] * item_bytes, ncclUint8, (int)q, h->comm, h->stream));
+        if (x.rcnt[q]) NK(g_nccl.Recv(recv_base + (size_t)x.roff[q] * item_bytes, (size_t)x.rcnt[q] * item_bytes, ncclUint8, (int)q, h->comm, h->stream));
     }
     NK(g_nccl.GroupEnd());
-    // K2 at the owner over local + received outcomes
-    if (total) {
-        h->d.rows_hi = (uint32_t)h->rows_used;
-        agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, st);
-        agr_launch_k2(h->d, h->k2, total, st);
-        h->k2_launches += 7;
-        CK(cudaGetLastError());
-    }
-    // result codes back to the reporters, restored to the caller's order
-    int32_t* d_rback = (int32_t*)h->d_vback;
+    return 0;
+}
+// results of the received items back to where they came from (owner-major at the reporter), then the caller's order
+static int exchange_results(agr_handle* h, const exchange_plan& x, const uint8_t* res_all /*local first, then received*/, uint8_t* back,
+                            uint8_t* out_dev, uint32_t res_bytes) {
     NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
-        if (q == me) continue;
-        if (rcnt[q]) NK(g_nccl.Send(h->k2.results + n_local + roff[q], (size_t)rcnt[q] * 4, ncclUint8, (int)q, h->comm, st));
-        if (scnt[q]) NK(g_nccl.Recv(d_rback + soff[q], (size_t)scnt[q] * 4, ncclUint8, (int)q, h->comm, st));
+    for (uint32_t q = 0; q < x.G; ++q) {
+        if (q == x.me) continue;
+        if (x.rcnt[q]) NK(g_nccl.Send(res_all + (size_t)(x.n_local + x.roff[q]) * res_bytes, (size_t)x.rcnt[q] * res_bytes, ncclUint8, (int)q, h->comm, h->stream));
+        if (x.scnt[q]) NK(g_nccl.Recv(back + (size_t)x.soff[q] * res_bytes, (size_t)x.scnt[q] * res_bytes, ncclUint8, (int)q, h->comm, h->stream));
     }
     NK(g_nccl.GroupEnd());
-    if (n) {
-        agr_launch_k4_unpermute(p, h->k2.results, d_rback, h->d_vout, 4, st);
+    if (x.p.n) {
+        agr_launch_k4_unpermute(x.p, res_all, back, out_dev, res_bytes, h->stream);
         h->k4_launches += 1;
         CK(cudaGetLastError());
-        if (results) CK(cudaMemcpyAsync(h->h_results, h->d_vout, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    if (n && results) memcpy(results, h->h_results, (size_t)n * 4);
-    if (info) {
-        memset(info, 0, sizeof *info);
-        info->world = G; info->rank = me; info->n_local = n_local; info->n_sent = n - n_local; info->n_received = n_recv;
-        for (uint32_t q = 0; q < G; ++q) { info->sent_to[q] = (q == me) ? 0 : scnt[q]; info->received_from[q] = rcnt[q]; }
     }
     return 0;
+}
+static void exchange_fill_info(const exchange_plan& x, uint32_t n, uint64_t first, agr_exchange_info* info) {
+    if (!info) return;
+    memset(info, 0, sizeof *info);
+    info->world = x.G; info->rank = x.me; info->n_local = x.n_local; info->n_sent = n - x.n_local; info->n_received = x.n_recv; info->first_rid = first;
+    for (uint32_t q = 0; q < x.G; ++q) { info->sent_to[q] = (q == x.me) ? 0 : x.scnt[q]; info->received_from[q] = x.rcnt[q]; }
 }
 
 int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
-    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
-    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
-    const uint32_t G = (uint32_t)h->world, me = (uint32_t)h->rank;
-    cudaStream_t st = h->stream;
-    uint32_t* d_gtotal = h->d_k4cnt; uint32_t* d_goff = h->d_k4cnt + 40; uint32_t* d_rcnt = h->d_k4cnt + 80;
-    // 1. batch -> staging, owners + per-owner counts (K4 count + scan)
-    if (n) CK(cudaMemcpyAsync(h->d_stage, recs, (size_t)n * AGR_REC, cudaMemcpyHostToDevice, st));
-    agr_k4_params p{};
-    p.items = h->d_stage; p.item_bytes = AGR_REC; p.agent_off = AGR_OFF_AGENT_ID; p.n = n; p.G = G; p.me = me;
-    uint32_t per = (n + h->k4_nwarps - 1) / std::max<uint32_t>(1, h->k4_nwarps);
-    per = std::max<uint32_t>(32, (per + 31) & ~31u);
-    p.per_warp = per; p.nwarps = std::max<uint32_t>(1, (n + per - 1) / per);
-    p.matrix = h->d_k4matrix; p.gtotal = d_gtotal; p.goff = d_goff; p.owner = h->d_owner; p.perm = h->d_perm;
-    agr_launch_k4_count(p, st);
-    h->k4_launches += 2;
-    CK(cudaGetLastError());
-    // 2. counts all-to-all (one int per peer), then both count vectors to the host
-    NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
-        NK(g_nccl.Send(d_gtotal + q, 1, ncclUint32, (int)q, h->comm, st));
-        NK(g_nccl.Recv(d_rcnt + q, 1, ncclUint32, (int)q, h->comm, st));
-    }
-    NK(g_nccl.GroupEnd());
-    uint32_t* hc = h->h_small;                       // [0..31] send counts, [32..63] recv counts
-    CK(cudaMemcpyAsync(hc, d_gtotal, G * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hc + 32, d_rcnt, G * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    uint32_t scnt[32], rcnt[32], soff[33], roff[33];
-    soff[0] = 0; roff[0] = 0;
-    for (uint32_t q = 0; q < G; ++q) { scnt[q] = hc[q]; rcnt[q] = (q == me) ? 0 : hc[32 + q]; soff[q + 1] = soff[q] + scnt[q]; roff[q + 1] = roff[q] + rcnt[q]; }
-    const uint32_t n_local = scnt[me], n_recv = roff[G], total = n_local + n_recv;
-    if (total > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more records than 2 * max_batch");
+    exchange_plan x;
+    TRY(exchange_begin(h, recs, AGR_REC, AGR_OFF_AGENT_ID, n, x));
+    const uint32_t total = x.n_local + x.n_recv;
     uint64_t first = 0;
     TRY(reserve_rows_locked(h, total, &first));
-    // 3. stable pack: own records straight into their slab rows, peer segments into the send buffer
-    p.local_dst = h->d.slab + first * AGR_REC; p.send_dst = h->d_send;
-    if (n) { agr_launch_k4_scatter(p, st); h->k4_launches += 1; CK(cudaGetLastError()); }
-    // 4. the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
-    uint8_t* recv_base = h->d.slab + (first + n_local) * AGR_REC;
-    NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
-        if (q == me) continue;
-        if (scnt[q]) NK(g_nccl.Send(h->d_send + (size_t)soff[q] * AGR_REC, (size_t)scnt[q] * AGR_REC, ncclUint8, (int)q, h->comm, st));
-        if (rcnt[q]) NK(g_nccl.Recv(recv_base + (size_t)roff[q] * AGR_REC, (size_t)rcnt[q] * AGR_REC, ncclUint8, (int)q, h->comm, st));
-    }
-    NK(g_nccl.GroupEnd());
-    // 5. K1 at the owner over local + received rows (received rows were unpacked by the receive itself)
+    // stable pack: own records straight into their slab rows, peer segments into the send buffer
+    x.p.local_dst = h->d.slab + first * AGR_REC; x.p.send_dst = h->d_send;
+    if (n) { agr_launch_k4_scatter(x.p, h->stream); h->k4_launches += 1; CK(cudaGetLastError()); }
+    // the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
+    TRY(exchange_payload(h, x, h->d_send, h->d.slab + (first + x.n_local) * AGR_REC, AGR_REC));
+    // K1 at the owner over local + received rows (received rows were unpacked by the receive itself)
     if (total) TRY(launch_k1_locked(h, first, total, h->d_xverd));
-    // 6. verdicts back to where the records came from, then restored to the caller's order
-    NK(g_nccl.GroupStart());
-    for (uint32_t q = 0; q < G; ++q) {
-        if (q == me) continue;
-        if (rcnt[q]) NK(g_nccl.Send(h->d_xverd + n_local + roff[q], (size_t)rcnt[q] * sizeof(agr_verdict), ncclUint8, (int)q, h->comm, st));
-        if (scnt[q]) NK(g_nccl.Recv(h->d_vback + soff[q], (size_t)scnt[q] * sizeof(agr_verdict), ncclUint8, (int)q, h->comm, st));
-    }
-    NK(g_nccl.GroupEnd());
-    if (n) {
-        agr_launch_k4_unpermute(p, h->d_xverd, h->d_vback, h->d_vout, sizeof(agr_verdict), st);
-        h->k4_launches += 1;
-        CK(cudaGetLastError());
-        if (out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_vout, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
+    // verdicts back to where the records came from, restored to the caller's order
+    TRY(exchange_results(h, x, (const uint8_t*)h->d_xverd, (uint8_t*)h->d_vback, (uint8_t*)h->d_vout, sizeof(agr_verdict)));
+    if (n && out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_vout, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     if (n && out) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
-    if (info) {
-        memset(info, 0, sizeof *info);
-        info->world = G; info->rank = me; info->n_local = n_local; info->n_sent = n - n_local; info->n_received = n_recv; info->first_rid = first;
-        for (uint32_t q = 0; q < G; ++q) { info->sent_to[q] = (q == me) ? 0 : scnt[q]; info->received_from[q] = rcnt[q]; }
+    exchange_fill_info(x, n, first, info);
+    return 0;
+}
+
+int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info) {
+    if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    exchange_plan x;
+    TRY(exchange_begin(h, outs, sizeof(agr_outcome), 16, n, x));
+    const uint32_t total = x.n_local + x.n_recv;
+    // pack: own outcomes straight into the K2 input array, peer segments into the send buffer
+    x.p.local_dst = (uint8_t*)h->d_outs; x.p.send_dst = h->d_send;
+    if (n) { agr_launch_k4_scatter(x.p, h->stream); h->k4_launches += 1; CK(cudaGetLastError()); }
+    TRY(exchange_payload(h, x, h->d_send, (uint8_t*)(h->d_outs + x.n_local), sizeof(agr_outcome)));
+    // K2 at the owner over local + received outcomes (own host first, then peers by rank)
+    if (total) {
+        h->d.rows_hi = (uint32_t)h->rows_used;
+        agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, h->stream);
+        agr_launch_k2(h->d, h->k2, total, h->stream);
+        h->k2_launches += 7;
+        CK(cudaGetLastError());
     }
+    TRY(exchange_results(h, x, (const uint8_t*)h->k2.results, (uint8_t*)h->d_vback, (uint8_t*)h->d_vout, 4));
+    if (n && results) CK(cudaMemcpyAsync(h->h_results, h->d_vout, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n && results) memcpy(results, h->h_results, (size_t)n * 4);
+    exchange_fill_info(x, n, 0, info);
     return 0;
 }
 
