@@ -586,7 +586,6 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
     CK(cudaEventRecord(h->chunk_ev[nchunks], h->stream));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[nchunks], 0));
     int bk = 0;
-    static const bool early_d2h = getenv("AGR_EARLY_D2H") != nullptr;      // A/B switch for the read-back placement
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint32_t off = c * AGR_INGEST_CHUNK, cn = std::min(AGR_INGEST_CHUNK, n - off);
         uint8_t* dst = h->d.slab + (first + off) * AGR_REC;
@@ -607,18 +606,10 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
         CK(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
         TRY(launch_k1_locked(h, first + off, cn, out ? h->d_verdicts + off : nullptr, ids ? h->d_ids + (size_t)off * 16 : nullptr));
-        if (early_d2h) {
-            if (out) CK(cudaMemcpyAsync((out_pinned ? out : h->h_verdicts) + off, h->d_verdicts + off, (size_t)cn * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
-            if (ids) CK(cudaMemcpyAsync((ids_pinned ? (uint8_t*)ids : h->h_ids) + (size_t)off * 16, h->d_ids + (size_t)off * 16, (size_t)cn * 16, cudaMemcpyDeviceToHost, h->stream));
-        }
     }
-    // The read-backs are small (8 + 16 B per record) but a D2H running beside the H2D stream slows the big copy by ~20 %
-    // on this link (10.1 -> 12.1 ms per 512 MiB measured), so they are issued once, after the last K1 — i.e. after the
-    // last H2D chunk has landed.
-    if (!early_d2h) {
-        if (out) CK(cudaMemcpyAsync(out_pinned ? out : h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
-        if (ids) CK(cudaMemcpyAsync(ids_pinned ? (uint8_t*)ids : h->h_ids, h->d_ids, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
-    }
+    // the read-backs are small (8 + 16 B per record): one copy each, after the last K1
+    if (out) CK(cudaMemcpyAsync(out_pinned ? out : h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
+    if (ids) CK(cudaMemcpyAsync(ids_pinned ? (uint8_t*)ids : h->h_ids, h->d_ids, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (out && !out_pinned) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
     if (ids && !ids_pinned) memcpy(ids, h->h_ids, (size_t)n * 16);

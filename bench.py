@@ -346,18 +346,23 @@ def run_ours(args, wl, rank, world, local_rank):
     if args.diag_flags:
         print("WARNING: diagnostic flags set; numbers below are for attribution only", file=sys.stderr)
     # ---- e2e through the public C-ABI call with pinned host buffers (H2D + kernels + D2H verdicts timed)
-    pin = eng.pinned(B)
+    # a two-slot pinned ring, like a host producer would use: the NEXT step's records are written while (here: before) the
+    # current slot is ingested, so the slot being DMA'd is not sitting dirty in the host caches
+    pins = [eng.pinned(B), eng.pinned(B)]
     pin_v = eng.pinned(B, A.verdict_dtype)
     pin_ids = eng.pinned(B * 16, np.uint8)
     ids_view = pin_ids.array.reshape(B, 16)
     e_times = []
     launches_before = st["k1_launches"]
+    e_mint = (eng, first) if id_flags else None
+    parallel_fill(A, pins[0].array, (W + S) * B, wl, synth["seed"], nanos0, mint=e_mint)
     for s in range(e_warm + e_steps):
-        parallel_fill(A, pin.array, (W + S + s) * B, wl, synth["seed"], nanos0, mint=(eng, first) if id_flags else None)
+        if s + 1 < e_warm + e_steps:
+            parallel_fill(A, pins[(s + 1) % 2].array, (W + S + s + 1) * B, wl, synth["seed"], nanos0, mint=e_mint)
         if dist:
             dist.barrier()
         t = time.perf_counter()
-        eng.ingest_ex(pin.array, pin_v.array, ids_view)          # verdicts AND Request.IDs back on the host
+        eng.ingest_ex(pins[s % 2].array, pin_v.array, ids_view)   # verdicts AND Request.IDs back on the host
         dt = time.perf_counter() - t
         verdicts = pin_v.array
         if s >= e_warm:
@@ -366,7 +371,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if id_flags:
         assert (ids_view[:64] == eng.mint_ids(eng.stats()["rows_used"] - B, 64)).all()
     del verdicts, ids_view
-    pin.free(); pin_v.free(); pin_ids.free()
+    pins[0].free(); pins[1].free(); pin_v.free(); pin_ids.free()
     e_ms = 1e3 * sum(e_times) / len(e_times)
     # ---- secondary kernels: K2 over one batch of outcomes, K3 replay scan over the slab (device time)
     secondary = None
