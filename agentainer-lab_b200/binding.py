@@ -39,7 +39,7 @@ class AgrStats(C.Structure):
         "rows_used", "rows_cap", "ingested", "stored", "replay_flagged", "dedupe_hits", "forwarded", "queued",
         "unavailable", "not_found", "dup_ids", "completions", "completion_misses", "failures", "dead_lettered",
         "dial_errors", "replay_scans", "replay_dispatched", "completed_log_len", "failed_log_len",
-        "k1_launches", "k2_launches", "k3_launches", "k4_launches")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
+        "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
 
 
 class AgrExchangeInfo(C.Structure):
@@ -62,6 +62,7 @@ ABI_SYMBOLS = [
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
+    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json",
 ]
 
 _lib = None
@@ -127,6 +128,11 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_agent_shard": (u32, [C.c_char_p, u32]),
         "agr_store_response_body": (i32, [vp, C.c_char_p, vp, vp, u32]),
         "agr_get_response_body": (i32, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]),
+        "agr_store_response": (i32, [vp, C.c_char_p, vp, vp, u32, vp, u32]),
+        "agr_store_error_text": (i32, [vp, C.c_char_p, vp, vp, u32]),
+        "agr_get_record_json": (i32, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]),
+        "agr_pending_json": (i32, [vp, C.c_char_p, vp, u64, C.POINTER(u64), C.POINTER(u32)]),
+        "agr_rows_json": (i32, [vp, u64, u32, i32, vp, u64, C.POINTER(u64), vp]),
         "agr_snapshot": (i32, [vp, C.c_char_p]),
         "agr_restore": (i32, [C.POINTER(AgrConfig), C.c_char_p, C.POINTER(vp)]),
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
@@ -219,10 +225,10 @@ class Engine:
     """One shard (one GPU) of the request engine.  Thin wrapper: every method is one C-ABI call."""
 
     def __init__(self, *, device=-1, slab_rows=1 << 16, max_agents=1024, max_batch=0, flags=0, table_slots=0,
-                 log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0, restore_from=None):
+                 log_entries=0, k1_variant=0, id_secret=0, vslab_bytes=0, resp_bytes=0, restore_from=None):
         self.lib = load_library()
         cfg = AgrConfig(device, flags, slab_rows, table_slots, max_agents, max_batch or min(slab_rows, 1 << 20),
-                        log_entries, id_secret, vslab_bytes, 0, k1_variant, 0)
+                        log_entries, id_secret, vslab_bytes, resp_bytes, k1_variant, 0)
         self.mint = bool(flags & K.AGR_CFG_MINT_IDS)
         self.varlen = bool(flags & K.AGR_CFG_VARLEN)
         h = C.c_void_p()
@@ -446,6 +452,63 @@ class Engine:
             return False
         _check(self.lib, rc)
         return True
+
+    def store_response(self, agent_id: str, request_id: bytes, headers: bytes, body: bytes) -> bool:
+        """requests.Response of StoreResponse (requests.go:142-147): flattened first-value headers + body."""
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        hb = (C.c_uint8 * max(1, len(headers))).from_buffer_copy(headers or b"\0")
+        bb = (C.c_uint8 * max(1, len(body))).from_buffer_copy(body or b"\0")
+        rc = self.lib.agr_store_response(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), C.cast(hb, C.c_void_p), len(headers),
+                                         C.cast(bb, C.c_void_p), len(body))
+        if rc == K.AGR_ENOTFOUND:
+            return False
+        _check(self.lib, rc)
+        return True
+
+    def store_error_text(self, agent_id: str, request_id: bytes, text: bytes) -> bool:
+        """Request.Error = err.Error() (requests.go:244)."""
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        tb = (C.c_uint8 * max(1, len(text))).from_buffer_copy(text or b"\0")
+        rc = self.lib.agr_store_error_text(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), C.cast(tb, C.c_void_p), len(text))
+        if rc == K.AGR_ENOTFOUND:
+            return False
+        _check(self.lib, rc)
+        return True
+
+    def get_record_json(self, agent_id: str, request_id: bytes) -> Optional[bytes]:
+        """The value of agent:{a}:requests:{r}: json.Marshal(requests.Request) (requests.go:101,169,264)."""
+        rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
+        cap = 1 << 16
+        while True:
+            out = (C.c_uint8 * cap)()
+            ln = C.c_uint32()
+            rc = self.lib.agr_get_record_json(self.h, agent_id.encode(), C.cast(rid, C.c_void_p), C.cast(out, C.c_void_p), cap, C.byref(ln))
+            if rc == K.AGR_ENOTFOUND:
+                return None
+            if rc == K.AGR_ECAP:
+                cap = int(ln.value)
+                continue
+            _check(self.lib, rc)
+            return bytes(out[: ln.value])
+
+    def pending_json(self, agent_id: str) -> Tuple[bytes, int]:
+        """json.Marshal(GetPendingRequests(agent)) (requests.go:197-225, server.go:646-650) and the entry count."""
+        ln, cnt = C.c_uint64(), C.c_uint32()
+        _check(self.lib, self.lib.agr_pending_json(self.h, agent_id.encode(), None, 0, C.byref(ln), C.byref(cnt)))
+        out = np.zeros(max(1, ln.value), dtype=np.uint8)
+        _check(self.lib, self.lib.agr_pending_json(self.h, agent_id.encode(), _ptr(out), out.size, C.byref(ln), C.byref(cnt)))
+        return out[: ln.value].tobytes(), int(cnt.value)
+
+    def rows_json(self, first_rid: int, n: int, as_array: bool = False, fetch: bool = True):
+        """Rows [first_rid, +n) in wire form.  fetch=False leaves the bytes on the device and returns only the length."""
+        ln = C.c_uint64()
+        _check(self.lib, self.lib.agr_rows_json(self.h, first_rid, n, int(as_array), None, 0, C.byref(ln), None))
+        if not fetch:
+            return int(ln.value)
+        out = np.zeros(max(1, ln.value), dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        _check(self.lib, self.lib.agr_rows_json(self.h, first_rid, n, int(as_array), _ptr(out), out.size, C.byref(ln), _ptr(offs)))
+        return out[: ln.value].tobytes(), offs
 
     def get_response_body(self, agent_id: str, request_id: bytes) -> Optional[bytes]:
         rid = (C.c_uint8 * 16).from_buffer_copy(request_id)

@@ -8,6 +8,7 @@
 //   aux[rid]  : u32  response status | error kind                                (K2 writes)
 //   cksum[rid]: u64  position-weighted checksum of the 512 B record              (K1 writes)
 //   head[rid] : u32  K2 per-batch chain head of the row
+//   ptime[rid]: u64  processed_at / received_at of the latest stored response        (K2 writes, K5 reads)
 //   table     : hash-id mode only: open-addressing dedupe index, 32 B slots {id128, ~rid}, 128-bit CAS on the id
 //               (absent with engine-minted ids, where the id is a keyed bijection of rid: agr_mint_id below)
 //   logs      : completed / failed append-only logs of rid (per-agent lists are stable filters of them)
@@ -42,6 +43,9 @@
 #define ST_INQ 0x8u        // member of agent:{a}:requests:pending
 #define ST_INFLIGHT 0x10u  // extension bookkeeping (never reference-visible): forward issued, no outcome yet
 #define ST_STORED 0x20u    // row holds a record that StoreRequest persisted
+#define ST_RESPONDED 0x40u // StoreResponse has run on it: Response / ProcessedAt are set (requests.go:165-167)
+#define ST_RESP_RT 0x80u   // the stored Response has been through a later Unmarshal + Marshal (only the JSON form of
+#define ST_ERR_RT 0x01000000u  // invalid UTF-8 depends on it: "\ufffd" when first written, EF BF BD afterwards); same for Error
 #define ST_RETRY_SHIFT 8
 #define ST_RETRY_MASK 0xff00u
 #define ST_MAX_SHIFT 16

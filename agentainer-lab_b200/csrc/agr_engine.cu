@@ -88,6 +88,12 @@ struct agr_handle {
     // stored responses: byte slab + per-row (offset, length), written off the hot path
     uint8_t* d_resp = nullptr; uint64_t resp_used = 0, resp_cap = 0;
     unsigned long long* d_resp_off = nullptr; uint32_t* d_resp_len = nullptr;
+    uint32_t* d_resp_hlen = nullptr;           // leading bytes of the stored response that are its flattened headers
+    unsigned long long* d_err_off = nullptr; uint32_t* d_err_len = nullptr;   // Request.Error text, same byte slab
+    // K5 (JSON wire form) scratch
+    uint32_t* d_jlen = nullptr; unsigned long long* d_joff = nullptr; unsigned long long* d_jchunk = nullptr; uint32_t j_cap = 0;
+    uint8_t* d_json = nullptr; uint64_t json_cap = 0;
+    uint64_t k5_launches = 0;
     // flat-combining front-end for concurrent small ingests (AGR_CFG_COMBINE)
     std::mutex cmu; std::condition_variable ccv;
     agr_record* c_ring = nullptr;              // pinned [AGR_COMBINE_RING]
@@ -121,8 +127,8 @@ struct agr_handle {
     agr_verdict* d_vout = nullptr;             // caller-order verdicts [max_batch]
     // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
     std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
-    cudaEvent_t op_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] last K2 group, [2,3] last K3 select group
-    bool op_timed[2] = {false, false};
+    cudaEvent_t op_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0,1] last K2 group, [2,3] last K3 select group, [4,5] last K5 encode
+    bool op_timed[3] = {false, false, false};
 };
 #define AGR_TIMING_RING 1024
 #define AGR_COMBINE_RING 16384u
@@ -271,6 +277,10 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->d_resp, (size_t)c.resp_bytes, false));
     TRY(dev_alloc(h, &h->d_resp_off, c.slab_rows, true));
     TRY(dev_alloc(h, &h->d_resp_len, c.slab_rows, true));
+    TRY(dev_alloc(h, &h->d_resp_hlen, c.slab_rows, true));
+    TRY(dev_alloc(h, &h->d_err_off, c.slab_rows, true));
+    TRY(dev_alloc(h, &h->d_err_len, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.ptime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
     d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
     d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
@@ -1020,20 +1030,43 @@ static int resolve_one_locked(agr_handle* h, const char* agent_id, const uint8_t
     return 0;
 }
 
-int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* bytes, uint32_t len) {
-    if (!h || !agent_id || !request_id || (len && !bytes)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
+// which: 0 = response (hdr_len leading bytes are its flattened headers), 1 = error text
+static int store_bytes_locked(agr_handle* h, const char* agent_id, const uint8_t request_id[16], int which, const uint8_t* a, uint32_t alen,
+                              const uint8_t* b, uint32_t blen) {
     uint32_t rid = 0;
     TRY(resolve_one_locked(h, agent_id, request_id, &rid));
+    const uint32_t len = alen + blen;
     if (h->resp_used + len > h->resp_cap) return fail(AGR_ENOSPC, "response slab full");
     const unsigned long long off = h->resp_used;
     h->resp_used += (len + 15u) & ~15ull;
-    if (len) CK(cudaMemcpyAsync(h->d_resp + off, bytes, len, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_resp_off + rid, &off, 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_resp_len + rid, &len, 4, cudaMemcpyHostToDevice, h->stream));
+    if (alen) CK(cudaMemcpyAsync(h->d_resp + off, a, alen, cudaMemcpyHostToDevice, h->stream));
+    if (blen) CK(cudaMemcpyAsync(h->d_resp + off + alen, b, blen, cudaMemcpyHostToDevice, h->stream));
+    if (which == 0) {
+        CK(cudaMemcpyAsync(h->d_resp_off + rid, &off, 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_resp_len + rid, &len, 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_resp_hlen + rid, &alen, 4, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(h->d_err_off + rid, &off, 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_err_len + rid, &len, 4, cudaMemcpyHostToDevice, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+int agr_store_response(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* headers, uint32_t hdr_len,
+                       const uint8_t* body, uint32_t body_len) {
+    if (!h || !agent_id || !request_id || (hdr_len && !headers) || (body_len && !body)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return store_bytes_locked(h, agent_id, request_id, 0, headers, hdr_len, body, body_len);
+}
+int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* bytes, uint32_t len) {
+    return agr_store_response(h, agent_id, request_id, nullptr, 0, bytes, len);
+}
+int agr_store_error_text(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const char* text, uint32_t len) {
+    if (!h || !agent_id || !request_id || (len && !text)) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return store_bytes_locked(h, agent_id, request_id, 1, (const uint8_t*)text, len, nullptr, 0);
 }
 
 int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
@@ -1052,9 +1085,113 @@ int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t req
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ K5: JSON wire form
+// Encodes n records (rows d_rids[0..n) or first_rid + [0..n)) into h->d_json; *total = bytes.  Offsets stay in h->d_joff.
+static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint32_t first_rid, uint32_t n, bool array, uint64_t* total) {
+    *total = 0;
+    if (n == 0) return 0;
+    if (n > h->j_cap) {
+        const uint32_t cap = std::max<uint32_t>(n, 1024);
+        TRY(dev_alloc(h, &h->d_jlen, cap, false));
+        TRY(dev_alloc(h, &h->d_joff, (size_t)cap + 1, false));
+        TRY(dev_alloc(h, &h->d_jchunk, (size_t)agr_k5_chunks(cap) + 1, false));
+        h->j_cap = cap;
+    }
+    agr_k5_params p{};
+    p.rids = d_rids; p.first_rid = first_rid; p.n = n; p.array = array ? 1u : 0u;
+    p.len = h->d_jlen; p.off = h->d_joff; p.chunk_sum = h->d_jchunk; p.out = nullptr;
+    p.bytes = h->d_resp; p.resp_off = h->d_resp_off; p.resp_len = h->d_resp_len; p.resp_hlen = h->d_resp_hlen;
+    p.err_off = h->d_err_off; p.err_len = h->d_err_len; p.ptime = h->d.ptime;
+    const bool timing = (h->cfg.flags & AGR_CFG_TIMING) != 0;
+    if (timing) {
+        for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(h->op_ev[4], h->stream));
+    }
+    agr_launch_k5_measure(h->d, p, h->stream);
+    CK(cudaGetLastError());
+    unsigned long long tot = 0;
+    CK(cudaMemcpyAsync(&tot, h->d_jchunk + agr_k5_chunks(n), 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (tot + 16 > h->json_cap) {
+        const uint64_t cap = std::max<uint64_t>(tot + tot / 4 + 16, 1 << 16);
+        TRY(dev_alloc(h, &h->d_json, (size_t)cap, false));
+        h->json_cap = cap;
+    }
+    p.out = h->d_json;
+    agr_launch_k5_emit(h->d, p, h->stream);
+    CK(cudaGetLastError());
+    if (timing) { CK(cudaEventRecord(h->op_ev[5], h->stream)); h->op_timed[2] = true; }
+    h->k5_launches += 3;
+    *total = tot;
+    return 0;
+}
+static int json_copy_out(agr_handle* h, uint64_t total, uint8_t* out, uint64_t cap, uint64_t* len) {
+    *len = total;
+    if (!out) { CK(cudaStreamSynchronize(h->stream)); return 0; }
+    if (total > cap) return fail(AGR_ECAP, "output buffer too small");
+    if (total) CK(cudaMemcpyAsync(out, h->d_json, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, uint8_t* out, uint64_t cap, uint64_t* len, uint64_t* offsets) {
+    if (!h || !len) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (first_rid + n > h->rows_used) return fail(AGR_EINVAL, "row range beyond the rows in use");
+    uint64_t total = 0;
+    TRY(json_encode_locked(h, nullptr, (uint32_t)first_rid, n, as_array != 0, &total));
+    if (n == 0 && as_array) {                                    // json.Marshal of a nil slice
+        *len = 4;
+        if (out) { if (cap < 4) return fail(AGR_ECAP, "output buffer too small"); memcpy(out, "null", 4); }
+        if (offsets) offsets[0] = 0;
+        return 0;
+    }
+    if (offsets && n) CK(cudaMemcpyAsync(offsets, h->d_joff, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    else if (offsets) offsets[0] = 0;
+    return json_copy_out(h, total, out, cap, len);
+}
+
+int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* count) {
+    if (!h || !agent_id || !len) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (count) *count = 0;
+    uint32_t total_rows = 0;
+    int slot = agent_find(h, agent_id);
+    if (slot >= 0) {
+        const uint32_t cap0 = std::max<uint32_t>(h->out_cap, 1024);
+        TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap0, &total_rows));
+        if (total_rows > cap0)                                   // counts only: run again with room for all of it
+            TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, total_rows, &total_rows));
+    }
+    if (count) *count = total_rows;
+    if (total_rows == 0) {                                       // var requests []*Request stays nil (requests.go:204): "null"
+        *len = 4;
+        if (out) { if (cap < 4) return fail(AGR_ECAP, "output buffer too small"); memcpy(out, "null", 4); }
+        return 0;
+    }
+    uint64_t total = 0;
+    TRY(json_encode_locked(h, h->d_out_rid, 0, total_rows, true, &total));
+    return json_copy_out(h, total, out, cap, len);
+}
+
+int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
+    if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint32_t rid = 0;
+    TRY(resolve_one_locked(h, agent_id, request_id, &rid));
+    uint64_t total = 0, l = 0;
+    TRY(json_encode_locked(h, nullptr, rid, 1, false, &total));
+    int rc = json_copy_out(h, total, out, cap, &l);
+    *len = (uint32_t)l;
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------ durability
 struct snap_header {
-    char magic[8];                 // "AGRSNAP1"
+    char magic[8];                 // "AGRSNAP2"
     uint32_t flags, n_agents, shard, gen;
     uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used;
 };
@@ -1087,7 +1224,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     FILE* f = fopen(path, "wb");
     if (!f) return fail(AGR_EINVAL, std::string("snapshot: cannot open ") + path);
     snap_header hd{};
-    memcpy(hd.magic, "AGRSNAP1", 8);
+    memcpy(hd.magic, "AGRSNAP2", 8);
     hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
@@ -1119,6 +1256,10 @@ int agr_snapshot(agr_handle* h, const char* path) {
     if ((rc = dump_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_resp_off, R * 8)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_resp_len, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_resp_hlen, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_err_off, R * 8)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_err_len, R * 4)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.ptime, R * 8)) < 0) return done(rc);
     return done(0);
 }
 
@@ -1128,7 +1269,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(AGR_EINVAL, std::string("restore: cannot open ") + path);
     snap_header hd{};
-    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "AGRSNAP1", 8) != 0) { fclose(f); return fail(AGR_EINVAL, "restore: not a snapshot"); }
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "AGRSNAP2", 8) != 0) { fclose(f); return fail(AGR_EINVAL, "restore: not a snapshot"); }
     agr_config c = *cfg;
     if (c.flags == 0) c.flags = AGR_CFG_PERSISTENCE;
     const uint32_t mode_bits = AGR_CFG_MINT_IDS | AGR_CFG_VARLEN;
@@ -1167,6 +1308,10 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if ((rc = load_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_resp_off, R * 8)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_resp_len, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_resp_hlen, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_err_off, R * 8)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_err_len, R * 4)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d.ptime, R * 8)) < 0) return bail(rc);
     h->resp_used = hd.resp_used;
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
@@ -1218,7 +1363,7 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->replay_scans = h->replay_scans; out->replay_dispatched = h->replay_dispatched;
     out->completed_log_len = lens[0]; out->failed_log_len = lens[1];
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
-    out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches;
+    out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches; out->k5_launches = h->k5_launches;
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
     return 0;
 }
@@ -1427,7 +1572,7 @@ int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, voi
 }
 
 int agr_op_time(agr_handle* h, int which, double* ms) {
-    if (!h || !ms || which < 0 || which > 1) return fail(AGR_EINVAL, "bad argument");
+    if (!h || !ms || which < 0 || which > 2) return fail(AGR_EINVAL, "bad argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     if (!h->op_timed[which]) return fail(AGR_ENOTFOUND, "no timed launch of that group yet (needs AGR_CFG_TIMING)");

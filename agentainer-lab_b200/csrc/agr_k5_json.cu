@@ -1,0 +1,481 @@
+// agr_k5_json.cu — K5: the wire form of a stored record.
+//
+// The reference keeps every record in Redis as json.Marshal(requests.Request) (requests.go:101,169,264) and its
+// management surface hands that JSON on: GET /agents/{id}/requests marshals []*Request (server.go:626-652),
+// GET /agents/{id}/requests/{reqId} re-marshals one record (server.go:655-679), the CLI parses both
+// (cmd/agentainer/main.go:1143-1174).  K5 produces those bytes from the binary rows: field order = struct order
+// (requests.go:27-41,44-49), encoding/json's string escaping with HTML escaping on, map keys in sorted order,
+// []byte as padded std base64, time.Time as RFC 3339 with nanoseconds (UTC), omitempty on processed_at / response /
+// error.  Two passes of the same code: MEASURE gives every record's exact length, a scan turns lengths into
+// offsets, EMIT writes.  One warp per record; output is staged in shared memory and leaves as aligned 16 B stores.
+//
+// Pure byte work: per record ~0.5 KB read, ~1 KB written; bounded by HBM bandwidth and, before that, by issue rate.
+#include "agr_device.cuh"
+
+#define K5_WARPS 8
+#define K5_CHUNK 256u          // records per CTA (32 per warp)
+#define K5_SB 1280u            // staging bytes per warp
+#define K5_FLUSH 1024u
+
+#define JLIT(W, S) (W).lit(S, (uint32_t)(sizeof(S) - 1))
+
+namespace {
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+__device__ __forceinline__ char hexc(uint32_t v) { return (char)(v < 10 ? '0' + v : 'a' + (v - 10)); }
+
+template <bool EMIT>
+struct jwriter {
+    uint8_t* sb;                 // this warp's staging buffer (16 B aligned)
+    uint8_t* gout;
+    unsigned long long gbase;    // global offset of sb[0]; 16-aligned
+    uint32_t fill;               // bytes staged (including `head` foreign bytes of the first word)
+    uint32_t head;
+    unsigned long long total;    // MEASURE
+    int lane;
+
+    __device__ __forceinline__ void begin(uint8_t* out, unsigned long long off) {
+        gout = out; gbase = off & ~15ull; head = (uint32_t)(off & 15ull); fill = head; total = 0;
+    }
+    __device__ __forceinline__ void flush(bool final) {
+        __syncwarp();
+        const uint32_t nwords = fill >> 4;
+        uint32_t w0 = 0;
+        if (head) {
+            const uint32_t e = min(16u, fill);
+            if ((uint32_t)lane >= head && (uint32_t)lane < e) gout[gbase + lane] = sb[lane];
+            w0 = 1;
+        }
+        for (uint32_t w = w0 + lane; w < nwords; w += 32)
+            *reinterpret_cast<uint4*>(gout + gbase + 16ull * w) = *reinterpret_cast<const uint4*>(sb + 16u * w);
+        const uint32_t rem = fill & 15u;
+        if (final) {
+            if (nwords >= w0 && (uint32_t)lane < rem) gout[gbase + 16ull * nwords + lane] = sb[16u * nwords + lane];
+        } else {
+            uint8_t v = 0;
+            if ((uint32_t)lane < rem) v = sb[16u * nwords + lane];
+            __syncwarp();
+            if ((uint32_t)lane < rem) sb[lane] = v;
+            gbase += 16ull * nwords; fill = rem; head = 0;
+            __syncwarp();
+        }
+    }
+    // the caller has written k bytes at sb[fill ..)
+    __device__ __forceinline__ void commit(uint32_t k) {
+        if (EMIT) { fill += k; if (fill >= K5_FLUSH) flush(false); }
+        else total += k;
+    }
+    __device__ __forceinline__ void lit(const char* s, uint32_t k) {       // k <= 32
+        if (EMIT && (uint32_t)lane < k) sb[fill + lane] = (uint8_t)s[lane];
+        commit(k);
+    }
+    __device__ __forceinline__ void ch(char c) {
+        if (EMIT && lane == 0) sb[fill] = (uint8_t)c;
+        commit(1);
+    }
+    __device__ __forceinline__ void uint(uint32_t v) {
+        uint32_t nd = 1;
+        for (uint32_t t = v; t >= 10; t /= 10) ++nd;
+        if (EMIT && (uint32_t)lane < nd) {
+            uint32_t t = v;
+            for (uint32_t k = nd - 1 - lane; k; --k) t /= 10;
+            sb[fill + lane] = (uint8_t)('0' + t % 10);
+        }
+        commit(nd);
+    }
+    // uuid.UUID.String(): 8-4-4-4-12 lower-case hex
+    __device__ __forceinline__ void uuid(unsigned long long lo, unsigned long long hi) {
+        if (EMIT && lane < 32) {
+            const int i = lane;                                      // nibble index
+            const int b = i >> 1;
+            const uint32_t byte = (uint32_t)((b < 8 ? lo >> (8 * b) : hi >> (8 * (b - 8))) & 0xffu);
+            const uint32_t nib = (i & 1) ? (byte & 15u) : (byte >> 4);
+            const int pos = i + (i >= 8) + (i >= 12) + (i >= 16) + (i >= 20);
+            sb[fill + pos] = (uint8_t)hexc(nib);
+            if (i < 4) sb[fill + 8 + 5 * i] = '-';
+        }
+        commit(36);
+    }
+    // time.Time.MarshalJSON of time.Unix(0, ns).UTC(): RFC3339Nano (trailing zeros of the fraction dropped)
+    __device__ __forceinline__ void time(unsigned long long ns) {
+        const unsigned long long secs = ns / 1000000000ull;
+        uint32_t frac = (uint32_t)(ns % 1000000000ull);
+        const uint32_t sod = (uint32_t)(secs % 86400ull);
+        const long long z = (long long)(secs / 86400ull) + 719468;    // days since 0000-03-01 (civil-from-days)
+        const long long era = z / 146097;
+        const uint32_t doe = (uint32_t)(z - era * 146097);
+        const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+        uint32_t y = yoe + (uint32_t)era * 400;
+        const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+        const uint32_t mp = (5 * doy + 2) / 153;
+        const uint32_t dd = doy - (153 * mp + 2) / 5 + 1;
+        const uint32_t mm = mp < 10 ? mp + 3 : mp - 9;
+        if (mm <= 2) ++y;
+        uint32_t nd = 0;
+        if (frac) { nd = 9; while (frac % 10 == 0) { frac /= 10; --nd; } }
+        const uint32_t len = 19 + (nd ? 1 + nd : 0) + 1;
+        if (EMIT && (uint32_t)lane < len) {
+            const uint32_t hh = sod / 3600, mi = sod / 60 % 60, ss = sod % 60;
+            char c;
+            const int i = lane;
+            switch (i) {
+                case 0: c = '0' + y / 1000 % 10; break;  case 1: c = '0' + y / 100 % 10; break;
+                case 2: c = '0' + y / 10 % 10; break;    case 3: c = '0' + y % 10; break;
+                case 4: c = '-'; break;                  case 5: c = '0' + mm / 10; break;
+                case 6: c = '0' + mm % 10; break;        case 7: c = '-'; break;
+                case 8: c = '0' + dd / 10; break;        case 9: c = '0' + dd % 10; break;
+                case 10: c = 'T'; break;                 case 11: c = '0' + hh / 10; break;
+                case 12: c = '0' + hh % 10; break;       case 13: c = ':'; break;
+                case 14: c = '0' + mi / 10; break;       case 15: c = '0' + mi % 10; break;
+                case 16: c = ':'; break;                 case 17: c = '0' + ss / 10; break;
+                case 18: c = '0' + ss % 10; break;
+                default:
+                    if ((uint32_t)i == len - 1) c = 'Z';
+                    else if (i == 19) c = '.';
+                    else { uint32_t t = frac; for (uint32_t k = nd - 1 - (uint32_t)(i - 20); k; --k) t /= 10; c = '0' + t % 10; }
+            }
+            sb[fill + lane] = (uint8_t)c;
+        }
+        commit(len);
+    }
+};
+
+__device__ __forceinline__ uint32_t byte_at(const uint8_t* s, uint32_t len, long long p) {
+    return (p >= 0 && p < (long long)len) ? s[p] : 0u;      // outside the string: a non-continuation byte
+}
+// utf8.DecodeRuneInString at a NON-continuation byte j: length of the valid sequence starting there, 0 if invalid
+// (unicode/utf8 `first` / acceptRanges tables)
+__device__ __forceinline__ uint32_t utf8_seq(const uint8_t* s, uint32_t len, long long j) {
+    const uint32_t b0 = byte_at(s, len, j);
+    if (b0 < 0x80u) return 1;
+    uint32_t need, lo = 0x80u, hi = 0xbfu;
+    if (b0 >= 0xc2u && b0 <= 0xdfu) need = 2;
+    else if (b0 >= 0xe0u && b0 <= 0xefu) { need = 3; if (b0 == 0xe0u) lo = 0xa0u; else if (b0 == 0xedu) hi = 0x9fu; }
+    else if (b0 >= 0xf0u && b0 <= 0xf4u) { need = 4; if (b0 == 0xf0u) lo = 0x90u; else if (b0 == 0xf4u) hi = 0x8fu; }
+    else return 0;
+    if (j + need > (long long)len) return 0;
+    const uint32_t b1 = byte_at(s, len, j + 1);
+    if (b1 < lo || b1 > hi) return 0;
+    for (uint32_t k = 2; k < need; ++k) { const uint32_t b = byte_at(s, len, j + k); if (b < 0x80u || b > 0xbfu) return 0; }
+    return need;
+}
+
+// encoding/json encodeState.string (escapeHTML = true) for the byte at position p of the string s[0..len).
+// Returns how many output bytes this position contributes (0..6) and packs them little-endian into `chars`.
+// `touched`: the record has been through json.Unmarshal + Marshal (StoreResponse / MarkRequestFailed), which turns an
+// invalid byte into a REAL U+FFFD that the second Marshal copies through as EF BF BD instead of writing "�".
+__device__ __forceinline__ uint32_t esc_byte(const uint8_t* s, uint32_t len, uint32_t p, uint32_t b, bool touched,
+                                             unsigned long long& chars) {
+    if (b < 0x80u) {
+        if (b >= 0x20u && b != '"' && b != '\\' && b != '<' && b != '>' && b != '&') { chars = b; return 1; }
+        char e = 0;
+        switch (b) {
+            case '"': e = '"'; break;   case '\\': e = '\\'; break;
+            case '\n': e = 'n'; break;  case '\r': e = 'r'; break;  case '\t': e = 't'; break;
+            case '\b': e = 'b'; break;  case '\f': e = 'f'; break;          // Go >= 1.22 (go.mod: go 1.23)
+        }
+        if (e) { chars = (unsigned long long)'\\' | ((unsigned long long)(uint8_t)e << 8); return 2; }
+        chars = (unsigned long long)'\\' | ((unsigned long long)'u' << 8) | ((unsigned long long)'0' << 16) |
+                ((unsigned long long)'0' << 24) | ((unsigned long long)(uint8_t)hexc(b >> 4) << 32) |
+                ((unsigned long long)(uint8_t)hexc(b & 15u) << 40);
+        return 6;
+    }
+    // multi-byte territory: find the sequence this byte belongs to
+    long long j = p;
+    if (b <= 0xbfu) {                                        // continuation byte: nearest non-continuation byte before it
+        j = -1;
+        for (int k = 1; k <= 3; ++k) {
+            const long long q = (long long)p - k;
+            if (q < 0) break;
+            const uint32_t c = s[q];
+            if (c < 0x80u || c > 0xbfu) { j = q; break; }
+        }
+    }
+    uint32_t sl = 0;
+    if (j >= 0) { sl = utf8_seq(s, len, j); if ((long long)p - j >= (long long)sl) sl = 0; }
+    if (sl == 0) {                                           // RuneError, width 1
+        if (touched) { chars = 0xefull | (0xbfull << 8) | (0xbdull << 16); return 3; }
+        chars = (unsigned long long)'\\' | ((unsigned long long)'u' << 8) | ((unsigned long long)'f' << 16) |
+                ((unsigned long long)'f' << 24) | ((unsigned long long)'f' << 32) | ((unsigned long long)'d' << 40);
+        return 6;
+    }
+    // U+2028 / U+2029 are escaped (JSONP safety): E2 80 A8 / E2 80 A9
+    if (sl == 3 && s[j] == 0xe2u && s[j + 1] == 0x80u && (s[j + 2] == 0xa8u || s[j + 2] == 0xa9u)) {
+        if ((long long)p != j) return 0;
+        chars = (unsigned long long)'\\' | ((unsigned long long)'u' << 8) | ((unsigned long long)'2' << 16) |
+                ((unsigned long long)'0' << 24) | ((unsigned long long)'2' << 32) |
+                ((unsigned long long)(s[j + 2] == 0xa8u ? '8' : '9') << 40);
+        return 6;
+    }
+    chars = b;
+    return 1;
+}
+
+template <bool EMIT>
+__device__ __forceinline__ void put_packed(jwriter<EMIT>& w, uint32_t el, unsigned long long chars) {
+    uint32_t tot;
+    const uint32_t off = warp_excl_scan(el, w.lane, tot);
+    if (EMIT) for (uint32_t k = 0; k < el; ++k) w.sb[w.fill + off + k] = (uint8_t)(chars >> (8 * k));
+    w.commit(tot);
+}
+
+// a JSON string body (no quotes) from s[0..len)
+template <bool EMIT>
+__device__ __forceinline__ void put_escaped(jwriter<EMIT>& w, const uint8_t* s, uint32_t len, bool touched) {
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t p = base + w.lane;
+        unsigned long long chars = 0; uint32_t el = 0;
+        if (p < len) el = esc_byte(s, len, p, s[p], touched, chars);
+        put_packed(w, el, chars);
+    }
+}
+
+// map[string]string from its flattened form "Key: Value\n"... (keys already in sorted order, Q5): {"k":"v","k2":"v2"}
+template <bool EMIT>
+__device__ __forceinline__ void put_headers(jwriter<EMIT>& w, const uint8_t* s, uint32_t len, bool touched) {
+    if (len == 0) { JLIT(w, "{}"); return; }
+    JLIT(w, "{\"");
+    bool in_val = false, prev_sep = false;                   // carried across 32-byte steps (warp-uniform)
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t p = base + w.lane;
+        const uint32_t b = p < len ? s[p] : 0u;
+        const uint32_t nl = __ballot_sync(FULL, p < len && b == '\n');
+        const uint32_t co = __ballot_sync(FULL, p < len && b == ':');
+        const uint32_t below = (1u << w.lane) - 1u;
+        const uint32_t prev_nl = nl & below;
+        const uint32_t start = prev_nl ? 32u - __clz(prev_nl) : 0u;
+        const uint32_t same_line = below & ~((start >= 32u) ? 0xffffffffu : ((1u << start) - 1u));
+        const bool inval = (co & same_line) != 0u || (prev_nl == 0u && in_val);
+        const bool is_sep = p < len && b == ':' && !inval;
+        const uint32_t sepm = __ballot_sync(FULL, is_sep);
+        const bool after_sep = w.lane ? ((sepm >> (w.lane - 1)) & 1u) : prev_sep;
+        unsigned long long chars = 0; uint32_t el = 0;
+        if (p < len) {
+            if (is_sep) { chars = (unsigned long long)'"' | ((unsigned long long)':' << 8) | ((unsigned long long)'"' << 16); el = 3; }
+            else if (b == ' ' && after_sep) el = 0;
+            else if (b == '\n') {
+                if (p == len - 1) { chars = '"'; el = 1; }
+                else { chars = (unsigned long long)'"' | ((unsigned long long)',' << 8) | ((unsigned long long)'"' << 16); el = 3; }
+            } else el = esc_byte(s, len, p, b, touched, chars);
+        }
+        put_packed(w, el, chars);
+        // carry: state after the last byte of this step
+        const uint32_t last_nl = nl ? 32u - __clz(nl) : 0u;            // index after the last newline in the step
+        const uint32_t tail = (last_nl >= 32u) ? 0u : ~((1u << last_nl) - 1u);
+        in_val = (co & tail) != 0u || (nl == 0u && in_val);
+        prev_sep = (sepm >> 31) & 1u;
+    }
+    w.ch('}');
+}
+
+// []byte -> base64.StdEncoding (padded), no quotes
+template <bool EMIT>
+__device__ __forceinline__ void put_base64(jwriter<EMIT>& w, const uint8_t* s, uint32_t len) {
+    const uint32_t groups = (len + 2u) / 3u;
+    if (!EMIT) w.commit(4u * groups);
+    else for (uint32_t g0 = 0; g0 < groups; g0 += 32) {
+        const uint32_t g = g0 + w.lane;
+        if (g < groups) {
+            const uint32_t p = 3u * g;
+            const uint32_t b0 = s[p], b1 = p + 1 < len ? s[p + 1] : 0u, b2 = p + 2 < len ? s[p + 2] : 0u;
+            const uint32_t v = (b0 << 16) | (b1 << 8) | b2;
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = (v >> (18 - 6 * k)) & 63u;
+                const uint32_t c = x < 26 ? 'A' + x : x < 52 ? 'a' + (x - 26) : x < 62 ? '0' + (x - 52) : x == 62 ? '+' : '/';
+                out |= c << (8 * k);
+            }
+            if (p + 1 >= len) out = (out & 0x0000ffffu) | ((uint32_t)'=' << 16) | ((uint32_t)'=' << 24);
+            else if (p + 2 >= len) out = (out & 0x00ffffffu) | ((uint32_t)'=' << 24);
+            uint8_t* dst = w.sb + w.fill + 4u * w.lane;
+            dst[0] = (uint8_t)out; dst[1] = (uint8_t)(out >> 8); dst[2] = (uint8_t)(out >> 16); dst[3] = (uint8_t)(out >> 24);
+        }
+        w.commit(4u * min(32u, groups - g0));
+    }
+}
+
+__device__ __forceinline__ uint32_t cstr_len(const uint8_t* s, uint32_t cap) {
+    uint32_t n = 0;
+    while (n < cap && s[n]) ++n;
+    return n;
+}
+
+// json.Marshal(requests.Request) for the record in row `rid`
+template <bool EMIT>
+__device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d, const agr_k5_params& p, uint32_t rid,
+                                              const uint8_t* rec /* header + payload, generic pointer */) {
+    const uint32_t st = d.state[rid];
+    if (!(st & ST_STORED)) { JLIT(w, "null"); return; }
+    const uint32_t aux = d.aux[rid];
+    const bool responded = (st & ST_RESPONDED) != 0u;
+    const uint32_t retry = st_retry(st);
+    const bool touched = responded || retry != 0u;
+    unsigned long long lo, hi;
+    if (d.cfg_flags & AGR_CFG_MINT_IDS) agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+    else { lo = *reinterpret_cast<const unsigned long long*>(rec); hi = *reinterpret_cast<const unsigned long long*>(rec + 8); }
+    const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(rec + AGR_OFF_SEQ);
+    const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec + AGR_OFF_FLAGS);
+    const uint32_t path_len = *reinterpret_cast<const uint16_t*>(rec + AGR_OFF_PATH_LEN);
+    const uint32_t hdr_len = *reinterpret_cast<const uint16_t*>(rec + AGR_OFF_HDR_LEN);
+    const uint32_t body_len = *reinterpret_cast<const uint32_t*>(rec + AGR_OFF_BODY_LEN);
+    const uint8_t* pay = rec + AGR_OFF_PAYLOAD;
+
+    JLIT(w, "{\"id\":\"");
+    w.uuid(lo, hi);
+    JLIT(w, "\",\"agent_id\":\"");
+    put_escaped(w, rec + AGR_OFF_AGENT_ID, cstr_len(rec + AGR_OFF_AGENT_ID, AGR_AGENT_ID_BYTES), touched);
+    JLIT(w, "\",\"method\":\"");
+    switch ((flags & AGR_F_METHOD_MASK) >> AGR_F_METHOD_SHIFT) {
+        case AGR_M_GET: JLIT(w, "GET"); break;        case AGR_M_POST: JLIT(w, "POST"); break;
+        case AGR_M_PUT: JLIT(w, "PUT"); break;        case AGR_M_DELETE: JLIT(w, "DELETE"); break;
+        case AGR_M_PATCH: JLIT(w, "PATCH"); break;    case AGR_M_HEAD: JLIT(w, "HEAD"); break;
+        case AGR_M_OPTIONS: JLIT(w, "OPTIONS"); break;
+    }
+    JLIT(w, "\",\"path\":\"");
+    put_escaped(w, pay, path_len, touched);
+    JLIT(w, "\",\"headers\":");
+    put_headers(w, pay + path_len, hdr_len, touched);
+    JLIT(w, ",\"body\":\"");
+    put_base64(w, pay + path_len + hdr_len, body_len);
+    JLIT(w, "\",\"status\":\"");
+    switch (st_status(st)) {
+        case AGR_ST_PENDING: JLIT(w, "pending"); break;      case AGR_ST_PROCESSING: JLIT(w, "processing"); break;
+        case AGR_ST_COMPLETED: JLIT(w, "completed"); break;  case AGR_ST_FAILED: JLIT(w, "failed"); break;
+    }
+    JLIT(w, "\",\"retry_count\":");
+    w.uint(retry);
+    JLIT(w, ",\"max_retries\":");
+    w.uint(st_max(st));
+    JLIT(w, ",\"created_at\":\"");
+    w.time(seq);
+    w.ch('"');
+    if (responded) {                                         // requests.go:165-167
+        const unsigned long long t = p.ptime[rid];
+        JLIT(w, ",\"processed_at\":\"");
+        w.time(t);
+        JLIT(w, "\",\"response\":{\"status_code\":");
+        w.uint(aux & 0xffffu);
+        JLIT(w, ",\"headers\":");
+        const uint32_t rl = p.resp_len[rid], rh = min(p.resp_hlen[rid], rl);
+        const uint8_t* rb = p.bytes + p.resp_off[rid];
+        put_headers(w, rb, rh, (st & ST_RESP_RT) != 0u);
+        JLIT(w, ",\"body\":\"");
+        put_base64(w, rb + rh, rl - rh);
+        JLIT(w, "\",\"received_at\":\"");
+        w.time(t);
+        JLIT(w, "\"}");
+    }
+    if (retry != 0u) {                                       // requests.go:244 request.Error = err.Error()
+        JLIT(w, ",\"error\":\"");
+        const uint32_t el = p.err_len[rid];
+        if (el) put_escaped(w, p.bytes + p.err_off[rid], el, (st & ST_ERR_RT) != 0u);
+        else JLIT(w, "transport error");
+        w.ch('"');
+    }
+    w.ch('}');
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(K5_WARPS * 32) k5_json(const agr_dev d, const agr_k5_params p) {
+    __shared__ __align__(16) uint8_t s_stage[EMIT ? K5_WARPS * K5_SB : 16];
+    __shared__ __align__(16) uint4 s_rec[K5_WARPS][32];
+    __shared__ unsigned long long s_off[K5_CHUNK];
+    __shared__ unsigned long long s_wsum[K5_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk0 = blockIdx.x * K5_CHUNK;
+    const uint32_t in_chunk = min(K5_CHUNK, p.n - chunk0);
+    if (EMIT) {
+        // exclusive scan of this chunk's record lengths on top of the chunk's base
+        const uint32_t t = threadIdx.x;
+        const uint32_t v = t < in_chunk ? p.len[chunk0 + t] : 0u;
+        uint32_t tot;
+        const uint32_t ex = warp_excl_scan(v, lane, tot);
+        if (lane == 0) s_wsum[warp] = tot;
+        __syncthreads();
+        unsigned long long base = p.chunk_sum[blockIdx.x];
+        for (int k = 0; k < warp; ++k) base += s_wsum[k];
+        s_off[t] = base + ex;
+        if (t < in_chunk) p.off[chunk0 + t] = base + ex;
+        if (chunk0 + t + 1 == p.n) p.off[p.n] = base + ex + v;
+        __syncthreads();
+    }
+    jwriter<EMIT> w;
+    w.lane = lane;
+    w.sb = EMIT ? s_stage + warp * K5_SB : nullptr;
+    unsigned long long wsum = 0;
+    for (uint32_t k = 0; k < 32; ++k) {
+        const uint32_t r = k * K5_WARPS + warp;              // neighbouring warps write neighbouring output
+        if (r >= in_chunk) break;
+        const uint32_t i = chunk0 + r;
+        const uint32_t rid = p.rids ? p.rids[i] : p.first_rid + i;
+        const uint8_t* src = rec_ptr(d, rid);
+        const uint8_t* rec = src;
+        if (!d.voff) {                                       // fixed 512 B rows: stage the record in shared memory
+            __syncwarp();
+            s_rec[warp][lane] = ldg_nc_v4(src + lane * 16);
+            __syncwarp();
+            rec = reinterpret_cast<const uint8_t*>(&s_rec[warp][0]);
+        }
+        if (EMIT) w.begin(p.out, s_off[r]); else w.total = 0;
+        if (p.array) w.ch(i == 0 ? '[' : ',');
+        encode_record<EMIT>(w, d, p, rid, rec);
+        if (p.array && i + 1 == p.n) w.ch(']');
+        if (EMIT) w.flush(true);
+        else { if (lane == 0) p.len[i] = (uint32_t)w.total; wsum += w.total; }
+    }
+    if (!EMIT) {
+        if (lane == 0) s_wsum[warp] = wsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long s = 0;
+            for (int k = 0; k < K5_WARPS; ++k) s += s_wsum[k];
+            p.chunk_sum[blockIdx.x] = s;
+        }
+    }
+}
+
+// exclusive scan of the chunk sums in place; chunk_sum[nchunks] = grand total
+__global__ void __launch_bounds__(1024) k5_scan(unsigned long long* chunk_sum, const uint32_t nchunks) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nchunks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < nchunks ? chunk_sum[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        unsigned long long pre = s_carry;
+        for (int k = 0; k < warp; ++k) pre += s_w[k];
+        if (i < nchunks) chunk_sum[i] = pre + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_sum[nchunks] = s_carry;
+}
+
+}  // namespace
+
+uint32_t agr_k5_chunks(uint32_t n) { return (n + K5_CHUNK - 1) / K5_CHUNK; }
+void agr_launch_k5_measure(const agr_dev& d, const agr_k5_params& p, cudaStream_t st) {
+    if (!p.n) return;
+    const uint32_t nch = agr_k5_chunks(p.n);
+    k5_json<false><<<nch, K5_WARPS * 32, 0, st>>>(d, p);
+    k5_scan<<<1, 1024, 0, st>>>(p.chunk_sum, nch);
+}
+void agr_launch_k5_emit(const agr_dev& d, const agr_k5_params& p, cudaStream_t st) {
+    if (!p.n) return;
+    k5_json<true><<<agr_k5_chunks(p.n), K5_WARPS * 32, 0, st>>>(d, p);
+}

@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
     }
     if (root) {
         uint32_t st = d.state[rid], aux = d.aux[rid];
+        unsigned long long ptime = 0; bool responded = false;
         long long last = -1;
         for (;;) {
             // next op of this row in ascending op index
@@ -364,14 +365,18 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
             const agr_dop op = s.ops[best];
             uint8_t eff = 0;
             if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
-                st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED;  // :166
+                st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED | ST_RESPONDED;  // :166
+                ptime = op.seq; responded = true;                                // :164,167 now / ProcessedAt
+                st &= ~ST_RESP_RT;                                               // a fresh Response object
+                if (st_retry(st)) st |= ST_ERR_RT;                               // Error went through Unmarshal + Marshal
                 aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
                 st &= ~ST_INQ;                                                   // :180-184 LREM pending 1 id
                 eff |= 1; ncomp++;                                               // :187-191 RPUSH completed
             } else if (op.kind == AGR_OUT_ERROR) {                               // MarkRequestFailed, requests.go:243-262
                 uint32_t retry = st_retry(st);
                 if (retry < 255u) retry++;                                       // :245
-                st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT)) | (retry << ST_RETRY_SHIFT);
+                st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT | ST_ERR_RT)) | (retry << ST_RETRY_SHIFT);
+                if (st & ST_RESPONDED) st |= ST_RESP_RT;
                 aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
                 nerr++;
                 if (retry < st_max(st)) {
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
         }
         d.state[rid] = st;
         d.aux[rid] = aux;
+        if (responded) d.ptime[rid] = ptime;
         d.head[rid] = 0;
     }
     ncomp = __reduce_add_sync(FULL, ncomp);

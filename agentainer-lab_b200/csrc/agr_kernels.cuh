@@ -30,6 +30,7 @@ struct agr_dev {
     unsigned long long log_cap;
     uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
+    unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
     unsigned long long* voff;  // variable-length mode: byte offset of row's record in the slab (nullptr = fixed 512 B rows)
     uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
@@ -88,6 +89,24 @@ void agr_launch_var_lens(const agr_dev& d, const uint32_t* rids, uint32_t n, uin
 void agr_launch_var_copy(const agr_dev& d, const uint32_t* rids, uint32_t n, const unsigned long long* out_off, uint8_t* out, cudaStream_t st);
 #define AGR_VT_TILE 8192u   // lower bound of the tile size used by agr_k1_var.cu (sizes the tile index)
 #define AGR_VT_MAXREC 8192u
+
+// K5: JSON wire form of stored records (agr_k5_json.cu)
+struct agr_k5_params {
+    const uint32_t* rids;            // nullable: record i lives in row first_rid + i
+    uint32_t first_rid, n;
+    uint32_t array;                  // 1: emit json.Marshal([]*Request) = [rec,rec,...]; 0: records back to back
+    uint32_t* len;                   // [n] encoded length of record i (with its '[' / ',' / ']' in array mode)
+    unsigned long long* off;         // [n + 1] byte offsets of the records in out
+    unsigned long long* chunk_sum;   // [chunks + 1]; chunk_sum[chunks] = total bytes after agr_launch_k5_measure
+    uint8_t* out;
+    const uint8_t* bytes;            // byte slab of stored responses and error texts
+    const unsigned long long* resp_off; const uint32_t* resp_len; const uint32_t* resp_hlen;
+    const unsigned long long* err_off; const uint32_t* err_len;
+    const unsigned long long* ptime;
+};
+uint32_t agr_k5_chunks(uint32_t n);
+void agr_launch_k5_measure(const agr_dev& d, const agr_k5_params& p, cudaStream_t st);
+void agr_launch_k5_emit(const agr_dev& d, const agr_k5_params& p, cudaStream_t st);
 
 // K4: shard binning / stable pack for the multi-GPU exchange
 struct agr_k4_params {

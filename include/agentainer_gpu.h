@@ -245,7 +245,35 @@ int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t reques
  * path, and come back for GET /agents/{id}/requests/{reqId} (server.go:655-679).  The latest store wins, like the
  * reference's SET.  AGR_ENOTFOUND if the record does not exist. */
 int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* bytes, uint32_t len);
+/* The same with the two parts of requests.Response told apart (requests.go:44-49): headers = the first-value header map
+ * flattened as "Key: Value\n" lines sorted by key (the form agr_record.payload uses), body = the raw body.  This is
+ * what the JSON wire form below reads; agr_store_response_body(bytes) == agr_store_response(no headers, bytes). */
+int agr_store_response(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* headers, uint32_t hdr_len,
+                       const uint8_t* body, uint32_t body_len);
+/* Request.Error = err.Error() (requests.go:244): the text MarkRequestFailed stored last.  agr_complete carries only the
+ * fact of the failure; the Go shim hands the text over here (off the hot path).  Without it the wire form says
+ * "transport error". */
+int agr_store_error_text(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const char* text, uint32_t len);
 int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
+
+/* ------------------------------------------------- JSON wire form (K5) */
+/* The reference stores and serves records as json.Marshal(requests.Request) (requests.go:27-49,101,169,264): the value
+ * of the Redis key agent:{a}:requests:{r} read by GET /agents/{id}/requests/{reqId} and the replay handler
+ * (server.go:661-668,687-694), and the "pending" array of GET /agents/{id}/requests (server.go:626-652).  K5 produces
+ * exactly those bytes on the device from the binary rows: struct field order, encoding/json string escaping (HTML-safe,
+ * invalid UTF-8 -> U+FFFD, U+2028/9 escaped), header maps in key order, []byte as padded std base64, times as RFC 3339
+ * with nanoseconds in UTC (agr_record.seq / agr_outcome.seq are read as Unix nanoseconds), omitempty on processed_at /
+ * response / error.
+ *   agr_get_record_json : the stored value of one record;            AGR_ENOTFOUND like storage.Get's miss
+ *   agr_pending_json    : json.Marshal(GetPendingRequests(agent)) — "[{...},{...}]", or "null" for an empty list (the Go
+ *                         slice is nil then, requests.go:204); *count = entries
+ *   agr_rows_json       : rows [first_rid, first_rid + n) as an array (as_array != 0) or back to back with
+ *                         offsets[0..n] (nullable); rows that hold no stored record encode as null.  out == NULL
+ *                         leaves the bytes on the device and only reports *len (sizing call / resident bench).
+ * AGR_ECAP if cap is too small (*len holds the size needed). */
+int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
+int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* count);
+int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, uint8_t* out, uint64_t cap, uint64_t* len, uint64_t* offsets);
 
 /* ------------------------------------------------- durability */
 /* What Redis persistence gave the reference (records and queues survive a server restart, docker-compose.yml:11-12):
@@ -266,6 +294,7 @@ typedef struct agr_stats {
     uint64_t replay_scans, replay_dispatched;
     uint64_t completed_log_len, failed_log_len;
     uint64_t k1_launches, k2_launches, k3_launches, k4_launches;   /* kernels of this library launched so far */
+    uint64_t k5_launches;
     uint32_t agents, device;
 } agr_stats;
 int agr_stats_get(agr_handle* h, agr_stats* out);
@@ -293,7 +322,8 @@ void* agr_stream(agr_handle* h);                 /* cudaStream_t the kernels run
  * call (at most the latest 1024), from CUDA events recorded on the launching stream.  Synchronises. */
 int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches);
 /* With AGR_CFG_TIMING: device time (CUDA events on the launching stream) of the most recent kernel group:
- * which = 0 the K2 kernels of the last agr_complete, 1 the K3 select kernels of the last scan / pending / list. */
+ * which = 0 the K2 kernels of the last agr_complete, 1 the K3 select kernels of the last scan / pending / list,
+ * 2 the K5 kernels of the last JSON encode (measure + scan + emit, including the host's read of the total between them). */
 int agr_op_time(agr_handle* h, int which, double* ms);
 void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row */
 

@@ -28,6 +28,8 @@ import fnmatch
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
+from . import gojson
+
 # RequestStatus, internal/requests/requests.go:19-24
 STATUS_PENDING = "pending"
 STATUS_PROCESSING = "processing"   # declared, never assigned anywhere (Q1)
@@ -160,6 +162,7 @@ class Manager:
             request = copy.deepcopy(self.redis.get(key))                         # :153
         except RedisNil as e:
             raise KeyError(f"failed to get request: {e}")                        # :154-156
+        gojson.unmarshal_strings(request)                                        # :158-161 json.Unmarshal
         request["response"] = response                                           # :165
         request["status"] = STATUS_COMPLETED                                     # :166
         request["processed_at"] = resp.now                                       # :167
@@ -186,6 +189,7 @@ class Manager:
             request = copy.deepcopy(self.redis.get(key))                         # :232
         except RedisNil as e:
             raise KeyError(f"failed to get request: {e}")                        # :233-235
+        gojson.unmarshal_strings(request)                                        # :237-240 json.Unmarshal
         request["status"] = STATUS_FAILED                                        # :243
         request["error"] = err                                                   # :244
         request["retry_count"] += 1                                              # :245

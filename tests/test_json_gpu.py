@@ -1,0 +1,141 @@
+"""the JSON wire form of stored records (K5) against the Go-JSON restatement, byte for byte.
+
+The model side is oracle/model.py's Manager doing what StoreRequest / StoreResponse / MarkRequestFailed do (with the
+json.Unmarshal + Marshal round trips those functions perform); the engine side is agr_ingest + agr_complete +
+agr_store_response / agr_store_error_text, read back through agr_get_record_json / agr_pending_json / agr_rows_json."""
+import json
+
+import numpy as np
+import pytest
+
+import agentainer_lab_b200 as A
+from agentainer_lab_b200 import constants as K
+from oracle import gojson as G
+from jsoncase import make_requests, make_script, run_model, records_array, var_batch
+
+pytestmark = pytest.mark.gpu
+MODES = {"hash": K.AGR_CFG_PERSISTENCE, "mint": K.AGR_CFG_PERSISTENCE | K.AGR_CFG_MINT_IDS,
+         "var": K.AGR_CFG_PERSISTENCE | K.AGR_CFG_VARLEN | K.AGR_CFG_MINT_IDS}
+AGENTS = ["agent-1700000000000000001", "agent-1700000000000000002", "agent-1700000000000000003"]
+
+
+def drive_engine(eng, reqs, script, batch=64):
+    """Ingest, then apply the outcome script; fills r.rid with the ids the engine knows the records by."""
+    for k, a in enumerate(AGENTS):
+        eng.set_agent_state(a, K.AGR_AGENT_RUNNING if k != 1 else K.AGR_AGENT_STOPPED)
+    first = None
+    for lo in range(0, len(reqs), batch):
+        chunk = reqs[lo:lo + batch]
+        if eng.varlen:
+            blob, offs = var_batch(chunk)
+            _, ids, rid0 = eng.ingest_var(blob, offs)
+        else:
+            recs = records_array(chunk)
+            out = np.zeros(len(chunk), dtype=A.verdict_dtype)
+            ids = np.zeros((len(chunk), 16), dtype=np.uint8)
+            rid0 = eng.ingest_ex(recs, out, ids)
+        first = rid0 if first is None else first
+        for r, i in zip(chunk, ids):
+            r.rid = bytes(i)
+    pending_ops = []
+
+    def flush():
+        if pending_ops:
+            outs = np.zeros(len(pending_ops), dtype=A.outcome_dtype)
+            for j, (rid, agent, kind, http, seq) in enumerate(pending_ops):
+                outs[j]["request_id"] = np.frombuffer(rid, dtype=np.uint8)
+                outs[j]["agent_id"] = agent.encode()
+                outs[j]["kind"], outs[j]["http_status"], outs[j]["seq"] = kind, http, seq
+            res = eng.complete(outs)
+            assert (res == 0).all()
+            pending_ops.clear()
+
+    for n, op in enumerate(script):
+        r = reqs[op[1]]
+        if op[0] == "resp":
+            pending_ops.append((r.rid, r.agent_id, K.AGR_OUT_RESPONSE, op[2], op[5]))
+        else:
+            pending_ops.append((r.rid, r.agent_id, K.AGR_OUT_ERROR, 0, 0))
+        if n % 7 == 6:                                          # several outcomes (often of one record) per K2 batch
+            flush()
+    flush()
+    # the bytes travel off the hot path; the latest store per record wins, like the reference's SET
+    for op in script:
+        r = reqs[op[1]]
+        if op[0] == "resp":
+            hdr = b"".join(k + b": " + v + b"\n" for k, v in sorted(op[3].items()))
+            assert eng.store_response(r.agent_id, r.rid, hdr, op[4])
+        else:
+            assert eng.store_error_text(r.agent_id, r.rid, op[2])
+    return first
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_wire_form_is_byte_identical(mode, seed):
+    reqs = make_requests(seed, 260, AGENTS, big_bodies=False)
+    if mode == "var":
+        reqs = make_requests(seed, 260, AGENTS, max_payload=7000, big_bodies=True)
+    script = make_script(seed, len(reqs), 330)
+    with A.Engine(slab_rows=1 << 12, max_agents=64, flags=MODES[mode], vslab_bytes=8 << 20, resp_bytes=4 << 20) as eng:
+        first = drive_engine(eng, reqs, script)
+        redis, mgr = run_model(reqs, script)                      # after the drive: mint mode filled in the ids
+        for r in reqs:
+            want = G.marshal_request(redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}"))
+            got = eng.get_record_json(r.agent_id, r.rid)
+            assert got == want, (r, got, want)
+        assert eng.get_record_json(AGENTS[0], bytes(range(16))) is None
+        n_pending = 0
+        for a in AGENTS + ["agent-unknown"]:
+            want = G.marshal_list(mgr.get_pending_requests(a))
+            got, cnt = eng.pending_json(a)
+            assert got == want
+            assert cnt == len(redis.lrange_all(f"agent:{a}:requests:pending"))
+            n_pending += cnt
+        assert n_pending > 20
+        # all rows at once: array form and back-to-back form with offsets
+        every = [redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}") for r in reqs]
+        got, offs = eng.rows_json(first, len(reqs), as_array=True)
+        assert got == G.marshal_list(every)
+        assert len(json.loads(got)) == len(reqs)
+        got, offs = eng.rows_json(first, len(reqs), as_array=False)
+        for i, rec in enumerate(every):
+            assert got[int(offs[i]):int(offs[i + 1])] == G.marshal_request(rec)
+        assert eng.rows_json(first, 0, as_array=True)[0] == b"null"
+        assert eng.stats()["k5_launches"] > 0
+
+
+def test_default_error_text_and_unstored_rows():
+    """Without agr_store_error_text the wire form says "transport error" (what oracle/model.py's proxy passes to
+    MarkRequestFailed); rows that hold no stored record (replay-flagged arrivals) encode as null."""
+    reqs = make_requests(5, 4, AGENTS[:1])
+    with A.Engine(slab_rows=1 << 10, max_agents=8, flags=MODES["hash"]) as eng:
+        eng.set_agent_state(AGENTS[0], K.AGR_AGENT_RUNNING)
+        recs = records_array(reqs)
+        recs[3]["flags"] |= K.AGR_F_REPLAY                        # not stored (server.go:508)
+        recs[3]["replay_of"] = recs[0]["request_id"]
+        out = np.zeros(4, dtype=A.verdict_dtype); ids = np.zeros((4, 16), dtype=np.uint8)
+        first = eng.ingest_ex(recs, out, ids)
+        outs = np.zeros(1, dtype=A.outcome_dtype)
+        outs[0]["request_id"] = recs[1]["request_id"]; outs[0]["agent_id"] = AGENTS[0].encode(); outs[0]["kind"] = K.AGR_OUT_ERROR
+        eng.complete(outs)
+        d = json.loads(eng.get_record_json(AGENTS[0], reqs[1].rid))
+        assert d["error"] == "transport error" and d["retry_count"] == 1 and d["status"] == "pending"
+        got, offs = eng.rows_json(first, 4, as_array=True)
+        assert json.loads(got)[3] is None
+
+
+def test_large_pending_list():
+    """A pending list far larger than one CTA's chunk: offsets across chunk boundaries, the array framing, the count."""
+    n = 5000
+    reqs = make_requests(9, n, AGENTS[:1])
+    with A.Engine(slab_rows=1 << 13, max_agents=8, flags=MODES["mint"]) as eng:
+        eng.set_agent_state(AGENTS[0], K.AGR_AGENT_STOPPED)
+        out = np.zeros(n, dtype=A.verdict_dtype); ids = np.zeros((n, 16), dtype=np.uint8)
+        eng.ingest_ex(records_array(reqs), out, ids)
+        for r, i in zip(reqs, ids):
+            r.rid = bytes(i)
+        redis, mgr = run_model(reqs, [])
+        got, cnt = eng.pending_json(AGENTS[0])
+        assert cnt == n
+        assert got == G.marshal_list(mgr.get_pending_requests(AGENTS[0]))
