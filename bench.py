@@ -396,11 +396,19 @@ def run_ours(args, wl, rank, world, local_rank):
         for k in range(wl["agents"]):
             eng.set_agent_state(A.synth_agent_id(k, agent_nanos0=nanos0), "running")
         scanned = eng.stats()["rows_used"]
+        # K5: the JSON wire form (json.Marshal(requests.Request)) of the same batch, left on the device
+        eng.rows_json(first + W * B, B, as_array=True, fetch=False)        # warm-up: sizes the output buffer
+        json_bytes = eng.rows_json(first + W * B, B, as_array=True, fetch=False)
+        k5_ms = eng.op_time(2)
         secondary = {"k2_complete": {"outcomes": B, "ms": k2_ms, "outcomes_per_s": B / (k2_ms * 1e-3), "algorithmic_bytes_per_outcome": 72,
                                      "GBps": 72 * B / (k2_ms * 1e-3) / 1e9},
                      "k3_replay_scan": {"rows_scanned": scanned, "dispatched": int(len(disp)), "ms": k3_ms,
                                         "rows_per_s": scanned / (k3_ms * 1e-3), "algorithmic_bytes_per_row": 8,
-                                        "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9}}
+                                        "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9},
+                     "k5_json": {"records": B, "ms": k5_ms, "records_per_s": B / (k5_ms * 1e-3), "json_bytes": json_bytes,
+                                 "algorithmic_bytes_per_record": 512 + json_bytes / B,
+                                 "GBps": (512 * B + json_bytes) / (k5_ms * 1e-3) / 1e9,
+                                 "note": "measure + scan + emit kernels and the host's read of the total between them"}}
     # ---- the same workload and kernel in the OTHER id mode: "mint" = the engine mints
     # Request.ID like StoreRequest does (requests.go:87) and ids are a keyed bijection of the row; "hash" = caller-supplied
     # random ids kept in a 32 B/slot dedupe index (one CAS.128 + RED per stored record)
