@@ -15,12 +15,33 @@
 #define K5_WARPS 8
 #define K5_CHUNK 256u          // records per CTA (32 per warp)
 #define K5_SB 1280u            // staging bytes per warp
-#define K5_FLUSH 1024u
+#define K5_FLUSH 768u
 
-#define JLIT(W, S) (W).lit(S, (uint32_t)(sizeof(S) - 1))
+// up to 32 literal bytes as four packed words, evaluated at compile time: no memory access, the lane picks its byte
+__host__ __device__ constexpr unsigned long long jpack(const char* s, size_t n, size_t k) {
+    unsigned long long w = 0;
+    for (size_t i = 0; i < 8; ++i) if (8 * k + i < n) w |= (unsigned long long)(unsigned char)s[8 * k + i] << (8 * i);
+    return w;
+}
+#define JLIT(W, S) do { constexpr unsigned long long _a = jpack(S, sizeof(S) - 1, 0), _b = jpack(S, sizeof(S) - 1, 1), \
+                                                      _c = jpack(S, sizeof(S) - 1, 2), _d = jpack(S, sizeof(S) - 1, 3); \
+                        static_assert(sizeof(S) - 1 <= 32, "literal too long"); \
+                        (W).lit(_a, _b, _c, _d, (uint32_t)(sizeof(S) - 1)); } while (0)
 
 namespace {
 
+__device__ __forceinline__ uint32_t pick_byte(unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d, int i) {
+    const unsigned long long w = (i & 16) ? ((i & 8) ? d : c) : ((i & 8) ? b : a);
+    return (uint32_t)(w >> (8 * (i & 7))) & 0xffu;
+}
+// exclusive prefix of per-lane lengths that only take the values 0, 1, 2, 3, 6 — four ballots instead of a shuffle scan
+__device__ __forceinline__ uint32_t len_scan(uint32_t el, int lane, uint32_t& total) {
+    const uint32_t g1 = __ballot_sync(FULL, el >= 1u), g2 = __ballot_sync(FULL, el >= 2u), g3 = __ballot_sync(FULL, el >= 3u),
+                   g6 = __ballot_sync(FULL, el == 6u);
+    const uint32_t below = (1u << lane) - 1u;
+    total = __popc(g1) + __popc(g2) + __popc(g3) + 3u * __popc(g6);
+    return __popc(g1 & below) + __popc(g2 & below) + __popc(g3 & below) + 3u * __popc(g6 & below);
+}
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
     uint32_t x = v;
 #pragma unroll
@@ -29,6 +50,54 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return x - v;
 }
 __device__ __forceinline__ char hexc(uint32_t v) { return (char)(v < 10 ? '0' + v : 'a' + (v - 10)); }
+
+// time.Time.MarshalJSON of time.Unix(0, ns).UTC(): RFC3339Nano, trailing zeros of the fraction dropped, no quotes.
+// w0..w3 hold the 9-digit form "YYYY-MM-DDTHH:MM:SS.fffffffff"; the text is its first len-1 characters followed by 'Z'.
+struct jtime { unsigned long long w0, w1, w2, w3; uint32_t len; };
+__device__ __forceinline__ uint32_t time_len(unsigned long long ns) {
+    uint32_t ft = (uint32_t)(ns % 1000000000ull), nd = 0;
+    if (ft) { nd = 9; while (ft % 10u == 0u) { ft /= 10u; --nd; } }
+    return 19u + (nd ? 1u + nd : 0u) + 1u;
+}
+__device__ __forceinline__ jtime fmt_time(unsigned long long ns) {
+    const unsigned long long secs = ns / 1000000000ull;
+    const uint32_t frac = (uint32_t)(ns - secs * 1000000000ull);
+    const uint32_t days = (uint32_t)(secs / 86400ull);
+    const uint32_t sod = (uint32_t)(secs - (unsigned long long)days * 86400ull);
+    const uint32_t z = days + 719468u;                                // days since 0000-03-01 (civil-from-days)
+    const uint32_t era = z / 146097u;
+    const uint32_t doe = z - era * 146097u;
+    const uint32_t yoe = (doe - doe / 1460u + doe / 36524u - doe / 146096u) / 365u;
+    uint32_t y = yoe + era * 400u;
+    const uint32_t doy = doe - (365u * yoe + yoe / 4u - yoe / 100u);
+    const uint32_t mp = (5u * doy + 2u) / 153u;
+    const uint32_t dd = doy - (153u * mp + 2u) / 5u + 1u;
+    const uint32_t mm = mp < 10u ? mp + 3u : mp - 9u;
+    if (mm <= 2u) ++y;
+    uint32_t nd = 0, ft = frac;
+    if (frac) { nd = 9; while (ft % 10u == 0u) { ft /= 10u; --nd; } }
+    const uint32_t hh = sod / 3600u, mi = sod / 60u % 60u, ss = sod % 60u;
+    const uint32_t fa = frac / 100000u, fb = frac % 100000u;          // 4 + 5 fraction digits
+    jtime t;
+#define D8(v, sh) ((unsigned long long)('0' + (v)) << (sh))
+    t.w0 = D8(y / 1000u % 10u, 0) | D8(y / 100u % 10u, 8) | D8(y / 10u % 10u, 16) | D8(y % 10u, 24) |
+           ((unsigned long long)'-' << 32) | D8(mm / 10u, 40) | D8(mm % 10u, 48) | ((unsigned long long)'-' << 56);
+    t.w1 = D8(dd / 10u, 0) | D8(dd % 10u, 8) | ((unsigned long long)'T' << 16) | D8(hh / 10u, 24) | D8(hh % 10u, 32) |
+           ((unsigned long long)':' << 40) | D8(mi / 10u, 48) | D8(mi % 10u, 56);
+    t.w2 = ((unsigned long long)':' << 0) | D8(ss / 10u, 8) | D8(ss % 10u, 16) | ((unsigned long long)'.' << 24) |
+           D8(fa / 1000u, 32) | D8(fa / 100u % 10u, 40) | D8(fa / 10u % 10u, 48) | D8(fa % 10u, 56);
+    t.w3 = D8(fb / 10000u, 0) | D8(fb / 1000u % 10u, 8) | D8(fb / 100u % 10u, 16) | D8(fb / 10u % 10u, 24) | D8(fb % 10u, 32);
+#undef D8
+    t.len = 19u + (nd ? 1u + nd : 0u) + 1u;
+    return t;
+}
+__device__ __forceinline__ jtime bcast_time(const jtime& t, int src) {
+    jtime r;
+    r.w0 = __shfl_sync(FULL, t.w0, src); r.w1 = __shfl_sync(FULL, t.w1, src);
+    r.w2 = __shfl_sync(FULL, t.w2, src); r.w3 = __shfl_sync(FULL, t.w3, src);
+    r.len = __shfl_sync(FULL, t.len, src);
+    return r;
+}
 
 template <bool EMIT>
 struct jwriter {
@@ -66,32 +135,35 @@ struct jwriter {
             __syncwarp();
         }
     }
-    // the caller has written k bytes at sb[fill ..)
+    // the caller has written k bytes at sb[fill ..).  Nothing flushes here: check() does, and is called at least every
+    // K5_SB - K5_FLUSH staged bytes (every step of the variable-length loops, once per group of fixed fields)
     __device__ __forceinline__ void commit(uint32_t k) {
-        if (EMIT) { fill += k; if (fill >= K5_FLUSH) flush(false); }
-        else total += k;
+        if (EMIT) fill += k; else total += k;
     }
-    __device__ __forceinline__ void lit(const char* s, uint32_t k) {       // k <= 32
-        if (EMIT && (uint32_t)lane < k) sb[fill + lane] = (uint8_t)s[lane];
+    __device__ __forceinline__ void check() {
+        if (EMIT && fill >= K5_FLUSH) flush(false);
+    }
+    __device__ __forceinline__ void lit(unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d, uint32_t k) {
+        if (EMIT && (uint32_t)lane < k) sb[fill + lane] = (uint8_t)pick_byte(a, b, c, d, lane);
         commit(k);
     }
     __device__ __forceinline__ void ch(char c) {
         if (EMIT && lane == 0) sb[fill] = (uint8_t)c;
         commit(1);
     }
-    __device__ __forceinline__ void uint(uint32_t v) {
-        uint32_t nd = 1;
-        for (uint32_t t = v; t >= 10; t /= 10) ++nd;
+    __device__ __forceinline__ void uint(uint32_t v) {           // v < 100000 (status codes, retry counters)
+        const uint32_t d4 = v / 10000u, d3 = v / 1000u % 10u, d2 = v / 100u % 10u, d1 = v / 10u % 10u, d0 = v % 10u;
+        const uint32_t nd = v >= 10000u ? 5u : v >= 1000u ? 4u : v >= 100u ? 3u : v >= 10u ? 2u : 1u;
         if (EMIT && (uint32_t)lane < nd) {
-            uint32_t t = v;
-            for (uint32_t k = nd - 1 - lane; k; --k) t /= 10;
-            sb[fill + lane] = (uint8_t)('0' + t % 10);
+            const unsigned long long digs = (unsigned long long)d0 | ((unsigned long long)d1 << 8) | ((unsigned long long)d2 << 16) |
+                                            ((unsigned long long)d3 << 24) | ((unsigned long long)d4 << 32);
+            sb[fill + lane] = (uint8_t)('0' + ((digs >> (8 * (nd - 1 - lane))) & 0xffu));
         }
         commit(nd);
     }
     // uuid.UUID.String(): 8-4-4-4-12 lower-case hex
     __device__ __forceinline__ void uuid(unsigned long long lo, unsigned long long hi) {
-        if (EMIT && lane < 32) {
+        if (EMIT) {
             const int i = lane;                                      // nibble index
             const int b = i >> 1;
             const uint32_t byte = (uint32_t)((b < 8 ? lo >> (8 * b) : hi >> (8 * (b - 8))) & 0xffu);
@@ -102,44 +174,11 @@ struct jwriter {
         }
         commit(36);
     }
-    // time.Time.MarshalJSON of time.Unix(0, ns).UTC(): RFC3339Nano (trailing zeros of the fraction dropped)
-    __device__ __forceinline__ void time(unsigned long long ns) {
-        const unsigned long long secs = ns / 1000000000ull;
-        uint32_t frac = (uint32_t)(ns % 1000000000ull);
-        const uint32_t sod = (uint32_t)(secs % 86400ull);
-        const long long z = (long long)(secs / 86400ull) + 719468;    // days since 0000-03-01 (civil-from-days)
-        const long long era = z / 146097;
-        const uint32_t doe = (uint32_t)(z - era * 146097);
-        const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-        uint32_t y = yoe + (uint32_t)era * 400;
-        const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-        const uint32_t mp = (5 * doy + 2) / 153;
-        const uint32_t dd = doy - (153 * mp + 2) / 5 + 1;
-        const uint32_t mm = mp < 10 ? mp + 3 : mp - 9;
-        if (mm <= 2) ++y;
-        uint32_t nd = 0;
-        if (frac) { nd = 9; while (frac % 10 == 0) { frac /= 10; --nd; } }
-        const uint32_t len = 19 + (nd ? 1 + nd : 0) + 1;
+    // a formatted time (jtime, below): lane i writes character i
+    __device__ __forceinline__ void time(unsigned long long w0, unsigned long long w1, unsigned long long w2, unsigned long long w3, uint32_t len) {
         if (EMIT && (uint32_t)lane < len) {
-            const uint32_t hh = sod / 3600, mi = sod / 60 % 60, ss = sod % 60;
-            char c;
-            const int i = lane;
-            switch (i) {
-                case 0: c = '0' + y / 1000 % 10; break;  case 1: c = '0' + y / 100 % 10; break;
-                case 2: c = '0' + y / 10 % 10; break;    case 3: c = '0' + y % 10; break;
-                case 4: c = '-'; break;                  case 5: c = '0' + mm / 10; break;
-                case 6: c = '0' + mm % 10; break;        case 7: c = '-'; break;
-                case 8: c = '0' + dd / 10; break;        case 9: c = '0' + dd % 10; break;
-                case 10: c = 'T'; break;                 case 11: c = '0' + hh / 10; break;
-                case 12: c = '0' + hh % 10; break;       case 13: c = ':'; break;
-                case 14: c = '0' + mi / 10; break;       case 15: c = '0' + mi % 10; break;
-                case 16: c = ':'; break;                 case 17: c = '0' + ss / 10; break;
-                case 18: c = '0' + ss % 10; break;
-                default:
-                    if ((uint32_t)i == len - 1) c = 'Z';
-                    else if (i == 19) c = '.';
-                    else { uint32_t t = frac; for (uint32_t k = nd - 1 - (uint32_t)(i - 20); k; --k) t /= 10; c = '0' + t % 10; }
-            }
+            uint32_t c = pick_byte(w0, w1, w2, w3, lane);
+            if ((uint32_t)lane == len - 1u) c = 'Z';
             sb[fill + lane] = (uint8_t)c;
         }
         commit(len);
@@ -220,9 +259,16 @@ __device__ __forceinline__ uint32_t esc_byte(const uint8_t* s, uint32_t len, uin
 template <bool EMIT>
 __device__ __forceinline__ void put_packed(jwriter<EMIT>& w, uint32_t el, unsigned long long chars) {
     uint32_t tot;
-    const uint32_t off = warp_excl_scan(el, w.lane, tot);
-    if (EMIT) for (uint32_t k = 0; k < el; ++k) w.sb[w.fill + off + k] = (uint8_t)(chars >> (8 * k));
+    const uint32_t off = len_scan(el, w.lane, tot);
+    if (EMIT) {
+        uint8_t* dst = w.sb + w.fill + off;
+        if (el >= 1u) dst[0] = (uint8_t)chars;
+        if (el >= 2u) dst[1] = (uint8_t)(chars >> 8);
+        if (el >= 3u) dst[2] = (uint8_t)(chars >> 16);
+        if (el == 6u) { dst[3] = (uint8_t)(chars >> 24); dst[4] = (uint8_t)(chars >> 32); dst[5] = (uint8_t)(chars >> 40); }
+    }
     w.commit(tot);
+    w.check();
 }
 
 // a JSON string body (no quotes) from s[0..len)
@@ -230,8 +276,17 @@ template <bool EMIT>
 __device__ __forceinline__ void put_escaped(jwriter<EMIT>& w, const uint8_t* s, uint32_t len, bool touched) {
     for (uint32_t base = 0; base < len; base += 32) {
         const uint32_t p = base + w.lane;
+        const uint32_t b = p < len ? s[p] : 0x20u;
+        const bool special = b < 0x20u || b >= 0x80u || b == '"' || b == '\\' || b == '<' || b == '>' || b == '&';
+        if (!__any_sync(FULL, special)) {                     // the common step: bytes copy through
+            const uint32_t k = min(32u, len - base);
+            if (EMIT && p < len) w.sb[w.fill + w.lane] = (uint8_t)b;
+            w.commit(k);
+            w.check();
+            continue;
+        }
         unsigned long long chars = 0; uint32_t el = 0;
-        if (p < len) el = esc_byte(s, len, p, s[p], touched, chars);
+        if (p < len) el = esc_byte(s, len, p, b, touched, chars);
         put_packed(w, el, chars);
     }
 }
@@ -289,7 +344,8 @@ __device__ __forceinline__ void put_base64(jwriter<EMIT>& w, const uint8_t* s, u
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t x = (v >> (18 - 6 * k)) & 63u;
-                const uint32_t c = x < 26 ? 'A' + x : x < 52 ? 'a' + (x - 26) : x < 62 ? '0' + (x - 52) : x == 62 ? '+' : '/';
+                // 'A'+x | 'a'+x-26 | '0'+x-52 | '+' | '/' as one running offset
+                const uint32_t c = x + 65u + (x >= 26u ? 6u : 0u) - (x >= 52u ? 75u : 0u) - (x >= 62u ? 15u : 0u) + (x >= 63u ? 3u : 0u);
                 out |= c << (8 * k);
             }
             if (p + 1 >= len) out = (out & 0x0000ffffu) | ((uint32_t)'=' << 16) | ((uint32_t)'=' << 24);
@@ -298,13 +354,13 @@ __device__ __forceinline__ void put_base64(jwriter<EMIT>& w, const uint8_t* s, u
             dst[0] = (uint8_t)out; dst[1] = (uint8_t)(out >> 8); dst[2] = (uint8_t)(out >> 16); dst[3] = (uint8_t)(out >> 24);
         }
         w.commit(4u * min(32u, groups - g0));
+        w.check();
     }
 }
 
-__device__ __forceinline__ uint32_t cstr_len(const uint8_t* s, uint32_t cap) {
-    uint32_t n = 0;
-    while (n < cap && s[n]) ++n;
-    return n;
+__device__ __forceinline__ uint32_t cstr_len32(const uint8_t* s, int lane) {      // strnlen(s, 32), one byte per lane
+    const uint32_t z = __ballot_sync(FULL, s[lane] == 0);
+    return z ? (uint32_t)__ffs(z) - 1u : 32u;
 }
 
 // json.Marshal(requests.Request) for the record in row `rid`
@@ -330,7 +386,8 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
     JLIT(w, "{\"id\":\"");
     w.uuid(lo, hi);
     JLIT(w, "\",\"agent_id\":\"");
-    put_escaped(w, rec + AGR_OFF_AGENT_ID, cstr_len(rec + AGR_OFF_AGENT_ID, AGR_AGENT_ID_BYTES), touched);
+    w.check();
+    put_escaped(w, rec + AGR_OFF_AGENT_ID, cstr_len32(rec + AGR_OFF_AGENT_ID, w.lane), touched);
     JLIT(w, "\",\"method\":\"");
     switch ((flags & AGR_F_METHOD_MASK) >> AGR_F_METHOD_SHIFT) {
         case AGR_M_GET: JLIT(w, "GET"); break;        case AGR_M_POST: JLIT(w, "POST"); break;
@@ -354,23 +411,32 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
     JLIT(w, ",\"max_retries\":");
     w.uint(st_max(st));
     JLIT(w, ",\"created_at\":\"");
-    w.time(seq);
+    // the two timestamps of a record are formatted side by side (odd lanes: processed_at, even lanes: created_at)
+    const unsigned long long pt = responded ? p.ptime[rid] : 0ull;
+    jtime tc{}, tp{};
+    if (EMIT) {
+        const jtime mine = fmt_time((w.lane & 1) ? pt : seq);
+        tc = bcast_time(mine, 0); tp = bcast_time(mine, 1);
+    } else { tc.len = time_len(seq); tp.len = responded ? time_len(pt) : 0u; }
+    w.time(tc.w0, tc.w1, tc.w2, tc.w3, tc.len);
     w.ch('"');
+    w.check();
     if (responded) {                                         // requests.go:165-167
-        const unsigned long long t = p.ptime[rid];
         JLIT(w, ",\"processed_at\":\"");
-        w.time(t);
+        w.time(tp.w0, tp.w1, tp.w2, tp.w3, tp.len);
         JLIT(w, "\",\"response\":{\"status_code\":");
         w.uint(aux & 0xffffu);
         JLIT(w, ",\"headers\":");
+        w.check();
         const uint32_t rl = p.resp_len[rid], rh = min(p.resp_hlen[rid], rl);
         const uint8_t* rb = p.bytes + p.resp_off[rid];
         put_headers(w, rb, rh, (st & ST_RESP_RT) != 0u);
         JLIT(w, ",\"body\":\"");
         put_base64(w, rb + rh, rl - rh);
         JLIT(w, "\",\"received_at\":\"");
-        w.time(t);
+        w.time(tp.w0, tp.w1, tp.w2, tp.w3, tp.len);
         JLIT(w, "\"}");
+        w.check();
     }
     if (retry != 0u) {                                       // requests.go:244 request.Error = err.Error()
         JLIT(w, ",\"error\":\"");
@@ -383,7 +449,7 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(K5_WARPS * 32) k5_json(const agr_dev d, const agr_k5_params p) {
+__global__ void __launch_bounds__(K5_WARPS * 32, EMIT ? 3 : 6) k5_json(const agr_dev d, const agr_k5_params p) {
     __shared__ __align__(16) uint8_t s_stage[EMIT ? K5_WARPS * K5_SB : 16];
     __shared__ __align__(16) uint4 s_rec[K5_WARPS][32];
     __shared__ unsigned long long s_off[K5_CHUNK];
