@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
-    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json",
+    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire",
 ]
 
 _lib = None
@@ -136,6 +136,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_snapshot": (i32, [vp, C.c_char_p]),
         "agr_restore": (i32, [C.POINTER(AgrConfig), C.c_char_p, C.POINTER(vp)]),
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "agr_expire": (i32, [vp, u64, u64, C.POINTER(u64)]),
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
@@ -522,6 +523,12 @@ class Engine:
 
     def snapshot(self, path: str) -> None:
         _check(self.lib, self.lib.agr_snapshot(self.h, path.encode()))
+
+    def expire(self, now: int, ttl: int) -> int:
+        """Drop the records whose last SET is ttl or more before now (the reference's 24 h key TTL); returns how many."""
+        n = C.c_uint64()
+        _check(self.lib, self.lib.agr_expire(self.h, now, ttl, C.byref(n)))
+        return int(n.value)
 
     def verify(self) -> Tuple[int, int]:
         rows, bad = C.c_uint64(), C.c_uint64()

@@ -94,6 +94,7 @@ struct agr_handle {
     uint32_t* d_jlen = nullptr; unsigned long long* d_joff = nullptr; unsigned long long* d_jchunk = nullptr; uint32_t j_cap = 0;
     uint8_t* d_json = nullptr; uint64_t json_cap = 0;
     uint64_t k5_launches = 0;
+    uint64_t expired_total = 0;                // records dropped by agr_expire so far
     // flat-combining front-end for concurrent small ingests (AGR_CFG_COMBINE)
     std::mutex cmu; std::condition_variable ccv;
     agr_record* c_ring = nullptr;              // pinned [AGR_COMBINE_RING]
@@ -281,6 +282,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->d_err_off, c.slab_rows, true));
     TRY(dev_alloc(h, &h->d_err_len, c.slab_rows, true));
     TRY(dev_alloc(h, &d.ptime, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.mtime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
     d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
     d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
@@ -829,7 +831,8 @@ int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16],
     if (slot < 0) return 0;
     uint32_t total = 0;
     if (which == AGR_LIST_PENDING) {
-        TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap, &total));
+        // LRANGE: ids of expired records are still in the list; they lie below the scan's low-water mark
+        TRY(select_locked(h, K3_AGENT_PENDING_IDS, (uint32_t)slot, nullptr, h->expired_total ? 0 : h->scan_lo, h->rows_used, cap, &total));
     } else {
         unsigned long long lens[2];
         CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
@@ -1193,7 +1196,7 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 struct snap_header {
     char magic[8];                 // "AGRSNAP2"
     uint32_t flags, n_agents, shard, gen;
-    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total;
 };
 static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
     const size_t chunk = h->bounce_bytes;
@@ -1228,7 +1231,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
-    hd.resp_used = h->resp_used;
+    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total;
     unsigned long long lens[2];
     int rc = 0;
     auto done = [&](int r) { fclose(f); return r; };
@@ -1260,6 +1263,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     if ((rc = dump_dev(h, f, h->d_err_off, R * 8)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_err_len, R * 4)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.ptime, R * 8)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d.mtime, R * 8)) < 0) return done(rc);
     return done(0);
 }
 
@@ -1312,7 +1316,8 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if ((rc = load_dev(h, f, h->d_err_off, R * 8)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_err_len, R * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.ptime, R * 8)) < 0) return bail(rc);
-    h->resp_used = hd.resp_used;
+    if ((rc = load_dev(h, f, h->d.mtime, R * 8)) < 0) return bail(rc);
+    h->resp_used = hd.resp_used; h->expired_total = hd.expired_total;
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->scan_lo = hd.scan_lo;
@@ -1324,6 +1329,23 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     }
     fclose(f);
     *out = h;
+    return 0;
+}
+
+int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
+    if (!h) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
+    CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
+    agr_launch_expire(h->d, h->rows_used, now, ttl, d_cnt, h->stream);
+    h->k3_launches += 1;
+    CK(cudaGetLastError());
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->expired_total += v;
+    if (expired) *expired = v;
     return 0;
 }
 

@@ -228,6 +228,27 @@ __global__ void __launch_bounds__(256) k_verify(const agr_dev d, const unsigned 
     c1 = __reduce_add_sync(FULL, c1);
     if (lane == 0 && agr_cksum_pack(c0, c1) != d.cksum[rid]) atomicAdd(bad, 1ULL);
 }
+// TTL sweep: the reference stores every record with SET ... EX 24h (requests.go:106,175,270); a record whose last SET is
+// ttl or more in the past is gone (GET misses), while its id stays in whatever lists hold it.  Thread per row.
+__global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned long long rows, const unsigned long long now,
+                                                const unsigned long long ttl, unsigned long long* __restrict__ expired) {
+    const unsigned long long rid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool gone = false;
+    if (rid < rows) {
+        const uint32_t st = d.state[rid];
+        if (st & ST_STORED) {
+            unsigned long long t = d.mtime[rid];
+            if (t == 0) t = *reinterpret_cast<const unsigned long long*>(rec_ptr(d, (uint32_t)rid) + AGR_OFF_SEQ);
+            if (now >= t && now - t >= ttl) { d.state[rid] = st & ~ST_STORED; gone = true; }
+        }
+    }
+    const uint32_t m = __ballot_sync(FULL, gone);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(expired, (unsigned long long)__popc(m));
+}
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
+                       unsigned long long* expired, cudaStream_t st) {
+    if (rows) k_expire<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, rows, now, ttl, expired);
+}
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st) {
     if (rows) k_verify<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(d, rows, bad);
 }
@@ -351,7 +372,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
     }
     if (root) {
         uint32_t st = d.state[rid], aux = d.aux[rid];
-        unsigned long long ptime = 0; bool responded = false;
+        unsigned long long ptime = 0, mtime = 0; bool responded = false, written = false;
         long long last = -1;
         for (;;) {
             // next op of this row in ascending op index
@@ -367,6 +388,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
             if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
                 st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED | ST_RESPONDED;  // :166
                 ptime = op.seq; responded = true;                                // :164,167 now / ProcessedAt
+                mtime = op.seq; written = true;                                  // :175 SET ... EX 24h restarts the TTL (Q11)
                 st &= ~ST_RESP_RT;                                               // a fresh Response object
                 if (st_retry(st)) st |= ST_ERR_RT;                               // Error went through Unmarshal + Marshal
                 aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
@@ -378,6 +400,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
                 st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT | ST_ERR_RT)) | (retry << ST_RETRY_SHIFT);
                 if (st & ST_RESPONDED) st |= ST_RESP_RT;
                 aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
+                mtime = op.seq; written = true;                                  // :270 SET ... EX 24h
                 nerr++;
                 if (retry < st_max(st)) {
                     st |= AGR_ST_PENDING;                                        // :248-249, keeps queue position (Q11)
@@ -394,6 +417,7 @@ __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_sc
         d.state[rid] = st;
         d.aux[rid] = aux;
         if (responded) d.ptime[rid] = ptime;
+        if (written) d.mtime[rid] = mtime;
         d.head[rid] = 0;
     }
     ncomp = __reduce_add_sync(FULL, ncomp);
@@ -510,8 +534,12 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
     }
     const uint32_t rid = (uint32_t)it;
     if (!(st & ST_INQ)) return o;                       // not in agent:{a}:requests:pending
-    o.inq = true;
     o.rid = rid; o.slot = rt_slot(rt);
+    if (p.mode == K3_AGENT_PENDING_IDS) { o.sel = (o.slot == p.slot); return o; }   // LRANGE pending 0 -1
+    // the record key has expired (agr_expire): its id stays in the list but GetPendingRequests skips it
+    // (requests.go:210-213, Q10), so it is neither returned nor replayed, and it no longer holds the scan's low-water mark
+    if (!(st & ST_STORED)) return o;
+    o.inq = true;
     if (p.mode == K3_AGENT_PENDING) { o.sel = (o.slot == p.slot); return o; }   // GetPendingRequests, requests.go:197-225
     // K3_TICK: isAgentRunning (replay_worker.go:76-81,166-189) + the skip rule of :101
     if (d.astatus[o.slot] != AGR_AGENT_RUNNING) return o;

@@ -31,6 +31,7 @@ struct agr_dev {
     uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
     unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
+    unsigned long long* mtime; // [rows] time of the latest SET of the record by K2 (0: only StoreRequest's, = the record's seq)
     unsigned long long* voff;  // variable-length mode: byte offset of row's record in the slab (nullptr = fixed 512 B rows)
     uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
@@ -59,7 +60,7 @@ struct agr_k2_scratch {
 };
 
 // K3 select modes
-enum { K3_TICK = 0, K3_AGENT_PENDING = 1, K3_LOG_AGENT = 2 };
+enum { K3_TICK = 0, K3_AGENT_PENDING = 1, K3_LOG_AGENT = 2, K3_AGENT_PENDING_IDS = 3 /* LRANGE: expired records' ids included */ };
 struct agr_k3_params {
     int mode;
     uint32_t slot;             // agent for the single-agent modes
@@ -130,6 +131,8 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */,
                    void* ids = nullptr /* device u8[n][16]: Request.ID per record, written by k1_post */);
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
+                       unsigned long long* expired, cudaStream_t st);
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st);
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);

@@ -282,6 +282,13 @@ int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, u
  * In hash-id mode the dedupe index is not stored: it is rebuilt on the device from the restored rows. */
 int agr_snapshot(agr_handle* h, const char* path);
 int agr_restore(const agr_config* cfg, const char* path, agr_handle** out);
+/* The 24 h TTL of the record keys (SET ... EX 24h at requests.go:106,175,270; every SET restarts it, Q11).  Times are the
+ * callers' own clock: agr_record.seq for StoreRequest's SET, agr_outcome.seq for the SETs of StoreResponse /
+ * MarkRequestFailed.  agr_expire drops every record whose last SET lies ttl or more before `now` (same unit as seq):
+ * GET misses from then on (agr_get_record / agr_complete: AGR_ENOTFOUND, "failed to get request"), GetPendingRequests and
+ * the replay scan skip it (requests.go:210-213), and — like in the reference — its id stays in the pending / completed /
+ * failed lists (agr_list).  *expired (nullable) = records dropped by this call.  Rows are not reclaimed. */
+int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired);
 /* Integrity sweep: recomputes the checksum of every stored record on the device and compares it with the one K1 took at
  * ingest.  *bad = number of rows that differ (0 on a healthy slab). */
 int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad);

@@ -53,6 +53,11 @@ class MiniRedis:
         self.lists: Dict[str, List[str]] = {}
         self.ops: List[Tuple] = []          # command trace, used by KAT-A
         self.trace = False
+        # key expiry (SET ... EX): the server's clock is set by the event stream (same unit as the stream's times,
+        # nanoseconds by default); it stays 0 in streams that never advance it, so nothing expires there
+        self.now = 0
+        self.ticks_per_second = 1_000_000_000
+        self.expires_at: Dict[str, int] = {}
 
     def _t(self, *op) -> None:
         if self.trace:
@@ -61,9 +66,15 @@ class MiniRedis:
     def set(self, key: str, value, ttl_s: int = 0) -> None:   # SET key value EX ttl (TTL reset on every SET, Q11)
         self._t("SET", key)
         self.strings[key] = value
+        if ttl_s:
+            self.expires_at[key] = self.now + ttl_s * self.ticks_per_second
+        else:
+            self.expires_at.pop(key, None)
 
     def get(self, key: str):
         self._t("GET", key)
+        if key in self.expires_at and self.now >= self.expires_at[key]:    # expired keys are gone
+            del self.strings[key], self.expires_at[key]
         if key not in self.strings:
             raise RedisNil(key)
         return self.strings[key]
@@ -100,6 +111,7 @@ class MiniRedis:
     def delete(self, key: str) -> None:
         self._t("DEL", key)
         self.strings.pop(key, None)
+        self.expires_at.pop(key, None)
         self.lists.pop(key, None)
 
 
@@ -426,7 +438,10 @@ class ReferencePath:
         return {q: self.redis.lrange_all(f"agent:{agent_id}:requests:{q}") for q in ("pending", "completed", "failed")}
 
     def record(self, agent_id: str, request_id: str) -> Optional[dict]:
-        return self.redis.strings.get(f"agent:{agent_id}:requests:{request_id}")
+        try:
+            return self.redis.get(f"agent:{agent_id}:requests:{request_id}")
+        except RedisNil:
+            return None
 
     def record_state(self, agent_id: str, request_id: str) -> Optional[Tuple[str, int, int]]:
         r = self.record(agent_id, request_id)

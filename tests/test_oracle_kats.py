@@ -61,3 +61,24 @@ def test_replay_path_strip():
     ref.set_agent(AGENT_A, "running")
     ref.tick(lambda a, r: ("response", 200), now=9)
     assert seen == [f"/agent/{AGENT_A}/chat", f"/agent/{AGENT_A}/", f"/agent/{AGENT_A}/"]
+
+
+def test_model_key_ttl():
+    """SET ... EX 24h (requests.go:106): the record key expires 24 h after its LAST SET; list entries stay (Q10, Q11)."""
+    from oracle import model as M
+    redis = M.MiniRedis(); mgr = M.Manager(redis)
+    day = 24 * 3600 * redis.ticks_per_second
+    mgr.store_request("a", M.HttpRequest("GET", "/agent/a/x", {}, b"", new_id="r1", now=0))
+    mgr.store_request("a", M.HttpRequest("GET", "/agent/a/y", {}, b"", new_id="r2", now=0))
+    redis.now = day // 2
+    mgr.mark_request_failed("a", "r2", "boom")                 # SET again: r2's TTL restarts
+    redis.now = day - 1
+    assert [r["id"] for r in mgr.get_pending_requests("a")] == ["r1", "r2"]
+    redis.now = day
+    assert [r["id"] for r in mgr.get_pending_requests("a")] == ["r2"]          # r1 skipped, :210-213
+    assert redis.lrange_all("agent:a:requests:pending") == ["r1", "r2"]        # but still listed
+    import pytest
+    with pytest.raises(KeyError):
+        mgr.store_response("a", "r1", M.HttpResponse(200, now=redis.now))
+    redis.now = day + day // 2
+    assert mgr.get_pending_requests("a") == []
