@@ -16,7 +16,7 @@
 #define VT_TAIL 4608u                 // stage room behind the tile for the last owned record (a 4 KB body fits); a record that
                                       // ends beyond the stage (> 4.5 KiB and badly placed: rare) is read from global memory
 #define VT_STAGE (VT_TILE + VT_TAIL)  // 12800 B = 100 x 128
-#define VT_MAXCNT (VT_TILE / 96u + 2u)   // at most this many records can start in one tile
+#define VT_MAXCNT (VT_TILE / 96u + 2u)   // at most this many records can start in one tile (87: three offsets per lane)
 
 __device__ __forceinline__ uint32_t v_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint4 v_lds128(uint32_t a) {
@@ -59,21 +59,9 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
     const uint32_t bar = v_smem_u32(&bars[warp]);
     const uint32_t tstride = gridDim.x * WARPS;
 
-    // next non-empty tile at or after t: returns its record range and leaves its offsets in s_off[warp][buf]
-    auto fetch_meta = [&](uint32_t t, int buf, uint32_t& a, uint32_t& cnt) -> uint32_t {
-        for (; t < ntiles; t += tstride) {
-            a = __ldg(&tile_first[t]);
-            const uint32_t b = __ldg(&tile_first[t + 1]);
-            if (a != b) {                                       // (a tile inside a long record owns nothing)
-                cnt = b - a;
-                for (uint32_t k = lane; k <= cnt; k += 32) s_off[warp][buf][k] = __ldg(&off[a + k]);
-                __syncwarp();
-                return t;
-            }
-        }
-        cnt = 0;
-        return ntiles;
-    };
+    // Tile metadata is software-pipelined two tiles deep so that no global-load latency sits on the warp's critical path:
+    // while tile T is processed, the record offsets of T+1 are in flight into registers (their range [a1, b1) was read one
+    // iteration earlier) and the range of T+2 is being read.  A tile inside one long record owns nothing (cnt == 0).
     auto issue = [&](int buf, uint32_t cnt) {
         if (lane == 0) {
             const uint32_t start = s_off[warp][buf][0];
@@ -84,15 +72,48 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
                          ::"r"(stage), "l"(blob + start), "r"(bytes), "r"(bar) : "memory");
         }
     };
+    auto range_of = [&](uint32_t t, uint32_t& ra, uint32_t& rb) {
+        ra = rb = 0;
+        if (t < ntiles) { ra = __ldg(&tile_first[t]); rb = __ldg(&tile_first[t + 1]); }
+    };
 
     int cur = 0;
-    uint32_t a = 0, cnt = 0, phase = 0;
-    uint32_t tile = fetch_meta(blockIdx.x * WARPS + warp, cur, a, cnt);
-    if (tile < ntiles) issue(cur, cnt);
+    uint32_t phase = 0;
+    uint32_t tile = blockIdx.x * WARPS + warp;
+    uint32_t a, b1v, a1, b1;
+    range_of(tile, a, b1v);
+    uint32_t cnt = b1v - a;
+    if (cnt) {
+        for (uint32_t k = lane; k <= cnt; k += 32) s_off[warp][cur][k] = __ldg(&off[a + k]);
+        __syncwarp();
+        issue(cur, cnt);
+    }
+    range_of(tile + tstride, a1, b1);
     while (tile < ntiles) {
-        // the NEXT tile's record range and offsets arrive while this tile's bulk copy is in flight
-        uint32_t na = 0, ncnt = 0;
-        const uint32_t ntile = fetch_meta(tile + tstride, cur ^ 1, na, ncnt);
+        // offsets of the next tile -> registers (at most 3 per lane), range of the one after it -> registers
+        const uint32_t ncnt = b1 - a1;
+        uint32_t o0 = 0, o1 = 0, o2 = 0, a2, b2;
+        if (ncnt) {
+            if ((uint32_t)lane <= ncnt) o0 = __ldg(&off[a1 + lane]);
+            if ((uint32_t)lane + 32u <= ncnt) o1 = __ldg(&off[a1 + lane + 32u]);
+            if ((uint32_t)lane + 64u <= ncnt) o2 = __ldg(&off[a1 + lane + 64u]);
+        }
+        range_of(tile + 2u * tstride, a2, b2);
+        auto stage_next = [&]() {                                 // called once this tile's stage has been consumed
+            if (ncnt) {
+                uint32_t* nso = s_off[warp][cur ^ 1];
+                if ((uint32_t)lane <= ncnt) nso[lane] = o0;
+                if ((uint32_t)lane + 32u <= ncnt) nso[lane + 32u] = o1;
+                if ((uint32_t)lane + 64u <= ncnt) nso[lane + 64u] = o2;
+                __syncwarp();
+                issue(cur ^ 1, ncnt);
+            }
+        };
+        if (cnt == 0) {                                           // nothing starts in this tile
+            stage_next();
+            tile += tstride; a = a1; cnt = ncnt; a1 = a2; b1 = b2; cur ^= 1;
+            continue;
+        }
         const uint32_t* so = s_off[warp][cur];
         const uint32_t start = so[0], bytes = min(so[cnt] - start, VT_STAGE);
         asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
@@ -145,10 +166,10 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
         const bool mine = (uint32_t)lane < cnt;
         if (mine) load_header(lane, h0, h1, h2, h3, h4, h5);
         __syncwarp();                                             // the stage has been consumed
-        if (ntile < ntiles) issue(cur ^ 1, ncnt);
+        stage_next();
         if (mine) decide(lane, h0, h1, h2, h3, h4, h5);
         __syncwarp();
-        tile = ntile; a = na; cnt = ncnt; cur ^= 1;
+        tile += tstride; a = a1; cnt = ncnt; a1 = a2; b1 = b2; cur ^= 1;
     }
     k1_flush_counters(d, lc, s_ctr);
 }
