@@ -95,7 +95,7 @@ Error Manager::Decide(const std::string& agentID, const HttpRequest& req, Verdic
     mint_uuid(id);
     if (replay) { auto r = req.Header.find("X-Agentainer-Request-ID"); if (r != req.Header.end()) ParseUUID(r->second, of); }   // :519-522
     agr_record rec; agr_verdict v;
-    ToRecord(agentID, req, id, replay, of, ++seq_, &rec);
+    ToRecord(agentID, req, id, replay, of, now(), &rec);
     uint8_t minted[1][16];
     int rc = agr_ingest_ex(h_, &rec, 1, &v, minted, nullptr);
     if (rc < 0) return std::string("failed to store request: ") + agr_last_error();
@@ -122,18 +122,58 @@ Error Manager::complete(const std::string& agentID, const std::string& requestID
     agr_outcome o; memset(&o, 0, sizeof o);
     if (!ParseUUID(requestID, o.request_id)) return "failed to get request: malformed id";
     strncpy(o.agent_id, agentID.c_str(), AGR_AGENT_ID_BYTES - 1);
-    o.kind = kind; o.http_status = (uint16_t)http; o.seq = ++seq_;
+    o.kind = kind; o.http_status = (uint16_t)http; o.seq = now();
     int32_t res = 0;
     int rc = agr_complete(h_, &o, 1, &res);
     if (rc < 0) return std::string("failed to update request: ") + agr_last_error();
     if (res == AGR_ENOTFOUND) return "failed to get request: redis: nil";                  // requests.go:153-156,232-235
     return "";
 }
-Error Manager::StoreResponse(const std::string& agentID, const std::string& requestID, const Response& resp) {
-    return complete(agentID, requestID, AGR_OUT_RESPONSE, resp.StatusCode);
+static std::string flatten(const std::map<std::string, std::string>& h) {      // sorted by key, "Key: Value\n"
+    std::string out;
+    for (const auto& kv : h) out += kv.first + ": " + kv.second + "\n";
+    return out;
 }
-Error Manager::MarkRequestFailed(const std::string& agentID, const std::string& requestID, const std::string&) {
-    return complete(agentID, requestID, AGR_OUT_ERROR, 0);
+Error Manager::StoreResponse(const std::string& agentID, const std::string& requestID, const Response& resp) {
+    Error e = complete(agentID, requestID, AGR_OUT_RESPONSE, resp.StatusCode);
+    if (!e.empty()) return e;
+    if (resp.Headers.empty() && resp.Body.empty()) return "";               // nothing besides the status code to keep
+    uint8_t id[16]; ParseUUID(requestID, id);
+    const std::string hdr = flatten(resp.Headers);                          // requests.go:134-147
+    if (agr_store_response(h_, agentID.c_str(), id, (const uint8_t*)hdr.data(), (uint32_t)hdr.size(), resp.Body.data(), (uint32_t)resp.Body.size()) < 0)
+        return std::string("failed to update request: ") + agr_last_error();
+    return "";
+}
+Error Manager::MarkRequestFailed(const std::string& agentID, const std::string& requestID, const std::string& err) {
+    Error e = complete(agentID, requestID, AGR_OUT_ERROR, 0);
+    if (!e.empty()) return e;
+    uint8_t id[16]; ParseUUID(requestID, id);
+    if (agr_store_error_text(h_, agentID.c_str(), id, err.data(), (uint32_t)err.size()) < 0)   // request.Error = err.Error(), requests.go:244
+        return std::string("failed to update request: ") + agr_last_error();
+    return "";
+}
+Error Manager::GetRequestJSON(const std::string& agentID, const std::string& requestID, std::string* out) {
+    uint8_t id[16];
+    if (!ParseUUID(requestID, id)) return "redis: nil";
+    uint32_t len = 0;
+    out->resize(4096);
+    int rc = agr_get_record_json(h_, agentID.c_str(), id, (uint8_t*)&(*out)[0], (uint32_t)out->size(), &len);
+    if (rc == AGR_ECAP) { out->resize(len); rc = agr_get_record_json(h_, agentID.c_str(), id, (uint8_t*)&(*out)[0], len, &len); }
+    if (rc < 0) { out->clear(); return "redis: nil"; }                      // storage.Get's miss (server.go:662-666)
+    out->resize(len);
+    return "";
+}
+Error Manager::GetPendingRequestsJSON(const std::string& agentID, std::string* out, size_t* count) {
+    uint64_t len = 0; uint32_t n = 0;
+    if (agr_pending_json(h_, agentID.c_str(), nullptr, 0, &len, &n) < 0) return std::string("failed to get pending queue: ") + agr_last_error();
+    out->resize(len);
+    if (agr_pending_json(h_, agentID.c_str(), (uint8_t*)&(*out)[0], len, &len, &n) < 0) return std::string("failed to get pending queue: ") + agr_last_error();
+    out->resize(len);
+    if (count) *count = n;
+    return "";
+}
+Error Manager::Expire(uint64_t now_ns, uint64_t ttl, uint64_t* expired) {
+    return agr_expire(h_, now_ns, ttl, expired) < 0 ? std::string("expire: ") + agr_last_error() : "";
 }
 Error Manager::RecordTransportError(const std::string& agentID, const std::string& requestID, const std::string& err) {
     // server.go:600-602: substring tests on err.Error()

@@ -72,6 +72,12 @@ class Manager {
     Error GetPendingRequests(const std::string& agentID, std::vector<Request>* out);
     // MarkRequestFailed (requests.go:228-275)
     Error MarkRequestFailed(const std::string& agentID, const std::string& requestID, const std::string& err);
+    // json.Marshal(record) as the reference keeps it in Redis (requests.go:101,169,264; read by server.go:661-668,687-694)
+    Error GetRequestJSON(const std::string& agentID, const std::string& requestID, std::string* out);
+    // json.Marshal(GetPendingRequests(agentID)) — the "pending" member of GET /agents/{id}/requests (server.go:646-650)
+    Error GetPendingRequestsJSON(const std::string& agentID, std::string* out, size_t* count);
+    // the 24 h TTL of the record keys (SET ... EX, requests.go:106,175,270): drop what was last SET ttl or more before now
+    Error Expire(uint64_t now, uint64_t ttl, uint64_t* expired);
     // interceptTransport.RoundTrip's classification (server.go:597-611): dial errors leave the record pending
     Error RecordTransportError(const std::string& agentID, const std::string& requestID, const std::string& err);
     agr_handle* handle() const { return h_; }
@@ -84,6 +90,13 @@ class Manager {
     agr_handle* h_;
     bool mint_;
     std::atomic<uint64_t> seq_{0};
+
+  public:
+    // time.Now() of the mirror: a logical counter by default; SetClock makes it the caller's clock (Unix nanoseconds)
+    void SetClock(std::function<uint64_t()> now) { now_ = std::move(now); }
+  private:
+    uint64_t now() { return now_ ? now_() : ++seq_; }
+    std::function<uint64_t()> now_;
 };
 
 // ReplayWorker (replay_worker.go:16-55).  The HTTP re-injection (replayRequest, :120-163) stays host I/O: the caller

@@ -70,9 +70,43 @@ static int run(bool mint, bool combine) {
     CHECK(list_ids(h, B, AGR_LIST_PENDING).empty());
     CHECK((list_ids(h, B, AGR_LIST_COMPLETED) == std::vector<std::string>{ids[0], ids[0], ids[1], ids[1], ids[2], ids[2]}));
 
+    // wire form + TTL through the mirror: a failed-then-answered record in the reference's JSON, then expiry
+    {
+        const char* D = "agent-1700000000000000004";
+        CHECK(agr_set_agent_state(h, D, AGR_AGENT_STOPPED) == 2);
+        uint64_t clock = 1700000000ull * 1000000000ull;
+        mgr.SetClock([&] { return clock; });
+        HttpRequest r = post; r.Path = std::string("/agent/") + D + "/x<y>"; r.Body = {'h', 'i'};
+        Verdict jv; CHECK(mgr.Decide(D, r, &jv).empty() && jv.Code == AGR_V_QUEUED);
+        std::string js; CHECK(mgr.GetRequestJSON(D, jv.RequestID, &js).empty());
+        const std::string want0 = std::string("{\"id\":\"") + jv.RequestID + "\",\"agent_id\":\"" + D + "\",\"method\":\"POST\",\"path\":\"/agent/" + D +
+            "/x\\u003cy\\u003e\",\"headers\":{\"Content-Type\":\"application/json\"},\"body\":\"aGk=\",\"status\":\"pending\",\"retry_count\":0,"
+            "\"max_retries\":3,\"created_at\":\"2023-11-14T22:13:20Z\"}";
+        CHECK(js == want0);
+        clock += 1500000000ull;
+        CHECK(mgr.MarkRequestFailed(D, jv.RequestID, "EOF").empty());
+        clock += 1000000000ull;
+        Response rr; rr.StatusCode = 201; rr.Headers["Server"] = "x"; rr.Body = {'o', 'k'};
+        CHECK(mgr.StoreResponse(D, jv.RequestID, rr).empty());
+        CHECK(mgr.GetRequestJSON(D, jv.RequestID, &js).empty());
+        CHECK(js.find("\"status\":\"completed\",\"retry_count\":1,") != std::string::npos);
+        CHECK(js.find("\"processed_at\":\"2023-11-14T22:13:22.5Z\",\"response\":{\"status_code\":201,\"headers\":{\"Server\":\"x\"},\"body\":\"b2s=\","
+                      "\"received_at\":\"2023-11-14T22:13:22.5Z\"},\"error\":\"EOF\"}") != std::string::npos);
+        Verdict jv2; CHECK(mgr.Decide(D, r, &jv2).empty());
+        size_t cnt = 0; CHECK(mgr.GetPendingRequestsJSON(D, &js, &cnt).empty());
+        CHECK(cnt == 1 && js.front() == '[' && js.back() == ']' && js.find(jv2.RequestID) != std::string::npos);
+        uint64_t gone = 0;
+        CHECK(mgr.Expire(clock + 24ull * 3600 * 1000000000ull, 24ull * 3600 * 1000000000ull, &gone).empty());
+        CHECK(gone >= 2);                                                    // everything of this run is a day old by then
+        CHECK(!mgr.GetRequestJSON(D, jv.RequestID, &js).empty());            // redis: nil
+        CHECK(mgr.GetPendingRequestsJSON(D, &js, &cnt).empty() && js == "null" && cnt == 0);
+        mgr.SetClock(nullptr);
+        // the rest of the driver continues on the logical clock; rows ingested before stay expired, which the counters below ignore
+    }
+
     // concurrency: NT threads x 500 requests against a running agent, each completed by its own thread
     const char* C = "agent-1700000000000000003";
-    CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 2);
+    CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 3);
     const int NT = combine ? 64 : 8;
     std::vector<std::thread> ths; std::atomic<int> bad{0};
     auto t0 = std::chrono::steady_clock::now();
@@ -90,7 +124,7 @@ static int run(bool mint, bool combine) {
     CHECK(bad == 0);
     CHECK(list_ids(h, C, AGR_LIST_PENDING).empty());
     agr_stats st; CHECK(agr_stats_get(h, &st) == 0);
-    CHECK(st.completions == (uint64_t)(1 + 6 + NT * 500) && st.completion_misses == 1);
+    CHECK(st.completions == (uint64_t)(1 + 6 + 1 + NT * 500) && st.completion_misses == 1);
     printf("host mirror OK (%s ids%s): KAT-A/B/C + %d concurrent single-request Decide+StoreResponse round trips from %d threads, %.0f req/s, %llu K1 launches\n",
            mint ? "engine-minted" : "caller-supplied", combine ? ", flat-combined ingest" : "", NT * 500, NT, NT * 500 / secs,
            (unsigned long long)st.k1_launches);
