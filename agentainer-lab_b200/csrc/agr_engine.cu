@@ -145,6 +145,23 @@ static int dev_alloc(agr_handle* h, T** p, size_t count, bool zero) {
     *p = (T*)q;
     return 0;
 }
+// grow-only scratch: replaces *p by a larger buffer and releases the old one (every user of the old buffer has been
+// synchronised by then: the callers hold the handle mutex and the previous operation ended with a stream sync)
+template <typename T>
+static int dev_regrow(agr_handle* h, T** p, size_t count, bool zero) {
+    T* old = *p;
+    int rc = dev_alloc(h, p, count, zero);
+    if (rc < 0) return rc;
+    if (old) {
+        cudaStreamSynchronize(h->stream);
+        auto it = std::find(h->dev_allocs.begin(), h->dev_allocs.end(), (void*)old);
+        if (it != h->dev_allocs.end()) h->dev_allocs.erase(it);
+        cudaFree(old);
+    }
+    return 0;
+}
+template <typename T>
+static int host_regrow(agr_handle* h, T** p, size_t count);
 template <typename T>
 static int host_alloc(agr_handle* h, T** p, size_t count) {
     void* q = nullptr;
@@ -152,6 +169,19 @@ static int host_alloc(agr_handle* h, T** p, size_t count) {
     if (e != cudaSuccess) return fail(AGR_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     h->host_allocs.push_back(q);
     *p = (T*)q;
+    return 0;
+}
+template <typename T>
+static int host_regrow(agr_handle* h, T** p, size_t count) {
+    T* old = *p;
+    int rc = host_alloc(h, p, count);
+    if (rc < 0) return rc;
+    if (old) {
+        cudaStreamSynchronize(h->stream);
+        auto it = std::find(h->host_allocs.begin(), h->host_allocs.end(), (void*)old);
+        if (it != h->host_allocs.end()) h->host_allocs.erase(it);
+        cudaFreeHost(old);
+    }
     return 0;
 }
 #define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
@@ -717,14 +747,14 @@ static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, i
 static int ensure_out(agr_handle* h, uint32_t cap) {
     if (cap <= h->out_cap) return 0;
     uint32_t ncap = std::max<uint32_t>(cap, 1024);
-    TRY(dev_alloc(h, &h->d_out_rid, ncap, false));
-    TRY(dev_alloc(h, &h->d_out_slot, ncap, false));
+    TRY(dev_regrow(h, &h->d_out_rid, ncap, false));
+    TRY(dev_regrow(h, &h->d_out_slot, ncap, false));
     h->out_cap = ncap;
     return 0;
 }
 static int ensure_gather(agr_handle* h, size_t bytes) {
-    if (bytes > h->gather_bytes) { TRY(dev_alloc(h, &h->d_gather, bytes, false)); h->gather_bytes = bytes; }
-    if (bytes > h->h_gather_bytes) { TRY(host_alloc(h, &h->h_gather, bytes)); h->h_gather_bytes = bytes; }
+    if (bytes > h->gather_bytes) { TRY(dev_regrow(h, &h->d_gather, bytes, false)); h->gather_bytes = bytes; }
+    if (bytes > h->h_gather_bytes) { TRY(host_regrow(h, &h->h_gather, bytes)); h->h_gather_bytes = bytes; }
     return 0;
 }
 
@@ -745,7 +775,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.per_warp = (uint32_t)per;
     p.nwarps = (uint32_t)((items + per - 1) / per);
     size_t need = (size_t)p.nwarps * p.groups;
-    if (need > h->matrix_entries) { TRY(dev_alloc(h, &h->d_matrix, need, false)); h->matrix_entries = need; }
+    if (need > h->matrix_entries) { TRY(dev_regrow(h, &h->d_matrix, need, false)); h->matrix_entries = need; }
     TRY(ensure_out(h, cap));
     p.matrix = h->d_matrix; p.gtotal = h->d_gtotal; p.goff = h->d_goff;
     p.out_rid = h->d_out_rid; p.out_slot = h->d_out_slot; p.cap = cap;
@@ -935,8 +965,8 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
 static int gather_var_locked(agr_handle* h, uint32_t total, uint8_t* blob, uint64_t blob_cap, uint64_t* offsets, uint64_t* blob_bytes) {
     if (total > h->lens_cap) {
         uint32_t ncap = std::max<uint32_t>(total, 1024);
-        TRY(dev_alloc(h, &h->d_lens, ncap, false));
-        TRY(dev_alloc(h, &h->d_goffs, (size_t)ncap + 1, false));
+        TRY(dev_regrow(h, &h->d_lens, ncap, false));
+        TRY(dev_regrow(h, &h->d_goffs, (size_t)ncap + 1, false));
         h->lens_cap = ncap;
     }
     agr_launch_var_lens(h->d, h->d_out_rid, total, h->d_lens, h->stream);
@@ -1095,9 +1125,9 @@ static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint32_t fi
     if (n == 0) return 0;
     if (n > h->j_cap) {
         const uint32_t cap = std::max<uint32_t>(n, 1024);
-        TRY(dev_alloc(h, &h->d_jlen, cap, false));
-        TRY(dev_alloc(h, &h->d_joff, (size_t)cap + 1, false));
-        TRY(dev_alloc(h, &h->d_jchunk, (size_t)agr_k5_chunks(cap) + 1, false));
+        TRY(dev_regrow(h, &h->d_jlen, cap, false));
+        TRY(dev_regrow(h, &h->d_joff, (size_t)cap + 1, false));
+        TRY(dev_regrow(h, &h->d_jchunk, (size_t)agr_k5_chunks(cap) + 1, false));
         h->j_cap = cap;
     }
     agr_k5_params p{};
@@ -1117,7 +1147,7 @@ static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint32_t fi
     CK(cudaStreamSynchronize(h->stream));
     if (tot + 16 > h->json_cap) {
         const uint64_t cap = std::max<uint64_t>(tot + tot / 4 + 16, 1 << 16);
-        TRY(dev_alloc(h, &h->d_json, (size_t)cap, false));
+        TRY(dev_regrow(h, &h->d_json, (size_t)cap, false));
         h->json_cap = cap;
     }
     p.out = h->d_json;
@@ -1708,7 +1738,7 @@ int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index,
     if (s->zipf_milli) {
         std::vector<unsigned long long> cdf;
         zipf_cdf(s->n_agents, s->zipf_milli, cdf);
-        if (h->cdf_n < s->n_agents) { TRY(dev_alloc(h, &h->d_cdf, s->n_agents, false)); h->cdf_n = s->n_agents; }
+        if (h->cdf_n < s->n_agents) { TRY(dev_regrow(h, &h->d_cdf, s->n_agents, false)); h->cdf_n = s->n_agents; }
         CK(cudaMemcpyAsync(h->d_cdf, cdf.data(), (size_t)s->n_agents * 8, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         dcdf = h->d_cdf;
