@@ -39,7 +39,7 @@ class AgrStats(C.Structure):
         "rows_used", "rows_cap", "ingested", "stored", "replay_flagged", "dedupe_hits", "forwarded", "queued",
         "unavailable", "not_found", "dup_ids", "completions", "completion_misses", "failures", "dead_lettered",
         "dial_errors", "replay_scans", "replay_dispatched", "completed_log_len", "failed_log_len",
-        "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
+        "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches", "rows_tail")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
 
 
 class AgrExchangeInfo(C.Structure):
@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
-    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire",
+    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim",
 ]
 
 _lib = None
@@ -137,6 +137,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_restore": (i32, [C.POINTER(AgrConfig), C.c_char_p, C.POINTER(vp)]),
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "agr_expire": (i32, [vp, u64, u64, C.POINTER(u64)]),
+        "agr_reclaim": (i32, [vp, C.POINTER(u64)]),
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
@@ -500,8 +501,10 @@ class Engine:
         _check(self.lib, self.lib.agr_pending_json(self.h, agent_id.encode(), _ptr(out), out.size, C.byref(ln), C.byref(cnt)))
         return out[: ln.value].tobytes(), int(cnt.value)
 
-    def rows_json(self, first_rid: int, n: int, as_array: bool = False, fetch: bool = True):
-        """Rows [first_rid, +n) in wire form.  fetch=False leaves the bytes on the device and returns only the length."""
+    def rows_json(self, first_rid: int, n: int, as_array: bool = False, fetch: bool = True, roundtrip: bool = False):
+        """Rows [first_rid, +n) in wire form.  fetch=False leaves the bytes on the device and returns only the length.
+        roundtrip: strings as they read after a json.Unmarshal (what GetPendingRequests hands on)."""
+        as_array = int(as_array) | (2 if roundtrip else 0)
         ln = C.c_uint64()
         _check(self.lib, self.lib.agr_rows_json(self.h, first_rid, n, int(as_array), None, 0, C.byref(ln), None))
         if not fetch:
@@ -528,6 +531,12 @@ class Engine:
         """Drop the records whose last SET is ttl or more before now (the reference's 24 h key TTL); returns how many."""
         n = C.c_uint64()
         _check(self.lib, self.lib.agr_expire(self.h, now, ttl, C.byref(n)))
+        return int(n.value)
+
+    def reclaim(self) -> int:
+        """AGR_CFG_RING: release the rows at the tail that hold no record any more; returns how many."""
+        n = C.c_uint64()
+        _check(self.lib, self.lib.agr_reclaim(self.h, C.byref(n)))
         return int(n.value)
 
     def verify(self) -> Tuple[int, int]:

@@ -42,6 +42,15 @@ __device__ __forceinline__ unsigned long long table_find(const agr_dev& d, unsig
     return ~0ULL;
 }
 
+// logical <-> physical row (see agr_dev)
+__device__ __forceinline__ unsigned long long row_logical(const agr_dev& d, uint32_t p) {
+    if (!d.ring_rows) return p;
+    return d.tail + (p >= d.tail_phys ? p - d.tail_phys : p + d.ring_rows - d.tail_phys);
+}
+__device__ __forceinline__ uint32_t row_physical(const agr_dev& d, unsigned long long l) {
+    return d.ring_rows ? (uint32_t)(l % d.ring_rows) : (uint32_t)l;
+}
+
 // address of a row's record: fixed 512 B stride, or the byte offset kept per row in variable-length mode
 __device__ __forceinline__ const uint8_t* rec_ptr(const agr_dev& d, uint32_t rid) {
     return d.voff ? d.slab + d.voff[rid] : d.slab + (size_t)rid * AGR_REC;
@@ -54,10 +63,10 @@ __device__ __forceinline__ uint32_t lookup_rid(const agr_dev& d, unsigned long l
     if (d.cfg_flags & AGR_CFG_MINT_IDS) {
         unsigned long long rid; uint32_t shard, gen;
         if (!agr_unmint_id(lo, d.id_secret, rid, shard, gen)) return AGR_RID_NONE;
-        if (rid >= d.rows_hi || shard != d.shard_id || gen != d.id_gen) return AGR_RID_NONE;
+        if (rid < d.tail || rid >= d.head_l || shard != d.shard_id || gen != d.id_gen) return AGR_RID_NONE;   // not a live row
         unsigned long long mlo, mhi;
         agr_mint_id(rid, shard, gen, d.id_secret, mlo, mhi);
-        return (mlo == lo && mhi == hi) ? (uint32_t)rid : AGR_RID_NONE;
+        return (mlo == lo && mhi == hi) ? row_physical(d, rid) : AGR_RID_NONE;
     }
     const unsigned long long idx = table_find(d, lo, hi);
     if (idx == ~0ULL) return AGR_RID_NONE;

@@ -53,7 +53,10 @@ struct agr_handle {
     uint8_t* d_ids = nullptr;                  // [max_batch][16] Request.ID per record (agr_ingest_ex)
     uint8_t* h_ids = nullptr;                  // pinned
     agr_dev d{};
-    uint64_t rows_used = 0;
+    uint64_t rows_used = 0;   // LOGICAL rows handed out so far (ring: includes the rows skipped at a wrap)
+    uint64_t tail = 0;        // ring: first logical row that has not been released
+    uint32_t* d_log_scratch = nullptr; uint32_t* d_lc_chunks = nullptr;   // ring: log compaction
+    uint64_t released_total = 0;
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
     // host agent map + mirror
     std::unordered_map<std::string, uint32_t> slot_of;
@@ -186,6 +189,18 @@ static int host_regrow(agr_handle* h, T** p, size_t count) {
 }
 #define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
 
+// ---- logical rows (arrival numbers, what the API speaks) vs physical rows (where the record lives; see agr_dev)
+static inline bool is_ring(const agr_handle* h) { return (h->cfg.flags & AGR_CFG_RING) != 0; }
+static inline uint64_t phys_row(const agr_handle* h, uint64_t l) { return is_ring(h) ? l % h->cfg.slab_rows : l; }
+static inline uint64_t rows_span(const agr_handle* h) {       // physical rows that have ever been handed out
+    return is_ring(h) ? std::min<uint64_t>(h->rows_used, h->cfg.slab_rows) : h->rows_used;
+}
+static inline void sync_window(agr_handle* h) {               // the live window the kernels check decoded ids against
+    h->d.tail = h->tail; h->d.head_l = h->rows_used;
+    h->d.ring_rows = is_ring(h) ? (uint32_t)h->cfg.slab_rows : 0u;
+    h->d.tail_phys = is_ring(h) ? (uint32_t)(h->tail % h->cfg.slab_rows) : 0u;
+}
+
 struct nccl_api {
     void* lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -255,6 +270,11 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (c.max_agents == 0) c.max_agents = 4096;
     if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
     if (c.max_batch == 0) c.max_batch = 1u << 20;
+    if (c.flags & AGR_CFG_RING) {
+        if (!mint || (c.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "AGR_CFG_RING needs AGR_CFG_MINT_IDS and fixed-stride records");
+        if (c.max_batch > c.slab_rows / 2) c.max_batch = (uint32_t)(c.slab_rows / 2);
+        if (c.max_batch == 0) return fail(AGR_EINVAL, "AGR_CFG_RING: slab_rows too small");
+    }
     if (c.log_entries == 0) c.log_entries = c.slab_rows * 2;
     if ((c.k1_variant & 0xfu) == 0) c.k1_variant |= 4u;      // default K1 shape: TMA, 14 warps x 1 stage, fused index
     int ndev = 0;
@@ -303,6 +323,10 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
     TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
+    if (c.flags & AGR_CFG_RING) {
+        TRY(dev_alloc(h, &h->d_log_scratch, c.log_entries, false));
+        TRY(dev_alloc(h, &h->d_lc_chunks, (size_t)(c.log_entries / 1024 + 4), false));
+    }
     if (c.resp_bytes == 0) c.resp_bytes = 64ull * c.slab_rows;
     h->cfg.resp_bytes = c.resp_bytes; h->resp_cap = c.resp_bytes;
     TRY(dev_alloc(h, &h->d_resp, (size_t)c.resp_bytes, false));
@@ -315,7 +339,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.mtime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
     d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
-    d.shard_id = 0; d.id_gen = 1; d.rows_hi = 0;
+    d.shard_id = 0; d.id_gen = 1; d.tail = 0; d.head_l = 0; d.ring_rows = 0; d.tail_phys = 0;
     if (!varlen && (c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags & 0xffffu;
@@ -454,7 +478,7 @@ int agr_drop_agent(agr_handle* h, const char* agent_id) {
     unsigned long long lens[2];
     CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    agr_launch_drop_agent(h->d, (uint32_t)slot, h->rows_used, std::max(lens[0], lens[1]), h->stream);
+    agr_launch_drop_agent(h->d, (uint32_t)slot, rows_span(h), std::max(lens[0], lens[1]), h->stream);
     h->k3_launches += 2;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -463,14 +487,28 @@ int agr_drop_agent(agr_handle* h, const char* agent_id) {
 
 // ------------------------------------------------------------------------------------------ K1
 static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
-    if (h->rows_used + n > h->cfg.slab_rows) return fail(AGR_ENOSPC, "slab full");
+    if (!is_ring(h)) {
+        if (h->rows_used + n > h->cfg.slab_rows) return fail(AGR_ENOSPC, "slab full");
+        *first = h->rows_used;
+        h->rows_used += n;
+        sync_window(h);
+        return 0;
+    }
+    // ring: a batch never wraps — if it does not fit before the end of the slab, the rows up to the end are skipped
+    // (they stay "no record": released rows are zeroed), at most max_batch rows per lap
+    const uint64_t R = h->cfg.slab_rows;
+    const uint64_t at = h->rows_used % R;
+    const uint64_t pad = (at + n > R) ? R - at : 0;
+    if (h->rows_used + pad + n - h->tail > R) return fail(AGR_ENOSPC, "slab full: agr_expire + agr_reclaim release rows at the tail");
+    h->rows_used += pad;
     *first = h->rows_used;
     h->rows_used += n;
+    sync_window(h);
     return 0;
 }
 
 static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out, uint8_t* d_ids = nullptr) {
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
         if (h->tev.empty()) {
@@ -480,7 +518,7 @@ static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdi
         const uint64_t k = h->tev_next++ % AGR_TIMING_RING;
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
     }
-    agr_launch_k1(h->d, (uint32_t)first, n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr,
+    agr_launch_k1(h->d, (uint32_t)phys_row(h, first), n, h->cfg.k1_variant, (h->cfg.k1_variant & 0xfu) != AGR_K1_LSU ? h->tmap : nullptr,
                   h->sm_count, h->stream, e0, e1, d_out, d_ids);
     h->k1_launches += agr_k1_launches_per_batch(h->cfg.k1_variant);
     CK(cudaGetLastError());
@@ -537,7 +575,10 @@ int agr_sync(agr_handle* h) {
     return 0;
 }
 void* agr_stream(agr_handle* h) { return h ? (void*)h->stream : nullptr; }
-void* agr_slab_ptr(agr_handle* h, uint64_t rid) { return (h && rid < h->cfg.slab_rows) ? (void*)(h->d.slab + rid * AGR_REC) : nullptr; }
+void* agr_slab_ptr(agr_handle* h, uint64_t rid) {
+    if (!h || rid >= h->rows_used || rid < h->tail) return nullptr;
+    return (void*)(h->d.slab + phys_row(h, rid) * AGR_REC);
+}
 
 // host -> slab rows -> K1 -> verdicts, pipelined in chunks: the H2D copy of chunk k+1 (copy stream) overlaps K1 and the
 // verdict D2H of chunk k (compute stream).  Chunks are consecutive sub-batches in arrival order, so the result is
@@ -630,7 +671,7 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
     int bk = 0;
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint32_t off = c * AGR_INGEST_CHUNK, cn = std::min(AGR_INGEST_CHUNK, n - off);
-        uint8_t* dst = h->d.slab + (first + off) * AGR_REC;
+        uint8_t* dst = h->d.slab + (phys_row(h, first) + off) * AGR_REC;
         const uint8_t* src = (const uint8_t*)(recs + off);
         size_t bytes = (size_t)cn * AGR_REC;
         if (src_pinned) {
@@ -722,7 +763,7 @@ static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, i
         memcpy(h->h_outs, outs, (size_t)n * sizeof(agr_outcome));
         CK(cudaMemcpyAsync(h->d_outs, h->h_outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
     }
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     const bool timing = (h->cfg.flags & AGR_CFG_TIMING) != 0;
     if (timing) {
         for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
@@ -796,7 +837,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     *total = h->h_small[0];
     if (mode == K3_TICK) {
         uint32_t m = h->h_small[1];
-        h->scan_lo = (m == AGR_RID_NONE) ? hi : std::max<uint64_t>(h->scan_lo, m);
+        h->scan_lo = (m == AGR_RID_NONE) ? hi : std::max<uint64_t>(h->scan_lo, lo + m);
     }
     return 0;
 }
@@ -862,7 +903,7 @@ int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16],
     uint32_t total = 0;
     if (which == AGR_LIST_PENDING) {
         // LRANGE: ids of expired records are still in the list; they lie below the scan's low-water mark
-        TRY(select_locked(h, K3_AGENT_PENDING_IDS, (uint32_t)slot, nullptr, h->expired_total ? 0 : h->scan_lo, h->rows_used, cap, &total));
+        TRY(select_locked(h, K3_AGENT_PENDING_IDS, (uint32_t)slot, nullptr, h->expired_total ? h->tail : h->scan_lo, h->rows_used, cap, &total));
     } else {
         unsigned long long lens[2];
         CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
@@ -896,7 +937,7 @@ int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id
     memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     agr_launch_resolve(h->d, h->k2, 1, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
@@ -939,7 +980,7 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
     CK(cudaMemcpyAsync(h->d.slab + base, blob, bytes, cudaMemcpyHostToDevice, st));
     if (is_pinned(offsets)) CK(cudaMemcpyAsync(h->d_voffsets, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
     else { memcpy(h->h_voffsets, offsets, ((size_t)n + 1) * 4); CK(cudaMemcpyAsync(h->d_voffsets, h->h_voffsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st)); }
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     CK(cudaMemsetAsync(h->d.dupfix, 0, 8, st));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
@@ -1028,7 +1069,7 @@ int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t reques
     memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     agr_launch_resolve(h->d, h->k2, 1, h->stream);
     CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1053,7 +1094,7 @@ static int resolve_one_locked(agr_handle* h, const char* agent_id, const uint8_t
     memcpy(&op.id_lo, request_id, 8); memcpy(&op.id_hi, request_id + 8, 8);
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
-    h->d.rows_hi = (uint32_t)h->rows_used;
+    sync_window(h);
     agr_launch_resolve(h->d, h->k2, 1, h->stream);
     h->k3_launches += 1;
     CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1120,7 +1161,7 @@ int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t req
 
 // ------------------------------------------------------------------------------------------ K5: JSON wire form
 // Encodes n records (rows d_rids[0..n) or first_rid + [0..n)) into h->d_json; *total = bytes.  Offsets stay in h->d_joff.
-static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint32_t first_rid, uint32_t n, bool array, uint64_t* total) {
+static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint64_t first_rid, uint32_t n, bool array, uint64_t* total, bool roundtrip = false) {
     *total = 0;
     if (n == 0) return 0;
     if (n > h->j_cap) {
@@ -1131,7 +1172,8 @@ static int json_encode_locked(agr_handle* h, const uint32_t* d_rids, uint32_t fi
         h->j_cap = cap;
     }
     agr_k5_params p{};
-    p.rids = d_rids; p.first_rid = first_rid; p.n = n; p.array = array ? 1u : 0u;
+    p.rids = d_rids; p.first_l = first_rid; p.n = n; p.array = array ? 1u : 0u; p.roundtrip = roundtrip ? 1u : 0u;
+    sync_window(h);
     p.len = h->d_jlen; p.off = h->d_joff; p.chunk_sum = h->d_jchunk; p.out = nullptr;
     p.bytes = h->d_resp; p.resp_off = h->d_resp_off; p.resp_len = h->d_resp_len; p.resp_hlen = h->d_resp_hlen;
     p.err_off = h->d_err_off; p.err_len = h->d_err_len; p.ptime = h->d.ptime;
@@ -1171,10 +1213,10 @@ int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, u
     if (!h || !len) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
-    if (first_rid + n > h->rows_used) return fail(AGR_EINVAL, "row range beyond the rows in use");
+    if (first_rid + n > h->rows_used || first_rid < h->tail) return fail(AGR_EINVAL, "row range outside the rows in use");
     uint64_t total = 0;
-    TRY(json_encode_locked(h, nullptr, (uint32_t)first_rid, n, as_array != 0, &total));
-    if (n == 0 && as_array) {                                    // json.Marshal of a nil slice
+    TRY(json_encode_locked(h, nullptr, first_rid, n, (as_array & 1) != 0, &total, (as_array & 2) != 0));
+    if (n == 0 && (as_array & 1)) {                              // json.Marshal of a nil slice
         *len = 4;
         if (out) { if (cap < 4) return fail(AGR_ECAP, "output buffer too small"); memcpy(out, "null", 4); }
         if (offsets) offsets[0] = 0;
@@ -1205,7 +1247,7 @@ int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t
         return 0;
     }
     uint64_t total = 0;
-    TRY(json_encode_locked(h, h->d_out_rid, 0, total_rows, true, &total));
+    TRY(json_encode_locked(h, h->d_out_rid, 0, total_rows, true, &total, true));   // GetPendingRequests unmarshals every record
     return json_copy_out(h, total, out, cap, len);
 }
 
@@ -1216,7 +1258,7 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
     uint32_t rid = 0;
     TRY(resolve_one_locked(h, agent_id, request_id, &rid));
     uint64_t total = 0, l = 0;
-    TRY(json_encode_locked(h, nullptr, rid, 1, false, &total));
+    TRY(json_encode_locked(h, h->k2.hrid, 0, 1, false, &total));   // k2.hrid[0] = the physical row resolve_one_locked found
     int rc = json_copy_out(h, total, out, cap, &l);
     *len = (uint32_t)l;
     return rc;
@@ -1224,9 +1266,9 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 
 // ------------------------------------------------------------------------------------------ durability
 struct snap_header {
-    char magic[8];                 // "AGRSNAP2"
+    char magic[8];                 // "AGRSNAP3"
     uint32_t flags, n_agents, shard, gen;
-    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total, tail, released_total, slab_rows;
 };
 static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
     const size_t chunk = h->bounce_bytes;
@@ -1257,11 +1299,11 @@ int agr_snapshot(agr_handle* h, const char* path) {
     FILE* f = fopen(path, "wb");
     if (!f) return fail(AGR_EINVAL, std::string("snapshot: cannot open ") + path);
     snap_header hd{};
-    memcpy(hd.magic, "AGRSNAP2", 8);
-    hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN);
+    memcpy(hd.magic, "AGRSNAP3", 8);
+    hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN | AGR_CFG_RING);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
-    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total;
+    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total; hd.tail = h->tail; hd.released_total = h->released_total; hd.slab_rows = h->cfg.slab_rows;
     unsigned long long lens[2];
     int rc = 0;
     auto done = [&](int r) { fclose(f); return r; };
@@ -1273,7 +1315,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
         strncpy(name, h->agent_names[a].c_str(), AGR_AGENT_ID_BYTES - 1);
         fwrite(name, 1, AGR_AGENT_ID_BYTES, f); fwrite(&h->agent_status[a], 1, 1, f);
     }
-    const size_t R = hd.rows_used;
+    const size_t R = (size_t)rows_span(h);
     const size_t slab_bytes = (h->cfg.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
     if ((rc = dump_dev(h, f, h->d.slab, slab_bytes)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.state, R * 4)) < 0) return done(rc);
@@ -1303,10 +1345,10 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     FILE* f = fopen(path, "rb");
     if (!f) return fail(AGR_EINVAL, std::string("restore: cannot open ") + path);
     snap_header hd{};
-    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "AGRSNAP2", 8) != 0) { fclose(f); return fail(AGR_EINVAL, "restore: not a snapshot"); }
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "AGRSNAP3", 8) != 0) { fclose(f); return fail(AGR_EINVAL, "restore: not a snapshot"); }
     agr_config c = *cfg;
     if (c.flags == 0) c.flags = AGR_CFG_PERSISTENCE;
-    const uint32_t mode_bits = AGR_CFG_MINT_IDS | AGR_CFG_VARLEN;
+    const uint32_t mode_bits = AGR_CFG_MINT_IDS | AGR_CFG_VARLEN | AGR_CFG_RING;
     if ((c.flags & mode_bits) != (hd.flags & mode_bits)) { fclose(f); return fail(AGR_EINVAL, "restore: id mode / record form differ from the snapshot"); }
     if (c.id_secret == 0) c.id_secret = hd.id_secret;
     if (c.id_secret != hd.id_secret) { fclose(f); return fail(AGR_EINVAL, "restore: id_secret differs from the snapshot"); }
@@ -1315,7 +1357,9 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if (rc < 0) { fclose(f); return rc; }
     auto bail = [&](int r) { std::string keep = g_err; fclose(f); agr_destroy(h); g_err = keep; return r; };
     if (hd.resp_used > h->resp_cap) return bail(fail(AGR_ENOSPC, "restore: stored responses larger than resp_bytes"));
-    if (hd.rows_used > h->cfg.slab_rows || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && hd.vused > h->vcap))
+    const bool snap_ring = (hd.flags & AGR_CFG_RING) != 0;
+    if (snap_ring && hd.slab_rows != h->cfg.slab_rows) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same slab_rows (rows live at logical mod slab_rows)"));
+    if ((!snap_ring && hd.rows_used > h->cfg.slab_rows) || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && hd.vused > h->vcap))
         return bail(fail(AGR_ENOSPC, "restore: snapshot larger than the configured capacities"));
     for (uint32_t a = 0; a < hd.n_agents; ++a) {
         char name[AGR_AGENT_ID_BYTES]; uint8_t st;
@@ -1326,7 +1370,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
         if (removed) { std::lock_guard<std::mutex> lk(h->mu); h->agent_status[a] = AG_STATUS_REMOVED; if ((rc = push_agent_status(h, a, AG_STATUS_REMOVED)) < 0) return bail(rc); }
     }
     std::lock_guard<std::mutex> lk(h->mu);
-    const size_t R = hd.rows_used;
+    const size_t R = snap_ring ? (size_t)std::min<uint64_t>(hd.rows_used, hd.slab_rows) : (size_t)hd.rows_used;
     const size_t slab_bytes = (hd.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
     if ((rc = load_dev(h, f, h->d.slab, slab_bytes)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.state, R * 4)) < 0) return bail(rc);
@@ -1351,7 +1395,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->scan_lo = hd.scan_lo;
-    h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->d.rows_hi = (uint32_t)hd.rows_used;
+    h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->tail = hd.tail; h->released_total = hd.released_total; sync_window(h);
     if (!(hd.flags & AGR_CFG_MINT_IDS) && R) {        // hash-id mode: rebuild the dedupe index from the restored rows
         agr_launch_reindex(h->d, (uint32_t)R, h->stream);
         h->k1_launches += 1;
@@ -1368,7 +1412,8 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     CK(cudaSetDevice(h->device));
     unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
-    agr_launch_expire(h->d, h->rows_used, now, ttl, d_cnt, h->stream);
+    sync_window(h);
+    agr_launch_expire(h->d, rows_span(h), now, ttl, d_cnt, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
     unsigned long long v = 0;
@@ -1379,20 +1424,65 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     return 0;
 }
 
+// AGR_CFG_RING: hand the rows at the tail that hold no record any more (expired or never stored) back to the ring, up to
+// the first row that still does, and drop their entries from the completed / failed logs.
+int agr_reclaim(agr_handle* h, uint64_t* released) {
+    if (!h) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (released) *released = 0;
+    if (!is_ring(h)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_RING");
+    sync_window(h);
+    if (h->rows_used == h->tail) return 0;
+    uint32_t* d_off = h->d_min_inq;                                            // 4-byte scratch
+    CK(cudaMemsetAsync(d_off, 0xff, 4, h->stream));
+    agr_launch_first_live(h->d, d_off, h->stream);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_small, d_off, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t count = (h->h_small[0] == 0xffffffffu) ? h->rows_used - h->tail : h->h_small[0];
+    h->k3_launches += 1;
+    if (count == 0) return 0;
+    agr_launch_release_rows(h->d, (uint32_t)count, h->d_resp_len, h->d_resp_hlen, h->d_err_len, h->stream);
+    unsigned long long lens[2];
+    CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 2; ++k) {                                              // completed, failed
+        uint32_t*& log = k == 0 ? h->d.completed_log : h->d.failed_log;
+        agr_launch_log_compact(h->d, log, lens[k], (uint32_t)count, h->d_log_scratch, h->d_lc_chunks, h->stream);
+        CK(cudaGetLastError());
+        const uint32_t nch = (uint32_t)((lens[k] + 1023) / 1024);
+        CK(cudaMemcpyAsync(h->h_small, h->d_lc_chunks + nch, 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        lens[k] = lens[k] ? h->h_small[0] : 0;
+        std::swap(log, h->d_log_scratch);                                      // the compacted copy becomes the log
+    }
+    CK(cudaMemcpyAsync(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->k3_launches += 8;
+    h->tail += count;
+    h->released_total += count;
+    if (h->scan_lo < h->tail) h->scan_lo = h->tail;
+    sync_window(h);
+    if (released) *released = count;
+    return 0;
+}
+
 int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad) {
     if (!h || !bad) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     unsigned long long* d_bad = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_bad, 0, 8, h->stream));
-    agr_launch_verify(h->d, h->rows_used, d_bad, h->stream);
+    sync_window(h);
+    agr_launch_verify(h->d, rows_span(h), d_bad, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
     unsigned long long v = 0;
     CK(cudaMemcpyAsync(&v, d_bad, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *bad = v;
-    if (rows_checked) *rows_checked = h->rows_used;
+    if (rows_checked) *rows_checked = rows_span(h);
     return 0;
 }
 
@@ -1415,7 +1505,7 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->replay_scans = h->replay_scans; out->replay_dispatched = h->replay_dispatched;
     out->completed_log_len = lens[0]; out->failed_log_len = lens[1];
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
-    out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches; out->k5_launches = h->k5_launches;
+    out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches; out->k5_launches = h->k5_launches; out->rows_tail = h->tail;
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
     return 0;
 }
@@ -1563,10 +1653,10 @@ int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_ve
     uint64_t first = 0;
     TRY(reserve_rows_locked(h, total, &first));
     // stable pack: own records straight into their slab rows, peer segments into the send buffer
-    x.p.local_dst = h->d.slab + first * AGR_REC; x.p.send_dst = h->d_send;
+    x.p.local_dst = h->d.slab + phys_row(h, first) * AGR_REC; x.p.send_dst = h->d_send;
     if (n) { agr_launch_k4_scatter(x.p, h->stream); h->k4_launches += 1; CK(cudaGetLastError()); }
     // the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
-    TRY(exchange_payload(h, x, h->d_send, h->d.slab + (first + x.n_local) * AGR_REC, AGR_REC));
+    TRY(exchange_payload(h, x, h->d_send, h->d.slab + (phys_row(h, first) + x.n_local) * AGR_REC, AGR_REC));
     // K1 at the owner over local + received rows (received rows were unpacked by the receive itself)
     if (total) TRY(launch_k1_locked(h, first, total, h->d_xverd));
     // verdicts back to where the records came from, restored to the caller's order
@@ -1591,7 +1681,7 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
     TRY(exchange_payload(h, x, h->d_send, (uint8_t*)(h->d_outs + x.n_local), sizeof(agr_outcome)));
     // K2 at the owner over local + received outcomes (own host first, then peers by rank)
     if (total) {
-        h->d.rows_hi = (uint32_t)h->rows_used;
+        sync_window(h);
         agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, h->stream);
         agr_launch_k2(h->d, h->k2, total, h->stream);
         h->k2_launches += 7;
@@ -1609,16 +1699,20 @@ int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, voi
     if (!h || (n && !out)) return fail(AGR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
-    if (first_rid + n > h->cfg.slab_rows) return fail(AGR_EINVAL, "row range out of bounds");
-    const void* src = nullptr; size_t w = 4;
+    if (!is_ring(h) && first_rid + n > h->cfg.slab_rows) return fail(AGR_EINVAL, "row range out of bounds");
+    if (is_ring(h) && (first_rid + n > h->rows_used || n > h->cfg.slab_rows)) return fail(AGR_EINVAL, "row range out of bounds");
+    const uint8_t* base = nullptr; size_t w = 4;
     switch (which) {
-        case AGR_DBG_STATE: src = h->d.state + first_rid; break;
-        case AGR_DBG_ROUTE: src = h->d.route + first_rid; break;
-        case AGR_DBG_AUX: src = h->d.aux + first_rid; break;
-        case AGR_DBG_CKSUM: src = h->d.cksum + first_rid; w = 8; break;
+        case AGR_DBG_STATE: base = (const uint8_t*)h->d.state; break;
+        case AGR_DBG_ROUTE: base = (const uint8_t*)h->d.route; break;
+        case AGR_DBG_AUX: base = (const uint8_t*)h->d.aux; break;
+        case AGR_DBG_CKSUM: base = (const uint8_t*)h->d.cksum; w = 8; break;
         default: return fail(AGR_EINVAL, "bad array selector");
     }
-    CK(cudaMemcpyAsync(out, src, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream));
+    const uint64_t p0 = phys_row(h, first_rid);
+    const uint64_t n0 = is_ring(h) ? std::min<uint64_t>(n, h->cfg.slab_rows - p0) : n;          // a logical range may wrap once
+    if (n0) CK(cudaMemcpyAsync(out, base + p0 * w, (size_t)n0 * w, cudaMemcpyDeviceToHost, h->stream));
+    if (n > n0) CK(cudaMemcpyAsync((uint8_t*)out + n0 * w, base, (size_t)(n - n0) * w, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1743,7 +1837,7 @@ int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index,
         CK(cudaStreamSynchronize(h->stream));
         dcdf = h->d_cdf;
     }
-    agr_launch_synth(h->d.slab + first_rid * AGR_REC, synth_params(s, dcdf), first_index, n, h->stream);
+    agr_launch_synth(h->d.slab + phys_row(h, first_rid) * AGR_REC, synth_params(s, dcdf), first_index, n, h->stream);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -372,9 +372,9 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
     const uint32_t aux = d.aux[rid];
     const bool responded = (st & ST_RESPONDED) != 0u;
     const uint32_t retry = st_retry(st);
-    const bool touched = responded || retry != 0u;
+    const bool touched = responded || retry != 0u || p.roundtrip != 0u;
     unsigned long long lo, hi;
-    if (d.cfg_flags & AGR_CFG_MINT_IDS) agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+    if (d.cfg_flags & AGR_CFG_MINT_IDS) agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
     else { lo = *reinterpret_cast<const unsigned long long*>(rec); hi = *reinterpret_cast<const unsigned long long*>(rec + 8); }
     const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(rec + AGR_OFF_SEQ);
     const uint32_t flags = *reinterpret_cast<const uint32_t*>(rec + AGR_OFF_FLAGS);
@@ -430,7 +430,7 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
         w.check();
         const uint32_t rl = p.resp_len[rid], rh = min(p.resp_hlen[rid], rl);
         const uint8_t* rb = p.bytes + p.resp_off[rid];
-        put_headers(w, rb, rh, (st & ST_RESP_RT) != 0u);
+        put_headers(w, rb, rh, (st & ST_RESP_RT) != 0u || p.roundtrip != 0u);
         JLIT(w, ",\"body\":\"");
         put_base64(w, rb + rh, rl - rh);
         JLIT(w, "\",\"received_at\":\"");
@@ -441,7 +441,7 @@ __device__ __forceinline__ void encode_record(jwriter<EMIT>& w, const agr_dev& d
     if (retry != 0u) {                                       // requests.go:244 request.Error = err.Error()
         JLIT(w, ",\"error\":\"");
         const uint32_t el = p.err_len[rid];
-        if (el) put_escaped(w, p.bytes + p.err_off[rid], el, (st & ST_ERR_RT) != 0u);
+        if (el) put_escaped(w, p.bytes + p.err_off[rid], el, (st & ST_ERR_RT) != 0u || p.roundtrip != 0u);
         else JLIT(w, "transport error");
         w.ch('"');
     }
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(K5_WARPS * 32, EMIT ? 3 : 6) k5_json(const agr
         const uint32_t r = k * K5_WARPS + warp;              // neighbouring warps write neighbouring output
         if (r >= in_chunk) break;
         const uint32_t i = chunk0 + r;
-        const uint32_t rid = p.rids ? p.rids[i] : p.first_rid + i;
+        const uint32_t rid = p.rids ? p.rids[i] : row_physical(d, p.first_l + i);
         const uint8_t* src = rec_ptr(d, rid);
         const uint8_t* rec = src;
         if (!d.voff) {                                       // fixed 512 B rows: stage the record in shared memory

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
         if (ids) {        // Request.ID as the engine knows it
             if (d.cfg_flags & AGR_CFG_MINT_IDS) {
                 unsigned long long lo, hi;
-                agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+                agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
                 ids[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
             } else {
                 ids[i] = ldg_nc_v4(rec_ptr(d, rid));
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) k_verify(const agr_dev d, const unsigned 
     const int lane = threadIdx.x & 31;
     if (w >= rows) return;
     const uint32_t rid = (uint32_t)w;
+    if (d.ring_rows && !(d.state[rid] & ST_STORED)) return;    // ring: released / skipped rows hold no record
     const uint8_t* src = rec_ptr(d, rid);
     const uint32_t chunks = d.voff ? (d.vlen[rid] >> 4) : 32u;
     uint32_t c0 = 0, c1 = 0;
@@ -249,6 +250,102 @@ void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long 
                        unsigned long long* expired, cudaStream_t st) {
     if (rows) k_expire<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, rows, now, ttl, expired);
 }
+// ---- ring mode (AGR_CFG_RING): releasing rows at the tail
+// offset (from the tail) of the first row that still holds a stored record
+__global__ void __launch_bounds__(256) k_first_live(const agr_dev d, uint32_t* __restrict__ out_off) {
+    const unsigned long long live = d.head_l - d.tail;
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mine = 0xffffffffu;
+    if (k < live && (d.state[row_physical(d, d.tail + k)] & ST_STORED)) mine = (uint32_t)k;
+    mine = __reduce_min_sync(FULL, mine);
+    if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
+}
+void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st) {
+    const unsigned long long live = d.head_l - d.tail;
+    if (live) k_first_live<<<(unsigned)((live + 255) / 256), 256, 0, st>>>(d, out_off);
+}
+// rows tail .. tail + count go back to the pool: every per-row word reads "no record"
+__global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uint32_t count, uint32_t* __restrict__ resp_len,
+                                                      uint32_t* __restrict__ resp_hlen, uint32_t* __restrict__ err_len) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t p = row_physical(d, d.tail + k);
+    d.state[p] = 0; d.route[p] = 0; d.aux[p] = 0; d.head[p] = 0; d.ptime[p] = 0; d.mtime[p] = 0;
+    resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;
+}
+void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
+    if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
+}
+// stable compaction of a log: entries whose row is among the `released` rows at the tail drop out
+#define LC_CHUNK 1024u
+__device__ __forceinline__ bool log_keep(const agr_dev& d, uint32_t p, uint32_t released) {
+    if (p == AGR_RID_NONE) return false;
+    const uint32_t off = p >= d.tail_phys ? p - d.tail_phys : p + d.ring_rows - d.tail_phys;   // distance from the tail
+    return off >= released;
+}
+__global__ void __launch_bounds__(256) k_log_count(const agr_dev d, const uint32_t* __restrict__ log, const unsigned long long len,
+                                                   const uint32_t released, uint32_t* __restrict__ chunk_cnt) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const unsigned long long base = (unsigned long long)blockIdx.x * LC_CHUNK;
+    uint32_t c = 0;
+    for (uint32_t j = threadIdx.x; j < LC_CHUNK; j += 256) {
+        const unsigned long long i = base + j;
+        if (i < len && log_keep(d, log[i], released)) c++;
+    }
+    c = __reduce_add_sync(FULL, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_cnt[blockIdx.x] = s_cnt;
+}
+__global__ void __launch_bounds__(1024) k_log_scan(uint32_t* chunk_cnt, const uint32_t nchunks) {     // exclusive, total at [nchunks]
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nchunks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nchunks ? chunk_cnt[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        uint32_t pre = s_carry;
+        for (int k = 0; k < warp; ++k) pre += s_w[k];
+        if (i < nchunks) chunk_cnt[i] = pre + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pre + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_cnt[nchunks] = s_carry;
+}
+// one warp per chunk keeps the order: 32 entries per step, ballot + popc
+__global__ void __launch_bounds__(32) k_log_scatter(const agr_dev d, const uint32_t* __restrict__ log, const unsigned long long len,
+                                                    const uint32_t released, const uint32_t* __restrict__ chunk_off, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x;
+    const unsigned long long base = (unsigned long long)blockIdx.x * LC_CHUNK;
+    uint32_t pos = chunk_off[blockIdx.x];
+    for (uint32_t j = 0; j < LC_CHUNK; j += 32) {
+        const unsigned long long i = base + j + lane;
+        const uint32_t v = i < len ? log[i] : AGR_RID_NONE;
+        const bool keep = i < len && log_keep(d, v, released);
+        const uint32_t m = __ballot_sync(FULL, keep);
+        if (keep) out[pos + __popc(m & ((1u << lane) - 1u))] = v;
+        pos += __popc(m);
+    }
+}
+void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long long len, uint32_t released, uint32_t* out,
+                            uint32_t* chunk_cnt, cudaStream_t st) {
+    if (!len) { cudaMemsetAsync(chunk_cnt, 0, 4, st); return; }
+    const uint32_t nch = (uint32_t)((len + LC_CHUNK - 1) / LC_CHUNK);
+    k_log_count<<<nch, 256, 0, st>>>(d, log, len, released, chunk_cnt);
+    k_log_scan<<<1, 1024, 0, st>>>(chunk_cnt, nch);
+    k_log_scatter<<<nch, 32, 0, st>>>(d, log, len, released, chunk_cnt, out);
+}
+
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st) {
     if (rows) k_verify<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(d, rows, bad);
 }
@@ -522,7 +619,8 @@ void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaSt
 struct k3_item { bool sel; uint32_t rid; uint32_t slot; bool inq; };
 
 // `st` = the row's state word (row modes; prefetched by the caller) — unused in log mode
-__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it, uint32_t st, uint32_t rt) {
+// `prow` = the physical row of item `it` (row modes)
+__device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params& p, unsigned long long it, uint32_t prow, uint32_t st, uint32_t rt) {
     k3_item o{false, AGR_RID_NONE, RT_SLOT_NONE, false};
     if (it >= p.hi) return o;
     if (p.mode == K3_LOG_AGENT) {
@@ -532,7 +630,7 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
         o.sel = (o.slot == p.slot);
         return o;
     }
-    const uint32_t rid = (uint32_t)it;
+    const uint32_t rid = prow;
     if (!(st & ST_INQ)) return o;                       // not in agent:{a}:requests:pending
     o.rid = rid; o.slot = rt_slot(rt);
     if (p.mode == K3_AGENT_PENDING_IDS) { o.sel = (o.slot == p.slot); return o; }   // LRANGE pending 0 -1
@@ -569,16 +667,25 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     if (e > p.hi) e = p.hi;
     uint32_t mininq = AGR_RID_NONE;
     const bool rows = (p.mode != K3_LOG_AGENT);
-    uint32_t st_next = (rows && b + lane < e) ? d.state[b + lane] : 0u;
-    uint32_t rt_next = (rows && b + lane < e) ? d.route[b + lane] : 0u;
+    // physical row of item k: the warp's run is contiguous in the ring and wraps at most once
+    const uint32_t pb = rows ? row_physical(d, b) : 0u;
+    auto prow_of = [&](unsigned long long k) -> uint32_t {
+        uint32_t q = pb + (uint32_t)(k - b);
+        if (d.ring_rows && q >= d.ring_rows) q -= d.ring_rows;
+        return q;
+    };
+    uint32_t pr_next = prow_of(b + lane);
+    uint32_t st_next = (rows && b + lane < e) ? d.state[pr_next] : 0u;
+    uint32_t rt_next = (rows && b + lane < e) ? d.route[pr_next] : 0u;
     for (unsigned long long k0 = b; k0 < e; k0 += 32) {
-        const uint32_t st = st_next, rt = rt_next;
+        const uint32_t st = st_next, rt = rt_next, pr = pr_next;
         const bool more = rows && k0 + 32 + lane < e;                                // next step's words are in flight
-        st_next = more ? d.state[k0 + 32 + lane] : 0u;
-        rt_next = more ? d.route[k0 + 32 + lane] : 0u;
+        pr_next = prow_of(k0 + 32 + lane);
+        st_next = more ? d.state[pr_next] : 0u;
+        rt_next = more ? d.route[pr_next] : 0u;
         if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;                // nothing pending in these 32 rows
-        k3_item it = k3_eval(d, p, k0 + lane, st, rt);
-        if (it.inq && it.rid < mininq) mininq = it.rid;
+        k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
+        if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
         const uint32_t g = (p.groups == 1) ? 0u : it.slot;
         const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
         const uint32_t peers = __match_any_sync(FULL, key);
@@ -698,7 +805,7 @@ __global__ void __launch_bounds__(256) k3_gather(const agr_dev d, const uint32_t
     uint4 v = ldg_nc_v4(src + lane * 16);
     if (lane == 0 && (d.cfg_flags & AGR_CFG_MINT_IDS)) {          // Request.ID = what the engine minted for this row
         unsigned long long lo, hi;
-        agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+        agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
         v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
     }
     if (out_recs) {
@@ -713,7 +820,8 @@ __global__ void __launch_bounds__(256) k3_gather(const agr_dev d, const uint32_t
     id.x = __shfl_sync(FULL, v.x, 0); id.y = __shfl_sync(FULL, v.y, 0);
     id.z = __shfl_sync(FULL, v.z, 0); id.w = __shfl_sync(FULL, v.w, 0);
     if (out_dispatch && lane == 0) {
-        uint4 head = make_uint4(rid, 0u, slots ? slots[w] : rt_slot(d.route[rid]), 0u);
+        const unsigned long long lrow = row_logical(d, rid);                  // agr_dispatch.rid: the row id the API speaks
+        uint4 head = make_uint4((uint32_t)lrow, (uint32_t)(lrow >> 32), slots ? slots[w] : rt_slot(d.route[rid]), 0u);
         *reinterpret_cast<uint4*>(out_dispatch + (size_t)w * 32) = head;
         *reinterpret_cast<uint4*>(out_dispatch + (size_t)w * 32 + 16) = id;
     }

@@ -36,7 +36,13 @@ struct agr_dev {
     uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
     uint32_t shard_id, id_gen;
-    uint32_t rows_hi;          // rows handed out so far (bound for decoded row ids)
+    // Rows are named two ways.  The LOGICAL row id counts arrivals (what the API calls first_rid, what a minted id encodes,
+    // what FIFO order means); the PHYSICAL row is where the record lives: the same number in append-only mode, logical
+    // mod ring_rows with AGR_CFG_RING.  Every per-row array is indexed by the physical row; [tail, head_l) is the live
+    // logical window (tail = 0 without the ring).
+    unsigned long long tail, head_l;
+    uint32_t ring_rows;        // 0 = append-only slab
+    uint32_t tail_phys;        // tail % ring_rows
     uint32_t cfg_flags;
 };
 
@@ -75,7 +81,7 @@ struct agr_k3_params {
     uint32_t* out_rid;         // [cap]
     uint32_t* out_slot;        // [cap]
     uint32_t cap;
-    uint32_t* min_inq;         // TICK: lowest rid still in a pending list (low-water mark for the next scan)
+    uint32_t* min_inq;         // TICK: lowest item (offset from lo) still in a pending list: low-water mark for the next scan
 };
 
 // K1 variants (agr_config.k1_variant low nibble): 0 = default (= 4); 1..4 = TMA kernel shapes (agr_k1_tma.cu:
@@ -93,9 +99,11 @@ void agr_launch_var_copy(const agr_dev& d, const uint32_t* rids, uint32_t n, con
 
 // K5: JSON wire form of stored records (agr_k5_json.cu)
 struct agr_k5_params {
-    const uint32_t* rids;            // nullable: record i lives in row first_rid + i
-    uint32_t first_rid, n;
+    const uint32_t* rids;            // physical rows; nullable: record i is logical row first_l + i
+    unsigned long long first_l;
+    uint32_t n;
     uint32_t array;                  // 1: emit json.Marshal([]*Request) = [rec,rec,...]; 0: records back to back
+    uint32_t roundtrip;              // 1: every string has been through json.Unmarshal (GetPendingRequests, requests.go:215-221)
     uint32_t* len;                   // [n] encoded length of record i (with its '[' / ',' / ']' in array mode)
     unsigned long long* off;         // [n + 1] byte offsets of the records in out
     unsigned long long* chunk_sum;   // [chunks + 1]; chunk_sum[chunks] = total bytes after agr_launch_k5_measure
@@ -133,6 +141,12 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    void* ids = nullptr /* device u8[n][16]: Request.ID per record, written by k1_post */);
 void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
                        unsigned long long* expired, cudaStream_t st);
+// ring mode: first live (STORED) row at or after the tail, as an offset from it (0xffffffff: none), then release of
+// `count` rows from the tail and stable compaction of a log (entries of released rows drop out)
+void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st);
+void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st);
+void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long long len, uint32_t released, uint32_t* out,
+                            uint32_t* chunk_cnt /* [chunks + 1] */, cudaStream_t st);
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st);
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);

@@ -96,6 +96,11 @@ typedef struct agr_record {
 #define AGR_CFG_COMBINE       0x20u /* flat-combine concurrent small agr_ingest / agr_ingest_ex calls (n <= 32) into one K1 launch:
                                        callers append to a pinned ring, the first one to arrive leads the batch, the others wait
                                        for their verdicts; the ring order is the event order (SURVEY 8b threading) */
+#define AGR_CFG_RING          0x40u /* the slab is a ring (needs AGR_CFG_MINT_IDS, fixed-stride records): row ids keep counting arrivals, a
+                                       record lives at row id mod slab_rows, and agr_reclaim hands the rows at the tail that no longer hold
+                                       a record (agr_expire) back for reuse — a shard then runs indefinitely instead of filling up.
+                                       A batch never wraps: rows left before the end of the slab are skipped (<= max_batch per lap;
+                                       max_batch is clamped to slab_rows / 2).  Without the flag the slab is append-only. */
 #define AGR_CFG_VARLEN        0x10u /* variable-length records (BASELINE config 5): byte-addressed slab, agr_ingest_var / *_var reads */
 #define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
 #define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */
@@ -266,9 +271,12 @@ int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t req
  * response / error.
  *   agr_get_record_json : the stored value of one record;            AGR_ENOTFOUND like storage.Get's miss
  *   agr_pending_json    : json.Marshal(GetPendingRequests(agent)) — "[{...},{...}]", or "null" for an empty list (the Go
- *                         slice is nil then, requests.go:204); *count = entries
- *   agr_rows_json       : rows [first_rid, first_rid + n) as an array (as_array != 0) or back to back with
- *                         offsets[0..n] (nullable); rows that hold no stored record encode as null.  out == NULL
+ *                         slice is nil then, requests.go:204); *count = entries.  GetPendingRequests json.Unmarshals every
+ *                         record first (requests.go:215-221), so invalid UTF-8 appears here as a raw U+FFFD, while the stored
+ *                         value (agr_get_record_json) of a never-updated record still spells it \ufffd
+ *   agr_rows_json       : rows [first_rid, first_rid + n) as an array (as_array & 1) or back to back with
+ *                         offsets[0..n] (nullable); as_array & 2: strings in their after-Unmarshal form, like
+ *                         agr_pending_json; rows that hold no stored record encode as null.  out == NULL
  *                         leaves the bytes on the device and only reports *len (sizing call / resident bench).
  * AGR_ECAP if cap is too small (*len holds the size needed). */
 int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
@@ -289,6 +297,12 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out);
  * the replay scan skip it (requests.go:210-213), and — like in the reference — its id stays in the pending / completed /
  * failed lists (agr_list).  *expired (nullable) = records dropped by this call.  Rows are not reclaimed. */
 int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired);
+/* AGR_CFG_RING: releases the rows at the tail of the ring that hold no record any more — everything up to the first row
+ * whose record is still stored — and drops their entries from the completed / failed lists (a deviation from the
+ * reference, where the ids of expired records stay listed forever, Q10: the lists of a long-running shard stay bounded
+ * instead).  Ids of released rows are never valid again (a minted id is checked against the live window).  *released
+ * (nullable) = rows handed back.  Typical use: agr_expire(now, 24 h) then agr_reclaim, from the same ticker. */
+int agr_reclaim(agr_handle* h, uint64_t* released);
 /* Integrity sweep: recomputes the checksum of every stored record on the device and compares it with the one K1 took at
  * ingest.  *bad = number of rows that differ (0 on a healthy slab). */
 int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad);
@@ -302,6 +316,7 @@ typedef struct agr_stats {
     uint64_t completed_log_len, failed_log_len;
     uint64_t k1_launches, k2_launches, k3_launches, k4_launches;   /* kernels of this library launched so far */
     uint64_t k5_launches;
+    uint64_t rows_tail;     /* AGR_CFG_RING: first row id that has not been released (0 otherwise); rows_used - rows_tail <= rows_cap */
     uint32_t agents, device;
 } agr_stats;
 int agr_stats_get(agr_handle* h, agr_stats* out);

@@ -191,7 +191,7 @@ class Manager:
                 data = self.redis.get(f"agent:{agent_id}:requests:{rid}")        # :208-209
             except RedisNil:
                 continue                                                         # :210-213 (Q10: stays in list)
-            out.append(copy.deepcopy(data))                                      # :215-221
+            out.append(gojson.unmarshal_strings(copy.deepcopy(data)))            # :215-221 json.Unmarshal
         return out
 
     # requests.go:228-275

@@ -96,11 +96,14 @@ def test_wire_form_is_byte_identical(mode, seed):
         # all rows at once: array form and back-to-back form with offsets
         every = [redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}") for r in reqs]
         got, offs = eng.rows_json(first, len(reqs), as_array=True)
-        assert got == G.marshal_list(every)
+        assert got == G.marshal_list(every)                              # the stored values, as an array
         assert len(json.loads(got)) == len(reqs)
         got, offs = eng.rows_json(first, len(reqs), as_array=False)
         for i, rec in enumerate(every):
             assert got[int(offs[i]):int(offs[i + 1])] == G.marshal_request(rec)
+        import copy
+        got, offs = eng.rows_json(first, len(reqs), as_array=True, roundtrip=True)      # after a json.Unmarshal of every record
+        assert got == G.marshal_list([G.unmarshal_strings(copy.deepcopy(r)) for r in every])
         assert eng.rows_json(first, 0, as_array=True)[0] == b"null"
         assert eng.stats()["k5_launches"] > 0
 

@@ -1,0 +1,167 @@
+"""AGR_CFG_RING: the slab as a ring.  A shard with 4096 rows takes three times that many requests while agr_expire +
+agr_reclaim release the rows at the tail; every observable stays equal to oracle/model.py's (with its key TTL), FIFO order
+holds across the wrap, ids of released rows stop resolving, and a restart in the middle is invisible."""
+import numpy as np
+import pytest
+
+import agentainer_lab_b200 as A
+from agentainer_lab_b200 import constants as K
+from oracle import model as M, gojson as G
+from jsoncase import make_requests, records_array
+
+pytestmark = pytest.mark.gpu
+AGENTS = ["agent-1700000000000000001", "agent-1700000000000000002", "agent-1700000000000000003"]
+SEC = 1_000_000_000
+HOUR = 3600 * SEC
+T0 = 1_700_000_000 * SEC
+STEP = 3 * HOUR          # one round of traffic every three hours
+TTL = 24 * HOUR          # the reference's key TTL (requests.go:106); oracle/model.py uses the same
+FLAGS = K.AGR_CFG_PERSISTENCE | K.AGR_CFG_MINT_IDS | K.AGR_CFG_RING
+
+
+def outcomes(rows):
+    outs = np.zeros(len(rows), dtype=A.outcome_dtype)
+    for j, (rid, agent, kind, http, seq) in enumerate(rows):
+        outs[j]["request_id"] = np.frombuffer(rid, dtype=np.uint8)
+        outs[j]["agent_id"] = agent.encode()
+        outs[j]["kind"], outs[j]["http_status"], outs[j]["seq"] = kind, http, seq
+    return outs
+
+
+def test_ring_runs_past_its_capacity(tmp_path):
+    R, per_round, rounds = 4096, 300, 42
+    kw = dict(slab_rows=R, max_agents=8, flags=FLAGS)
+    eng = A.Engine(**kw)
+    redis = M.MiniRedis(); mgr = M.Manager(redis)
+    agents = M.AgentStore(redis); proxy = M.Proxy(redis, agents); worker = M.ReplayWorker(redis, agents, proxy)
+    status = {AGENTS[0]: "running", AGENTS[1]: "stopped", AGENTS[2]: "stopped"}
+    for a, s in status.items():
+        eng.set_agent_state(a, s); agents.save(a, s)
+    known = []                                    # (request, logical row)
+    rng = np.random.default_rng(7)
+    wrapped_with_backlog = 0
+    try:
+        for rnd in range(rounds):
+            now = T0 + rnd * STEP
+            redis.now = now
+            reqs = make_requests(1000 + rnd, per_round, AGENTS)
+            for i, r in enumerate(reqs):
+                r.now = now + i
+            out = np.zeros(per_round, dtype=A.verdict_dtype); ids = np.zeros((per_round, 16), dtype=np.uint8)
+            first = eng.ingest_ex(records_array(reqs), out, ids)
+            for i, (r, rid) in enumerate(zip(reqs, ids)):
+                r.rid = bytes(rid)
+                known.append((r, first + i))
+                mgr.store_request(r.agent_id, M.HttpRequest(r.method, r.path, dict(r.headers), r.body, new_id=G.format_uuid(r.rid), now=r.now))
+            # the running agent answers most of its requests of this round; a few fail
+            ops = []
+            for r in reqs:
+                if r.agent_id == AGENTS[0]:
+                    u = rng.random()
+                    if u < 0.8:
+                        ops.append((r, K.AGR_OUT_RESPONSE, 200))
+                    elif u < 0.9:
+                        ops.append((r, K.AGR_OUT_ERROR, 0))
+            t = now + 10 * SEC
+            redis.now = t
+            for r, kind, code in ops:
+                if kind == K.AGR_OUT_RESPONSE:
+                    mgr.store_response(r.agent_id, G.format_uuid(r.rid), M.HttpResponse(code, {}, b"", now=t))
+                else:
+                    mgr.mark_request_failed(r.agent_id, G.format_uuid(r.rid), "transport error")
+            res = eng.complete(outcomes([(r.rid, r.agent_id, kind, code, t) for r, kind, code in ops]))
+            assert (res == 0).all()
+            # agent 3 comes up every 5th round for one tick: its backlog (possibly lying across the wrap) replays in FIFO order
+            if rnd % 5 == 4:
+                eng.set_agent_state(AGENTS[2], "running"); agents.save(AGENTS[2], "running")
+                disp, _ = eng.replay_scan(with_records=False)
+                want = worker.process_agents(lambda a, q: ("response", 200), now=t)
+                got = [(AGENTS[int(d["agent_slot"])], G.format_uuid(bytes(d["request_id"]))) for d in disp]
+                assert got == want and len(got) > 50
+                rows = [int(d["rid"]) for d in disp if int(d["agent_slot"]) == 2]
+                assert rows == sorted(rows)                                   # arrival order == ascending logical row
+                if (rows[0] % R) > (rows[-1] % R):
+                    wrapped_with_backlog += 1                                 # the backlog straddled the physical wrap
+                # what the Go side does with a dispatched request (replay_worker.go:120-163): through the proxy, then StoreResponse
+                outs = []
+                for a, rid_s in got:
+                    raw = bytes.fromhex(rid_s.replace("-", ""))
+                    outs.append((raw, a, K.AGR_OUT_RESPONSE, 200, t)); outs.append((raw, a, K.AGR_OUT_RESPONSE, 200, t))
+                assert (eng.complete(outcomes(outs)) == 0).all()
+                eng.set_agent_state(AGENTS[2], "stopped"); agents.save(AGENTS[2], "stopped")
+            # TTL, then hand the dead rows at the tail back
+            redis.now = now + 30 * SEC
+            eng.expire(redis.now, TTL)
+            eng.reclaim()
+            st = eng.stats()
+            tail = st["rows_tail"]
+            assert st["rows_used"] - tail <= R
+            if rnd == 20:                                                     # a restart in the middle
+                path = str(tmp_path / "ring.snap")
+                eng.snapshot(path); eng.close()
+                eng = A.Engine(restore_from=path, **kw)
+                assert eng.stats()["rows_tail"] == tail
+            if rnd % 3 == 2 or rnd == rounds - 1:
+                # records: live ones read the same, released / expired ones are gone on both sides
+                sample = known[-900:] + known[:: max(1, len(known) // 200)]
+                for r, lrow in sample:
+                    try:
+                        want = G.marshal_request(redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}"))
+                    except M.RedisNil:
+                        want = None
+                    assert eng.get_record_json(r.agent_id, r.rid) == want
+                    if lrow < tail:
+                        assert want is None
+                live_ids = {G.format_uuid(r.rid) for r, lrow in known if lrow >= tail}
+                for a in AGENTS:
+                    got, cnt = eng.pending_json(a)
+                    assert got == G.marshal_list(mgr.get_pending_requests(a))
+                    for which, q in ((K.AGR_LIST_PENDING, "pending"), (K.AGR_LIST_COMPLETED, "completed"), (K.AGR_LIST_FAILED, "failed")):
+                        ids_e = [G.format_uuid(bytes(i)) for i in eng.list(a, which, cap=1 << 14)]
+                        assert ids_e == [i for i in redis.lrange_all(f"agent:{a}:requests:{q}") if i in live_ids], (rnd, a, q)
+        st = eng.stats()
+        assert st["rows_used"] > 3 * R - 2 * per_round and st["rows_tail"] > 2 * R
+        assert wrapped_with_backlog >= 1
+        assert eng.verify()[1] == 0
+    finally:
+        eng.close()
+
+
+def test_ring_full_then_reclaimed():
+    R = 1024
+    with A.Engine(slab_rows=R, max_agents=4, flags=FLAGS) as eng:
+        eng.set_agent_state(AGENTS[0], "stopped")
+        reqs = make_requests(3, 256, AGENTS[:1])
+        for i, r in enumerate(reqs):
+            r.now = T0 + i
+        recs = records_array(reqs)
+        out = np.zeros(256, dtype=A.verdict_dtype); ids = np.zeros((256, 16), dtype=np.uint8)
+        firsts = [eng.ingest_ex(recs, out, ids) for _ in range(4)]
+        assert firsts == [0, 256, 512, 768]
+        with pytest.raises(A.AgrError) as e:
+            eng.ingest_ex(recs, out, ids)
+        assert e.value.code == K.AGR_ENOSPC
+        old = bytes(eng.mint_ids(0, 1)[0])
+        assert eng.get_record_json(AGENTS[0], old) is not None
+        assert eng.reclaim() == 0                                             # everything still holds a record
+        assert eng.expire(T0 + 10 * HOUR, HOUR) == 1024
+        assert eng.reclaim() == 1024
+        assert eng.get_record_json(AGENTS[0], old) is None                    # ids of released rows never resolve again
+        assert eng.ingest_ex(recs, out, ids) == 1024                          # row ids keep counting
+        assert eng.get_record_json(AGENTS[0], bytes(ids[5])) is not None
+        assert eng.pending_json(AGENTS[0])[1] == 256
+        # a batch that would wrap skips to the start of the slab
+        small = recs[:200]
+        o2 = np.zeros(200, dtype=A.verdict_dtype); i2 = np.zeros((200, 16), dtype=np.uint8)
+        f = [eng.ingest_ex(small, o2, i2) for _ in range(3)]                  # 1280, 1480, 1680 -> next would end at 2080 > 2048
+        assert f == [1280, 1480, 1680]
+        assert eng.expire(T0 + 100 * HOUR, HOUR) > 0 and eng.reclaim() > 0
+        assert eng.ingest_ex(small, o2, i2) == 2 * R                          # 168 rows skipped at the end of the lap
+        assert eng.ingest_ex(small, o2, i2) == 2 * R + 200
+        st = eng.stats()
+        assert st["rows_used"] == 2 * R + 400 and st["rows_tail"] == 1880
+
+
+def test_ring_needs_minted_ids():
+    with pytest.raises(A.AgrError):
+        A.Engine(slab_rows=1024, flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_RING)
