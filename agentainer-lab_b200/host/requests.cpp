@@ -172,6 +172,9 @@ Error Manager::GetPendingRequestsJSON(const std::string& agentID, std::string* o
     if (count) *count = n;
     return "";
 }
+Error Manager::Reclaim(uint64_t* released) {
+    return agr_reclaim(h_, released) < 0 ? std::string("reclaim: ") + agr_last_error() : "";
+}
 Error Manager::Expire(uint64_t now_ns, uint64_t ttl, uint64_t* expired) {
     return agr_expire(h_, now_ns, ttl, expired) < 0 ? std::string("expire: ") + agr_last_error() : "";
 }

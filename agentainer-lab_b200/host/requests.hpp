@@ -78,6 +78,8 @@ class Manager {
     Error GetPendingRequestsJSON(const std::string& agentID, std::string* out, size_t* count);
     // the 24 h TTL of the record keys (SET ... EX, requests.go:106,175,270): drop what was last SET ttl or more before now
     Error Expire(uint64_t now, uint64_t ttl, uint64_t* expired);
+    // AGR_CFG_RING: release the rows at the tail that no longer hold a record
+    Error Reclaim(uint64_t* released);
     // interceptTransport.RoundTrip's classification (server.go:597-611): dial errors leave the record pending
     Error RecordTransportError(const std::string& agentID, const std::string& requestID, const std::string& err);
     agr_handle* handle() const { return h_; }
