@@ -62,7 +62,7 @@ ABI_SYMBOLS = [
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
-    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim",
+    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim", "agr_set_agent_states",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "agr_expire": (i32, [vp, u64, u64, C.POINTER(u64)]),
         "agr_reclaim": (i32, [vp, C.POINTER(u64)]),
+        "agr_set_agent_states": (i32, [vp, vp, vp, u32, vp]),
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
@@ -262,6 +263,18 @@ class Engine:
     def set_agent_state(self, agent_id: str, status) -> int:
         code = K.AGENT_STATUS_CODES[status] if isinstance(status, str) else int(status)
         return _check(self.lib, self.lib.agr_set_agent_state(self.h, agent_id.encode(), code))
+
+    def set_agent_states(self, agent_ids, statuses) -> np.ndarray:
+        """Bulk status feed (state sync): returns the slot (or negative error) per agent."""
+        n = len(agent_ids)
+        ids = np.zeros((n, 32), dtype=np.uint8)
+        for i, a in enumerate(agent_ids):
+            b = a.encode()
+            ids[i, : len(b)] = np.frombuffer(b, dtype=np.uint8)
+        st = np.array([K.AGENT_STATUS_CODES[s] if isinstance(s, str) else int(s) for s in statuses], dtype=np.uint8)
+        slots = np.zeros(n, dtype=np.int32)
+        _check(self.lib, self.lib.agr_set_agent_states(self.h, _ptr(ids), _ptr(st), n, _ptr(slots)))
+        return slots
 
     def drop_agent(self, agent_id: str) -> None:
         _check(self.lib, self.lib.agr_drop_agent(self.h, agent_id.encode()))

@@ -426,13 +426,11 @@ static int push_agent_status(agr_handle* h, uint32_t slot, uint8_t status) {
     return 0;
 }
 
-int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
-    if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
+// core of agr_set_agent_state; `upload` = push the change to the device now (the bulk call uploads the tables once instead)
+static int set_agent_state_locked(agr_handle* h, const char* agent_id, uint8_t status, bool upload) {
     size_t len = strnlen(agent_id, AGR_AGENT_ID_BYTES);
     if (len == 0 || len >= AGR_AGENT_ID_BYTES) return fail(AGR_EINVAL, "agent id must be 1..31 bytes");
     if (status > AGR_AGENT_FAILED) return fail(AGR_EINVAL, "bad agent status");
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
     int slot = agent_find(h, agent_id);
     if (slot < 0) {
         if (h->agent_names.size() >= h->cfg.max_agents) return fail(AGR_ENOSPC, "agent table full");
@@ -449,14 +447,43 @@ int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
             idx = (idx + 1) & h->d.amask;
         h->akeys_host[idx] = key;
         h->akey_index.push_back(idx);
-        // status first, then the key that makes the slot reachable; both are stream-ordered before the next kernel
-        CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d.akeys + idx, &key, sizeof key, cudaMemcpyHostToDevice, h->stream));
+        if (upload) {
+            // status first, then the key that makes the slot reachable; both are stream-ordered before the next kernel
+            CK(cudaMemcpyAsync(h->d.astatus + slot, &status, 1, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->d.akeys + idx, &key, sizeof key, cudaMemcpyHostToDevice, h->stream));
+        }
     } else {
         h->agent_status[slot] = status;
-        TRY(push_agent_status(h, (uint32_t)slot, status));
+        if (upload) TRY(push_agent_status(h, (uint32_t)slot, status));
+        else h->akeys_host[h->akey_index[slot]].status = status;
     }
     return slot;
+}
+int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
+    if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    return set_agent_state_locked(h, agent_id, status, true);
+}
+int agr_set_agent_states(agr_handle* h, const char (*agent_ids)[AGR_AGENT_ID_BYTES], const uint8_t* statuses, uint32_t n, int32_t* slots) {
+    if (!h || (n && (!agent_ids || !statuses))) return fail(AGR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    const bool bulk = n > 16;                       // many writes: update the host mirror, upload both tables once
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        char id[AGR_AGENT_ID_BYTES];
+        memcpy(id, agent_ids[i], AGR_AGENT_ID_BYTES); id[AGR_AGENT_ID_BYTES - 1] = 0;
+        const int s = set_agent_state_locked(h, id, statuses[i], !bulk);
+        if (slots) slots[i] = s;
+        if (s < 0 && rc == 0) rc = s;               // keep going: one bad entry must not hide the other status writes
+    }
+    if (bulk && !h->agent_status.empty()) {
+        CK(cudaMemcpyAsync(h->d.astatus, h->agent_status.data(), h->agent_status.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d.akeys, h->akeys_host.data(), h->akeys_host.size() * sizeof(agr_agent_key), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));       // the host vectors may be reallocated by the next call
+    }
+    return rc;
 }
 
 int agr_agent_slot(agr_handle* h, const char* agent_id) {

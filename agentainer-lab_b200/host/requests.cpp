@@ -1,5 +1,6 @@
 // requests.cpp — see requests.hpp.  Thin: every state change is a C-ABI call; nothing is decided on the host.
 #include "requests.hpp"
+#include <algorithm>
 
 #include <chrono>
 #include <cstring>
@@ -226,6 +227,43 @@ size_t ReplayWorker::ProcessAgents() {
         if (status < 0) m_->MarkRequestFailed(req.AgentID, req.ID, "request failed"); // :109-112
         else { Response r; r.StatusCode = status; m_->StoreResponse(req.AgentID, req.ID, r); }   // :158 (second completion, Q7)
     }
+    return n;
+}
+
+size_t ReplayWorker::ProcessAgentsConcurrent(unsigned workers) {
+    uint32_t n = 0, cap = 1024;
+    std::vector<agr_dispatch> disp; std::vector<agr_record> recs;
+    for (;;) {
+        disp.resize(cap); recs.resize(cap);
+        int rc = agr_replay_scan(m_->handle(), disp.data(), recs.data(), cap, &n);
+        if (rc == AGR_ECAP) { cap = n; continue; }
+        if (rc < 0) return 0;
+        break;
+    }
+    // the dispatch list is grouped by agent: cut it into runs
+    std::vector<std::pair<uint32_t, uint32_t>> runs;                                  // [begin, end)
+    for (uint32_t i = 0; i < n;) {
+        uint32_t j = i + 1;
+        while (j < n && disp[j].agent_slot == disp[i].agent_slot) ++j;
+        runs.emplace_back(i, j);
+        i = j;
+    }
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        for (size_t r; (r = next.fetch_add(1)) < runs.size();) {
+            for (uint32_t i = runs[r].first; i < runs[r].second; ++i) {               // FIFO inside the agent
+                Request req; Manager::FromRecord(recs[i], &req);
+                const int status = send_(req.AgentID, req);
+                if (status < 0) m_->MarkRequestFailed(req.AgentID, req.ID, "request failed");
+                else { Response rr; rr.StatusCode = status; m_->StoreResponse(req.AgentID, req.ID, rr); }
+            }
+        }
+    };
+    std::vector<std::thread> ths;
+    const unsigned nt = std::max(1u, std::min<unsigned>(workers, (unsigned)runs.size()));
+    for (unsigned t = 1; t < nt; ++t) ths.emplace_back(work);
+    work();
+    for (auto& th : ths) th.join();
     return n;
 }
 

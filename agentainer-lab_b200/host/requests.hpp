@@ -110,6 +110,11 @@ class ReplayWorker {
     void Start(unsigned interval_ms = 5000);   // :36-50 (5 s ticker)
     void Stop();                               // :53-55
     size_t ProcessAgents();                    // :58-117 — one tick; returns the number of replays dispatched
+    // The same tick with the agents replayed CONCURRENTLY by `workers` threads.  The reference walks agents
+    // and their requests strictly one after the other (Q14); nothing in its semantics orders two different agents, so the
+    // per-agent runs of the dispatch list may proceed side by side while each run stays FIFO.  `send` is called from
+    // several threads at once.
+    size_t ProcessAgentsConcurrent(unsigned workers);
   private:
     Manager* m_;
     Sender send_;

@@ -4,6 +4,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -104,9 +106,47 @@ static int run(bool mint, bool combine) {
         // the rest of the driver continues on the logical clock; rows ingested before stay expired, which the counters below ignore
     }
 
+    // concurrent replay: six stopped agents queue 40 requests each, all start, one tick on four workers;
+    // every agent's requests are replayed in its arrival order and its completed list holds each id twice, in order (Q7)
+    {
+        std::vector<std::string> names; std::vector<std::vector<std::string>> want(6);
+        char ids[6][AGR_AGENT_ID_BYTES]; uint8_t sts[6]; int32_t slots[6];
+        for (int a = 0; a < 6; ++a) {
+            names.push_back("agent-17000000000000001" + std::to_string(10 + a));
+            memset(ids[a], 0, sizeof ids[a]); strncpy(ids[a], names[a].c_str(), AGR_AGENT_ID_BYTES - 1); sts[a] = AGR_AGENT_STOPPED;
+        }
+        CHECK(agr_set_agent_states(h, ids, sts, 6, slots) == 0 && slots[5] == slots[0] + 5);
+        for (int i = 0; i < 40; ++i) for (int a = 0; a < 6; ++a) {
+            HttpRequest r = post; r.Path = "/agent/" + names[a] + "/chat"; r.Body.push_back((uint8_t)i);
+            Verdict qv; CHECK(mgr.Decide(names[a], r, &qv).empty() && qv.Code == AGR_V_QUEUED);
+            want[a].push_back(qv.RequestID);
+        }
+        for (int a = 0; a < 6; ++a) sts[a] = AGR_AGENT_RUNNING;
+        CHECK(agr_set_agent_states(h, ids, sts, 6, nullptr) == 0);
+        std::mutex smu; std::map<std::string, std::vector<std::string>> seen_by;
+        ReplayWorker cw(&mgr, [&](const std::string& agent, const Request& req) {
+            { std::lock_guard<std::mutex> g(smu); seen_by[agent].push_back(req.ID); }
+            HttpRequest rr; rr.Method = req.Method; rr.Path = req.Path; rr.Header = req.Headers; rr.Body = req.Body;
+            rr.Header["X-Agentainer-Request-ID"] = req.ID; rr.Header["X-Agentainer-Replay"] = "true";
+            Verdict pv; mgr.Decide(agent, rr, &pv);
+            if (pv.Code != AGR_V_FORWARD) return pv.HTTPStatus;
+            Response r200; r200.StatusCode = 200;
+            mgr.StoreResponse(agent, pv.RequestID, r200);
+            return 200;
+        });
+        CHECK(cw.ProcessAgentsConcurrent(4) == 240);
+        for (int a = 0; a < 6; ++a) {
+            CHECK(seen_by[names[a]] == want[a]);
+            std::vector<std::string> twice;
+            for (const auto& id : want[a]) { twice.push_back(id); twice.push_back(id); }
+            CHECK(list_ids(h, names[a].c_str(), AGR_LIST_COMPLETED) == twice);
+            CHECK(list_ids(h, names[a].c_str(), AGR_LIST_PENDING).empty());
+        }
+    }
+
     // concurrency: NT threads x 500 requests against a running agent, each completed by its own thread
     const char* C = "agent-1700000000000000003";
-    CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 3);
+    CHECK(agr_set_agent_state(h, C, AGR_AGENT_RUNNING) == 9);
     const int NT = combine ? 64 : 8;
     std::vector<std::thread> ths; std::atomic<int> bad{0};
     auto t0 = std::chrono::steady_clock::now();
@@ -124,7 +164,7 @@ static int run(bool mint, bool combine) {
     CHECK(bad == 0);
     CHECK(list_ids(h, C, AGR_LIST_PENDING).empty());
     agr_stats st; CHECK(agr_stats_get(h, &st) == 0);
-    CHECK(st.completions == (uint64_t)(1 + 6 + 1 + NT * 500) && st.completion_misses == 1);
+    CHECK(st.completions == (uint64_t)(1 + 6 + 1 + 480 + NT * 500) && st.completion_misses == 1);
     printf("host mirror OK (%s ids%s): KAT-A/B/C + %d concurrent single-request Decide+StoreResponse round trips from %d threads, %.0f req/s, %llu K1 launches\n",
            mint ? "engine-minted" : "caller-supplied", combine ? ", flat-combined ingest" : "", NT * 500, NT, NT * 500 / secs,
            (unsigned long long)st.k1_launches);

@@ -140,6 +140,11 @@ const char* agr_strerror(int code);
  * handed out in registration order.  Returns the slot (>= 0) or a negative error. */
 enum { AGR_AGENT_CREATED = 0, AGR_AGENT_RUNNING = 1, AGR_AGENT_STOPPED = 2, AGR_AGENT_PAUSED = 3, AGR_AGENT_FAILED = 4 };  /* agent.go:23-29 */
 int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status);
+/* The same for a batch of status writes (the periodic state sync, sync/state_sync.go:190-210, and quick sync,
+ * pkg/agentsync/quick_sync.go:89-102, walk every agent): ids are fixed-stride NUL-padded strings; slots (nullable)
+ * receives the slot or the negative error of each entry; the return value is 0 or the first error.  More than 16
+ * entries are applied to the host mirror and uploaded as two table copies instead of one small copy per agent. */
+int agr_set_agent_states(agr_handle* h, const char (*agent_ids)[AGR_AGENT_ID_BYTES], const uint8_t* statuses, uint32_t n, int32_t* slots);
 /* replaces the queue cleanup of agent.Manager.Remove (agent.go:343-359): DEL agent:{id} and the three lists.
  * Records are left orphaned exactly like the reference (Q17). */
 int agr_drop_agent(agr_handle* h, const char* agent_id);

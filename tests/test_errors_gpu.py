@@ -71,3 +71,30 @@ def test_sharded_calls_need_a_communicator():
         with pytest.raises(A.AgrError) as e:
             eng.ingest_sharded(np.zeros(1, dtype=A.record_dtype))
         assert e.value.code == K.AGR_ECOMM
+
+
+def test_bulk_agent_state_feed():
+    """agr_set_agent_states == the same agr_set_agent_state calls one by one (small and table-upload paths)."""
+    import numpy as np
+    from jsoncase import make_requests, records_array
+    names = [f"agent-17000000000000{i:05d}" for i in range(300)]
+    with A.Engine(slab_rows=1 << 12, max_agents=512) as one, A.Engine(slab_rows=1 << 12, max_agents=512) as bulk:
+        sts = ["running" if i % 3 else "stopped" for i in range(300)]
+        for n_, s_ in zip(names, sts):
+            one.set_agent_state(n_, s_)
+        assert list(bulk.set_agent_states(names[:5], sts[:5])) == [0, 1, 2, 3, 4]            # per-entry copies
+        assert list(bulk.set_agent_states(names, sts)) == list(range(300))                    # table upload
+        flip = ["stopped" if s == "running" else "running" for s in sts]
+        for n_, s_ in zip(names[::7], flip[::7]):
+            one.set_agent_state(n_, s_)
+        bulk.set_agent_states(names[::7], flip[::7])
+        reqs = make_requests(4, 600, names)
+        recs = records_array(reqs)
+        outs = []
+        for eng in (one, bulk):
+            out = np.zeros(600, dtype=A.verdict_dtype); ids = np.zeros((600, 16), dtype=np.uint8)
+            eng.ingest_ex(recs, out, ids)
+            outs.append(out.copy())
+        assert (outs[0] == outs[1]).all() and len(set(outs[0]["code"].tolist())) >= 2
+        bad = bulk.lib.agr_set_agent_states(bulk.h, None, None, 3, None)
+        assert bad == K.AGR_EINVAL
