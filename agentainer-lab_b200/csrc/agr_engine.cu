@@ -1465,28 +1465,23 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
     CK(cudaMemsetAsync(d_off, 0xff, 4, h->stream));
     agr_launch_first_live(h->d, d_off, h->stream);
     CK(cudaGetLastError());
+    unsigned long long* lens = (unsigned long long*)(h->h_small + 2);          // pinned
     CK(cudaMemcpyAsync(h->h_small, d_off, 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(lens, h->d.log_len, 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));                                      // the only host round trip
     const uint64_t count = (h->h_small[0] == 0xffffffffu) ? h->rows_used - h->tail : h->h_small[0];
     h->k3_launches += 1;
     if (count == 0) return 0;
     agr_launch_release_rows(h->d, (uint32_t)count, h->d_resp_len, h->d_resp_hlen, h->d_err_len, h->stream);
-    unsigned long long lens[2];
-    CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    h->k3_launches += 1;
     for (int k = 0; k < 2; ++k) {                                              // completed, failed
+        if (!lens[k]) continue;
         uint32_t*& log = k == 0 ? h->d.completed_log : h->d.failed_log;
-        agr_launch_log_compact(h->d, log, lens[k], (uint32_t)count, h->d_log_scratch, h->d_lc_chunks, h->stream);
+        agr_launch_log_compact(h->d, log, lens[k], (uint32_t)count, h->d_log_scratch, h->d_lc_chunks, h->d.log_len + k, h->stream);
         CK(cudaGetLastError());
-        const uint32_t nch = (uint32_t)((lens[k] + 1023) / 1024);
-        CK(cudaMemcpyAsync(h->h_small, h->d_lc_chunks + nch, 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        lens[k] = lens[k] ? h->h_small[0] : 0;
         std::swap(log, h->d_log_scratch);                                      // the compacted copy becomes the log
+        h->k3_launches += 3;
     }
-    CK(cudaMemcpyAsync(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->k3_launches += 8;
     h->tail += count;
     h->released_total += count;
     if (h->scan_lo < h->tail) h->scan_lo = h->tail;

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_log_count(const agr_dev d, const uint32
     __syncthreads();
     if (threadIdx.x == 0) chunk_cnt[blockIdx.x] = s_cnt;
 }
-__global__ void __launch_bounds__(1024) k_log_scan(uint32_t* chunk_cnt, const uint32_t nchunks) {     // exclusive, total at [nchunks]
+__global__ void __launch_bounds__(1024) k_log_scan(uint32_t* chunk_cnt, const uint32_t nchunks, unsigned long long* new_len) {   // exclusive; total -> *new_len
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(1024) k_log_scan(uint32_t* chunk_cnt, const ui
         if (threadIdx.x == 1023) s_carry = pre + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) chunk_cnt[nchunks] = s_carry;
+    if (threadIdx.x == 0) { chunk_cnt[nchunks] = s_carry; *new_len = s_carry; }
 }
 // one warp per chunk keeps the order: 32 entries per step, ballot + popc
 __global__ void __launch_bounds__(32) k_log_scatter(const agr_dev d, const uint32_t* __restrict__ log, const unsigned long long len,
@@ -338,11 +338,11 @@ __global__ void __launch_bounds__(32) k_log_scatter(const agr_dev d, const uint3
     }
 }
 void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long long len, uint32_t released, uint32_t* out,
-                            uint32_t* chunk_cnt, cudaStream_t st) {
-    if (!len) { cudaMemsetAsync(chunk_cnt, 0, 4, st); return; }
+                            uint32_t* chunk_cnt, unsigned long long* new_len, cudaStream_t st) {
+    if (!len) return;
     const uint32_t nch = (uint32_t)((len + LC_CHUNK - 1) / LC_CHUNK);
     k_log_count<<<nch, 256, 0, st>>>(d, log, len, released, chunk_cnt);
-    k_log_scan<<<1, 1024, 0, st>>>(chunk_cnt, nch);
+    k_log_scan<<<1, 1024, 0, st>>>(chunk_cnt, nch, new_len);
     k_log_scatter<<<nch, 32, 0, st>>>(d, log, len, released, chunk_cnt, out);
 }
 

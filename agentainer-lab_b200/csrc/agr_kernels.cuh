@@ -146,7 +146,8 @@ void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long 
 void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st);
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st);
 void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long long len, uint32_t released, uint32_t* out,
-                            uint32_t* chunk_cnt /* [chunks + 1] */, cudaStream_t st);
+                            uint32_t* chunk_cnt /* [chunks + 1] */, unsigned long long* new_len /* device: receives the kept count */,
+                            cudaStream_t st);
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st);
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);

@@ -266,6 +266,43 @@ def measure_resident(A, K, torch, dist, args, wl, rank, local_rank, extra_flags,
     return dev_ms, k_ms / max(1, k_n)
 
 
+def measure_sustained(A, K, torch, local_rank, variant, steps=48):
+    """The ring under load (AGR_CFG_RING): 1 M records per step through an 8 M-row slab, every record left pending and
+    dropped by the key TTL four steps later; each step = K1 over the batch + agr_expire + agr_reclaim.  Device time per step
+    from CUDA events around those three calls (the record generator that refills the rows is outside them)."""
+    B = 1 << 20
+    R = 8 * B
+    eng = A.Engine(device=local_rank, slab_rows=R, max_agents=1024, max_batch=B, k1_variant=variant,
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_MINT_IDS | K.AGR_CFG_RING)
+    nanos0 = 1700000000000000000
+    names = [A.synth_agent_id(k, agent_nanos0=nanos0) for k in range(256)]
+    eng.set_agent_states(names, ["stopped"] * 256)
+    synth = dict(seed=11, n_agents=256, agent_nanos0=nanos0)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
+    warm = 10
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    released = 0
+    for s in range(warm + steps):
+        first = eng.reserve_rows(B)
+        eng.synth_fill_rows(s * B, first, B, **synth)           # seq of record j = its stream index: the clock of this run
+        if s >= warm:
+            evs[s - warm][0].record(stream)
+        eng.ingest_rows_async(first, B)
+        eng.expire((s + 1) * B, 4 * B)
+        released += eng.reclaim()
+        if s >= warm:
+            evs[s - warm][1].record(stream)
+    eng.sync(); torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    st = eng.stats()
+    assert st["stored"] == (warm + steps) * B and st["rows_used"] == (warm + steps) * B, st
+    assert st["rows_used"] - st["rows_tail"] <= R and released >= (warm + steps - 5) * B, (st, released)
+    eng.close()
+    return {"records_per_step": B, "ring_rows": R, "steps": steps, "laps": (warm + steps) * B / R, "ms_per_step": ms,
+            "requests_per_s": B / (ms * 1e-3), "rows_released": released,
+            "what": "K1 + agr_expire (TTL sweep over the slab) + agr_reclaim (release 1 M rows, compact the logs) per step, device time"}
+
+
 def bind_to_gpu_numa_node(index: int):
     """Run on (and therefore allocate pinned host memory from) the CPUs NVML reports as local to the GPU: DMA from the far
     socket of a two-socket host loses ~25 % of the PCIe bandwidth.  A host process serving one GPU would be pinned the same way."""
@@ -409,6 +446,8 @@ def run_ours(args, wl, rank, world, local_rank):
                                  "algorithmic_bytes_per_record": 512 + json_bytes / B,
                                  "GBps": (512 * B + json_bytes) / (k5_ms * 1e-3) / 1e9,
                                  "note": "measure + scan + emit kernels and the host's read of the total between them"}}
+        eng_sust = measure_sustained(A, K, torch, local_rank, args.variant)
+        secondary["sustained_ring"] = eng_sust
     # ---- the same workload and kernel in the OTHER id mode: "mint" = the engine mints
     # Request.ID like StoreRequest does (requests.go:87) and ids are a keyed bijection of the row; "hash" = caller-supplied
     # random ids kept in a 32 B/slot dedupe index (one CAS.128 + RED per stored record)
