@@ -114,7 +114,8 @@ struct agr_handle {
     std::vector<uint8_t> k_flag;
     bool k_leader = false;
     // variable-length mode
-    uint64_t vused = 0, vcap = 0;
+    uint64_t vused = 0, vcap = 0;               // bytes appended so far (ring: logical, pads included) / capacity
+    uint64_t vtail = 0;                        // ring: logical offset of the first byte that has not been released
     uint32_t* d_voffsets = nullptr; uint32_t* d_tile_first = nullptr;   // per-batch offsets [max_batch+1], tile index
     uint32_t* h_voffsets = nullptr;
     uint32_t* d_lens = nullptr; unsigned long long* d_goffs = nullptr;  // gather scratch [out_cap]
@@ -271,7 +272,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
     if (c.max_batch == 0) c.max_batch = 1u << 20;
     if (c.flags & AGR_CFG_RING) {
-        if (!mint || (c.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "AGR_CFG_RING needs AGR_CFG_MINT_IDS and fixed-stride records");
+        if (!mint) return fail(AGR_EINVAL, "AGR_CFG_RING needs AGR_CFG_MINT_IDS");
         if (c.max_batch > c.slab_rows / 2) c.max_batch = (uint32_t)(c.slab_rows / 2);
         if (c.max_batch == 0) return fail(AGR_EINVAL, "AGR_CFG_RING: slab_rows too small");
     }
@@ -998,10 +999,19 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
         if (offsets[i + 1] < offsets[i] || (len & 15u) || len < AGR_HEADER_BYTES || len > AGR_VAR_MAX_RECORD)
             return fail(AGR_EINVAL, "record " + std::to_string(i) + ": length must be a multiple of 16 in [96, 8192]");
     }
-    if (h->vused + bytes > h->vcap) return fail(AGR_ENOSPC, "byte slab full");
+    uint64_t vpad = 0;
+    if (!is_ring(h)) {
+        if (h->vused + bytes > h->vcap) return fail(AGR_ENOSPC, "byte slab full");
+    } else {                                                      // byte ring: a blob never wraps either
+        if (bytes > h->vcap / 2) return fail(AGR_EINVAL, "batch larger than half the byte slab");
+        const uint64_t at = h->vused % h->vcap;
+        vpad = (at + bytes > h->vcap) ? h->vcap - at : 0;
+        if (h->vused + vpad + bytes - h->vtail > h->vcap) return fail(AGR_ENOSPC, "byte slab full: agr_expire + agr_reclaim release bytes at the tail");
+    }
     TRY(reserve_rows_locked(h, n, &first));
     if (first_rid) *first_rid = first;
-    const uint64_t base = h->vused;
+    h->vused += vpad;
+    const uint64_t base = is_ring(h) ? h->vused % h->vcap : h->vused;          // physical byte offset of the blob
     h->vused += bytes;
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->d.slab + base, blob, bytes, cudaMemcpyHostToDevice, st));
@@ -1016,9 +1026,9 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
         e0 = h->tev[2 * k]; e1 = h->tev[2 * k + 1];
         CK(cudaEventRecord(e0, st));
     }
-    CK(agr_launch_k1_var(h->d, h->d.slab + base, h->d_voffsets, n, bytes, h->d_tile_first, (uint32_t)first, base, h->sm_count, st));
+    CK(agr_launch_k1_var(h->d, h->d.slab + base, h->d_voffsets, n, bytes, h->d_tile_first, (uint32_t)phys_row(h, first), base, h->sm_count, st));
     if (e1) CK(cudaEventRecord(e1, st));
-    agr_launch_k1_post(h->d, (uint32_t)first, n, h->sm_count, st, out ? h->d_verdicts : nullptr, ids ? h->d_ids : nullptr);
+    agr_launch_k1_post(h->d, (uint32_t)phys_row(h, first), n, h->sm_count, st, out ? h->d_verdicts : nullptr, ids ? h->d_ids : nullptr);
     h->k1_launches += 3;
     CK(cudaGetLastError());
     if (out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, st));
@@ -1295,7 +1305,7 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 struct snap_header {
     char magic[8];                 // "AGRSNAP3"
     uint32_t flags, n_agents, shard, gen;
-    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total, tail, released_total, slab_rows;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total, tail, released_total, slab_rows, vtail, vcap;
 };
 static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
     const size_t chunk = h->bounce_bytes;
@@ -1330,7 +1340,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN | AGR_CFG_RING);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
-    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total; hd.tail = h->tail; hd.released_total = h->released_total; hd.slab_rows = h->cfg.slab_rows;
+    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total; hd.tail = h->tail; hd.released_total = h->released_total; hd.slab_rows = h->cfg.slab_rows; hd.vtail = h->vtail; hd.vcap = h->vcap;
     unsigned long long lens[2];
     int rc = 0;
     auto done = [&](int r) { fclose(f); return r; };
@@ -1343,7 +1353,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
         fwrite(name, 1, AGR_AGENT_ID_BYTES, f); fwrite(&h->agent_status[a], 1, 1, f);
     }
     const size_t R = (size_t)rows_span(h);
-    const size_t slab_bytes = (h->cfg.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
+    const size_t slab_bytes = (h->cfg.flags & AGR_CFG_VARLEN) ? (size_t)(is_ring(h) ? std::min<uint64_t>(hd.vused, h->vcap) : hd.vused) : R * AGR_REC;
     if ((rc = dump_dev(h, f, h->d.slab, slab_bytes)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.state, R * 4)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.route, R * 4)) < 0) return done(rc);
@@ -1385,8 +1395,9 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     auto bail = [&](int r) { std::string keep = g_err; fclose(f); agr_destroy(h); g_err = keep; return r; };
     if (hd.resp_used > h->resp_cap) return bail(fail(AGR_ENOSPC, "restore: stored responses larger than resp_bytes"));
     const bool snap_ring = (hd.flags & AGR_CFG_RING) != 0;
+    if (snap_ring && (hd.flags & AGR_CFG_VARLEN) && hd.vcap != h->vcap) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same vslab_bytes"));
     if (snap_ring && hd.slab_rows != h->cfg.slab_rows) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same slab_rows (rows live at logical mod slab_rows)"));
-    if ((!snap_ring && hd.rows_used > h->cfg.slab_rows) || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && hd.vused > h->vcap))
+    if ((!snap_ring && hd.rows_used > h->cfg.slab_rows) || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && !snap_ring && hd.vused > h->vcap))
         return bail(fail(AGR_ENOSPC, "restore: snapshot larger than the configured capacities"));
     for (uint32_t a = 0; a < hd.n_agents; ++a) {
         char name[AGR_AGENT_ID_BYTES]; uint8_t st;
@@ -1398,7 +1409,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     }
     std::lock_guard<std::mutex> lk(h->mu);
     const size_t R = snap_ring ? (size_t)std::min<uint64_t>(hd.rows_used, hd.slab_rows) : (size_t)hd.rows_used;
-    const size_t slab_bytes = (hd.flags & AGR_CFG_VARLEN) ? (size_t)hd.vused : R * AGR_REC;
+    const size_t slab_bytes = (hd.flags & AGR_CFG_VARLEN) ? (size_t)(snap_ring ? std::min<uint64_t>(hd.vused, hd.vcap) : hd.vused) : R * AGR_REC;
     if ((rc = load_dev(h, f, h->d.slab, slab_bytes)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.state, R * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.route, R * 4)) < 0) return bail(rc);
@@ -1421,7 +1432,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     h->resp_used = hd.resp_used; h->expired_total = hd.expired_total;
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
-    h->rows_used = hd.rows_used; h->vused = hd.vused; h->scan_lo = hd.scan_lo;
+    h->rows_used = hd.rows_used; h->vused = hd.vused; h->vtail = hd.vtail; h->scan_lo = hd.scan_lo;
     h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->tail = hd.tail; h->released_total = hd.released_total; sync_window(h);
     if (!(hd.flags & AGR_CFG_MINT_IDS) && R) {        // hash-id mode: rebuild the dedupe index from the restored rows
         agr_launch_reindex(h->d, (uint32_t)R, h->stream);
@@ -1486,6 +1497,17 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
     h->released_total += count;
     if (h->scan_lo < h->tail) h->scan_lo = h->tail;
     sync_window(h);
+    if (h->cfg.flags & AGR_CFG_VARLEN) {                          // the byte ring's tail follows: first byte of the first live record
+        if (h->tail == h->rows_used) h->vtail = h->vused;
+        else {
+            unsigned long long q = 0;
+            CK(cudaMemcpyAsync(&q, h->d.voff + phys_row(h, h->tail), 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            uint64_t used = (h->vused % h->vcap + h->vcap - q) % h->vcap;
+            if (used == 0) used = h->vcap;                         // head == tail with live records: the ring is exactly full
+            h->vtail = h->vused - used;
+        }
+    }
     if (released) *released = count;
     return 0;
 }

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_var_copy(const agr_dev d, const uint32_
         uint4 v = ldg_nc_v4(src + (size_t)c * 16);
         if (c == 0 && (d.cfg_flags & AGR_CFG_MINT_IDS)) {
             unsigned long long lo, hi;
-            agr_mint_id(rid, d.shard_id, d.id_gen, d.id_secret, lo, hi);
+            agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
             v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         }
         if (c == 5) {   // bytes 80..95: body_len | status,retry,max,err | resp_status  (live state patched in)

@@ -7,7 +7,7 @@ import pytest
 import agentainer_lab_b200 as A
 from agentainer_lab_b200 import constants as K
 from oracle import model as M, gojson as G
-from jsoncase import make_requests, records_array
+from jsoncase import make_requests, records_array, var_batch
 
 pytestmark = pytest.mark.gpu
 AGENTS = ["agent-1700000000000000001", "agent-1700000000000000002", "agent-1700000000000000003"]
@@ -28,9 +28,12 @@ def outcomes(rows):
     return outs
 
 
-def test_ring_runs_past_its_capacity(tmp_path):
+@pytest.mark.parametrize("mode", ["fixed", "var"])
+def test_ring_runs_past_its_capacity(mode, tmp_path):
     R, per_round, rounds = 4096, 300, 42
-    kw = dict(slab_rows=R, max_agents=8, flags=FLAGS)
+    var = mode == "var"
+    # variable-length records: the byte slab (6 MiB) is a ring too and laps about as often as the rows do
+    kw = dict(slab_rows=R, max_agents=8, flags=FLAGS | (K.AGR_CFG_VARLEN if var else 0), vslab_bytes=6 << 20)
     eng = A.Engine(**kw)
     redis = M.MiniRedis(); mgr = M.Manager(redis)
     agents = M.AgentStore(redis); proxy = M.Proxy(redis, agents); worker = M.ReplayWorker(redis, agents, proxy)
@@ -40,15 +43,21 @@ def test_ring_runs_past_its_capacity(tmp_path):
     known = []                                    # (request, logical row)
     rng = np.random.default_rng(7)
     wrapped_with_backlog = 0
+    bytes_in = 0
     try:
         for rnd in range(rounds):
             now = T0 + rnd * STEP
             redis.now = now
-            reqs = make_requests(1000 + rnd, per_round, AGENTS)
+            reqs = make_requests(1000 + rnd, per_round, AGENTS, max_payload=7000 if var else 416, big_bodies=var)
             for i, r in enumerate(reqs):
                 r.now = now + i
-            out = np.zeros(per_round, dtype=A.verdict_dtype); ids = np.zeros((per_round, 16), dtype=np.uint8)
-            first = eng.ingest_ex(records_array(reqs), out, ids)
+            if var:
+                blob, offs = var_batch(reqs)
+                bytes_in += int(offs[-1])
+                _, ids, first = eng.ingest_var(blob, offs)
+            else:
+                out = np.zeros(per_round, dtype=A.verdict_dtype); ids = np.zeros((per_round, 16), dtype=np.uint8)
+                first = eng.ingest_ex(records_array(reqs), out, ids)
             for i, (r, rid) in enumerate(zip(reqs, ids)):
                 r.rid = bytes(rid)
                 known.append((r, first + i))
@@ -74,7 +83,7 @@ def test_ring_runs_past_its_capacity(tmp_path):
             # agent 3 comes up every 5th round for one tick: its backlog (possibly lying across the wrap) replays in FIFO order
             if rnd % 5 == 4:
                 eng.set_agent_state(AGENTS[2], "running"); agents.save(AGENTS[2], "running")
-                disp, _ = eng.replay_scan(with_records=False)
+                disp = eng.replay_scan_var()[0] if var else eng.replay_scan(with_records=False)[0]
                 want = worker.process_agents(lambda a, q: ("response", 200), now=t)
                 got = [(AGENTS[int(d["agent_slot"])], G.format_uuid(bytes(d["request_id"]))) for d in disp]
                 assert got == want and len(got) > 50
@@ -122,6 +131,7 @@ def test_ring_runs_past_its_capacity(tmp_path):
         st = eng.stats()
         assert st["rows_used"] > 3 * R - 2 * per_round and st["rows_tail"] > 2 * R
         assert wrapped_with_backlog >= 1
+        assert not var or bytes_in > 2 * (6 << 20)                            # the byte ring lapped too
         assert eng.verify()[1] == 0
     finally:
         eng.close()
