@@ -174,6 +174,125 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
     k1_flush_counters(d, lc, s_ctr);
 }
 
+// ---- LSU form of the same kernel (k1_variant bit 0x20): no shared-memory stage and no TMA — the warp streams its tile
+// straight from global memory with coalesced 16 B loads.  Without a 12.5 KiB stage per warp an SM holds 48 warps instead
+// of 16, which is what the byte-tiled kernel above is short of (every warp there issues once per 8 cycles).  The
+// checksums come from ONE linear sweep over the tile: the record checksum weights word k of the record by k + 1; with g =
+// the word's index in the sweep that is (g + 1) - 4 lo (lo = the record's first chunk), so every lane accumulates
+// s0 = sum w and s1 = sum (g + 1) w of the chunks it meets and a record's pair is (S0, S1 - 4 lo S0) over the chunks between
+// two record starts.  A bitmap of record-start chunks tells each 32-chunk row where records begin: rows without a start
+// cost a load and a dozen integer ops; a row with a start closes the running record with two REDUX; records that lie
+// entirely inside one row are summed by a segmented shuffle reduction.
+#define VL_WARPS 8
+#define VL_MAXCH ((VT_TILE + VT_MAXREC) / 16u)         // chunks a tile's sweep can span (1024)
+#define VL_HWORDS (VL_MAXCH / 32u)
+__global__ void __launch_bounds__(VL_WARPS * 32, 5)
+k1_ingest_var_lsu(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t* __restrict__ off, const uint32_t* __restrict__ tile_first,
+                  const uint32_t ntiles, const uint32_t first_rid, const unsigned long long blob_base) {
+    __shared__ uint32_t s_off[VL_WARPS][VT_MAXCNT + 1];
+    __shared__ unsigned long long s_ck[VL_WARPS][VT_MAXCNT];
+    __shared__ uint32_t s_heads[VL_WARPS][VL_HWORDS];
+    __shared__ uint32_t s_ctr[K1_NLC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t lc[K1_NLC];
+#pragma unroll
+    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    const uint32_t tstride = gridDim.x * VL_WARPS;
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t* so = s_off[warp];
+    uint32_t* hb = s_heads[warp];
+    auto range_of = [&](uint32_t t, uint32_t& ra, uint32_t& rb) {
+        ra = rb = 0;
+        if (t < ntiles) { ra = __ldg(&tile_first[t]); rb = __ldg(&tile_first[t + 1]); }
+    };
+    uint32_t tile = blockIdx.x * VL_WARPS + warp;
+    uint32_t a, b, a1, b1;
+    range_of(tile, a, b);
+    range_of(tile + tstride, a1, b1);
+    for (; tile < ntiles; tile += tstride) {
+        const uint32_t cnt = b - a;
+        uint32_t a2, b2;
+        range_of(tile + 2u * tstride, a2, b2);                    // two tiles ahead: in flight during this tile's sweep
+        if (cnt) {
+            for (uint32_t k = lane; k <= cnt; k += 32) so[k] = __ldg(&off[a + k]);
+            if (lane < (int)VL_HWORDS) hb[lane] = 0;
+            __syncwarp();
+            const uint32_t start = so[0], nch = (so[cnt] - start) >> 4;
+            for (uint32_t r = lane; r < cnt; r += 32) { const uint32_t c = (so[r] - start) >> 4; atomicOr(&hb[c >> 5], 1u << (c & 31u)); }
+            __syncwarp();
+            const uint8_t* base = blob + start;
+            uint32_t a0 = 0, a1s = 0, base_r = 0, cur_r = 0xffffffffu, cur_lo = 0;
+            const uint32_t nrows = (nch + 31u) >> 5;
+            auto load_row = [&](uint32_t row) -> uint4 {
+                const uint32_t g = (row << 5) + lane;
+                return g < nch ? ldg_nc_v4(base + ((size_t)g << 4)) : make_uint4(0, 0, 0, 0);
+            };
+            auto do_row = [&](const uint4 v, const uint32_t row) {
+                const uint32_t g = (row << 5) + lane;
+                const uint32_t s0 = v.x + v.y + v.z + v.w;
+                const uint32_t s1 = 4u * g * s0 + (v.x + 2u * v.y + 3u * v.z + 4u * v.w);
+                const uint32_t word = hb[row];
+                if (word == 0) { a0 += s0; a1s += s1; return; }
+                const uint32_t first = __ffs(word) - 1u, last = 31u - __clz(word);
+                if ((uint32_t)lane < first) { a0 += s0; a1s += s1; }
+                if (cur_r != 0xffffffffu) {                                    // the running record ends at the first start
+                    const uint32_t S0 = __reduce_add_sync(FULL, a0), S1 = __reduce_add_sync(FULL, a1s);
+                    if (lane == 0) s_ck[warp][cur_r] = agr_cksum_pack(S0, S1 - 4u * cur_lo * S0);
+                }
+                if (word & (word - 1u)) {                                      // records that start AND end inside this row
+                    const bool in = (uint32_t)lane >= first && (uint32_t)lane < last;
+                    uint32_t x0 = in ? s0 : 0u, x1 = in ? s1 : 0u;
+                    const uint32_t ahead = lane < 31 ? word >> (lane + 1) : 0u;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y0 = __shfl_down_sync(FULL, x0, o), y1 = __shfl_down_sync(FULL, x1, o);
+                        if (lane + o < 32 && (ahead & ((1u << o) - 1u)) == 0u) { x0 += y0; x1 += y1; }
+                    }
+                    if (((word >> lane) & 1u) && (uint32_t)lane != last)
+                        s_ck[warp][base_r + __popc(word & below)] = agr_cksum_pack(x0, x1 - 4u * g * x0);
+                }
+                const bool tail = (uint32_t)lane >= last;
+                a0 = tail ? s0 : 0u; a1s = tail ? s1 : 0u;
+                base_r += __popc(word);
+                cur_r = base_r - 1u; cur_lo = (row << 5) + last;
+            };
+            // four rows (2 KiB per warp) stay in flight: a slot is refilled as soon as it has been consumed
+            uint4 q0 = load_row(0), q1 = load_row(1), q2 = load_row(2), q3 = load_row(3);
+            for (uint32_t row = 0; row < nrows; row += 4) {
+                do_row(q0, row);     q0 = load_row(row + 4);
+                if (row + 1 < nrows) { do_row(q1, row + 1); q1 = load_row(row + 5); }
+                if (row + 2 < nrows) { do_row(q2, row + 2); q2 = load_row(row + 6); }
+                if (row + 3 < nrows) { do_row(q3, row + 3); q3 = load_row(row + 7); }
+            }
+            if (cur_r != 0xffffffffu) {
+                const uint32_t S0 = __reduce_add_sync(FULL, a0), S1 = __reduce_add_sync(FULL, a1s);
+                if (lane == 0) s_ck[warp][cur_r] = agr_cksum_pack(S0, S1 - 4u * cur_lo * S0);
+            }
+            __syncwarp();
+            // ---- decisions, one record per lane; the headers were streamed a moment ago and come back from L2
+            for (uint32_t r = lane; r < cnt; r += 32) {
+                const uint8_t* gp = blob + so[r];
+                const uint4 h0 = ldg_nc_v4(gp), h1 = ldg_nc_v4(gp + 16), h2 = ldg_nc_v4(gp + 32), h3 = ldg_nc_v4(gp + 48),
+                            h4 = ldg_nc_v4(gp + 64), h5 = ldg_nc_v4(gp + 80);
+                const uint32_t rid = first_rid + a + r;
+                k1_ctx cx;
+                k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, cx);
+                const k1_result res = k1_finish(d, rid, h1, h5, cx, lc);
+                d.state[rid] = res.state;
+                d.route[rid] = res.route;
+                d.cksum[rid] = s_ck[warp][r];
+                d.voff[rid] = blob_base + so[r];
+                d.vlen[rid] = so[r + 1] - so[r];
+            }
+            __syncwarp();
+        }
+        a = a1; b = b1; a1 = a2; b1 = b2;
+    }
+    k1_flush_counters(d, lc, s_ctr);
+}
+
 // gather of variable-length rows: lens pass, then copy pass (offsets are scanned on the host: a per-tick operation)
 __global__ void __launch_bounds__(256) k_var_lens(const agr_dev d, const uint32_t* __restrict__ rids, const uint32_t n, uint32_t* __restrict__ lens) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,7 +324,18 @@ __global__ void __launch_bounds__(256) k_var_copy(const agr_dev d, const uint32_
 }
 
 cudaError_t agr_launch_k1_var(const agr_dev& d, const uint8_t* blob, const uint32_t* off, uint32_t n, unsigned long long blob_bytes,
-                              uint32_t* tile_first, uint32_t first_rid, unsigned long long blob_base, int sm_count, cudaStream_t st) {
+                              uint32_t* tile_first, uint32_t first_rid, unsigned long long blob_base, int sm_count, cudaStream_t st,
+                              uint32_t variant) {
+    if (variant & 0x20u) {                                       // LSU form
+        const uint32_t ntiles = (uint32_t)((blob_bytes + VT_TILE - 1) / VT_TILE);
+        k1v_tile_index<<<(n + 1 + 255u) / 256u, 256, 0, st>>>(off, n, tile_first, ntiles);
+        uint32_t blocks = (uint32_t)sm_count * 5u;
+        const uint32_t need = (ntiles + VL_WARPS - 1) / VL_WARPS;
+        if (blocks > need) blocks = need;
+        if (blocks == 0) blocks = 1;
+        k1_ingest_var_lsu<<<blocks, VL_WARPS * 32, 0, st>>>(d, blob, off, tile_first, ntiles, first_rid, blob_base);
+        return cudaGetLastError();
+    }
     constexpr int WARPS = VT_WARPS;
     const size_t smem = (size_t)WARPS * VT_STAGE + 128;
     static bool attr_done = false;

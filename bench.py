@@ -575,7 +575,7 @@ def run_varlen(args, rank, world, local_rank):
     n, na, S, W = 1 << 18, 256, args.steps, args.warmup
     rng = np.random.default_rng(7 + rank)
     eng = A.Engine(device=local_rank, slab_rows=(S + W) * n, max_agents=1024, max_batch=n, vslab_bytes=(S + W) * n * 1400,
-                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_VARLEN | K.AGR_CFG_MINT_IDS | K.AGR_CFG_TIMING)
+                   k1_variant=args.variant, flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_VARLEN | K.AGR_CFG_MINT_IDS | K.AGR_CFG_TIMING)
     for k in range(na):
         eng.set_agent_state(A.synth_agent_id(k), "running")
     wall, total_bytes = [], 0

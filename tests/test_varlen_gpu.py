@@ -2,6 +2,8 @@
 parity with the (size-agnostic) Python oracle, stored bytes round trip, checksum, tile-ownership edge cases."""
 import dataclasses
 
+import os
+
 import numpy as np
 import pytest
 
@@ -19,6 +21,7 @@ def engine(flags=VAR, **kw):
     kw.setdefault("slab_rows", 1 << 15)
     kw.setdefault("max_agents", 256)
     kw.setdefault("vslab_bytes", 256 << 20)
+    kw.setdefault("k1_variant", int(os.environ.get("AGR_TEST_K1_VARIANT", "0"), 0))   # e.g. 0x20: the LSU form of K1v
     return A.Engine(flags=flags, **kw)
 
 
