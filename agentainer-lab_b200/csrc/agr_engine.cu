@@ -272,7 +272,6 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
     if (c.max_batch == 0) c.max_batch = 1u << 20;
     if (c.flags & AGR_CFG_RING) {
-        if (!mint) return fail(AGR_EINVAL, "AGR_CFG_RING needs AGR_CFG_MINT_IDS");
         if (c.max_batch > c.slab_rows / 2) c.max_batch = (uint32_t)(c.slab_rows / 2);
         if (c.max_batch == 0) return fail(AGR_EINVAL, "AGR_CFG_RING: slab_rows too small");
     }
@@ -1497,6 +1496,17 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
     h->released_total += count;
     if (h->scan_lo < h->tail) h->scan_lo = h->tail;
     sync_window(h);
+    if (!(h->cfg.flags & AGR_CFG_MINT_IDS)) {
+        // hash-id mode: the released rows' ids must leave the dedupe index before their rows are reused.  Open addressing
+        // has no cheap delete; a release is a periodic event, so the index is rebuilt from the live window instead.
+        CK(cudaMemsetAsync(h->d.table, 0, (size_t)(h->d.table_mask + 1) * sizeof(agr_slot), h->stream));
+        const uint64_t R = h->cfg.slab_rows, live = h->rows_used - h->tail, p0 = h->tail % R;
+        const uint64_t n0 = std::min<uint64_t>(live, R - p0);
+        agr_launch_reindex_range(h->d, (uint32_t)p0, (uint32_t)n0, h->stream);
+        if (live > n0) agr_launch_reindex_range(h->d, 0, (uint32_t)(live - n0), h->stream);
+        CK(cudaGetLastError());
+        h->k1_launches += 2;
+    }
     if (h->cfg.flags & AGR_CFG_VARLEN) {                          // the byte ring's tail follows: first byte of the first live record
         if (h->tail == h->rows_used) h->vtail = h->vused;
         else {

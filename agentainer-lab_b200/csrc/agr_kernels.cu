@@ -349,6 +349,25 @@ void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st) {
     if (rows) k_verify<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(d, rows, bad);
 }
+// hash-id ring: rebuild of the dedupe index over a range of physical rows — only rows that still hold a record go in
+__global__ void __launch_bounds__(256) k_reindex_range(const agr_dev d, const uint32_t first, const uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t rid = first + i;
+    if (!(d.state[rid] & ST_STORED)) return;
+    const uint4 h0 = ldg_nc_v4(rec_ptr(d, rid));
+    const u128 key = make_u128(pack64(h0.x, h0.y), pack64(h0.z, h0.w));
+    unsigned long long idx = agr_hash_id(pack64(h0.x, h0.y), pack64(h0.z, h0.w)) & d.table_mask;
+    for (;;) {
+        const u128 old = cas128(&d.table[idx], 0, key);
+        if (old == 0 || old == key) break;
+        idx = (idx + 1) & d.table_mask;
+    }
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(~rid) : "memory");
+}
+void agr_launch_reindex_range(const agr_dev& d, uint32_t first, uint32_t n, cudaStream_t st) {
+    if (n) k_reindex_range<<<(n + 255u) / 256u, 256, 0, st>>>(d, first, n);
+}
 // rebuild of the dedupe index from restored rows (hash-id mode): k1_index over every stored row
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st) {
     if (rows) k1_index<<<(rows + 255u) / 256u, 256, 0, st>>>(d, 0u, rows);

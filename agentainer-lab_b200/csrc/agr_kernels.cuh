@@ -151,6 +151,7 @@ void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long
                             cudaStream_t st);
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st);
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
+void agr_launch_reindex_range(const agr_dev& d, uint32_t first, uint32_t n, cudaStream_t st);
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);
 int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
 void agr_launch_k2_prepare(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, agr_dop* ops, uint32_t n, cudaStream_t st);

@@ -96,11 +96,12 @@ typedef struct agr_record {
 #define AGR_CFG_COMBINE       0x20u /* flat-combine concurrent small agr_ingest / agr_ingest_ex calls (n <= 32) into one K1 launch:
                                        callers append to a pinned ring, the first one to arrive leads the batch, the others wait
                                        for their verdicts; the ring order is the event order (SURVEY 8b threading) */
-#define AGR_CFG_RING          0x40u /* the slab is a ring (needs AGR_CFG_MINT_IDS; with AGR_CFG_VARLEN the byte slab is a ring too): row ids keep counting arrivals, a
+#define AGR_CFG_RING          0x40u /* the slab is a ring (with AGR_CFG_VARLEN the byte slab is a ring too): row ids keep counting arrivals, a
                                        record lives at row id mod slab_rows, and agr_reclaim hands the rows at the tail that no longer hold
                                        a record (agr_expire) back for reuse — a shard then runs indefinitely instead of filling up.
                                        A batch never wraps: rows left before the end of the slab are skipped (<= max_batch per lap;
-                                       max_batch is clamped to slab_rows / 2).  Without the flag the slab is append-only. */
+                                       max_batch is clamped to slab_rows / 2).  With caller-supplied ids every agr_reclaim rebuilds the dedupe
+                                       index from the live rows.  Without the flag the slab is append-only. */
 #define AGR_CFG_VARLEN        0x10u /* variable-length records (BASELINE config 5): byte-addressed slab, agr_ingest_var / *_var reads */
 #define AGR_CFG_DIAG_NO_INDEX  0x100u /* DIAGNOSTIC ONLY (results invalid): K1 skips the dedupe-index insert, to attribute kernel time */
 #define AGR_CFG_DIAG_NO_CKSUM  0x200u /* DIAGNOSTIC ONLY (results invalid): K1 skips the record checksum */

@@ -28,12 +28,12 @@ def outcomes(rows):
     return outs
 
 
-@pytest.mark.parametrize("mode", ["fixed", "var"])
+@pytest.mark.parametrize("mode", ["fixed", "var", "hash"])
 def test_ring_runs_past_its_capacity(mode, tmp_path):
     R, per_round, rounds = 4096, 300, 42
     var = mode == "var"
     # variable-length records: the byte slab (6 MiB) is a ring too and laps about as often as the rows do
-    kw = dict(slab_rows=R, max_agents=8, flags=FLAGS | (K.AGR_CFG_VARLEN if var else 0), vslab_bytes=6 << 20)
+    kw = dict(slab_rows=R, max_agents=8, flags=(FLAGS & ~K.AGR_CFG_MINT_IDS if mode == "hash" else FLAGS) | (K.AGR_CFG_VARLEN if var else 0), vslab_bytes=6 << 20)
     eng = A.Engine(**kw)
     redis = M.MiniRedis(); mgr = M.Manager(redis)
     agents = M.AgentStore(redis); proxy = M.Proxy(redis, agents); worker = M.ReplayWorker(redis, agents, proxy)
@@ -172,6 +172,21 @@ def test_ring_full_then_reclaimed():
         assert st["rows_used"] == 2 * R + 400 and st["rows_tail"] == 1880
 
 
-def test_ring_needs_minted_ids():
-    with pytest.raises(A.AgrError):
-        A.Engine(slab_rows=1024, flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_RING)
+def test_ring_with_caller_ids_forgets_released_ids():
+    """hash-id mode: an id whose row was released leaves the dedupe index (rebuilt at every release) and may be stored again."""
+    with A.Engine(slab_rows=1024, max_agents=4, flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_RING) as eng:
+        eng.set_agent_state(AGENTS[0], "stopped")
+        reqs = make_requests(8, 100, AGENTS[:1])
+        for i, r in enumerate(reqs):
+            r.now = T0 + i
+        recs = records_array(reqs)
+        out = np.zeros(100, dtype=A.verdict_dtype); ids = np.zeros((100, 16), dtype=np.uint8)
+        eng.ingest_ex(recs, out, ids)
+        assert (out["flags"] & K.AGR_VF_STORED).all()
+        eng.ingest_ex(recs, out, ids)
+        assert (out["flags"] & K.AGR_VF_DUP_ID).all()                         # same ids again: refused while the first are live
+        assert eng.expire(T0 + 10 * HOUR, HOUR) == 100 and eng.reclaim() == 200
+        assert eng.get_record_json(AGENTS[0], reqs[0].rid) is None
+        eng.ingest_ex(recs, out, ids)
+        assert (out["flags"] & K.AGR_VF_STORED).all()
+        assert eng.get_record_json(AGENTS[0], reqs[0].rid) is not None
