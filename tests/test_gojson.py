@@ -74,3 +74,13 @@ def test_invalid_utf8_changes_form_after_a_round_trip():
     mgr.store_response("a", "i", M.HttpResponse(200, {b"K": b"\xff"}, b"", now=0))
     js = G.marshal_request(redis.get("agent:a:requests:i"))
     assert b'"error":"e\xef\xbf\xbd"' in js and b'"headers":{"K":"\\ufffd"}' in js
+
+
+def test_oracle_reproduces_the_committed_stream():
+    """tests/golden/json_stream.json pins the oracle's bytes for the seeded stream (regenerate with make_json_golden.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_json_golden", os.path.join(HERE, "golden", "make_json_golden.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    with open(os.path.join(HERE, "golden", "json_stream.json")) as f:
+        want = json.load(f)
+    assert mod.build(want["seed"], want["n"], want["n_ops"]) == want

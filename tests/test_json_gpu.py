@@ -142,3 +142,21 @@ def test_large_pending_list():
         got, cnt = eng.pending_json(AGENTS[0])
         assert cnt == n
         assert got == G.marshal_list(mgr.get_pending_requests(AGENTS[0]))
+
+
+def test_engine_matches_the_committed_stream():
+    """The same seeded stream as tests/golden/json_stream.json (caller-supplied ids, so the bytes are reproducible): the
+    engine's output hashes to the committed values."""
+    import hashlib, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "json_stream.json")) as f:
+        want = json.load(f)
+    reqs = make_requests(want["seed"], want["n"], AGENTS)
+    script = make_script(want["seed"], want["n"], want["n_ops"])
+    with A.Engine(slab_rows=1 << 12, max_agents=64, flags=MODES["hash"], resp_bytes=4 << 20) as eng:
+        drive_engine(eng, reqs, script)
+        records = [eng.get_record_json(r.agent_id, r.rid) for r in reqs]
+        assert hashlib.sha256(b"\n".join(records)).hexdigest() == want["records_sha256"]
+        assert [records[i].decode("latin-1") for i in (0, 7, 19, 42, 100)] == want["examples_latin1"]
+        for a in AGENTS:
+            got, cnt = eng.pending_json(a)
+            assert hashlib.sha256(got).hexdigest() == want["pending_sha256"][a] and cnt == want["pending_counts"][a]
