@@ -836,7 +836,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.groups = (mode == K3_TICK) ? std::max<uint32_t>(1, (uint32_t)h->agent_names.size()) : 1;
     uint64_t items = hi - lo;
     uint64_t max_warps = std::max<uint64_t>(1, (4u << 20) / p.groups);
-    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 32, (items + 1023) / 1024);
+    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 64, (items + 1023) / 1024);
     p.nwarps = (uint32_t)std::max<uint64_t>(1, std::min(want, max_warps));
     uint64_t per = (items + p.nwarps - 1) / p.nwarps;
     per = (per + 31) & ~31ull;

@@ -693,33 +693,50 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
         if (d.ring_rows && q >= d.ring_rows) q -= d.ring_rows;
         return q;
     };
-    uint32_t pr_next = prow_of(b + lane);
-    uint32_t st_next = (rows && b + lane < e) ? d.state[pr_next] : 0u;
-    uint32_t rt_next = (rows && b + lane < e) ? d.route[pr_next] : 0u;
-    for (unsigned long long k0 = b; k0 < e; k0 += 32) {
-        const uint32_t st = st_next, rt = rt_next, pr = pr_next;
-        const bool more = rows && k0 + 32 + lane < e;                                // next step's words are in flight
-        pr_next = prow_of(k0 + 32 + lane);
-        st_next = more ? d.state[pr_next] : 0u;
-        rt_next = more ? d.route[pr_next] : 0u;
-        if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;                // nothing pending in these 32 rows
-        k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
-        if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
-        const uint32_t g = (p.groups == 1) ? 0u : it.slot;
-        const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
-        const uint32_t peers = __match_any_sync(FULL, key);
-        if (it.sel) {
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            volatile uint32_t* cell = (SMEM ? srow : grow) + g;
-            const uint32_t base = *cell;
-            if (SCATTER) {
-                const uint32_t pos = p.goff[g] + base + rank;
+    // the row words of four steps (128 rows) are loaded at once, and the next four while these are being worked on
+    uint32_t st_c[4], rt_c[4], pr_c[4], st_n[4], rt_n[4], pr_n[4];
+    auto load4 = [&](unsigned long long k0, uint32_t (&st)[4], uint32_t (&rt)[4], uint32_t (&pr)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long k = k0 + 32u * j + lane;
+            pr[j] = prow_of(k);
+            const bool ok = rows && k < e;
+            st[j] = ok ? d.state[pr[j]] : 0u;
+            rt[j] = ok ? d.route[pr[j]] : 0u;
+        }
+    };
+    load4(b, st_c, rt_c, pr_c);
+    for (unsigned long long k4 = b; k4 < e; k4 += 128) {
+        load4(k4 + 128, st_n, rt_n, pr_n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned long long k0 = k4 + 32u * j;
+            if (k0 >= e) break;
+            const uint32_t st = st_c[j], rt = rt_c[j], pr = pr_c[j];
+            if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;            // nothing pending in these 32 rows
+            k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
+            if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
+            const uint32_t g = (p.groups == 1) ? 0u : it.slot;
+            if (!SCATTER) {
+                // counting needs no order: one shared (or global) reduction per selected row
+                if (it.sel) atomicAdd((SMEM ? srow : grow) + g, 1u);
+                continue;
+            }
+            if (!__any_sync(FULL, it.sel)) continue;
+            const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
+            const uint32_t peers = __match_any_sync(FULL, key);
+            if (it.sel) {
+                // the lowest lane of each group claims room for the whole group; stable rank inside the group = popc below
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const uint32_t pos = p.goff[g] + base + __popc(peers & ((1u << lane) - 1u));
                 if (pos < p.cap) { p.out_rid[pos] = it.rid; p.out_slot[pos] = it.slot; }
             }
-            __syncwarp(peers);
-            if (rank == 0) *cell = base + __popc(peers);
         }
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st_c[j] = st_n[j]; rt_c[j] = rt_n[j]; pr_c[j] = pr_n[j]; }
     }
     if (SMEM && !SCATTER) {
         __syncwarp();
@@ -740,16 +757,20 @@ __global__ void __launch_bounds__(256) k3_seg_sum(const agr_k3_params p, uint32_
     if (g >= p.groups) return;
     const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
     uint32_t sum = 0;
-    for (uint32_t w = w0; w < w1; ++w) sum += p.matrix[(size_t)w * p.groups + g];
+#pragma unroll 8
+    for (uint32_t w = w0; w < w1; ++w) sum += __ldcg(&p.matrix[(size_t)w * p.groups + g]);
     partial[(size_t)seg * p.groups + g] = sum;
 }
 __global__ void __launch_bounds__(256) k3_seg_scan(const agr_k3_params p, uint32_t* __restrict__ partial) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.groups) return;
     uint32_t run = 0;
-    for (uint32_t seg = 0; seg < K3_SEGS; ++seg) {
-        uint32_t* c = partial + (size_t)seg * p.groups + g;
-        const uint32_t v = *c; *c = run; run += v;
+    for (uint32_t s0 = 0; s0 < K3_SEGS; s0 += 8) {               // eight independent loads, then the serial prefix
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = partial[(size_t)(s0 + k) * p.groups + g];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { partial[(size_t)(s0 + k) * p.groups + g] = run; run += v[k]; }
     }
     p.gtotal[g] = run;
 }
@@ -758,9 +779,12 @@ __global__ void __launch_bounds__(256) k3_seg_apply(const agr_k3_params p, const
     if (g >= p.groups) return;
     const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
     uint32_t run = partial[(size_t)seg * p.groups + g];
-    for (uint32_t w = w0; w < w1; ++w) {
-        uint32_t* cell = p.matrix + (size_t)w * p.groups + g;
-        const uint32_t c = *cell; *cell = run; run += c;
+    for (uint32_t wb = w0; wb < w1; wb += 8) {                   // eight independent loads, then the serial prefix
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (wb + k < w1) ? p.matrix[(size_t)(wb + k) * p.groups + g] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (wb + k < w1) { p.matrix[(size_t)(wb + k) * p.groups + g] = run; run += v[k]; }
     }
 }
 static void k3_scan_groups_launch(const agr_k3_params& p, cudaStream_t st) {
