@@ -160,6 +160,12 @@ def test_ring_full_then_reclaimed():
         assert eng.ingest_ex(recs, out, ids) == 1024                          # row ids keep counting
         assert eng.get_record_json(AGENTS[0], bytes(ids[5])) is not None
         assert eng.pending_json(AGENTS[0])[1] == 256
+        # row ranges are addressed by row id wherever the rows physically are (1024.. live in physical rows 0..)
+        blob, offs = eng.rows_json(1024, 256)
+        for i in (0, 1, 100, 255):
+            assert blob[int(offs[i]):int(offs[i + 1])] == eng.get_record_json(AGENTS[0], bytes(ids[i]))
+        st_words = eng.debug_read("state", 1024, 256)
+        assert (st_words & 0x20).all()                                        # ST_STORED
         # a batch that would wrap skips to the start of the slab
         small = recs[:200]
         o2 = np.zeros(200, dtype=A.verdict_dtype); i2 = np.zeros((200, 16), dtype=np.uint8)
