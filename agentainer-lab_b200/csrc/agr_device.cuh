@@ -201,5 +201,7 @@ __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc
     }
     __syncthreads();
     if (threadIdx.x < K1_NLC && s_ctr[threadIdx.x]) atomicAdd(&d.ctr[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+    // per-batch note for k1_post: replay-flagged records need its "stored earlier?" pass
+    if (threadIdx.x == C_REPLAY && s_ctr[C_REPLAY]) atomicAdd(d.dupfix + 2, s_ctr[C_REPLAY]);
 }
 

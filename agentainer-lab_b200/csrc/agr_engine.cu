@@ -57,6 +57,7 @@ struct agr_handle {
     uint64_t tail = 0;        // ring: first logical row that has not been released
     uint32_t* d_log_scratch = nullptr; uint32_t* d_lc_chunks = nullptr;   // ring: log compaction
     uint64_t released_total = 0;
+    uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
     // host agent map + mirror
     std::unordered_map<std::string, uint32_t> slot_of;
@@ -322,7 +323,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.failed_log, c.log_entries, false));
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
-    TRY(dev_alloc(h, &d.dupfix, (size_t)2, true));
+    TRY(dev_alloc(h, &d.dupfix, (size_t)8, true));
+    h->dupfix_base = d.dupfix; d.dupfix_next = d.dupfix + 4;
     if (c.flags & AGR_CFG_RING) {
         TRY(dev_alloc(h, &h->d_log_scratch, c.log_entries, false));
         TRY(dev_alloc(h, &h->d_lc_chunks, (size_t)(c.log_entries / 1024 + 4), false));
@@ -534,8 +536,15 @@ static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
     return 0;
 }
 
+// every K1 batch gets a zeroed set of per-batch words; the set it does not use is cleared by its k1_post for the next one
+static inline void flip_batch_words(agr_handle* h) {
+    h->batch_phase ^= 1u;
+    h->d.dupfix = h->dupfix_base + 4u * h->batch_phase;
+    h->d.dupfix_next = h->dupfix_base + 4u * (h->batch_phase ^ 1u);
+}
 static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* d_out, uint8_t* d_ids = nullptr) {
     sync_window(h);
+    flip_batch_words(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
         if (h->tev.empty()) {
@@ -1017,7 +1026,7 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
     if (is_pinned(offsets)) CK(cudaMemcpyAsync(h->d_voffsets, offsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
     else { memcpy(h->h_voffsets, offsets, ((size_t)n + 1) * 4); CK(cudaMemcpyAsync(h->d_voffsets, h->h_voffsets, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st)); }
     sync_window(h);
-    CK(cudaMemsetAsync(h->d.dupfix, 0, 8, st));
+    flip_batch_words(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->cfg.flags & AGR_CFG_TIMING) {
         if (h->tev.empty()) { h->tev.resize(2 * AGR_TIMING_RING); for (auto& e : h->tev) CK(cudaEventCreate(&e)); }

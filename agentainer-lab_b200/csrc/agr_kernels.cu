@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts,
                                                uint4* __restrict__ ids) {
     const uint32_t dupfix = __ldcg(d.dupfix);
+    if (blockIdx.x == 0 && threadIdx.x < 4) d.dupfix_next[threadIdx.x] = 0;      // the previous batch is done with these words
+    // nothing to do: no in-batch id races, no replay-flagged records to resolve, nobody asked for verdicts or ids
+    if (dupfix == 0u && __ldcg(d.dupfix + 2) == 0u && verdicts == nullptr && ids == nullptr) return;
     const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     uint32_t hits = 0;
@@ -389,7 +392,6 @@ void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
                    cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, void* verdicts, void* ids) {
     if (n == 0) return;
-    cudaMemsetAsync(d.dupfix, 0, 2 * sizeof(uint32_t), st);    // [0] duplicate-race counter, [1] tile counter
     if (ev0) cudaEventRecord(ev0, st);
     if ((variant & 0xfu) != AGR_K1_LSU && tmap != nullptr) {
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);

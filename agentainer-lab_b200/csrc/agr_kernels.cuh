@@ -28,7 +28,8 @@ struct agr_dev {
     uint32_t* failed_log;
     unsigned long long* log_len;   // [0] completed, [1] failed
     unsigned long long log_cap;
-    uint32_t* dupfix;          // in-batch duplicate-id race counter (see k1_post)
+    uint32_t* dupfix;          // per-batch words: [0] in-batch duplicate-id races (see k1_post), [1] spare, [2] replay-flagged records
+    uint32_t* dupfix_next;     // the other copy of those words: k1_post clears it for the next batch (no memset between batches)
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
     unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
     unsigned long long* mtime; // [rows] time of the latest SET of the record by K2 (0: only StoreRequest's, = the record's seq)
