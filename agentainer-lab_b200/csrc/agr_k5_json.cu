@@ -144,7 +144,13 @@ struct jwriter {
         if (EMIT && fill >= K5_FLUSH) flush(false);
     }
     __device__ __forceinline__ void lit(unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d, uint32_t k) {
-        if (EMIT && (uint32_t)lane < k) sb[fill + lane] = (uint8_t)pick_byte(a, b, c, d, lane);
+        if (EMIT && (uint32_t)lane < k) {                        // k is a compile-time constant at every call site
+            uint32_t ch_;
+            if (k <= 8) ch_ = (uint32_t)(a >> (8 * (lane & 7)));
+            else if (k <= 16) ch_ = (uint32_t)(((lane & 8) ? b : a) >> (8 * (lane & 7)));
+            else ch_ = pick_byte(a, b, c, d, lane);
+            sb[fill + lane] = (uint8_t)ch_;
+        }
         commit(k);
     }
     __device__ __forceinline__ void ch(char c) {
@@ -340,14 +346,13 @@ __device__ __forceinline__ void put_base64(jwriter<EMIT>& w, const uint8_t* s, u
             const uint32_t p = 3u * g;
             const uint32_t b0 = s[p], b1 = p + 1 < len ? s[p + 1] : 0u, b2 = p + 2 < len ? s[p + 2] : 0u;
             const uint32_t v = (b0 << 16) | (b1 << 8) | b2;
-            uint32_t out = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t x = (v >> (18 - 6 * k)) & 63u;
-                // 'A'+x | 'a'+x-26 | '0'+x-52 | '+' | '/' as one running offset
-                const uint32_t c = x + 65u + (x >= 26u ? 6u : 0u) - (x >= 52u ? 75u : 0u) - (x >= 62u ? 15u : 0u) + (x >= 63u ? 3u : 0u);
-                out |= c << (8 * k);
-            }
+            // the four 6-bit values, one per byte, mapped to their characters together (SWAR): a byte holds x < 64, so
+            // x + (128 - t) sets bit 7 exactly when x >= t and never carries into the next byte; the character is
+            // x + 'A', + 6 from 'a' on, - 75 from '0' on, - 15 for '+', + 3 for '/' — no byte borrows at any step.
+            const uint32_t X = ((v >> 18) & 63u) | (((v >> 12) & 63u) << 8) | (((v >> 6) & 63u) << 16) | ((v & 63u) << 24);
+            const uint32_t ge26 = ((X + 0x66666666u) >> 7) & 0x01010101u, ge52 = ((X + 0x4c4c4c4cu) >> 7) & 0x01010101u,
+                           ge62 = ((X + 0x42424242u) >> 7) & 0x01010101u, ge63 = ((X + 0x41414141u) >> 7) & 0x01010101u;
+            uint32_t out = X + 0x41414141u + 6u * ge26 + 3u * ge63 - 75u * ge52 - 15u * ge62;
             if (p + 1 >= len) out = (out & 0x0000ffffu) | ((uint32_t)'=' << 16) | ((uint32_t)'=' << 24);
             else if (p + 2 >= len) out = (out & 0x00ffffffu) | ((uint32_t)'=' << 24);
             uint8_t* dst = w.sb + w.fill + 4u * w.lane;
