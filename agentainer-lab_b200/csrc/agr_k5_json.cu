@@ -158,8 +158,18 @@ struct jwriter {
         commit(1);
     }
     __device__ __forceinline__ void uint(uint32_t v) {           // v < 100000 (status codes, retry counters)
+        if (v < 1000u) {                                         // the usual case: three digits at most
+            const uint32_t d2 = v / 100u, r = v - 100u * d2, d1 = r / 10u, d0 = r - 10u * d1;
+            const uint32_t nd = 1u + (v >= 10u) + (v >= 100u);
+            if (EMIT && (uint32_t)lane < nd) {
+                const uint32_t pos = nd - 1u - (uint32_t)lane;   // 0 = units
+                sb[fill + lane] = (uint8_t)('0' + (pos == 0u ? d0 : pos == 1u ? d1 : d2));
+            }
+            commit(nd);
+            return;
+        }
         const uint32_t d4 = v / 10000u, d3 = v / 1000u % 10u, d2 = v / 100u % 10u, d1 = v / 10u % 10u, d0 = v % 10u;
-        const uint32_t nd = v >= 10000u ? 5u : v >= 1000u ? 4u : v >= 100u ? 3u : v >= 10u ? 2u : 1u;
+        const uint32_t nd = v >= 10000u ? 5u : 4u;
         if (EMIT && (uint32_t)lane < nd) {
             const unsigned long long digs = (unsigned long long)d0 | ((unsigned long long)d1 << 8) | ((unsigned long long)d2 << 16) |
                                             ((unsigned long long)d3 << 24) | ((unsigned long long)d4 << 32);

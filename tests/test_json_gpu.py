@@ -160,3 +160,20 @@ def test_engine_matches_the_committed_stream():
         for a in AGENTS:
             got, cnt = eng.pending_json(a)
             assert hashlib.sha256(got).hexdigest() == want["pending_sha256"][a] and cnt == want["pending_counts"][a]
+
+
+@pytest.mark.parametrize("code", [7, 99, 100, 999, 1000, 9999, 10000, 65535])
+def test_status_code_digits(code):
+    """Response.StatusCode is an int in the reference; every digit count the 16-bit field can hold."""
+    reqs = make_requests(6, 1, AGENTS[:1])
+    with A.Engine(slab_rows=1 << 10, max_agents=8, flags=MODES["mint"]) as eng:
+        eng.set_agent_state(AGENTS[0], K.AGR_AGENT_RUNNING)
+        out = np.zeros(1, dtype=A.verdict_dtype); ids = np.zeros((1, 16), dtype=np.uint8)
+        eng.ingest_ex(records_array(reqs), out, ids)
+        outs = np.zeros(1, dtype=A.outcome_dtype)
+        outs[0]["request_id"] = ids[0]; outs[0]["agent_id"] = AGENTS[0].encode()
+        outs[0]["kind"], outs[0]["http_status"], outs[0]["seq"] = K.AGR_OUT_RESPONSE, code, 1_700_000_000_000_000_000
+        assert eng.complete(outs)[0] == 0
+        d = json.loads(eng.get_record_json(AGENTS[0], bytes(ids[0])))
+        assert d["response"]["status_code"] == code and d["status"] == "completed"
+        assert d["processed_at"] == d["response"]["received_at"] == "2023-11-14T22:13:20Z"
