@@ -122,17 +122,43 @@ typedef struct { char* p; size_t n, cap; } sbuf;
 static void sb_need(sbuf* b, size_t m) { if (b->n + m > b->cap) { b->cap = (b->n + m) * 2 + 64; b->p = (char*)realloc(b->p, b->cap); } }
 static void sb_put(sbuf* b, const char* s, size_t m) { sb_need(b, m); memcpy(b->p + b->n, s, m); b->n += m; }
 static void sb_str(sbuf* b, const char* s) { sb_put(b, s, strlen(s)); }
-static void sb_jstr(sbuf* b, const char* s, size_t m) {    /* encoding/json string escaping incl. HTML-safe escapes */
+/* unicode/utf8.DecodeRune at s[i..m): width of the valid sequence starting there, 0 if the byte starts none */
+static int utf8_width(const unsigned char* s, size_t i, size_t m) {
+    unsigned char c = s[i]; int need; unsigned lo = 0x80, hi = 0xbf;
+    if (c < 0x80) return 1;
+    if (c >= 0xc2 && c <= 0xdf) need = 2;
+    else if (c >= 0xe0 && c <= 0xef) { need = 3; if (c == 0xe0) lo = 0xa0; else if (c == 0xed) hi = 0x9f; }
+    else if (c >= 0xf0 && c <= 0xf4) { need = 4; if (c == 0xf0) lo = 0x90; else if (c == 0xf4) hi = 0x8f; }
+    else return 0;
+    if (i + (size_t)need > m) return 0;
+    if (s[i + 1] < lo || s[i + 1] > hi) return 0;
+    for (int k = 2; k < need; ++k) if (s[i + k] < 0x80 || s[i + k] > 0xbf) return 0;
+    return need;
+}
+static void sb_jstr(sbuf* b, const char* s_, size_t m) {   /* encoding/json encodeState.string, escapeHTML = true (Go 1.23) */
     static const char hex[] = "0123456789abcdef";
+    const unsigned char* s = (const unsigned char*)s_;
     sb_need(b, m * 6 + 2); b->p[b->n++] = '"';
-    for (size_t i = 0; i < m; ++i) {
-        unsigned char c = (unsigned char)s[i];
-        if (c == '"' || c == '\\') { b->p[b->n++] = '\\'; b->p[b->n++] = (char)c; }
-        else if (c == '\n') { b->p[b->n++] = '\\'; b->p[b->n++] = 'n'; }
-        else if (c == '\r') { b->p[b->n++] = '\\'; b->p[b->n++] = 'r'; }
-        else if (c == '\t') { b->p[b->n++] = '\\'; b->p[b->n++] = 't'; }
-        else if (c < 0x20 || c == '<' || c == '>' || c == '&') { memcpy(b->p + b->n, "\\u00", 4); b->n += 4; b->p[b->n++] = hex[c >> 4]; b->p[b->n++] = hex[c & 15]; }
-        else b->p[b->n++] = (char)c;
+    for (size_t i = 0; i < m;) {
+        unsigned char c = s[i];
+        if (c < 0x80) {
+            if (c == '"' || c == '\\') { b->p[b->n++] = '\\'; b->p[b->n++] = (char)c; }
+            else if (c == '\n') { b->p[b->n++] = '\\'; b->p[b->n++] = 'n'; }
+            else if (c == '\r') { b->p[b->n++] = '\\'; b->p[b->n++] = 'r'; }
+            else if (c == '\t') { b->p[b->n++] = '\\'; b->p[b->n++] = 't'; }
+            else if (c == '\b') { b->p[b->n++] = '\\'; b->p[b->n++] = 'b'; }
+            else if (c == '\f') { b->p[b->n++] = '\\'; b->p[b->n++] = 'f'; }
+            else if (c < 0x20 || c == '<' || c == '>' || c == '&') { memcpy(b->p + b->n, "\\u00", 4); b->n += 4; b->p[b->n++] = hex[c >> 4]; b->p[b->n++] = hex[c & 15]; }
+            else b->p[b->n++] = (char)c;
+            i++;
+            continue;
+        }
+        int w = utf8_width(s, i, m);
+        if (w == 0) { memcpy(b->p + b->n, "\\ufffd", 6); b->n += 6; i++; continue; }      /* RuneError, width 1 */
+        if (w == 3 && c == 0xe2 && s[i + 1] == 0x80 && (s[i + 2] == 0xa8 || s[i + 2] == 0xa9)) {
+            memcpy(b->p + b->n, s[i + 2] == 0xa8 ? "\\u2028" : "\\u2029", 6); b->n += 6; i += 3; continue;
+        }
+        memcpy(b->p + b->n, s + i, (size_t)w); b->n += (size_t)w; i += (size_t)w;
     }
     b->p[b->n++] = '"';
 }
@@ -152,8 +178,16 @@ static void uuid_text(const uint8_t id[16], char out[37]) {
 }
 static int hexv(char c) { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; }
 static void uuid_parse(const char* t, uint8_t id[16]) { int o = 0; for (int i = 0; i < 16; ++i) { if (t[o] == '-') o++; id[i] = (uint8_t)((hexv(t[o]) << 4) | hexv(t[o + 1])); o += 2; } }
-static void sb_time(sbuf* b, uint64_t seq) {               /* RFC3339Nano stand-in carrying the logical time */
-    char t[48]; int m = snprintf(t, sizeof t, "\"2025-01-01T00:00:%02u.%09uZ\"", (unsigned)((seq / 1000000000ULL) % 60), (unsigned)(seq % 1000000000ULL));
+static void sb_time(sbuf* b, uint64_t ns) {                 /* time.Unix(0, ns).UTC().MarshalJSON(): RFC3339Nano */
+    uint64_t secs = ns / 1000000000ULL; unsigned frac = (unsigned)(ns % 1000000000ULL);
+    uint64_t days = secs / 86400ULL; unsigned sod = (unsigned)(secs % 86400ULL);
+    int64_t z = (int64_t)days + 719468; int64_t era = z / 146097; unsigned doe = (unsigned)(z - era * 146097);
+    unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365; unsigned y = yoe + (unsigned)era * 400;
+    unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100); unsigned mp = (5 * doy + 2) / 153;
+    unsigned d = doy - (153 * mp + 2) / 5 + 1; unsigned mth = mp < 10 ? mp + 3 : mp - 9; if (mth <= 2) y++;
+    char t[64]; int m = snprintf(t, sizeof t, "\"%04u-%02u-%02uT%02u:%02u:%02u", y, mth, d, sod / 3600, sod / 60 % 60, sod % 60);
+    if (frac) { char f[16]; snprintf(f, sizeof f, "%09u", frac); int k = 9; while (k > 0 && f[k - 1] == '0') k--; t[m++] = '.'; memcpy(t + m, f, (size_t)k); m += k; }
+    t[m++] = 'Z'; t[m++] = '"';
     sb_put(b, t, (size_t)m);
 }
 static const char* status_name(int s) { return s == AGR_ST_PENDING ? "pending" : s == AGR_ST_PROCESSING ? "processing" : s == AGR_ST_COMPLETED ? "completed" : s == AGR_ST_FAILED ? "failed" : ""; }
@@ -184,13 +218,13 @@ static void marshal_request(sbuf* b, const reqdoc* d) {
         h = nl + 1;
     }
     sb_str(b, "},\"body\":");
-    if (r->body_len) sb_b64(b, r->payload + r->path_len + r->hdr_len, r->body_len); else sb_str(b, "null");
+    sb_b64(b, r->payload + r->path_len + r->hdr_len, r->body_len);       /* io.ReadAll: a non-nil empty slice is "" */
     sb_str(b, ",\"status\":\""); sb_str(b, status_name(r->status));
     char t[96]; int m = snprintf(t, sizeof t, "\",\"retry_count\":%u,\"max_retries\":%u,\"created_at\":", r->retry_count, r->max_retries);
     sb_put(b, t, (size_t)m); sb_time(b, r->seq);
     if (d->processed_at || d->has_response) { sb_str(b, ",\"processed_at\":"); sb_time(b, d->processed_at); }
     if (d->has_response) {
-        m = snprintf(t, sizeof t, ",\"response\":{\"status_code\":%u,\"headers\":{},\"body\":null,\"received_at\":", d->resp_status);
+        m = snprintf(t, sizeof t, ",\"response\":{\"status_code\":%u,\"headers\":{},\"body\":\"\",\"received_at\":", d->resp_status);
         sb_put(b, t, (size_t)m); sb_time(b, d->received_at); sb_put(b, "}", 1);
     }
     if (d->error[0]) { sb_str(b, ",\"error\":"); sb_jstr(b, d->error, strlen(d->error)); }
@@ -206,8 +240,13 @@ static size_t j_string(jr* j, char* out, size_t cap) {   /* decodes escapes; ret
         char c = *j->p++;
         if (c == '\\') {
             char x = *j->p++;
-            if (x == 'n') c = '\n'; else if (x == 't') c = '\t'; else if (x == 'r') c = '\r';
-            else if (x == 'u') { c = (char)((hexv(j->p[2]) << 4) | hexv(j->p[3])); j->p += 4; }
+            if (x == 'n') c = '\n'; else if (x == 't') c = '\t'; else if (x == 'r') c = '\r'; else if (x == 'b') c = '\b'; else if (x == 'f') c = '\f';
+            else if (x == 'u') {                                  /* \uXXXX -> UTF-8 (encoding/json writes no surrogate pairs here) */
+                unsigned cp = (unsigned)((hexv(j->p[0]) << 12) | (hexv(j->p[1]) << 8) | (hexv(j->p[2]) << 4) | hexv(j->p[3])); j->p += 4;
+                if (cp < 0x80) c = (char)cp;
+                else if (cp < 0x800) { if (n < cap) out[n] = (char)(0xc0 | (cp >> 6)); n++; c = (char)(0x80 | (cp & 0x3f)); }
+                else { if (n < cap) out[n] = (char)(0xe0 | (cp >> 12)); n++; if (n < cap) out[n] = (char)(0x80 | ((cp >> 6) & 0x3f)); n++; c = (char)(0x80 | (cp & 0x3f)); }
+            }
             else c = x;
         }
         if (n < cap) out[n] = c;
@@ -224,7 +263,16 @@ static size_t j_b64(jr* j, uint8_t* out, size_t cap) {
     return n;
 }
 static uint64_t j_uint(jr* j) { uint64_t v = 0; while (j->p < j->e && *j->p >= '0' && *j->p <= '9') v = v * 10 + (uint64_t)(*j->p++ - '0'); return v; }
-static uint64_t j_time(jr* j) { char t[48]; size_t n = j_string(j, t, sizeof t - 1); t[n < 47 ? n : 47] = 0; unsigned s = 0, ns = 0; sscanf(t + 17, "%2u.%9u", &s, &ns); return (uint64_t)s * 1000000000ULL + ns; }
+static uint64_t j_time(jr* j) {                             /* time.Time.UnmarshalJSON of the form sb_time writes */
+    char t[48]; size_t n = j_string(j, t, sizeof t - 1); t[n < 47 ? n : 47] = 0;
+    unsigned y = 0, mo = 0, d = 0, hh = 0, mi = 0, ss = 0; uint64_t frac = 0;
+    sscanf(t, "%4u-%2u-%2uT%2u:%2u:%2u", &y, &mo, &d, &hh, &mi, &ss);
+    if (t[19] == '.') { int k = 0; for (const char* q = t + 20; *q >= '0' && *q <= '9'; ++q, ++k) frac = frac * 10 + (uint64_t)(*q - '0'); for (; k < 9; ++k) frac *= 10; }
+    int64_t yy = (int64_t)y - (mo <= 2); int64_t era = yy / 400; unsigned yoe = (unsigned)(yy - era * 400);
+    unsigned doy = (153 * (mo > 2 ? mo - 3 : mo + 9) + 2) / 5 + d - 1; unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    int64_t days = era * 146097 + (int64_t)doe - 719468;
+    return ((uint64_t)days * 86400ULL + hh * 3600ULL + mi * 60ULL + ss) * 1000000000ULL + frac;
+}
 static void j_skip(jr* j) {
     j_ws(j);
     if (*j->p == '"') { char d[1]; j_string(j, d, 0); return; }
@@ -491,3 +539,15 @@ int cref_list(cref* c, const char* agent_id, int which, uint8_t (*ids)[16], uint
     return 0;
 }
 uint64_t cref_keys(cref* c) { return c->ks.used; }
+/* the value of agent:{a}:requests:{r} as it sits in the keyspace (what storage.Get returns, server.go:661-662) */
+int cref_get_json(cref* c, const char* agent_id, const uint8_t request_id[16], char* out, uint32_t cap, uint32_t* len) {
+    char key[128], idt[37];
+    uuid_text(request_id, idt);
+    int kl = rec_key(key, sizeof key, agent_id, idt);
+    kent* e = r_get(&c->ks, key, (uint32_t)kl);
+    if (!e) return AGR_ENOTFOUND;
+    *len = e->vlen;
+    if (e->vlen > cap) return AGR_ECAP;
+    memcpy(out, e->val, e->vlen);
+    return 0;
+}

@@ -40,6 +40,7 @@ def load():
         lib.cref_get_record.restype, lib.cref_get_record.argtypes = C.c_int, [vp, C.c_char_p, vp, vp]
         lib.cref_list.restype, lib.cref_list.argtypes = C.c_int, [vp, C.c_char_p, C.c_int, vp, u32, C.POINTER(u32)]
         lib.cref_keys.restype, lib.cref_keys.argtypes = C.c_uint64, [vp]
+        lib.cref_get_json.restype, lib.cref_get_json.argtypes = C.c_int, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]
         _lib = lib
     return _lib
 
@@ -107,6 +108,14 @@ class CRef:
         rid = np.frombuffer(request_id, dtype=np.uint8).copy()
         rc = self.lib.cref_get_record(self.h, agent_id.encode(), _p(rid), _p(out))
         return None if rc == AGR_ENOTFOUND else out[0]
+
+    def get_json(self, agent_id, request_id):
+        """The stored value of agent:{a}:requests:{r}: the C port's own json.Marshal(request), after every round trip."""
+        out = np.zeros(1 << 14, dtype=np.uint8)
+        rid = np.frombuffer(request_id, dtype=np.uint8).copy()
+        n = C.c_uint32()
+        rc = self.lib.cref_get_json(self.h, agent_id.encode(), _p(rid), _p(out), out.size, C.byref(n))
+        return None if rc == AGR_ENOTFOUND else out[: n.value].tobytes()
 
     def list(self, agent_id, which, cap=1 << 12):
         while True:

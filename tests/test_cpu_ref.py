@@ -57,3 +57,48 @@ def test_config1_stream_c_port_equals_python_oracle():
     assert_same(ref, got)
     # the scenario's records are byte-identical to the synthetic stream's
     assert make_records([synth_to_req(recs[7])]).tobytes() == recs[7:8].tobytes()
+
+
+def test_two_restatements_of_the_wire_form_agree():
+    """oracle/cpu_ref.c keeps every record as JSON TEXT in its keyspace and really parses and re-marshals it on each update
+    (like the Go code); oracle/model.py + oracle/gojson.py keep dicts and carry the round trip in their types.  On a stream
+    with awkward strings (quotes, HTML characters, control bytes, invalid UTF-8, U+2028) and several updates per record the two
+    must produce the same bytes."""
+    import numpy as np
+    from jsoncase import make_requests, records_array
+    from oracle import gojson as G, model as M
+    from oracle.cpu_ref import CRef, record_dtype
+    from agentainer_lab_b200 import constants as K, outcome_dtype
+    agents = ["agent-1700000000000000001", "agent-1700000000000000002"]
+    reqs = make_requests(31, 300, agents, max_payload=330)         # room for invalid bytes growing to EF BF BD after a round trip
+    for r in reqs:                                                 # the C port parses times back: keep them in its supported range
+        r.now = 1_700_000_000_000_000_000 + (r.now % 10**15)
+    c = CRef()
+    redis = M.MiniRedis(); mgr = M.Manager(redis)
+    for a in agents:
+        c.set_agent_state(a, "running")
+    recs = records_array(reqs).astype(record_dtype)
+    c.ingest(recs)
+    for r in reqs:
+        mgr.store_request(r.agent_id, M.HttpRequest(r.method, r.path, dict(r.headers), r.body, new_id=G.format_uuid(r.rid), now=r.now))
+    import random
+    rng = random.Random(5)
+    ops = [(rng.randrange(len(reqs)), rng.random() < 0.6, 1_700_000_000_000_000_000 + rng.randrange(10**12) * 1000 + rng.choice([0, 0, 1, 500]))
+           for _ in range(500)]
+    for i, is_resp, t in ops:
+        r = reqs[i]
+        out = np.zeros(1, dtype=outcome_dtype)
+        out[0]["request_id"] = np.frombuffer(r.rid, dtype=np.uint8); out[0]["agent_id"] = r.agent_id.encode()
+        out[0]["kind"], out[0]["http_status"], out[0]["seq"] = (K.AGR_OUT_RESPONSE, 200, t) if is_resp else (K.AGR_OUT_ERROR, 0, t)
+        c.complete(out)
+        if is_resp:
+            mgr.store_response(r.agent_id, G.format_uuid(r.rid), M.HttpResponse(200, {}, b"", now=t))
+        else:
+            mgr.mark_request_failed(r.agent_id, G.format_uuid(r.rid), "transport error")
+    checked = 0
+    for r in reqs:
+        want = G.marshal_request(redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}"))
+        assert c.get_json(r.agent_id, r.rid) == want, (r, c.get_json(r.agent_id, r.rid), want)
+        checked += 1
+    assert checked == 300
+    c.close()
