@@ -539,6 +539,24 @@ int cref_list(cref* c, const char* agent_id, int which, uint8_t (*ids)[16], uint
     return 0;
 }
 uint64_t cref_keys(cref* c) { return c->ks.used; }
+/* json.Marshal(GetPendingRequests(agent)) — the "pending" member of GET /agents/{id}/requests (server.go:638-650): every
+ * record is unmarshalled by GetPendingRequests and marshalled again by the handler; a nil slice is null */
+int cref_pending_json(cref* c, const char* agent_id, char* out, uint32_t cap, uint32_t* len) {
+    reqdoc* docs; uint32_t m = pending_of(c, agent_id, &docs);
+    sbuf all = {0, 0, 0}, one = {0, 0, 0};
+    if (m == 0) sb_str(&all, "null");
+    else {
+        sb_put(&all, "[", 1);
+        for (uint32_t i = 0; i < m; ++i) { if (i) sb_put(&all, ",", 1); marshal_request(&one, &docs[i]); sb_put(&all, one.p, one.n); }
+        sb_put(&all, "]", 1);
+    }
+    free(docs);
+    *len = (uint32_t)all.n;
+    int rc = 0;
+    if (all.n > cap) rc = AGR_ECAP; else memcpy(out, all.p, all.n);
+    free(all.p); free(one.p);
+    return rc;
+}
 /* the value of agent:{a}:requests:{r} as it sits in the keyspace (what storage.Get returns, server.go:661-662) */
 int cref_get_json(cref* c, const char* agent_id, const uint8_t request_id[16], char* out, uint32_t cap, uint32_t* len) {
     char key[128], idt[37];

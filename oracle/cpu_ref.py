@@ -41,6 +41,7 @@ def load():
         lib.cref_list.restype, lib.cref_list.argtypes = C.c_int, [vp, C.c_char_p, C.c_int, vp, u32, C.POINTER(u32)]
         lib.cref_keys.restype, lib.cref_keys.argtypes = C.c_uint64, [vp]
         lib.cref_get_json.restype, lib.cref_get_json.argtypes = C.c_int, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]
+        lib.cref_pending_json.restype, lib.cref_pending_json.argtypes = C.c_int, [vp, C.c_char_p, vp, u32, C.POINTER(u32)]
         _lib = lib
     return _lib
 
@@ -116,6 +117,17 @@ class CRef:
         n = C.c_uint32()
         rc = self.lib.cref_get_json(self.h, agent_id.encode(), _p(rid), _p(out), out.size, C.byref(n))
         return None if rc == AGR_ENOTFOUND else out[: n.value].tobytes()
+
+    def pending_json(self, agent_id):
+        cap = 1 << 20
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            n = C.c_uint32()
+            rc = self.lib.cref_pending_json(self.h, agent_id.encode(), _p(out), cap, C.byref(n))
+            if rc == AGR_ECAP:
+                cap = int(n.value)
+                continue
+            return out[: n.value].tobytes()
 
     def list(self, agent_id, which, cap=1 << 12):
         while True:

@@ -101,4 +101,6 @@ def test_two_restatements_of_the_wire_form_agree():
         assert c.get_json(r.agent_id, r.rid) == want, (r, c.get_json(r.agent_id, r.rid), want)
         checked += 1
     assert checked == 300
+    for a in agents + ["agent-nobody"]:
+        assert c.pending_json(a) == G.marshal_list(mgr.get_pending_requests(a))
     c.close()
