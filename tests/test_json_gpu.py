@@ -177,3 +177,40 @@ def test_status_code_digits(code):
         d = json.loads(eng.get_record_json(AGENTS[0], bytes(ids[0])))
         assert d["response"]["status_code"] == code and d["status"] == "completed"
         assert d["processed_at"] == d["response"]["received_at"] == "2023-11-14T22:13:20Z"
+
+
+def test_wire_form_against_the_c_restatement_at_scale():
+    """100 k records of the synthetic stream, half of them answered or failed: every record's wire form from the engine
+    (one agr_rows_json call, 391 chunks of offsets) equals the value the C restatement holds in its keyspace."""
+    from oracle.cpu_ref import CRef, record_dtype as cref_record
+    n, na = 100_000, 64
+    recs = A.synth_fill_host(0, n, seed=9, n_agents=na)
+    names = [A.synth_agent_id(k) for k in range(na)]
+    rng = np.random.default_rng(3)
+    with A.Engine(slab_rows=1 << 17, max_agents=128, flags=MODES["hash"]) as eng:
+        c = CRef()
+        eng.set_agent_states(names, ["running"] * na)
+        for nm in names:
+            c.set_agent_state(nm, "running")
+        out = np.zeros(n, dtype=A.verdict_dtype); ids = np.zeros((n, 16), dtype=np.uint8)
+        first = eng.ingest_ex(recs, out, ids)
+        c.ingest(recs.astype(cref_record))
+        pick = rng.permutation(n)[: n // 2]
+        outs = np.zeros(len(pick), dtype=A.outcome_dtype)
+        outs["request_id"] = recs["request_id"][pick]; outs["agent_id"] = recs["agent_id"][pick]
+        is_resp = rng.random(len(pick)) < 0.7
+        outs["kind"] = np.where(is_resp, K.AGR_OUT_RESPONSE, K.AGR_OUT_ERROR)
+        outs["http_status"] = np.where(is_resp, rng.choice([200, 201, 404, 500], len(pick)), 0)
+        outs["seq"] = 1_000_000 + np.arange(len(pick))
+        assert (eng.complete(outs) == 0).all()
+        c.complete(outs)
+        blob, offs = eng.rows_json(first, n)
+        bad = 0
+        for i in range(n):
+            want = c.get_json(recs["agent_id"][i].decode(), recs["request_id"][i].tobytes())
+            if blob[int(offs[i]):int(offs[i + 1])] != want:
+                bad += 1
+                if bad < 3:
+                    print(i, blob[int(offs[i]):int(offs[i + 1])], want)
+        assert bad == 0
+        c.close()
