@@ -79,3 +79,36 @@ def test_null_arguments_are_rejected(lib):
     assert lib.agr_complete(None, None, 0, None) == K.AGR_EINVAL
     assert lib.agr_replay_scan(None, None, None, 0, C.byref(n)) == K.AGR_EINVAL
     assert lib.agr_create(None, None) == K.AGR_EINVAL
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile a C program against include/agentainer_gpu.h that prints sizeof / offsetof of every struct the Python
+    harness mirrors, and compare with ctypes and numpy: a silent drift would corrupt stats or configs."""
+    import subprocess
+    from agentainer_lab_b200.binding import AgrStats, AgrExchangeInfo, AgrSynth
+    structs = {"agr_config": AgrConfig, "agr_stats": AgrStats, "agr_exchange_info": AgrExchangeInfo, "agr_synth": AgrSynth}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "agentainer_gpu.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    for cname, dt in (("agr_record", A.record_dtype), ("agr_outcome", A.outcome_dtype), ("agr_verdict", A.verdict_dtype),
+                      ("agr_dispatch", A.dispatch_dtype)):
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname in dt.names:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+    for cname, dt in (("agr_record", A.record_dtype), ("agr_outcome", A.outcome_dtype), ("agr_verdict", A.verdict_dtype),
+                      ("agr_dispatch", A.dispatch_dtype)):
+        assert int(got[cname]) == dt.itemsize, cname
+        for fname in dt.names:
+            assert int(got[f"{cname}.{fname}"]) == dt.fields[fname][1], f"{cname}.{fname}"
