@@ -112,3 +112,17 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(got[cname]) == dt.itemsize, cname
         for fname in dt.names:
             assert int(got[f"{cname}.{fname}"]) == dt.fields[fname][1], f"{cname}.{fname}"
+
+
+def test_integration_text_only_names_what_the_header_declares():
+    """The cgo shim in INTEGRATION.md cannot be compiled here (no Go toolchain); at least every C function, constant and
+    struct field it names must exist in the header it binds."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    syms = set(declared_symbols())
+    used = set(re.findall(r"\bC\.(agr_[a-z0-9_]+)\(", text))
+    assert used and used <= syms, sorted(used - syms)
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    for name in set(re.findall(r"\bC\.(AGR_[A-Z0-9_]+)\b", text)):
+        assert re.search(rf"\b{name}\b", body), name
+    for st in set(re.findall(r"\bC\.(agr_[a-z_]+)\{", text)) | set(re.findall(r"var \w+ C\.(agr_[a-z_]+)\b", text)):
+        assert re.search(rf"typedef struct {st}\b", body), st
