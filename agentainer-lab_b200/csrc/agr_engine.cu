@@ -91,7 +91,8 @@ struct agr_handle {
     std::vector<void*> dev_allocs, host_allocs;
     alignas(64) unsigned char tmap[128];       // CUtensorMap of the slab for the TMA K1 variants
     // stored responses: byte slab + per-row (offset, length), written off the hot path
-    uint8_t* d_resp = nullptr; uint64_t resp_used = 0, resp_cap = 0;
+    uint8_t* d_resp = nullptr; uint64_t resp_used = 0, resp_cap = 0;   // bytes appended so far (ring: logical, pads included) / capacity
+    uint64_t resp_tail = 0;                    // ring: logical offset of the oldest byte a live row still refers to
     unsigned long long* d_resp_off = nullptr; uint32_t* d_resp_len = nullptr;
     uint32_t* d_resp_hlen = nullptr;           // leading bytes of the stored response that are its flattened headers
     unsigned long long* d_err_off = nullptr; uint32_t* d_err_len = nullptr;   // Request.Error text, same byte slab
@@ -1172,9 +1173,22 @@ static int store_bytes_locked(agr_handle* h, const char* agent_id, const uint8_t
     uint32_t rid = 0;
     TRY(resolve_one_locked(h, agent_id, request_id, &rid));
     const uint32_t len = alen + blen;
-    if (h->resp_used + len > h->resp_cap) return fail(AGR_ENOSPC, "response slab full");
-    const unsigned long long off = h->resp_used;
-    h->resp_used += (len + 15u) & ~15ull;
+    const uint64_t need = ((uint64_t)len + 15u) & ~15ull;
+    unsigned long long off;
+    if (!is_ring(h)) {
+        if (h->resp_used + len > h->resp_cap) return fail(AGR_ENOSPC, "response slab full");
+        off = h->resp_used;
+        h->resp_used += need;
+    } else {                                                     // byte ring: a blob never wraps; agr_reclaim advances resp_tail
+        if (need > h->resp_cap / 2) return fail(AGR_ENOSPC, "response larger than half the response slab");
+        const uint64_t at = h->resp_used % h->resp_cap;
+        const uint64_t pad = (at + need > h->resp_cap) ? h->resp_cap - at : 0;
+        if (h->resp_used + pad + need - h->resp_tail > h->resp_cap)
+            return fail(AGR_ENOSPC, "response slab full: agr_reclaim releases the bytes of released rows");
+        h->resp_used += pad;
+        off = h->resp_used % h->resp_cap;                        // the rows keep PHYSICAL offsets
+        h->resp_used += need;
+    }
     if (alen) CK(cudaMemcpyAsync(h->d_resp + off, a, alen, cudaMemcpyHostToDevice, h->stream));
     if (blen) CK(cudaMemcpyAsync(h->d_resp + off + alen, b, blen, cudaMemcpyHostToDevice, h->stream));
     if (which == 0) {
@@ -1330,7 +1344,7 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 struct snap_header {
     char magic[8];                 // "AGRSNAP3"
     uint32_t flags, n_agents, shard, gen;
-    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total, tail, released_total, slab_rows, vtail, vcap;
+    uint64_t rows_used, vused, log_len[2], id_secret, scan_lo, resp_used, expired_total, tail, released_total, slab_rows, vtail, vcap, resp_tail, resp_cap;
 };
 static int dump_dev(agr_handle* h, FILE* f, const void* dsrc, size_t bytes) {
     const size_t chunk = h->bounce_bytes;
@@ -1365,7 +1379,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     hd.flags = h->cfg.flags & (AGR_CFG_PERSISTENCE | AGR_CFG_MINT_IDS | AGR_CFG_VARLEN | AGR_CFG_RING);
     hd.n_agents = (uint32_t)h->agent_names.size(); hd.shard = h->d.shard_id; hd.gen = h->d.id_gen;
     hd.rows_used = h->rows_used; hd.vused = h->vused; hd.id_secret = h->d.id_secret; hd.scan_lo = h->scan_lo;
-    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total; hd.tail = h->tail; hd.released_total = h->released_total; hd.slab_rows = h->cfg.slab_rows; hd.vtail = h->vtail; hd.vcap = h->vcap;
+    hd.resp_used = h->resp_used; hd.expired_total = h->expired_total; hd.tail = h->tail; hd.released_total = h->released_total; hd.slab_rows = h->cfg.slab_rows; hd.vtail = h->vtail; hd.vcap = h->vcap; hd.resp_tail = h->resp_tail; hd.resp_cap = h->resp_cap;
     unsigned long long lens[2];
     int rc = 0;
     auto done = [&](int r) { fclose(f); return r; };
@@ -1390,7 +1404,7 @@ int agr_snapshot(agr_handle* h, const char* path) {
     }
     if ((rc = dump_dev(h, f, h->d.completed_log, (size_t)lens[0] * 4)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d.failed_log, (size_t)lens[1] * 4)) < 0) return done(rc);
-    if ((rc = dump_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return done(rc);
+    if ((rc = dump_dev(h, f, h->d_resp, (size_t)(is_ring(h) ? std::min<uint64_t>(hd.resp_used, h->resp_cap) : hd.resp_used))) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_resp_off, R * 8)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_resp_len, R * 4)) < 0) return done(rc);
     if ((rc = dump_dev(h, f, h->d_resp_hlen, R * 4)) < 0) return done(rc);
@@ -1418,8 +1432,9 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     int rc = agr_create(&c, &h);
     if (rc < 0) { fclose(f); return rc; }
     auto bail = [&](int r) { std::string keep = g_err; fclose(f); agr_destroy(h); g_err = keep; return r; };
-    if (hd.resp_used > h->resp_cap) return bail(fail(AGR_ENOSPC, "restore: stored responses larger than resp_bytes"));
     const bool snap_ring = (hd.flags & AGR_CFG_RING) != 0;
+    if (!snap_ring && hd.resp_used > h->resp_cap) return bail(fail(AGR_ENOSPC, "restore: stored responses larger than resp_bytes"));
+    if (snap_ring && hd.resp_cap != h->resp_cap) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same resp_bytes"));
     if (snap_ring && (hd.flags & AGR_CFG_VARLEN) && hd.vcap != h->vcap) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same vslab_bytes"));
     if (snap_ring && hd.slab_rows != h->cfg.slab_rows) return bail(fail(AGR_EINVAL, "restore: a ring snapshot needs the same slab_rows (rows live at logical mod slab_rows)"));
     if ((!snap_ring && hd.rows_used > h->cfg.slab_rows) || hd.log_len[0] > h->d.log_cap || hd.log_len[1] > h->d.log_cap || ((hd.flags & AGR_CFG_VARLEN) && !snap_ring && hd.vused > h->vcap))
@@ -1446,7 +1461,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     }
     if ((rc = load_dev(h, f, h->d.completed_log, (size_t)hd.log_len[0] * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.failed_log, (size_t)hd.log_len[1] * 4)) < 0) return bail(rc);
-    if ((rc = load_dev(h, f, h->d_resp, (size_t)hd.resp_used)) < 0) return bail(rc);
+    if ((rc = load_dev(h, f, h->d_resp, (size_t)(snap_ring ? std::min<uint64_t>(hd.resp_used, hd.resp_cap) : hd.resp_used))) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_resp_off, R * 8)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_resp_len, R * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d_resp_hlen, R * 4)) < 0) return bail(rc);
@@ -1454,7 +1469,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if ((rc = load_dev(h, f, h->d_err_len, R * 4)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.ptime, R * 8)) < 0) return bail(rc);
     if ((rc = load_dev(h, f, h->d.mtime, R * 8)) < 0) return bail(rc);
-    h->resp_used = hd.resp_used; h->expired_total = hd.expired_total;
+    h->resp_used = hd.resp_used; h->resp_tail = hd.resp_tail; h->expired_total = hd.expired_total;
     unsigned long long lens[2] = {hd.log_len[0], hd.log_len[1]};
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->vtail = hd.vtail; h->scan_lo = hd.scan_lo;
@@ -1532,6 +1547,17 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
         if (live > n0) agr_launch_reindex_range(h->d, 0, (uint32_t)(live - n0), h->stream);
         CK(cudaGetLastError());
         h->k1_launches += 2;
+    }
+    {   // the response / error byte ring: its tail follows the oldest blob a live row still refers to
+        unsigned long long* d_span = (unsigned long long*)(h->d.ctr + C_NCTR - 1);              // last counter slot as scratch
+        CK(cudaMemsetAsync(d_span, 0, 8, h->stream));
+        agr_launch_bytes_span(h->d, h->resp_used % h->resp_cap, h->resp_cap, h->d_resp_off, h->d_resp_len, h->d_err_off, h->d_err_len, d_span, h->stream);
+        CK(cudaGetLastError());
+        unsigned long long span = 0;
+        CK(cudaMemcpyAsync(&span, d_span, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->resp_tail = h->resp_used - span;
+        h->k3_launches += 1;
     }
     if (h->cfg.flags & AGR_CFG_VARLEN) {                          // the byte ring's tail follows: first byte of the first live record
         if (h->tail == h->rows_used) h->vtail = h->vused;

@@ -279,6 +279,29 @@ __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uin
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
     if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
 }
+// how far back from the byte slab's head (physical offset `head`) the oldest blob lies that a live row still refers to
+__global__ void __launch_bounds__(256) k_bytes_span(const agr_dev d, const unsigned long long head, const unsigned long long cap,
+                                                    const unsigned long long* __restrict__ resp_off, const uint32_t* __restrict__ resp_len,
+                                                    const unsigned long long* __restrict__ err_off, const uint32_t* __restrict__ err_len,
+                                                    unsigned long long* __restrict__ span) {
+    const unsigned long long live = d.head_l - d.tail;
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (k < live) {
+        const uint32_t p = row_physical(d, d.tail + k);
+        if (resp_len[p]) { unsigned long long dist = (head + cap - resp_off[p]) % cap; if (dist == 0) dist = cap; mine = dist; }
+        if (err_len[p]) { unsigned long long dist = (head + cap - err_off[p]) % cap; if (dist == 0) dist = cap; if (dist > mine) mine = dist; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const unsigned long long y = __shfl_xor_sync(FULL, mine, o); if (y > mine) mine = y; }
+    if ((threadIdx.x & 31) == 0 && mine) atomicMax(span, mine);
+}
+void agr_launch_bytes_span(const agr_dev& d, unsigned long long head, unsigned long long cap, const unsigned long long* resp_off,
+                           const uint32_t* resp_len, const unsigned long long* err_off, const uint32_t* err_len, unsigned long long* span,
+                           cudaStream_t st) {
+    const unsigned long long live = d.head_l - d.tail;
+    if (live) k_bytes_span<<<(unsigned)((live + 255) / 256), 256, 0, st>>>(d, head, cap, resp_off, resp_len, err_off, err_len, span);
+}
 // stable compaction of a log: entries whose row is among the `released` rows at the tail drop out
 #define LC_CHUNK 1024u
 __device__ __forceinline__ bool log_keep(const agr_dev& d, uint32_t p, uint32_t released) {

@@ -147,6 +147,9 @@ void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long 
 // `count` rows from the tail and stable compaction of a log (entries of released rows drop out)
 void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st);
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st);
+void agr_launch_bytes_span(const agr_dev& d, unsigned long long head, unsigned long long cap, const unsigned long long* resp_off,
+                           const uint32_t* resp_len, const unsigned long long* err_off, const uint32_t* err_len, unsigned long long* span,
+                           cudaStream_t st);
 void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long long len, uint32_t released, uint32_t* out,
                             uint32_t* chunk_cnt /* [chunks + 1] */, unsigned long long* new_len /* device: receives the kept count */,
                             cudaStream_t st);

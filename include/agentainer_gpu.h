@@ -264,10 +264,9 @@ int agr_store_response(agr_handle* h, const char* agent_id, const uint8_t reques
 /* Request.Error = err.Error() (requests.go:244): the text MarkRequestFailed stored last.  agr_complete carries only the
  * fact of the failure; the Go shim hands the text over here (off the hot path).  Without it the wire form says
  * "transport error".
- * Both stores append to one byte slab of agr_config.resp_bytes.  The slab is not recycled yet, not even with
- * AGR_CFG_RING (released rows forget their bytes, the bytes are not reused): size it for the traffic between two
- * snapshot / restore cycles; when it is full the stores fail with AGR_ENOSPC and the records keep working without the
- * extra bytes. */
+ * Both stores append to one byte slab of agr_config.resp_bytes.  With AGR_CFG_RING the slab is a ring as well:
+ * agr_reclaim moves its tail to the oldest bytes a live row still refers to.  Without the ring it is append-only.  When it
+ * is full the stores fail with AGR_ENOSPC and the records keep working without the extra bytes. */
 int agr_store_error_text(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const char* text, uint32_t len);
 int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
 

@@ -33,7 +33,9 @@ def test_ring_runs_past_its_capacity(mode, tmp_path):
     R, per_round, rounds = 4096, 300, 42
     var = mode == "var"
     # variable-length records: the byte slab (6 MiB) is a ring too and laps about as often as the rows do
-    kw = dict(slab_rows=R, max_agents=8, flags=(FLAGS & ~K.AGR_CFG_MINT_IDS if mode == "hash" else FLAGS) | (K.AGR_CFG_VARLEN if var else 0), vslab_bytes=6 << 20)
+    RESP = 64 << 10                                            # the response / error byte slab is a ring too: 64 KiB, lapped twice
+    kw = dict(slab_rows=R, max_agents=8, flags=(FLAGS & ~K.AGR_CFG_MINT_IDS if mode == "hash" else FLAGS) | (K.AGR_CFG_VARLEN if var else 0),
+              vslab_bytes=6 << 20, resp_bytes=RESP if mode == "fixed" else 0)
     eng = A.Engine(**kw)
     redis = M.MiniRedis(); mgr = M.Manager(redis)
     agents = M.AgentStore(redis); proxy = M.Proxy(redis, agents); worker = M.ReplayWorker(redis, agents, proxy)
@@ -44,6 +46,7 @@ def test_ring_runs_past_its_capacity(mode, tmp_path):
     rng = np.random.default_rng(7)
     wrapped_with_backlog = 0
     bytes_in = 0
+    stored_bytes = 0
     try:
         for rnd in range(rounds):
             now = T0 + rnd * STEP
@@ -73,13 +76,30 @@ def test_ring_runs_past_its_capacity(mode, tmp_path):
                         ops.append((r, K.AGR_OUT_ERROR, 0))
             t = now + 10 * SEC
             redis.now = t
+            with_bytes = mode == "fixed"                       # responses and error texts carry bytes in this mode
+            texts = {}
             for r, kind, code in ops:
                 if kind == K.AGR_OUT_RESPONSE:
-                    mgr.store_response(r.agent_id, G.format_uuid(r.rid), M.HttpResponse(code, {}, b"", now=t))
+                    body = bytes(rng.integers(0, 256, int(rng.integers(0, 48)), dtype=np.uint8)) if with_bytes else b""
+                    hdrs = {b"Server": b"x<y>"} if with_bytes and rng.random() < 0.5 else {}
+                    texts[r.rid] = (hdrs, body)
+                    mgr.store_response(r.agent_id, G.format_uuid(r.rid), M.HttpResponse(code, dict(hdrs), body, now=t))
                 else:
-                    mgr.mark_request_failed(r.agent_id, G.format_uuid(r.rid), "transport error")
+                    text = (b"EOF", b"read tcp: connection reset by peer")[int(rng.integers(0, 2))] if with_bytes else b"transport error"
+                    texts[r.rid] = text
+                    mgr.mark_request_failed(r.agent_id, G.format_uuid(r.rid), text if with_bytes else "transport error")
             res = eng.complete(outcomes([(r.rid, r.agent_id, kind, code, t) for r, kind, code in ops]))
             assert (res == 0).all()
+            if with_bytes:
+                for r, kind, code in ops:
+                    if kind == K.AGR_OUT_RESPONSE:
+                        hdrs, body = texts[r.rid]
+                        flat = b"".join(k + b": " + v + b"\n" for k, v in sorted(hdrs.items()))
+                        assert eng.store_response(r.agent_id, r.rid, flat, body)
+                        stored_bytes += (len(flat) + len(body) + 15) // 16 * 16
+                    else:
+                        assert eng.store_error_text(r.agent_id, r.rid, texts[r.rid])
+                        stored_bytes += (len(texts[r.rid]) + 15) // 16 * 16
             # agent 3 comes up every 5th round for one tick: its backlog (possibly lying across the wrap) replays in FIFO order
             if rnd % 5 == 4:
                 eng.set_agent_state(AGENTS[2], "running"); agents.save(AGENTS[2], "running")
@@ -132,6 +152,7 @@ def test_ring_runs_past_its_capacity(mode, tmp_path):
         assert st["rows_used"] > 3 * R - 2 * per_round and st["rows_tail"] > 2 * R
         assert wrapped_with_backlog >= 1
         assert not var or bytes_in > 2 * (6 << 20)                            # the byte ring lapped too
+        assert mode != "fixed" or stored_bytes > 2 * RESP                     # and so did the response / error byte ring
         assert eng.verify()[1] == 0
     finally:
         eng.close()
