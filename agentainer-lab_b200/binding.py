@@ -42,6 +42,13 @@ class AgrStats(C.Structure):
         "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches", "rows_tail")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
 
 
+class AgrDecoded(C.Structure):
+    _fields_ = [("status", C.c_uint8), ("retry_count", C.c_uint8), ("max_retries", C.c_uint8), ("has_response", C.c_uint8),
+                ("resp_status", C.c_uint16), ("reserved", C.c_uint16), ("record_len", C.c_uint32), ("resp_hdr_len", C.c_uint32),
+                ("resp_body_len", C.c_uint32), ("error_len", C.c_uint32), ("reserved2", C.c_uint32),
+                ("created_at", C.c_uint64), ("processed_at", C.c_uint64), ("received_at", C.c_uint64)]
+
+
 class AgrExchangeInfo(C.Structure):
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("n_local", C.c_uint32), ("n_sent", C.c_uint32),
                 ("n_received", C.c_uint32), ("sent_to", C.c_uint32 * 32), ("received_from", C.c_uint32 * 32),
@@ -62,7 +69,7 @@ ABI_SYMBOLS = [
     "agr_host_alloc", "agr_host_free", "agr_mint_ids", "agr_reserve_rows", "agr_ingest_rows", "agr_ingest_rows_async", "agr_sync",
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
-    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim", "agr_set_agent_states",
+    "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim", "agr_set_agent_states", "agr_json_decode",
 ]
 
 _lib = None
@@ -139,6 +146,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_expire": (i32, [vp, u64, u64, C.POINTER(u64)]),
         "agr_reclaim": (i32, [vp, C.POINTER(u64)]),
         "agr_set_agent_states": (i32, [vp, vp, vp, u32, vp]),
+        "agr_json_decode": (i32, [vp, u32, vp, u32, vp, u32, vp, u32, vp]),
         "agr_comm_unique_id": (i32, [vp]),
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
@@ -188,6 +196,26 @@ def synth_agent_id(k: int, *, agent_nanos0=0) -> str:
     s = _synth(0, 1, 0, 0, agent_nanos0)
     _check(lib, lib.agr_synth_agent_id(C.byref(s), k, buf))
     return buf.value.decode()
+
+
+def json_decode(js: bytes):
+    """agr_json_decode: the wire form back into (header fields, path, flattened headers, body, AgrDecoded, response headers,
+    response body, error text).  Host only: needs no GPU."""
+    lib = load_library()
+    src = np.frombuffer(js, dtype=np.uint8).copy() if js else np.zeros(1, dtype=np.uint8)
+    rec = np.zeros(8192, dtype=np.uint8)
+    resp = np.zeros(1 << 16, dtype=np.uint8)
+    err = np.zeros(1 << 12, dtype=np.uint8)
+    d = AgrDecoded()
+    rc = lib.agr_json_decode(_ptr(src), len(js), _ptr(rec), rec.size, _ptr(resp), resp.size, _ptr(err), err.size, C.byref(d))
+    if rc < 0:
+        return rc, None
+    head = rec[:96].view(header_dtype)[0]
+    pl, hl, bl = int(head["path_len"]), int(head["hdr_len"]), int(head["body_len"])
+    pay = rec[96: 96 + pl + hl + bl].tobytes()
+    return 0, dict(header=head, path=pay[:pl], headers=pay[pl:pl + hl], body=pay[pl + hl:], info=d,
+                   resp_headers=resp[: d.resp_hdr_len].tobytes(), resp_body=resp[d.resp_hdr_len: d.resp_hdr_len + d.resp_body_len].tobytes(),
+                   error=err[: d.error_len].tobytes(), record=rec[: d.record_len].copy())
 
 
 def comm_unique_id() -> bytes:

@@ -292,6 +292,25 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* count);
 int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, uint8_t* out, uint64_t cap, uint64_t* len, uint64_t* offsets);
 
+/* The other direction, on the host: json.Unmarshal of that form (requests.go:159,216,238; server.go:667,693) into the
+ * variable-length record form (96-byte header of agr_record + path | flattened headers | body, 16-byte rounded) plus the
+ * fields that live outside the record.  Pure host code, no handle, no CUDA call: for migrating an existing Redis keyspace
+ * and for checking what K5 produced.  Accepts what encoding/json accepts for this shape (members in any order, unknown
+ * members skipped, every string escape, null for absent maps / slices / pointers, RFC 3339 times with any offset).
+ * resp receives the flattened response headers followed by the response body; error receives Request.Error (not
+ * NUL-terminated).  AGR_EINVAL: malformed or not representable (record longer than AGR_VAR_MAX_RECORD, agent id longer
+ * than 31 bytes); AGR_ECAP: a buffer is too small (out holds the sizes needed). */
+typedef struct agr_decoded {
+    uint8_t  status, retry_count, max_retries, has_response;   /* AGR_ST_*; Request.RetryCount / MaxRetries; Response != nil */
+    uint16_t resp_status, reserved;
+    uint32_t record_len;                                       /* bytes written to record */
+    uint32_t resp_hdr_len, resp_body_len, error_len;           /* bytes written to resp (headers, then body) and to error */
+    uint32_t reserved2;
+    uint64_t created_at, processed_at, received_at;            /* Unix nanoseconds; 0 = absent */
+} agr_decoded;
+int agr_json_decode(const uint8_t* json, uint32_t len, uint8_t* record, uint32_t record_cap, uint8_t* resp, uint32_t resp_cap,
+                    char* error, uint32_t error_cap, agr_decoded* out);
+
 /* ------------------------------------------------- durability */
 /* What Redis persistence gave the reference (records and queues survive a server restart, docker-compose.yml:11-12):
  * agr_snapshot writes the live state (slab rows, per-row state words, completed / failed logs, agent table) to a file;

@@ -85,8 +85,9 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     """Compile a C program against include/agentainer_gpu.h that prints sizeof / offsetof of every struct the Python
     harness mirrors, and compare with ctypes and numpy: a silent drift would corrupt stats or configs."""
     import subprocess
-    from agentainer_lab_b200.binding import AgrStats, AgrExchangeInfo, AgrSynth
-    structs = {"agr_config": AgrConfig, "agr_stats": AgrStats, "agr_exchange_info": AgrExchangeInfo, "agr_synth": AgrSynth}
+    from agentainer_lab_b200.binding import AgrStats, AgrExchangeInfo, AgrSynth, AgrDecoded
+    structs = {"agr_config": AgrConfig, "agr_stats": AgrStats, "agr_exchange_info": AgrExchangeInfo, "agr_synth": AgrSynth,
+               "agr_decoded": AgrDecoded}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "agentainer_gpu.h"', 'int main(void) {']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

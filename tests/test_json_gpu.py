@@ -214,3 +214,42 @@ def test_wire_form_against_the_c_restatement_at_scale():
                     print(i, blob[int(offs[i]):int(offs[i + 1])], want)
         assert bad == 0
         c.close()
+
+
+def test_encode_then_decode_gives_the_records_back():
+    """Size-independent property, no oracle involved: what K5 writes, the host-side reader (agr_json_decode) turns back into
+    the fields that were ingested and the state the outcomes left."""
+    n, na = 20_000, 32
+    recs = A.synth_fill_host(0, n, seed=21, n_agents=na)
+    names = [A.synth_agent_id(k) for k in range(na)]
+    rng = np.random.default_rng(8)
+    with A.Engine(slab_rows=1 << 15, max_agents=64, flags=MODES["mint"]) as eng:
+        eng.set_agent_states(names, ["running"] * na)
+        out = np.zeros(n, dtype=A.verdict_dtype); ids = np.zeros((n, 16), dtype=np.uint8)
+        first = eng.ingest_ex(recs, out, ids)
+        pick = rng.permutation(n)[: n // 2]
+        outs = np.zeros(len(pick), dtype=A.outcome_dtype)
+        outs["request_id"] = ids[pick]; outs["agent_id"] = recs["agent_id"][pick]
+        is_resp = rng.random(len(pick)) < 0.6
+        outs["kind"] = np.where(is_resp, K.AGR_OUT_RESPONSE, K.AGR_OUT_ERROR)
+        outs["http_status"] = np.where(is_resp, 200, 0)
+        outs["seq"] = 1_700_000_000_000_000_000 + np.arange(len(pick)) * 1000
+        assert (eng.complete(outs) == 0).all()
+        state = {int(i): (bool(r), int(t)) for i, r, t in zip(pick, is_resp, outs["seq"])}
+        blob, offs = eng.rows_json(first, n)
+        for i in range(n):
+            rc, d = A.json_decode(blob[int(offs[i]):int(offs[i + 1])])
+            assert rc == 0
+            h, info, r = d["header"], d["info"], recs[i]
+            pl, hl, bl = int(r["path_len"]), int(r["hdr_len"]), int(r["body_len"])
+            pay = r["payload"].tobytes()
+            assert bytes(h["request_id"]) == bytes(ids[i]) and h["agent_id"] == r["agent_id"] and int(h["seq"]) == int(r["seq"])
+            assert d["path"] == pay[:pl] and d["headers"] == pay[pl:pl + hl] and d["body"] == pay[pl + hl:pl + hl + bl]
+            assert (int(h["flags"]) >> 8) & 0xff == (int(r["flags"]) >> 8) & 0xff
+            if i not in state:
+                assert info.status == K.AGR_ST_PENDING and info.retry_count == 0 and not info.has_response and d["error"] == b""
+            elif state[i][0]:
+                assert info.status == K.AGR_ST_COMPLETED and info.has_response and info.resp_status == 200
+                assert info.processed_at == info.received_at == state[i][1]
+            else:
+                assert info.status == K.AGR_ST_PENDING and info.retry_count == 1 and d["error"] == b"transport error"
