@@ -102,3 +102,32 @@ def test_decode_then_marshal_is_gos_round_trip():
                               "body": d["resp_body"], "received_at": info.received_at} if info.has_response else None),
                 "error": d["error"].decode()}
         assert G.marshal_request(back) == G.marshal_request(G.unmarshal_strings(copy.deepcopy(rec)))
+
+
+def test_decoder_survives_mutated_input_under_asan(tmp_path):
+    """The reader takes untrusted bytes (a Redis dump): 100 k mutations of real documents through an ASAN + UBSAN build of
+    the decoder, with exact-size input buffers and deliberately small output buffers."""
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None:
+        import pytest
+        pytest.skip("no g++")
+    reqs = make_requests(3, 40, AGENTS[:2])
+    redis, _ = run_model(reqs, make_script(3, 40, 60))
+    seeds = tmp_path / "seeds.bin"
+    with open(seeds, "wb") as f:
+        for r in reqs:
+            j = G.marshal_request(redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}"))
+            f.write(len(j).to_bytes(4, "little") + j)
+    exe = tmp_path / "fuzz"
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                            "-I", os.path.join(root, "include"), os.path.join(root, "agentainer-lab_b200", "csrc", "agr_json_host.cpp"),
+                            os.path.join(root, "tests", "fuzz_json_decode.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        import pytest
+        pytest.skip("sanitizers not available in this toolchain")
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe), str(seeds), "100000"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-3000:]
+    ok, ecap, einval = (int(x) for x in run.stdout.split()[1::2])
+    assert ok > 1000 and ecap > 1000 and einval > 1000
