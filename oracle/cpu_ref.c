@@ -38,10 +38,11 @@ typedef struct {
     char* key; uint32_t klen; uint64_t hash; int type;
     char* val; uint32_t vlen, vcap;            /* T_STRING (val lives in the arena: never freed, reused in place) */
     lid* items; uint32_t n, cap;               /* T_LIST */
+    uint64_t expires;                          /* SET ... EX: the server's clock value at which the key is gone; 0 = none */
 } kent;
 /* bump arena per keyspace: one Redis instance = one allocator, so shards on different threads never contend */
 typedef struct achunk { struct achunk* next; size_t used, cap; } achunk;
-typedef struct { kent* e; uint64_t cap, used, tomb; achunk* arena; } keyspace;
+typedef struct { kent* e; uint64_t cap, used, tomb; achunk* arena; uint64_t now; } keyspace;   /* now: the server's clock (set by the stream) */
 static char* arena_alloc(keyspace* k, size_t n) {
     n = (n + 15) & ~(size_t)15;
     if (!k->arena || k->arena->used + n > k->arena->cap) {
@@ -55,10 +56,10 @@ static char* arena_alloc(keyspace* k, size_t n) {
 }
 
 static uint64_t fnv(const char* s, uint32_t n) { uint64_t h = 0xcbf29ce484222325ULL; for (uint32_t i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 0x100000001b3ULL; } return h; }
-static void ks_init(keyspace* k, uint64_t cap) { k->cap = cap; k->used = k->tomb = 0; k->arena = NULL; k->e = (kent*)calloc(cap, sizeof(kent)); }
+static void ks_init(keyspace* k, uint64_t cap) { k->cap = cap; k->used = k->tomb = 0; k->arena = NULL; k->now = 0; k->e = (kent*)calloc(cap, sizeof(kent)); }
 static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create);
 static void ks_grow(keyspace* k) {
-    keyspace n; ks_init(&n, k->cap * 2); n.arena = k->arena;
+    keyspace n; ks_init(&n, k->cap * 2); n.arena = k->arena; n.now = k->now;
     for (uint64_t i = 0; i < k->cap; ++i) if (k->e[i].key && k->e[i].type) {
         uint64_t j = k->e[i].hash & (n.cap - 1);
         while (n.e[j].key) j = (j + 1) & (n.cap - 1);
@@ -76,7 +77,7 @@ static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create) {
             if (!create) return NULL;
             if (firsttomb) { e = firsttomb; k->tomb--; }
             e->key = arena_alloc(k, klen + 1); memcpy(e->key, key, klen); e->key[klen] = 0;
-            e->klen = klen; e->hash = h; e->type = 0; e->val = NULL; e->vlen = e->vcap = 0; e->items = NULL; e->n = e->cap = 0;
+            e->klen = klen; e->hash = h; e->type = 0; e->val = NULL; e->vlen = e->vcap = 0; e->items = NULL; e->n = e->cap = 0; e->expires = 0;
             k->used++;
             return e;
         }
@@ -88,10 +89,12 @@ static kent* ks_find(keyspace* k, const char* key, uint32_t klen, int create) {
 static void ks_del_entry(keyspace* k, kent* e) {          /* DEL */
     if (!e || !e->type) return;
     free(e->items); e->val = NULL; e->items = NULL; e->n = e->cap = 0; e->vlen = e->vcap = 0;
-    e->type = 0; k->used--; k->tomb++;
+    e->type = 0; e->expires = 0; k->used--; k->tomb++;
 }
-static void r_set(keyspace* k, const char* key, uint32_t klen, const char* v, uint32_t vlen) {   /* SET key val EX 24h */
+#define TTL_24H (24ULL * 3600ULL * 1000000000ULL)           /* requests.go:106,175,270; the stream's clock is in nanoseconds */
+static void r_set_ex(keyspace* k, const char* key, uint32_t klen, const char* v, uint32_t vlen, uint64_t ttl) {   /* SET key val [EX ttl] */
     kent* e = ks_find(k, key, klen, 1);
+    e->expires = ttl ? k->now + ttl : 0;                      /* every SET restarts the TTL (Q11) */
     if (e->type == T_LIST) { free(e->items); e->items = NULL; e->val = NULL; e->vcap = 0; }
     if (e->val == NULL || vlen + 1 > e->vcap) {              /* room for the response that StoreResponse adds later */
         e->vcap = vlen + vlen / 2 + 128;
@@ -99,7 +102,12 @@ static void r_set(keyspace* k, const char* key, uint32_t klen, const char* v, ui
     }
     memcpy(e->val, v, vlen); e->val[vlen] = 0; e->vlen = vlen; e->type = T_STRING;
 }
-static kent* r_get(keyspace* k, const char* key, uint32_t klen) { kent* e = ks_find(k, key, klen, 0); return (e && e->type == T_STRING) ? e : NULL; }
+static void r_set(keyspace* k, const char* key, uint32_t klen, const char* v, uint32_t vlen) { r_set_ex(k, key, klen, v, vlen, TTL_24H); }   /* the record keys */
+static kent* r_get(keyspace* k, const char* key, uint32_t klen) {
+    kent* e = ks_find(k, key, klen, 0);
+    if (e && e->type == T_STRING && e->expires && k->now >= e->expires) { ks_del_entry(k, e); return NULL; }   /* expired keys are gone */
+    return (e && e->type == T_STRING) ? e : NULL;
+}
 static void r_rpush(keyspace* k, const char* key, uint32_t klen, const char* id) {
     kent* e = ks_find(k, key, klen, 1);
     if (e->type != T_LIST) { e->val = NULL; e->vcap = 0; e->type = T_LIST; e->n = 0; }
@@ -361,7 +369,7 @@ int cref_set_agent_state(cref* c, const char* agent_id, uint8_t status) {
         "\"status\":\"%s\",\"env_vars\":{\"OPENAI_API_KEY\":\"sk-test\"},\"cpu_limit\":1000000000,\"memory_limit\":536870912,\"auto_restart\":true,"
         "\"token\":\"agentainer-default-token\",\"ports\":[],\"volumes\":[],\"created_at\":\"2025-01-01T00:00:00Z\",\"updated_at\":\"2025-01-01T00:00:00Z\"}",
         agent_id, agent_status_name(status));
-    r_set(&c->ks, key, (uint32_t)kl, doc, (uint32_t)dl);
+    r_set_ex(&c->ks, key, (uint32_t)kl, doc, (uint32_t)dl, 0);      /* saveAgent: no TTL (agent.go:519-522) */
     return idx;
 }
 /* GetAgent (agent.go:372-390): GET agent:{id} + json.Unmarshal; returns status code or -1 */
@@ -539,6 +547,7 @@ int cref_list(cref* c, const char* agent_id, int which, uint8_t (*ids)[16], uint
     return 0;
 }
 uint64_t cref_keys(cref* c) { return c->ks.used; }
+void cref_set_now(cref* c, uint64_t now) { c->ks.now = now; }   /* the Redis server's clock, same unit as the records' times */
 /* json.Marshal(GetPendingRequests(agent)) — the "pending" member of GET /agents/{id}/requests (server.go:638-650): every
  * record is unmarshalled by GetPendingRequests and marshalled again by the handler; a nil slice is null */
 int cref_pending_json(cref* c, const char* agent_id, char* out, uint32_t cap, uint32_t* len) {

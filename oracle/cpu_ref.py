@@ -41,6 +41,7 @@ def load():
         lib.cref_list.restype, lib.cref_list.argtypes = C.c_int, [vp, C.c_char_p, C.c_int, vp, u32, C.POINTER(u32)]
         lib.cref_keys.restype, lib.cref_keys.argtypes = C.c_uint64, [vp]
         lib.cref_get_json.restype, lib.cref_get_json.argtypes = C.c_int, [vp, C.c_char_p, vp, vp, u32, C.POINTER(u32)]
+        lib.cref_set_now.restype, lib.cref_set_now.argtypes = None, [vp, C.c_uint64]
         lib.cref_pending_json.restype, lib.cref_pending_json.argtypes = C.c_int, [vp, C.c_char_p, vp, u32, C.POINTER(u32)]
         _lib = lib
     return _lib
@@ -109,6 +110,10 @@ class CRef:
         rid = np.frombuffer(request_id, dtype=np.uint8).copy()
         rc = self.lib.cref_get_record(self.h, agent_id.encode(), _p(rid), _p(out))
         return None if rc == AGR_ENOTFOUND else out[0]
+
+    def set_now(self, now):
+        """The Redis server's clock (key TTLs); same unit as the records' times."""
+        self.lib.cref_set_now(self.h, int(now))
 
     def get_json(self, agent_id, request_id):
         """The stored value of agent:{a}:requests:{r}: the C port's own json.Marshal(request), after every round trip."""

@@ -104,3 +104,58 @@ def test_two_restatements_of_the_wire_form_agree():
     for a in agents + ["agent-nobody"]:
         assert c.pending_json(a) == G.marshal_list(mgr.get_pending_requests(a))
     c.close()
+
+
+def test_two_restatements_agree_on_the_key_ttl():
+    """SET ... EX 24h in both restatements: records vanish 24 h after their LAST SET, their ids stay in the lists, updates of
+    a vanished record fail with "failed to get request", GetPendingRequests skips them."""
+    import random
+    import numpy as np
+    from jsoncase import make_requests, records_array
+    from oracle import gojson as G, model as M
+    from oracle.cpu_ref import CRef, record_dtype
+    from agentainer_lab_b200 import constants as K, outcome_dtype
+    SEC = 1_000_000_000; HOUR = 3600 * SEC; T0 = 1_700_000_000 * SEC
+    agents = ["agent-1700000000000000001", "agent-1700000000000000002"]
+    c = CRef(); redis = M.MiniRedis(); mgr = M.Manager(redis)
+    c.set_agent_state(agents[0], "running"); c.set_agent_state(agents[1], "stopped")
+    rng = random.Random(9)
+    known = []
+    for rnd in range(16):                                    # a batch every 4 hours, over 64 hours
+        now = T0 + rnd * 4 * HOUR
+        c.set_now(now); redis.now = now
+        reqs = make_requests(200 + rnd, 40, agents, max_payload=330)
+        for i, r in enumerate(reqs):
+            r.now = now + i
+            mgr.store_request(r.agent_id, M.HttpRequest(r.method, r.path, dict(r.headers), r.body, new_id=G.format_uuid(r.rid), now=r.now))
+        c.ingest(records_array(reqs).astype(record_dtype))
+        known += reqs
+        t = now + HOUR
+        c.set_now(t); redis.now = t
+        for r in rng.sample(known, 30):                      # updates hit fresh and long-gone records alike
+            out = np.zeros(1, dtype=outcome_dtype)
+            out[0]["request_id"] = np.frombuffer(r.rid, dtype=np.uint8); out[0]["agent_id"] = r.agent_id.encode()
+            is_resp = rng.random() < 0.5
+            out[0]["kind"], out[0]["http_status"], out[0]["seq"] = (K.AGR_OUT_RESPONSE, 200, t) if is_resp else (K.AGR_OUT_ERROR, 0, t)
+            res = c.complete(out)
+            try:
+                if is_resp:
+                    mgr.store_response(r.agent_id, G.format_uuid(r.rid), M.HttpResponse(200, {}, b"", now=t))
+                else:
+                    mgr.mark_request_failed(r.agent_id, G.format_uuid(r.rid), "transport error")
+                assert res[0] == 0
+            except KeyError:
+                assert res[0] == K.AGR_ENOTFOUND               # "failed to get request"
+        gone = 0
+        for r in known:
+            try:
+                want = G.marshal_request(redis.get(f"agent:{r.agent_id}:requests:{G.format_uuid(r.rid)}"))
+            except M.RedisNil:
+                want = None; gone += 1
+            assert c.get_json(r.agent_id, r.rid) == want
+        for a in agents:
+            assert c.pending_json(a) == G.marshal_list(mgr.get_pending_requests(a))
+            for which, q in ((0, "pending"), (1, "completed"), (2, "failed")):
+                assert [G.format_uuid(bytes(i)) for i in c.list(a, which, cap=1 << 12)] == redis.lrange_all(f"agent:{a}:requests:{q}")
+    assert gone > 200
+    c.close()
