@@ -186,6 +186,7 @@ static void uuid_text(const uint8_t id[16], char out[37]) {
 }
 static int hexv(char c) { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; }
 static void uuid_parse(const char* t, uint8_t id[16]) { int o = 0; for (int i = 0; i < 16; ++i) { if (t[o] == '-') o++; id[i] = (uint8_t)((hexv(t[o]) << 4) | hexv(t[o + 1])); o += 2; } }
+static char* put2(char* t, unsigned v) { t[0] = (char)('0' + v / 10); t[1] = (char)('0' + v % 10); return t + 2; }
 static void sb_time(sbuf* b, uint64_t ns) {                 /* time.Unix(0, ns).UTC().MarshalJSON(): RFC3339Nano */
     uint64_t secs = ns / 1000000000ULL; unsigned frac = (unsigned)(ns % 1000000000ULL);
     uint64_t days = secs / 86400ULL; unsigned sod = (unsigned)(secs % 86400ULL);
@@ -193,10 +194,16 @@ static void sb_time(sbuf* b, uint64_t ns) {                 /* time.Unix(0, ns).
     unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365; unsigned y = yoe + (unsigned)era * 400;
     unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100); unsigned mp = (5 * doy + 2) / 153;
     unsigned d = doy - (153 * mp + 2) / 5 + 1; unsigned mth = mp < 10 ? mp + 3 : mp - 9; if (mth <= 2) y++;
-    char t[64]; int m = snprintf(t, sizeof t, "\"%04u-%02u-%02uT%02u:%02u:%02u", y, mth, d, sod / 3600, sod / 60 % 60, sod % 60);
-    if (frac) { char f[16]; snprintf(f, sizeof f, "%09u", frac); int k = 9; while (k > 0 && f[k - 1] == '0') k--; t[m++] = '.'; memcpy(t + m, f, (size_t)k); m += k; }
-    t[m++] = 'Z'; t[m++] = '"';
-    sb_put(b, t, (size_t)m);
+    char t[48]; char* q = t;
+    *q++ = '"'; q = put2(q, y / 100); q = put2(q, y % 100); *q++ = '-'; q = put2(q, mth); *q++ = '-'; q = put2(q, d); *q++ = 'T';
+    q = put2(q, sod / 3600); *q++ = ':'; q = put2(q, sod / 60 % 60); *q++ = ':'; q = put2(q, sod % 60);
+    if (frac) {
+        char f[9]; unsigned v = frac; for (int k = 8; k >= 0; --k) { f[k] = (char)('0' + v % 10); v /= 10; }
+        int k = 9; while (k > 0 && f[k - 1] == '0') k--;
+        *q++ = '.'; memcpy(q, f, (size_t)k); q += k;
+    }
+    *q++ = 'Z'; *q++ = '"';
+    sb_put(b, t, (size_t)(q - t));
 }
 static const char* status_name(int s) { return s == AGR_ST_PENDING ? "pending" : s == AGR_ST_PROCESSING ? "processing" : s == AGR_ST_COMPLETED ? "completed" : s == AGR_ST_FAILED ? "failed" : ""; }
 static const char* method_name(uint32_t f) { static const char* m[] = {"", "GET", "POST", "PUT", "DELETE", "PATCH", "HEAD", "OPTIONS"}; uint32_t c = (f & AGR_F_METHOD_MASK) >> AGR_F_METHOD_SHIFT; return c < 8 ? m[c] : ""; }
@@ -271,10 +278,12 @@ static size_t j_b64(jr* j, uint8_t* out, size_t cap) {
     return n;
 }
 static uint64_t j_uint(jr* j) { uint64_t v = 0; while (j->p < j->e && *j->p >= '0' && *j->p <= '9') v = v * 10 + (uint64_t)(*j->p++ - '0'); return v; }
+static unsigned get_n(const char* t, int n) { unsigned v = 0; for (int k = 0; k < n; ++k) v = v * 10 + (unsigned)(t[k] - '0'); return v; }
 static uint64_t j_time(jr* j) {                             /* time.Time.UnmarshalJSON of the form sb_time writes */
     char t[48]; size_t n = j_string(j, t, sizeof t - 1); t[n < 47 ? n : 47] = 0;
-    unsigned y = 0, mo = 0, d = 0, hh = 0, mi = 0, ss = 0; uint64_t frac = 0;
-    sscanf(t, "%4u-%2u-%2uT%2u:%2u:%2u", &y, &mo, &d, &hh, &mi, &ss);
+    if (n < 20) return 0;
+    unsigned y = get_n(t, 4), mo = get_n(t + 5, 2), d = get_n(t + 8, 2), hh = get_n(t + 11, 2), mi = get_n(t + 14, 2), ss = get_n(t + 17, 2);
+    uint64_t frac = 0;
     if (t[19] == '.') { int k = 0; for (const char* q = t + 20; *q >= '0' && *q <= '9'; ++q, ++k) frac = frac * 10 + (uint64_t)(*q - '0'); for (; k < 9; ++k) frac *= 10; }
     int64_t yy = (int64_t)y - (mo <= 2); int64_t era = yy / 400; unsigned yoe = (unsigned)(yy - era * 400);
     unsigned doy = (153 * (mo > 2 ? mo - 3 : mo + 9) + 2) / 5 + d - 1; unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
