@@ -119,7 +119,8 @@ typedef struct agr_config {
     uint64_t vslab_bytes;    /* AGR_CFG_VARLEN: capacity of the byte slab; 0 = 1024 * slab_rows */
     uint64_t resp_bytes;     /* capacity of the stored-response byte slab; 0 = 64 * slab_rows */
     uint32_t k1_variant;     /* 0 = default K1 kernel (TMA, 14 warps x 1 stage, fused index); 1..4 TMA shapes, 5 = LSU kernel,
-                                | 0x10 = split stream / index kernels — alternates kept for A/B measurement */
+                                | 0x10 = split stream / index kernels, | 0x20 = LSU form of the variable-length kernel —
+                                alternates kept for A/B measurement */
     uint32_t reserved;
 } agr_config;
 
