@@ -3,7 +3,7 @@ outcomes, driven into oracle/model.py's Manager (the literal Go restatement) and
 from __future__ import annotations
 
 import random
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
 import numpy as np

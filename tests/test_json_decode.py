@@ -2,9 +2,6 @@
 Pure host code: these tests need no GPU.  Checked against oracle/gojson.py: decoding what the oracle marshals gives back
 the fields Go's decoder would hold, for fresh and for round-tripped records."""
 import base64
-import json
-
-import numpy as np
 
 import agentainer_lab_b200 as A
 from agentainer_lab_b200 import constants as K

@@ -1,7 +1,6 @@
 """Property tests: for ANY event stream the implementation equals the oracle on per-request
 verdicts, per-record (status, retry, response), per-agent pending / completed / failed id sequences and per-tick replay
 dispatch order.  CPU: the C restatement against the Python oracle.  GPU: the CUDA path against the Python oracle."""
-import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
 
