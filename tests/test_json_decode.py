@@ -128,3 +128,31 @@ def test_decoder_survives_mutated_input_under_asan(tmp_path):
     assert run.returncode == 0, run.stderr[-3000:]
     ok, ecap, einval = (int(x) for x in run.stdout.split()[1::2])
     assert ok > 1000 and ecap > 1000 and einval > 1000
+
+
+def test_decoder_on_the_hand_derived_kats():
+    """tests/golden/gojson_kats.json was written by hand from encoding/json's rules; the product's reader must turn each
+    document back into the record it was derived from."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gojson_kats.json")) as f:
+        kats = json.load(f)["records"]
+    assert len(kats) >= 6
+    for k in kats:
+        rec = k["record"]
+        rc, d = A.json_decode(k["json"].encode())
+        assert rc == 0, k["name"]
+        h, info = d["header"], d["info"]
+        assert G.format_uuid(bytes(h["request_id"])) == rec["id"] and h["agent_id"].decode() == rec["agent_id"], k["name"]
+        assert METHODS[((int(h["flags"]) >> 8) & 0xff) - 1] == rec["method"] and d["path"].decode() == rec["path"]
+        assert d["headers"] == "".join(f"{a}: {b}\n" for a, b in sorted(rec["headers"].items(), key=lambda kv: kv[0].encode())).encode()
+        assert d["body"] == bytes.fromhex(rec["body_hex"])
+        assert info.status == ST[rec["status"]] and info.retry_count == rec["retry_count"] and info.max_retries == rec["max_retries"]
+        assert info.created_at == rec["created_at"] and d["error"].decode() == rec["error"]
+        if rec["response"]:
+            r = rec["response"]
+            assert info.has_response and info.resp_status == r["status_code"] and info.received_at == r["received_at"]
+            assert info.processed_at == rec["processed_at"] and d["resp_body"] == bytes.fromhex(r["body_hex"])
+            assert d["resp_headers"] == "".join(f"{a}: {b}\n" for a, b in sorted(r["headers"].items())).encode()
+        else:
+            assert not info.has_response
