@@ -253,3 +253,49 @@ def test_encode_then_decode_gives_the_records_back():
                 assert info.processed_at == info.received_at == state[i][1]
             else:
                 assert info.status == K.AGR_ST_PENDING and info.retry_count == 1 and d["error"] == b"transport error"
+
+
+def test_engine_reproduces_the_hand_derived_kats():
+    """The hand-written documents of tests/golden/gojson_kats.json, byte for byte, from the engine itself: each record is
+    ingested with its id, driven to its state with agr_complete / agr_store_*, and read back.  (A KAT whose received_at
+    differs from its processed_at is skipped: the engine keeps one time per StoreResponse)"""
+    import os
+    from agentainer_lab_b200 import record_dtype
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gojson_kats.json")) as f:
+        kats = json.load(f)["records"]
+    done = 0
+    for k in kats:
+        rec = k["record"]
+        resp = rec["response"]
+        if resp and resp["received_at"] != rec["processed_at"]:
+            continue
+        rid = bytes.fromhex(rec["id"].replace("-", ""))
+        path = rec["path"].encode()
+        hdrs = "".join(f"{a}: {b}\n" for a, b in sorted(rec["headers"].items(), key=lambda kv: kv[0].encode())).encode()
+        body = bytes.fromhex(rec["body_hex"])
+        r = np.zeros(1, dtype=record_dtype)
+        r[0]["request_id"] = np.frombuffer(rid, dtype=np.uint8); r[0]["agent_id"] = rec["agent_id"].encode(); r[0]["seq"] = rec["created_at"]
+        r[0]["flags"] = K.METHOD_CODES[rec["method"]] << K.AGR_F_METHOD_SHIFT
+        r[0]["path_len"], r[0]["hdr_len"], r[0]["body_len"] = len(path), len(hdrs), len(body)
+        r[0]["status"], r[0]["max_retries"] = K.AGR_ST_PENDING, rec["max_retries"]
+        blob = path + hdrs + body
+        r[0]["payload"][: len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        with A.Engine(slab_rows=1 << 10, max_agents=8, flags=MODES["hash"]) as eng:
+            eng.set_agent_state(rec["agent_id"], K.AGR_AGENT_STOPPED)
+            out = np.zeros(1, dtype=A.verdict_dtype); ids = np.zeros((1, 16), dtype=np.uint8)
+            eng.ingest_ex(r, out, ids)
+            outs = np.zeros(1, dtype=A.outcome_dtype)
+            outs[0]["request_id"] = np.frombuffer(rid, dtype=np.uint8); outs[0]["agent_id"] = rec["agent_id"].encode()
+            for _ in range(rec["retry_count"]):
+                outs[0]["kind"], outs[0]["http_status"], outs[0]["seq"] = K.AGR_OUT_ERROR, 0, rec["created_at"] + 1
+                assert eng.complete(outs)[0] == 0
+            if rec["error"]:
+                assert eng.store_error_text(rec["agent_id"], rid, rec["error"].encode())
+            if resp:
+                outs[0]["kind"], outs[0]["http_status"], outs[0]["seq"] = K.AGR_OUT_RESPONSE, resp["status_code"], rec["processed_at"]
+                assert eng.complete(outs)[0] == 0
+                rh = "".join(f"{a}: {b}\n" for a, b in sorted(resp["headers"].items(), key=lambda kv: kv[0].encode())).encode()
+                assert eng.store_response(rec["agent_id"], rid, rh, bytes.fromhex(resp["body_hex"]))
+            assert eng.get_record_json(rec["agent_id"], rid).decode() == k["json"], k["name"]
+        done += 1
+    assert done >= 5
