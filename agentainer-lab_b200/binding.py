@@ -519,7 +519,7 @@ class Engine:
         return True
 
     def get_record_json(self, agent_id: str, request_id: bytes) -> Optional[bytes]:
-        """The value of agent:{a}:requests:{r}: json.Marshal(requests.Request) (requests.go:101,169,264)."""
+        """The value of agent:{a}:requests:{r}: json.Marshal(requests.Request) (requests.go:101,170,265)."""
         rid = (C.c_uint8 * 16).from_buffer_copy(request_id)
         cap = 1 << 16
         while True:

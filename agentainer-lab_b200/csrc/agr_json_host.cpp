@@ -1,7 +1,7 @@
 // agr_json_host.cpp — host-side reader of the wire form: json.Marshal(requests.Request) -> binary record.
 //
 // The other direction of K5 (agr_k5_json.cu).  The reference keeps every record in Redis as this JSON
-// (requests.go:101,169,264) and reads it back with json.Unmarshal (requests.go:159,216,238; server.go:667,693); a host that
+// (requests.go:101,170,265) and reads it back with json.Unmarshal (requests.go:159,216,238; server.go:669,695); a host that
 // migrates an existing Redis keyspace, or that checks what K5 produced, needs the same reader.  Pure host code: no CUDA
 // call, no handle.  Accepts what encoding/json accepts for this shape: members in any order, unknown members skipped,
 // all string escapes incl. surrogate pairs, null for absent maps / slices / pointers, RFC 3339 times with any offset.

@@ -1,6 +1,6 @@
 // agr_k5_json.cu — K5: the wire form of a stored record.
 //
-// The reference keeps every record in Redis as json.Marshal(requests.Request) (requests.go:101,169,264) and its
+// The reference keeps every record in Redis as json.Marshal(requests.Request) (requests.go:101,170,265) and its
 // management surface hands that JSON on: GET /agents/{id}/requests marshals []*Request (server.go:626-652),
 // GET /agents/{id}/requests/{reqId} re-marshals one record (server.go:655-679), the CLI parses both
 // (cmd/agentainer/main.go:1143-1174).  K5 produces those bytes from the binary rows: field order = struct order

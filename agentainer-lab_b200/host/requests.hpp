@@ -72,7 +72,7 @@ class Manager {
     Error GetPendingRequests(const std::string& agentID, std::vector<Request>* out);
     // MarkRequestFailed (requests.go:228-275)
     Error MarkRequestFailed(const std::string& agentID, const std::string& requestID, const std::string& err);
-    // json.Marshal(record) as the reference keeps it in Redis (requests.go:101,169,264; read by server.go:661-668,687-694)
+    // json.Marshal(record) as the reference keeps it in Redis (requests.go:101,170,265; read by server.go:661-669,687-695)
     Error GetRequestJSON(const std::string& agentID, const std::string& requestID, std::string* out);
     // json.Marshal(GetPendingRequests(agentID)) — the "pending" member of GET /agents/{id}/requests (server.go:646-650)
     Error GetPendingRequestsJSON(const std::string& agentID, std::string* out, size_t* count);

@@ -272,9 +272,9 @@ int agr_store_error_text(agr_handle* h, const char* agent_id, const uint8_t requ
 int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len);
 
 /* ------------------------------------------------- JSON wire form (K5) */
-/* The reference stores and serves records as json.Marshal(requests.Request) (requests.go:27-49,101,169,264): the value
+/* The reference stores and serves records as json.Marshal(requests.Request) (requests.go:27-49,101,170,265): the value
  * of the Redis key agent:{a}:requests:{r} read by GET /agents/{id}/requests/{reqId} and the replay handler
- * (server.go:661-668,687-694), and the "pending" array of GET /agents/{id}/requests (server.go:626-652).  K5 produces
+ * (server.go:661-669,687-695), and the "pending" array of GET /agents/{id}/requests (server.go:626-652).  K5 produces
  * exactly those bytes on the device from the binary rows: struct field order, encoding/json string escaping (HTML-safe,
  * invalid UTF-8 -> U+FFFD, U+2028/9 escaped), header maps in key order, []byte as padded std base64, times as RFC 3339
  * with nanoseconds in UTC (agr_record.seq / agr_outcome.seq are read as Unix nanoseconds), omitempty on processed_at /
@@ -293,7 +293,7 @@ int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t reque
 int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* count);
 int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, uint8_t* out, uint64_t cap, uint64_t* len, uint64_t* offsets);
 
-/* The other direction, on the host: json.Unmarshal of that form (requests.go:159,216,238; server.go:667,693) into the
+/* The other direction, on the host: json.Unmarshal of that form (requests.go:159,216,238; server.go:669,695) into the
  * variable-length record form (96-byte header of agr_record + path | flattened headers | body, 16-byte rounded) plus the
  * fields that live outside the record.  Pure host code, no handle, no CUDA call: for migrating an existing Redis keyspace
  * and for checking what K5 produced.  Accepts what encoding/json accepts for this shape (members in any order, unknown

@@ -11,8 +11,8 @@ What the reference marshals (all paths relative to the reference tree):
   * requests.Request, internal/requests/requests.go:27-41 — field order is struct order; `omitempty` on
     processed_at (*time.Time), response (*Response) and error (string);
   * requests.Response, requests.go:44-49;
-  * json.Marshal call sites: requests.go:101 (StoreRequest), :169 (StoreResponse, after Unmarshal of the stored value),
-    :264 (MarkRequestFailed, after Unmarshal), server.go:646-650 / 674-678 (management reads re-marshal).
+  * json.Marshal call sites: requests.go:101 (StoreRequest), :170 (StoreResponse, after Unmarshal of the stored value),
+    :265 (MarkRequestFailed, after Unmarshal), server.go:646-650 / 674-678 (management reads re-marshal).
 
 encoding/json rules used (Go 1.23, src/encoding/json/encode.go):
   * strings: `"` and `\\` backslash-escaped; \\n \\r \\t \\b \\f short forms (\\b, \\f since Go 1.22); other bytes < 0x20 as
