@@ -39,7 +39,8 @@ class AgrStats(C.Structure):
         "rows_used", "rows_cap", "ingested", "stored", "replay_flagged", "dedupe_hits", "forwarded", "queued",
         "unavailable", "not_found", "dup_ids", "completions", "completion_misses", "failures", "dead_lettered",
         "dial_errors", "replay_scans", "replay_dispatched", "completed_log_len", "failed_log_len",
-        "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches", "rows_tail")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
+        "k1_launches", "k2_launches", "k3_launches", "k4_launches", "k5_launches", "rows_tail", "malformed", "log_overflow",
+        "svc_batches", "svc_ops")] + [("agents", C.c_uint32), ("device", C.c_uint32)]
 
 
 class AgrDecoded(C.Structure):
@@ -155,7 +156,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.agr_abi_version() != 1:
+    if lib.agr_abi_version() != 2:
         raise RuntimeError("ABI version mismatch")
     if path is None:
         _lib = lib
@@ -568,8 +569,12 @@ class Engine:
     def snapshot(self, path: str) -> None:
         _check(self.lib, self.lib.agr_snapshot(self.h, path.encode()))
 
-    def expire(self, now: int, ttl: int) -> int:
-        """Drop the records whose last SET is ttl or more before now (the reference's 24 h key TTL); returns how many."""
+    def expire(self, now: int, ttl: int, want_count: bool = True) -> Optional[int]:
+        """Drop the records whose last SET is ttl or more before now (the reference's 24 h key TTL); returns how many
+        (want_count=False: no count, and the call does not wait for the sweep)."""
+        if not want_count:
+            _check(self.lib, self.lib.agr_expire(self.h, now, ttl, None))
+            return None
         n = C.c_uint64()
         _check(self.lib, self.lib.agr_expire(self.h, now, ttl, C.byref(n)))
         return int(n.value)

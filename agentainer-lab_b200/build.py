@@ -1,47 +1,75 @@
 """In-tree build of the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+import hashlib
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
 LIBNAME = "libagentainer_b200.so"
-SOURCES = ["agr_kernels.cu", "agr_k1_tma.cu", "agr_k1_var.cu", "agr_k4.cu", "agr_k5_json.cu", "agr_json_host.cpp", "agr_engine.cu"]
-HEADERS = ["agr_common.h", "agr_synth.h", "agr_kernels.cuh", "agr_device.cuh", os.path.join("..", "..", "include", "agentainer_gpu.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["agr_kernels.cu", "agr_k1_tma.cu", "agr_k1_var.cu", "agr_k4.cu", "agr_k5_json.cu", "agr_svc.cu", "agr_json_host.cpp", "agr_engine.cu"]
+HEADERS = ["agr_common.h", "agr_synth.h", "agr_kernels.cuh", "agr_device.cuh", "agr_svc.h", os.path.join("..", "..", "include", "agentainer_gpu.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def lib_path() -> str:
     return os.path.join(LIBDIR, LIBNAME)
 
 
+def source_hash() -> str:
+    """sha256 over every source, header and the compiler flags: what the built library is a function of."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p):
+            h.update(f.encode()); h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def _stamp_path() -> str:
+    return lib_path() + ".srchash"
+
+
 def _stale() -> bool:
-    out = lib_path()
-    if not os.path.exists(out):
+    """The library is stale when it is missing or was built from other sources than the ones in the tree (content hash, not
+    mtime: a checkout or a copy to another machine changes mtimes but not what the binary was compiled from)."""
+    if not os.path.exists(lib_path()) or not os.path.exists(_stamp_path()):
         return True
-    t = os.path.getmtime(out)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    return open(_stamp_path()).read().strip() != source_hash()
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into lib/libagentainer_b200.so.  Returns the library path."""
+    """Compile csrc/* into lib/libagentainer_b200.so (one nvcc per translation unit, in parallel, then one link)."""
     if not force and not _stale():
         return lib_path()
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libagentainer_b200.so (and there is no CPU fallback)")
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", lib_path(), "-lcudart", "-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    os.makedirs(OBJDIR, exist_ok=True)
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas=-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, _, res in results:
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [o for _, o, _ in results] + [
+        "-o", lib_path(), "-lcudart", "-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    with open(_stamp_path(), "w") as f:
+        f.write(source_hash() + "\n")
     return lib_path()
 
 

@@ -4,7 +4,7 @@
 //   slab      : rows of 512 B (agr_record), row index = rid, rows are handed out in arrival order and never
 //               move; the slab IS the arrival log, so "FIFO within an agent" == ascending rid.
 //   state[rid]: u32  status | INQ | INFLIGHT | STORED | retry | max_retries      (K1 writes, K2 RMWs, K3 reads)
-//   route[rid]: u32  agent slot | verdict | verdict flags                        (K1 writes, K2/K3 read)
+//   route[rid]: u32  agent slot(23) | verdict(3) | verdict flags(6)                       (K1 writes, K2/K3 read)
 //   aux[rid]  : u32  response status | error kind                                (K2 writes)
 //   cksum[rid]: u64  position-weighted checksum of the 512 B record              (K1 writes)
 //   head[rid] : u32  K2 per-batch chain head of the row
@@ -55,11 +55,11 @@ AGR_HD uint32_t st_retry(uint32_t s) { return (s & ST_RETRY_MASK) >> ST_RETRY_SH
 AGR_HD uint32_t st_max(uint32_t s) { return (s & ST_MAX_MASK) >> ST_MAX_SHIFT; }
 
 // ---- route word
-#define RT_SLOT_MASK 0x00ffffffu
-#define RT_SLOT_NONE 0x00ffffffu
-#define RT_CODE_SHIFT 24
-#define RT_CODE_MASK 0x07000000u
-#define RT_FLAG_SHIFT 27   // AGR_VF_* << 27
+#define RT_SLOT_MASK 0x007fffffu
+#define RT_SLOT_NONE 0x007fffffu
+#define RT_CODE_SHIFT 23
+#define RT_CODE_MASK 0x03800000u
+#define RT_FLAG_SHIFT 26   // AGR_VF_* << 26 (six flag bits)
 AGR_HD uint32_t rt_slot(uint32_t r) { return r & RT_SLOT_MASK; }
 AGR_HD uint32_t rt_code(uint32_t r) { return (r & RT_CODE_MASK) >> RT_CODE_SHIFT; }
 AGR_HD uint32_t rt_flags(uint32_t r) { return r >> RT_FLAG_SHIFT; }
@@ -69,6 +69,8 @@ AGR_HD uint32_t rt_flags(uint32_t r) { return r >> RT_FLAG_SHIFT; }
 
 #define AGR_RID_NONE 0xffffffffu
 #define AGR_CFGI_SPLIT_INDEX 0x10000u   // internal cfg_flags bit: K1 runs as stream kernel + k1_index kernel
+#define AGR_CFGI_HOLES 0x20000u         // internal cfg_flags bit (set per launch by the exchange path): rows whose record carries
+#define AGR_FI_HOLE 0x80000000u         // AGR_FI_HOLE in its flags were emptied by K4 (shipped to their owner shard) and are skipped
 
 // ---- dedupe-index slot.  key == 0 means empty (a UUIDv4 is never all-zero); inv_rid = ~rid so that a zeroed
 // slot is "no rid yet" and atomicMax keeps the LOWEST rid (arrival order wins among duplicate ids).

@@ -6,6 +6,7 @@
 // There is NO CPU fallback: every state transition happens in the kernels of agr_kernels.cu.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/random.h>
 #include <nccl.h>      // types only: every NCCL symbol is resolved with dlopen/dlsym at run time
 #include <stdint.h>
 #include <stdio.h>
@@ -22,6 +23,11 @@
 
 #include "../../include/agentainer_gpu.h"
 #include "agr_kernels.cuh"
+#include "agr_svc.h"
+#include <atomic>
+#include <chrono>
+#include <immintrin.h>
+#include <sched.h>
 
 static_assert(sizeof(agr_record) == 512, "agr_record must be 512 B");
 static_assert(sizeof(agr_outcome) == 64, "agr_outcome must be 64 B");
@@ -30,6 +36,7 @@ static_assert(sizeof(agr_verdict) == 8, "agr_verdict must be 8 B");
 static_assert(sizeof(agr_slot) == 32, "agr_slot must be 32 B");
 static_assert(sizeof(agr_agent_key) == 48, "agr_agent_key must be 48 B");
 static_assert(sizeof(agr_dop) == 32, "agr_dop must be 32 B");
+static_assert(sizeof(agr_k2op) == 16, "agr_k2op must be 16 B");
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -60,6 +67,7 @@ struct agr_handle {
     uint64_t released_total = 0;
     uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
+    uint64_t sweep_clean = 0; // TTL sweep: rows below were ingested when agr_expire last ran (their chunks' time bounds are valid)
     // host agent map + mirror
     std::unordered_map<std::string, uint32_t> slot_of;
     std::vector<std::string> agent_names;
@@ -74,8 +82,11 @@ struct agr_handle {
     agr_outcome* h_outs = nullptr;             // pinned [max_batch]
     agr_outcome* d_outs = nullptr;             // [max_batch]
     int32_t* h_results = nullptr;              // pinned [max_batch]
-    agr_k2_scratch k2{};
+    agr_k2_scratch k2{}; uint32_t k2_cap = 0;   // K2 scratch sized for k2_cap outcomes
+    uint32_t* d_hrid = nullptr;                // rows found by the single-key resolve (k_resolve)
+    uint32_t* h_k2flag = nullptr;              // pinned: k2_append's overflow flag of the last batch
     agr_dop* d_ops = nullptr;
+    std::vector<std::pair<uint64_t, uint64_t>> resv;   // rows handed out by agr_reserve_rows and not ingested yet: [first, end)
     // K3
     uint32_t* d_matrix = nullptr; size_t matrix_entries = 0;
     uint32_t* d_gtotal = nullptr; uint32_t* d_goff = nullptr;
@@ -101,21 +112,8 @@ struct agr_handle {
     uint8_t* d_json = nullptr; uint64_t json_cap = 0;
     uint64_t k5_launches = 0;
     uint64_t expired_total = 0;                // records dropped by agr_expire so far
-    // flat-combining front-end for concurrent small ingests (AGR_CFG_COMBINE)
-    std::mutex cmu; std::condition_variable ccv;
-    agr_record* c_ring = nullptr;              // pinned [AGR_COMBINE_RING]
-    agr_verdict* c_verd = nullptr; uint8_t* c_ids = nullptr; int32_t* c_rc = nullptr; uint64_t* c_rid = nullptr;
-    uint64_t c_head = 0, c_taken = 0, c_done = 0;   // slots assigned / handed to a leader / finished
-    uint64_t c_low = 0;                        // every slot below has been collected by its owner (ring space is [c_low, c_head))
-    std::vector<uint8_t> c_flag;               // [AGR_COMBINE_RING] collected marks for out-of-order owners
-    bool c_leader = false;
-    uint64_t c_batches = 0, c_records = 0;
-    // the same for agr_complete
-    std::mutex kmu; std::condition_variable kcv;
-    agr_outcome* k_ring = nullptr; int32_t* k_res = nullptr; int32_t* k_rc = nullptr;
-    uint64_t k_head = 0, k_taken = 0, k_done = 0, k_low = 0;
-    std::vector<uint8_t> k_flag;
-    bool k_leader = false;
+    // single-request front end (AGR_CFG_COMBINE): pinned op ring + dispatcher thread + resident service kernel (agr_svc.h)
+    struct svc_host* svc = nullptr;
     // variable-length mode
     uint64_t vused = 0, vcap = 0;               // bytes appended so far (ring: logical, pads included) / capacity
     uint64_t vtail = 0;                        // ring: logical offset of the first byte that has not been released
@@ -139,8 +137,6 @@ struct agr_handle {
     bool op_timed[3] = {false, false, false};
 };
 #define AGR_TIMING_RING 1024
-#define AGR_COMBINE_RING 16384u
-#define AGR_COMBINE_MAX 32u
 
 template <typename T>
 static int dev_alloc(agr_handle* h, T** p, size_t count, bool zero) {
@@ -192,6 +188,20 @@ static int host_regrow(agr_handle* h, T** p, size_t count) {
     return 0;
 }
 #define TRY(x) do { int r_ = (x); if (r_ < 0) return r_; } while (0)
+
+// K2 scratch for up to n outcomes per batch
+static int k2_scratch_alloc(agr_handle* h, size_t n) {
+    TRY(dev_alloc(h, &h->k2.ops, n, false));
+    TRY(dev_alloc(h, &h->k2.nxt, n, false));
+    TRY(dev_alloc(h, &h->k2.eff, n + 8, false));
+    TRY(dev_alloc(h, &h->k2.results, n, false));
+    const size_t tiles = agr_k2_tiles((uint32_t)n) + 1;
+    TRY(dev_alloc(h, &h->k2.tiles, tiles + 1, true));
+    h->k2.ticket = (uint32_t*)(h->k2.tiles + tiles);
+    h->k2.overflow = h->k2.ticket + 1;
+    h->k2_cap = (uint32_t)n;
+    return 0;
+}
 
 // ---- logical rows (arrival numbers, what the API speaks) vs physical rows (where the record lives; see agr_dev)
 static inline bool is_ring(const agr_handle* h) { return (h->cfg.flags & AGR_CFG_RING) != 0; }
@@ -249,6 +259,274 @@ static void pack_agent_id(const char* id, unsigned long long w[4]) {
     memcpy(w, buf, 32);
 }
 
+
+// ------------------------------------------------------------------------------------------ single-request front end
+// Host side of agr_svc.h.  Lock-free for the callers: one fetch_add claims ring slots, the payload is written into pinned
+// device-mapped memory, a release store publishes it, and the caller waits on a word the GPU writes.  One dispatcher thread
+// per handle turns the published prefix of the ring into batch descriptors; the resident service kernel (k_svc) does the rest.
+extern "C" { static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first); }
+cudaError_t agr_launch_svc(const agr_dev& d, const svc_dev& v, const agr_k2_scratch& k2, unsigned long long next_seq, cudaStream_t st);
+unsigned long long agr_svc_desc_check(const svc_desc* dsc);
+
+struct svc_host {
+    // pinned, device-mapped
+    svc_desc* desc = nullptr; uint8_t* payload = nullptr; svc_res* res = nullptr; svc_ctl* ctl = nullptr;
+    // host only
+    std::atomic<uint64_t> head{0};                      // next ring slot to hand out (absolute number)
+    std::atomic<uint32_t>* ready = nullptr;             // [SVC_SLOTS] lap + 1 once the slot's payload is complete
+    std::atomic<uint32_t>* free_lap = nullptr;          // [SVC_SLOTS] the lap that may write the slot (previous user has collected)
+    uint8_t* kind = nullptr;                            // [SVC_SLOTS] SVC_OP_* of the published op
+    uint64_t taken = 0;                                 // dispatcher: first slot not yet put into a batch
+    uint64_t seq = 0;                                   // dispatcher: last batch number published
+    bool running = false;                               // service kernel resident (changed under the handle mutex only)
+    std::chrono::steady_clock::time_point started;      // when it was launched
+    agr_k2_scratch k2{};                                // K2 scratch of the service kernel (SVC_MAX_OPS ops)
+    uint32_t* d_dupfix = nullptr;
+    std::thread thr;
+    std::atomic<bool> shutdown{false}, sleeping{false};
+    std::mutex smu; std::condition_variable scv;        // the dispatcher sleeps here when the ring has been empty for a while
+    std::atomic<uint64_t> batches{0}, ops{0};
+    std::atomic<int> fatal{0};                          // a CUDA error in the dispatcher: every later call fails with it
+};
+
+static inline void cpu_relax(uint32_t& spins) {
+    if (++spins < 4096u) _mm_pause();
+    else { sched_yield(); }
+}
+
+// stops the resident kernel; the caller holds h->mu, so no new batch can be published meanwhile
+static int svc_stop_locked(agr_handle* h) {
+    svc_host* s = h->svc;
+    if (!s || !s->running) return 0;
+    s->ctl->stop = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    s->ctl->stop = 0;
+    s->running = false;
+    if (e != cudaSuccess) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, std::string("service kernel: ") + cudaGetErrorString(e)); }
+    if (s->ctl->done_seq != s->seq) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, "service kernel left with batches unprocessed"); }
+    return 0;
+}
+static int svc_start_locked(agr_handle* h) {
+    svc_host* s = h->svc;
+    if (s->running) return 0;
+    svc_dev v{};
+    v.desc = s->desc; v.payload = s->payload; v.res = s->res; v.ctl = s->ctl; v.dupfix = s->d_dupfix;
+    v.idle_ns = 2000000000ULL;                                   // safety only: the dispatcher stops the kernel long before
+    s->ctl->state = 1; s->ctl->stop = 0;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    sync_window(h);
+    cudaError_t e = agr_launch_svc(h->d, v, s->k2, s->seq + 1, h->stream);
+    if (e != cudaSuccess) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, std::string("service kernel launch: ") + cudaGetErrorString(e)); }
+    s->running = true;
+    s->started = std::chrono::steady_clock::now();
+    return 0;
+}
+
+// the handle lock every entry point other than the single-request path takes: the resident kernel owns the handle's stream
+// while it runs, so it is stopped first (it finishes the batches already published) and started again by the dispatcher
+struct HLock {
+    agr_handle* h;
+    explicit HLock(agr_handle* h_) : h(h_) {
+        h->mu.lock();
+        if (h->svc && h->svc->running) { cudaSetDevice(h->device); svc_stop_locked(h); }
+    }
+    ~HLock() { h->mu.unlock(); }
+    HLock(const HLock&) = delete; HLock& operator=(const HLock&) = delete;
+};
+
+// fails every op of [from, to) from the host side (slab full, CUDA error): the callers see result = rc
+static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only) {
+    for (uint64_t a = from; a < to; ++a) {
+        const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
+        if (records_only && s->kind[slot] != SVC_OP_RECORD) continue;
+        s->res[slot].result = rc;
+        std::atomic_thread_fence(std::memory_order_release);
+        s->res[slot].done = (uint32_t)(a / SVC_SLOTS) + 1u;
+    }
+}
+
+static void svc_dispatcher(agr_handle* h) {
+    svc_host* s = h->svc;
+    cudaSetDevice(h->device);
+    auto last_work = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    while (!s->shutdown.load(std::memory_order_acquire)) {
+        // the contiguous published prefix [taken, to)
+        uint64_t to = s->taken;
+        uint32_t nrec = 0;
+        while (to - s->taken < SVC_MAX_OPS) {
+            const uint32_t slot = (uint32_t)(to & (SVC_SLOTS - 1u));
+            if (s->ready[slot].load(std::memory_order_acquire) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
+            if (s->kind[slot] == SVC_OP_RECORD) { if (nrec == 256u) break; nrec++; }
+            to++;
+        }
+        const auto now = std::chrono::steady_clock::now();
+        if (to == s->taken) {
+            const auto idle = std::chrono::duration_cast<std::chrono::microseconds>(now - last_work).count();
+            if (idle > 2000) {
+                // nothing for 2 ms: give the GPU (and this core) back; the next caller wakes us up
+                { std::lock_guard<std::mutex> hl(h->mu); if (s->running) svc_stop_locked(h); }
+                std::unique_lock<std::mutex> lk(s->smu);
+                s->sleeping.store(true, std::memory_order_seq_cst);
+                const uint32_t slot = (uint32_t)(s->taken & (SVC_SLOTS - 1u));
+                if (s->ready[slot].load(std::memory_order_seq_cst) != (uint32_t)(s->taken / SVC_SLOTS) + 1u && !s->shutdown.load())
+                    s->scv.wait_for(lk, std::chrono::milliseconds(50));
+                s->sleeping.store(false, std::memory_order_seq_cst);
+                last_work = std::chrono::steady_clock::now();
+            } else {
+                cpu_relax(spins);
+            }
+            continue;
+        }
+        spins = 0;
+        last_work = now;
+        // never more than SVC_DESCS / 2 batches ahead of the kernel (a descriptor slot is reused after SVC_DESCS batches)
+        { uint32_t w = 0; while (s->running && s->seq - s->ctl->done_seq >= SVC_DESCS / 2) cpu_relax(w); }
+        std::lock_guard<std::mutex> hl(h->mu);
+        if (s->fatal.load()) { svc_fail_ops(s, s->taken, to, s->fatal.load(), false); s->taken = to; continue; }
+        // a resident kernel blocks device-wide synchronisations of other threads (cudaFree ...): let it go every 20 ms
+        if (s->running && std::chrono::duration_cast<std::chrono::milliseconds>(now - s->started).count() > 20) svc_stop_locked(h);
+        uint64_t first = 0;
+        bool have_rows = true;
+        if (nrec) {
+            if (reserve_rows_locked(h, nrec, &first) < 0) { svc_fail_ops(s, s->taken, to, AGR_ENOSPC, true); have_rows = false; }
+        }
+        svc_desc dsc{};
+        for (uint64_t a = s->taken; a < to; ++a) {
+            const uint32_t k = (uint32_t)(a - s->taken);
+            uint32_t kd = s->kind[a & (SVC_SLOTS - 1u)];
+            if (kd == SVC_OP_RECORD && !have_rows) kd = SVC_OP_SKIP;
+            dsc.kinds[k >> 4] |= kd << ((k & 15u) * 2u);
+        }
+        dsc.from = s->taken; dsc.count = (uint32_t)(to - s->taken); dsc.n_records = have_rows ? nrec : 0u;
+        dsc.first_l = first; dsc.first_p = (uint32_t)phys_row(h, first);
+        dsc.tail = h->tail; dsc.head_l = h->rows_used; dsc.tail_phys = is_ring(h) ? (uint32_t)(h->tail % h->cfg.slab_rows) : 0u;
+        dsc.idx_base = h->d.idx_base;
+        dsc.seq = s->seq + 1;
+        dsc.check = agr_svc_desc_check(&dsc);
+        svc_desc* slot = s->desc + (dsc.seq % SVC_DESCS);
+        // the batch number goes last; the kernel also verifies the check word, so a torn read is never accepted
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(&dsc);
+        volatile uint64_t* dst = reinterpret_cast<volatile uint64_t*>(slot);
+        for (int i = 0; i < 31; ++i) dst[i] = src[i];
+        std::atomic_thread_fence(std::memory_order_release);
+        dst[31] = src[31];
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        s->seq = dsc.seq;
+        s->taken = to;
+        s->batches.fetch_add(1, std::memory_order_relaxed);
+        s->ops.fetch_add(dsc.count, std::memory_order_relaxed);
+        h->k1_launches += nrec ? 1 : 0;                         // accounting: batches with records / with outcomes served by k_svc
+        h->k2_launches += (dsc.count > nrec) ? 1 : 0;
+        if (!s->running && svc_start_locked(h) < 0) {
+            // could not launch: nothing will ever process this batch — fail it from here
+            svc_fail_ops(s, dsc.from, to, AGR_ECUDA, false);
+        }
+    }
+    std::lock_guard<std::mutex> hl(h->mu);
+    cudaSetDevice(h->device);
+    svc_stop_locked(h);
+}
+
+static int svc_create(agr_handle* h) {
+    svc_host* s = new svc_host();
+    h->svc = s;
+    auto pin = [&](void** p, size_t bytes) -> int {
+        cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) return fail(AGR_ENOMEM, std::string("cudaHostAlloc (request ring): ") + cudaGetErrorString(e));
+        memset(*p, 0, bytes);
+        h->host_allocs.push_back(*p);
+        return 0;
+    };
+    TRY(pin((void**)&s->desc, sizeof(svc_desc) * SVC_DESCS));
+    TRY(pin((void**)&s->payload, (size_t)SVC_SLOTS * SVC_PAYLOAD));
+    TRY(pin((void**)&s->res, sizeof(svc_res) * SVC_SLOTS));
+    TRY(pin((void**)&s->ctl, sizeof(svc_ctl)));
+    s->ready = new std::atomic<uint32_t>[SVC_SLOTS];
+    s->free_lap = new std::atomic<uint32_t>[SVC_SLOTS];
+    s->kind = new uint8_t[SVC_SLOTS];
+    for (uint32_t i = 0; i < SVC_SLOTS; ++i) { s->ready[i].store(0); s->free_lap[i].store(0); s->kind[i] = 0; }
+    TRY(dev_alloc(h, &s->k2.ops, (size_t)SVC_MAX_OPS, false));
+    TRY(dev_alloc(h, &s->k2.nxt, (size_t)SVC_MAX_OPS, false));
+    TRY(dev_alloc(h, &s->k2.eff, (size_t)SVC_MAX_OPS + 8, false));
+    TRY(dev_alloc(h, &s->k2.results, (size_t)SVC_MAX_OPS, false));
+    TRY(dev_alloc(h, &s->d_dupfix, (size_t)4, true));
+    CK(cudaStreamSynchronize(h->stream));
+    s->thr = std::thread(svc_dispatcher, h);
+    return 0;
+}
+static void svc_destroy(agr_handle* h) {
+    svc_host* s = h->svc;
+    if (!s) return;
+    if (s->thr.joinable()) {
+        s->shutdown.store(true, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_all(); }
+        s->thr.join();
+    }
+    delete[] s->ready; delete[] s->free_lap; delete[] s->kind;
+    h->svc = nullptr;
+    delete s;
+}
+
+// caller side: claim n slots, write the payloads, publish, wake the dispatcher if it sleeps.  Returns the first slot.
+static uint64_t svc_submit(svc_host* s, uint32_t kind, const void* items, size_t item_bytes, uint32_t n) {
+    const uint64_t pos = s->head.fetch_add(n, std::memory_order_relaxed);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t a = pos + i;
+        const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
+        uint32_t w = 0;
+        while (s->free_lap[slot].load(std::memory_order_acquire) != lap) cpu_relax(w);    // the slot's previous user has collected
+        memcpy(s->payload + (size_t)slot * SVC_PAYLOAD, (const uint8_t*)items + (size_t)i * item_bytes, item_bytes);
+        s->kind[slot] = (uint8_t)kind;
+        s->ready[slot].store(lap + 1u, std::memory_order_release);
+    }
+    if (s->sleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_one(); }
+    return pos;
+}
+static inline const svc_res* svc_wait(svc_host* s, uint64_t a) {
+    const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), want = (uint32_t)(a / SVC_SLOTS) + 1u;
+    const svc_res* r = s->res + slot;
+    uint32_t w = 0;
+    while (r->done != want) cpu_relax(w);
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return r;
+}
+static inline void svc_release(svc_host* s, uint64_t a) {
+    s->free_lap[a & (SVC_SLOTS - 1u)].store((uint32_t)(a / SVC_SLOTS) + 1u, std::memory_order_release);
+}
+
+static int svc_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
+    svc_host* s = h->svc;
+    const uint64_t pos = svc_submit(s, SVC_OP_RECORD, recs, sizeof(agr_record), n);
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const svc_res* r = svc_wait(s, pos + i);
+        if (r->result < 0) rc = r->result;
+        else {
+            if (out) memcpy(&out[i], r->verdict, sizeof(agr_verdict));
+            if (ids) memcpy(ids[i], r->id, 16);
+            if (i == 0 && first_rid) *first_rid = r->rid;   // records of one call sit in consecutive slots of one batch... or of two
+        }
+        svc_release(s, pos + i);
+    }
+    if (rc < 0) return fail(rc, rc == AGR_ENOSPC ? "slab full" : "single-request front end: CUDA error");
+    return 0;
+}
+static int svc_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
+    svc_host* s = h->svc;
+    const uint64_t pos = svc_submit(s, SVC_OP_OUTCOME, outs, sizeof(agr_outcome), n);
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const svc_res* r = svc_wait(s, pos + i);
+        if (r->result < 0 && r->result != AGR_ENOTFOUND) rc = r->result;
+        if (results) results[i] = r->result;
+        svc_release(s, pos + i);
+    }
+    if (rc < 0) return fail(rc, "single-request front end: CUDA error");
+    return 0;
+}
+
 extern "C" {
 
 uint32_t agr_abi_version(void) { return AGR_ABI_VERSION; }
@@ -288,13 +566,13 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     if (!mint && c.table_slots < c.slab_rows + c.slab_rows / 4) return fail(AGR_EINVAL, "table_slots must be >= 1.25 * slab_rows");
     if (c.table_slots > (1ull << 32)) return fail(AGR_EINVAL, "table_slots must be <= 2^32");
     if (c.max_agents == 0) c.max_agents = 4096;
-    if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^24 - 1");
+    if (c.max_agents >= RT_SLOT_NONE) return fail(AGR_EINVAL, "max_agents must be < 2^23 - 1");
     if (c.max_batch == 0) c.max_batch = 1u << 20;
     if (c.flags & AGR_CFG_RING) {
         if (c.max_batch > c.slab_rows / 2) c.max_batch = (uint32_t)(c.slab_rows / 2);
         if (c.max_batch == 0) return fail(AGR_EINVAL, "AGR_CFG_RING: slab_rows too small");
     }
-    if (c.log_entries == 0) c.log_entries = c.slab_rows * 2;
+    if (c.log_entries == 0) c.log_entries = c.slab_rows * 3;   // a replayed request pushes twice (Q7), plus once per earlier retry
     if ((c.k1_variant & 0xfu) == 0) c.k1_variant |= 4u;      // default K1 shape: TMA, 14 warps x 1 stage, fused index
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(AGR_ENODEV, "no CUDA device visible (this library has no CPU fallback)"); }
@@ -358,8 +636,15 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.ptime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.mtime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
-    d.id_secret = c.id_secret ? c.id_secret : 0x6a09e667f3bcc908ULL;
-    d.shard_id = 0; d.id_gen = 1; d.tail = 0; d.head_l = 0; d.ring_rows = 0; d.tail_phys = 0;
+    TRY(dev_alloc(h, &d.cmin, (size_t)(c.slab_rows / AGR_CHUNK_ROWS + 2), true));
+    // the key of the id permutation: drawn from the OS CSPRNG unless the caller brings one (a restore passes the snapshot's),
+    // so that ids of one engine instance never resolve in another and cannot be guessed (the reference mints uuid.New())
+    d.id_secret = c.id_secret;
+    while (d.id_secret == 0) {
+        if (getrandom(&d.id_secret, sizeof d.id_secret, 0) != (ssize_t)sizeof d.id_secret) return fail(AGR_EINVAL, "getrandom failed: pass agr_config.id_secret");
+    }
+    h->cfg.id_secret = d.id_secret;
+    d.shard_id = 0; d.id_gen = 1; d.tail = 0; d.head_l = 0; d.ring_rows = 0; d.tail_phys = 0; d.idx_base = 0;
     if (!varlen && (c.k1_variant & 0xfu) != AGR_K1_LSU && agr_k1_tma_make_map(d.slab, c.slab_rows, h->tmap) != 0)
         return fail(AGR_ECUDA, "cuTensorMapEncodeTiled failed for the slab");
     d.cfg_flags = c.flags & 0xffffu;
@@ -379,29 +664,15 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->d_outs, c.max_batch, false));
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
-    if (c.flags & AGR_CFG_COMBINE) {
-        TRY(host_alloc(h, &h->c_ring, (size_t)AGR_COMBINE_RING));
-        TRY(host_alloc(h, &h->c_verd, (size_t)AGR_COMBINE_RING));
-        TRY(host_alloc(h, &h->c_ids, (size_t)AGR_COMBINE_RING * 16));
-        TRY(host_alloc(h, &h->c_rc, (size_t)AGR_COMBINE_RING));
-        TRY(host_alloc(h, &h->c_rid, (size_t)AGR_COMBINE_RING));
-        h->c_flag.assign(AGR_COMBINE_RING, 0);
-        TRY(host_alloc(h, &h->k_ring, (size_t)AGR_COMBINE_RING));
-        TRY(host_alloc(h, &h->k_res, (size_t)AGR_COMBINE_RING));
-        TRY(host_alloc(h, &h->k_rc, (size_t)AGR_COMBINE_RING));
-        h->k_flag.assign(AGR_COMBINE_RING, 0);
-    }
-    TRY(dev_alloc(h, &h->d_ops, c.max_batch, false));
-    h->k2.ops = h->d_ops;
-    TRY(dev_alloc(h, &h->k2.nxt, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.hrid, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.eff, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.results, c.max_batch, false));
-    TRY(dev_alloc(h, &h->k2.chunk_base, (size_t)2048 + 8, false));
+    TRY(dev_alloc(h, &h->d_ops, (size_t)16, false));
+    TRY(dev_alloc(h, &h->d_hrid, (size_t)16, false));
+    TRY(host_alloc(h, &h->h_k2flag, (size_t)4));
+    TRY(k2_scratch_alloc(h, c.max_batch));
     TRY(dev_alloc(h, &h->d_gtotal, ((size_t)c.max_agents + 8) * 66, false));   // gtotal + 64 segment partials per group
     TRY(dev_alloc(h, &h->d_goff, (size_t)c.max_agents + 2, false));
     TRY(dev_alloc(h, &h->d_min_inq, (size_t)1, false));
     CK(cudaStreamSynchronize(h->stream));
+    if ((c.flags & AGR_CFG_COMBINE) && !varlen) TRY(svc_create(h));
     return 0;
 }
 
@@ -417,6 +688,7 @@ int agr_create(const agr_config* cfg, agr_handle** out) {
 
 void agr_destroy(agr_handle* h) {
     if (!h) return;
+    svc_destroy(h);
     if (h->stream) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
     for (void* p : h->dev_allocs) cudaFree(p);
     for (void* p : h->host_allocs) cudaFreeHost(p);
@@ -481,13 +753,13 @@ static int set_agent_state_locked(agr_handle* h, const char* agent_id, uint8_t s
 }
 int agr_set_agent_state(agr_handle* h, const char* agent_id, uint8_t status) {
     if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return set_agent_state_locked(h, agent_id, status, true);
 }
 int agr_set_agent_states(agr_handle* h, const char (*agent_ids)[AGR_AGENT_ID_BYTES], const uint8_t* statuses, uint32_t n, int32_t* slots) {
     if (!h || (n && (!agent_ids || !statuses))) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     const bool bulk = n > 16;                       // many writes: update the host mirror, upload both tables once
     int rc = 0;
@@ -508,7 +780,7 @@ int agr_set_agent_states(agr_handle* h, const char (*agent_ids)[AGR_AGENT_ID_BYT
 
 int agr_agent_slot(agr_handle* h, const char* agent_id) {
     if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     int s = agent_find(h, agent_id);
     if (s < 0 || h->agent_status[s] == AG_STATUS_REMOVED) return fail(AGR_ENOTFOUND, "agent not found");
     return s;
@@ -516,7 +788,7 @@ int agr_agent_slot(agr_handle* h, const char* agent_id) {
 
 int agr_drop_agent(agr_handle* h, const char* agent_id) {
     if (!h || !agent_id) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     int slot = agent_find(h, agent_id);
     if (slot < 0) return fail(AGR_ENOTFOUND, "agent not found");
@@ -532,6 +804,23 @@ int agr_drop_agent(agr_handle* h, const char* agent_id) {
     return 0;
 }
 
+// Rows handed out by agr_reserve_rows hold no record until agr_ingest_rows has run over them.  The replay scan, the pending
+// views and agr_reclaim stop at the first such row: otherwise a scan that finds "nothing pending" above its low-water mark
+// would move the mark past rows that K1 fills in later, and those requests would never be replayed.
+static uint64_t ingested_bound(const agr_handle* h) {
+    uint64_t b = h->rows_used;
+    for (const auto& r : h->resv) b = std::min(b, r.first);
+    return b;
+}
+static void resv_remove(agr_handle* h, uint64_t first, uint64_t end) {
+    std::vector<std::pair<uint64_t, uint64_t>> keep;
+    for (const auto& r : h->resv) {
+        if (r.second <= first || r.first >= end) { keep.push_back(r); continue; }
+        if (r.first < first) keep.emplace_back(r.first, first);
+        if (r.second > end) keep.emplace_back(end, r.second);
+    }
+    h->resv.swap(keep);
+}
 // ------------------------------------------------------------------------------------------ K1
 static int reserve_rows_locked(agr_handle* h, uint32_t n, uint64_t* first) {
     if (!is_ring(h)) {
@@ -584,6 +873,7 @@ static int ingest_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_ver
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     if (n == 0) return 0;
     TRY(launch_k1_locked(h, first, n, out ? h->d_verdicts : nullptr));
+    if (!h->resv.empty()) resv_remove(h, first, first + n);
     if (out) {
         CK(cudaMemcpyAsync(h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -607,18 +897,23 @@ int agr_mint_ids(agr_handle* h, uint64_t first_rid, uint32_t n, uint8_t (*ids)[1
 
 int agr_reserve_rows(agr_handle* h, uint32_t n, uint64_t* first_rid) {
     if (!h || !first_rid) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
-    return reserve_rows_locked(h, n, first_rid);
+    HLock lk(h);
+    TRY(reserve_rows_locked(h, n, first_rid));
+    if (n) {
+        if (!h->resv.empty() && h->resv.back().second == *first_rid) h->resv.back().second += n;   // back-to-back reservations merge
+        else h->resv.emplace_back(*first_rid, *first_rid + n);
+    }
+    return 0;
 }
 int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out) {
     if (!h) return fail(AGR_EINVAL, "NULL handle");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return ingest_rows_locked(h, first_rid, n, out, true);
 }
 int agr_ingest_rows_async(agr_handle* h, uint64_t first_rid, uint32_t n) {
     if (!h) return fail(AGR_EINVAL, "NULL handle");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return ingest_rows_locked(h, first_rid, n, nullptr, false);
 }
@@ -645,62 +940,11 @@ int agr_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* o
 
 static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid);
 
-// Flat combining: the ring order is the event order.  A caller appends its records; if nobody leads, it becomes the leader:
-// it takes everything queued so far (its own records included), runs it as ONE batch through the normal path, publishes the
-// verdicts, and steps down as soon as its own records are done (another waiter then leads the next batch).
-static int combine_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
-    std::unique_lock<std::mutex> lk(h->cmu);
-    h->ccv.wait(lk, [&] { return h->c_head + n - h->c_low <= AGR_COMBINE_RING; });
-    const uint64_t my = h->c_head;
-    h->c_head += n;
-    for (uint32_t i = 0; i < n; ++i) h->c_ring[(my + i) % AGR_COMBINE_RING] = recs[i];
-    while (h->c_done < my + n) {
-        if (h->c_leader) { h->ccv.wait(lk); continue; }
-        h->c_leader = true;
-        const uint64_t from = h->c_taken, to = h->c_head;
-        h->c_taken = to;
-        lk.unlock();
-        for (uint64_t a = from; a < to;) {                      // at most two contiguous pieces of the ring
-            const uint64_t pos = a % AGR_COMBINE_RING;
-            const uint32_t cn = (uint32_t)std::min<uint64_t>(to - a, AGR_COMBINE_RING - pos);
-            uint64_t first = 0;
-            int rc;
-            {
-                std::lock_guard<std::mutex> hl(h->mu);
-                rc = cudaSetDevice(h->device) == cudaSuccess
-                         ? ingest_ex_locked(h, h->c_ring + pos, cn, h->c_verd + pos, (uint8_t(*)[16])(h->c_ids + pos * 16), &first)
-                         : AGR_ECUDA;
-            }
-            for (uint32_t i = 0; i < cn; ++i) { h->c_rc[pos + i] = rc; h->c_rid[pos + i] = first + i; }
-            a += cn;
-        }
-        lk.lock();
-        h->c_batches++; h->c_records += to - from;
-        h->c_done = to;
-        h->c_leader = false;
-        h->ccv.notify_all();
-    }
-    int rc = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t pos = (my + i) % AGR_COMBINE_RING;
-        if (h->c_rc[pos] < 0) rc = h->c_rc[pos];
-        if (out) out[i] = h->c_verd[pos];
-        if (ids) memcpy(ids[i], h->c_ids + pos * 16, 16);
-    }
-    if (first_rid) *first_rid = h->c_rid[my % AGR_COMBINE_RING];   // rows of one caller are consecutive (appended under the lock)
-    if (rc < 0) g_err = "combined ingest failed";
-    for (uint32_t i = 0; i < n; ++i) h->c_flag[(my + i) % AGR_COMBINE_RING] = 1;
-    while (h->c_low < h->c_done && h->c_flag[h->c_low % AGR_COMBINE_RING]) { h->c_flag[h->c_low % AGR_COMBINE_RING] = 0; h->c_low++; }
-    lk.unlock();
-    h->ccv.notify_all();                                          // ring space was released
-    return rc;
-}
-
 int agr_ingest_ex(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     if (h->cfg.flags & AGR_CFG_VARLEN) return fail(AGR_EINVAL, "variable-length engine: use agr_ingest_var");
-    if ((h->cfg.flags & AGR_CFG_COMBINE) && n >= 1 && n <= AGR_COMBINE_MAX) return combine_ingest(h, recs, n, out, ids, first_rid);
-    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->svc && n >= 1 && n <= SVC_MAX_CALL) return svc_ingest(h, recs, n, out, ids, first_rid);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return ingest_ex_locked(h, recs, n, out, ids, first_rid);
 }
@@ -756,53 +1000,10 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
 // ------------------------------------------------------------------------------------------ K2
 static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results);
 
-// flat combining of concurrent small agr_complete calls; same protocol as combine_ingest (ring order = event order)
-static int combine_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
-    std::unique_lock<std::mutex> lk(h->kmu);
-    h->kcv.wait(lk, [&] { return h->k_head + n - h->k_low <= AGR_COMBINE_RING; });
-    const uint64_t my = h->k_head;
-    h->k_head += n;
-    for (uint32_t i = 0; i < n; ++i) h->k_ring[(my + i) % AGR_COMBINE_RING] = outs[i];
-    while (h->k_done < my + n) {
-        if (h->k_leader) { h->kcv.wait(lk); continue; }
-        h->k_leader = true;
-        const uint64_t from = h->k_taken, to = h->k_head;
-        h->k_taken = to;
-        lk.unlock();
-        for (uint64_t a = from; a < to;) {
-            const uint64_t pos = a % AGR_COMBINE_RING;
-            const uint32_t cn = (uint32_t)std::min<uint64_t>(to - a, AGR_COMBINE_RING - pos);
-            int rc;
-            {
-                std::lock_guard<std::mutex> hl(h->mu);
-                rc = cudaSetDevice(h->device) == cudaSuccess ? complete_locked(h, h->k_ring + pos, cn, h->k_res + pos) : AGR_ECUDA;
-            }
-            for (uint32_t i = 0; i < cn; ++i) h->k_rc[pos + i] = rc;
-            a += cn;
-        }
-        lk.lock();
-        h->k_done = to;
-        h->k_leader = false;
-        h->kcv.notify_all();
-    }
-    int rc = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t pos = (my + i) % AGR_COMBINE_RING;
-        if (h->k_rc[pos] < 0) rc = h->k_rc[pos];
-        if (results) results[i] = h->k_res[pos];
-        h->k_flag[pos] = 1;
-    }
-    while (h->k_low < h->k_done && h->k_flag[h->k_low % AGR_COMBINE_RING]) { h->k_flag[h->k_low % AGR_COMBINE_RING] = 0; h->k_low++; }
-    if (rc < 0) g_err = "combined complete failed";
-    lk.unlock();
-    h->kcv.notify_all();
-    return rc;
-}
-
 int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
     if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
-    if ((h->cfg.flags & AGR_CFG_COMBINE) && n >= 1 && n <= AGR_COMBINE_MAX) return combine_complete(h, outs, n, results);
-    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->svc && n >= 1 && n <= SVC_MAX_CALL) return svc_complete(h, outs, n, results);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return complete_locked(h, outs, n, results);
 }
@@ -823,11 +1024,11 @@ static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, i
         for (auto& e : h->op_ev) if (!e) CK(cudaEventCreate(&e));
         CK(cudaEventRecord(h->op_ev[0], h->stream));
     }
-    agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, n, h->stream);
-    agr_launch_k2(h->d, h->k2, n, h->stream);
-    h->k2_launches += 7;
+    agr_launch_k2(h->d, h->d_outs, h->k2, n, h->stream);
+    h->k2_launches += 3;
     CK(cudaGetLastError());
     if (timing) { CK(cudaEventRecord(h->op_ev[1], h->stream)); h->op_timed[0] = true; }
+    CK(cudaMemcpyAsync(h->h_k2flag, h->k2.overflow, 4, cudaMemcpyDeviceToHost, h->stream));
     if (results) {
         CK(cudaMemcpyAsync(h->h_results, h->k2.results, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -835,6 +1036,8 @@ static int complete_locked(agr_handle* h, const agr_outcome* outs, uint32_t n, i
     } else {
         CK(cudaStreamSynchronize(h->stream));
     }
+    // the state transitions were applied; list entries beyond the log capacity were dropped (agr_config.log_entries)
+    if (*h->h_k2flag) return fail(AGR_ENOSPC, "completed / failed log full: entries of this batch were dropped (raise agr_config.log_entries, or agr_reclaim)");
     return 0;
 }
 
@@ -899,12 +1102,12 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
 int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t cap, uint32_t* n) {
     if (!h || !n) return fail(AGR_EINVAL, "NULL argument");
     if ((h->cfg.flags & AGR_CFG_VARLEN) && recs) return fail(AGR_EINVAL, "variable-length engine: use agr_replay_scan_var to gather records");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     *n = 0;
     h->replay_scans++;
     uint32_t total = 0;
-    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, ingested_bound(h), cap, &total));
     *n = total;
     if (total > cap) return fail(AGR_ECAP, "dispatch array too small");
     h->replay_dispatched += total;
@@ -925,13 +1128,13 @@ int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t
 
 int agr_pending(agr_handle* h, const char* agent_id, agr_record* out, uint32_t cap, uint32_t* n) {
     if (!h || !agent_id || !n) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     *n = 0;
     int slot = agent_find(h, agent_id);
     if (slot < 0) return 0;     // LRANGE on a missing key is an empty list
     uint32_t total = 0;
-    TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, ingested_bound(h), cap, &total));
     *n = total;
     if (total > cap) return fail(AGR_ECAP, "output array too small");
     if (total == 0 || !out) return 0;
@@ -949,7 +1152,7 @@ int agr_pending(agr_handle* h, const char* agent_id, agr_record* out, uint32_t c
 int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16], uint32_t cap, uint32_t* n) {
     if (!h || !agent_id || !n) return fail(AGR_EINVAL, "NULL argument");
     if (which < AGR_LIST_PENDING || which > AGR_LIST_FAILED) return fail(AGR_EINVAL, "bad list selector");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     *n = 0;
     int slot = agent_find(h, agent_id);
@@ -957,7 +1160,7 @@ int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16],
     uint32_t total = 0;
     if (which == AGR_LIST_PENDING) {
         // LRANGE: ids of expired records are still in the list; they lie below the scan's low-water mark
-        TRY(select_locked(h, K3_AGENT_PENDING_IDS, (uint32_t)slot, nullptr, h->expired_total ? h->tail : h->scan_lo, h->rows_used, cap, &total));
+        TRY(select_locked(h, K3_AGENT_PENDING_IDS, (uint32_t)slot, nullptr, h->expired_total ? h->tail : h->scan_lo, ingested_bound(h), cap, &total));
     } else {
         unsigned long long lens[2];
         CK(cudaMemcpyAsync(lens, h->d.log_len, sizeof lens, cudaMemcpyDeviceToHost, h->stream));
@@ -983,7 +1186,7 @@ int agr_list(agr_handle* h, const char* agent_id, int which, uint8_t (*ids)[16],
 // storage.Get("agent:{a}:requests:{r}") (server.go:661-662): read-only resolve in the dedupe index, then a 1-row gather
 int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id[16], agr_record* out) {
     if (!h || !agent_id || !request_id || !out) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     int slot = agent_find(h, agent_id);
     if (slot < 0) return fail(AGR_ENOTFOUND, "request not found");
@@ -992,14 +1195,14 @@ int agr_get_record(agr_handle* h, const char* agent_id, const uint8_t request_id
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
     sync_window(h);
-    agr_launch_resolve(h->d, h->k2, 1, h->stream);
+    agr_launch_resolve(h->d, h->d_ops, h->d_hrid, 1, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_small, h->d_hrid, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
     TRY(ensure_gather(h, AGR_REC));
-    agr_launch_k3_gather(h->d, h->k2.hrid, nullptr, 1, h->d_gather, nullptr, nullptr, h->stream);
+    agr_launch_k3_gather(h->d, h->d_hrid, nullptr, 1, h->d_gather, nullptr, nullptr, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_gather, h->d_gather, AGR_REC, cudaMemcpyDeviceToHost, h->stream));
@@ -1013,7 +1216,7 @@ int agr_ingest_var(agr_handle* h, const uint8_t* blob, const uint32_t* offsets, 
                    uint64_t* first_rid) {
     if (!h || (n && (!blob || !offsets))) return fail(AGR_EINVAL, "NULL argument");
     if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     uint64_t first = 0;
@@ -1099,12 +1302,12 @@ int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_
                         uint32_t* n, uint64_t* blob_bytes) {
     if (!h || !n || !blob_bytes) return fail(AGR_EINVAL, "NULL argument");
     if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     *n = 0; *blob_bytes = 0;
     h->replay_scans++;
     uint32_t total = 0;
-    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, h->rows_used, cap, &total));
+    TRY(select_locked(h, K3_TICK, 0, nullptr, h->scan_lo, ingested_bound(h), cap, &total));
     *n = total;
     if (total > cap) return fail(AGR_ECAP, "dispatch array too small");
     h->replay_dispatched += total;
@@ -1124,7 +1327,7 @@ int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_
 int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
     if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
     if (!(h->cfg.flags & AGR_CFG_VARLEN)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_VARLEN");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     int slot = agent_find(h, agent_id);
     if (slot < 0) return fail(AGR_ENOTFOUND, "request not found");
@@ -1133,12 +1336,12 @@ int agr_get_record_var(agr_handle* h, const char* agent_id, const uint8_t reques
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
     sync_window(h);
-    agr_launch_resolve(h->d, h->k2, 1, h->stream);
-    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    agr_launch_resolve(h->d, h->d_ops, h->d_hrid, 1, h->stream);
+    CK(cudaMemcpyAsync(h->h_small, h->d_hrid, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
     TRY(ensure_out(h, 1));
-    CK(cudaMemcpyAsync(h->d_out_rid, h->k2.hrid, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_out_rid, h->d_hrid, 4, cudaMemcpyDeviceToDevice, h->stream));
     uint64_t bytes = 0;
     std::vector<uint8_t> tmp(AGR_VAR_MAX_RECORD);
     uint64_t offs[2];
@@ -1158,9 +1361,9 @@ static int resolve_one_locked(agr_handle* h, const char* agent_id, const uint8_t
     op.slot = (uint32_t)slot; op.http = 0; op.kind = 0; op.pad = 0; op.seq = 0;
     CK(cudaMemcpyAsync(h->d_ops, h->h_ops, sizeof(agr_dop), cudaMemcpyHostToDevice, h->stream));
     sync_window(h);
-    agr_launch_resolve(h->d, h->k2, 1, h->stream);
+    agr_launch_resolve(h->d, h->d_ops, h->d_hrid, 1, h->stream);
     h->k3_launches += 1;
-    CK(cudaMemcpyAsync(h->h_small, h->k2.hrid, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_small, h->d_hrid, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_small[0] == AGR_RID_NONE) return fail(AGR_ENOTFOUND, "request not found");
     *rid = h->h_small[0];
@@ -1205,7 +1408,7 @@ static int store_bytes_locked(agr_handle* h, const char* agent_id, const uint8_t
 int agr_store_response(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const uint8_t* headers, uint32_t hdr_len,
                        const uint8_t* body, uint32_t body_len) {
     if (!h || !agent_id || !request_id || (hdr_len && !headers) || (body_len && !body)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return store_bytes_locked(h, agent_id, request_id, 0, headers, hdr_len, body, body_len);
 }
@@ -1214,14 +1417,14 @@ int agr_store_response_body(agr_handle* h, const char* agent_id, const uint8_t r
 }
 int agr_store_error_text(agr_handle* h, const char* agent_id, const uint8_t request_id[16], const char* text, uint32_t len) {
     if (!h || !agent_id || !request_id || (len && !text)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     return store_bytes_locked(h, agent_id, request_id, 1, (const uint8_t*)text, len, nullptr, 0);
 }
 
 int agr_get_response_body(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
     if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     uint32_t rid = 0;
     TRY(resolve_one_locked(h, agent_id, request_id, &rid));
@@ -1287,7 +1490,7 @@ static int json_copy_out(agr_handle* h, uint64_t total, uint8_t* out, uint64_t c
 
 int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, uint8_t* out, uint64_t cap, uint64_t* len, uint64_t* offsets) {
     if (!h || !len) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (first_rid + n > h->rows_used || first_rid < h->tail) return fail(AGR_EINVAL, "row range outside the rows in use");
     uint64_t total = 0;
@@ -1305,16 +1508,16 @@ int agr_rows_json(agr_handle* h, uint64_t first_rid, uint32_t n, int as_array, u
 
 int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t cap, uint64_t* len, uint32_t* count) {
     if (!h || !agent_id || !len) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (count) *count = 0;
     uint32_t total_rows = 0;
     int slot = agent_find(h, agent_id);
     if (slot >= 0) {
         const uint32_t cap0 = std::max<uint32_t>(h->out_cap, 1024);
-        TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, cap0, &total_rows));
+        TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, ingested_bound(h), cap0, &total_rows));
         if (total_rows > cap0)                                   // counts only: run again with room for all of it
-            TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, h->rows_used, total_rows, &total_rows));
+            TRY(select_locked(h, K3_AGENT_PENDING, (uint32_t)slot, nullptr, h->scan_lo, ingested_bound(h), total_rows, &total_rows));
     }
     if (count) *count = total_rows;
     if (total_rows == 0) {                                       // var requests []*Request stays nil (requests.go:204): "null"
@@ -1329,12 +1532,12 @@ int agr_pending_json(agr_handle* h, const char* agent_id, uint8_t* out, uint64_t
 
 int agr_get_record_json(agr_handle* h, const char* agent_id, const uint8_t request_id[16], uint8_t* out, uint32_t cap, uint32_t* len) {
     if (!h || !agent_id || !request_id || !len) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     uint32_t rid = 0;
     TRY(resolve_one_locked(h, agent_id, request_id, &rid));
     uint64_t total = 0, l = 0;
-    TRY(json_encode_locked(h, h->k2.hrid, 0, 1, false, &total));   // k2.hrid[0] = the physical row resolve_one_locked found
+    TRY(json_encode_locked(h, h->d_hrid, 0, 1, false, &total));   // k2.hrid[0] = the physical row resolve_one_locked found
     int rc = json_copy_out(h, total, out, cap, &l);
     *len = (uint32_t)l;
     return rc;
@@ -1369,7 +1572,7 @@ static int load_dev(agr_handle* h, FILE* f, void* ddst, size_t bytes) {
 
 int agr_snapshot(agr_handle* h, const char* path) {
     if (!h || !path) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     FILE* f = fopen(path, "wb");
@@ -1445,9 +1648,9 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
         name[AGR_AGENT_ID_BYTES - 1] = 0;
         const bool removed = (st == AG_STATUS_REMOVED);
         if ((rc = agr_set_agent_state(h, name, removed ? (uint8_t)AGR_AGENT_STOPPED : st)) < 0) return bail(rc);
-        if (removed) { std::lock_guard<std::mutex> lk(h->mu); h->agent_status[a] = AG_STATUS_REMOVED; if ((rc = push_agent_status(h, a, AG_STATUS_REMOVED)) < 0) return bail(rc); }
+        if (removed) { HLock lk(h); h->agent_status[a] = AG_STATUS_REMOVED; if ((rc = push_agent_status(h, a, AG_STATUS_REMOVED)) < 0) return bail(rc); }
     }
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     const size_t R = snap_ring ? (size_t)std::min<uint64_t>(hd.rows_used, hd.slab_rows) : (size_t)hd.rows_used;
     const size_t slab_bytes = (hd.flags & AGR_CFG_VARLEN) ? (size_t)(snap_ring ? std::min<uint64_t>(hd.vused, hd.vcap) : hd.vused) : R * AGR_REC;
     if ((rc = load_dev(h, f, h->d.slab, slab_bytes)) < 0) return bail(rc);
@@ -1474,6 +1677,7 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->vtail = hd.vtail; h->scan_lo = hd.scan_lo;
     h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->tail = hd.tail; h->released_total = hd.released_total; sync_window(h);
+    h->d.idx_base = h->tail; h->sweep_clean = h->tail;
     if (!(hd.flags & AGR_CFG_MINT_IDS) && R) {        // hash-id mode: rebuild the dedupe index from the restored rows
         agr_launch_reindex(h->d, (uint32_t)R, h->stream);
         h->k1_launches += 1;
@@ -1484,21 +1688,43 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     return 0;
 }
 
+// physical chunks that hold rows of the logical range [lo, hi): their cached time bounds are reset to "unknown"
+static int sweep_invalidate(agr_handle* h, uint64_t lo, uint64_t hi) {
+    if (hi <= lo) return 0;
+    const uint64_t R = h->cfg.slab_rows;
+    if (is_ring(h) && hi - lo >= R) return cudaMemsetAsync(h->d.cmin, 0, (size_t)(R / AGR_CHUNK_ROWS + 1) * 8, h->stream) == cudaSuccess ? 0 : fail(AGR_ECUDA, "cmin memset");
+    const uint64_t p0 = phys_row(h, lo), p1 = phys_row(h, hi - 1);
+    auto zero = [&](uint64_t a, uint64_t b) {                      // physical rows [a, b]
+        const uint64_t c0 = a / AGR_CHUNK_ROWS, c1 = b / AGR_CHUNK_ROWS;
+        return cudaMemsetAsync(h->d.cmin + c0, 0, (size_t)(c1 - c0 + 1) * 8, h->stream) == cudaSuccess;
+    };
+    bool ok = (p0 <= p1) ? zero(p0, p1) : (zero(p0, R - 1) && zero(0, p1));
+    return ok ? 0 : fail(AGR_ECUDA, "cmin memset");
+}
+
 int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     if (!h) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
     sync_window(h);
-    agr_launch_expire(h->d, rows_span(h), now, ttl, d_cnt, h->stream);
+    // chunks that received rows since the last sweep (and the ones still being filled) lose their cached bound
+    TRY(sweep_invalidate(h, std::max(h->sweep_clean, h->tail), h->rows_used));
+    const uint64_t bound = ingested_bound(h);
+    agr_launch_expire(h->d, rows_span(h), now, ttl, bound, d_cnt, h->stream);
+    h->sweep_clean = bound;
     h->k3_launches += 1;
     CK(cudaGetLastError());
+    if (!expired) {                       // no count wanted: stay asynchronous (the sweep is stream-ordered before whatever follows)
+        h->expired_total = std::max<uint64_t>(h->expired_total, 1);   // "records may have expired": the list views widen their scan
+        return 0;
+    }
     unsigned long long v = 0;
     CK(cudaMemcpyAsync(&v, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->expired_total += v;
-    if (expired) *expired = v;
+    *expired = v;
     return 0;
 }
 
@@ -1506,21 +1732,22 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
 // the first row that still does, and drop their entries from the completed / failed logs.
 int agr_reclaim(agr_handle* h, uint64_t* released) {
     if (!h) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (released) *released = 0;
     if (!is_ring(h)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_RING");
     sync_window(h);
-    if (h->rows_used == h->tail) return 0;
+    const uint64_t bound = ingested_bound(h);                                  // reserved rows that K1 has not filled yet are not "dead"
+    if (bound <= h->tail) return 0;
     uint32_t* d_off = h->d_min_inq;                                            // 4-byte scratch
     CK(cudaMemsetAsync(d_off, 0xff, 4, h->stream));
-    agr_launch_first_live(h->d, d_off, h->stream);
+    agr_launch_first_live(h->d, bound - h->tail, d_off, h->stream);
     CK(cudaGetLastError());
     unsigned long long* lens = (unsigned long long*)(h->h_small + 2);          // pinned
     CK(cudaMemcpyAsync(h->h_small, d_off, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(lens, h->d.log_len, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));                                      // the only host round trip
-    const uint64_t count = (h->h_small[0] == 0xffffffffu) ? h->rows_used - h->tail : h->h_small[0];
+    const uint64_t count = (h->h_small[0] == 0xffffffffu) ? bound - h->tail : h->h_small[0];
     h->k3_launches += 1;
     if (count == 0) return 0;
     agr_launch_release_rows(h->d, (uint32_t)count, h->d_resp_len, h->d_resp_hlen, h->d_err_len, h->stream);
@@ -1541,6 +1768,7 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
         // hash-id mode: the released rows' ids must leave the dedupe index before their rows are reused.  Open addressing
         // has no cheap delete; a release is a periodic event, so the index is rebuilt from the live window instead.
         CK(cudaMemsetAsync(h->d.table, 0, (size_t)(h->d.table_mask + 1) * sizeof(agr_slot), h->stream));
+        h->d.idx_base = h->tail;                                              // row words of the rebuilt index are relative to the new tail
         const uint64_t R = h->cfg.slab_rows, live = h->rows_used - h->tail, p0 = h->tail % R;
         const uint64_t n0 = std::min<uint64_t>(live, R - p0);
         agr_launch_reindex_range(h->d, (uint32_t)p0, (uint32_t)n0, h->stream);
@@ -1548,7 +1776,7 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
         CK(cudaGetLastError());
         h->k1_launches += 2;
     }
-    {   // the response / error byte ring: its tail follows the oldest blob a live row still refers to
+    if (h->resp_used != h->resp_tail) {   // the response / error byte ring: its tail follows the oldest blob a live row still refers to
         unsigned long long* d_span = (unsigned long long*)(h->d.ctr + C_NCTR - 1);              // last counter slot as scratch
         CK(cudaMemsetAsync(d_span, 0, 8, h->stream));
         agr_launch_bytes_span(h->d, h->resp_used % h->resp_cap, h->resp_cap, h->d_resp_off, h->d_resp_len, h->d_err_off, h->d_err_len, d_span, h->stream);
@@ -1576,7 +1804,7 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
 
 int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad) {
     if (!h || !bad) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     unsigned long long* d_bad = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_bad, 0, 8, h->stream));
@@ -1595,7 +1823,7 @@ int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad) {
 // ------------------------------------------------------------------------------------------ stats
 int agr_stats_get(agr_handle* h, agr_stats* out) {
     if (!h || !out) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     unsigned long long c[C_NCTR], lens[2];
     CK(cudaMemcpyAsync(c, h->d.ctr, sizeof c, cudaMemcpyDeviceToHost, h->stream));
@@ -1612,6 +1840,8 @@ int agr_stats_get(agr_handle* h, agr_stats* out) {
     out->completed_log_len = lens[0]; out->failed_log_len = lens[1];
     out->k1_launches = h->k1_launches; out->k2_launches = h->k2_launches;
     out->k3_launches = h->k3_launches; out->k4_launches = h->k4_launches; out->k5_launches = h->k5_launches; out->rows_tail = h->tail;
+    out->malformed = c[C_BAD_LEN]; out->log_overflow = c[C_LOG_OVERFLOW];
+    if (h->svc) { out->svc_batches = h->svc->batches.load(); out->svc_ops = h->svc->ops.load(); }
     out->agents = (uint32_t)h->agent_names.size(); out->device = (uint32_t)h->device;
     return 0;
 }
@@ -1644,7 +1874,7 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     if (!h || !id) return fail(AGR_EINVAL, "NULL argument");
     if (world < 1 || world > 32 || rank < 0 || rank >= world) return fail(AGR_EINVAL, "bad rank / world (1..32 shards)");
     TRY(nccl_load());
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     ncclUniqueId uid; memcpy(uid.internal, id, 128);
     NK(g_nccl.CommInitRank(&h->comm, world, uid, rank));
@@ -1663,12 +1893,7 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     TRY(dev_alloc(h, &h->d_vout, mb, false));
     // K2 over local + received outcomes: scratch for 2 * max_batch ops
     TRY(dev_alloc(h, &h->d_outs, 2 * mb, false));
-    TRY(dev_alloc(h, &h->d_ops, 2 * mb, false));
-    h->k2.ops = h->d_ops;
-    TRY(dev_alloc(h, &h->k2.nxt, 2 * mb, false));
-    TRY(dev_alloc(h, &h->k2.hrid, 2 * mb, false));
-    TRY(dev_alloc(h, &h->k2.eff, 2 * mb, false));
-    TRY(dev_alloc(h, &h->k2.results, 2 * mb, false));
+    TRY(k2_scratch_alloc(h, 2 * mb));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1751,7 +1976,7 @@ static void exchange_fill_info(const exchange_plan& x, uint32_t n, uint64_t firs
 
 int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     exchange_plan x;
     TRY(exchange_begin(h, recs, AGR_REC, AGR_OFF_AGENT_ID, n, x));
@@ -1776,7 +2001,7 @@ int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_ve
 
 int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info) {
     if (!h || (n && !outs)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     exchange_plan x;
     TRY(exchange_begin(h, outs, sizeof(agr_outcome), 16, n, x));
@@ -1788,9 +2013,8 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
     // K2 at the owner over local + received outcomes (own host first, then peers by rank)
     if (total) {
         sync_window(h);
-        agr_launch_k2_prepare(h->d, h->d_outs, h->d_ops, total, h->stream);
-        agr_launch_k2(h->d, h->k2, total, h->stream);
-        h->k2_launches += 7;
+        agr_launch_k2(h->d, h->d_outs, h->k2, total, h->stream);
+        h->k2_launches += 3;
         CK(cudaGetLastError());
     }
     TRY(exchange_results(h, x, (const uint8_t*)h->k2.results, (uint8_t*)h->d_vback, (uint8_t*)h->d_vout, 4));
@@ -1803,7 +2027,7 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
 
 int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, void* out) {
     if (!h || (n && !out)) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (!is_ring(h) && first_rid + n > h->cfg.slab_rows) return fail(AGR_EINVAL, "row range out of bounds");
     if (is_ring(h) && (first_rid + n > h->rows_used || n > h->cfg.slab_rows)) return fail(AGR_EINVAL, "row range out of bounds");
@@ -1825,7 +2049,7 @@ int agr_debug_read(agr_handle* h, int which, uint64_t first_rid, uint32_t n, voi
 
 int agr_op_time(agr_handle* h, int which, double* ms) {
     if (!h || !ms || which < 0 || which > 2) return fail(AGR_EINVAL, "bad argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (!h->op_timed[which]) return fail(AGR_ENOTFOUND, "no timed launch of that group yet (needs AGR_CFG_TIMING)");
     CK(cudaStreamSynchronize(h->stream));
@@ -1837,7 +2061,7 @@ int agr_op_time(agr_handle* h, int which, double* ms) {
 
 int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches) {
     if (!h || !sum_ms || !launches) return fail(AGR_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     *sum_ms = 0; *launches = 0;
@@ -1931,7 +2155,7 @@ int agr_synth_fill_host(const agr_synth* s, uint64_t first_index, uint32_t n, ag
 }
 int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index, uint64_t first_rid, uint32_t n) {
     if (!h || !s || s->n_agents == 0) return fail(AGR_EINVAL, "bad argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    HLock lk(h);
     CK(cudaSetDevice(h->device));
     if (first_rid + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
     const unsigned long long* dcdf = nullptr;

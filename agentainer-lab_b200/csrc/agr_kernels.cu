@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
         // ---- long-latency chain first: agent probe -> classification -> first index CAS in flight
         const ag_probe ap = k1_agent_issue(d, h2, h3);
         k1_ctx cx;
-        if (valid) k1_begin(d, ap, h0, h2, h3, h4, cx);
+        if (valid) k1_begin(d, ap, h0, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, cx);
         // ---- pass 2 (pure streaming, independent of the decision chain): payload checksum
         uint32_t c0 = 0, c1 = 0;
         {
@@ -94,77 +94,16 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
     if (dupfix == 0u && __ldcg(d.dupfix + 2) == 0u && verdicts == nullptr && ids == nullptr) return;
     const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    uint32_t hits = 0;
-    int stored_delta = 0, q_delta = 0;
+    int delta[3] = {0, 0, 0};                                                     // dedupe hits, stored, queued
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
         const uint32_t i = i0 + threadIdx.x;
         if (i >= n) continue;
         const uint32_t rid = first_rid + i;
-        uint32_t r = d.route[rid];
-        uint32_t vf = rt_flags(r);
-        if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
-            uint4 t = ldg_nc_v4(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF);
-            const uint32_t orid = lookup_rid(d, pack64(t.x, t.y), pack64(t.z, t.w));
-            if (orid != AGR_RID_NONE && orid < rid && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
-                r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
-                d.route[rid] = r;
-                hits++;
-            }
-        }
-        if (dupfix != 0u && (vf & (AGR_VF_STORED | AGR_VF_DUP_ID))) {
-            const uint4 h0 = ldg_nc_v4(rec_ptr(d, rid));
-            const unsigned long long idx = table_find(d, pack64(h0.x, h0.y), pack64(h0.z, h0.w));
-            const uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : ~__ldcg(&d.table[idx].inv_rid);
-            uint32_t code = rt_code(r);
-            const bool running = d.astatus[rt_slot(r)] == AGR_AGENT_RUNNING;
-            if ((vf & AGR_VF_STORED) && owner != rid) {                 // demote
-                if (code == AGR_V_QUEUED) { code = AGR_V_UNAVAILABLE; q_delta--; }
-                vf = (vf & ~(AGR_VF_STORED | AGR_VF_TRACKED)) | AGR_VF_DUP_ID;
-                d.state[rid] = 0;
-                stored_delta--;
-            } else if ((vf & AGR_VF_DUP_ID) && owner == rid && (pack64(h0.x, h0.y) | pack64(h0.z, h0.w)) != 0ULL) {   // promote
-                const uint4 h5 = ldg_nc_v4(rec_ptr(d, rid) + 80);
-                uint32_t maxr = (h5.y >> 16) & 0xffu;
-                if (maxr == 0) maxr = 3;
-                uint32_t st = AGR_ST_PENDING | ST_INQ | ST_STORED | (maxr << ST_MAX_SHIFT);
-                if (running) st |= ST_INFLIGHT;
-                else if (code == AGR_V_UNAVAILABLE) { code = AGR_V_QUEUED; q_delta++; }
-                vf = (vf & ~AGR_VF_DUP_ID) | AGR_VF_STORED | AGR_VF_TRACKED;
-                d.state[rid] = st;
-                stored_delta++;
-            }
-            r = rt_slot(r) | (code << RT_CODE_SHIFT) | (vf << RT_FLAG_SHIFT);
-            d.route[rid] = r;
-        }
-        if (verdicts) {   // agr_verdict {u8 code, u8 flags, u16 http_status, u32 agent_slot}, written for the D2H copy
-            const uint32_t code = rt_code(r);
-            const uint32_t http = code == AGR_V_QUEUED ? 202u : code == AGR_V_UNAVAILABLE ? 503u : code == AGR_V_NOT_FOUND ? 404u : 0u;
-            verdicts[i] = make_uint2(code | (rt_flags(r) << 8) | (http << 16), rt_slot(r));
-        }
-        if (ids) {        // Request.ID as the engine knows it
-            if (d.cfg_flags & AGR_CFG_MINT_IDS) {
-                unsigned long long lo, hi;
-                agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
-                ids[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-            } else {
-                ids[i] = ldg_nc_v4(rec_ptr(d, rid));
-            }
-        }
+        const uint32_t r = k1_post_one(d, rid, dupfix, delta);
+        if (verdicts) verdicts[i] = k1_verdict_word(r);
+        if (ids) ids[i] = k1_request_id(d, rid);
     }
-    hits = __reduce_add_sync(FULL, hits);
-    stored_delta = __reduce_add_sync(FULL, stored_delta);
-    q_delta = __reduce_add_sync(FULL, q_delta);
-    if (lane == 0) {
-        if (hits) atomicAdd(&d.ctr[C_DEDUPE_HITS], (unsigned long long)hits);
-        if (stored_delta) {
-            atomicAdd(&d.ctr[C_STORED], (unsigned long long)(long long)stored_delta);
-            atomicAdd(&d.ctr[C_DUP_IDS], (unsigned long long)(long long)(-stored_delta));
-        }
-        if (q_delta) {
-            atomicAdd(&d.ctr[C_QUEUED], (unsigned long long)(long long)q_delta);
-            atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)(long long)(-q_delta));
-        }
-    }
+    k1_post_flush(d, delta, lane);
 }
 
 // K1b (split mode): the dedupe-index insert of every provisionally stored row, one thread per record at full
@@ -189,7 +128,7 @@ __global__ void __launch_bounds__(256) k1_index(const agr_dev d, const uint32_t 
                 if (old == key) { dup = true; break; }
                 idx = (idx + 1) & d.table_mask;
             }
-            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(~rid) : "memory");
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(idx_encode(d, rid)) : "memory");
             if (dup) {
                 asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(d.dupfix) : "memory");
                 uint32_t code = rt_code(r);
@@ -233,39 +172,71 @@ __global__ void __launch_bounds__(256) k_verify(const agr_dev d, const unsigned 
     if (lane == 0 && agr_cksum_pack(c0, c1) != d.cksum[rid]) atomicAdd(bad, 1ULL);
 }
 // TTL sweep: the reference stores every record with SET ... EX 24h (requests.go:106,175,270); a record whose last SET is
-// ttl or more in the past is gone (GET misses), while its id stays in whatever lists hold it.  Thread per row.
+// ttl or more in the past is gone (GET misses), while its id stays in whatever lists hold it.
+// One CTA per chunk of AGR_CHUNK_ROWS physical rows.  cmin[c] caches a lower bound of the last-SET times of the chunk's
+// stored rows (0 = unknown, ~0 = no stored row): a chunk whose bound says nothing can have expired costs one 8-byte
+// load instead of a sweep, so a periodic call touches only the chunks that are due (and the ones ingested since the last
+// call, whose bound the host has reset).  K2 lowers the bound if an outcome carries an older time than the bound.
 __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned long long rows, const unsigned long long now,
-                                                const unsigned long long ttl, unsigned long long* __restrict__ expired) {
-    const unsigned long long rid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool gone = false;
-    if (rid < rows) {
+                                                const unsigned long long ttl, const unsigned long long bound /* rows below are ingested */,
+                                                unsigned long long* __restrict__ expired) {
+    __shared__ unsigned long long s_min[8];
+    __shared__ uint32_t s_cnt;
+    const uint32_t c = blockIdx.x;
+    const unsigned long long cm = d.cmin[c];
+    if (cm == ~0ULL) return;
+    if (cm != 0ULL && (now < cm || now - cm < ttl)) return;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const unsigned long long r0 = (unsigned long long)c * AGR_CHUNK_ROWS;
+    unsigned long long lmin = ~0ULL;
+    uint32_t gone = 0;
+    for (uint32_t k = threadIdx.x; k < AGR_CHUNK_ROWS; k += 256) {
+        const unsigned long long rid = r0 + k;
+        if (rid >= rows) break;
         const uint32_t st = d.state[rid];
-        if (st & ST_STORED) {
-            unsigned long long t = d.mtime[rid];
-            if (t == 0) t = *reinterpret_cast<const unsigned long long*>(rec_ptr(d, (uint32_t)rid) + AGR_OFF_SEQ);
-            if (now >= t && now - t >= ttl) { d.state[rid] = st & ~ST_STORED; gone = true; }
-        }
+        if (!(st & ST_STORED)) continue;
+        unsigned long long t = d.mtime[rid];
+        if (t == 0) t = *reinterpret_cast<const unsigned long long*>(rec_ptr(d, (uint32_t)rid) + AGR_OFF_SEQ);
+        if (now >= t && now - t >= ttl) { d.state[rid] = st & ~ST_STORED; gone++; }
+        else if (t < lmin) lmin = t;
     }
-    const uint32_t m = __ballot_sync(FULL, gone);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(expired, (unsigned long long)__popc(m));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const unsigned long long y = __shfl_xor_sync(FULL, lmin, o); if (y < lmin) lmin = y; }
+    gone = __reduce_add_sync(FULL, gone);
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lmin; if (gone) atomicAdd(&s_cnt, gone); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) if (s_min[w] < lmin) lmin = s_min[w];
+        if (s_cnt) atomicAdd(expired, (unsigned long long)s_cnt);
+        // cache the bound only for chunks no batch can still add rows to (every row of the chunk lies below the ingested bound)
+        unsigned long long last = r0 + AGR_CHUNK_ROWS - 1; if (last >= rows) last = rows - 1;
+        const bool settled = row_logical(d, (uint32_t)r0) < bound && row_logical(d, (uint32_t)last) < bound;
+        d.cmin[c] = settled ? (lmin == 0ULL ? 1ULL : lmin) : 0ULL;
+    }
 }
-void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl, unsigned long long bound,
                        unsigned long long* expired, cudaStream_t st) {
-    if (rows) k_expire<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d, rows, now, ttl, expired);
+    if (rows) k_expire<<<(unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, rows, now, ttl, bound, expired);
 }
 // ---- ring mode (AGR_CFG_RING): releasing rows at the tail
-// offset (from the tail) of the first row that still holds a stored record
-__global__ void __launch_bounds__(256) k_first_live(const agr_dev d, uint32_t* __restrict__ out_off) {
-    const unsigned long long live = d.head_l - d.tail;
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+// offset (from the tail) of the first row that still holds a stored record, among the `live` rows behind the tail.  Blocks
+// walk the window in order; a block that starts behind an offset already found has nothing to add and leaves at once.
+__global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsigned long long live, uint32_t* __restrict__ out_off) {
+    const unsigned long long b0 = (unsigned long long)blockIdx.x * AGR_CHUNK_ROWS;
+    if (*reinterpret_cast<volatile uint32_t*>(out_off) < b0) return;
     uint32_t mine = 0xffffffffu;
-    if (k < live && (d.state[row_physical(d, d.tail + k)] & ST_STORED)) mine = (uint32_t)k;
+    for (uint32_t k = threadIdx.x; k < AGR_CHUNK_ROWS; k += 256) {
+        const unsigned long long q = b0 + k;
+        if (q >= live) break;
+        if (d.state[row_physical(d, d.tail + q)] & ST_STORED) { mine = (uint32_t)q; break; }
+    }
     mine = __reduce_min_sync(FULL, mine);
     if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
 }
-void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st) {
-    const unsigned long long live = d.head_l - d.tail;
-    if (live) k_first_live<<<(unsigned)((live + 255) / 256), 256, 0, st>>>(d, out_off);
+void agr_launch_first_live(const agr_dev& d, unsigned long long live, uint32_t* out_off, cudaStream_t st) {
+    if (live) k_first_live<<<(unsigned)((live + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, live, out_off);
 }
 // rows tail .. tail + count go back to the pool: every per-row word reads "no record"
 __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uint32_t count, uint32_t* __restrict__ resp_len,
@@ -275,6 +246,7 @@ __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uin
     const uint32_t p = row_physical(d, d.tail + k);
     d.state[p] = 0; d.route[p] = 0; d.aux[p] = 0; d.head[p] = 0; d.ptime[p] = 0; d.mtime[p] = 0;
     resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;
+    if ((p & (AGR_CHUNK_ROWS - 1u)) == 0u || k == 0u) d.cmin[p / AGR_CHUNK_ROWS] = 0;   // the chunk's time bound is unknown again
 }
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
     if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
@@ -389,7 +361,7 @@ __global__ void __launch_bounds__(256) k_reindex_range(const agr_dev d, const ui
         if (old == 0 || old == key) break;
         idx = (idx + 1) & d.table_mask;
     }
-    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(~rid) : "memory");
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(&d.table[idx].inv_rid), "r"(idx_encode(d, rid)) : "memory");
 }
 void agr_launch_reindex_range(const agr_dev& d, uint32_t first, uint32_t n, cudaStream_t st) {
     if (n) k_reindex_range<<<(n + 255u) / 256u, 256, 0, st>>>(d, first, n);
@@ -436,223 +408,143 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
 
 // ------------------------------------------------------------------------------------------------ K2
 // Outcomes must be applied in array order per record (MarkRequestFailed then StoreResponse is not the same as the
-// reverse, KAT-H).  k2_link resolves each outcome to its row and threads all outcomes of one row onto a chain
-// rooted in the index slot; k2_apply lets the chain root replay that row's outcomes in ascending op index on a
-// private copy of the state word (so Q24's lost updates cannot happen); k2_offsets + k2_append push the
-// completed / failed list entries in op order (RPUSH order == call order).
-// agr_outcome (64 B, caller's form: request id + agent id string) -> agr_dop (32 B: id + agent slot).  The agent id is
-// resolved in the DEVICE agent table (same probe as K1), so agr_complete has no per-outcome host work.
-__global__ void __launch_bounds__(256) k2_prepare(const agr_dev d, const uint8_t* __restrict__ outs, agr_dop* __restrict__ ops, const uint32_t n) {
+// reverse, KAT-H).  Three launches (device functions in agr_device.cuh, shared with the service kernel of agr_svc.cu):
+//   k2_link   reads the caller's 64 B outcome, resolves the agent id in the device agent table and the request id to its
+//             row, writes a 16 B op {row, kind|http, seq} and threads the outcomes of one row onto a chain rooted in head[row];
+//   k2_apply  the chain root replays its row's outcomes in ascending op index on a private copy of the state word (Q24's
+//             lost updates cannot happen) and notes which ops push to the completed / failed lists;
+//   k2_append one pass with decoupled look-back: the pushes are appended in op order (RPUSH order == call order, Q7) and
+//             the last tile moves the log tails.
+__global__ void __launch_bounds__(256) k2_link(const agr_dev d, const uint8_t* __restrict__ outs, const agr_k2_scratch s, const uint32_t n) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint8_t* o = outs + (size_t)j * 64;
     const uint4 id = ldg_nc_v4(o), a0 = ldg_nc_v4(o + 16), a1 = ldg_nc_v4(o + 32), t = ldg_nc_v4(o + 48);
-    uint32_t slot, status;
-    agent_resolve(d, k1_agent_issue(d, a0, a1), a0, a1, slot, status);
-    agr_dop op;
-    op.id_lo = pack64(id.x, id.y); op.id_hi = pack64(id.z, id.w);
-    op.slot = slot;                              // RT_SLOT_NONE for an unknown agent: the key cannot exist
-    op.kind = (uint8_t)(t.x & 0xffu); op.pad = 0; op.http = (uint16_t)(t.x >> 16);
-    op.seq = pack64(t.z, t.w);
-    ops[j] = op;
-}
-void agr_launch_k2_prepare(const agr_dev& d, const void* outs, agr_dop* ops, uint32_t n, cudaStream_t st) {
-    if (n) k2_prepare<<<(n + 255u) / 256u, 256, 0, st>>>(d, (const uint8_t*)outs, ops, n);
-}
-
-__global__ void __launch_bounds__(256) k2_link(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const agr_dop op = s.ops[j];
-    s.eff[j] = 0;
-    s.nxt[j] = 0;
-    uint32_t rid = AGR_RID_NONE;
-    int32_t res = 0;
-    const bool ext = (d.cfg_flags & AGR_CFG_SKIP_INFLIGHT) != 0;
-    if ((op.id_lo | op.id_hi) != 0ULL && (op.kind == AGR_OUT_RESPONSE || op.kind == AGR_OUT_ERROR ||
-                                            (op.kind == AGR_OUT_DIAL_ERR && ext))) {
-        const uint32_t cand = lookup_rid(d, op.id_lo, op.id_hi);
-        // the Redis key is agent:{a}:requests:{r}: the agent is part of the key (requests.go:150,229)
-        if (cand != AGR_RID_NONE && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) {
-            rid = cand;
-            s.nxt[j] = atomicExch(&d.head[rid], j + 1u);
-        }
-        if (rid == AGR_RID_NONE && op.kind != AGR_OUT_DIAL_ERR) {
-            res = AGR_ENOTFOUND;                                   // requests.go:153-156 / 232-235
-            atomicAdd(&d.ctr[C_COMPLETION_MISSES], 1ULL);
-        }
-    }
-    if (op.kind == AGR_OUT_DIAL_ERR) atomicAdd(&d.ctr[C_DIAL_ERRORS], 1ULL);    // server.go:600-605: stays pending
-    s.hrid[j] = rid;
-    if (s.results) s.results[j] = res;
+    k2_link_one(d, s, j, id, a0, a1, t);
 }
 
 // read-only resolve of (agent slot, request id) -> rid, used by agr_get_record
-__global__ void __launch_bounds__(256) k_resolve(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+__global__ void __launch_bounds__(256) k_resolve(const agr_dev d, const agr_dop* __restrict__ ops, uint32_t* __restrict__ hrid, const uint32_t n) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const agr_dop op = s.ops[j];
+    const agr_dop op = ops[j];
     uint32_t rid = AGR_RID_NONE;
     const uint32_t cand = lookup_rid(d, op.id_lo, op.id_hi);
     if (cand != AGR_RID_NONE && (d.state[cand] & ST_STORED) && rt_slot(d.route[cand]) == op.slot) rid = cand;
-    s.hrid[j] = rid;
+    hrid[j] = rid;
 }
-void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
-    if (n) k_resolve<<<(n + 255u) / 256u, 256, 0, st>>>(d, s, n);
+void agr_launch_resolve(const agr_dev& d, const agr_dop* ops, uint32_t* hrid, uint32_t n, cudaStream_t st) {
+    if (n) k_resolve<<<(n + 255u) / 256u, 256, 0, st>>>(d, ops, hrid, n);
 }
 
 __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    uint32_t ncomp = 0, nfail = 0, nerr = 0;
-    uint32_t rid = AGR_RID_NONE;
-    bool root = false;
-    if (j < n) {
-        rid = s.hrid[j];
-        if (rid != AGR_RID_NONE) root = (__ldcg(&d.head[rid]) == j + 1u);   // chain root = last op linked onto this row
-    }
-    if (root) {
-        uint32_t st = d.state[rid], aux = d.aux[rid];
-        unsigned long long ptime = 0, mtime = 0; bool responded = false, written = false;
-        long long last = -1;
-        for (;;) {
-            // next op of this row in ascending op index
-            uint32_t best = 0xffffffffu;
-            for (uint32_t cur = j + 1u; cur != 0u; cur = s.nxt[cur - 1u]) {
-                uint32_t o = cur - 1u;
-                if ((long long)o > last && o < best) best = o;
-            }
-            if (best == 0xffffffffu) break;
-            last = best;
-            const agr_dop op = s.ops[best];
-            uint8_t eff = 0;
-            if (op.kind == AGR_OUT_RESPONSE) {                                   // StoreResponse, requests.go:163-191
-                st = (st & ~(ST_STATUS_MASK | ST_INFLIGHT)) | AGR_ST_COMPLETED | ST_RESPONDED;  // :166
-                ptime = op.seq; responded = true;                                // :164,167 now / ProcessedAt
-                mtime = op.seq; written = true;                                  // :175 SET ... EX 24h restarts the TTL (Q11)
-                st &= ~ST_RESP_RT;                                               // a fresh Response object
-                if (st_retry(st)) st |= ST_ERR_RT;                               // Error went through Unmarshal + Marshal
-                aux = (aux & 0xffff0000u) | op.http;                             // :165 request.Response
-                st &= ~ST_INQ;                                                   // :180-184 LREM pending 1 id
-                eff |= 1; ncomp++;                                               // :187-191 RPUSH completed
-            } else if (op.kind == AGR_OUT_ERROR) {                               // MarkRequestFailed, requests.go:243-262
-                uint32_t retry = st_retry(st);
-                if (retry < 255u) retry++;                                       // :245
-                st = (st & ~(ST_RETRY_MASK | ST_STATUS_MASK | ST_INFLIGHT | ST_ERR_RT)) | (retry << ST_RETRY_SHIFT);
-                if (st & ST_RESPONDED) st |= ST_RESP_RT;
-                aux = (aux & 0xff00ffffu) | ((uint32_t)AGR_OUT_ERROR << AUX_ERR_SHIFT);   // :244 request.Error
-                mtime = op.seq; written = true;                                  // :270 SET ... EX 24h
-                nerr++;
-                if (retry < st_max(st)) {
-                    st |= AGR_ST_PENDING;                                        // :248-249, keeps queue position (Q11)
-                } else {
-                    st |= AGR_ST_FAILED;                                         // :243
-                    eff |= 2; nfail++;                                           // :252-255 RPUSH failed
-                    st &= ~ST_INQ;                                               // :258-261 LREM pending 1 id
-                }
-            } else {                                                             // dial error, extension bookkeeping only
-                st &= ~ST_INFLIGHT;
-            }
-            s.eff[best] = eff;
-        }
-        d.state[rid] = st;
-        d.aux[rid] = aux;
-        if (responded) d.ptime[rid] = ptime;
-        if (written) d.mtime[rid] = mtime;
-        d.head[rid] = 0;
-    }
-    ncomp = __reduce_add_sync(FULL, ncomp);
-    nerr = __reduce_add_sync(FULL, nerr);
-    nfail = __reduce_add_sync(FULL, nfail);
+    uint32_t cnt[3] = {0u, 0u, 0u};                                  // completions, errors, dead-lettered
+    if (j < n) k2_apply_one(d, s, j, cnt);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cnt[k] = __reduce_add_sync(FULL, cnt[k]);
     if (lane == 0) {
-        if (ncomp) atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)ncomp);
-        if (nerr) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)nerr);
-        if (nfail) atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)nfail);
+        if (cnt[0]) atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)cnt[0]);
+        if (cnt[1]) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)cnt[1]);
+        if (cnt[2]) atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)cnt[2]);
     }
 }
 
-// warp per chunk: counts of completed / failed pushes in the chunk (coalesced bytes, ballot + popc)
-__global__ void __launch_bounds__(256) k2_count(const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
-    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t nchunks = (n + csize - 1) / csize;
-    if (chunk >= nchunks) return;
-    const uint32_t b = chunk * csize, e = min(n, b + csize);
-    uint32_t cc = 0, cf = 0;
-    for (uint32_t k0 = b; k0 < e; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        const uint8_t f = (k < e) ? s.eff[k] : 0;
-        cc += __popc(__ballot_sync(FULL, f & 1u));
-        cf += __popc(__ballot_sync(FULL, f & 2u));
-    }
-    if (lane == 0) { s.chunk_base[chunk] = cc; s.chunk_base[1024 + chunk] = cf; }
-}
-// one CTA: exclusive scan of the <= 1024 chunk counts -> chunk bases; computes the new log tails
-__global__ void __launch_bounds__(1024) k2_offsets(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
-    __shared__ uint32_t sc[1024], sf[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t nchunks = (n + csize - 1) / csize;
-    const uint32_t cc = (t < nchunks) ? s.chunk_base[t] : 0u, cf = (t < nchunks) ? s.chunk_base[1024 + t] : 0u;
-    sc[t] = cc; sf[t] = cf;
+// Order-preserving append of the batch's completed / failed pushes.  Tiles of K2_TILE ops are claimed through a ticket (so a
+// tile's predecessors are always running or done) and chained with decoupled look-back: a tile publishes its aggregate
+// {completed, failed} count, then its inclusive prefix once the look-back over its predecessors has found one.
+// tile word: flag(2) << 62 | completed(31) << 31 | failed(31);  flag 1 = aggregate, 2 = inclusive prefix.
+#define K2_TILE 2048u
+__global__ void __launch_bounds__(256) k2_append(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_wc[8], s_wf[8];
+    __shared__ unsigned long long s_prefix;
+    const unsigned long long base_c = d.log_len[0], base_f = d.log_len[1];   // read before this tile publishes anything
+    if (threadIdx.x == 0) s_tile = atomicAdd(s.ticket, 1u);
     __syncthreads();
-    for (uint32_t off = 1; off < 1024; off <<= 1) {      // Hillis-Steele inclusive scan
-        uint32_t ac = 0, af = 0;
-        if (t >= off) { ac = sc[t - off]; af = sf[t - off]; }
-        __syncthreads();
-        sc[t] += ac; sf[t] += af;
-        __syncthreads();
+    const uint32_t tile = s_tile, ntiles = (n + K2_TILE - 1u) / K2_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread t owns 8 consecutive ops of the tile: one 8-byte load of their effect bytes
+    const uint32_t k0 = tile * K2_TILE + threadIdx.x * 8u;
+    unsigned long long eff8 = 0;
+    if (k0 + 8u <= n) eff8 = *reinterpret_cast<const unsigned long long*>(s.eff + k0);
+    else for (uint32_t q = 0; k0 + q < n && q < 8u; ++q) eff8 |= (unsigned long long)s.eff[k0 + q] << (8u * q);
+    const uint32_t mc = __popcll(eff8 & 0x0101010101010101ULL), mf = __popcll(eff8 & 0x0202020202020202ULL);
+    uint32_t xc = mc, xf = mf;                                        // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yc = __shfl_up_sync(FULL, xc, o), yf = __shfl_up_sync(FULL, xf, o);
+        if (lane >= o) { xc += yc; xf += yf; }
     }
-    const unsigned long long base_c = d.log_len[0], base_f = d.log_len[1];
-    // chunk bases are offsets from the current log tail; the tail itself is read again in k2_append
-    s.chunk_base[t] = sc[t] - cc;
-    s.chunk_base[1024 + t] = sf[t] - cf;
-    if (t == 1023) {
-        unsigned long long tc = base_c + sc[1023], tf = base_f + sf[1023];       // new tails, applied by k2_tail after the append
-        if (tc > d.log_cap || tf > d.log_cap) atomicAdd(&d.ctr[C_LOG_OVERFLOW], 1ULL);
-        s.chunk_base[2048] = (uint32_t)min(tc, d.log_cap);       s.chunk_base[2049] = (uint32_t)(min(tc, d.log_cap) >> 32);
-        s.chunk_base[2050] = (uint32_t)min(tf, d.log_cap);       s.chunk_base[2051] = (uint32_t)(min(tf, d.log_cap) >> 32);
+    if (lane == 31) { s_wc[warp] = xc; s_wf[warp] = xf; }
+    __syncthreads();
+    uint32_t pc = 0, pf = 0, tc = 0, tf = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) { pc += s_wc[w]; pf += s_wf[w]; } tc += s_wc[w]; tf += s_wf[w]; }
+    if (warp == 0) {
+        volatile unsigned long long* st = s.tiles;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) { st[0] = (2ULL << 62) | ((unsigned long long)tc << 31) | tf; }
+        } else {
+            if (lane == 0) { st[tile] = (1ULL << 62) | ((unsigned long long)tc << 31) | tf; }
+            __threadfence();
+            // look back 32 tiles at a time: lane l looks at tile - 1 - l
+            long long look = (long long)tile - 1;
+            for (;;) {
+                const long long mine = look - lane;
+                unsigned long long v = 0;
+                if (mine >= 0) { do { v = st[mine]; } while ((v >> 62) == 0ULL); }
+                const uint32_t incl_mask = __ballot_sync(FULL, mine >= 0 && (v >> 62) == 2ULL);
+                const int stop = incl_mask ? __ffs(incl_mask) - 1 : 32;          // nearest predecessor with an inclusive prefix
+                unsigned long long add = (mine >= 0 && lane <= stop) ? (v & 0x3fffffffffffffffULL) : 0ULL;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) add += __shfl_xor_sync(FULL, add, o);   // fields cannot carry into each other (sums <= n < 2^31)
+                excl += add;
+                if (incl_mask || look - 32 < 0) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                const unsigned long long incl = excl + (((unsigned long long)tc << 31) | tf);
+                __threadfence();
+                st[tile] = (2ULL << 62) | incl;
+            }
+        }
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    const unsigned long long ex = s_prefix;
+    unsigned long long wc = base_c + (uint32_t)(ex >> 31) + pc + (xc - mc);
+    unsigned long long wf = base_f + (uint32_t)(ex & 0x7fffffffULL) + pf + (xf - mf);
+    if (eff8) {
+#pragma unroll
+        for (uint32_t q = 0; q < 8u; ++q) {
+            const uint32_t f = (uint32_t)(eff8 >> (8u * q)) & 3u;
+            if (f & 1u) { if (wc < d.log_cap) d.completed_log[wc] = s.ops[k0 + q].rid; wc++; }
+            if (f & 2u) { if (wf < d.log_cap) d.failed_log[wf] = s.ops[k0 + q].rid; wf++; }
+        }
+    }
+    if (tile == ntiles - 1u && threadIdx.x == 0) {                   // the last tile's inclusive prefix is the batch total
+        unsigned long long nc = base_c + (uint32_t)(ex >> 31) + tc, nf = base_f + (uint32_t)(ex & 0x7fffffffULL) + tf;
+        if (nc > d.log_cap || nf > d.log_cap) {
+            atomicAdd(&d.ctr[C_LOG_OVERFLOW], 1ULL);
+            *s.overflow = 1u;
+            if (nc > d.log_cap) nc = d.log_cap;
+            if (nf > d.log_cap) nf = d.log_cap;
+        }
+        d.log_len[0] = nc; d.log_len[1] = nf;
     }
 }
 
-// warp per chunk: order-preserving append; the last warp to finish nothing special — tails advanced by k2_tail
-__global__ void __launch_bounds__(256) k2_append(const agr_dev d, const agr_k2_scratch s, const uint32_t n, const uint32_t csize) {
-    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t nchunks = (n + csize - 1) / csize;
-    if (chunk >= nchunks) return;
-    unsigned long long pc = d.log_len[0] + s.chunk_base[chunk];
-    unsigned long long pf = d.log_len[1] + s.chunk_base[1024 + chunk];
-    const uint32_t b = chunk * csize, e = min(n, b + csize);
-    for (uint32_t k0 = b; k0 < e; k0 += 32) {
-        const uint32_t k = k0 + lane;
-        uint8_t f = (k < e) ? s.eff[k] : 0;
-        const uint32_t rid = (k < e) ? s.hrid[k] : AGR_RID_NONE;
-        uint32_t mc = __ballot_sync(FULL, f & 1u), mf = __ballot_sync(FULL, f & 2u);
-        const uint32_t lt = (1u << lane) - 1u;
-        if (f & 1u) { unsigned long long p = pc + __popc(mc & lt); if (p < d.log_cap) d.completed_log[p] = rid; }
-        if (f & 2u) { unsigned long long p = pf + __popc(mf & lt); if (p < d.log_cap) d.failed_log[p] = rid; }
-        pc += __popc(mc); pf += __popc(mf);
-    }
-}
-
-__global__ void k2_tail(const agr_dev d, const agr_k2_scratch s) {
-    d.log_len[0] = ((unsigned long long)s.chunk_base[2049] << 32) | s.chunk_base[2048];
-    d.log_len[1] = ((unsigned long long)s.chunk_base[2051] << 32) | s.chunk_base[2050];
-}
-
-void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
+uint32_t agr_k2_tiles(uint32_t n) { return (n + K2_TILE - 1u) / K2_TILE; }
+void agr_launch_k2(const agr_dev& d, const void* outs, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
     if (n == 0) return;
-    const uint32_t blocks = (n + 255u) / 256u;
-    k2_link<<<blocks, 256, 0, st>>>(d, s, n);
+    const uint32_t blocks = (n + 255u) / 256u, ntiles = agr_k2_tiles(n);
+    cudaMemsetAsync(s.tiles, 0, (size_t)(ntiles + 2u) * 8u, st);   // tile words, then {ticket, overflow}
+    k2_link<<<blocks, 256, 0, st>>>(d, (const uint8_t*)outs, s, n);
     k2_apply<<<blocks, 256, 0, st>>>(d, s, n);
-    uint32_t csize = (n + 1023u) / 1024u;
-    csize = (csize + 31u) & ~31u;
-    if (csize < 32u) csize = 32u;
-    const uint32_t nchunks = (n + csize - 1) / csize;
-    k2_count<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(s, n, csize);
-    k2_offsets<<<1, 1024, 0, st>>>(d, s, n, csize);
-    k2_append<<<(nchunks * 32u + 255u) / 256u, 256, 0, st>>>(d, s, n, csize);
-    k2_tail<<<1, 1, 0, st>>>(d, s);
+    k2_append<<<ntiles, 256, 0, st>>>(d, s, n);
 }
 
 // ------------------------------------------------------------------------------------------------ K3

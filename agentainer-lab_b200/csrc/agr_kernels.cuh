@@ -5,9 +5,11 @@
 #include "agr_common.h"
 #include "agr_synth.h"
 
+#define AGR_CHUNK_ROWS 4096u   // granularity of the TTL sweep's per-chunk time bounds (k_expire) and of k_first_live
+
 // global counters (device u64 array), mirrored into agr_stats
 enum {
-    C_INGESTED = 0, C_STORED, C_REPLAY, C_DEDUPE_HITS, C_FORWARDED, C_QUEUED, C_UNAVAILABLE, C_NOT_FOUND, C_DUP_IDS,
+    C_INGESTED = 0, C_STORED, C_REPLAY, C_DEDUPE_HITS, C_FORWARDED, C_QUEUED, C_UNAVAILABLE, C_NOT_FOUND, C_DUP_IDS, C_BAD_LEN,
     C_COMPLETIONS, C_COMPLETION_MISSES, C_FAILURES, C_DEAD_LETTERED, C_DIAL_ERRORS,
     C_REPLAY_DISPATCHED, C_LOG_OVERFLOW, C_NCTR = 24
 };
@@ -33,6 +35,7 @@ struct agr_dev {
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
     unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
     unsigned long long* mtime; // [rows] time of the latest SET of the record by K2 (0: only StoreRequest's, = the record's seq)
+    unsigned long long* cmin;  // [rows / AGR_CHUNK_ROWS + 1] TTL sweep: lower bound of the last-SET times in a chunk (0 unknown, ~0 empty)
     unsigned long long* voff;  // variable-length mode: byte offset of row's record in the slab (nullptr = fixed 512 B rows)
     uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
@@ -42,12 +45,13 @@ struct agr_dev {
     // mod ring_rows with AGR_CFG_RING.  Every per-row array is indexed by the physical row; [tail, head_l) is the live
     // logical window (tail = 0 without the ring).
     unsigned long long tail, head_l;
+    unsigned long long idx_base;   // hash-id mode: arrival number the dedupe index's row words are relative to (idx_encode)
     uint32_t ring_rows;        // 0 = append-only slab
     uint32_t tail_phys;        // tail % ring_rows
     uint32_t cfg_flags;
 };
 
-// K2 device descriptor (host resolves agent_id -> slot)
+// single-key lookup descriptor (agr_get_record & co.: the host resolves agent_id -> slot)
 struct __attribute__((aligned(16))) agr_dop {
     unsigned long long id_lo, id_hi;
     uint32_t slot;
@@ -57,13 +61,21 @@ struct __attribute__((aligned(16))) agr_dop {
     unsigned long long seq;
 };
 
+// K2 on-device op, 16 B: what is left of a 64 B agr_outcome once its ids are resolved
+struct __attribute__((aligned(16))) agr_k2op {
+    uint32_t rid;              // physical row, AGR_RID_NONE = nothing to apply
+    uint32_t kh;               // kind | http_status << 16
+    unsigned long long seq;    // the outcome's logical time (processed_at / received_at, and the TTL clock)
+};
+
 struct agr_k2_scratch {
-    const agr_dop* ops;
-    uint32_t* nxt;      // chain link (op index + 1, 0 = end)
-    uint32_t* hrid;     // resolved rid or AGR_RID_NONE
-    uint8_t* eff;       // bit0 push completed, bit1 push failed
-    int32_t* results;   // 0 / AGR_ENOTFOUND
-    uint32_t* chunk_base;  // [2][1024]
+    agr_k2op* ops;             // [n]
+    uint32_t* nxt;             // [n] chain link (op index + 1, 0 = end)
+    uint8_t* eff;              // [n] bit0 push completed, bit1 push failed (8-byte aligned)
+    int32_t* results;          // [n] 0 / AGR_ENOTFOUND
+    unsigned long long* tiles; // [tiles + 2] k2_append's look-back words, then {ticket, overflow} as two u32
+    uint32_t* ticket;          // = (uint32_t*)(tiles + tiles_cap)
+    uint32_t* overflow;        // = ticket + 1: set when the batch's pushes did not fit the logs
 };
 
 // K3 select modes
@@ -141,11 +153,11 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */,
                    void* ids = nullptr /* device u8[n][16]: Request.ID per record, written by k1_post */);
-void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl, unsigned long long bound,
                        unsigned long long* expired, cudaStream_t st);
 // ring mode: first live (STORED) row at or after the tail, as an offset from it (0xffffffff: none), then release of
 // `count` rows from the tail and stable compaction of a log (entries of released rows drop out)
-void agr_launch_first_live(const agr_dev& d, uint32_t* out_off, cudaStream_t st);
+void agr_launch_first_live(const agr_dev& d, unsigned long long live, uint32_t* out_off, cudaStream_t st);
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st);
 void agr_launch_bytes_span(const agr_dev& d, unsigned long long head, unsigned long long cap, const unsigned long long* resp_off,
                            const uint32_t* resp_len, const unsigned long long* err_off, const uint32_t* err_len, unsigned long long* span,
@@ -158,9 +170,9 @@ void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
 void agr_launch_reindex_range(const agr_dev& d, uint32_t first, uint32_t n, cudaStream_t st);
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);
 int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
-void agr_launch_k2_prepare(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, agr_dop* ops, uint32_t n, cudaStream_t st);
-void agr_launch_k2(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
-void agr_launch_resolve(const agr_dev& d, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
+uint32_t agr_k2_tiles(uint32_t n);
+void agr_launch_k2(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);
+void agr_launch_resolve(const agr_dev& d, const agr_dop* ops, uint32_t* hrid, uint32_t n, cudaStream_t st);
 void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int sm_count, cudaStream_t st);
 void agr_launch_k3_gather(const agr_dev& d, const uint32_t* rids, const uint32_t* slots, uint32_t n,
                           uint8_t* out_recs /*nullable*/, uint8_t* out_dispatch /*nullable, 32 B each*/,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define AGR_ABI_VERSION 1u
+#define AGR_ABI_VERSION 2u
 
 /* ------------------------------------------------------------------ errors */
 #define AGR_OK          0
@@ -93,9 +93,13 @@ typedef struct agr_record {
                                        exact invertible function of the record's row, agr_record.request_id of fresh records is
                                        ignored on input, callers read the ids with agr_mint_ids.  No dedupe-index table exists in
                                        this mode (lookups decode the row and verify all 128 bits). */
-#define AGR_CFG_COMBINE       0x20u /* flat-combine concurrent small agr_ingest / agr_ingest_ex calls (n <= 32) into one K1 launch:
-                                       callers append to a pinned ring, the first one to arrive leads the batch, the others wait
-                                       for their verdicts; the ring order is the event order (SURVEY 8b threading) */
+#define AGR_CFG_COMBINE       0x20u /* single-request front end (SURVEY 8b threading: one goroutine per HTTP request, server.go:493): calls of
+                                       agr_ingest / agr_ingest_ex / agr_complete with n <= 32 go through a lock-free ring in pinned,
+                                       device-mapped host memory (one fetch_add per call), a dispatcher thread batches whatever is
+                                       published, and ONE resident service kernel decides the batch and writes verdicts / ids / result
+                                       codes straight back into host memory — no launch, copy or stream sync per request.  Event
+                                       order: batch by batch; inside a batch records in ring order, then outcomes in ring order (all
+                                       of them were in flight together).  Fixed-stride engines only (ignored with AGR_CFG_VARLEN). */
 #define AGR_CFG_RING          0x40u /* the slab is a ring (with AGR_CFG_VARLEN the byte slab is a ring too): row ids keep counting arrivals, a
                                        record lives at row id mod slab_rows, and agr_reclaim hands the rows at the tail that no longer hold
                                        a record (agr_expire) back for reuse — a shard then runs indefinitely instead of filling up.
@@ -166,6 +170,9 @@ enum {
 #define AGR_VF_KNOWN    0x08u  /* replay-flagged and replay_of names a record stored earlier (dedupe hit) */
 #define AGR_VF_DUP_ID   0x10u  /* fresh record whose request_id already exists: contract violation, handled as a
                                   persistence failure (server.go:511-514): not stored, untracked */
+#define AGR_VF_BAD_LEN  0x20u  /* path_len + hdr_len + body_len exceeds the record's payload (416 B fixed form, stored length - 96
+                                  variable-length form): the record cannot be persisted; handled like a StoreRequest error
+                                  (server.go:511-514, Q20): not stored, untracked, the request itself still gets its verdict */
 
 typedef struct agr_verdict {
     uint8_t  code;        /* AGR_V_* */
@@ -324,7 +331,9 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out);
  * MarkRequestFailed.  agr_expire drops every record whose last SET lies ttl or more before `now` (same unit as seq):
  * GET misses from then on (agr_get_record / agr_complete: AGR_ENOTFOUND, "failed to get request"), GetPendingRequests and
  * the replay scan skip it (requests.go:210-213), and — like in the reference — its id stays in the pending / completed /
- * failed lists (agr_list).  *expired (nullable) = records dropped by this call.  Rows are not reclaimed. */
+ * failed lists (agr_list).  *expired (nullable) = records dropped by this call; with expired == NULL the call only enqueues
+ * the sweep and returns (stream-ordered before any later call on the handle).  The sweep keeps a lower bound of the last-SET
+ * times per 4096-row chunk, so a periodic call reads only the chunks that can hold something due.  Rows are not reclaimed. */
 int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired);
 /* AGR_CFG_RING: releases the rows at the tail of the ring that hold no record any more — everything up to the first row
  * whose record is still stored — and drops their entries from the completed / failed lists (a deviation from the
@@ -346,6 +355,9 @@ typedef struct agr_stats {
     uint64_t k1_launches, k2_launches, k3_launches, k4_launches;   /* kernels of this library launched so far */
     uint64_t k5_launches;
     uint64_t rows_tail;     /* AGR_CFG_RING: first row id that has not been released (0 otherwise); rows_used - rows_tail <= rows_cap */
+    uint64_t malformed;     /* records rejected with AGR_VF_BAD_LEN */
+    uint64_t log_overflow;  /* agr_complete batches whose completed / failed pushes did not fit the log (they returned AGR_ENOSPC) */
+    uint64_t svc_batches, svc_ops;   /* AGR_CFG_COMBINE: batches formed by the dispatcher / single-request operations served */
     uint32_t agents, device;
 } agr_stats;
 int agr_stats_get(agr_handle* h, agr_stats* out);

@@ -46,7 +46,7 @@ def test_struct_sizes():
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.agr_abi_version() == 1
+    assert lib.agr_abi_version() == 2
     assert lib.agr_strerror(K.AGR_ENOTFOUND) == b"not found"
     assert lib.agr_strerror(K.AGR_ENODEV) == b"no usable CUDA device"
 
