@@ -76,11 +76,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 HOST = os.path.join(_HERE, "host")
 
 
-def build_host(force: bool = False) -> str:
-    """Compile the C++ mirror of requests.Manager / ReplayWorker and its threaded driver (host/test_host)."""
-    out = os.path.join(HOST, "test_host")
-    srcs = [os.path.join(HOST, f) for f in ("requests.cpp", "test_host.cpp")]
-    deps = srcs + [os.path.join(HOST, "requests.hpp"), lib_path()]
+def _gxx(srcs, out, force):
+    deps = srcs + [os.path.join(HOST, "requests.hpp"), os.path.join(_HERE, "..", "include", "agentainer_gpu.h"), lib_path()]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
         return out
     gxx = shutil.which("g++")
@@ -92,3 +89,10 @@ def build_host(force: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
     return out
+
+
+def build_host(force: bool = False) -> str:
+    """Compile the C++ mirror of requests.Manager / ReplayWorker with its threaded driver (host/test_host) and the
+    single-request caller benchmark (host/bench_callers)."""
+    _gxx([os.path.join(HOST, "bench_callers.cpp")], os.path.join(HOST, "bench_callers"), force)
+    return _gxx([os.path.join(HOST, f) for f in ("requests.cpp", "test_host.cpp")], os.path.join(HOST, "test_host"), force)

@@ -28,6 +28,7 @@
 #include <chrono>
 #include <immintrin.h>
 #include <sched.h>
+#include <time.h>
 
 static_assert(sizeof(agr_record) == 512, "agr_record must be 512 B");
 static_assert(sizeof(agr_outcome) == 64, "agr_outcome must be 64 B");
@@ -195,10 +196,12 @@ static int k2_scratch_alloc(agr_handle* h, size_t n) {
     TRY(dev_alloc(h, &h->k2.nxt, n, false));
     TRY(dev_alloc(h, &h->k2.eff, n + 8, false));
     TRY(dev_alloc(h, &h->k2.results, n, false));
-    const size_t tiles = agr_k2_tiles((uint32_t)n) + 1;
-    TRY(dev_alloc(h, &h->k2.tiles, tiles + 1, true));
-    h->k2.ticket = (uint32_t*)(h->k2.tiles + tiles);
+    // word 0 = {ticket, overflow}, then one look-back word per tile: agr_launch_k2 clears the prefix a batch uses
+    unsigned long long* words = nullptr;
+    TRY(dev_alloc(h, &words, (size_t)agr_k2_tiles((uint32_t)n) + 2, true));
+    h->k2.ticket = (uint32_t*)words;
     h->k2.overflow = h->k2.ticket + 1;
+    h->k2.tiles = words + 1;
     h->k2_cap = (uint32_t)n;
     return 0;
 }
@@ -287,6 +290,12 @@ struct svc_host {
     std::mutex smu; std::condition_variable scv;        // the dispatcher sleeps here when the ring has been empty for a while
     std::atomic<uint64_t> batches{0}, ops{0};
     std::atomic<int> fatal{0};                          // a CUDA error in the dispatcher: every later call fails with it
+    std::atomic<uint32_t> waiters{0};                   // callers blocked in svc_wait right now
+    uint32_t spin_cpus = 1;                             // how many of them may spin (CPU allowance minus dispatcher and driver threads)
+    std::atomic<int64_t> inflight{0};                   // tickets handed out by agr_submit_* and not yet collected
+    // diagnostics (AGR_SVC_DEBUG=1 prints them when the handle is destroyed)
+    uint64_t starts = 0, stops = 0, sleeps = 0, flow_waits = 0;
+    double cyc[4] = {0, 0, 0, 0}; uint64_t polls = 0;
 };
 
 static inline void cpu_relax(uint32_t& spins) {
@@ -303,6 +312,9 @@ static int svc_stop_locked(agr_handle* h) {
     cudaError_t e = cudaStreamSynchronize(h->stream);
     s->ctl->stop = 0;
     s->running = false;
+    s->stops++;
+    s->cyc[0] += (double)s->ctl->cyc_wait; s->cyc[1] += (double)s->ctl->cyc_load; s->cyc[2] += (double)s->ctl->cyc_work; s->cyc[3] += (double)s->ctl->cyc_publish;
+    s->polls += s->ctl->heartbeat;
     if (e != cudaSuccess) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, std::string("service kernel: ") + cudaGetErrorString(e)); }
     if (s->ctl->done_seq != s->seq) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, "service kernel left with batches unprocessed"); }
     return 0;
@@ -316,9 +328,13 @@ static int svc_start_locked(agr_handle* h) {
     s->ctl->state = 1; s->ctl->stop = 0;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     sync_window(h);
-    cudaError_t e = agr_launch_svc(h->d, v, s->k2, s->seq + 1, h->stream);
+    // resume at the first batch the previous incarnation did not run (normally none is pending; a batch published right
+    // before this launch is)
+    cudaError_t e = agr_launch_svc(h->d, v, s->k2, s->ctl->done_seq + 1, h->stream);
     if (e != cudaSuccess) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, std::string("service kernel launch: ") + cudaGetErrorString(e)); }
     s->running = true;
+    s->starts++;
+    s->ctl->cyc_wait = 0; s->ctl->cyc_load = 0; s->ctl->cyc_work = 0; s->ctl->cyc_publish = 0; s->ctl->heartbeat = 0;
     s->started = std::chrono::steady_clock::now();
     return 0;
 }
@@ -335,14 +351,16 @@ struct HLock {
     HLock(const HLock&) = delete; HLock& operator=(const HLock&) = delete;
 };
 
-// fails every op of [from, to) from the host side (slab full, CUDA error): the callers see result = rc
+// answers every op of [from, to) from the host side (slab full, CUDA error): the callers see rc
 static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only) {
     for (uint64_t a = from; a < to; ++a) {
         const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
-        if (records_only && s->kind[slot] != SVC_OP_RECORD) continue;
-        s->res[slot].result = rc;
+        const bool rec = s->kind[slot] == SVC_OP_RECORD;
+        if (records_only && !rec) continue;
+        svc_res* r = s->res + slot;
+        r->w[0] = rec ? 0u : (uint32_t)rc; r->w[1] = rec ? (uint32_t)rc : 0u; r->w[2] = 0;
         std::atomic_thread_fence(std::memory_order_release);
-        s->res[slot].done = (uint32_t)(a / SVC_SLOTS) + 1u;
+        r->w[3] = svc_tag(a) << 16;
     }
 }
 
@@ -369,6 +387,7 @@ static void svc_dispatcher(agr_handle* h) {
                 { std::lock_guard<std::mutex> hl(h->mu); if (s->running) svc_stop_locked(h); }
                 std::unique_lock<std::mutex> lk(s->smu);
                 s->sleeping.store(true, std::memory_order_seq_cst);
+                s->sleeps++;
                 const uint32_t slot = (uint32_t)(s->taken & (SVC_SLOTS - 1u));
                 if (s->ready[slot].load(std::memory_order_seq_cst) != (uint32_t)(s->taken / SVC_SLOTS) + 1u && !s->shutdown.load())
                     s->scv.wait_for(lk, std::chrono::milliseconds(50));
@@ -379,12 +398,18 @@ static void svc_dispatcher(agr_handle* h) {
             }
             continue;
         }
-        spins = 0;
         last_work = now;
-        // never more than SVC_DESCS / 2 batches ahead of the kernel (a descriptor slot is reused after SVC_DESCS batches)
-        { uint32_t w = 0; while (s->running && s->seq - s->ctl->done_seq >= SVC_DESCS / 2) cpu_relax(w); }
+        // Batching window = the kernel's own pace: at most two batches are outstanding (one running, one queued so the kernel
+        // never idles); while both are, keep collecting — whatever arrives meanwhile joins the next batch instead of queueing
+        // behind a train of one-request batches.
+        if (s->running && s->seq - s->ctl->done_seq >= 2 && to - s->taken < SVC_MAX_OPS) { s->flow_waits++; _mm_pause(); continue; }
+        spins = 0;
         std::lock_guard<std::mutex> hl(h->mu);
         if (s->fatal.load()) { svc_fail_ops(s, s->taken, to, s->fatal.load(), false); s->taken = to; continue; }
+        if (s->running && s->ctl->state != 1u) {                // it left on its own (safety timeout): note it and start another
+            cudaStreamSynchronize(h->stream);
+            s->running = false;
+        }
         // a resident kernel blocks device-wide synchronisations of other threads (cudaFree ...): let it go every 20 ms
         if (s->running && std::chrono::duration_cast<std::chrono::milliseconds>(now - s->started).count() > 20) svc_stop_locked(h);
         uint64_t first = 0;
@@ -429,6 +454,20 @@ static void svc_dispatcher(agr_handle* h) {
     svc_stop_locked(h);
 }
 
+// CPUs this process may keep busy: the cgroup CPU quota if there is one, else the online CPUs
+static uint32_t cpu_allowance() {
+    uint32_t n = std::max(1u, std::thread::hardware_concurrency());
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char a[64]; unsigned long long period = 0;
+        if (fscanf(f, "%63s %llu", a, &period) == 2 && strcmp(a, "max") != 0 && period) {
+            const unsigned long long q = strtoull(a, nullptr, 10);
+            if (q) n = std::min<uint32_t>(n, (uint32_t)std::max<unsigned long long>(1, q / period));
+        }
+        fclose(f);
+    }
+    return n;
+}
+
 static int svc_create(agr_handle* h) {
     svc_host* s = new svc_host();
     h->svc = s;
@@ -453,6 +492,8 @@ static int svc_create(agr_handle* h) {
     TRY(dev_alloc(h, &s->k2.results, (size_t)SVC_MAX_OPS, false));
     TRY(dev_alloc(h, &s->d_dupfix, (size_t)4, true));
     CK(cudaStreamSynchronize(h->stream));
+    const uint32_t cpus = cpu_allowance();
+    s->spin_cpus = cpus > 3 ? cpus - 3 : 1;
     s->thr = std::thread(svc_dispatcher, h);
     return 0;
 }
@@ -463,6 +504,15 @@ static void svc_destroy(agr_handle* h) {
         s->shutdown.store(true, std::memory_order_release);
         { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_all(); }
         s->thr.join();
+    }
+    if (getenv("AGR_SVC_DEBUG")) {
+        const double mhz = 1965.0, tot = s->cyc[0] + s->cyc[1] + s->cyc[2] + s->cyc[3];
+        const double nb = (double)std::max<uint64_t>(1, s->batches.load());
+        fprintf(stderr, "[agr svc] batches %llu ops %llu (%.1f/batch) | kernel starts %llu stops %llu, dispatcher sleeps %llu, flow waits %llu | "
+                        "per batch: wait %.2f us, load %.2f us, work %.2f us, publish %.2f us (kernel alive %.1f ms), polls %llu\n",
+                (unsigned long long)s->batches.load(), (unsigned long long)s->ops.load(), (double)s->ops.load() / nb,
+                (unsigned long long)s->starts, (unsigned long long)s->stops, (unsigned long long)s->sleeps, (unsigned long long)s->flow_waits,
+                s->cyc[0] / mhz / nb, s->cyc[1] / mhz / nb, s->cyc[2] / mhz / nb, s->cyc[3] / mhz / nb, tot / mhz / 1000.0, (unsigned long long)s->polls);
     }
     delete[] s->ready; delete[] s->free_lap; delete[] s->kind;
     h->svc = nullptr;
@@ -484,16 +534,40 @@ static uint64_t svc_submit(svc_host* s, uint32_t kind, const void* items, size_t
     if (s->sleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_one(); }
     return pos;
 }
-static inline const svc_res* svc_wait(svc_host* s, uint64_t a) {
-    const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), want = (uint32_t)(a / SVC_SLOTS) + 1u;
-    const svc_res* r = s->res + slot;
-    uint32_t w = 0;
-    while (r->done != want) cpu_relax(w);
+struct svc_answer { uint32_t w0, w1; uint64_t rid; };
+static inline bool svc_try(svc_host* s, uint64_t a, svc_answer* out) {
+    const svc_res* r = s->res + (a & (SVC_SLOTS - 1u));
+    const uint32_t w3 = r->w[3];
+    if ((w3 >> 16) != svc_tag(a)) return false;
     std::atomic_thread_fence(std::memory_order_acquire);
-    return r;
+    out->w0 = r->w[0]; out->w1 = r->w[1]; out->rid = (uint64_t)r->w[2] | ((uint64_t)(w3 & 0xffffu) << 32);
+    return true;
+}
+// Blocking wait.  The first spin_cpus waiters spin (the answer is ~20 us away); waiters beyond that many would only burn the
+// process's CPU allowance against each other (a container with a CPU quota throttles ALL its threads once it is spent), so they
+// sleep in short naps instead.
+static inline void svc_wait(svc_host* s, uint64_t a, svc_answer* out) {
+    if (svc_try(s, a, out)) return;
+    const uint32_t me = s->waiters.fetch_add(1, std::memory_order_relaxed);
+    if (me < s->spin_cpus) {
+        uint32_t w = 0;
+        while (!svc_try(s, a, out)) cpu_relax(w);
+    } else {
+        struct timespec ts = {0, 20000};
+        while (!svc_try(s, a, out)) nanosleep(&ts, nullptr);
+    }
+    s->waiters.fetch_sub(1, std::memory_order_relaxed);
 }
 static inline void svc_release(svc_host* s, uint64_t a) {
     s->free_lap[a & (SVC_SLOTS - 1u)].store((uint32_t)(a / SVC_SLOTS) + 1u, std::memory_order_release);
+}
+// Request.ID of the record in ring slot a: minted from its row, or the caller's own (still in the slot's payload)
+static inline void svc_request_id(agr_handle* h, uint64_t a, uint64_t rid, uint8_t id[16]) {
+    if (h->cfg.flags & AGR_CFG_MINT_IDS) {
+        unsigned long long lo, hi;
+        agr_mint_id(rid, h->d.shard_id, h->d.id_gen, h->d.id_secret, lo, hi);
+        memcpy(id, &lo, 8); memcpy(id + 8, &hi, 8);
+    } else memcpy(id, h->svc->payload + (size_t)(a & (SVC_SLOTS - 1u)) * SVC_PAYLOAD, 16);
 }
 
 static int svc_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
@@ -501,12 +575,12 @@ static int svc_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_ver
     const uint64_t pos = svc_submit(s, SVC_OP_RECORD, recs, sizeof(agr_record), n);
     int rc = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        const svc_res* r = svc_wait(s, pos + i);
-        if (r->result < 0) rc = r->result;
+        svc_answer r; svc_wait(s, pos + i, &r);
+        if ((r.w0 & 0xffu) == 0u) rc = (int)r.w1;
         else {
-            if (out) memcpy(&out[i], r->verdict, sizeof(agr_verdict));
-            if (ids) memcpy(ids[i], r->id, 16);
-            if (i == 0 && first_rid) *first_rid = r->rid;   // records of one call sit in consecutive slots of one batch... or of two
+            if (out) { memcpy(&out[i], &r.w0, 4); memcpy((uint8_t*)&out[i] + 4, &r.w1, 4); }
+            if (ids) svc_request_id(h, pos + i, r.rid, ids[i]);
+            if (i == 0 && first_rid) *first_rid = r.rid;
         }
         svc_release(s, pos + i);
     }
@@ -518,9 +592,10 @@ static int svc_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int3
     const uint64_t pos = svc_submit(s, SVC_OP_OUTCOME, outs, sizeof(agr_outcome), n);
     int rc = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        const svc_res* r = svc_wait(s, pos + i);
-        if (r->result < 0 && r->result != AGR_ENOTFOUND) rc = r->result;
-        if (results) results[i] = r->result;
+        svc_answer r; svc_wait(s, pos + i, &r);
+        const int32_t res = (int32_t)r.w0;
+        if (res < 0 && res != AGR_ENOTFOUND) rc = res;
+        if (results) results[i] = res;
         svc_release(s, pos + i);
     }
     if (rc < 0) return fail(rc, "single-request front end: CUDA error");
@@ -995,6 +1070,49 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
     if (out && !out_pinned) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
     if (ids && !ids_pinned) memcpy(ids, h->h_ids, (size_t)n * 16);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------ tickets (submit / collect)
+uint32_t agr_ring_capacity(void) { return SVC_SLOTS / 2; }
+static int submit_one(agr_handle* h, uint32_t kind, const void* item, size_t bytes, agr_ticket* ticket) {
+    if (!h || !item || !ticket) return fail(AGR_EINVAL, "NULL argument");
+    svc_host* s = h->svc;
+    if (!s) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
+    if (s->inflight.fetch_add(1, std::memory_order_acq_rel) >= (int64_t)(SVC_SLOTS / 2)) {
+        s->inflight.fetch_sub(1, std::memory_order_acq_rel);
+        return AGR_EAGAIN;
+    }
+    *ticket = svc_submit(s, kind, item, bytes, 1);
+    return 0;
+}
+int agr_submit_ingest(agr_handle* h, const agr_record* rec, agr_ticket* ticket) { return submit_one(h, SVC_OP_RECORD, rec, sizeof(agr_record), ticket); }
+int agr_submit_complete(agr_handle* h, const agr_outcome* outcome, agr_ticket* ticket) { return submit_one(h, SVC_OP_OUTCOME, outcome, sizeof(agr_outcome), ticket); }
+static int collect(agr_handle* h, agr_ticket t, const svc_answer& r, agr_result* out) {
+    svc_host* s = h->svc;
+    const bool rec = s->kind[t & (SVC_SLOTS - 1u)] == SVC_OP_RECORD;
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->is_outcome = rec ? 0u : 1u;
+        if (rec) {
+            if ((r.w0 & 0xffu) == 0u) out->result = (int32_t)r.w1;
+            else { memcpy(&out->verdict, &r.w0, 4); memcpy((uint8_t*)&out->verdict + 4, &r.w1, 4); out->rid = r.rid; svc_request_id(h, t, r.rid, out->request_id); }
+        } else out->result = (int32_t)r.w0;
+    }
+    svc_release(s, t);
+    s->inflight.fetch_sub(1, std::memory_order_acq_rel);
+    return 0;
+}
+int agr_poll(agr_handle* h, agr_ticket ticket, agr_result* out) {
+    if (!h || !h->svc) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
+    svc_answer r;
+    if (!svc_try(h->svc, ticket, &r)) return AGR_EAGAIN;
+    return collect(h, ticket, r, out);
+}
+int agr_wait(agr_handle* h, agr_ticket ticket, agr_result* out) {
+    if (!h || !h->svc) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
+    svc_answer r;
+    svc_wait(h->svc, ticket, &r);
+    return collect(h, ticket, r, out);
 }
 
 // ------------------------------------------------------------------------------------------ K2

@@ -541,7 +541,7 @@ uint32_t agr_k2_tiles(uint32_t n) { return (n + K2_TILE - 1u) / K2_TILE; }
 void agr_launch_k2(const agr_dev& d, const void* outs, const agr_k2_scratch& s, uint32_t n, cudaStream_t st) {
     if (n == 0) return;
     const uint32_t blocks = (n + 255u) / 256u, ntiles = agr_k2_tiles(n);
-    cudaMemsetAsync(s.tiles, 0, (size_t)(ntiles + 2u) * 8u, st);   // tile words, then {ticket, overflow}
+    cudaMemsetAsync(s.ticket, 0, (size_t)(ntiles + 1u) * 8u, st);   // {ticket, overflow}, then the batch's tile words
     k2_link<<<blocks, 256, 0, st>>>(d, (const uint8_t*)outs, s, n);
     k2_apply<<<blocks, 256, 0, st>>>(d, s, n);
     k2_append<<<ntiles, 256, 0, st>>>(d, s, n);

@@ -73,9 +73,9 @@ struct agr_k2_scratch {
     uint32_t* nxt;             // [n] chain link (op index + 1, 0 = end)
     uint8_t* eff;              // [n] bit0 push completed, bit1 push failed (8-byte aligned)
     int32_t* results;          // [n] 0 / AGR_ENOTFOUND
-    unsigned long long* tiles; // [tiles + 2] k2_append's look-back words, then {ticket, overflow} as two u32
-    uint32_t* ticket;          // = (uint32_t*)(tiles + tiles_cap)
+    uint32_t* ticket;          // k2_append's tile ticket; one 8-byte word {ticket, overflow} directly in front of tiles[]
     uint32_t* overflow;        // = ticket + 1: set when the batch's pushes did not fit the logs
+    unsigned long long* tiles; // [tiles] k2_append's look-back words
 };
 
 // K3 select modes

@@ -29,6 +29,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 __device__ __forceinline__ uint4 lds_v4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st_res(svc_res* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {   // one 16-byte write
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // check word of a descriptor (the dispatcher computes the same over the same 62 words, agr_svc_desc_check below)
 __host__ __device__ __forceinline__ unsigned long long svc_mix_word(uint32_t w, uint32_t i) {
@@ -48,6 +51,7 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     unsigned long long last_work = globaltimer_ns();
     unsigned long long polls = 0;
+    long long c_wait = 0, c_load = 0, c_work = 0, c_pub = 0, c0 = clock64();
 
     for (;;) {
         // ------------------------------------------------------------------ wait for batch next_seq (warp 0 polls)
@@ -94,6 +98,7 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
             }
             return;
         }
+        { const long long c = clock64(); c_wait += c - c0; c0 = c; }
         const svc_desc& D = *reinterpret_cast<const svc_desc*>(s_dw);
         const uint32_t count = D.count, nrec = D.n_records;
         const unsigned long long from = D.from;
@@ -140,6 +145,7 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
             }
         }
         __syncthreads();
+        { const long long c = clock64(); c_load += c - c0; c0 = c; }
 
         // ------------------------------------------------------------------ records: slab rows + checksum (warp per record)
         for (uint32_t i = warp; i < nrec; i += SVC_THREADS / 32u) {
@@ -173,13 +179,9 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
             if (tid < nrec) {
                 const uint32_t rid = D.first_p + tid;
                 const uint32_t r = k1_post_one(d, rid, dupfix, delta);
-                svc_res* out = v.res + ((from + s_rec_op[tid]) & (SVC_SLOTS - 1u));
+                const unsigned long long slot_abs = from + s_rec_op[tid], lrow = D.first_l + tid;
                 const uint2 vw = k1_verdict_word(r);
-                const uint4 id = k1_request_id(d, rid);
-                out->verdict[0] = vw.x; out->verdict[1] = vw.y;
-                out->id[0] = id.x; out->id[1] = id.y; out->id[2] = id.z; out->id[3] = id.w;
-                out->rid = D.first_l + tid;
-                out->result = 0;
+                st_res(v.res + (slot_abs & (SVC_SLOTS - 1u)), vw.x, vw.y, (uint32_t)lrow, (uint32_t)((lrow >> 32) & 0xffffu) | (svc_tag(slot_abs) << 16));
             }
             k1_post_flush(d, delta, (int)lane);
 #pragma unroll
@@ -223,7 +225,6 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
                 if (eff & 1u) { const unsigned long long p = s_logbase[0] + pc + __popc(bc & lt); if (p < d.log_cap) d.completed_log[p] = rid; }
                 if (eff & 2u) { const unsigned long long p = s_logbase[1] + pf + __popc(bf & lt); if (p < d.log_cap) d.failed_log[p] = rid; }
             }
-            if (tid < nout) v.res[(from + s_out_op[tid]) & (SVC_SLOTS - 1u)].result = k2.results[tid];
             __syncthreads();
             if (tid == 0 && (tc | tf)) {
                 unsigned long long nc = s_logbase[0] + tc, nf = s_logbase[1] + tf;
@@ -236,14 +237,19 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
             }
         }
 
-        // ------------------------------------------------------------------ publish: results first, then the done words
-        __threadfence_system();
-        __syncthreads();
-        if (tid < count && kind != SVC_OP_SKIP) {
-            const unsigned long long slot_abs = from + tid;
-            v.res[slot_abs & (SVC_SLOTS - 1u)].done = (uint32_t)(slot_abs / SVC_SLOTS) + 1u;
+        // ------------------------------------------------------------------ publish the outcomes' result codes (the records'
+        // verdicts went out as soon as they were final); ops the dispatcher had to skip were answered by the dispatcher
+        { const long long c = clock64(); c_work += c - c0; c0 = c; }
+        if (tid < nout) {
+            const unsigned long long slot_abs = from + s_out_op[tid];
+            st_res(v.res + (slot_abs & (SVC_SLOTS - 1u)), (uint32_t)k2.results[tid], 0u, 0u, svc_tag(slot_abs) << 16);
         }
-        if (tid == 0) { v.ctl->done_seq = next_seq; v.ctl->heartbeat = polls; }
+        __syncthreads();
+        { const long long c = clock64(); c_pub += c - c0; c0 = c; }
+        if (tid == 0) {
+            v.ctl->done_seq = next_seq; v.ctl->heartbeat = polls;
+            v.ctl->cyc_wait = c_wait; v.ctl->cyc_load = c_load; v.ctl->cyc_work = c_work; v.ctl->cyc_publish = c_pub;
+        }
         next_seq++;
         last_work = globaltimer_ns();
         __syncthreads();

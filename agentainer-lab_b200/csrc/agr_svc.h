@@ -46,17 +46,19 @@ struct __attribute__((aligned(64))) svc_desc {
 
 static_assert(sizeof(svc_desc) == 256, "svc_desc must be 256 B (sixteen 16 B lanes)");
 
-// per-slot result, written by the kernel (device -> host), read by the caller
-struct __attribute__((aligned(64))) svc_res {
-    uint32_t verdict[2];                  // agr_verdict
-    uint32_t id[4];                       // Request.ID
-    uint64_t rid;                         // logical row of the record
-    int32_t result;                       // outcome: 0 / AGR_ENOTFOUND; record: 0 / AGR_ENOSPC / AGR_ECUDA (set by the dispatcher)
-    uint32_t pad0;
-    uint64_t pad1[2];
-    uint32_t pad2;
-    volatile uint32_t done;               // lap + 1 once everything above is valid (written after a system fence)
-};
+// per-slot result: ONE 16-byte store from the kernel (a single PCIe write inside one cache line: the caller sees all of it or
+// none of it, so no system-wide fence sits between "result" and "done"):
+//   record   w0, w1 = agr_verdict (w0's low byte = AGR_V_*, never 0);  w2 | (w3 & 0xffff) << 32 = logical row
+//            host-side failure (slab full / CUDA error, written by the dispatcher): w0 = 0, w1 = (uint32_t)error code
+//   outcome  w0 = (uint32_t)result (0 / AGR_ENOTFOUND / error code)
+//   w3 >> 16 = tag of the slot's lap (svc_tag): the caller spins on it.
+// Request.ID is not shipped: with engine-minted ids it is a function of the row (agr_mint_id, computed by the caller's
+// thread), with caller-supplied ids the caller has it already.
+struct __attribute__((aligned(16))) svc_res { volatile uint32_t w[4]; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint32_t svc_tag(uint64_t slot_abs) { return (uint32_t)((slot_abs / SVC_SLOTS) & 0x7fffu) + 1u; }
 
 // control block (host memory): how the host stops the kernel and how the kernel says where it stopped
 struct __attribute__((aligned(64))) svc_ctl {
@@ -64,9 +66,11 @@ struct __attribute__((aligned(64))) svc_ctl {
     volatile uint32_t state;              // kernel -> host: 1 running, 0 exited, 2 exited on the safety timeout
     volatile uint64_t done_seq;           // kernel -> host: last batch completed
     volatile uint64_t heartbeat;          // kernel -> host: polls so far (diagnostics)
+    volatile uint64_t cyc_wait, cyc_load, cyc_work, cyc_publish;   // kernel -> host: SM cycles spent waiting for a batch, pulling
+                                          // payloads, deciding, publishing results (diagnostics, AGR_SVC_DEBUG)
 };
 
-static_assert(sizeof(svc_res) == 64, "svc_res must be 64 B");
+static_assert(sizeof(svc_res) == 16, "svc_res must be 16 B");
 
 struct svc_dev {                          // device-visible addresses of the pinned ring (UVA: host pointer == device pointer)
     const svc_desc* desc;

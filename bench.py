@@ -2,10 +2,12 @@
 """bench.py — headline benchmark of the hot path (BASELINE.json): agent requests/sec through
 ingest + dedupe + route on 512 B records.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5]
 
-A "step" is ONE pass of the hot path (K1: ingest + dedupe + route) over ONE batch of the workload's records
-(c2 = BASELINE configs[1]: 1 M synthetic 512 B records, 256 agent ids, uniform, all agents running).
+A "step" is ONE pass of the hot path (K1: ingest + dedupe + route) over ONE batch of the workload's records.  The
+headline workload is c3 = BASELINE configs[2], the largest single-GPU configuration and the one with duplicate
+idempotency keys (10 M+ records in 1 M-record steps, 256 agent ids Zipf s = 1.2, 10 % replay-flagged duplicates);
+c2 = configs[1] (1 M records, uniform, no duplicates) and both id modes are reported next to it under "configs".
   value     whole-job records/s, records already resident in the HBM slab when the timed region starts
             (CUDA events on the engine's stream, barrier + synchronize on both sides, max over ranks);
   e2e       the same metric through the C-ABI call a host makes (agr_ingest) with PINNED HOST buffers: the
@@ -38,7 +40,7 @@ ALG_BYTES_PER_RECORD = 520          # 512 B record read + 4 B qu
 WORKLOADS = {
     "c2": dict(name="C2: 1M synthetic 512B POST /agent/<id>/chat records per step, 256 agent ids, uniform, all agents running, no crash-replay",
                records=1 << 20, agents=256, zipf_milli=0, dup_permille=0),
-    "c3": dict(name="C3: 10M records (10 steps of 1M), 256 agent ids Zipf s=1.2, 10% replay-flagged duplicates",
+    "c3": dict(name="C3: 1M-record steps of the 10M+ record stream, 256 agent ids Zipf s=1.2, 10% replay-flagged duplicates (duplicate idempotency keys: replay_of names an earlier request of the same agent)",
                records=1 << 20, agents=256, zipf_milli=1200, dup_permille=100),
 }
 
@@ -51,6 +53,46 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def k1_traffic(mode, variant):
+    """DRAM bytes per K1 launch from the committed ncu capture of the same kernel and batch size.  NOT measured in this run:
+    ncu replays the kernel ~40 times and a number printed under it is no bench value; the source file is named."""
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    try:
+        doc = json.load(open(tp))
+        e = doc.get(f"{mode}_variant{variant}", {})
+        return e.get("dram_bytes_per_launch"), f"profiles/k1_traffic.json <- {e.get('source', doc.get('_source', 'ncu --set full capture'))} (read from the committed file, NOT measured in this run)"
+    except Exception:
+        return None, "no committed ncu capture for this mode"
+
+
+def run_callers(local_rank, seconds=2.0):
+    """e2e_callers: the reference's real call pattern (one request per call, server.go:493) through the C-ABI, measured by the
+    C++ driver host/bench_callers in its own process: blocking agr_ingest_ex(n=1) + agr_complete(n=1) from T OS threads, and
+    the ticket form (agr_submit_* / agr_poll) with many requests parked per thread."""
+    import agentainer_lab_b200 as A
+    exe = os.path.join(os.path.dirname(A.build_host()), "bench_callers")
+    out = {"unit": "round trips/s (one StoreRequest+decision and one StoreResponse each)", "blocking": {}, "tickets": {}}
+    try:
+        quota = open("/sys/fs/cgroup/cpu.max").read().split()
+        out["host_cpu_allowance"] = (os.cpu_count() if quota[0] == "max" else int(quota[0]) / int(quota[1]))
+    except Exception:
+        out["host_cpu_allowance"] = os.cpu_count()
+    def one(threads, inflight):
+        try:
+            r = subprocess.run([exe, str(threads), str(seconds), str(local_rank), "mint", "256", str(inflight)], capture_output=True, text=True, timeout=90)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            return {"error": repr(e)}
+    for t in (8, 64, 256):
+        out["blocking"][f"threads_{t}"] = one(t, 0)
+    for t, w in ((4, 512), (12, 256)):
+        out["tickets"][f"threads_{t}_inflight_{w}"] = one(t, w)
+    best = max((v.get("round_trips_per_s", 0), k, v) for d in (out["blocking"], out["tickets"]) for k, v in d.items())
+    out["value"], out["best"] = best[0], best[1]
+    out["p50_us"], out["p99_us"] = best[2].get("p50_us"), best[2].get("p99_us")
+    return out
 
 
 SAMPLER_SRC = """
@@ -288,7 +330,7 @@ def measure_sustained(A, K, torch, local_rank, variant, steps=48):
         if s >= warm:
             evs[s - warm][0].record(stream)
         eng.ingest_rows_async(first, B)
-        eng.expire((s + 1) * B, 4 * B)
+        eng.expire((s + 1) * B, 4 * B, want_count=False)           # enqueue the TTL sweep; agr_reclaim's one read-back syncs
         released += eng.reclaim()
         if s >= warm:
             evs[s - warm][1].record(stream)
@@ -300,7 +342,7 @@ def measure_sustained(A, K, torch, local_rank, variant, steps=48):
     eng.close()
     return {"records_per_step": B, "ring_rows": R, "steps": steps, "laps": (warm + steps) * B / R, "ms_per_step": ms,
             "requests_per_s": B / (ms * 1e-3), "rows_released": released,
-            "what": "K1 + agr_expire (TTL sweep over the slab) + agr_reclaim (release 1 M rows, compact the logs) per step, device time"}
+            "what": "K1 + agr_expire (TTL sweep: per-chunk time bounds, only due chunks are read) + agr_reclaim (release 1 M rows) per step, device time"}
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -437,8 +479,12 @@ def run_ours(args, wl, rank, world, local_rank):
         eng.rows_json(first + W * B, B, as_array=True, fetch=False)        # warm-up: sizes the output buffer
         json_bytes = eng.rows_json(first + W * B, B, as_array=True, fetch=False)
         k5_ms = eng.op_time(2)
-        secondary = {"k2_complete": {"outcomes": B, "ms": k2_ms, "outcomes_per_s": B / (k2_ms * 1e-3), "algorithmic_bytes_per_outcome": 72,
-                                     "GBps": 72 * B / (k2_ms * 1e-3) / 1e9},
+        peak_s, _ = measured_peak()
+        secondary = {"k2_complete": {"outcomes": B, "ms": k2_ms, "outcomes_per_s": B / (k2_ms * 1e-3), "launches": 3,
+                                     "algorithmic_bytes_per_outcome": 72, "GBps": 72 * B / (k2_ms * 1e-3) / 1e9,
+                                     "frac_of_peak": 72 * B / (k2_ms * 1e-3) / 1e9 / peak_s,
+                                     "survey_bytes_per_outcome": 16, "frac_of_peak_survey_bytes": 16 * B / (k2_ms * 1e-3) / 1e9 / peak_s,
+                                     "note": "72 B = the 64 B agr_outcome the ABI delivers (16 B id + 32 B agent id + kind/status/time) + 4 B state RMW + 4 B list append; SURVEY 8d sketched an 8 B descriptor (16 B/outcome)"},
                      "k3_replay_scan": {"rows_scanned": scanned, "dispatched": int(len(disp)), "ms": k3_ms,
                                         "rows_per_s": scanned / (k3_ms * 1e-3), "algorithmic_bytes_per_row": 8,
                                         "GBps": 8 * scanned / (k3_ms * 1e-3) / 1e9},
@@ -448,15 +494,18 @@ def run_ours(args, wl, rank, world, local_rank):
                                  "note": "measure + scan + emit kernels and the host's read of the total between them"}}
         eng_sust = measure_sustained(A, K, torch, local_rank, args.variant)
         secondary["sustained_ring"] = eng_sust
-    # ---- the same workload and kernel in the OTHER id mode: "mint" = the engine mints
-    # Request.ID like StoreRequest does (requests.go:87) and ids are a keyed bijection of the row; "hash" = caller-supplied
-    # random ids kept in a 32 B/slot dedupe index (one CAS.128 + RED per stored record)
-    other = None
+    # ---- the other named configurations, each on a fresh engine with its own roofline: the same workload in the OTHER id
+    # mode ("mint" = the engine mints Request.ID like StoreRequest does, requests.go:87, ids are a keyed bijection of the row;
+    # "hash" = caller-supplied random ids kept in the dedupe index: one CAS.128 + RED per stored record), and the other
+    # single-GPU workload in both modes
+    subs = []
     if not args.no_other_mode:
-        o_flags = 0 if id_flags else K.AGR_CFG_MINT_IDS
-        o_steps = min(S, 10)
-        o_dev_ms, o_k = measure_resident(A, K, torch, dist, args, wl, rank, local_rank, o_flags, o_steps, W)
-        other = (o_dev_ms / o_steps, o_k)
+        o_steps = min(S, 20)
+        other_wl = "c2" if args.workload == "c3" else "c3"
+        for wname, mode in ((args.workload, "hash" if id_flags else "mint"), (other_wl, "mint"), (other_wl, "hash")):
+            o_dev_ms, o_k = measure_resident(A, K, torch, dist, args, WORKLOADS[wname], rank, local_rank,
+                                             K.AGR_CFG_MINT_IDS if mode == "mint" else 0, o_steps, W)
+            subs.append((wname, mode, o_dev_ms / o_steps, o_k))
     # ---- N > 1: the exchange path (BASELINE config 4): 5 % of every rank's batch are replay-flagged records whose agent
     # lives on another shard -> K4 bin/pack, NCCL all-to-all to the owners, K1 there, verdicts back.  Host buffers in,
     # verdicts out, wall clock with a barrier on both sides (max over ranks by construction of the barrier).
@@ -497,23 +546,18 @@ def run_ours(args, wl, rank, world, local_rank):
                     "nvlink_bytes_per_step": float(cnt[0]) * (512 + 8) / len(x_times),
                     "api": "agr_ingest_sharded (pinned host records in, K4 + NCCL all-to-all + K1 at owner + verdicts back)"}
     if dist:
-        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)] + (list(other) if other else [0.0, 0.0]), device="cuda", dtype=torch.float64)
+        t_all = torch.tensor([dev_ms, e_ms, k_ms / max(1, k_n)] + [x for sub in subs for x in sub[2:]], device="cuda", dtype=torch.float64)
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dev_ms, e_ms, k_avg = [float(x) for x in t_all.tolist()[:3]]
-        if other:
-            other = tuple(float(x) for x in t_all.tolist()[3:5])
+        vals = [float(x) for x in t_all.tolist()]
+        dev_ms, e_ms, k_avg = vals[:3]
+        subs = [(sub[0], sub[1], vals[3 + 2 * i], vals[4 + 2 * i]) for i, sub in enumerate(subs)]
     else:
         k_avg = k_ms / max(1, k_n)
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = ALG_BYTES_PER_RECORD * B / (k_avg * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(f"{args.id_mode}_variant{args.variant}", {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic_of = lambda mode: k1_traffic(mode, args.variant)
+        traffic, traffic_src = traffic_of(args.id_mode)
         cpu = cpu_port_single(A, wl) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": world * B * S / (dev_ms * 1e-3), "unit": "requests/s", "n_gpus": world, "steps": S, "warmup": W,
@@ -526,12 +570,13 @@ def run_ours(args, wl, rank, world, local_rank):
                        "id_mode": args.id_mode + (" (engine-minted Request.ID = keyed bijection of the row, as StoreRequest mints uuid.New(); no dedupe-index table)"
                                                    if id_flags else " (caller-supplied random ids in a 32 B/slot dedupe index)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "kernel": "k1_ingest", "kernel_ms": k_avg, "launches_timed": k_n, "algorithmic_bytes_per_record": ALG_BYTES_PER_RECORD,
                          "peak_source": peak_src},
             "e2e": {"value": world * B / (e_ms * 1e-3), "unit": "requests/s", "h2d_bytes_per_step": B * 512, "d2h_bytes_per_step": B * 24,
                     "steps": len(e_times), "ms_per_step": e_ms, "api": "agr_ingest_ex (pinned host records in; verdicts + Request.IDs out)",
                     "host_cpus_local_to_gpu": local_cpus},
-            "gpu_launches": S * 2, "wall_ms_timed_region": wall_ms, "clocks": clocks,
+            "gpu_launches": S * 2, "wall_ms_timed_region": wall_ms, "device_ms_timed_region": dev_ms, "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -539,12 +584,21 @@ def run_ours(args, wl, rank, world, local_rank):
             line["exchange"] = exchange
         if secondary:
             line["secondary_kernels"] = secondary
-        if other:
-            o_ach = ALG_BYTES_PER_RECORD * B / (other[1] * 1e-3) / 1e9
-            line["other_id_mode"] = {"id_mode": "hash" if id_flags else "mint", "value": world * B / (other[0] * 1e-3), "unit": "requests/s",
-                                     "ms_per_step": other[0], "kernel_ms": other[1], "roofline_frac": o_ach / peak, "achieved_GBps": o_ach}
-        print(json.dumps(line))
+        if subs:
+            cfgs = {}
+            for wname, mode, ms, kms in subs:
+                ach = ALG_BYTES_PER_RECORD * B / (kms * 1e-3) / 1e9
+                tr, tr_src = traffic_of(mode)
+                cfgs[f"{wname}_{mode}"] = {"workload": WORKLOADS[wname]["name"], "id_mode": mode, "value": world * B / (ms * 1e-3), "unit": "requests/s",
+                                           "ms_per_step": ms, "steps": min(S, 20),
+                                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                                        "kernel": "k1_ingest", "kernel_ms": kms, "traffic": tr, "traffic_source": tr_src}}
+            line["configs"] = cfgs
     eng.close()
+    if rank == 0:
+        if world == 1 and not args.no_callers:
+            line["e2e_callers"] = run_callers(local_rank)
+        print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
 
@@ -613,16 +667,17 @@ def run_varlen(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--variant", type=lambda x: int(x, 0), default=0)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exchange", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true")
+    ap.add_argument("--no-callers", action="store_true")
     ap.add_argument("--id-mode", default="mint", choices=["mint", "hash"])
     ap.add_argument("--x-steps", type=int, default=3)
     ap.add_argument("--diag-flags", type=lambda x: int(x, 0), default=0, help="extra AGR_CFG_DIAG_* bits (results invalid; attribution only)")

@@ -44,6 +44,7 @@ extern "C" {
 #define AGR_ECUDA      -6   /* CUDA runtime error (message in agr_last_error) */
 #define AGR_ECAP       -7   /* caller's output array too small; *n holds the needed count */
 #define AGR_ECOMM      -8   /* multi-GPU exchange (NCCL) error */
+#define AGR_EAGAIN      1   /* not an error: agr_poll — not decided yet; agr_submit_* — the request ring is full, poll first */
 
 /* ---------------------------------------------------------- record layout */
 /*
@@ -213,6 +214,30 @@ typedef struct agr_outcome {
  * "failed to get request" error the callers only log, Q20).  An all-zero request_id is a no-op
  * (t.requestID == "", server.go:588,597). */
 int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results);
+
+/* ------------------------------------------------- single requests without a blocked thread (AGR_CFG_COMBINE) */
+/* The reference handles every HTTP request on its own goroutine (server.go:493); goroutines are not OS threads, and a cgo call
+ * that blocks until the verdict is back would pin one OS thread per in-flight request.  These calls are the same single-request
+ * operations as agr_ingest_ex(n = 1) / agr_complete(n = 1), split into "hand it over" and "collect": the goroutine submits,
+ * parks on a channel, and a few reaper goroutines collect.  Event order is the front end's: batch by batch.
+ *   agr_submit_ingest / agr_submit_complete  copy ONE record / outcome into the pinned request ring and return a ticket at once;
+ *                                            AGR_EAGAIN if agr_ring_capacity() tickets are already outstanding
+ *   agr_poll    AGR_OK: *out is filled and the ticket is spent;  AGR_EAGAIN: not decided yet (the ticket stays valid)
+ *   agr_wait    the same, spinning until decided (what agr_ingest_ex / agr_complete do internally)
+ * A ticket must be collected exactly once.  AGR_EINVAL on an engine created without AGR_CFG_COMBINE. */
+typedef uint64_t agr_ticket;
+typedef struct agr_result {
+    agr_verdict verdict;       /* record: the proxy decision (zeroed for an outcome) */
+    uint8_t  request_id[16];   /* record: Request.ID as the engine knows it */
+    uint64_t rid;              /* record: its row */
+    int32_t  result;           /* 0, AGR_ENOTFOUND (outcome: "failed to get request"), AGR_ENOSPC (record: slab full), AGR_ECUDA */
+    uint32_t is_outcome;
+} agr_result;                  /* 40 B */
+int agr_submit_ingest(agr_handle* h, const agr_record* rec, agr_ticket* ticket);
+int agr_submit_complete(agr_handle* h, const agr_outcome* outcome, agr_ticket* ticket);
+int agr_poll(agr_handle* h, agr_ticket ticket, agr_result* out);
+int agr_wait(agr_handle* h, agr_ticket ticket, agr_result* out);
+uint32_t agr_ring_capacity(void);
 
 /* ------------------------------------------------------------ K3 replay scan */
 typedef struct agr_dispatch {

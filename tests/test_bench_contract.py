@@ -52,7 +52,7 @@ import pytest
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", "--no-other-mode", "--e2e-steps", "2"],
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", "--no-other-mode", "--no-callers", "--e2e-steps", "2"],
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
@@ -64,6 +64,8 @@ def test_gpu_arm_line():
     assert d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.3 < r["frac"] < 1.2
+    assert "NOT measured in this run" in r["traffic_source"] or r["traffic"] is None
+    assert "Zipf" in d["config"]["workload"]                        # the headline is the configuration with duplicate idempotency keys
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 512 * d["config"]["records_per_step_per_gpu"] and e["d2h_bytes_per_step"] > 0
     assert 0 < e["value"] < d["value"]                             # the host link binds end to end
