@@ -29,6 +29,7 @@
 #include <immintrin.h>
 #include <sched.h>
 #include <time.h>
+#include <sys/prctl.h>
 
 static_assert(sizeof(agr_record) == 512, "agr_record must be 512 B");
 static_assert(sizeof(agr_outcome) == 64, "agr_outcome must be 64 B");
@@ -276,9 +277,7 @@ struct svc_host {
     svc_desc* desc = nullptr; uint8_t* payload = nullptr; svc_res* res = nullptr; svc_ctl* ctl = nullptr;
     // host only
     std::atomic<uint64_t> head{0};                      // next ring slot to hand out (absolute number)
-    std::atomic<uint32_t>* ready = nullptr;             // [SVC_SLOTS] lap + 1 once the slot's payload is complete
-    std::atomic<uint32_t>* free_lap = nullptr;          // [SVC_SLOTS] the lap that may write the slot (previous user has collected)
-    uint8_t* kind = nullptr;                            // [SVC_SLOTS] SVC_OP_* of the published op
+    std::atomic<uint32_t>* ready = nullptr;             // [SVC_SLOTS] (lap + 1) << 2 | SVC_OP_* once the slot's payload is complete
     uint64_t taken = 0;                                 // dispatcher: first slot not yet put into a batch
     uint64_t seq = 0;                                   // dispatcher: last batch number published
     bool running = false;                               // service kernel resident (changed under the handle mutex only)
@@ -292,7 +291,6 @@ struct svc_host {
     std::atomic<int> fatal{0};                          // a CUDA error in the dispatcher: every later call fails with it
     std::atomic<uint32_t> waiters{0};                   // callers blocked in svc_wait right now
     uint32_t spin_cpus = 1;                             // how many of them may spin (CPU allowance minus dispatcher and driver threads)
-    std::atomic<int64_t> inflight{0};                   // tickets handed out by agr_submit_* and not yet collected
     // diagnostics (AGR_SVC_DEBUG=1 prints them when the handle is destroyed)
     uint64_t starts = 0, stops = 0, sleeps = 0, flow_waits = 0;
     double cyc[4] = {0, 0, 0, 0}; uint64_t polls = 0;
@@ -355,7 +353,7 @@ struct HLock {
 static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only) {
     for (uint64_t a = from; a < to; ++a) {
         const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
-        const bool rec = s->kind[slot] == SVC_OP_RECORD;
+        const bool rec = (s->ready[slot].load(std::memory_order_relaxed) & 3u) == SVC_OP_RECORD;
         if (records_only && !rec) continue;
         svc_res* r = s->res + slot;
         r->w[0] = rec ? 0u : (uint32_t)rc; r->w[1] = rec ? (uint32_t)rc : 0u; r->w[2] = 0;
@@ -373,10 +371,13 @@ static void svc_dispatcher(agr_handle* h) {
         // the contiguous published prefix [taken, to)
         uint64_t to = s->taken;
         uint32_t nrec = 0;
+        uint32_t kinds[SVC_MAX_OPS / 16] = {0};
         while (to - s->taken < SVC_MAX_OPS) {
             const uint32_t slot = (uint32_t)(to & (SVC_SLOTS - 1u));
-            if (s->ready[slot].load(std::memory_order_acquire) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
-            if (s->kind[slot] == SVC_OP_RECORD) { if (nrec == 256u) break; nrec++; }
+            const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
+            if ((rw >> 2) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
+            if ((rw & 3u) == SVC_OP_RECORD) { if (nrec == 256u) break; nrec++; }
+            kinds[(to - s->taken) >> 4] |= (rw & 3u) << (((to - s->taken) & 15u) * 2u);
             to++;
         }
         const auto now = std::chrono::steady_clock::now();
@@ -389,7 +390,7 @@ static void svc_dispatcher(agr_handle* h) {
                 s->sleeping.store(true, std::memory_order_seq_cst);
                 s->sleeps++;
                 const uint32_t slot = (uint32_t)(s->taken & (SVC_SLOTS - 1u));
-                if (s->ready[slot].load(std::memory_order_seq_cst) != (uint32_t)(s->taken / SVC_SLOTS) + 1u && !s->shutdown.load())
+                if ((s->ready[slot].load(std::memory_order_seq_cst) >> 2) != (uint32_t)(s->taken / SVC_SLOTS) + 1u && !s->shutdown.load())
                     s->scv.wait_for(lk, std::chrono::milliseconds(50));
                 s->sleeping.store(false, std::memory_order_seq_cst);
                 last_work = std::chrono::steady_clock::now();
@@ -418,9 +419,8 @@ static void svc_dispatcher(agr_handle* h) {
             if (reserve_rows_locked(h, nrec, &first) < 0) { svc_fail_ops(s, s->taken, to, AGR_ENOSPC, true); have_rows = false; }
         }
         svc_desc dsc{};
-        for (uint64_t a = s->taken; a < to; ++a) {
-            const uint32_t k = (uint32_t)(a - s->taken);
-            uint32_t kd = s->kind[a & (SVC_SLOTS - 1u)];
+        for (uint32_t k = 0; k < (uint32_t)(to - s->taken); ++k) {
+            uint32_t kd = (kinds[k >> 4] >> ((k & 15u) * 2u)) & 3u;
             if (kd == SVC_OP_RECORD && !have_rows) kd = SVC_OP_SKIP;
             dsc.kinds[k >> 4] |= kd << ((k & 15u) * 2u);
         }
@@ -483,9 +483,7 @@ static int svc_create(agr_handle* h) {
     TRY(pin((void**)&s->res, sizeof(svc_res) * SVC_SLOTS));
     TRY(pin((void**)&s->ctl, sizeof(svc_ctl)));
     s->ready = new std::atomic<uint32_t>[SVC_SLOTS];
-    s->free_lap = new std::atomic<uint32_t>[SVC_SLOTS];
-    s->kind = new uint8_t[SVC_SLOTS];
-    for (uint32_t i = 0; i < SVC_SLOTS; ++i) { s->ready[i].store(0); s->free_lap[i].store(0); s->kind[i] = 0; }
+    for (uint32_t i = 0; i < SVC_SLOTS; ++i) s->ready[i].store(0);
     TRY(dev_alloc(h, &s->k2.ops, (size_t)SVC_MAX_OPS, false));
     TRY(dev_alloc(h, &s->k2.nxt, (size_t)SVC_MAX_OPS, false));
     TRY(dev_alloc(h, &s->k2.eff, (size_t)SVC_MAX_OPS + 8, false));
@@ -493,7 +491,7 @@ static int svc_create(agr_handle* h) {
     TRY(dev_alloc(h, &s->d_dupfix, (size_t)4, true));
     CK(cudaStreamSynchronize(h->stream));
     const uint32_t cpus = cpu_allowance();
-    s->spin_cpus = cpus > 3 ? cpus - 3 : 1;
+    s->spin_cpus = cpus > 6 ? cpus - 6 : 1;             // leave room for the dispatcher, the driver's threads and the nappers' wake-ups
     s->thr = std::thread(svc_dispatcher, h);
     return 0;
 }
@@ -514,7 +512,7 @@ static void svc_destroy(agr_handle* h) {
                 (unsigned long long)s->starts, (unsigned long long)s->stops, (unsigned long long)s->sleeps, (unsigned long long)s->flow_waits,
                 s->cyc[0] / mhz / nb, s->cyc[1] / mhz / nb, s->cyc[2] / mhz / nb, s->cyc[3] / mhz / nb, tot / mhz / 1000.0, (unsigned long long)s->polls);
     }
-    delete[] s->ready; delete[] s->free_lap; delete[] s->kind;
+    delete[] s->ready;
     h->svc = nullptr;
     delete s;
 }
@@ -525,11 +523,21 @@ static uint64_t svc_submit(svc_host* s, uint32_t kind, const void* items, size_t
     for (uint32_t i = 0; i < n; ++i) {
         const uint64_t a = pos + i;
         const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
-        uint32_t w = 0;
-        while (s->free_lap[slot].load(std::memory_order_acquire) != lap) cpu_relax(w);    // the slot's previous user has collected
-        memcpy(s->payload + (size_t)slot * SVC_PAYLOAD, (const uint8_t*)items + (size_t)i * item_bytes, item_bytes);
-        s->kind[slot] = (uint8_t)kind;
-        s->ready[slot].store(lap + 1u, std::memory_order_release);
+        if (lap) {                                                      // the slot's previous user (one lap ago) has collected
+            const uint32_t want = (svc_tag(a - SVC_SLOTS) | SVC_COLLECTED) << 16;
+            uint32_t w = 0;
+            while ((s->res[slot].w[3] & 0xffff0000u) != want) cpu_relax(w);
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        // streaming stores: the slot's lines were last written by another core a lap ago and are read next by the GPU (DMA),
+        // so pulling them into this core's cache first (read-for-ownership) would only cost a miss per line
+        {
+            __m128i* dst = reinterpret_cast<__m128i*>(s->payload + (size_t)slot * SVC_PAYLOAD);
+            const __m128i* src = reinterpret_cast<const __m128i*>((const uint8_t*)items + (size_t)i * item_bytes);
+            for (size_t k = 0; k < item_bytes / 16; ++k) _mm_stream_si128(dst + k, _mm_loadu_si128(src + k));
+            _mm_sfence();
+        }
+        s->ready[slot].store(((lap + 1u) << 2) | kind, std::memory_order_release);
     }
     if (s->sleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_one(); }
     return pos;
@@ -553,13 +561,16 @@ static inline void svc_wait(svc_host* s, uint64_t a, svc_answer* out) {
         uint32_t w = 0;
         while (!svc_try(s, a, out)) cpu_relax(w);
     } else {
-        struct timespec ts = {0, 20000};
+        static thread_local bool slack_set = false;
+        if (!slack_set) { prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); slack_set = true; }   // naps of tens of us, not the default +50 us
+        struct timespec ts = {0, 25000};
         while (!svc_try(s, a, out)) nanosleep(&ts, nullptr);
     }
     s->waiters.fetch_sub(1, std::memory_order_relaxed);
 }
-static inline void svc_release(svc_host* s, uint64_t a) {
-    s->free_lap[a & (SVC_SLOTS - 1u)].store((uint32_t)(a / SVC_SLOTS) + 1u, std::memory_order_release);
+static inline void svc_release(svc_host* s, uint64_t a) {       // everything of the answer (and of the payload) has been read
+    std::atomic_thread_fence(std::memory_order_release);
+    s->res[a & (SVC_SLOTS - 1u)].w[3] = (svc_tag(a) | SVC_COLLECTED) << 16;
 }
 // Request.ID of the record in ring slot a: minted from its row, or the caller's own (still in the slot's payload)
 static inline void svc_request_id(agr_handle* h, uint64_t a, uint64_t rid, uint8_t id[16]) {
@@ -1073,23 +1084,21 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
 }
 
 // ------------------------------------------------------------------------------------------ tickets (submit / collect)
-uint32_t agr_ring_capacity(void) { return SVC_SLOTS / 2; }
+uint32_t agr_ring_capacity(void) { return SVC_SLOTS; }
+#define TICKET_OUTCOME (1ULL << 63)                               // a ticket = ring slot number | kind
 static int submit_one(agr_handle* h, uint32_t kind, const void* item, size_t bytes, agr_ticket* ticket) {
     if (!h || !item || !ticket) return fail(AGR_EINVAL, "NULL argument");
     svc_host* s = h->svc;
     if (!s) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
-    if (s->inflight.fetch_add(1, std::memory_order_acq_rel) >= (int64_t)(SVC_SLOTS / 2)) {
-        s->inflight.fetch_sub(1, std::memory_order_acq_rel);
-        return AGR_EAGAIN;
-    }
-    *ticket = svc_submit(s, kind, item, bytes, 1);
+    *ticket = svc_submit(s, kind, item, bytes, 1) | (kind == SVC_OP_OUTCOME ? TICKET_OUTCOME : 0ULL);
     return 0;
 }
 int agr_submit_ingest(agr_handle* h, const agr_record* rec, agr_ticket* ticket) { return submit_one(h, SVC_OP_RECORD, rec, sizeof(agr_record), ticket); }
 int agr_submit_complete(agr_handle* h, const agr_outcome* outcome, agr_ticket* ticket) { return submit_one(h, SVC_OP_OUTCOME, outcome, sizeof(agr_outcome), ticket); }
-static int collect(agr_handle* h, agr_ticket t, const svc_answer& r, agr_result* out) {
+static int collect(agr_handle* h, agr_ticket ticket, const svc_answer& r, agr_result* out) {
     svc_host* s = h->svc;
-    const bool rec = s->kind[t & (SVC_SLOTS - 1u)] == SVC_OP_RECORD;
+    const bool rec = !(ticket & TICKET_OUTCOME);
+    const uint64_t t = ticket & ~TICKET_OUTCOME;
     if (out) {
         memset(out, 0, sizeof *out);
         out->is_outcome = rec ? 0u : 1u;
@@ -1099,19 +1108,18 @@ static int collect(agr_handle* h, agr_ticket t, const svc_answer& r, agr_result*
         } else out->result = (int32_t)r.w0;
     }
     svc_release(s, t);
-    s->inflight.fetch_sub(1, std::memory_order_acq_rel);
     return 0;
 }
 int agr_poll(agr_handle* h, agr_ticket ticket, agr_result* out) {
     if (!h || !h->svc) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
     svc_answer r;
-    if (!svc_try(h->svc, ticket, &r)) return AGR_EAGAIN;
+    if (!svc_try(h->svc, ticket & ~TICKET_OUTCOME, &r)) return AGR_EAGAIN;
     return collect(h, ticket, r, out);
 }
 int agr_wait(agr_handle* h, agr_ticket ticket, agr_result* out) {
     if (!h || !h->svc) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
     svc_answer r;
-    svc_wait(h->svc, ticket, &r);
+    svc_wait(h->svc, ticket & ~TICKET_OUTCOME, &r);
     return collect(h, ticket, r, out);
 }
 

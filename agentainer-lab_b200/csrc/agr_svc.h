@@ -51,14 +51,16 @@ static_assert(sizeof(svc_desc) == 256, "svc_desc must be 256 B (sixteen 16 B lan
 //   record   w0, w1 = agr_verdict (w0's low byte = AGR_V_*, never 0);  w2 | (w3 & 0xffff) << 32 = logical row
 //            host-side failure (slab full / CUDA error, written by the dispatcher): w0 = 0, w1 = (uint32_t)error code
 //   outcome  w0 = (uint32_t)result (0 / AGR_ENOTFOUND / error code)
-//   w3 >> 16 = tag of the slot's lap (svc_tag): the caller spins on it.
+//   w3 >> 16 = tag of the slot's lap (svc_tag): the caller spins on it, and sets SVC_COLLECTED in it once it has read the
+//              answer — that line is in the collector's cache anyway, so freeing a slot costs no extra miss.
 // Request.ID is not shipped: with engine-minted ids it is a function of the row (agr_mint_id, computed by the caller's
 // thread), with caller-supplied ids the caller has it already.
 struct __attribute__((aligned(16))) svc_res { volatile uint32_t w[4]; };
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline uint32_t svc_tag(uint64_t slot_abs) { return (uint32_t)((slot_abs / SVC_SLOTS) & 0x7fffu) + 1u; }
+static inline uint32_t svc_tag(uint64_t slot_abs) { return (uint32_t)((slot_abs / SVC_SLOTS) & 0x3fffu) + 1u; }   // 1 .. 16384
+#define SVC_COLLECTED 0x8000u     // or-ed into the tag by whoever collected the answer: the slot may be written for the next lap
 
 // control block (host memory): how the host stops the kernel and how the kernel says where it stopped
 struct __attribute__((aligned(64))) svc_ctl {

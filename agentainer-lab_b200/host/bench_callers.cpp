@@ -59,25 +59,31 @@ int main(int argc, char** argv) {
         auto& my = lat[t]; my.reserve(1 << 20);
         while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
         if (inflight > 0) {
+            // Tickets are answered in hand-over order (batch by batch), so the thread keeps its requests in a FIFO and polls only
+            // the OLDEST one: a poll that says "not yet" means nothing younger is ready either.
             struct flight { int stage; agr_ticket t; std::chrono::steady_clock::time_point t0; uint32_t rec; };
-            std::vector<flight> fl((size_t)inflight);
-            for (auto& f : fl) f.stage = -1;
+            std::vector<flight> q((size_t)inflight);
+            size_t head = 0, count = 0;                                   // FIFO over q: [head, head + count)
+            auto push = [&](const flight& f) { q[(head + count) % q.size()] = f; count++; };
             while (!stop.load(std::memory_order_relaxed)) {
-                for (auto& f : fl) {
-                    if (f.stage == -1) {                                   // start a request: StoreRequest + routing decision
-                        f.rec = (uint32_t)(n & 63); agr_record& r = recs[f.rec];
-                        if (!mint) { uint64_t a = splitmix(x), b = splitmix(x) | 1; memcpy(r.request_id, &a, 8); memcpy(r.request_id + 8, &b, 8); }
-                        r.seq = n;
-                        f.t0 = std::chrono::steady_clock::now();
-                        const int rc = agr_submit_ingest(h, &r, &f.t);
-                        if (rc == AGR_EAGAIN) continue;
-                        if (rc < 0) { bad++; stop.store(true); break; }
-                        f.stage = 0; n++;
-                        continue;
-                    }
+                while (count < q.size()) {                                 // start requests: StoreRequest + routing decision
+                    flight f; f.rec = (uint32_t)(n & 63); agr_record& r = recs[f.rec];
+                    if (!mint) { uint64_t a = splitmix(x), b = splitmix(x) | 1; memcpy(r.request_id, &a, 8); memcpy(r.request_id + 8, &b, 8); }
+                    r.seq = n;
+                    f.t0 = std::chrono::steady_clock::now();
+                    const int rc = agr_submit_ingest(h, &r, &f.t);
+                    if (rc == AGR_EAGAIN) break;
+                    if (rc < 0) { bad++; stop.store(true); break; }
+                    f.stage = 0; n++;
+                    push(f);
+                }
+                uint32_t reaped = 0;
+                while (count && reaped < 64) {
+                    flight f = q[head];
                     agr_result res;
                     const int rc = agr_poll(h, f.t, &res);
-                    if (rc == AGR_EAGAIN) continue;
+                    if (rc == AGR_EAGAIN) break;
+                    head = (head + 1) % q.size(); count--; reaped++;
                     if (rc < 0 || res.result != 0) { bad++; stop.store(true); break; }
                     if (f.stage == 0) {                                    // forwarded: the agent answered, StoreResponse
                         if (res.verdict.code != AGR_V_FORWARD) { bad++; stop.store(true); break; }
@@ -88,14 +94,14 @@ int main(int argc, char** argv) {
                         while ((rc2 = agr_submit_complete(h, &o, &f.t)) == AGR_EAGAIN) {}
                         if (rc2 < 0) { bad++; stop.store(true); break; }
                         f.stage = 1;
+                        push(f);
                     } else {
                         const auto t1 = std::chrono::steady_clock::now();
                         if (my.size() < my.capacity()) my.push_back((uint32_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - f.t0).count());
-                        f.stage = -1;
                     }
                 }
             }
-            for (auto& f : fl) if (f.stage >= 0) { agr_result res; agr_wait(h, f.t, &res); }   // drain what is still in flight
+            while (count) { agr_result res; agr_wait(h, q[head].t, &res); head = (head + 1) % q.size(); count--; }   // drain
             total += n;
             return;
         }
