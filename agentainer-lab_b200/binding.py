@@ -53,7 +53,7 @@ class AgrDecoded(C.Structure):
 class AgrExchangeInfo(C.Structure):
     _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("n_local", C.c_uint32), ("n_sent", C.c_uint32),
                 ("n_received", C.c_uint32), ("sent_to", C.c_uint32 * 32), ("received_from", C.c_uint32 * 32),
-                ("first_rid", C.c_uint64)]
+                ("first_rid", C.c_uint64), ("recv_first_rid", C.c_uint64)]
 
 
 class AgrSynth(C.Structure):
@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
     "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim", "agr_set_agent_states", "agr_json_decode",
-    "agr_submit_ingest", "agr_submit_complete", "agr_poll", "agr_wait", "agr_ring_capacity",
+    "agr_submit_ingest", "agr_submit_complete", "agr_poll", "agr_wait", "agr_ring_capacity", "agr_ingest_sharded_rows", "agr_fill_rows",
 ]
 
 _lib = None
@@ -153,6 +153,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_comm_init": (i32, [vp, vp, i32, i32]),
         "agr_ingest_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
         "agr_complete_sharded": (i32, [vp, vp, u32, vp, C.POINTER(AgrExchangeInfo)]),
+        "agr_ingest_sharded_rows": (i32, [vp, u64, u32, vp, C.POINTER(AgrExchangeInfo)]),
+        "agr_fill_rows": (i32, [vp, u64, vp, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -427,6 +429,17 @@ class Engine:
         out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
         info = AgrExchangeInfo()
         _check(self.lib, self.lib.agr_ingest_sharded(self.h, _ptr(recs) if n else None, n, _ptr(out) if (want_verdicts and n) else None, C.byref(info)))
+        return out, info
+
+    def fill_rows(self, first_rid: int, recs: np.ndarray) -> None:
+        assert recs.dtype == record_dtype and recs.flags["C_CONTIGUOUS"]
+        _check(self.lib, self.lib.agr_fill_rows(self.h, first_rid, _ptr(recs), len(recs)))
+
+    def ingest_sharded_rows(self, first_rid: int, n: int, want_verdicts: bool = False):
+        """agr_ingest_sharded over rows already resident on the device (agr_reserve_rows + a device-side fill)."""
+        out = np.zeros(n, dtype=verdict_dtype) if want_verdicts else None
+        info = AgrExchangeInfo()
+        _check(self.lib, self.lib.agr_ingest_sharded_rows(self.h, first_rid, n, _ptr(out) if want_verdicts and n else None, C.byref(info)))
         return out, info
 
     def complete_sharded(self, outs: np.ndarray):

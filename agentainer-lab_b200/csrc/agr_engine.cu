@@ -991,6 +991,18 @@ int agr_reserve_rows(agr_handle* h, uint32_t n, uint64_t* first_rid) {
     }
     return 0;
 }
+int agr_fill_rows(agr_handle* h, uint64_t first_rid, const agr_record* recs, uint32_t n) {
+    if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
+    HLock lk(h);
+    CK(cudaSetDevice(h->device));
+    if (h->cfg.flags & AGR_CFG_VARLEN) return fail(AGR_EINVAL, "fixed-stride engines only");
+    if (first_rid + n > h->rows_used || first_rid < h->tail) return fail(AGR_EINVAL, "rows not reserved");
+    if (n == 0) return 0;
+    if (phys_row(h, first_rid) + n > h->cfg.slab_rows) return fail(AGR_EINVAL, "row range wraps");
+    CK(cudaMemcpyAsync(h->d.slab + phys_row(h, first_rid) * AGR_REC, recs, (size_t)n * AGR_REC, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out) {
     if (!h) return fail(AGR_EINVAL, "NULL handle");
     HLock lk(h);
@@ -2007,7 +2019,7 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     h->rank = rank; h->world = world;
     h->d.shard_id = (uint32_t)rank;
     const size_t mb = h->cfg.max_batch;
-    TRY(dev_alloc(h, &h->d_stage, mb * AGR_REC, false));
+    TRY(dev_alloc(h, &h->d_stage, mb * sizeof(agr_outcome), false));   // outcomes before binning (records are binned in their slab rows)
     TRY(dev_alloc(h, &h->d_send, mb * AGR_REC, false));
     TRY(dev_alloc(h, &h->d_owner, mb, false));
     TRY(dev_alloc(h, &h->d_perm, mb, false));
@@ -2024,21 +2036,23 @@ int agr_comm_init(agr_handle* h, const uint8_t id[128], int rank, int world) {
     return 0;
 }
 
-// Shared first half of the exchanges: stage the caller's items, find every item's owner (K4 count + scan), swap the
-// per-peer counts with one grouped send/recv, and lay out the owner-major send offsets and the source-major receive offsets.
+// Shared first half of the exchanges: find every item's owner (K4 count + scan), swap the per-peer counts with one grouped
+// send/recv, and lay out the owner-major send offsets and the source-major receive offsets.  `d_items` are the items on the
+// device: the staging buffer (outcomes), or the slab rows the batch was DMA'd into (records, in-place mode).
 struct exchange_plan {
     agr_k4_params p{};
     uint32_t G = 1, me = 0, scnt[32], rcnt[32], soff[33], roff[33], n_local = 0, n_recv = 0;
+    uint32_t recv_res_base = 0;      // index of the first received item's result in the result array
 };
-static int exchange_begin(agr_handle* h, const void* items, uint32_t item_bytes, uint32_t agent_off, uint32_t n, exchange_plan& x) {
+static int exchange_begin(agr_handle* h, uint8_t* d_items, uint32_t item_bytes, uint32_t agent_off, uint32_t n, bool inplace, exchange_plan& x) {
     if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
     if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
     x.G = (uint32_t)h->world; x.me = (uint32_t)h->rank;
     cudaStream_t st = h->stream;
     uint32_t* d_gtotal = h->d_k4cnt; uint32_t* d_goff = h->d_k4cnt + 40; uint32_t* d_rcnt = h->d_k4cnt + 80;
-    if (n) CK(cudaMemcpyAsync(h->d_stage, items, (size_t)n * item_bytes, cudaMemcpyHostToDevice, st));
     agr_k4_params& p = x.p;
-    p.items = h->d_stage; p.item_bytes = item_bytes; p.agent_off = agent_off; p.n = n; p.G = x.G; p.me = x.me;
+    p.items = d_items; p.items_rw = d_items; p.inplace = inplace ? 1u : 0u;
+    p.item_bytes = item_bytes; p.agent_off = agent_off; p.n = n; p.G = x.G; p.me = x.me;
     uint32_t per = (n + h->k4_nwarps - 1) / std::max<uint32_t>(1, h->k4_nwarps);
     per = std::max<uint32_t>(32, (per + 31) & ~31u);
     p.per_warp = per; p.nwarps = std::max<uint32_t>(1, (n + per - 1) / per);
@@ -2052,6 +2066,8 @@ static int exchange_begin(agr_handle* h, const void* items, uint32_t item_bytes,
         NK(g_nccl.Recv(d_rcnt + q, 1, ncclUint32, (int)q, h->comm, st));
     }
     NK(g_nccl.GroupEnd());
+    // the one host round trip of the exchange: ncclSend / ncclRecv take their element counts from the host, and the rows for
+    // the records that arrive have to be reserved
     uint32_t* hc = h->h_small;                       // [0..31] send counts, [32..63] receive counts
     CK(cudaMemcpyAsync(hc, d_gtotal, x.G * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hc + 32, d_rcnt, x.G * 4, cudaMemcpyDeviceToHost, st));
@@ -2059,10 +2075,12 @@ static int exchange_begin(agr_handle* h, const void* items, uint32_t item_bytes,
     x.soff[0] = 0; x.roff[0] = 0;
     for (uint32_t q = 0; q < x.G; ++q) {
         x.scnt[q] = hc[q]; x.rcnt[q] = (q == x.me) ? 0 : hc[32 + q];
-        x.soff[q + 1] = x.soff[q] + x.scnt[q]; x.roff[q + 1] = x.roff[q] + x.rcnt[q];
+        // in-place mode: the send buffer holds the peers' segments only
+        x.soff[q + 1] = x.soff[q] + ((inplace && q == x.me) ? 0u : x.scnt[q]); x.roff[q + 1] = x.roff[q] + x.rcnt[q];
     }
     x.n_local = x.scnt[x.me]; x.n_recv = x.roff[x.G];
-    if (x.n_local + x.n_recv > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more items than 2 * max_batch");
+    x.recv_res_base = inplace ? n : x.n_local;
+    if ((inplace ? n : x.n_local) + x.n_recv > 2 * h->cfg.max_batch) return fail(AGR_ENOSPC, "received more items than 2 * max_batch");
     return 0;
 }
 // the all-to-all itself: peer segments of `send` to their owners, landing at recv_base in source-rank order
@@ -2077,12 +2095,12 @@ static int exchange_payload(agr_handle* h, const exchange_plan& x, const uint8_t
     return 0;
 }
 // results of the received items back to where they came from (owner-major at the reporter), then the caller's order
-static int exchange_results(agr_handle* h, const exchange_plan& x, const uint8_t* res_all /*local first, then received*/, uint8_t* back,
+static int exchange_results(agr_handle* h, const exchange_plan& x, const uint8_t* res_all /*own items first, then received*/, uint8_t* back,
                             uint8_t* out_dev, uint32_t res_bytes) {
     NK(g_nccl.GroupStart());
     for (uint32_t q = 0; q < x.G; ++q) {
         if (q == x.me) continue;
-        if (x.rcnt[q]) NK(g_nccl.Send(res_all + (size_t)(x.n_local + x.roff[q]) * res_bytes, (size_t)x.rcnt[q] * res_bytes, ncclUint8, (int)q, h->comm, h->stream));
+        if (x.rcnt[q]) NK(g_nccl.Send(res_all + (size_t)(x.recv_res_base + x.roff[q]) * res_bytes, (size_t)x.rcnt[q] * res_bytes, ncclUint8, (int)q, h->comm, h->stream));
         if (x.scnt[q]) NK(g_nccl.Recv(back + (size_t)x.soff[q] * res_bytes, (size_t)x.scnt[q] * res_bytes, ncclUint8, (int)q, h->comm, h->stream));
     }
     NK(g_nccl.GroupEnd());
@@ -2093,36 +2111,90 @@ static int exchange_results(agr_handle* h, const exchange_plan& x, const uint8_t
     }
     return 0;
 }
-static void exchange_fill_info(const exchange_plan& x, uint32_t n, uint64_t first, agr_exchange_info* info) {
+static void exchange_fill_info(const exchange_plan& x, uint32_t n, uint64_t first, uint64_t recv_first, agr_exchange_info* info) {
     if (!info) return;
     memset(info, 0, sizeof *info);
-    info->world = x.G; info->rank = x.me; info->n_local = x.n_local; info->n_sent = n - x.n_local; info->n_received = x.n_recv; info->first_rid = first;
+    info->world = x.G; info->rank = x.me; info->n_local = x.n_local; info->n_sent = n - x.n_local; info->n_received = x.n_recv;
+    info->first_rid = first; info->recv_first_rid = recv_first;
     for (uint32_t q = 0; q < x.G; ++q) { info->sent_to[q] = (q == x.me) ? 0 : x.scnt[q]; info->received_from[q] = x.rcnt[q]; }
+}
+
+// The exchange over a batch that already lies in slab rows [first, first + n) (DMA'd there by agr_ingest_sharded, or filled on
+// the device).  Records of this shard's agents never move: K4 only copies the records owned by a PEER into the send buffer and
+// marks their rows empty; received records land in rows reserved behind the batch, straight from the all-to-all.
+static int sharded_rows_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
+    exchange_plan x;
+    uint8_t* rows = h->d.slab + phys_row(h, first) * AGR_REC;
+    TRY(exchange_begin(h, rows, AGR_REC, AGR_OFF_AGENT_ID, n, true, x));
+    uint64_t first2 = h->rows_used;
+    if (x.n_recv) TRY(reserve_rows_locked(h, x.n_recv, &first2));
+    const uint32_t n_remote = n - x.n_local;
+    x.p.local_dst = nullptr; x.p.send_dst = h->d_send;
+    if (n_remote) { agr_launch_k4_scatter(x.p, h->stream); h->k4_launches += 1; CK(cudaGetLastError()); }
+    // K1 over the batch's own rows (rows emptied by K4 are skipped) — runs while the all-to-all below moves the peers' records
+    if (n) {
+        const uint32_t keep = h->d.cfg_flags;
+        if (n_remote) h->d.cfg_flags |= AGR_CFGI_HOLES;
+        const int rc = launch_k1_locked(h, first, n, h->d_xverd);
+        h->d.cfg_flags = keep;
+        TRY(rc);
+    }
+    // the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
+    TRY(exchange_payload(h, x, h->d_send, h->d.slab + phys_row(h, first2) * AGR_REC, AGR_REC));
+    // K1 at the owner over the received rows (own host's records first, then peers by rank: the merge order)
+    if (x.n_recv) TRY(launch_k1_locked(h, first2, x.n_recv, h->d_xverd + n));
+    // verdicts back to where the records came from, restored to the caller's order
+    TRY(exchange_results(h, x, (const uint8_t*)h->d_xverd, (uint8_t*)h->d_vback, (uint8_t*)h->d_vout, sizeof(agr_verdict)));
+    if (n && out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_vout, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n && out) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
+    exchange_fill_info(x, n, first, first2, info);
+    return 0;
 }
 
 int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
     if (!h || (n && !recs)) return fail(AGR_EINVAL, "NULL argument");
     HLock lk(h);
     CK(cudaSetDevice(h->device));
-    exchange_plan x;
-    TRY(exchange_begin(h, recs, AGR_REC, AGR_OFF_AGENT_ID, n, x));
-    const uint32_t total = x.n_local + x.n_recv;
-    uint64_t first = 0;
-    TRY(reserve_rows_locked(h, total, &first));
-    // stable pack: own records straight into their slab rows, peer segments into the send buffer
-    x.p.local_dst = h->d.slab + phys_row(h, first) * AGR_REC; x.p.send_dst = h->d_send;
-    if (n) { agr_launch_k4_scatter(x.p, h->stream); h->k4_launches += 1; CK(cudaGetLastError()); }
-    // the all-to-all: every peer segment to its owner, landing directly in the owner's slab rows
-    TRY(exchange_payload(h, x, h->d_send, h->d.slab + (phys_row(h, first) + x.n_local) * AGR_REC, AGR_REC));
-    // K1 at the owner over local + received rows (received rows were unpacked by the receive itself)
-    if (total) TRY(launch_k1_locked(h, first, total, h->d_xverd));
-    // verdicts back to where the records came from, restored to the caller's order
-    TRY(exchange_results(h, x, (const uint8_t*)h->d_xverd, (uint8_t*)h->d_vback, (uint8_t*)h->d_vout, sizeof(agr_verdict)));
-    if (n && out) CK(cudaMemcpyAsync(h->h_verdicts, h->d_vout, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (n && out) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
-    exchange_fill_info(x, n, first, info);
-    return 0;
+    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    uint64_t first = h->rows_used;
+    if (n) {
+        TRY(reserve_rows_locked(h, n, &first));
+        // the batch goes STRAIGHT into its slab rows, in chunks on the copy stream (a pageable source through the bounce buffers)
+        const bool src_pinned = is_pinned(recs);
+        while (h->chunk_ev.size() < 2) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->chunk_ev.push_back(e); }
+        CK(cudaEventRecord(h->chunk_ev[0], h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[0], 0));
+        uint8_t* dst = h->d.slab + phys_row(h, first) * AGR_REC;
+        const size_t bytes = (size_t)n * AGR_REC;
+        if (src_pinned) CK(cudaMemcpyAsync(dst, recs, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        else {
+            int bk = 0;
+            for (size_t o = 0; o < bytes;) {
+                const size_t piece = std::min(h->bounce_bytes, bytes - o);
+                CK(cudaEventSynchronize(h->bounce_ev[bk]));
+                par_memcpy(h->bounce[bk], (const uint8_t*)recs + o, piece);
+                CK(cudaMemcpyAsync(dst + o, h->bounce[bk], piece, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->bounce_ev[bk], h->copy_stream));
+                o += piece; bk ^= 1;
+            }
+        }
+        CK(cudaEventRecord(h->chunk_ev[1], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[1], 0));
+    }
+    return sharded_rows_locked(h, first, n, out, info);
+}
+// The same over rows the caller reserved (agr_reserve_rows) and filled on the device: the exchange with the batch resident in HBM.
+int agr_ingest_sharded_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out, agr_exchange_info* info) {
+    if (!h) return fail(AGR_EINVAL, "NULL handle");
+    HLock lk(h);
+    CK(cudaSetDevice(h->device));
+    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
+    if (first_rid + n > h->rows_used) return fail(AGR_EINVAL, "rows not reserved");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    if (!h->resv.empty()) resv_remove(h, first_rid, first_rid + n);
+    return sharded_rows_locked(h, first_rid, n, out, info);
 }
 
 int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results, agr_exchange_info* info) {
@@ -2130,7 +2202,10 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
     HLock lk(h);
     CK(cudaSetDevice(h->device));
     exchange_plan x;
-    TRY(exchange_begin(h, outs, sizeof(agr_outcome), 16, n, x));
+    if (!h->comm) return fail(AGR_ECOMM, "agr_comm_init has not been called on this handle");
+    if (n > h->cfg.max_batch) return fail(AGR_EINVAL, "n exceeds max_batch");
+    if (n) CK(cudaMemcpyAsync(h->d_stage, outs, (size_t)n * sizeof(agr_outcome), cudaMemcpyHostToDevice, h->stream));
+    TRY(exchange_begin(h, h->d_stage, sizeof(agr_outcome), 16, n, false, x));
     const uint32_t total = x.n_local + x.n_recv;
     // pack: own outcomes straight into the K2 input array, peer segments into the send buffer
     x.p.local_dst = (uint8_t*)h->d_outs; x.p.send_dst = h->d_send;
@@ -2147,7 +2222,7 @@ int agr_complete_sharded(agr_handle* h, const agr_outcome* outs, uint32_t n, int
     if (n && results) CK(cudaMemcpyAsync(h->h_results, h->d_vout, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (n && results) memcpy(results, h->h_results, (size_t)n * 4);
-    exchange_fill_info(x, n, 0, info);
+    exchange_fill_info(x, n, 0, 0, info);
     return 0;
 }
 

@@ -56,18 +56,25 @@ __global__ void __launch_bounds__(256) k4_pass(const agr_k4_params p) {
         }
         __syncwarp();
         if (SCATTER) {
+            // in-place mode (records that were DMA'd straight into their slab rows): own items stay where they are, and the
+            // send buffer holds the peers' segments only — positions of owners behind this shard move up by its own count
+            if (p.inplace && valid && owner > p.me) pos -= p.gtotal[p.me];
             if (valid) p.perm[i] = pos;
             // warp-cooperative move of the step's items (item_bytes is a multiple of 16)
             const uint32_t chunks = p.item_bytes >> 4;
+            if (p.inplace && __all_sync(FULL, !valid || owner == p.me)) continue;     // nothing of this step leaves the shard
             for (int src = 0; src < 32; ++src) {
                 const uint32_t si = k0 + src;
                 if (si >= e) break;
                 const uint32_t sowner = __shfl_sync(FULL, owner, src), spos = __shfl_sync(FULL, pos, src);
+                if (p.inplace && sowner == p.me) continue;
                 uint8_t* dst = (sowner == p.me) ? p.local_dst + (size_t)(spos - p.goff[p.me]) * p.item_bytes
                                                 : p.send_dst + (size_t)spos * p.item_bytes;
                 const uint8_t* s = p.items + (size_t)si * p.item_bytes;
                 for (uint32_t c = lane; c < chunks; c += 32)
-                    *reinterpret_cast<uint4*>(dst + c * 16) = ldg_nc_v4(s + c * 16);
+                    *reinterpret_cast<uint4*>(dst + c * 16) = __ldcg(reinterpret_cast<const uint4*>(s + c * 16));
+                // the row it came from is now empty: K1 skips rows whose record carries AGR_FI_HOLE (k1_begin)
+                if (p.inplace && lane == 0) *reinterpret_cast<uint32_t*>(p.items_rw + (size_t)si * p.item_bytes + AGR_OFF_FLAGS) |= AGR_FI_HOLE;
             }
         }
     }
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(256) k4_unpermute(const agr_k4_params p, const
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const uint32_t owner = p.owner[i], pos = p.perm[i];
-    const uint8_t* s = (owner == p.me) ? local_res + (size_t)(pos - p.goff[p.me]) * res_bytes : remote_res + (size_t)pos * res_bytes;
+    const uint8_t* s = (owner == p.me) ? local_res + (size_t)(p.inplace ? i : pos - p.goff[p.me]) * res_bytes : remote_res + (size_t)pos * res_bytes;
     if (res_bytes == 8) *reinterpret_cast<uint2*>(out + (size_t)i * 8) = *reinterpret_cast<const uint2*>(s);
     else *reinterpret_cast<uint32_t*>(out + (size_t)i * 4) = *reinterpret_cast<const uint32_t*>(s);
 }

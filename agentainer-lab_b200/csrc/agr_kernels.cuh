@@ -143,6 +143,8 @@ struct agr_k4_params {
     uint32_t* perm;            // [n]   position of item i in owner-major order
     uint8_t* local_dst;        // where this shard's own items go (final slab rows / local op array)
     uint8_t* send_dst;         // owner-major send buffer (peer segments are shipped as they lie)
+    uint32_t inplace;          // 1: items are slab rows already in their final place: own items are not moved, peers' items are
+    uint8_t* items_rw;         //    copied to the (peers-only) send buffer and their rows marked empty (AGR_FI_HOLE)
 };
 void agr_launch_k4_count(const agr_k4_params& p, cudaStream_t st);
 void agr_launch_k4_scatter(const agr_k4_params& p, cudaStream_t st);

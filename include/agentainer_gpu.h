@@ -402,6 +402,7 @@ int agr_mint_ids(agr_handle* h, uint64_t first_rid, uint32_t n, uint8_t (*ids)[1
  * receive side of the multi-GPU exchange): reserve rows, fill them (agr_synth_fill_rows or a DMA of the caller's
  * own), then run K1 over them.  verdicts may be NULL (they stay on the device). */
 int agr_reserve_rows(agr_handle* h, uint32_t n, uint64_t* first_rid);
+int agr_fill_rows(agr_handle* h, uint64_t first_rid, const agr_record* recs, uint32_t n);   /* DMA host records into reserved rows (no K1) */
 int agr_ingest_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out);
 /* launch-only variants: enqueue on the handle's stream and return without synchronising */
 int agr_ingest_rows_async(agr_handle* h, uint64_t first_rid, uint32_t n);
@@ -420,9 +421,10 @@ void* agr_slab_ptr(agr_handle* h, uint64_t rid); /* device address of a slab row
 /* One handle per GPU; shard owner of an agent = agr_agent_shard(id, world).  Fresh traffic is steered to the owner by
  * the host when it parses /agent/{id} (server.go:494-495) and needs no collective.  Records that reach a non-owner shard
  * (BASELINE config 4: replay-flagged requests re-injected through another shard's proxy) are routed here:
- * K4 bins the batch by owner and packs it (local records go straight into their slab rows), ONE grouped
- * ncclSend/ncclRecv all-to-all over NVLink ships every peer segment to its owner, K1 runs at the owner over
- * local + received rows, and the verdicts travel back the same way and are restored to the caller's order.
+ * the batch is DMA'd straight into its slab rows; K4 bins it by owner there, copies only the records owned by a PEER into the
+ * send buffer (their rows are marked empty) and ONE grouped ncclSend/ncclRecv all-to-all over NVLink ships every peer segment
+ * into rows reserved at its owner; K1 runs over the own rows while the exchange is in flight and over the received rows after
+ * it, and the verdicts travel back the same way and are restored to the caller's order.
  * NCCL is loaded at run time (libnccl.so.2); without it agr_comm_init fails with AGR_ECOMM.  Collective: every rank of
  * the communicator must call agr_ingest_sharded the same number of times (n may be 0). */
 int agr_comm_unique_id(uint8_t out[128]);                                          /* rank 0; ship to the other ranks */
@@ -431,9 +433,13 @@ typedef struct agr_exchange_info {
     uint32_t world, rank;
     uint32_t n_local, n_sent, n_received;      /* records of the batch owned here / shipped / received from peers */
     uint32_t sent_to[32], received_from[32];
-    uint64_t first_rid;                        /* rows: [first_rid, +n_local) local, then received, grouped by source rank */
+    uint64_t first_rid;                        /* rows [first_rid, +n) hold the caller's batch in arrival order; the rows of records
+                                                  that were shipped to their owner are empty */
+    uint64_t recv_first_rid;                   /* rows [recv_first_rid, +n_received): the records received, grouped by source rank */
 } agr_exchange_info;
 int agr_ingest_sharded(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, agr_exchange_info* info);
+/* The same exchange over a batch that is already resident in rows [first_rid, +n) (agr_reserve_rows + a fill on the device). */
+int agr_ingest_sharded_rows(agr_handle* h, uint64_t first_rid, uint32_t n, agr_verdict* out, agr_exchange_info* info);
 /* The same route for outcomes (cross-shard replay reconciliation): an outcome reported at a shard that does not own the
  * agent (the worker of shard A replayed through shard B's proxy) is shipped to the owner, applied there by K2 in
  * (own host first, then peers by rank) order, and its result code comes back.  Collective like agr_ingest_sharded. */
