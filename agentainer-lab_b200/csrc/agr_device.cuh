@@ -209,6 +209,21 @@ __device__ __forceinline__ k1_result k1_finish(const agr_dev& d, uint32_t rid, c
     return out;
 }
 
+// TTL bookkeeping of a K1 tile: `mine` = this lane's record created_at (~0 for a lane without a record); the warp's minimum
+// lowers the time bound of the chunk(s) the tile's rows [first, first + count) lie in (k_expire reads them).  One or two
+// atomics per 32 records.
+__device__ __forceinline__ void k1_note_time(const agr_dev& d, const uint32_t first, const uint32_t count, const unsigned long long mine) {
+    const uint32_t hi = (uint32_t)(mine >> 32), hmin = __reduce_min_sync(FULL, hi);
+    const uint32_t lmin = __reduce_min_sync(FULL, hi == hmin ? (uint32_t)mine : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0 && count) {
+        unsigned long long t = pack64(lmin, hmin);
+        if (t == 0ULL) t = 1ULL;                                                          // 0 means "unknown"
+        const uint32_t c0 = first / AGR_CHUNK_ROWS, c1 = (first + count - 1u) / AGR_CHUNK_ROWS;
+        atomicMin(d.cmin + c0, t);
+        if (c1 != c0) atomicMin(d.cmin + c1, t);
+    }
+}
+
 #define K1_NLC 10  // counters C_INGESTED .. C_BAD_LEN are contiguous from 0
 
 __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc, uint32_t* s_ctr) {

@@ -69,7 +69,6 @@ struct agr_handle {
     uint64_t released_total = 0;
     uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
-    uint64_t sweep_clean = 0; // TTL sweep: rows below were ingested when agr_expire last ran (their chunks' time bounds are valid)
     // host agent map + mirror
     std::unordered_map<std::string, uint32_t> slot_of;
     std::vector<std::string> agent_names;
@@ -91,6 +90,7 @@ struct agr_handle {
     std::vector<std::pair<uint64_t, uint64_t>> resv;   // rows handed out by agr_reserve_rows and not ingested yet: [first, end)
     // K3
     uint32_t* d_matrix = nullptr; size_t matrix_entries = 0;
+    uint32_t* d_selmask = nullptr; size_t selmask_words = 0;   // one selection bit per scanned item (k3_mark -> k3_place)
     uint32_t* d_gtotal = nullptr; uint32_t* d_goff = nullptr;
     uint32_t* d_out_rid = nullptr; uint32_t* d_out_slot = nullptr; uint32_t out_cap = 0;
     uint32_t* d_min_inq = nullptr;
@@ -722,7 +722,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.ptime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.mtime, c.slab_rows, true));
     TRY(dev_alloc(h, &d.head, c.slab_rows, true));
-    TRY(dev_alloc(h, &d.cmin, (size_t)(c.slab_rows / AGR_CHUNK_ROWS + 2), true));
+    TRY(dev_alloc(h, &d.cmin, (size_t)(c.slab_rows / AGR_CHUNK_ROWS + 2), false));
+    CK(cudaMemsetAsync(d.cmin, 0xff, (size_t)(c.slab_rows / AGR_CHUNK_ROWS + 2) * 8, h->stream));   // ~0: no stored row in any chunk yet
     // the key of the id permutation: drawn from the OS CSPRNG unless the caller brings one (a restore passes the snapshot's),
     // so that ids of one engine instance never resolve in another and cannot be guessed (the reference mints uuid.New())
     d.id_secret = c.id_secret;
@@ -1204,14 +1205,17 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.groups = (mode == K3_TICK) ? std::max<uint32_t>(1, (uint32_t)h->agent_names.size()) : 1;
     uint64_t items = hi - lo;
     uint64_t max_warps = std::max<uint64_t>(1, (4u << 20) / p.groups);
-    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 64, (items + 1023) / 1024);
+    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 32, (items + 1023) / 1024);   // 32 warps per SM, eight 32-row steps in flight each
     p.nwarps = (uint32_t)std::max<uint64_t>(1, std::min(want, max_warps));
     uint64_t per = (items + p.nwarps - 1) / p.nwarps;
-    per = (per + 31) & ~31ull;
+    per = (per + 255) & ~255ull;
     p.per_warp = (uint32_t)per;
     p.nwarps = (uint32_t)((items + per - 1) / per);
     size_t need = (size_t)p.nwarps * p.groups;
     if (need > h->matrix_entries) { TRY(dev_regrow(h, &h->d_matrix, need, false)); h->matrix_entries = need; }
+    const size_t mask_words = (size_t)p.nwarps * (p.per_warp >> 5);
+    if (mask_words > h->selmask_words) { TRY(dev_regrow(h, &h->d_selmask, mask_words, false)); h->selmask_words = mask_words; }
+    p.selmask = h->d_selmask;
     TRY(ensure_out(h, cap));
     p.matrix = h->d_matrix; p.gtotal = h->d_gtotal; p.goff = h->d_goff;
     p.out_rid = h->d_out_rid; p.out_slot = h->d_out_slot; p.cap = cap;
@@ -1223,7 +1227,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
         CK(cudaEventRecord(h->op_ev[2], h->stream));
     }
     agr_launch_k3_select(h->d, p, h->sm_count, h->stream);
-    h->k3_launches += 6;
+    h->k3_launches += 4;
     CK(cudaGetLastError());
     if (timing) { CK(cudaEventRecord(h->op_ev[3], h->stream)); h->op_timed[1] = true; }
     CK(cudaMemcpyAsync(h->h_small, h->d_goff + p.groups, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1815,7 +1819,8 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     if (cudaMemcpy(h->d.log_len, lens, sizeof lens, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(AGR_ECUDA, "restore: log_len"));
     h->rows_used = hd.rows_used; h->vused = hd.vused; h->vtail = hd.vtail; h->scan_lo = hd.scan_lo;
     h->d.shard_id = hd.shard; h->d.id_gen = hd.gen; h->tail = hd.tail; h->released_total = hd.released_total; sync_window(h);
-    h->d.idx_base = h->tail; h->sweep_clean = h->tail;
+    h->d.idx_base = h->tail;
+    cudaMemsetAsync(h->d.cmin, 0, (size_t)(h->cfg.slab_rows / AGR_CHUNK_ROWS + 2) * 8, h->stream);       // time bounds unknown: the first sweep recomputes them
     if (!(hd.flags & AGR_CFG_MINT_IDS) && R) {        // hash-id mode: rebuild the dedupe index from the restored rows
         agr_launch_reindex(h->d, (uint32_t)R, h->stream);
         h->k1_launches += 1;
@@ -1826,20 +1831,6 @@ int agr_restore(const agr_config* cfg, const char* path, agr_handle** out) {
     return 0;
 }
 
-// physical chunks that hold rows of the logical range [lo, hi): their cached time bounds are reset to "unknown"
-static int sweep_invalidate(agr_handle* h, uint64_t lo, uint64_t hi) {
-    if (hi <= lo) return 0;
-    const uint64_t R = h->cfg.slab_rows;
-    if (is_ring(h) && hi - lo >= R) return cudaMemsetAsync(h->d.cmin, 0, (size_t)(R / AGR_CHUNK_ROWS + 1) * 8, h->stream) == cudaSuccess ? 0 : fail(AGR_ECUDA, "cmin memset");
-    const uint64_t p0 = phys_row(h, lo), p1 = phys_row(h, hi - 1);
-    auto zero = [&](uint64_t a, uint64_t b) {                      // physical rows [a, b]
-        const uint64_t c0 = a / AGR_CHUNK_ROWS, c1 = b / AGR_CHUNK_ROWS;
-        return cudaMemsetAsync(h->d.cmin + c0, 0, (size_t)(c1 - c0 + 1) * 8, h->stream) == cudaSuccess;
-    };
-    bool ok = (p0 <= p1) ? zero(p0, p1) : (zero(p0, R - 1) && zero(0, p1));
-    return ok ? 0 : fail(AGR_ECUDA, "cmin memset");
-}
-
 int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     if (!h) return fail(AGR_EINVAL, "NULL argument");
     HLock lk(h);
@@ -1847,11 +1838,7 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
     sync_window(h);
-    // chunks that received rows since the last sweep (and the ones still being filled) lose their cached bound
-    TRY(sweep_invalidate(h, std::max(h->sweep_clean, h->tail), h->rows_used));
-    const uint64_t bound = ingested_bound(h);
-    agr_launch_expire(h->d, rows_span(h), now, ttl, bound, d_cnt, h->stream);
-    h->sweep_clean = bound;
+    agr_launch_expire(h->d, rows_span(h), now, ttl, d_cnt, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
     if (!expired) {                       // no count wanted: stay asynchronous (the sweep is stream-ordered before whatever follows)

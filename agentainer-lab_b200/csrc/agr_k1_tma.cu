@@ -146,6 +146,7 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
 #pragma unroll
         for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
         if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
+        k1_note_time(d, first_rid + tile * TILE_RECS, min(TILE_RECS, n - tile * TILE_RECS), valid ? pack64(h4.x, h4.y) : ~0ULL);
         // previous tile: its CAS has had a full tile to come back
         if (pvalid) {
             const uint4 qh5 = make_uint4(0, ph5y, 0, 0);

@@ -25,6 +25,16 @@ __device__ __forceinline__ uint4 v_lds128(uint32_t a) {
     return v;
 }
 
+// TTL bookkeeping (k_expire): a stored record lowers its chunk's time bound to its created_at.  Arrival times hardly ever run
+// backwards, so after a chunk's first records the bound is already low enough and the atomic is skipped.
+__device__ __forceinline__ void k1v_note_time(const agr_dev& d, const uint32_t rid, const uint32_t state, const uint4& h4) {
+    if (!(state & ST_STORED)) return;
+    unsigned long long t = pack64(h4.x, h4.y);
+    if (t == 0ULL) t = 1ULL;
+    unsigned long long* cm = d.cmin + rid / AGR_CHUNK_ROWS;
+    if (t < __ldcg(cm)) atomicMin(cm, t);
+}
+
 // tile_first[t] = index of the first record whose start offset is >= t * VT_TILE, for t = 0 .. ntiles (tile_first[ntiles]
 // = n).  Record i is that record for every boundary t * VT_TILE in (start(i-1), start(i)]; the sentinel i == n takes the
 // boundaries after the last start.  Tile t then owns records [tile_first[t], tile_first[t+1]).
@@ -151,6 +161,7 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
             k1_ctx cx;
             k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, cx);
             const k1_result res = k1_finish(d, rid, h1, h5, cx, lc);
+            k1v_note_time(d, rid, res.state, h4);
             d.state[rid] = res.state;
             d.route[rid] = res.route;
             d.cksum[rid] = s_ck[warp][r];
@@ -280,6 +291,7 @@ k1_ingest_var_lsu(const agr_dev d, const uint8_t* __restrict__ blob, const uint3
                 k1_ctx cx;
                 k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, cx);
                 const k1_result res = k1_finish(d, rid, h1, h5, cx, lc);
+                k1v_note_time(d, rid, res.state, h4);
                 d.state[rid] = res.state;
                 d.route[rid] = res.route;
                 d.cksum[rid] = s_ck[warp][r];

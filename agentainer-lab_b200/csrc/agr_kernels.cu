@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
                 if ((uint32_t)lane == r0 + u) { c0 += p0; c1 += p1; }
             }
         }
+        k1_note_time(d, first_rid + tile * 32u, min(32u, n - tile * 32u), valid ? pack64(h4.x, h4.y) : ~0ULL);
         // ---- pass 1: decision chain, one record per lane
         if (valid) {
             k1_result r = k1_finish(d, rid, h1, h5, cx, lc);
@@ -173,13 +174,14 @@ __global__ void __launch_bounds__(256) k_verify(const agr_dev d, const unsigned 
 }
 // TTL sweep: the reference stores every record with SET ... EX 24h (requests.go:106,175,270); a record whose last SET is
 // ttl or more in the past is gone (GET misses), while its id stays in whatever lists hold it.
-// One CTA per chunk of AGR_CHUNK_ROWS physical rows.  cmin[c] caches a lower bound of the last-SET times of the chunk's
-// stored rows (0 = unknown, ~0 = no stored row): a chunk whose bound says nothing can have expired costs one 8-byte
-// load instead of a sweep, so a periodic call touches only the chunks that are due (and the ones ingested since the last
-// call, whose bound the host has reset).  K2 lowers the bound if an outcome carries an older time than the bound.
+// One CTA per chunk of AGR_CHUNK_ROWS physical rows.  cmin[c] is a lower bound of the last-SET times of the chunk's stored
+// rows (~0 = no stored row, 0 = unknown: after a restore): K1 lowers it to a tile's earliest created_at when it stores the
+// tile (k1_note_time), K2 lowers it if an outcome carries an older time, and this sweep replaces it by the exact minimum of
+// what it leaves behind.  A chunk whose bound says nothing can have expired costs one 8-byte load instead of a sweep, so
+// a periodic call reads only the chunks that are due.
+#define EXP_PER_THREAD (AGR_CHUNK_ROWS / 256u)
 __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned long long rows, const unsigned long long now,
-                                                const unsigned long long ttl, const unsigned long long bound /* rows below are ingested */,
-                                                unsigned long long* __restrict__ expired) {
+                                                const unsigned long long ttl, unsigned long long* __restrict__ expired) {
     __shared__ unsigned long long s_min[8];
     __shared__ uint32_t s_cnt;
     const uint32_t c = blockIdx.x;
@@ -189,17 +191,33 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const unsigned long long r0 = (unsigned long long)c * AGR_CHUNK_ROWS;
+    // three rounds of independent loads (state words, then the K2 times, then created_at of the rows K2 never wrote) instead
+    // of a dependent chain per row
+    uint32_t st[EXP_PER_THREAD];
+    unsigned long long t[EXP_PER_THREAD];
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+        const unsigned long long rid = r0 + threadIdx.x + q * 256u;
+        st[q] = rid < rows ? d.state[rid] : 0u;
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+        const unsigned long long rid = r0 + threadIdx.x + q * 256u;
+        t[q] = (st[q] & ST_STORED) ? d.mtime[rid] : 1ULL;
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+        const unsigned long long rid = r0 + threadIdx.x + q * 256u;
+        if ((st[q] & ST_STORED) && t[q] == 0ULL) t[q] = __ldcs(reinterpret_cast<const unsigned long long*>(rec_ptr(d, (uint32_t)rid) + AGR_OFF_SEQ));
+    }
     unsigned long long lmin = ~0ULL;
     uint32_t gone = 0;
-    for (uint32_t k = threadIdx.x; k < AGR_CHUNK_ROWS; k += 256) {
-        const unsigned long long rid = r0 + k;
-        if (rid >= rows) break;
-        const uint32_t st = d.state[rid];
-        if (!(st & ST_STORED)) continue;
-        unsigned long long t = d.mtime[rid];
-        if (t == 0) t = *reinterpret_cast<const unsigned long long*>(rec_ptr(d, (uint32_t)rid) + AGR_OFF_SEQ);
-        if (now >= t && now - t >= ttl) { d.state[rid] = st & ~ST_STORED; gone++; }
-        else if (t < lmin) lmin = t;
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+        if (!(st[q] & ST_STORED)) continue;
+        const unsigned long long rid = r0 + threadIdx.x + q * 256u;
+        if (now >= t[q] && now - t[q] >= ttl) { d.state[rid] = st[q] & ~ST_STORED; gone++; }
+        else if (t[q] < lmin) lmin = t[q];
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { const unsigned long long y = __shfl_xor_sync(FULL, lmin, o); if (y < lmin) lmin = y; }
@@ -210,15 +228,12 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
 #pragma unroll
         for (int w = 1; w < 8; ++w) if (s_min[w] < lmin) lmin = s_min[w];
         if (s_cnt) atomicAdd(expired, (unsigned long long)s_cnt);
-        // cache the bound only for chunks no batch can still add rows to (every row of the chunk lies below the ingested bound)
-        unsigned long long last = r0 + AGR_CHUNK_ROWS - 1; if (last >= rows) last = rows - 1;
-        const bool settled = row_logical(d, (uint32_t)r0) < bound && row_logical(d, (uint32_t)last) < bound;
-        d.cmin[c] = settled ? (lmin == 0ULL ? 1ULL : lmin) : 0ULL;
+        d.cmin[c] = (lmin == 0ULL) ? 1ULL : lmin;               // exact now (~0: the chunk holds no stored row any more)
     }
 }
-void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl, unsigned long long bound,
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
                        unsigned long long* expired, cudaStream_t st) {
-    if (rows) k_expire<<<(unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, rows, now, ttl, bound, expired);
+    if (rows) k_expire<<<(unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, rows, now, ttl, expired);
 }
 // ---- ring mode (AGR_CFG_RING): releasing rows at the tail
 // offset (from the tail) of the first row that still holds a stored record, among the `live` rows behind the tail.  Blocks
@@ -226,12 +241,16 @@ void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long 
 __global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsigned long long live, uint32_t* __restrict__ out_off) {
     const unsigned long long b0 = (unsigned long long)blockIdx.x * AGR_CHUNK_ROWS;
     if (*reinterpret_cast<volatile uint32_t*>(out_off) < b0) return;
-    uint32_t mine = 0xffffffffu;
-    for (uint32_t k = threadIdx.x; k < AGR_CHUNK_ROWS; k += 256) {
-        const unsigned long long q = b0 + k;
-        if (q >= live) break;
-        if (d.state[row_physical(d, d.tail + q)] & ST_STORED) { mine = (uint32_t)q; break; }
+    uint32_t st[EXP_PER_THREAD];
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+        const unsigned long long k = b0 + threadIdx.x + q * 256u;
+        st[q] = k < live ? d.state[row_physical(d, d.tail + k)] : 0u;
     }
+    uint32_t mine = 0xffffffffu;
+#pragma unroll
+    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q)
+        if ((st[q] & ST_STORED) && mine == 0xffffffffu) mine = (uint32_t)(b0 + threadIdx.x + q * 256u);
     mine = __reduce_min_sync(FULL, mine);
     if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
 }
@@ -245,8 +264,7 @@ __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uin
     if (k >= count) return;
     const uint32_t p = row_physical(d, d.tail + k);
     d.state[p] = 0; d.route[p] = 0; d.aux[p] = 0; d.head[p] = 0; d.ptime[p] = 0; d.mtime[p] = 0;
-    resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;
-    if ((p & (AGR_CHUNK_ROWS - 1u)) == 0u || k == 0u) d.cmin[p / AGR_CHUNK_ROWS] = 0;   // the chunk's time bound is unknown again
+    resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;      // (the chunk's time bound stays a valid lower bound of what is left)
 }
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
     if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
@@ -583,11 +601,15 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
     return o;
 }
 
-// SMEM: the warp's row of per-group cursors lives in shared memory (groups <= K3_SMEM_GROUPS); otherwise in the global
-// matrix through volatile accesses.
+// Two passes over a warp's contiguous run of items, but the row words are read ONCE:
+//   k3_mark   reads state + route (or the log entry and its row's route), decides, leaves one selection bit per item in
+//             selmask and the warp's per-group counts in its matrix row (shared-memory counters when groups <= K3_SMEM_GROUPS);
+//   column scan (k3_colscan + k3_scan_total): matrix[w][g] = number of group-g items in warps < w, goff = group offsets;
+//   k3_place  walks the selection bits (4 B per 32 items), fetches the agent slot of the SELECTED items only, and writes them
+//             at goff[g] + matrix[w][g] + stable rank (match_any + popc: the warp-ballot agent-id partition).
 #define K3_SMEM_GROUPS 1024u
-template <bool SCATTER, bool SMEM>
-__global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_params p) {
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_params p) {
     extern __shared__ uint32_t s_rows[];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -595,7 +617,7 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     uint32_t* grow = p.matrix + (size_t)w * p.groups;
     uint32_t* srow = s_rows + (size_t)(threadIdx.x >> 5) * p.groups;
     if (SMEM) {
-        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = SCATTER ? grow[g] : 0u;
+        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = 0u;
         __syncwarp();
     }
     const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
@@ -603,6 +625,7 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
     if (e > p.hi) e = p.hi;
     uint32_t mininq = AGR_RID_NONE;
     const bool rows = (p.mode != K3_LOG_AGENT);
+    uint32_t* mask = p.selmask + (size_t)w * (p.per_warp >> 5);
     // physical row of item k: the warp's run is contiguous in the ring and wraps at most once
     const uint32_t pb = rows ? row_physical(d, b) : 0u;
     auto prow_of = [&](unsigned long long k) -> uint32_t {
@@ -610,106 +633,120 @@ __global__ void __launch_bounds__(256) k3_pass(const agr_dev d, const agr_k3_par
         if (d.ring_rows && q >= d.ring_rows) q -= d.ring_rows;
         return q;
     };
-    // the row words of four steps (128 rows) are loaded at once, and the next four while these are being worked on
-    uint32_t st_c[4], rt_c[4], pr_c[4], st_n[4], rt_n[4], pr_n[4];
-    auto load4 = [&](unsigned long long k0, uint32_t (&st)[4], uint32_t (&rt)[4], uint32_t (&pr)[4]) {
+    // the row words of eight steps (256 rows) are in flight at once
+    constexpr int NS = 8;
+    uint32_t st_c[NS], rt_c[NS], pr_c[NS];
+    for (unsigned long long k8 = b; k8 < e; k8 += 32u * NS) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned long long k = k0 + 32u * j + lane;
-            pr[j] = prow_of(k);
+        for (int j = 0; j < NS; ++j) {
+            const unsigned long long k = k8 + 32u * j + lane;
+            pr_c[j] = prow_of(k);
             const bool ok = rows && k < e;
-            st[j] = ok ? d.state[pr[j]] : 0u;
-            rt[j] = ok ? d.route[pr[j]] : 0u;
+            st_c[j] = ok ? __ldcs(&d.state[pr_c[j]]) : 0u;
+            rt_c[j] = ok ? __ldcs(&d.route[pr_c[j]]) : 0u;
         }
-    };
-    load4(b, st_c, rt_c, pr_c);
-    for (unsigned long long k4 = b; k4 < e; k4 += 128) {
-        load4(k4 + 128, st_n, rt_n, pr_n);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned long long k0 = k4 + 32u * j;
+        for (int j = 0; j < NS; ++j) {
+            const unsigned long long k0 = k8 + 32u * j;
             if (k0 >= e) break;
             const uint32_t st = st_c[j], rt = rt_c[j], pr = pr_c[j];
-            if (rows && !__any_sync(FULL, (st & ST_INQ) != 0u)) continue;            // nothing pending in these 32 rows
-            k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
-            if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
-            const uint32_t g = (p.groups == 1) ? 0u : it.slot;
-            if (!SCATTER) {
-                // counting needs no order: one shared (or global) reduction per selected row
-                if (it.sel) atomicAdd((SMEM ? srow : grow) + g, 1u);
-                continue;
+            uint32_t selbits = 0u;
+            if (!rows || __any_sync(FULL, (st & ST_INQ) != 0u)) {                    // else: nothing pending in these 32 rows
+                const k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
+                if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
+                if (it.sel) atomicAdd((SMEM ? srow : grow) + ((p.groups == 1) ? 0u : it.slot), 1u);   // counting needs no order
+                selbits = __ballot_sync(FULL, it.sel);
             }
-            if (!__any_sync(FULL, it.sel)) continue;
-            const uint32_t key = it.sel ? g : (0x80000000u | (uint32_t)lane);
+            if (lane == 0) mask[(k0 - b) >> 5] = selbits;
+        }
+    }
+    if (SMEM) {
+        __syncwarp();
+        for (uint32_t g = lane; g < p.groups; g += 32) grow[g] = srow[g];
+    }
+    if (p.min_inq && p.mode == K3_TICK) {
+        mininq = __reduce_min_sync(FULL, mininq);
+        if (lane == 0 && mininq != AGR_RID_NONE) atomicMin(p.min_inq, mininq);
+    }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_params p) {
+    extern __shared__ uint32_t s_rows[];
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= p.nwarps) return;
+    uint32_t* grow = p.matrix + (size_t)w * p.groups;
+    uint32_t* srow = s_rows + (size_t)(threadIdx.x >> 5) * p.groups;
+    if (SMEM) {
+        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = grow[g];
+        __syncwarp();
+    }
+    const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
+    unsigned long long e = b + p.per_warp;
+    if (e > p.hi) e = p.hi;
+    const bool rows = (p.mode != K3_LOG_AGENT);
+    const uint32_t* mask = p.selmask + (size_t)w * (p.per_warp >> 5);
+    const uint32_t pb = rows ? row_physical(d, b) : 0u;
+    const uint32_t steps = (uint32_t)((e - b + 31u) >> 5);
+    for (uint32_t s0 = 0; s0 < steps; s0 += 32) {
+        const uint32_t mine = (s0 + lane < steps) ? mask[s0 + lane] : 0u;          // 32 steps' selection words in one load
+        uint32_t live = __ballot_sync(FULL, mine != 0u);
+        while (live) {
+            const int j = __ffs(live) - 1; live &= live - 1u;
+            const uint32_t bits = __shfl_sync(FULL, mine, j);
+            const unsigned long long k = b + ((unsigned long long)(s0 + j) << 5) + lane;
+            const bool sel = (bits >> lane) & 1u;
+            uint32_t rid = AGR_RID_NONE, slot = 0u;
+            if (sel) {
+                if (rows) { rid = pb + (uint32_t)(k - b); if (d.ring_rows && rid >= d.ring_rows) rid -= d.ring_rows; }
+                else rid = p.log[k];
+                slot = rt_slot(d.route[rid]);
+            }
+            const uint32_t g = (p.groups == 1) ? 0u : slot;
+            const uint32_t key = sel ? g : (0x80000000u | (uint32_t)lane);
             const uint32_t peers = __match_any_sync(FULL, key);
-            if (it.sel) {
+            if (sel) {
                 // the lowest lane of each group claims room for the whole group; stable rank inside the group = popc below
                 const int leader = __ffs(peers) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
                 base = __shfl_sync(peers, base, leader);
                 const uint32_t pos = p.goff[g] + base + __popc(peers & ((1u << lane) - 1u));
-                if (pos < p.cap) { p.out_rid[pos] = it.rid; p.out_slot[pos] = it.slot; }
+                if (pos < p.cap) { p.out_rid[pos] = rid; p.out_slot[pos] = slot; }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { st_c[j] = st_n[j]; rt_c[j] = rt_n[j]; pr_c[j] = pr_n[j]; }
-    }
-    if (SMEM && !SCATTER) {
-        __syncwarp();
-        for (uint32_t g = lane; g < p.groups; g += 32) grow[g] = srow[g];
-    }
-    if (!SCATTER && p.min_inq && p.mode == K3_TICK) {
-        mininq = __reduce_min_sync(FULL, mininq);
-        if (lane == 0 && mininq != AGR_RID_NONE) atomicMin(p.min_inq, mininq);
     }
 }
 
-// column scan, two levels, every access coalesced across groups: the warp rows are cut into K3_SEGS segments;
-// (1) thread (seg, g) sums its segment of column g, (2) thread g scans the K3_SEGS partial sums, (3) thread (seg, g) rewrites
-// its segment as exclusive prefixes.  Afterwards matrix[w][g] = number of group-g items in warps < w.
-#define K3_SEGS 64u
-__global__ void __launch_bounds__(256) k3_seg_sum(const agr_k3_params p, uint32_t* __restrict__ partial) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
-    if (g >= p.groups) return;
-    const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
+// Column scan of matrix[nwarps][groups] in ONE launch: a CTA owns 32 adjacent columns (coalesced 128 B rows); its 32 warps cut
+// the rows into 32 segments: (1) every warp sums its segment per column, (2) an exclusive scan over the 32 segment sums in shared
+// memory, (3) every warp rewrites its segment as exclusive prefixes.  gtotal[g] = the column total.
+__global__ void __launch_bounds__(1024) k3_colscan(const agr_k3_params p) {
+    __shared__ uint32_t s_seg[32][33];
+    const uint32_t g = blockIdx.x * 32u + (threadIdx.x & 31u), seg = threadIdx.x >> 5;
+    const uint32_t per = (p.nwarps + 31u) / 32u, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
+    const bool ok = g < p.groups;
     uint32_t sum = 0;
+    if (ok) {
 #pragma unroll 8
-    for (uint32_t w = w0; w < w1; ++w) sum += __ldcg(&p.matrix[(size_t)w * p.groups + g]);
-    partial[(size_t)seg * p.groups + g] = sum;
-}
-__global__ void __launch_bounds__(256) k3_seg_scan(const agr_k3_params p, uint32_t* __restrict__ partial) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.groups) return;
-    uint32_t run = 0;
-    for (uint32_t s0 = 0; s0 < K3_SEGS; s0 += 8) {               // eight independent loads, then the serial prefix
-        uint32_t v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = partial[(size_t)(s0 + k) * p.groups + g];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { partial[(size_t)(s0 + k) * p.groups + g] = run; run += v[k]; }
+        for (uint32_t w = w0; w < w1; ++w) sum += __ldcg(&p.matrix[(size_t)w * p.groups + g]);
     }
-    p.gtotal[g] = run;
-}
-__global__ void __launch_bounds__(256) k3_seg_apply(const agr_k3_params p, const uint32_t* __restrict__ partial) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
-    if (g >= p.groups) return;
-    const uint32_t per = (p.nwarps + K3_SEGS - 1) / K3_SEGS, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
-    uint32_t run = partial[(size_t)seg * p.groups + g];
-    for (uint32_t wb = w0; wb < w1; wb += 8) {                   // eight independent loads, then the serial prefix
-        uint32_t v[8];
+    s_seg[seg][threadIdx.x & 31u] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (wb + k < w1) ? p.matrix[(size_t)(wb + k) * p.groups + g] : 0u;
+    for (int k = 0; k < 32; ++k) { const uint32_t v = s_seg[k][threadIdx.x & 31u]; if ((uint32_t)k < seg) run += v; total += v; }
+    if (ok) {
+        for (uint32_t wb = w0; wb < w1; wb += 8) {                   // eight independent loads, then the serial prefix
+            uint32_t v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (wb + k < w1) { p.matrix[(size_t)(wb + k) * p.groups + g] = run; run += v[k]; }
+            for (int k = 0; k < 8; ++k) v[k] = (wb + k < w1) ? __ldcg(&p.matrix[(size_t)(wb + k) * p.groups + g]) : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (wb + k < w1) { p.matrix[(size_t)(wb + k) * p.groups + g] = run; run += v[k]; }
+        }
+        if (seg == 0) p.gtotal[g] = total;
     }
-}
-static void k3_scan_groups_launch(const agr_k3_params& p, cudaStream_t st) {
-    uint32_t* partial = p.gtotal + p.groups + 8;                 // scratch behind gtotal (sized by the engine)
-    const dim3 grid((p.groups + 255u) / 256u, K3_SEGS);
-    k3_seg_sum<<<grid, 256, 0, st>>>(p, partial);
-    k3_seg_scan<<<(p.groups + 255u) / 256u, 256, 0, st>>>(p, partial);
-    k3_seg_apply<<<grid, 256, 0, st>>>(p, partial);
 }
 // exclusive scan over groups (one CTA, loops for groups > 1024); goff[groups] = total
 __global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
@@ -740,16 +777,16 @@ void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStr
     const uint32_t blocks = (p.nwarps * 32u + 255u) / 256u;
     if (p.groups <= K3_SMEM_GROUPS) {
         const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 32 KiB
-        k3_pass<false, true><<<blocks, 256, smem, st>>>(d, p);
-        k3_scan_groups_launch(p, st);
+        k3_mark<true><<<blocks, 256, smem, st>>>(d, p);
+        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
-        k3_pass<true, true><<<blocks, 256, smem, st>>>(d, p);
+        k3_place<true><<<blocks, 256, smem, st>>>(d, p);
     } else {
         cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
-        k3_pass<false, false><<<blocks, 256, 0, st>>>(d, p);
-        k3_scan_groups_launch(p, st);
+        k3_mark<false><<<blocks, 256, 0, st>>>(d, p);
+        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
-        k3_pass<true, false><<<blocks, 256, 0, st>>>(d, p);
+        k3_place<false><<<blocks, 256, 0, st>>>(d, p);
     }
 }
 

@@ -35,7 +35,7 @@ struct agr_dev {
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
     unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
     unsigned long long* mtime; // [rows] time of the latest SET of the record by K2 (0: only StoreRequest's, = the record's seq)
-    unsigned long long* cmin;  // [rows / AGR_CHUNK_ROWS + 1] TTL sweep: lower bound of the last-SET times in a chunk (0 unknown, ~0 empty)
+    unsigned long long* cmin;  // [rows / AGR_CHUNK_ROWS + 2] TTL sweep: lower bound of the last-SET times in a chunk (0 unknown, ~0 empty)
     unsigned long long* voff;  // variable-length mode: byte offset of row's record in the slab (nullptr = fixed 512 B rows)
     uint32_t* vlen;            // variable-length mode: stored length of the record
     unsigned long long id_secret;   // AGR_CFG_MINT_IDS
@@ -94,6 +94,7 @@ struct agr_k3_params {
     uint32_t* out_rid;         // [cap]
     uint32_t* out_slot;        // [cap]
     uint32_t cap;
+    uint32_t* selmask;         // [nwarps * per_warp / 32] one selection bit per item, written by k3_mark, read by k3_place
     uint32_t* min_inq;         // TICK: lowest item (offset from lo) still in a pending list: low-water mark for the next scan
 };
 
@@ -155,7 +156,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
                    cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                    void* verdicts = nullptr /* device agr_verdict[n], written by k1_post */,
                    void* ids = nullptr /* device u8[n][16]: Request.ID per record, written by k1_post */);
-void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl, unsigned long long bound,
+void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
                        unsigned long long* expired, cudaStream_t st);
 // ring mode: first live (STORED) row at or after the tail, as an offset from it (0xffffffff: none), then release of
 // `count` rows from the tail and stable compaction of a log (entries of released rows drop out)

@@ -744,48 +744,155 @@ def make_var_blob(A, n, first_index, seed, n_agents, nanos0, rng):
     return blob, offs.astype(np.uint32), int(offs[-1])
 
 
-def run_varlen(args, rank, world, local_rank):
-    """--workload c5: mixed 128 B - 4 KB bodies through agr_ingest_var (byte-tiled K1, 1-D bulk TMA)."""
+def run_c5(args, rank, world, local_rank):
+    """--workload c5 (BASELINE configs[4]): a SUSTAINED stream of variable-length records (bodies log-uniform in 128 B .. 4 KB)
+    through a ring-mode engine on every GPU, with the whole state machine in the loop:
+      every batch   agr_ingest_var (byte-tiled K1v, 1-D bulk TMA)  ->  agr_complete for every forwarded request (K2)
+                    ->  agr_expire + agr_reclaim (TTL sweep, rows / bytes back to the ring);
+      every 25th    1 % of the agents CRASH for that batch: their container is dead while their status still says running, so
+                    the proxy forwards, the dial fails (AGR_OUT_DIAL_ERR, Q12) and the records stay pending; then they restart,
+                    one ReplayWorker tick (agr_replay_scan_var, K3) hands back their FULL pending queues, every record is
+                    re-injected replay-flagged (K1v: dedupe hit on the stored id) and completed TWICE (server side + worker
+                    side, Q7).
+    Shards are independent (agents steered to their owner): weak scaling, no data-path collective.  value = records / K1v kernel
+    time (there is no resident-input form of the variable-length ingest); e2e = records / wall time of the WHOLE loop."""
     import torch
     import agentainer_lab_b200 as A
     from agentainer_lab_b200 import constants as K
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    local_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
-    n, na, S, W = 1 << 18, 256, args.steps, args.warmup
+    n, na, W = 1 << 17, 256, max(3, args.warmup)
+    total_target = 100_000_000 if world == 8 else 3_000_000 * world
+    S = args.steps if args.steps != 200 else -(-total_target // (world * n))
+    R = 8 * n
+    TTLB = 4                                                           # a record lives four batches
     rng = np.random.default_rng(7 + rank)
-    eng = A.Engine(device=local_rank, slab_rows=(S + W) * n, max_agents=1024, max_batch=n, vslab_bytes=(S + W) * n * 1400,
-                   k1_variant=args.variant, flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_VARLEN | K.AGR_CFG_MINT_IDS | K.AGR_CFG_TIMING)
-    for k in range(na):
-        eng.set_agent_state(A.synth_agent_id(k), "running")
-    wall, total_bytes = [], 0
-    for s in range(W + S):
-        blob, offs, nbytes = make_var_blob(A, n, s * n, 5, na, 0, rng)
-        pin = eng.pinned(nbytes, np.uint8)
-        pin.array[:] = blob
-        if s == W:
-            eng.kernel_time()
-        t = time.perf_counter()
+    nanos0 = 1700000000000000000 + rank * 10_000_000_000
+    eng = A.Engine(device=local_rank, slab_rows=R, max_agents=1024, max_batch=n, vslab_bytes=R * 1500, k1_variant=args.variant, log_entries=4 * R,
+                   flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_VARLEN | K.AGR_CFG_MINT_IDS | K.AGR_CFG_TIMING | K.AGR_CFG_RING)
+    names = [A.synth_agent_id(k, agent_nanos0=nanos0) for k in range(na)]
+    eng.set_agent_states(names, ["running"] * na)
+    names_b = np.array([x.encode() for x in names], dtype="S32")
+    # four distinct pinned blobs, cycled; created_at (seq) is patched per use so the TTL clock keeps running
+    blobs = []
+    for q in range(4):
+        blob, offs, nbytes = make_var_blob(A, n, q * n, 5 + rank, na, nanos0, rng)
+        pin = eng.pinned(nbytes, np.uint8); pin.array[:] = blob
+        hdr_idx = (offs[:-1, None].astype(np.int64) + np.arange(96)[None, :]).ravel()
+        agents = blob[hdr_idx].reshape(n, 96)[:, 32:64].copy().view("S32").ravel()
+        blobs.append((pin, offs, nbytes, agents, offs[:-1].astype(np.int64) + 64))
+    seq_bytes = np.arange(8)
+    def patch_seq(pin, seq_off, first_seq):
+        v = (first_seq + np.arange(n, dtype=np.uint64)).view(np.uint8).reshape(n, 8)
+        pin.array[(seq_off[:, None] + seq_bytes[None, :]).ravel()] = v.ravel()
+    outs = eng.pinned(n, A.outcome_dtype)
+    stats = dict(records=0, bytes=0, dial=0, replayed=0, crash_cycles=0, completions=0)
+    wall = []
+    def step(b, timed):
+        pin, offs, nbytes, agents, seq_off = blobs[b % 4]
+        patch_seq(pin, seq_off, b * n)
+        crash = (b % 25 == 24)
+        dead = names_b[rng.choice(na, max(1, na // 100), replace=False)] if crash else None
+        t0 = time.perf_counter()
         v, ids, _ = eng.ingest_var(pin.array, offs)
-        dt = time.perf_counter() - t
-        pin.free()
+        o = outs.array
+        o["request_id"] = ids; o["agent_id"] = agents; o["http_status"] = 200; o["seq"] = b * n + n
+        o["kind"] = K.AGR_OUT_RESPONSE
+        n_dial = 0
+        if crash:
+            hit = np.isin(agents, dead)
+            o["kind"][hit] = K.AGR_OUT_DIAL_ERR                          # "dial tcp ... connection refused": stays pending (server.go:600-605)
+            n_dial = int(hit.sum())
+        eng.complete(o, want_results=False)
+        n_rep = 0
+        if crash:
+            # the agents are back: one tick replays their whole pending queues in arrival order
+            disp, rblob, roffs = eng.replay_scan_var(cap=1 << 16, blob_cap=1 << 27)
+            n_rep = len(disp)
+            assert n_rep == n_dial, (n_rep, n_dial)
+            if n_rep:
+                ro = roffs.astype(np.int64)
+                rb = np.ascontiguousarray(rblob)
+                fl = (ro[:-1, None] + 72 + np.arange(4)[None, :]).ravel()
+                flags = rb[fl].view(np.uint32) | 1                        # X-Agentainer-Replay: true
+                rb[fl] = flags.view(np.uint8)
+                rb[(ro[:-1, None] + 16 + np.arange(16)[None, :]).ravel()] = disp["request_id"].reshape(-1)   # X-Agentainer-Request-ID
+                rv, _, _ = eng.ingest_var(rb, ro.astype(np.uint32))
+                assert (rv["code"] == K.AGR_V_FORWARD).all() and ((rv["flags"] & K.AGR_VF_KNOWN) != 0).all()
+                ragents = rb[(ro[:-1, None] + 32 + np.arange(32)[None, :]).ravel()].reshape(n_rep, 32).copy().view("S32").ravel()
+                ro2 = np.zeros(2 * n_rep, dtype=A.outcome_dtype)          # interceptTransport's StoreResponse, then the worker's (Q7)
+                ro2["request_id"] = np.repeat(disp["request_id"], 2, axis=0); ro2["agent_id"] = np.repeat(ragents, 2)
+                ro2["kind"] = K.AGR_OUT_RESPONSE; ro2["http_status"] = 200; ro2["seq"] = b * n + n + 1
+                eng.complete(ro2, want_results=False)
+        eng.expire((b + 1) * n, TTLB * n, want_count=False)
+        eng.reclaim()
+        dt = time.perf_counter() - t0
         assert (v["code"] == K.AGR_V_FORWARD).all()
-        if s >= W:
-            wall.append(dt); total_bytes += nbytes
+        if timed:
+            wall.append(dt)
+            stats["records"] += n; stats["bytes"] += nbytes; stats["dial"] += n_dial; stats["replayed"] += n_rep
+            stats["crash_cycles"] += 1 if crash else 0; stats["completions"] += n - n_dial + 2 * n_rep
+    for b in range(W):
+        step(b, False)
+    eng.kernel_time()
+    st0 = eng.stats()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_all0 = time.perf_counter()
+    for b in range(W, W + S):
+        step(b, True)
+    torch.cuda.synchronize()
+    loop_s = time.perf_counter() - t_all0
+    if dist:
+        dist.barrier()
     k_ms, k_n = eng.kernel_time()
-    peak, peak_src = measured_peak()
-    alg = total_bytes + 8 * n * S
-    ach = alg / (k_ms * 1e-3) / 1e9
-    line = {"metric": METRIC.replace("512B", "128B-4KB"), "value": n * S / (k_ms * 1e-3), "unit": "requests/s", "n_gpus": 1, "steps": S, "warmup": W,
-            "ms_per_step": k_ms / max(1, k_n), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C5 shape: 256 Ki records per step, bodies log-uniform in [128 B, 4 KB], 256 agent ids, engine-minted ids",
-                       "records_per_step": n, "mean_record_bytes": total_bytes / (n * S), "l2": "each step reads a fresh ~330 MiB blob (> 126 MB L2)"},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "k1v_tile_index + k1_ingest_var", "kernel_ms": k_ms / max(1, k_n), "launches_timed": k_n,
-                         "algorithmic_bytes": "stored record length + 8 per record (SURVEY 8d)", "peak_source": peak_src},
-            "e2e": {"value": n * S / sum(wall), "unit": "requests/s", "h2d_bytes_per_step": total_bytes / S, "d2h_bytes_per_step": n * 24,
-                    "ms_per_step": 1e3 * sum(wall) / S, "api": "agr_ingest_var (pinned host blob + offsets in; verdicts + ids out)"},
-            "gpu_launches": S * 3}
-    print(json.dumps(line))
+    st = eng.stats()
+    # size-independent properties of the whole run: every fresh record stored, every replay a dedupe hit, every forwarded
+    # request completed exactly once (replayed ones twice more), nothing left pending, the ring never over-full
+    assert st["stored"] - st0["stored"] == stats["records"], (st, stats)
+    assert st["dedupe_hits"] - st0["dedupe_hits"] == stats["replayed"] and st["dial_errors"] - st0["dial_errors"] == stats["dial"], (st, stats)
+    assert st["completions"] - st0["completions"] == stats["completions"], (st, stats)
+    assert st["rows_used"] - st["rows_tail"] <= R
+    pend = sum(len(eng.list(a, K.AGR_LIST_PENDING, cap=1 << 16)) for a in names[:: max(1, na // 16)])
+    assert pend == 0, pend
     eng.close()
+    vals = torch.tensor([loop_s, k_ms, float(stats["records"]), float(stats["bytes"]), float(stats["replayed"]), float(stats["crash_cycles"])],
+                        dtype=torch.float64, device="cuda" if dist else "cpu")
+    mx = vals.clone(); sm = vals.clone(); per_gpu = [stats["records"]]
+    if dist:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(sm)
+        g = [None] * world
+        dist.all_gather_object(g, stats["records"]); per_gpu = g
+    if rank == 0:
+        loop_s, k_ms = float(mx[0]), float(mx[1])
+        recs, nbytes, replayed, cycles = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[5])
+        peak, peak_src = measured_peak()
+        alg = (nbytes + 8 * recs) / world                                # per GPU; the replayed records' re-reads are not counted
+        ach = alg / (k_ms * 1e-3) / 1e9
+        line = {"metric": METRIC.replace("512B", "128B-4KB"), "value": recs / (k_ms * 1e-3), "unit": "requests/s", "n_gpus": world, "steps": S, "warmup": W,
+                "ms_per_step": k_ms / max(1, S), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": f"C5: {world} x B200, {int(recs)} records sustained through a ring ({R} rows, {R * 1500 >> 20} MiB of bytes per GPU), bodies log-uniform in [128 B, 4 KB], every 25th batch 1% of the agents crash (dial errors -> pending) then restart + tick + full pending-queue replay",
+                           "records_per_step_per_gpu": n, "mean_record_bytes": nbytes / recs, "agents_per_gpu": na, "per_gpu_records": per_gpu,
+                           "parallelism": f"shard{world}: agents steered to their owner, no data-path collective" if world > 1 else "single",
+                           "l2": "each step reads a fresh ~170 MiB blob (> 126 MB L2)",
+                           "value_is": "records / K1v kernel time (CUDA events around the kernel, summed); e2e is the whole loop"},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "kernel": "k1v_tile_index + k1_ingest_var", "kernel_ms": k_ms / max(1, k_n), "launches_timed": k_n,
+                             "algorithmic_bytes": "stored record length + 8 per record (SURVEY 8d)", "peak_source": peak_src},
+                "e2e": {"value": recs / loop_s, "unit": "requests/s", "h2d_bytes_per_step": nbytes / world / S + n * 64, "d2h_bytes_per_step": n * 24,
+                        "ms_per_step": 1e3 * loop_s / S, "api": "agr_ingest_var + agr_complete + agr_expire + agr_reclaim every batch; agr_replay_scan_var + replay-flagged re-ingest + double completion on crash cycles",
+                        "host_cpus_local_to_gpu": local_cpus},
+                "crash_replay": {"cycles": int(cycles), "records_replayed": int(replayed), "agents_crashed_per_cycle": max(1, na // 100)},
+                "gpu_launches": int(S * 12)}
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
 
 
 def main():
@@ -814,9 +921,7 @@ def main():
         # the CPU path does the same per-record work whatever the GPU-side sharding: c4 / c5 are timed on their 512 B base stream
         return run_reference(args, WORKLOADS.get(args.workload, WORKLOADS["c2"]), rank, world)
     if args.workload == "c5":
-        if rank == 0:
-            run_varlen(args, rank, world, local_rank)
-        return
+        return run_c5(args, rank, world, local_rank)
     if args.workload == "c4":
         return run_c4(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
