@@ -219,3 +219,39 @@ def marshal_list(rs) -> bytes:
 def format_uuid(raw16: bytes) -> str:
     h = raw16.hex()
     return f"{h[0:8]}-{h[8:12]}-{h[12:16]}-{h[16:20]}-{h[20:32]}"
+
+
+def _parse_time(s: str) -> int:
+    """RFC 3339 (what time.Time.MarshalJSON writes) -> Unix nanoseconds; any numeric offset is accepted."""
+    import calendar
+    import re
+    m = re.fullmatch(r"(\d{4})-(\d{2})-(\d{2})T(\d{2}):(\d{2}):(\d{2})(?:\.(\d{1,9}))?(Z|[+-]\d{2}:\d{2})", s)
+    if not m:
+        raise ValueError(f"not an RFC 3339 time: {s!r}")
+    y, mo, d, h, mi, sec = (int(m.group(i)) for i in range(1, 7))
+    frac = int((m.group(7) or "0").ljust(9, "0"))
+    secs = calendar.timegm((y, mo, d, h, mi, sec, 0, 0, 0))
+    z = m.group(8)
+    if z != "Z":
+        off = (int(z[1:3]) * 60 + int(z[4:6])) * 60
+        secs -= off if z[0] == "+" else -off
+    return secs * 1_000_000_000 + frac
+
+
+def unmarshal_request(text: bytes) -> dict:
+    """json.Unmarshal of a stored record into the dict form marshal_request takes (used to check Redis values written by the
+    REFERENCE itself, tests/golden/from_reference: marshal_request(unmarshal_request(v)) == v pins the field order, the
+    escaping, base64, time and omitempty rules of this restatement to encoding/json's output)."""
+    import json as _json
+    d = _json.loads(text.decode("utf-8"))
+    body = None if d.get("body") is None else base64.b64decode(d["body"])
+    r = {"id": d["id"], "agent_id": d["agent_id"], "method": d["method"], "path": d["path"], "headers": d.get("headers"),
+         "body": body, "status": d["status"], "retry_count": d["retry_count"], "max_retries": d["max_retries"],
+         "created_at": _parse_time(d["created_at"]), "processed_at": None, "response": None, "error": d.get("error", "")}
+    if d.get("processed_at") is not None:
+        r["processed_at"] = _parse_time(d["processed_at"])
+    if d.get("response") is not None:
+        q = d["response"]
+        r["response"] = {"status_code": q["status_code"], "headers": q.get("headers"),
+                         "body": None if q.get("body") is None else base64.b64decode(q["body"]), "received_at": _parse_time(q["received_at"])}
+    return r

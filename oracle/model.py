@@ -433,6 +433,35 @@ class ReferencePath:
     def tick(self, backend_for, now: int, on_replay=None) -> List[Tuple[str, str]]:
         return self.worker.process_agents(backend_for, now, on_replay)
 
+    def manual_replay(self, agent_id: str, request_id: str, backend: Tuple, now: int) -> int:
+        """POST /agents/{id}/requests/{reqId}/replay — replayRequestHandler, internal/api/server.go:681-751.  Unlike the
+        worker it talks to the agent DIRECTLY (http://{id}:8000 + the stored path, prefix and all, Q3): no proxy, no
+        X-Agentainer-* headers, so ANY client error — a refused connection included — reaches MarkRequestFailed
+        (:728-733; through the proxy a dial error would not count, Q12).  Returns the status the caller of the
+        management API sees."""
+        key = f"agent:{agent_id}:requests:{request_id}"                          # :687
+        try:
+            self.redis.get(key)                                                 # :688 storage.Get
+        except RedisNil:
+            return 404                                                          # :689-692 "Request not found"
+        try:
+            agent_obj = self.agents.get_agent(agent_id)                         # :702
+        except KeyError:
+            return 404                                                          # :703-706 "Agent not found"
+        if agent_obj["status"] != AGENT_RUNNING:                                # :708
+            return 503                                                          # :709-711 "Agent is not running"
+        if backend[0] != BACKEND_RESPONSE:                                      # client.Do failed (:726)
+            try:
+                self.manager.mark_request_failed(agent_id, request_id, "transport error")   # :730
+            except KeyError:
+                pass
+            return 502                                                          # :731
+        try:
+            self.manager.store_response(agent_id, request_id, HttpResponse(backend[1], now=now))   # :739
+        except KeyError:
+            pass                                                                # :740-742 only warns
+        return 200                                                              # :744-751
+
     # ---- observables
     def lists(self, agent_id: str) -> Dict[str, List[str]]:
         return {q: self.redis.lrange_all(f"agent:{agent_id}:requests:{q}") for q in ("pending", "completed", "failed")}

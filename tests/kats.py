@@ -9,6 +9,9 @@ from scenario import Req, rid_of, ZERO16
 AGENT_A = "agent-1700000000000000001"
 AGENT_B = "agent-1700000000000000002"
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kats.json")
+# written by oracle/go/requests_kat_test.go from a run of the UNMODIFIED reference; preferred when present (parity "pinned")
+FROM_REFERENCE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "from_reference", "kats.json")
+PINNED = os.path.exists(FROM_REFERENCE)
 OK = ("response", 200)
 
 
@@ -56,6 +59,12 @@ SCENARIOS = {
                          ("req", R(2, agent=AGENT_B, replay=True, replay_of=rid_of(1)), OK)],
     # agent.Remove: lists deleted, record orphaned (Q17), later traffic 404
     "KAT-REMOVE": [("agent", AGENT_A, "stopped"), ("req", R(1), OK), ("remove", AGENT_A), ("req", R(2), OK)],
+    # POST /agents/{id}/requests/{reqId}/replay (server.go:681-751): direct call to the agent, ANY client error counts (Q12 note)
+    "KAT-MANUAL": [("agent", AGENT_A, "stopped"), ("req", R(1), OK), ("req", R(2), OK),
+                   ("manual", AGENT_A, rid_of(1), OK),
+                   ("agent", AGENT_A, "running"),
+                   ("manual", AGENT_A, rid_of(1), OK), ("manual", AGENT_A, rid_of(2), ("dial",)), ("manual", AGENT_A, rid_of(99), OK),
+                   ("tick", {}, None)],
     # FIFO across a failed-in-place entry: r1 errors (retry 1, keeps its position), r2 dial -> pending [r1, r2];
     # stop/start and tick: replay order r1 then r2
     "KAT-ORDER": [("agent", AGENT_A, "running"), ("req", R(1), ("error",)), ("req", R(2), ("dial",)),
@@ -63,9 +72,18 @@ SCENARIOS = {
 }
 
 
-def load_golden():
+def load_golden(path=None):
+    """Expected observables per scenario: the reference's own output when tests/golden/from_reference/kats.json exists
+    (PINNED), else the hand-derived tests/golden/kats.json."""
     with open(GOLDEN) as f:
         g = json.load(f)
+    if path is None and PINNED:
+        with open(FROM_REFERENCE) as f:
+            ref = json.load(f)
+        g = dict(g, kats=ref["kats"], _provenance=ref.get("_provenance", "reference run"))
+    elif path is not None:
+        with open(path) as f:
+            g = dict(g, kats=json.load(f)["kats"])
     sym = {f"r{i}": rid_of(i).hex() for i in range(1, 100)}
     names = {"A": AGENT_A, "B": AGENT_B}
 
@@ -79,5 +97,6 @@ def load_golden():
             "ticks": [[(ag(a), sym[r]) for a, r in t] for t in exp["ticks"]],
             "lists": {ag(a): {q: [sym[r] for r in ids] for q, ids in qs.items()} for a, qs in exp["lists"].items()},
             "records": {(ag(k.split("/")[0]), sym[k.split("/")[1]]): tuple(v) for k, v in exp["records"].items()},
+            "manual": list(exp.get("manual", [])),
         }
     return out, g

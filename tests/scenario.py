@@ -6,6 +6,8 @@ A scenario is a list of events in a total order (the order commands would reach 
   ("remove", agent_id)                         agent.Manager.Remove
   ("req",    Req, backend)                     one HTTP call to /agent/{id}/...; backend = what the agent side does
                                                if the proxy forwards it: ("response", code) | ("dial",) | ("error",)
+  ("manual", agent_id, rid, backend)           POST /agents/{id}/requests/{reqId}/replay (server.go:681-751): the agent is
+                                               called directly; backend as for "req" (every error kind counts as a failure)
   ("tick",   backends, flip)                   one ReplayWorker tick; backends maps request-id hex -> backend for
                                                that replay (default ("response", 200), also ("client",)); flip =
                                                None or (k, agent_id, status): status write right after the k-th
@@ -60,6 +62,7 @@ class Req:
 class Observed:
     verdicts: List[Tuple] = field(default_factory=list)        # per "req": (code, http, stored, tracked)
     ticks: List[List[Tuple[str, str]]] = field(default_factory=list)   # per tick: [(agent_id, id hex)] dispatch order
+    manual: List[int] = field(default_factory=list)            # per "manual": HTTP status of the management call
     lists: Dict[str, Dict[str, List[str]]] = field(default_factory=dict)   # agent -> pending/completed/failed id hex
     records: Dict[Tuple[str, str], Tuple] = field(default_factory=dict)   # (agent, id hex) -> (status, retry, resp)
 
@@ -116,6 +119,8 @@ def run_oracle(events, persistence: bool = True) -> Observed:
                     ref.set_agent(_f[1], _f[2])
 
             obs.ticks.append(ref.tick(backend_for, now=0, on_replay=on_replay))
+        elif e[0] == "manual":
+            obs.manual.append(ref.manual_replay(e[1], e[2].hex(), e[3], now=0))
         else:
             raise ValueError(e[0])
     for a in all_agents(events):
@@ -190,6 +195,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
     from agentainer_lab_b200 import constants as K
     obs = Observed()
     slot_name: Dict[int, str] = {}
+    agent_status: Dict[str, str] = {}                 # the Go side's own view (agentMgr.GetAgent), for the manual replay handler
     pend_reqs: List[Tuple[Req, Tuple]] = []
     # AGR_CFG_MINT_IDS: the engine mints the ids (like StoreRequest does); the scenario's symbolic ids are mapped to
     # them so that the oracle (which takes its ids from the stream) and the engine can be compared id for id
@@ -252,8 +258,31 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
         flush()
         if e[0] == "agent":
             slot_name[eng.set_agent_state(e[1], e[2])] = e[1]
+            agent_status[e[1]] = e[2]
         elif e[0] == "remove":
             eng.drop_agent(e[1])
+            agent_status.pop(e[1], None)
+        elif e[0] == "manual":
+            # what the Go handler does with the C-ABI: storage.Get -> agr_get_record, GetAgent stays Go (host-side status),
+            # client.Do stays Go, and the outcome goes through agr_complete: StoreResponse, or MarkRequestFailed for ANY error
+            agent_id, rid, backend = e[1], tin(e[2]), e[3]
+            known = (not mint) or (e[2] in s2e)
+            rec = None
+            if known:
+                rec = (eng.get_record_var(agent_id, rid) if varlen else eng.get_record(agent_id, rid))
+            if rec is None:
+                obs.manual.append(404)
+            elif agent_id not in agent_status:
+                obs.manual.append(404)
+            elif agent_status[agent_id] != "running":
+                obs.manual.append(503)
+            else:
+                outs = []
+                if backend[0] == "response":
+                    _outcome(outs, rid, agent_id, K.AGR_OUT_RESPONSE, backend[1]); obs.manual.append(200)
+                else:
+                    _outcome(outs, rid, agent_id, K.AGR_OUT_ERROR); obs.manual.append(502)
+                eng.complete(_outcomes_array(outs))
         elif e[0] == "tick":
             backends, flip = e[1], e[2]
             if varlen:
@@ -278,7 +307,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
                 cuts = [0, flip[0], len(recs)]
             for a, b in zip(cuts[:-1], cuts[1:]):
                 if a > 0 and flip is not None:
-                    eng.set_agent_state(flip[1], flip[2])
+                    eng.set_agent_state(flip[1], flip[2]); agent_status[flip[1]] = flip[2]
                 seg = np.ascontiguousarray(recs[a:b])
                 if len(seg) == 0:
                     continue
@@ -309,7 +338,7 @@ def run_engine(eng, events, max_batch: int = 1 << 30, rng=None) -> Observed:
                 if outs:
                     eng.complete(_outcomes_array(outs))
             if flip is not None and flip[0] >= len(recs):
-                eng.set_agent_state(flip[1], flip[2])
+                eng.set_agent_state(flip[1], flip[2]); agent_status[flip[1]] = flip[2]
         else:
             raise ValueError(e[0])
     flush()
@@ -332,6 +361,7 @@ def assert_same(o: Observed, g: Observed) -> None:
     assert o.verdicts == g.verdicts, _first_diff(o.verdicts, g.verdicts, "verdict")
     assert o.per_agent_ticks() == g.per_agent_ticks(), "replay dispatch order differs"
     assert o.ticks == g.ticks, "cross-agent dispatch order differs from the canonical (registration) order"
+    assert o.manual == g.manual, f"manual replay statuses differ: oracle {o.manual} != engine {g.manual}"
     assert o.lists == g.lists, _lists_diff(o.lists, g.lists)
     assert o.records == g.records, _first_diff(sorted(o.records.items()), sorted(g.records.items()), "record")
 
@@ -361,9 +391,10 @@ def rid_of(i: int) -> bytes:
     return bytes(b)
 
 
-def random_scenario(seed: int, n_events: int = 300, n_agents: int = 5, p_replay: float = 0.1) -> list:
+def random_scenario(seed: int, n_events: int = 300, n_agents: int = 5, p_replay: float = 0.1, p_manual: float = 0.0) -> list:
     """Mixed stream: status flips, fresh requests with all backend kinds, client-sent replay-flagged duplicates,
-    ticks with mixed replay outcomes and KAT-F style mid-tick flips."""
+    ticks with mixed replay outcomes and KAT-F style mid-tick flips; with p_manual > 0 also calls of the manual replay
+    handler (server.go:681-751) on known and unknown ids."""
     rng = np.random.default_rng(seed)
     agents = [f"agent-{1700000000000000000 + 1000003 * k}" for k in range(n_agents)]
     events: list = []
@@ -375,7 +406,13 @@ def random_scenario(seed: int, n_events: int = 300, n_agents: int = 5, p_replay:
     ctr = 0
     for _ in range(n_events):
         u = rng.random()
-        if u < 0.07:
+        if p_manual and rng.random() < p_manual:
+            a = agents[int(rng.integers(n_agents))]
+            w = rng.random()
+            target = fresh[a][int(rng.integers(len(fresh[a])))] if (fresh[a] and w < 0.85) else rid_of(20_000_000 + ctr)
+            v = rng.random()
+            events.append(("manual", a, target, ("response", int(rng.choice([200, 500]))) if v < 0.6 else (("dial",) if v < 0.8 else ("error",))))
+        elif u < 0.07:
             a = agents[int(rng.integers(n_agents))]
             status[a] = str(rng.choice(["running", "stopped", "paused", "failed", "created"], p=[0.5, 0.3, 0.1, 0.05, 0.05]))
             events.append(("agent", a, status[a]))

@@ -1,7 +1,7 @@
 """The oracle against the hand-derived known-answer traces.  CPU only."""
 import pytest
 
-from kats import SCENARIOS, load_golden, AGENT_A
+from kats import SCENARIOS, load_golden, AGENT_A, PINNED, GOLDEN, FROM_REFERENCE
 from scenario import run_oracle, rid_of, Req
 from oracle import model as M
 
@@ -14,9 +14,41 @@ def test_oracle_matches_golden(kat):
     exp = GOLD[kat]
     assert obs.verdicts == exp["verdicts"]
     assert obs.ticks == exp["ticks"]
+    assert obs.manual == exp["manual"]
     for a, qs in exp["lists"].items():
         assert obs.lists[a] == qs, (kat, a)
     assert obs.records == exp["records"]
+
+
+def test_parity_pin_status(capsys):
+    """Says which golden file the KAT tests ran against: the reference's own output (PINNED) or the hand derivation."""
+    with capsys.disabled():
+        print("\n[kats] " + ("PINNED: expected values are OUTPUT OF THE REFERENCE (tests/golden/from_reference/kats.json)" if PINNED else
+                            "parity UNPINNED: expected values are hand-derived (tests/golden/kats.json); run oracle/go/README.md to pin"))
+
+
+@pytest.mark.skipif(not PINNED, reason="no reference output (oracle/go/README.md)")
+def test_reference_output_agrees_with_the_hand_derivation():
+    ref, _ = load_golden()
+    hand, _ = load_golden(GOLDEN)
+    for kat in sorted(SCENARIOS):
+        for k in ("verdicts", "ticks", "lists", "records", "manual"):
+            assert ref[kat][k] == hand[kat][k], (kat, k)
+
+
+@pytest.mark.skipif(not PINNED, reason="no reference output (oracle/go/README.md)")
+def test_reference_stored_json():
+    """Every record's Redis value from the reference run is reproduced by oracle/gojson.py from its own parsed fields."""
+    import json
+    from oracle import gojson as G
+    raw = json.load(open(FROM_REFERENCE))["kats"]
+    n = 0
+    for kat, res in raw.items():
+        for key, text in res.get("stored_json", {}).items():
+            doc = G.unmarshal_request(text.encode())
+            assert G.marshal_request(doc) == text.encode(), (kat, key)
+            n += 1
+    assert n > 0
 
 
 def test_kat_a_redis_command_order():

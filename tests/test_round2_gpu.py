@@ -242,3 +242,17 @@ def test_single_request_front_end_under_threads(flags):
         out, ids = np.zeros(1, dtype=A.verdict_dtype), np.zeros((1, 16), dtype=np.uint8)
         eng.ingest_ex(make_records([Req(agents[1], rid_of(2 * 10 ** 6), 2 * 10 ** 6)]), out, ids)
         assert int(out[0]["code"]) == K.AGR_V_QUEUED
+
+
+@pytest.mark.parametrize("flags", [MINT, HASH, MINT | K.AGR_CFG_VARLEN])
+def test_random_streams_with_the_manual_replay_handler(flags):
+    """Random event streams that also call POST /agents/{id}/requests/{reqId}/replay (server.go:681-751: the agent is called
+    directly, every client error reaches MarkRequestFailed, misses answer 404 / 503 without touching anything)."""
+    from scenario import run_oracle, run_engine, assert_same, random_scenario
+    for seed in (21, 22, 23):
+        ev = random_scenario(seed, n_events=400, n_agents=4, p_manual=0.08)
+        assert sum(1 for e in ev if e[0] == "manual") > 10
+        with A.Engine(slab_rows=1 << 12, max_agents=16, flags=flags) as eng:
+            o, g = run_oracle(ev), run_engine(eng, ev)
+            assert_same(o, g)
+            assert {200, 502} <= set(o.manual) and (404 in o.manual or 503 in o.manual)
