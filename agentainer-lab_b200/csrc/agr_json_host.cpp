@@ -71,23 +71,27 @@ bool read_string(reader& r, std::string& out) {
     }
     return false;
 }
-bool skip_value(reader& r);
-bool skip_container(reader& r, char open, char close) {
+// encoding/json refuses documents nested deeper than 10000 ("exceeded max depth"); unknown members are skipped recursively, so
+// the same limit keeps a hostile document from overflowing the host stack
+#define JSON_MAX_DEPTH 10000
+bool skip_value(reader& r, int depth);
+bool skip_container(reader& r, char open, char close, int depth) {
+    if (depth > JSON_MAX_DEPTH) return false;
     if (!r.eat(open)) return false;
     if (r.eat(close)) return true;
     for (;;) {
         if (open == '{') { std::string k; if (!read_string(r, k) || !r.eat(':')) return false; }
-        if (!skip_value(r)) return false;
+        if (!skip_value(r, depth)) return false;
         if (r.eat(',')) continue;
         return r.eat(close);
     }
 }
-bool skip_value(reader& r) {
+bool skip_value(reader& r, int depth = 0) {
     r.ws();
     if (r.p >= r.e) return false;
     if (*r.p == '"') { std::string s; return read_string(r, s); }
-    if (*r.p == '{') return skip_container(r, '{', '}');
-    if (*r.p == '[') return skip_container(r, '[', ']');
+    if (*r.p == '{') return skip_container(r, '{', '}', depth + 1);
+    if (*r.p == '[') return skip_container(r, '[', ']', depth + 1);
     if (r.lit("null") || r.lit("true") || r.lit("false")) return true;
     const uint8_t* s = r.p;
     while (r.p < r.e && (*r.p == '-' || *r.p == '+' || *r.p == '.' || *r.p == 'e' || *r.p == 'E' || (*r.p >= '0' && *r.p <= '9'))) ++r.p;
@@ -109,6 +113,9 @@ bool read_headers(reader& r, std::string& flat) {
         for (;;) {
             std::string k, v;
             if (!read_string(r, k) || !r.eat(':') || !read_string(r, v)) return false;
+            // the flattened form frames a header as "Key: Value\n": a line feed in either part, or a colon in the key, cannot be
+            // represented (net/http never produces such a header; a document that holds one is refused, not mangled)
+            if (k.find('\n') != std::string::npos || v.find('\n') != std::string::npos || k.find(':') != std::string::npos) return false;
             bool dup = false;
             for (auto& e : kv) if (e.first == k) { e.second = v; dup = true; }   // the last duplicate wins, like a Go map
             if (!dup) kv.emplace_back(std::move(k), std::move(v));

@@ -1,5 +1,7 @@
 // requests.cpp — see requests.hpp.  Thin: every state change is a C-ABI call; nothing is decided on the host.
 #include "requests.hpp"
+#include <mutex>
+#include <stdexcept>
 #include <algorithm>
 
 #include <chrono>
@@ -87,6 +89,27 @@ void Manager::FromRecord(const agr_record& r, Request* out) {
     out->RetryCount = r.retry_count; out->MaxRetries = r.max_retries; out->CreatedAt = r.seq;
     out->ResponseStatus = r.resp_status;
     out->Error = r.error_code ? "transport error" : "";
+}
+
+// one shared handle per process (a14): the first Manager registers its handle, later ones must bring the same
+static std::mutex g_handle_mu;
+static agr_handle* g_process_handle = nullptr;
+static int g_managers = 0;
+Manager::Manager(agr_handle* h, bool engine_mints_ids) : h_(h), mint_(engine_mints_ids) {
+    std::lock_guard<std::mutex> lk(g_handle_mu);
+    if (g_managers > 0 && g_process_handle != h)
+        throw std::logic_error("requests.Manager: a second engine handle in one process — the server's and the replay worker's "
+                               "managers must share ONE handle (server.go:62, main.go:335)");
+    g_process_handle = h;
+    g_managers++;
+}
+Manager::~Manager() {
+    std::lock_guard<std::mutex> lk(g_handle_mu);
+    if (--g_managers == 0) g_process_handle = nullptr;
+}
+agr_handle* Manager::ProcessHandle() {
+    std::lock_guard<std::mutex> lk(g_handle_mu);
+    return g_process_handle;
 }
 
 Error Manager::Decide(const std::string& agentID, const HttpRequest& req, Verdict* out) {

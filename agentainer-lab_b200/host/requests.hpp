@@ -61,7 +61,11 @@ class Manager {
   public:
     // NewManager (requests.go:57).  engine_mints_ids: the handle was created with AGR_CFG_MINT_IDS, so Request.ID is what
     // the engine minted (read back through agr_ingest_ex), exactly as StoreRequest returns storedReq.ID (server.go:515).
-    explicit Manager(agr_handle* h, bool engine_mints_ids = false) : h_(h), mint_(engine_mints_ids) {}
+    // The reference builds TWO managers (api.NewServer, server.go:62, and runServer, main.go:335): harmless there, both are
+    // stateless wrappers of one Redis.  Here the state lives behind the handle, so every Manager of a process MUST wrap the
+    // same handle: the constructor throws std::logic_error when a second, different handle shows up.
+    explicit Manager(agr_handle* h, bool engine_mints_ids = false);
+    ~Manager();
     // proxyToAgentHandler's decision (server.go:493-541): agent lookup, replay-flag dedupe, StoreRequest, status gate.
     Error Decide(const std::string& agentID, const HttpRequest& req, Verdict* out);
     // StoreRequest (requests.go:64-117).  Persists and appends to the pending queue regardless of the agent's status.
@@ -83,6 +87,7 @@ class Manager {
     // interceptTransport.RoundTrip's classification (server.go:597-611): dial errors leave the record pending
     Error RecordTransportError(const std::string& agentID, const std::string& requestID, const std::string& err);
     agr_handle* handle() const { return h_; }
+    static agr_handle* ProcessHandle();          // the handle every live Manager of this process wraps (nullptr: none yet)
     static void ToRecord(const std::string& agentID, const HttpRequest& req, const uint8_t id[16], bool replay,
                          const uint8_t replay_of[16], uint64_t seq, agr_record* rec);
     static void FromRecord(const agr_record& rec, Request* out);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -28,6 +29,13 @@ static int run(bool mint, bool combine) {
     agr_handle* h = nullptr;
     if (agr_create(&cfg, &h) < 0) { printf("agr_create: %s\n", agr_last_error()); return 2; }
     Manager mgr(h, mint);
+    {   // a14: the reference's second manager (main.go:335) wraps the SAME handle; a different one is a wiring bug
+        Manager second(h, mint);
+        CHECK(Manager::ProcessHandle() == h);
+        bool threw = false;
+        try { Manager wrong(reinterpret_cast<agr_handle*>(&cfg), mint); } catch (const std::logic_error&) { threw = true; }
+        CHECK(threw);
+    }
     const char* A = "agent-1700000000000000001";
     HttpRequest post; post.Method = "POST"; post.Path = std::string("/agent/") + A + "/chat";
     post.Header["Content-Type"] = "application/json"; post.Body = {'{', '}'};

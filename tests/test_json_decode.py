@@ -156,3 +156,21 @@ def test_decoder_on_the_hand_derived_kats():
             assert d["resp_headers"] == "".join(f"{a}: {b}\n" for a, b in sorted(r["headers"].items())).encode()
         else:
             assert not info.has_response
+
+
+def test_decoder_refuses_what_it_cannot_represent():
+    """Hostile or unrepresentable documents: nesting deeper than encoding/json's 10000 levels in a skipped member (the reader
+    recurses there: without a limit a few hundred thousand brackets overflow the host stack), and header keys / values that
+    would break the flattened "Key: Value\\n" framing.  All of them are AGR_EINVAL, none of them crashes."""
+    base = ('{"id":"00000000-0000-4000-8000-000000000001","agent_id":"agent-1","method":"POST","path":"/agent/agent-1/x",'
+            '"headers":%s,"body":"aGk=","status":"pending","retry_count":0,"max_retries":3,"created_at":"2023-11-14T22:13:20Z"%s}')
+    ok = base % ('{"A":"b"}', "")
+    assert A.json_decode(ok.encode())[0] == 0
+    deep_ok = base % ('{"A":"b"}', ',"x":' + "[" * 5000 + "]" * 5000)
+    assert A.json_decode(deep_ok.encode())[0] == 0                                   # encoding/json accepts this depth too
+    deep = base % ('{"A":"b"}', ',"x":' + "[" * 400000 + "]" * 400000)
+    assert A.json_decode(deep.encode())[0] == K.AGR_EINVAL
+    deep_obj = base % ('{"A":"b"}', ',"x":' + '{"a":' * 300000 + "1" + "}" * 300000)
+    assert A.json_decode(deep_obj.encode())[0] == K.AGR_EINVAL
+    for hdr in ('{"A\\nB":"v"}', '{"A":"v\\nX: y"}', '{"A:B":"v"}'):
+        assert A.json_decode((base % (hdr, "")).encode())[0] == K.AGR_EINVAL, hdr
