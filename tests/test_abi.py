@@ -125,4 +125,4 @@ def test_integration_text_only_names_what_the_header_declares():
     for name in set(re.findall(r"\bC\.(AGR_[A-Z0-9_]+)\b", text)):
         assert re.search(rf"\b{name}\b", body), name
     for st in set(re.findall(r"\bC\.(agr_[a-z_]+)\{", text)) | set(re.findall(r"var \w+ C\.(agr_[a-z_]+)\b", text)):
-        assert re.search(rf"typedef struct {st}\b", body), st
+        assert re.search(rf"typedef (struct {st}\b|\w+ {st};)", body), st
