@@ -86,6 +86,7 @@ __device__ __forceinline__ uint32_t lookup_rid(const agr_dev& d, unsigned long l
 }
 
 // ------------------------------------------------------------------------------------------------ K1
+#define K1_NLC 10  // counters C_INGESTED .. C_BAD_LEN are contiguous from 0; lc[K1_NLC] counts rows left to the post pass
 // Decision + persistence for ONE record whose 96 B header is in registers: the sequential semantics of
 // proxyToAgentHandler (server.go:498-541) with StoreRequest (requests.go:64-117) inlined, split in stages so a
 // kernel can put independent work (the record checksum) between the long-latency global operations:
@@ -102,6 +103,8 @@ struct k1_ctx {
     u128 old;
     uint32_t slot, astatus;
     bool replay, want_store, cas_issued, deferred, bad, hole;
+    uint32_t known;            // replay-flagged + tracked: 0 n/a, 1 target row's words are in o_route / o_state, 2 resolve in the post pass,
+    uint32_t o_route, o_state; //                           3 the id names no live row (cannot be a dedupe hit)
 };
 
 __device__ __forceinline__ ag_probe agent_probe_load(const agr_dev& d, uint32_t idx) {
@@ -127,8 +130,13 @@ __device__ __forceinline__ void agent_resolve(const agr_dev& d, ag_probe p, cons
 
 // body_len = the record's body_len field, payload_cap = the payload bytes the record form can hold (416 for the fixed
 // stride, stored length - 96 for a variable-length record): a record whose lengths do not fit is never persisted.
-__device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, const uint4& h0, const uint4& h2, const uint4& h3,
-                                         const uint4& h4, const uint32_t body_len, const uint32_t payload_cap, k1_ctx& c) {
+// first_log: arrival number of the batch's first row, or 0.  With engine-minted ids the row a replay-flagged request names is a
+// pure function of the id; if it arrived BEFORE this batch its words are final, so the dedupe hit (AGR_VF_KNOWN) is decided
+// right here (two 4-byte loads in flight behind the tile's checksum) and only requests naming a row of the SAME batch — or, with
+// first_log == 0 / caller-supplied ids, every tracked replay — are left to the post pass.
+__device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, const uint4& h0, const uint4& h1, const uint4& h2, const uint4& h3,
+                                         const uint4& h4, const uint32_t body_len, const uint32_t payload_cap, const unsigned long long first_log,
+                                         k1_ctx& c) {
     c.id_lo = pack64(h0.x, h0.y); c.id_hi = pack64(h0.z, h0.w);
     c.replay = (h4.z & AGR_F_REPLAY) != 0;                                                // server.go:506
     c.hole = (d.cfg_flags & AGR_CFGI_HOLES) && (h4.z & AGR_FI_HOLE);                       // row emptied by the exchange (K4)
@@ -142,6 +150,15 @@ __device__ __forceinline__ void k1_begin(const agr_dev& d, const ag_probe& ap, c
     c.cas_issued = c.want_store && !c.bad && (c.id_lo | c.id_hi) != 0ULL && !c.deferred && !(d.cfg_flags & AGR_CFG_DIAG_NO_INDEX);
     c.old = 0;
     c.tidx = 0;
+    c.known = 0u; c.o_route = 0u; c.o_state = 0u;
+    if (c.replay && found && (h1.x | h1.y | h1.z | h1.w) != 0u) {
+        c.known = 2u;
+        if ((d.cfg_flags & AGR_CFG_MINT_IDS) && first_log) {
+            const uint32_t orid = lookup_rid(d, pack64(h1.x, h1.y), pack64(h1.z, h1.w));
+            if (orid == AGR_RID_NONE) c.known = 3u;
+            else if (row_logical(d, orid) < first_log) { c.o_route = __ldcg(&d.route[orid]); c.o_state = __ldcg(&d.state[orid]); c.known = 1u; }
+        }
+    }
     if (c.cas_issued) {
         c.tidx = agr_hash_id(c.id_lo, c.id_hi) & d.table_mask;
         c.old = cas128(&d.table[c.tidx], 0, make_u128(c.id_lo, c.id_hi));
@@ -195,7 +212,15 @@ __device__ __forceinline__ k1_result k1_finish(const agr_dev& d, uint32_t rid, c
         vflags |= AGR_VF_REPLAY;
         lc[C_REPLAY]++;
         tracked = (h1.x | h1.y | h1.z | h1.w) != 0u;
-        if (tracked) vflags |= AGR_VF_TRACKED;
+        if (tracked) {
+            vflags |= AGR_VF_TRACKED;
+            if (c.known == 1u) {                                                          // dedupe hit decided here (see k1_begin)
+                if (rt_slot(c.o_route) == c.slot && (c.o_state & ST_STORED)) { vflags |= AGR_VF_KNOWN; lc[C_DEDUPE_HITS]++; }
+            } else if (c.known == 2u) {
+                vflags |= AGR_VF_DUP_ID;                                                  // marker "resolve me in the post pass" (never
+                lc[K1_NLC]++;                                                             // a real flag of a replay-flagged row)
+            }
+        }
     }
     uint32_t code;
     if (c.astatus != AGR_AGENT_RUNNING) {                                                 // server.go:525
@@ -224,7 +249,6 @@ __device__ __forceinline__ void k1_note_time(const agr_dev& d, const uint32_t fi
     }
 }
 
-#define K1_NLC 10  // counters C_INGESTED .. C_BAD_LEN are contiguous from 0
 
 __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc, uint32_t* s_ctr) {
     const int lane = threadIdx.x & 31;
@@ -233,10 +257,12 @@ __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc
         uint32_t v = __reduce_add_sync(FULL, lc[c]);
         if (lane == 0 && v) atomicAdd(&s_ctr[c], v);
     }
+    {   // per-batch note for k1_post: how many replay-flagged rows wait for its "stored earlier?" pass
+        const uint32_t v = __reduce_add_sync(FULL, lc[K1_NLC]);
+        if (lane == 0 && v) atomicAdd(d.dupfix + 2, v);
+    }
     __syncthreads();
     if (threadIdx.x < K1_NLC && s_ctr[threadIdx.x]) atomicAdd(&d.ctr[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
-    // per-batch note for k1_post: replay-flagged records need its "stored earlier?" pass
-    if (threadIdx.x == C_REPLAY && s_ctr[C_REPLAY]) atomicAdd(d.dupfix + 2, s_ctr[C_REPLAY]);
 }
 
 
@@ -251,17 +277,19 @@ __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc
 __device__ __forceinline__ uint32_t k1_post_one(const agr_dev& d, const uint32_t rid, const uint32_t dupfix, int* delta) {
     uint32_t r = d.route[rid];
     uint32_t vf = rt_flags(r);
-    if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_TRACKED)) {
-        const uint4 t = ldg_nc_v4(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF);
+    if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_DUP_ID)) {              // a tracked replay K1 left for this pass (k1_finish's marker)
+        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF));
         const uint32_t orid = lookup_rid(d, pack64(t.x, t.y), pack64(t.z, t.w));
+        vf &= ~AGR_VF_DUP_ID;
         if (orid != AGR_RID_NONE && row_logical(d, orid) < row_logical(d, rid) && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
-            r |= (AGR_VF_KNOWN << RT_FLAG_SHIFT);
-            d.route[rid] = r;
+            vf |= AGR_VF_KNOWN;
             delta[0]++;
         }
+        r = (r & ((1u << RT_FLAG_SHIFT) - 1u)) | (vf << RT_FLAG_SHIFT);
+        d.route[rid] = r;
     }
     if (dupfix != 0u && (vf & (AGR_VF_STORED | AGR_VF_DUP_ID))) {
-        const uint4 h0 = ldg_nc_v4(rec_ptr(d, rid));
+        const uint4 h0 = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid)));
         const unsigned long long idx = table_find(d, pack64(h0.x, h0.y), pack64(h0.z, h0.w));
         const uint32_t owner = (idx == ~0ULL) ? AGR_RID_NONE : idx_decode(d, __ldcg(&d.table[idx].inv_rid));
         uint32_t code = rt_code(r);
@@ -272,7 +300,7 @@ __device__ __forceinline__ uint32_t k1_post_one(const agr_dev& d, const uint32_t
             d.state[rid] = 0;
             delta[1]--;
         } else if ((vf & AGR_VF_DUP_ID) && owner == rid && (pack64(h0.x, h0.y) | pack64(h0.z, h0.w)) != 0ULL) {   // promote
-            const uint4 h5 = ldg_nc_v4(rec_ptr(d, rid) + 80);
+            const uint4 h5 = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid) + 80));
             uint32_t maxr = (h5.y >> 16) & 0xffu;
             if (maxr == 0) maxr = 3;
             uint32_t st = AGR_ST_PENDING | ST_INQ | ST_STORED | (maxr << ST_MAX_SHIFT);
@@ -300,7 +328,7 @@ __device__ __forceinline__ uint4 k1_request_id(const agr_dev& d, const uint32_t 
         agr_mint_id(row_logical(d, rid), d.shard_id, d.id_gen, d.id_secret, lo, hi);
         return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
     }
-    return ldg_nc_v4(rec_ptr(d, rid));
+    return __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid)));
 }
 __device__ __forceinline__ void k1_post_flush(const agr_dev& d, int* delta, const int lane) {
     const int hits = __reduce_add_sync(FULL, delta[0]), stored = __reduce_add_sync(FULL, delta[1]), q = __reduce_add_sync(FULL, delta[2]);

@@ -61,10 +61,12 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    uint32_t lc[K1_NLC];
+    uint32_t lc[K1_NLC + 1];
 #pragma unroll
-    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
     const uint32_t tiles = (n + TILE_RECS - 1) / TILE_RECS;
+    const unsigned long long first_log = row_logical(d, first_rid);          // arrival number of the batch's first row (never 0 is not
+    (void)0;                                                                  // required: 0 only means "decide nothing in the kernel")
     const uint32_t my_smem = smem_base + (uint32_t)warp * STAGES * TILE_BYTES;
     const uint32_t my_bar = smem_u32(&bars[warp * STAGES]);
 
@@ -156,7 +158,7 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         }
         // this tile: agent loads have landed by now; classify and put the index CAS in flight.  pcx is dead here
         // (just consumed), so the CAS writes straight into the loop-carried registers.
-        if (valid) k1_begin(d, ap, h0, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, pcx);
+        if (valid) k1_begin(d, ap, h0, h1, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, first_log, pcx);
         ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid;
         if (s == STAGES - 1) phase ^= 1u;
     }

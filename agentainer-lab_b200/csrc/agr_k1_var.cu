@@ -62,9 +62,9 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
     if (threadIdx.x < WARPS) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(v_smem_u32(&bars[threadIdx.x])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    uint32_t lc[K1_NLC];
+    uint32_t lc[K1_NLC + 1];
 #pragma unroll
-    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
     const uint32_t stage = smem_base + (uint32_t)warp * VT_STAGE;
     const uint32_t bar = v_smem_u32(&bars[warp]);
     const uint32_t tstride = gridDim.x * WARPS;
@@ -159,7 +159,7 @@ k1_ingest_var(const agr_dev d, const uint8_t* __restrict__ blob, const uint32_t*
         auto decide = [&](uint32_t r, const uint4& h0, const uint4& h1, const uint4& h2, const uint4& h3, const uint4& h4, const uint4& h5) {
             const uint32_t rid = first_rid + a + r;
             k1_ctx cx;
-            k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, cx);
+            k1_begin(d, k1_agent_issue(d, h2, h3), h0, h1, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, 0ULL, cx);
             const k1_result res = k1_finish(d, rid, h1, h5, cx, lc);
             k1v_note_time(d, rid, res.state, h4);
             d.state[rid] = res.state;
@@ -207,9 +207,9 @@ k1_ingest_var_lsu(const agr_dev d, const uint8_t* __restrict__ blob, const uint3
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
     __syncthreads();
-    uint32_t lc[K1_NLC];
+    uint32_t lc[K1_NLC + 1];
 #pragma unroll
-    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
     const uint32_t tstride = gridDim.x * VL_WARPS;
     const uint32_t below = (1u << lane) - 1u;
     uint32_t* so = s_off[warp];
@@ -289,7 +289,7 @@ k1_ingest_var_lsu(const agr_dev d, const uint8_t* __restrict__ blob, const uint3
                             h4 = ldg_nc_v4(gp + 64), h5 = ldg_nc_v4(gp + 80);
                 const uint32_t rid = first_rid + a + r;
                 k1_ctx cx;
-                k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, cx);
+                k1_begin(d, k1_agent_issue(d, h2, h3), h0, h1, h2, h3, h4, h5.x, (so[r + 1] - so[r]) - AGR_OFF_PAYLOAD, 0ULL, cx);
                 const k1_result res = k1_finish(d, rid, h1, h5, cx, lc);
                 k1v_note_time(d, rid, res.state, h4);
                 d.state[rid] = res.state;

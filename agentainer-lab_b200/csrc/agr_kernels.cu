@@ -20,9 +20,9 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
     if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t lc[K1_NLC];
+    uint32_t lc[K1_NLC + 1];
 #pragma unroll
-    for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+    for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
     const uint32_t tiles = (n + 31u) >> 5;
     for (uint32_t tile = blockIdx.x * WARPS + warp; tile < tiles; tile += gridDim.x * WARPS) {
         const uint32_t i = tile * 32u + lane;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
         // ---- long-latency chain first: agent probe -> classification -> first index CAS in flight
         const ag_probe ap = k1_agent_issue(d, h2, h3);
         k1_ctx cx;
-        if (valid) k1_begin(d, ap, h0, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, cx);
+        if (valid) k1_begin(d, ap, h0, h1, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, 0ULL, cx);
         // ---- pass 2 (pure streaming, independent of the decision chain): payload checksum
         uint32_t c0 = 0, c1 = 0;
         {

@@ -158,15 +158,15 @@ k_svc(const agr_dev d0, const svc_dev v, const agr_k2_scratch k2, unsigned long 
             if (lane == 0) d.cksum[rid] = agr_cksum_pack(c0, c1);
         }
         // ------------------------------------------------------------------ records: decision chain, one record per thread
-        uint32_t lc[K1_NLC];
+        uint32_t lc[K1_NLC + 1];
 #pragma unroll
-        for (int c = 0; c < K1_NLC; ++c) lc[c] = 0;
+        for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
         if (tid < nrec) {
             const uint8_t* hp = s_rec + (size_t)tid * 512u;
             const uint4 h0 = lds_v4(hp), h1 = lds_v4(hp + 16), h2 = lds_v4(hp + 32), h3 = lds_v4(hp + 48), h4 = lds_v4(hp + 64), h5 = lds_v4(hp + 80);
             const uint32_t rid = D.first_p + tid;
             k1_ctx cx;
-            k1_begin(d, k1_agent_issue(d, h2, h3), h0, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, cx);
+            k1_begin(d, k1_agent_issue(d, h2, h3), h0, h1, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, 0ULL, cx);
             const k1_result r = k1_finish(d, rid, h1, h5, cx, lc);
             d.state[rid] = r.state;
             d.route[rid] = r.route;
