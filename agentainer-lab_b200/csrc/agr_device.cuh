@@ -238,6 +238,9 @@ __device__ __forceinline__ k1_result k1_finish(const agr_dev& d, uint32_t rid, c
 // lowers the time bound of the chunk(s) the tile's rows [first, first + count) lie in (k_expire reads them).  One or two
 // atomics per 32 records.
 __device__ __forceinline__ void k1_note_time(const agr_dev& d, const uint32_t first, const uint32_t count, const unsigned long long mine) {
+    // a ring runs for ever and sweeps every step: K1 keeps the bounds.  An append-only slab is swept rarely: agr_expire resets
+    // the bounds of the chunks filled since its last call instead (sweep_invalidate), and K1 spends nothing on it.
+    if (!(d.cfg_flags & AGR_CFG_RING)) return;
     const uint32_t hi = (uint32_t)(mine >> 32), hmin = __reduce_min_sync(FULL, hi);
     const uint32_t lmin = __reduce_min_sync(FULL, hi == hmin ? (uint32_t)mine : 0xffffffffu);
     if ((threadIdx.x & 31) == 0 && count) {
@@ -470,8 +473,8 @@ __device__ __forceinline__ void k2_apply_one(const agr_dev& d, const agr_k2_scra
     if (r.written) {
         d.mtime[rid] = r.mtime;
         unsigned long long* cm = d.cmin + rid / AGR_CHUNK_ROWS;             // the TTL sweep's bound must stay a lower bound
-        const unsigned long long cur = __ldcg(cm);
-        if (cur != 0ULL && r.mtime < cur) atomicMin(cm, r.mtime ? r.mtime : 1ULL);
+        const unsigned long long cur = __ldcg(cm), t = r.mtime ? r.mtime : 1ULL;
+        if (cur != 0ULL && t < cur) atomicMin(cm, t);
     }
     d.head[rid] = 0;
 }

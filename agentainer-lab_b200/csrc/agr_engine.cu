@@ -69,6 +69,7 @@ struct agr_handle {
     uint64_t released_total = 0;
     uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
+    uint64_t sweep_clean = 0; // append-only slab: rows below were ingested when agr_expire last ran (their chunks' time bounds are exact)
     // host agent map + mirror
     std::unordered_map<std::string, uint32_t> slot_of;
     std::vector<std::string> agent_names;
@@ -705,6 +706,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &d.failed_log, c.log_entries, false));
     TRY(dev_alloc(h, &d.log_len, (size_t)2, true));
     d.log_cap = c.log_entries;
+    TRY(dev_alloc(h, &d.marks, (size_t)(2 * (size_t)c.max_batch / 32 + 8), true));   // (2 x max_batch: the exchange runs K1 over own + received rows)
     TRY(dev_alloc(h, &d.dupfix, (size_t)8, true));
     h->dupfix_base = d.dupfix; d.dupfix_next = d.dupfix + 4;
     if (c.flags & AGR_CFG_RING) {
@@ -1838,6 +1840,13 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
     sync_window(h);
+    if (!is_ring(h) && h->rows_used > h->sweep_clean) {
+        // append-only slab: K1 does not keep the chunks' time bounds (k1_note_time); the chunks that received rows since the last
+        // sweep are marked "unknown" here and get their exact bound back from this sweep
+        const uint64_t c0 = h->sweep_clean / AGR_CHUNK_ROWS, c1 = (h->rows_used - 1) / AGR_CHUNK_ROWS;
+        CK(cudaMemsetAsync(h->d.cmin + c0, 0, (size_t)(c1 - c0 + 1) * 8, h->stream));
+        h->sweep_clean = ingested_bound(h);
+    }
     agr_launch_expire(h->d, rows_span(h), now, ttl, d_cnt, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());

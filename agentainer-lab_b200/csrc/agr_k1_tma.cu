@@ -65,8 +65,6 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
 #pragma unroll
     for (int c = 0; c <= K1_NLC; ++c) lc[c] = 0;
     const uint32_t tiles = (n + TILE_RECS - 1) / TILE_RECS;
-    const unsigned long long first_log = row_logical(d, first_rid);          // arrival number of the batch's first row (never 0 is not
-    (void)0;                                                                  // required: 0 only means "decide nothing in the kernel")
     const uint32_t my_smem = smem_base + (uint32_t)warp * STAGES * TILE_BYTES;
     const uint32_t my_bar = smem_u32(&bars[warp * STAGES]);
 
@@ -98,7 +96,7 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     uint32_t phase = 0;
     // software pipeline across tiles: the index CAS of tile t is issued in the middle of tile t and consumed in the
     // middle of tile t+1 (k1_finish), so its whole round trip hides behind a tile of checksum work
-    k1_ctx pcx; uint4 ph1 = make_uint4(0, 0, 0, 0); uint32_t ph5y = 0, prid = 0; bool pvalid = false;
+    k1_ctx pcx; uint4 ph1 = make_uint4(0, 0, 0, 0); uint32_t ph5y = 0, prid = 0, ptile = 0; bool pvalid = false;
     for (uint32_t it = 0;; ++it) {
         const int s = (STAGES == 1) ? 0 : (int)(it % STAGES);
         uint32_t tile;
@@ -150,23 +148,34 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
         k1_note_time(d, first_rid + tile * TILE_RECS, min(TILE_RECS, n - tile * TILE_RECS), valid ? pack64(h4.x, h4.y) : ~0ULL);
         // previous tile: its CAS has had a full tile to come back
-        if (pvalid) {
-            const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
-            const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
-            d.state[prid] = r.state;
-            d.route[prid] = r.route;
+        if (it) {                                                 // (warp-uniform: every lane has a previous tile or none has)
+            k1_result r{0u, 0u};
+            if (pvalid) {
+                const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
+                r = k1_finish(d, prid, ph1, qh5, pcx, lc);
+                d.state[prid] = r.state;
+                d.route[prid] = r.route;
+            }
+            // one bit per row the post pass has to visit (tracked replays): it then reads 4 B per 32 rows instead of every route word
+            const uint32_t mk = __ballot_sync(FULL, pvalid && (rt_flags(r.route) & (AGR_VF_REPLAY | AGR_VF_DUP_ID)) == (AGR_VF_REPLAY | AGR_VF_DUP_ID));
+            if (lane == 0 && d.marks) d.marks[ptile] = mk;
         }
         // this tile: agent loads have landed by now; classify and put the index CAS in flight.  pcx is dead here
         // (just consumed), so the CAS writes straight into the loop-carried registers.
-        if (valid) k1_begin(d, ap, h0, h1, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, first_log, pcx);
-        ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid;
+        if (valid) k1_begin(d, ap, h0, h1, h2, h3, h4, h5.x, AGR_REC - AGR_OFF_PAYLOAD, 0ULL, pcx);
+        ph1 = h1; ph5y = h5.y; prid = rid; pvalid = valid; ptile = tile;
         if (s == STAGES - 1) phase ^= 1u;
     }
-    if (pvalid) {
-        const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
-        const k1_result r = k1_finish(d, prid, ph1, qh5, pcx, lc);
-        d.state[prid] = r.state;
-        d.route[prid] = r.route;
+    if ((blockIdx.x * WARPS + warp) < tiles) {                    // this warp had at least one tile: flush its last one
+        k1_result r{0u, 0u};
+        if (pvalid) {
+            const uint4 qh5 = make_uint4(0, ph5y, 0, 0);
+            r = k1_finish(d, prid, ph1, qh5, pcx, lc);
+            d.state[prid] = r.state;
+            d.route[prid] = r.route;
+        }
+        const uint32_t mk = __ballot_sync(FULL, pvalid && (rt_flags(r.route) & (AGR_VF_REPLAY | AGR_VF_DUP_ID)) == (AGR_VF_REPLAY | AGR_VF_DUP_ID));
+        if (lane == 0 && d.marks) d.marks[ptile] = mk;
     }
     k1_flush_counters(d, lc, s_ctr);
 }

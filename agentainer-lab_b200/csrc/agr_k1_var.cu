@@ -28,7 +28,7 @@ __device__ __forceinline__ uint4 v_lds128(uint32_t a) {
 // TTL bookkeeping (k_expire): a stored record lowers its chunk's time bound to its created_at.  Arrival times hardly ever run
 // backwards, so after a chunk's first records the bound is already low enough and the atomic is skipped.
 __device__ __forceinline__ void k1v_note_time(const agr_dev& d, const uint32_t rid, const uint32_t state, const uint4& h4) {
-    if (!(state & ST_STORED)) return;
+    if (!(state & ST_STORED) || !(d.cfg_flags & AGR_CFG_RING)) return;
     unsigned long long t = pack64(h4.x, h4.y);
     if (t == 0ULL) t = 1ULL;
     unsigned long long* cm = d.cmin + rid / AGR_CHUNK_ROWS;

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 //       persistence failure (server.go:511-514); a provisional duplicate that IS the owner (it lost the CAS race to a
 //       later row of the same batch) is promoted to stored.
 __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts,
-                                               uint4* __restrict__ ids) {
+                                               uint4* __restrict__ ids, const uint32_t* __restrict__ marks) {
     const uint32_t dupfix = __ldcg(d.dupfix);
     if (blockIdx.x == 0 && threadIdx.x < 4) d.dupfix_next[threadIdx.x] = 0;      // the previous batch is done with these words
     // nothing to do: no in-batch id races, no replay-flagged records to resolve, nobody asked for verdicts or ids
@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride) {
         const uint32_t i = i0 + threadIdx.x;
         if (i >= n) continue;
+        // with the K1 kernel's row marks and nothing else to do for unmarked rows, 4 B per 32 rows decide who stays
+        if (marks && dupfix == 0u && verdicts == nullptr && ids == nullptr && !((__ldg(&marks[i >> 5]) >> (i & 31u)) & 1u)) continue;
         const uint32_t rid = first_rid + i;
         const uint32_t r = k1_post_one(d, rid, dupfix, delta);
         if (verdicts) verdicts[i] = k1_verdict_word(r);
@@ -398,8 +400,9 @@ static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
 cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t pf_dist,
                               int sm_count, cudaStream_t st);
 
-void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids) {
-    if (n) k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
+void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids,
+                        const uint32_t* marks) {
+    if (n) k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, marks);
 }
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
@@ -410,7 +413,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
+        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, d.marks);
         return;
     }
     constexpr int WARPS = 8;
@@ -421,7 +424,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
     if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids);
+    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

@@ -32,6 +32,7 @@ struct agr_dev {
     unsigned long long log_cap;
     uint32_t* dupfix;          // per-batch words: [0] in-batch duplicate-id races (see k1_post), [1] spare, [2] replay-flagged records
     uint32_t* dupfix_next;     // the other copy of those words: k1_post clears it for the next batch (no memset between batches)
+    uint32_t* marks;           // K1 (TMA kernel) -> k1_post: one bit per row of the batch that the post pass must visit; nullptr = visit all
     uint32_t* head;            // [rows] K2 per-batch chain head of a row (op index + 1, 0 when idle)
     unsigned long long* ptime; // [rows] time.Now() of the latest StoreResponse (requests.go:146,164), the outcome's seq
     unsigned long long* mtime; // [rows] time of the latest SET of the record by K2 (0: only StoreRequest's, = the record's seq)
@@ -171,7 +172,8 @@ void agr_launch_log_compact(const agr_dev& d, const uint32_t* log, unsigned long
 void agr_launch_verify(const agr_dev& d, unsigned long long rows, unsigned long long* bad, cudaStream_t st);
 void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st);
 void agr_launch_reindex_range(const agr_dev& d, uint32_t first, uint32_t n, cudaStream_t st);
-void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids);
+void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids,
+                        const uint32_t* marks = nullptr);
 int agr_k1_tma_make_map(void* slab, unsigned long long rows, void* out_map /*128 B, 64 B aligned*/);
 uint32_t agr_k2_tiles(uint32_t n);
 void agr_launch_k2(const agr_dev& d, const void* outs /*device agr_outcome[n]*/, const agr_k2_scratch& s, uint32_t n, cudaStream_t st);

@@ -581,6 +581,7 @@ def run_ours(args, wl, rank, world, local_rank):
         outs.array["request_id"] = eng.mint_ids(first + W * B, B) if id_flags else host["request_id"]
         outs.array["agent_id"] = host["agent_id"]
         outs.array["kind"] = K.AGR_OUT_RESPONSE; outs.array["http_status"] = 200
+        outs.array["seq"] = (W + S + 8) * B                          # processed_at: after every created_at of the run
         if wl["dup_permille"]:
             rep = (host["flags"] & 1) != 0
             outs.array["request_id"][rep] = host["replay_of"][rep]
