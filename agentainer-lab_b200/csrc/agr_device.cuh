@@ -277,14 +277,20 @@ __device__ __forceinline__ void k1_flush_counters(const agr_dev& d, uint32_t* lc
 //       persistence failure (server.go:511-514); a provisional duplicate that IS the owner (it lost the CAS race to a
 //       later row of the same batch) is promoted to stored.
 // Returns the row's final route word; delta = {dedupe hits, stored, queued} corrections for the global counters.
-__device__ __forceinline__ uint32_t k1_post_one(const agr_dev& d, const uint32_t rid, const uint32_t dupfix, int* delta) {
+// `marked`: the caller knows from K1's row marks that this row is a tracked replay, so the row's own route word and its
+// replay_of are fetched together, and the target row's two words together: two dependent round trips instead of four.
+__device__ __forceinline__ uint32_t k1_post_one(const agr_dev& d, const uint32_t rid, const uint32_t dupfix, int* delta, const bool marked = false) {
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (marked) t = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF));
     uint32_t r = d.route[rid];
     uint32_t vf = rt_flags(r);
     if ((vf & AGR_VF_REPLAY) && (vf & AGR_VF_DUP_ID)) {              // a tracked replay K1 left for this pass (k1_finish's marker)
-        const uint4 t = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF));
+        if (!marked) t = __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid) + AGR_OFF_REPLAY_OF));
         const uint32_t orid = lookup_rid(d, pack64(t.x, t.y), pack64(t.z, t.w));
         vf &= ~AGR_VF_DUP_ID;
-        if (orid != AGR_RID_NONE && row_logical(d, orid) < row_logical(d, rid) && rt_slot(d.route[orid]) == rt_slot(r) && (d.state[orid] & ST_STORED)) {
+        uint32_t oroute = 0u, ostate = 0u;
+        if (orid != AGR_RID_NONE) { oroute = __ldcg(&d.route[orid]); ostate = __ldcg(&d.state[orid]); }
+        if (orid != AGR_RID_NONE && row_logical(d, orid) < row_logical(d, rid) && rt_slot(oroute) == rt_slot(r) && (ostate & ST_STORED)) {
             vf |= AGR_VF_KNOWN;
             delta[0]++;
         }
@@ -474,7 +480,7 @@ __device__ __forceinline__ void k2_apply_one(const agr_dev& d, const agr_k2_scra
         d.mtime[rid] = r.mtime;
         unsigned long long* cm = d.cmin + rid / AGR_CHUNK_ROWS;             // the TTL sweep's bound must stay a lower bound
         const unsigned long long cur = __ldcg(cm), t = r.mtime ? r.mtime : 1ULL;
-        if (cur != 0ULL && t < cur) atomicMin(cm, t);
+        if (cur != 0ULL && cur != ~0ULL && t < cur) atomicMin(cm, t);   // (0: unknown, ~0: never swept / empty — both are recomputed)
     }
     d.head[rid] = 0;
 }

@@ -100,9 +100,10 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
         const uint32_t i = i0 + threadIdx.x;
         if (i >= n) continue;
         // with the K1 kernel's row marks and nothing else to do for unmarked rows, 4 B per 32 rows decide who stays
-        if (marks && dupfix == 0u && verdicts == nullptr && ids == nullptr && !((__ldg(&marks[i >> 5]) >> (i & 31u)) & 1u)) continue;
+        const bool marked = marks && ((__ldg(&marks[i >> 5]) >> (i & 31u)) & 1u);
+        if (marks && !marked && dupfix == 0u && verdicts == nullptr && ids == nullptr) continue;
         const uint32_t rid = first_rid + i;
-        const uint32_t r = k1_post_one(d, rid, dupfix, delta);
+        const uint32_t r = k1_post_one(d, rid, dupfix, delta, marked);
         if (verdicts) verdicts[i] = k1_verdict_word(r);
         if (ids) ids[i] = k1_request_id(d, rid);
     }
@@ -393,7 +394,7 @@ void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st) {
 
 int agr_k1_launches_per_batch(uint32_t variant) { return (variant & 0x10u) ? 3 : 2; }
 static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
-    uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 8u;
+    uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 32u;
     return b < cap ? b : cap;
 }
 
