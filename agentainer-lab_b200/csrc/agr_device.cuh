@@ -339,9 +339,9 @@ __device__ __forceinline__ uint4 k1_request_id(const agr_dev& d, const uint32_t 
     }
     return __ldcg(reinterpret_cast<const uint4*>(rec_ptr(d, rid)));
 }
-__device__ __forceinline__ void k1_post_flush(const agr_dev& d, int* delta, const int lane) {
-    const int hits = __reduce_add_sync(FULL, delta[0]), stored = __reduce_add_sync(FULL, delta[1]), q = __reduce_add_sync(FULL, delta[2]);
-    if (lane == 0) {
+__device__ __forceinline__ void k1_post_apply(const agr_dev& d, const int* tot) {
+    const int hits = tot[0], stored = tot[1], q = tot[2];
+    {
         if (hits) atomicAdd(&d.ctr[C_DEDUPE_HITS], (unsigned long long)hits);
         if (stored) {
             atomicAdd(&d.ctr[C_STORED], (unsigned long long)(long long)stored);
@@ -352,6 +352,10 @@ __device__ __forceinline__ void k1_post_flush(const agr_dev& d, int* delta, cons
             atomicAdd(&d.ctr[C_UNAVAILABLE], (unsigned long long)(long long)(-q));
         }
     }
+}
+__device__ __forceinline__ void k1_post_flush(const agr_dev& d, int* delta, const int lane) {
+    const int tot[3] = {__reduce_add_sync(FULL, delta[0]), __reduce_add_sync(FULL, delta[1]), __reduce_add_sync(FULL, delta[2])};
+    if (lane == 0) k1_post_apply(d, tot);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

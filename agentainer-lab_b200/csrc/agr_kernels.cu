@@ -107,7 +107,18 @@ __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t f
         if (verdicts) verdicts[i] = k1_verdict_word(r);
         if (ids) ids[i] = k1_request_id(d, rid);
     }
-    k1_post_flush(d, delta, lane);
+    // counter corrections: one global atomic per CTA and counter (thousands of warps adding to the same three words would
+    // serialise in L2 for longer than the pass itself takes)
+    __shared__ int s_delta[3];
+    if (threadIdx.x < 3) s_delta[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int v = __reduce_add_sync(FULL, delta[k]);
+        if (lane == 0 && v) atomicAdd(&s_delta[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot[3] = {s_delta[0], s_delta[1], s_delta[2]}; k1_post_apply(d, tot); }
 }
 
 // K1b (split mode): the dedupe-index insert of every provisionally stored row, one thread per record at full
@@ -394,7 +405,7 @@ void agr_launch_reindex(const agr_dev& d, uint32_t rows, cudaStream_t st) {
 
 int agr_k1_launches_per_batch(uint32_t variant) { return (variant & 0x10u) ? 3 : 2; }
 static uint32_t k1_post_blocks(uint32_t n, int sm_count) {
-    uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 32u;
+    uint32_t b = (n + 255u) / 256u, cap = (uint32_t)sm_count * 16u;
     return b < cap ? b : cap;
 }
 
@@ -460,16 +471,24 @@ void agr_launch_resolve(const agr_dev& d, const agr_dop* ops, uint32_t* hrid, ui
 }
 
 __global__ void __launch_bounds__(256) k2_apply(const agr_dev d, const agr_k2_scratch s, const uint32_t n) {
+    __shared__ uint32_t s_cnt[3];
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
     uint32_t cnt[3] = {0u, 0u, 0u};                                  // completions, errors, dead-lettered
     if (j < n) k2_apply_one(d, s, j, cnt);
+    // one global atomic per CTA and counter: a million outcomes are 32 K warps, and that many adds to one word serialise in L2
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cnt[k] = __reduce_add_sync(FULL, cnt[k]);
-    if (lane == 0) {
-        if (cnt[0]) atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)cnt[0]);
-        if (cnt[1]) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)cnt[1]);
-        if (cnt[2]) atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)cnt[2]);
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t v = __reduce_add_sync(FULL, cnt[k]);
+        if (lane == 0 && v) atomicAdd(&s_cnt[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(&d.ctr[C_COMPLETIONS], (unsigned long long)s_cnt[0]);
+        if (s_cnt[1]) atomicAdd(&d.ctr[C_FAILURES], (unsigned long long)s_cnt[1]);
+        if (s_cnt[2]) atomicAdd(&d.ctr[C_DEAD_LETTERED], (unsigned long long)s_cnt[2]);
     }
 }
 
