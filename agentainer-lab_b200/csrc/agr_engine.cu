@@ -91,6 +91,7 @@ struct agr_handle {
     std::vector<std::pair<uint64_t, uint64_t>> resv;   // rows handed out by agr_reserve_rows and not ingested yet: [first, end)
     // K3
     uint32_t* d_matrix = nullptr; size_t matrix_entries = 0;
+    uint32_t* d_cta_matrix = nullptr; size_t cta_matrix_entries = 0;
     uint32_t* d_selmask = nullptr; size_t selmask_words = 0;   // one selection bit per scanned item (k3_mark -> k3_place)
     uint32_t* d_gtotal = nullptr; uint32_t* d_goff = nullptr;
     uint32_t* d_out_rid = nullptr; uint32_t* d_out_slot = nullptr; uint32_t out_cap = 0;
@@ -1207,7 +1208,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.groups = (mode == K3_TICK) ? std::max<uint32_t>(1, (uint32_t)h->agent_names.size()) : 1;
     uint64_t items = hi - lo;
     uint64_t max_warps = std::max<uint64_t>(1, (4u << 20) / p.groups);
-    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 32, (items + 1023) / 1024);   // 32 warps per SM, eight 32-row steps in flight each
+    uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 128, (items + 1023) / 1024);  // several waves of 8-warp CTAs; the column scan runs over per-CTA rows
     p.nwarps = (uint32_t)std::max<uint64_t>(1, std::min(want, max_warps));
     uint64_t per = (items + p.nwarps - 1) / p.nwarps;
     per = (per + 255) & ~255ull;
@@ -1215,6 +1216,9 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     p.nwarps = (uint32_t)((items + per - 1) / per);
     size_t need = (size_t)p.nwarps * p.groups;
     if (need > h->matrix_entries) { TRY(dev_regrow(h, &h->d_matrix, need, false)); h->matrix_entries = need; }
+    const size_t need_cta = (size_t)((p.nwarps + 7) / 8) * p.groups;
+    if (need_cta > h->cta_matrix_entries) { TRY(dev_regrow(h, &h->d_cta_matrix, need_cta, false)); h->cta_matrix_entries = need_cta; }
+    p.cta_matrix = h->d_cta_matrix;
     const size_t mask_words = (size_t)p.nwarps * (p.per_warp >> 5);
     if (mask_words > h->selmask_words) { TRY(dev_regrow(h, &h->d_selmask, mask_words, false)); h->selmask_words = mask_words; }
     p.selmask = h->d_selmask;

@@ -630,22 +630,23 @@ __device__ __forceinline__ k3_item k3_eval(const agr_dev& d, const agr_k3_params
 //   column scan (k3_colscan + k3_scan_total): matrix[w][g] = number of group-g items in warps < w, goff = group offsets;
 //   k3_place  walks the selection bits (4 B per 32 items), fetches the agent slot of the SELECTED items only, and writes them
 //             at goff[g] + matrix[w][g] + stable rank (match_any + popc: the warp-ballot agent-id partition).
-#define K3_SMEM_GROUPS 1024u
+#define K3_SMEM_GROUPS 512u
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_params p) {
     extern __shared__ uint32_t s_rows[];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= p.nwarps) return;
-    uint32_t* grow = p.matrix + (size_t)w * p.groups;
+    const bool live = w < p.nwarps;                              // (a CTA's surplus warps only take part in its barrier)
+    uint32_t* grow = p.matrix + (size_t)(live ? w : 0u) * p.groups;
     uint32_t* srow = s_rows + (size_t)(threadIdx.x >> 5) * p.groups;
     if (SMEM) {
         for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = 0u;
         __syncwarp();
     }
     const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
-    unsigned long long e = b + p.per_warp;
+    unsigned long long e = live ? b + p.per_warp : b;
     if (e > p.hi) e = p.hi;
+    if (!live) e = b;
     uint32_t mininq = AGR_RID_NONE;
     const bool rows = (p.mode != K3_LOG_AGENT);
     uint32_t* mask = p.selmask + (size_t)w * (p.per_warp >> 5);
@@ -685,7 +686,16 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
     }
     if (SMEM) {
         __syncwarp();
-        for (uint32_t g = lane; g < p.groups; g += 32) grow[g] = srow[g];
+        if (live) for (uint32_t g = lane; g < p.groups; g += 32) grow[g] = srow[g];
+        // the CTA's eight warps own eight consecutive runs: their sum is the CTA's row of the (8x smaller) matrix the column scan
+        // runs over; k3_place rebuilds a warp's offsets from the CTA's scanned row and the earlier warps' counts
+        __syncthreads();
+        for (uint32_t g = threadIdx.x; g < p.groups; g += 256) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += s_rows[(size_t)k * p.groups + g];
+            p.cta_matrix[(size_t)blockIdx.x * p.groups + g] = sum;
+        }
     }
     if (p.min_inq && p.mode == K3_TICK) {
         mininq = __reduce_min_sync(FULL, mininq);
@@ -698,13 +708,23 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
     extern __shared__ uint32_t s_rows[];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= p.nwarps) return;
-    uint32_t* grow = p.matrix + (size_t)w * p.groups;
+    const bool live = w < p.nwarps;
+    uint32_t* grow = p.matrix + (size_t)(live ? w : 0u) * p.groups;
     uint32_t* srow = s_rows + (size_t)(threadIdx.x >> 5) * p.groups;
     if (SMEM) {
-        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = grow[g];
+        // cursors of this warp = the CTA's scanned row + the counts of the CTA's earlier warps (k3_mark left them in the matrix)
+        for (uint32_t g = lane; g < p.groups; g += 32) srow[g] = live ? grow[g] : 0u;
+        __syncthreads();
+        uint32_t* cur = s_rows + (size_t)(8u + (threadIdx.x >> 5)) * p.groups;
+        for (uint32_t g = lane; g < p.groups; g += 32) {
+            uint32_t base = p.cta_matrix[(size_t)blockIdx.x * p.groups + g];
+            for (uint32_t k = 0; k < (threadIdx.x >> 5); ++k) base += s_rows[(size_t)k * p.groups + g];
+            cur[g] = base;
+        }
         __syncwarp();
+        srow = cur;
     }
+    if (!live) return;
     const unsigned long long b = p.lo + (unsigned long long)w * p.per_warp;
     unsigned long long e = b + p.per_warp;
     if (e > p.hi) e = p.hi;
@@ -745,7 +765,8 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
 // Column scan of matrix[nwarps][groups] in ONE launch: a CTA owns 32 adjacent columns (coalesced 128 B rows); its 32 warps cut
 // the rows into 32 segments: (1) every warp sums its segment per column, (2) an exclusive scan over the 32 segment sums in shared
 // memory, (3) every warp rewrites its segment as exclusive prefixes.  gtotal[g] = the column total.
-__global__ void __launch_bounds__(1024) k3_colscan(const agr_k3_params p) {
+__global__ void __launch_bounds__(1024) k3_colscan(const agr_k3_params pp, uint32_t* __restrict__ matrix, const uint32_t nrows) {
+    agr_k3_params p = pp; p.matrix = matrix; p.nwarps = nrows;          // the matrix to scan: per-CTA rows (or per-warp rows, flat mode)
     __shared__ uint32_t s_seg[32][33];
     const uint32_t g = blockIdx.x * 32u + (threadIdx.x & 31u), seg = threadIdx.x >> 5;
     const uint32_t per = (p.nwarps + 31u) / 32u, w0 = seg * per, w1 = min(p.nwarps, w0 + per);
@@ -799,15 +820,15 @@ __global__ void __launch_bounds__(1024) k3_scan_total(const agr_k3_params p) {
 void agr_launch_k3_select(const agr_dev& d, const agr_k3_params& p, int, cudaStream_t st) {
     const uint32_t blocks = (p.nwarps * 32u + 255u) / 256u;
     if (p.groups <= K3_SMEM_GROUPS) {
-        const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 32 KiB
+        const size_t smem = (size_t)8 * p.groups * sizeof(uint32_t);          // <= 16 KiB of counters (mark); twice that for place
         k3_mark<true><<<blocks, 256, smem, st>>>(d, p);
-        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p);
+        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p, p.cta_matrix, blocks);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
-        k3_place<true><<<blocks, 256, smem, st>>>(d, p);
+        k3_place<true><<<blocks, 256, 2 * smem, st>>>(d, p);
     } else {
         cudaMemsetAsync(p.matrix, 0, (size_t)p.nwarps * p.groups * sizeof(uint32_t), st);
         k3_mark<false><<<blocks, 256, 0, st>>>(d, p);
-        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p);
+        k3_colscan<<<(p.groups + 31u) / 32u, 1024, 0, st>>>(p, p.matrix, p.nwarps);
         k3_scan_total<<<1, 1024, 0, st>>>(p);
         k3_place<false><<<blocks, 256, 0, st>>>(d, p);
     }

@@ -90,6 +90,7 @@ struct agr_k3_params {
     uint32_t nwarps;           // matrix rows
     uint32_t per_warp;         // items per warp chunk (multiple of 32)
     uint32_t* matrix;          // [nwarps][groups]
+    uint32_t* cta_matrix;      // [ceil(nwarps / 8)][groups] per-CTA sums of eight consecutive warp rows: what the column scan runs over
     uint32_t* gtotal;          // [groups]
     uint32_t* goff;            // [groups + 1]
     uint32_t* out_rid;         // [cap]
