@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "agr_stream", "agr_kernel_time", "agr_op_time", "agr_debug_read", "agr_slab_ptr", "agr_synth_agent_id", "agr_synth_fill_host", "agr_synth_fill_rows", "agr_synth_bind_mint",
     "agr_agent_hash", "agr_agent_shard", "agr_comm_unique_id", "agr_comm_init", "agr_ingest_sharded", "agr_complete_sharded", "agr_snapshot", "agr_restore", "agr_verify", "agr_store_response_body", "agr_get_response_body",
     "agr_store_response", "agr_store_error_text", "agr_get_record_json", "agr_pending_json", "agr_rows_json", "agr_expire", "agr_reclaim", "agr_set_agent_states", "agr_json_decode",
-    "agr_submit_ingest", "agr_submit_complete", "agr_poll", "agr_wait", "agr_ring_capacity", "agr_ingest_sharded_rows", "agr_fill_rows",
+    "agr_submit_ingest", "agr_submit_complete", "agr_poll", "agr_wait", "agr_ring_capacity", "agr_ingest_sharded_rows", "agr_fill_rows", "agr_reclaim_async",
 ]
 
 _lib = None
@@ -147,6 +147,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "agr_verify": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "agr_expire": (i32, [vp, u64, u64, C.POINTER(u64)]),
         "agr_reclaim": (i32, [vp, C.POINTER(u64)]),
+        "agr_reclaim_async": (i32, [vp, C.POINTER(u64)]),
         "agr_set_agent_states": (i32, [vp, vp, vp, u32, vp]),
         "agr_json_decode": (i32, [vp, u32, vp, u32, vp, u32, vp, u32, vp]),
         "agr_comm_unique_id": (i32, [vp]),
@@ -597,6 +598,12 @@ class Engine:
         """AGR_CFG_RING: release the rows at the tail that hold no record any more; returns how many."""
         n = C.c_uint64()
         _check(self.lib, self.lib.agr_reclaim(self.h, C.byref(n)))
+        return int(n.value)
+
+    def reclaim_async(self) -> int:
+        """agr_reclaim_async: releases what the previous call's scan found, starts the next scan; returns rows released now."""
+        n = C.c_uint64()
+        _check(self.lib, self.lib.agr_reclaim_async(self.h, C.byref(n)))
         return int(n.value)
 
     def verify(self) -> Tuple[int, int]:

@@ -67,6 +67,8 @@ struct agr_handle {
     uint64_t tail = 0;        // ring: first logical row that has not been released
     uint32_t* d_log_scratch = nullptr; uint32_t* d_lc_chunks = nullptr;   // ring: log compaction
     uint64_t released_total = 0;
+    uint8_t* d_reclaim = nullptr; uint8_t* h_reclaim = nullptr;   // agr_reclaim's scan result (device scratch / pinned copy)
+    cudaEvent_t reclaim_ev = nullptr; bool reclaim_pending = false; uint64_t reclaim_bound = 0;
     uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
     uint64_t scan_lo = 0;     // every row below has left its pending list for good
     uint64_t sweep_clean = 0; // append-only slab: rows below were ingested when agr_expire last ran (their chunks' time bounds are exact)
@@ -754,6 +756,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(dev_alloc(h, &h->d_outs, c.max_batch, false));
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
+    TRY(dev_alloc(h, &h->d_reclaim, (size_t)64, true));
+    TRY(host_alloc(h, &h->h_reclaim, (size_t)64));
     TRY(dev_alloc(h, &h->d_ops, (size_t)16, false));
     TRY(dev_alloc(h, &h->d_hrid, (size_t)16, false));
     TRY(host_alloc(h, &h->h_k2flag, (size_t)4));
@@ -786,6 +790,7 @@ void agr_destroy(agr_handle* h) {
     for (auto e : h->tev) cudaEventDestroy(e);
     for (auto e : h->op_ev) if (e) cudaEventDestroy(e);
     for (auto e : h->chunk_ev) cudaEventDestroy(e);
+    if (h->reclaim_ev) cudaEventDestroy(h->reclaim_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1264,7 +1269,7 @@ int agr_replay_scan(agr_handle* h, agr_dispatch* out, agr_record* recs, uint32_t
     TRY(ensure_gather(h, bytes));
     uint8_t* d_disp = h->d_gather;
     uint8_t* d_recs = recs ? h->d_gather + (size_t)total * 32 : nullptr;
-    agr_launch_k3_gather(h->d, h->d_out_rid, h->d_out_slot, total, d_recs, d_disp, nullptr, h->stream);
+    agr_launch_k3_gather(h->d, h->d_out_rid, nullptr, total, d_recs, d_disp, nullptr, h->stream);
     h->k3_launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_gather, h->d_gather, bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -1462,7 +1467,7 @@ int agr_replay_scan_var(agr_handle* h, agr_dispatch* out, uint8_t* blob, uint64_
     if (total == 0) return 0;
     if (out) {
         TRY(ensure_gather(h, (size_t)total * 32));
-        agr_launch_k3_gather(h->d, h->d_out_rid, h->d_out_slot, total, nullptr, h->d_gather, nullptr, h->stream);
+        agr_launch_k3_gather(h->d, h->d_out_rid, nullptr, total, nullptr, h->d_gather, nullptr, h->stream);
         h->k3_launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)total * 32, cudaMemcpyDeviceToHost, h->stream));
@@ -1866,34 +1871,41 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     return 0;
 }
 
-// AGR_CFG_RING: hand the rows at the tail that hold no record any more (expired or never stored) back to the ring, up to
-// the first row that still does, and drop their entries from the completed / failed logs.
-int agr_reclaim(agr_handle* h, uint64_t* released) {
-    if (!h) return fail(AGR_EINVAL, "NULL argument");
-    HLock lk(h);
-    CK(cudaSetDevice(h->device));
-    if (released) *released = 0;
-    if (!is_ring(h)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_RING");
+// what one scan of the ring's tail reports back (device -> pinned host, one 32-byte copy)
+struct reclaim_result { uint32_t off, pad; unsigned long long lens[2]; unsigned long long voff; };
+
+// enqueues the scan: first stored row behind the tail (k_first_live), the log lengths and — variable-length mode — the byte
+// offset of that row's record, packed by one tiny kernel and copied to pinned memory; nothing waits here
+static int reclaim_scan_launch(agr_handle* h, uint64_t bound) {
     sync_window(h);
-    const uint64_t bound = ingested_bound(h);                                  // reserved rows that K1 has not filled yet are not "dead"
-    if (bound <= h->tail) return 0;
     uint32_t* d_off = h->d_min_inq;                                            // 4-byte scratch
     CK(cudaMemsetAsync(d_off, 0xff, 4, h->stream));
     agr_launch_first_live(h->d, bound - h->tail, d_off, h->stream);
+    agr_launch_reclaim_pack(h->d, d_off, h->d_reclaim, h->stream);
     CK(cudaGetLastError());
-    unsigned long long* lens = (unsigned long long*)(h->h_small + 2);          // pinned
-    CK(cudaMemcpyAsync(h->h_small, d_off, 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(lens, h->d.log_len, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));                                      // the only host round trip
-    const uint64_t count = (h->h_small[0] == 0xffffffffu) ? bound - h->tail : h->h_small[0];
-    h->k3_launches += 1;
+    CK(cudaMemcpyAsync(h->h_reclaim, h->d_reclaim, sizeof(reclaim_result), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->reclaim_ev) CK(cudaEventCreateWithFlags(&h->reclaim_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->reclaim_ev, h->stream));
+    h->reclaim_bound = bound;
+    h->reclaim_pending = true;
+    h->k3_launches += 2;
+    return 0;
+}
+
+// releases what a finished scan found: rows [tail, tail + count) go back to the ring
+static int reclaim_apply(agr_handle* h, uint64_t* released) {
+    h->reclaim_pending = false;
+    const reclaim_result r = *reinterpret_cast<const reclaim_result*>(h->h_reclaim);
+    const uint64_t bound = h->reclaim_bound;
+    const uint64_t count = (r.off == 0xffffffffu) ? bound - h->tail : r.off;
     if (count == 0) return 0;
+    sync_window(h);
     agr_launch_release_rows(h->d, (uint32_t)count, h->d_resp_len, h->d_resp_hlen, h->d_err_len, h->stream);
     h->k3_launches += 1;
     for (int k = 0; k < 2; ++k) {                                              // completed, failed
-        if (!lens[k]) continue;
+        if (!r.lens[k]) continue;
         uint32_t*& log = k == 0 ? h->d.completed_log : h->d.failed_log;
-        agr_launch_log_compact(h->d, log, lens[k], (uint32_t)count, h->d_log_scratch, h->d_lc_chunks, h->d.log_len + k, h->stream);
+        agr_launch_log_compact(h->d, log, r.lens[k], (uint32_t)count, h->d_log_scratch, h->d_lc_chunks, h->d.log_len + k, h->stream);
         CK(cudaGetLastError());
         std::swap(log, h->d_log_scratch);                                      // the compacted copy becomes the log
         h->k3_launches += 3;
@@ -1926,17 +1938,49 @@ int agr_reclaim(agr_handle* h, uint64_t* released) {
         h->k3_launches += 1;
     }
     if (h->cfg.flags & AGR_CFG_VARLEN) {                          // the byte ring's tail follows: first byte of the first live record
-        if (h->tail == h->rows_used) h->vtail = h->vused;
+        if (r.off == 0xffffffffu) h->vtail = (bound == h->rows_used) ? h->vused : h->vtail;
         else {
-            unsigned long long q = 0;
-            CK(cudaMemcpyAsync(&q, h->d.voff + phys_row(h, h->tail), 8, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            uint64_t used = (h->vused % h->vcap + h->vcap - q) % h->vcap;
+            uint64_t used = (h->vused % h->vcap + h->vcap - r.voff) % h->vcap;
             if (used == 0) used = h->vcap;                         // head == tail with live records: the ring is exactly full
             h->vtail = h->vused - used;
         }
     }
     if (released) *released = count;
+    return 0;
+}
+
+// AGR_CFG_RING: hand the rows at the tail that hold no record any more (expired or never stored) back to the ring, up to
+// the first row that still does, and drop their entries from the completed / failed logs.
+int agr_reclaim(agr_handle* h, uint64_t* released) {
+    if (!h) return fail(AGR_EINVAL, "NULL argument");
+    HLock lk(h);
+    CK(cudaSetDevice(h->device));
+    if (released) *released = 0;
+    if (!is_ring(h)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_RING");
+    uint64_t got = 0;
+    if (h->reclaim_pending) { CK(cudaEventSynchronize(h->reclaim_ev)); TRY(reclaim_apply(h, &got)); }   // a scan agr_reclaim_async left behind
+    const uint64_t bound = ingested_bound(h);                                  // reserved rows that K1 has not filled yet are not "dead"
+    if (bound > h->tail) {
+        TRY(reclaim_scan_launch(h, bound));
+        CK(cudaStreamSynchronize(h->stream));                                  // the only host round trip
+        uint64_t more = 0;
+        TRY(reclaim_apply(h, &more));
+        got += more;
+    }
+    if (released) *released = got;
+    return 0;
+}
+// The same without the host round trip in the caller's way: releases what the scan started by the PREVIOUS call found (it has
+// long finished) and starts the next scan.  A ring that is maintained every step lags one step behind and never waits.
+int agr_reclaim_async(agr_handle* h, uint64_t* released) {
+    if (!h) return fail(AGR_EINVAL, "NULL argument");
+    HLock lk(h);
+    CK(cudaSetDevice(h->device));
+    if (released) *released = 0;
+    if (!is_ring(h)) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_RING");
+    if (h->reclaim_pending) { CK(cudaEventSynchronize(h->reclaim_ev)); TRY(reclaim_apply(h, released)); }
+    const uint64_t bound = ingested_bound(h);
+    if (bound > h->tail) TRY(reclaim_scan_launch(h, bound));
     return 0;
 }
 

@@ -268,6 +268,17 @@ __global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsig
     mine = __reduce_min_sync(FULL, mine);
     if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
 }
+// packs what agr_reclaim needs on the host into one 32-byte record: the offset found, both log lengths, and (variable-length
+// mode) the byte offset of the first live row's record
+__global__ void k_reclaim_pack(const agr_dev d, const uint32_t* __restrict__ off, unsigned long long* __restrict__ out) {
+    const uint32_t o = *off;
+    out[0] = o;
+    out[1] = d.log_len[0]; out[2] = d.log_len[1];
+    out[3] = (d.voff && o != 0xffffffffu) ? d.voff[row_physical(d, d.tail + o)] : 0ULL;
+}
+void agr_launch_reclaim_pack(const agr_dev& d, const uint32_t* off, void* out, cudaStream_t st) {
+    k_reclaim_pack<<<1, 1, 0, st>>>(d, off, (unsigned long long*)out);
+}
 void agr_launch_first_live(const agr_dev& d, unsigned long long live, uint32_t* out_off, cudaStream_t st) {
     if (live) k_first_live<<<(unsigned)((live + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, live, out_off);
 }
@@ -678,8 +689,13 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
             if (!rows || __any_sync(FULL, (st & ST_INQ) != 0u)) {                    // else: nothing pending in these 32 rows
                 const k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
                 if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
-                if (it.sel) atomicAdd((SMEM ? srow : grow) + ((p.groups == 1) ? 0u : it.slot), 1u);   // counting needs no order
                 selbits = __ballot_sync(FULL, it.sel);
+                if (selbits) {
+                    // counting needs no order, but a hot agent puts many lanes of a warp on ONE counter: add once per (warp, agent)
+                    const uint32_t g = (p.groups == 1) ? 0u : it.slot;
+                    const uint32_t peers = __match_any_sync(FULL, it.sel ? g : (0x80000000u | (uint32_t)lane));
+                    if (it.sel && (uint32_t)lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
+                }
             }
             if (lane == 0) mask[(k0 - b) >> 5] = selbits;
         }
@@ -756,7 +772,7 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
                 if (lane == leader) base = atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
                 base = __shfl_sync(peers, base, leader);
                 const uint32_t pos = p.goff[g] + base + __popc(peers & ((1u << lane) - 1u));
-                if (pos < p.cap) { p.out_rid[pos] = rid; p.out_slot[pos] = slot; }
+                if (pos < p.cap) p.out_rid[pos] = rid;              // (the agent slot is one load away for whoever needs it: route[rid])
             }
         }
     }

@@ -367,6 +367,10 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired);
  * instead).  Ids of released rows are never valid again (a minted id is checked against the live window).  *released
  * (nullable) = rows handed back.  Typical use: agr_expire(now, 24 h) then agr_reclaim, from the same ticker. */
 int agr_reclaim(agr_handle* h, uint64_t* released);
+/* The same without a host round trip in the caller's way: releases what the scan started by the PREVIOUS call found and starts the
+ * next scan.  For a ticker that maintains the ring every step (agr_expire(now, ttl, NULL); agr_reclaim_async(h, NULL)): the
+ * release lags one step, nothing waits for the GPU. */
+int agr_reclaim_async(agr_handle* h, uint64_t* released);
 /* Integrity sweep: recomputes the checksum of every stored record on the device and compares it with the one K1 took at
  * ingest.  *bad = number of rows that differ (0 on a healthy slab). */
 int agr_verify(agr_handle* h, uint64_t* rows_checked, uint64_t* bad);

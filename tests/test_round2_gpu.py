@@ -256,3 +256,40 @@ def test_random_streams_with_the_manual_replay_handler(flags):
             o, g = run_oracle(ev), run_engine(eng, ev)
             assert_same(o, g)
             assert {200, 502} <= set(o.manual) and (404 in o.manual or 503 in o.manual)
+
+
+@pytest.mark.parametrize("flags", [MINT, MINT | K.AGR_CFG_VARLEN])
+def test_reclaim_async_keeps_a_ring_running_one_step_behind(flags):
+    """agr_expire(now, ttl, NULL) + agr_reclaim_async every step: the release lags one step (it applies the previous call's scan) and
+    never waits; the ring still runs far past its capacity, live ids resolve, released ones do not."""
+    from jsoncase import make_requests, records_array, var_batch
+    R, per, ttl = 4096, 256, 3 * 256
+    var = bool(flags & K.AGR_CFG_VARLEN)
+    agent = "agent-1700000000000000001"
+    with A.Engine(slab_rows=R, max_agents=4, max_batch=per, vslab_bytes=4 << 20, flags=flags | K.AGR_CFG_RING) as eng:
+        eng.set_agent_state(agent, "stopped")
+        ids_by_step = []
+        released = 0
+        for step in range(80):                                   # 80 x 256 = 5 laps of the ring
+            reqs = make_requests(100 + step, per, [agent], max_payload=1500 if var else 416, big_bodies=var)
+            for i, r in enumerate(reqs):
+                r.now = step * per + i
+            if var:
+                blob, offs = var_batch(reqs)
+                _, ids, first = eng.ingest_var(blob, offs)
+            else:
+                out = np.zeros(per, dtype=A.verdict_dtype); ids = np.zeros((per, 16), dtype=np.uint8)
+                first = eng.ingest_ex(records_array(reqs), out, ids)
+            assert first >= step * per
+            ids_by_step.append(ids.copy())
+            eng.expire((step + 1) * per, ttl, want_count=False)
+            released += eng.reclaim_async()
+            st = eng.stats()
+            assert st["rows_used"] - st["rows_tail"] <= R
+        released += eng.reclaim()                                # drains the scan left pending and scans once more
+        st = eng.stats()
+        assert st["rows_tail"] == released and st["rows_used"] - st["rows_tail"] <= 4 * per + 64
+        get = (lambda rid: eng.get_record_var(agent, rid)) if var else (lambda rid: eng.get_record(agent, rid))
+        assert get(bytes(ids_by_step[-1][7])) is not None        # the last step's records are alive
+        assert get(bytes(ids_by_step[10][7])) is None            # long gone: expired, released, row reused
+        assert len(eng.list(agent, K.AGR_LIST_PENDING, cap=1 << 14)) <= 4 * per
