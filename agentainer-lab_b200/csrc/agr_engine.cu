@@ -2413,8 +2413,7 @@ int agr_synth_fill_rows(agr_handle* h, const agr_synth* s, uint64_t first_index,
         dcdf = h->d_cdf;
     }
     agr_launch_synth(h->d.slab + phys_row(h, first_rid) * AGR_REC, synth_params(s, dcdf), first_index, n, h->stream);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());                                      // (stream-ordered before whatever reads the rows: no wait here)
     return 0;
 }
 

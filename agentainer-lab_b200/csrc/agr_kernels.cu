@@ -689,13 +689,8 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
             if (!rows || __any_sync(FULL, (st & ST_INQ) != 0u)) {                    // else: nothing pending in these 32 rows
                 const k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
                 if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
+                if (it.sel) atomicAdd((SMEM ? srow : grow) + ((p.groups == 1) ? 0u : it.slot), 1u);   // counting needs no order
                 selbits = __ballot_sync(FULL, it.sel);
-                if (selbits) {
-                    // counting needs no order, but a hot agent puts many lanes of a warp on ONE counter: add once per (warp, agent)
-                    const uint32_t g = (p.groups == 1) ? 0u : it.slot;
-                    const uint32_t peers = __match_any_sync(FULL, it.sel ? g : (0x80000000u | (uint32_t)lane));
-                    if (it.sel && (uint32_t)lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
-                }
             }
             if (lane == 0) mask[(k0 - b) >> 5] = selbits;
         }
