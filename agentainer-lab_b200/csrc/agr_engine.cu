@@ -380,7 +380,7 @@ static void svc_dispatcher(agr_handle* h) {
             const uint32_t slot = (uint32_t)(to & (SVC_SLOTS - 1u));
             const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
             if ((rw >> 2) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
-            if ((rw & 3u) == SVC_OP_RECORD) { if (nrec == 256u) break; nrec++; }
+            if ((rw & 3u) == SVC_OP_RECORD) { if (nrec == 128u) break; nrec++; }
             kinds[(to - s->taken) >> 4] |= (rw & 3u) << (((to - s->taken) & 15u) * 2u);
             to++;
         }

@@ -19,7 +19,7 @@
 #include <stdint.h>
 
 #define SVC_SLOTS 16384u          // ring slots (power of two)
-#define SVC_MAX_OPS 512u          // operations per batch == threads of the service CTA
+#define SVC_MAX_OPS 256u          // operations per batch (<= 128 of them records: what one shared-memory stage of the kernel holds)
 #define SVC_MAX_CALL 32u          // records / outcomes per call that go through the ring
 #define SVC_DESCS 64u             // descriptor ring entries
 #define SVC_PAYLOAD 512u          // bytes per slot: an agr_record, or an agr_outcome in the first 64 B
@@ -30,7 +30,7 @@ enum { SVC_OP_SKIP = 0, SVC_OP_RECORD = 1, SVC_OP_OUTCOME = 2 };
 // in ONE poll; the kernel accepts it when the batch number matches and the check word agrees with the other 62 words (a poll
 // that raced the host's stores sees a mix of old and new words and fails the check), so no second PCIe round trip is needed
 struct __attribute__((aligned(64))) svc_desc {
-    uint32_t kinds[SVC_MAX_OPS / 16];     // words 0..31: 2 bits per op, SVC_OP_*
+    uint32_t kinds[SVC_MAX_OPS / 16];     // words 0..15: 2 bits per op, SVC_OP_*
     uint64_t from;                        // absolute number of the batch's first ring slot
     uint32_t count;                       // ops in the batch
     uint32_t n_records;                   // SVC_OP_RECORD ops among them: rows first_p .. first_p + n_records
@@ -39,7 +39,7 @@ struct __attribute__((aligned(64))) svc_desc {
     uint32_t tail_phys;                   // live window of the slab after this batch's rows were reserved
     uint64_t tail, head_l;
     uint64_t idx_base;
-    uint64_t reserved[7];
+    uint64_t reserved[15];
     uint64_t check;                       // words 60..61: XOR of svc_mix_word over words 0..59 and 62..63
     uint64_t seq;                         // words 62..63: batch number; the kernel waits for desc[seq % SVC_DESCS].seq == seq
 };
