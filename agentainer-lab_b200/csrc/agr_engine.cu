@@ -286,6 +286,7 @@ struct svc_host {
     uint64_t seq = 0;                                   // dispatcher: last batch number published
     bool running = false;                               // service kernel resident (changed under the handle mutex only)
     std::chrono::steady_clock::time_point started;      // when it was launched
+    std::chrono::steady_clock::time_point last_publish; // when the dispatcher last published a batch
     agr_k2_scratch k2{};                                // K2 scratch of the service kernel (SVC_MAX_OPS ops)
     uint32_t* d_dupfix = nullptr;
     std::thread thr;
@@ -371,11 +372,12 @@ static void svc_dispatcher(agr_handle* h) {
     cudaSetDevice(h->device);
     auto last_work = std::chrono::steady_clock::now();
     uint32_t spins = 0;
+    // the contiguous published prefix [taken, to), grown INCREMENTALLY: a slot is looked at until it is published and never again
+    // (re-reading the callers' ready words every iteration keeps pulling their cache lines away from the cores that write them)
+    uint64_t to = s->taken;
+    uint32_t nrec = 0;
+    uint32_t kinds[SVC_MAX_OPS / 16] = {0};
     while (!s->shutdown.load(std::memory_order_acquire)) {
-        // the contiguous published prefix [taken, to)
-        uint64_t to = s->taken;
-        uint32_t nrec = 0;
-        uint32_t kinds[SVC_MAX_OPS / 16] = {0};
         while (to - s->taken < SVC_MAX_OPS) {
             const uint32_t slot = (uint32_t)(to & (SVC_SLOTS - 1u));
             const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
@@ -404,13 +406,17 @@ static void svc_dispatcher(agr_handle* h) {
             continue;
         }
         last_work = now;
-        // Batching window = the kernel's own pace: at most two batches are outstanding (one running, one queued so the kernel
-        // never idles); while both are, keep collecting — whatever arrives meanwhile joins the next batch instead of queueing
-        // behind a train of one-request batches.
-        if (s->running && s->seq - s->ctl->done_seq >= 2 && to - s->taken < SVC_MAX_OPS) { s->flow_waits++; _mm_pause(); continue; }
+        // Batching window = the kernel's own pace: at most two batches are outstanding (one being decided, one being pulled by
+        // the kernel's loader warps); while both are, keep collecting — whatever arrives meanwhile joins the next batch instead
+        // of queueing behind a train of one-request batches.
+        if (s->running && s->seq - s->ctl->done_seq >= 2 && to - s->taken < SVC_MAX_OPS) {
+            s->flow_waits++;
+            for (int k = 0; k < 8; ++k) _mm_pause();
+            continue;
+        }
         spins = 0;
         std::lock_guard<std::mutex> hl(h->mu);
-        if (s->fatal.load()) { svc_fail_ops(s, s->taken, to, s->fatal.load(), false); s->taken = to; continue; }
+        if (s->fatal.load()) { svc_fail_ops(s, s->taken, to, s->fatal.load(), false); s->taken = to; nrec = 0; memset(kinds, 0, sizeof kinds); continue; }
         if (s->running && s->ctl->state != 1u) {                // it left on its own (safety timeout): note it and start another
             cudaStreamSynchronize(h->stream);
             s->running = false;
@@ -448,6 +454,7 @@ static void svc_dispatcher(agr_handle* h) {
         s->ops.fetch_add(dsc.count, std::memory_order_relaxed);
         h->k1_launches += nrec ? 1 : 0;                         // accounting: batches with records / with outcomes served by k_svc
         h->k2_launches += (dsc.count > nrec) ? 1 : 0;
+        nrec = 0; memset(kinds, 0, sizeof kinds);
         if (!s->running && svc_start_locked(h) < 0) {
             // could not launch: nothing will ever process this batch — fail it from here
             svc_fail_ops(s, dsc.from, to, AGR_ECUDA, false);

@@ -87,7 +87,7 @@ def run_callers(local_rank, seconds=2.0):
             return {"error": repr(e)}
     for t in (8, 64, 256):
         out["blocking"][f"threads_{t}"] = one(t, 0)
-    for t, w in ((4, 512), (12, 256)):
+    for t, w in ((4, 512), (8, 512), (12, 256)):
         out["tickets"][f"threads_{t}_inflight_{w}"] = one(t, w)
     best = max((v.get("round_trips_per_s", 0), k, v) for d in (out["blocking"], out["tickets"]) for k, v in d.items())
     out["value"], out["best"] = best[0], best[1]
