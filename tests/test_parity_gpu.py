@@ -434,3 +434,52 @@ def test_flat_combining_of_concurrent_single_request_calls():
                 assert pend == [] and sorted(comp) == sorted(rid for _, rid in mine)
         s = eng.stats()
         assert s["stored"] == nt * per and s["k1_launches"] < 2 * nt * per
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_full_size_configs_against_c_port(cfg):
+    """BASELINE configs[1] (1 M records, 256 agent ids, uniform) and configs[2] (10 M records, Zipf s = 1.2, 10 % replay-flagged
+    duplicates) at their FULL size, engine-minted ids, in 1 M-record batches: every verdict of every record, the result code of
+    every outcome (a fifth of the forwarded requests answer, some fail), the replay tick's dispatch list after a stop / start of
+    a fifth of the agents, and whole per-agent lists — CUDA path == C restatement of the reference, bit for bit."""
+    from oracle.cpu_ref import CRef
+    B, na = 1 << 20, 256
+    nb = 1 if cfg == "c2" else 10
+    zipf, dup = (0, 0) if cfg == "c2" else (1200, 100)
+    agents = [A.synth_agent_id(k) for k in range(na)]
+    with A.Engine(slab_rows=nb * B + 1024, max_agents=512, max_batch=B, flags=MINT) as eng, CRef() as ref:
+        for e in (eng, ref):
+            for k, a in enumerate(agents):
+                e.set_agent_state(a, "stopped" if k % 5 == 1 else "running")          # incl. the rank-1 hot agent
+        hits = 0
+        for b in range(nb):
+            recs = A.synth_fill_host(b * B, B, seed=3, n_agents=na, zipf_milli=zipf, dup_permille=dup, mint=(eng, 0))
+            recs["request_id"] = eng.mint_ids(b * B, B)                               # the checker gets the ids the engine mints
+            v0, first = eng.ingest(recs)
+            v1, _ = ref.ingest(recs)
+            assert first == b * B
+            assert (v0["code"] == v1["code"]).all() and ((v0["flags"] & 0x7) == (v1["flags"] & 0x7)).all(), b   # (KNOWN is the engine's own annotation)
+            assert (v0["agent_slot"] == v1["agent_slot"]).all()
+            hits += int(((v0["flags"] & K.AGR_VF_KNOWN) != 0).sum())
+            fwd = np.nonzero((v0["code"] == K.AGR_V_FORWARD) & ((v0["flags"] & K.AGR_VF_TRACKED) != 0))[0][::5]
+            outs = np.zeros(len(fwd), dtype=A.outcome_dtype)
+            outs["request_id"] = np.where(((recs["flags"][fwd] & 1) != 0)[:, None], recs["replay_of"][fwd], recs["request_id"][fwd])
+            outs["agent_id"] = recs["agent_id"][fwd]
+            outs["kind"] = np.where(np.arange(len(fwd)) % 7 == 3, K.AGR_OUT_ERROR, K.AGR_OUT_RESPONSE)
+            outs["http_status"], outs["seq"] = 200, (b + 1) * B
+            assert (eng.complete(outs) == ref.complete(outs)).all(), b
+        if dup:
+            assert hits > nb * B // 20                                                 # the duplicates really resolved
+        for e in (eng, ref):
+            for k, a in enumerate(agents):
+                if k % 5 == 1:
+                    e.set_agent_state(a, "running")
+        d0, _ = eng.replay_scan(with_records=False, cap=nb * B)
+        d1, _ = ref.replay_scan()
+        assert len(d0) == len(d1) > nb * B // 20
+        assert (d0["agent_slot"] == d1["agent_slot"]).all() and d0["request_id"].tobytes() == d1["request_id"].tobytes()
+        for a in agents[:4] + agents[100:102]:
+            for w in (0, 1, 2):
+                assert eng.list(a, w, cap=1 << 22).tobytes() == ref.list(a, w, cap=1 << 22).tobytes(), (a, w)
+        s = eng.stats()
+        assert s["ingested"] == nb * B
