@@ -1856,11 +1856,16 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
     CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
     sync_window(h);
-    if (!is_ring(h) && h->rows_used > h->sweep_clean) {
-        // append-only slab: K1 does not keep the chunks' time bounds (k1_note_time); the chunks that received rows since the last
-        // sweep are marked "unknown" here and get their exact bound back from this sweep
-        const uint64_t c0 = h->sweep_clean / AGR_CHUNK_ROWS, c1 = (h->rows_used - 1) / AGR_CHUNK_ROWS;
-        CK(cudaMemsetAsync(h->d.cmin + c0, 0, (size_t)(c1 - c0 + 1) * 8, h->stream));
+    if ((!is_ring(h) || (h->cfg.flags & AGR_CFG_VARLEN)) && h->rows_used > h->sweep_clean) {
+        // append-only slabs and variable-length engines: K1 does not keep the chunks' time bounds (k1_note_time); the chunks that
+        // received rows since the last sweep are marked "unknown" here and get their exact bound back from this sweep
+        const uint64_t R = h->cfg.slab_rows, lo = std::max(h->sweep_clean, h->tail), hi = h->rows_used;
+        if (is_ring(h) && hi - lo >= R) CK(cudaMemsetAsync(h->d.cmin, 0, (size_t)(R / AGR_CHUNK_ROWS + 1) * 8, h->stream));
+        else if (hi > lo) {
+            const uint64_t p0 = phys_row(h, lo), p1 = phys_row(h, hi - 1);
+            auto zero = [&](uint64_t a, uint64_t b) { return cudaMemsetAsync(h->d.cmin + a / AGR_CHUNK_ROWS, 0, (size_t)(b / AGR_CHUNK_ROWS - a / AGR_CHUNK_ROWS + 1) * 8, h->stream); };
+            if (p0 <= p1) CK(zero(p0, p1)); else { CK(zero(p0, R - 1)); CK(zero(0, p1)); }
+        }
         h->sweep_clean = ingested_bound(h);
     }
     agr_launch_expire(h->d, rows_span(h), now, ttl, d_cnt, h->stream);

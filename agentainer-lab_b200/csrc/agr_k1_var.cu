@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 v_lds128(uint32_t a) {
 // TTL bookkeeping (k_expire): a stored record lowers its chunk's time bound to its created_at.  Arrival times hardly ever run
 // backwards, so after a chunk's first records the bound is already low enough and the atomic is skipped.
 __device__ __forceinline__ void k1v_note_time(const agr_dev& d, const uint32_t rid, const uint32_t state, const uint4& h4) {
+    return;   // variable-length engines: agr_expire resets the bounds of the chunks filled since its last call instead (the
+              // per-record read of the bound cost this issue-bound kernel 8 %); kept for reference
     if (!(state & ST_STORED) || !(d.cfg_flags & AGR_CFG_RING)) return;
     unsigned long long t = pack64(h4.x, h4.y);
     if (t == 0ULL) t = 1ULL;
