@@ -277,28 +277,29 @@ cudaError_t agr_launch_svc(const agr_dev& d, const svc_dev& v, const agr_k2_scra
 unsigned long long agr_svc_desc_check(const svc_desc* dsc);
 
 struct svc_host {
-    // pinned, device-mapped
-    svc_desc* desc = nullptr; uint8_t* payload = nullptr; svc_res* res = nullptr; svc_ctl* ctl = nullptr;
-    // host only
-    std::atomic<uint64_t> head{0};                      // next ring slot to hand out (absolute number)
+    // ---- read-mostly (every caller reads these on every call; nothing here is written while callers run)
+    svc_desc* desc = nullptr; uint8_t* payload = nullptr; svc_res* res = nullptr; svc_ctl* ctl = nullptr;   // pinned, device-mapped
     std::atomic<uint32_t>* ready = nullptr;             // [SVC_SLOTS] (lap + 1) << 2 | SVC_OP_* once the slot's payload is complete
-    uint64_t taken = 0;                                 // dispatcher: first slot not yet put into a batch
-    uint64_t seq = 0;                                   // dispatcher: last batch number published
+    uint32_t spin_cpus = 1;                             // how many waiters may spin (CPU allowance minus dispatcher and driver threads)
+    std::atomic<bool> shutdown{false}, sleeping{false}; // (sleeping flips only when the ring has been empty for 2 ms)
+    std::atomic<int> fatal{0};                          // a CUDA error in the dispatcher: every later call fails with it
+    // ---- the words the callers / the dispatcher keep writing: a cache line each
+    alignas(64) std::atomic<uint64_t> head{0};          // next ring slot to hand out (absolute number)
+    alignas(64) std::atomic<uint32_t> waiters{0};       // callers blocked in svc_wait right now
+    alignas(64) std::atomic<uint64_t> scanned{0};       // dispatcher: first slot whose ready word it has not consumed yet (>= taken)
+    // ---- the dispatcher's own
+    alignas(64) uint64_t taken = 0;                     // first slot not yet put into a batch
+    uint64_t seq = 0;                                   // last batch number published
     bool running = false;                               // service kernel resident (changed under the handle mutex only)
     std::chrono::steady_clock::time_point started;      // when it was launched
-    std::chrono::steady_clock::time_point last_publish; // when the dispatcher last published a batch
     agr_k2_scratch k2{};                                // K2 scratch of the service kernel (SVC_MAX_OPS ops)
     uint32_t* d_dupfix = nullptr;
-    std::thread thr;
-    std::atomic<bool> shutdown{false}, sleeping{false};
-    std::mutex smu; std::condition_variable scv;        // the dispatcher sleeps here when the ring has been empty for a while
     std::atomic<uint64_t> batches{0}, ops{0};
-    std::atomic<int> fatal{0};                          // a CUDA error in the dispatcher: every later call fails with it
-    std::atomic<uint32_t> waiters{0};                   // callers blocked in svc_wait right now
-    uint32_t spin_cpus = 1;                             // how many of them may spin (CPU allowance minus dispatcher and driver threads)
     // diagnostics (AGR_SVC_DEBUG=1 prints them when the handle is destroyed)
     uint64_t starts = 0, stops = 0, sleeps = 0, flow_waits = 0;
     double cyc[4] = {0, 0, 0, 0}; uint64_t polls = 0;
+    std::thread thr;
+    alignas(64) std::mutex smu; std::condition_variable scv;   // the dispatcher sleeps here when the ring has been empty for a while
 };
 
 static inline void cpu_relax(uint32_t& spins) {
@@ -358,8 +359,9 @@ struct HLock {
 static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only) {
     for (uint64_t a = from; a < to; ++a) {
         const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
-        const bool rec = (s->ready[slot].load(std::memory_order_relaxed) & 3u) == SVC_OP_RECORD;
-        if (records_only && !rec) continue;
+        const uint32_t kd = s->ready[slot].load(std::memory_order_relaxed) & 3u;
+        const bool rec = kd == SVC_OP_RECORD;
+        if (kd == SVC_OP_SKIP || (records_only && !rec)) continue;                  // (a skipped slot has no waiter and keeps its old answer)
         svc_res* r = s->res + slot;
         r->w[0] = rec ? 0u : (uint32_t)rc; r->w[1] = rec ? (uint32_t)rc : 0u; r->w[2] = 0;
         std::atomic_thread_fence(std::memory_order_release);
@@ -386,6 +388,7 @@ static void svc_dispatcher(agr_handle* h) {
             kinds[(to - s->taken) >> 4] |= (rw & 3u) << (((to - s->taken) & 15u) * 2u);
             to++;
         }
+        if (to != s->scanned.load(std::memory_order_relaxed)) s->scanned.store(to, std::memory_order_release);
         const auto now = std::chrono::steady_clock::now();
         if (to == s->taken) {
             const auto idle = std::chrono::duration_cast<std::chrono::microseconds>(now - last_work).count();
@@ -529,29 +532,52 @@ static void svc_destroy(agr_handle* h) {
 }
 
 // caller side: claim n slots, write the payloads, publish, wake the dispatcher if it sleeps.  Returns the first slot.
-static uint64_t svc_submit(svc_host* s, uint32_t kind, const void* items, size_t item_bytes, uint32_t n) {
-    const uint64_t pos = s->head.fetch_add(n, std::memory_order_relaxed);
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint64_t a = pos + i;
-        const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
-        if (lap) {                                                      // the slot's previous user (one lap ago) has collected
-            const uint32_t want = (svc_tag(a - SVC_SLOTS) | SVC_COLLECTED) << 16;
-            uint32_t w = 0;
-            while ((s->res[slot].w[3] & 0xffff0000u) != want) cpu_relax(w);
-            std::atomic_thread_fence(std::memory_order_acquire);
-        }
+// Slot reuse.  A caller that draws slot number a (lap = a / SVC_SLOTS of the ring) may overwrite the slot's payload and ready
+// word only when the op one lap earlier is completely over: the dispatcher has consumed its ready word, the GPU has answered it
+// and its caller has collected the answer (svc_release puts SVC_COLLECTED into the answer's tag).  The first two depend on
+// the dispatcher and the GPU alone and are waited for.  The third depends on ANOTHER CALLER — the holder of that ticket, who may
+// itself be inside a submit, waiting for one of our uncollected tickets — so it is never waited for beyond a short spin:
+// the slot is published as a no-op instead (the ring moves on, the uncollected answer stays intact) and the caller is told to
+// collect and come again (AGR_EAGAIN from agr_submit_*; the blocking calls, which hold no tickets, simply take the next slot).
+static bool svc_slot_free(svc_host* s, uint64_t a, uint32_t slot, uint32_t lap) {
+    if (!lap) return true;
+    const uint32_t prev = svc_tag(a - SVC_SLOTS);
+    // usual case: the previous lap's op was a real one and is over (its tag in the cell says all three at once — and the ready
+    // word, which sits in the dispatcher's cache, need not be read)
+    if ((s->res[slot].w[3] >> 16) == (prev | SVC_COLLECTED)) return true;
+    uint32_t w = 0;
+    while (s->scanned.load(std::memory_order_acquire) <= a - SVC_SLOTS) cpu_relax(w);     // its ready word has been consumed
+    const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
+    if ((rw & 3u) != SVC_OP_SKIP) {
+        w = 0;
+        while (((s->res[slot].w[3] >> 16) & 0x7fffu) != prev) cpu_relax(w);                // answered (GPU, or svc_fail_ops)
+    }
+    // the previous lap was a no-op: the cell holds an older answer (or none at all)
+    for (uint32_t k = 0; k < 2000u; ++k) {                                                   // ~0.1 ms of patience
+        const uint32_t t = s->res[slot].w[3] >> 16;
+        if (t == 0u || (t & SVC_COLLECTED)) return true;
+        _mm_pause();
+    }
+    return false;
+}
+// hands ONE operation over.  true: *abs is its slot (ticket); false: the slot it drew was not free (see above).
+static bool svc_submit_one(svc_host* s, uint32_t kind, const void* item, size_t item_bytes, uint64_t* abs) {
+    const uint64_t a = s->head.fetch_add(1, std::memory_order_relaxed);
+    const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
+    const bool ok = svc_slot_free(s, a, slot, lap);
+    if (ok) {
+        std::atomic_thread_fence(std::memory_order_acquire);
         // streaming stores: the slot's lines were last written by another core a lap ago and are read next by the GPU (DMA),
         // so pulling them into this core's cache first (read-for-ownership) would only cost a miss per line
-        {
-            __m128i* dst = reinterpret_cast<__m128i*>(s->payload + (size_t)slot * SVC_PAYLOAD);
-            const __m128i* src = reinterpret_cast<const __m128i*>((const uint8_t*)items + (size_t)i * item_bytes);
-            for (size_t k = 0; k < item_bytes / 16; ++k) _mm_stream_si128(dst + k, _mm_loadu_si128(src + k));
-            _mm_sfence();
-        }
-        s->ready[slot].store(((lap + 1u) << 2) | kind, std::memory_order_release);
+        __m128i* dst = reinterpret_cast<__m128i*>(s->payload + (size_t)slot * SVC_PAYLOAD);
+        const __m128i* src = reinterpret_cast<const __m128i*>(item);
+        for (size_t k = 0; k < item_bytes / 16; ++k) _mm_stream_si128(dst + k, _mm_loadu_si128(src + k));
+        _mm_sfence();
     }
+    s->ready[slot].store(((lap + 1u) << 2) | (ok ? kind : (uint32_t)SVC_OP_SKIP), std::memory_order_release);
     if (s->sleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_one(); }
-    return pos;
+    *abs = a;
+    return ok;
 }
 struct svc_answer { uint32_t w0, w1; uint64_t rid; };
 static inline bool svc_try(svc_host* s, uint64_t a, svc_answer* out) {
@@ -594,31 +620,33 @@ static inline void svc_request_id(agr_handle* h, uint64_t a, uint64_t rid, uint8
 
 static int svc_ingest(agr_handle* h, const agr_record* recs, uint32_t n, agr_verdict* out, uint8_t (*ids)[16], uint64_t* first_rid) {
     svc_host* s = h->svc;
-    const uint64_t pos = svc_submit(s, SVC_OP_RECORD, recs, sizeof(agr_record), n);
+    uint64_t pos[SVC_MAX_CALL];
+    for (uint32_t i = 0; i < n; ++i) while (!svc_submit_one(s, SVC_OP_RECORD, &recs[i], sizeof(agr_record), &pos[i])) {}   // in call order
     int rc = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        svc_answer r; svc_wait(s, pos + i, &r);
+        svc_answer r; svc_wait(s, pos[i], &r);
         if ((r.w0 & 0xffu) == 0u) rc = (int)r.w1;
         else {
             if (out) { memcpy(&out[i], &r.w0, 4); memcpy((uint8_t*)&out[i] + 4, &r.w1, 4); }
-            if (ids) svc_request_id(h, pos + i, r.rid, ids[i]);
+            if (ids) svc_request_id(h, pos[i], r.rid, ids[i]);
             if (i == 0 && first_rid) *first_rid = r.rid;
         }
-        svc_release(s, pos + i);
+        svc_release(s, pos[i]);
     }
     if (rc < 0) return fail(rc, rc == AGR_ENOSPC ? "slab full" : "single-request front end: CUDA error");
     return 0;
 }
 static int svc_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* results) {
     svc_host* s = h->svc;
-    const uint64_t pos = svc_submit(s, SVC_OP_OUTCOME, outs, sizeof(agr_outcome), n);
+    uint64_t pos[SVC_MAX_CALL];
+    for (uint32_t i = 0; i < n; ++i) while (!svc_submit_one(s, SVC_OP_OUTCOME, &outs[i], sizeof(agr_outcome), &pos[i])) {}
     int rc = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        svc_answer r; svc_wait(s, pos + i, &r);
+        svc_answer r; svc_wait(s, pos[i], &r);
         const int32_t res = (int32_t)r.w0;
         if (res < 0 && res != AGR_ENOTFOUND) rc = res;
         if (results) results[i] = res;
-        svc_release(s, pos + i);
+        svc_release(s, pos[i]);
     }
     if (rc < 0) return fail(rc, "single-request front end: CUDA error");
     return 0;
@@ -1118,7 +1146,9 @@ static int submit_one(agr_handle* h, uint32_t kind, const void* item, size_t byt
     if (!h || !item || !ticket) return fail(AGR_EINVAL, "NULL argument");
     svc_host* s = h->svc;
     if (!s) return fail(AGR_EINVAL, "engine was not created with AGR_CFG_COMBINE");
-    *ticket = svc_submit(s, kind, item, bytes, 1) | (kind == SVC_OP_OUTCOME ? TICKET_OUTCOME : 0ULL);
+    uint64_t a = 0;
+    if (!svc_submit_one(s, kind, item, bytes, &a)) return AGR_EAGAIN;   // collect outstanding tickets (agr_poll) and come again
+    *ticket = a | (kind == SVC_OP_OUTCOME ? TICKET_OUTCOME : 0ULL);
     return 0;
 }
 int agr_submit_ingest(agr_handle* h, const agr_record* rec, agr_ticket* ticket) { return submit_one(h, SVC_OP_RECORD, rec, sizeof(agr_record), ticket); }

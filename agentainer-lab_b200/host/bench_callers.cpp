@@ -91,6 +91,7 @@ int main(int argc, char** argv) {
                         memcpy(o.request_id, res.request_id, 16); memcpy(o.agent_id, recs[f.rec].agent_id, AGR_AGENT_ID_BYTES);
                         o.kind = AGR_OUT_RESPONSE; o.http_status = 200; o.seq = n;
                         int rc2;
+                        // AGR_EAGAIN: the slot drawn still holds somebody's uncollected answer; the next draw is another slot
                         while ((rc2 = agr_submit_complete(h, &o, &f.t)) == AGR_EAGAIN) {}
                         if (rc2 < 0) { bad++; stop.store(true); break; }
                         f.stage = 1;

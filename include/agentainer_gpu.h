@@ -44,7 +44,8 @@ extern "C" {
 #define AGR_ECUDA      -6   /* CUDA runtime error (message in agr_last_error) */
 #define AGR_ECAP       -7   /* caller's output array too small; *n holds the needed count */
 #define AGR_ECOMM      -8   /* multi-GPU exchange (NCCL) error */
-#define AGR_EAGAIN      1   /* not an error: agr_poll — the ticket has not been decided yet */
+#define AGR_EAGAIN      1   /* not an error: agr_poll — the ticket has not been decided yet; agr_submit_* — the ring slot drawn still
+                               holds an answer nobody has collected: agr_poll your outstanding tickets, then submit again */
 
 /* ---------------------------------------------------------- record layout */
 /*
@@ -221,8 +222,9 @@ int agr_complete(agr_handle* h, const agr_outcome* outs, uint32_t n, int32_t* re
  * operations as agr_ingest_ex(n = 1) / agr_complete(n = 1), split into "hand it over" and "collect": the goroutine submits,
  * parks on a channel, and a few reaper goroutines collect.  Event order is the front end's: batch by batch.
  *   agr_submit_ingest / agr_submit_complete  copy ONE record / outcome into the pinned request ring and return a ticket at once
- *                                            (at most agr_ring_capacity() tickets may be outstanding per handle: with more, the
- *                                            call waits until the ticket one lap earlier has been collected)
+ *                                            (tickets live in a ring of agr_ring_capacity() slots; AGR_EAGAIN when the slot drawn
+ *                                            still holds an uncollected answer of a lap ago: poll, then submit again.  A submit
+ *                                            never waits for another thread's ticket, so callers cannot deadlock each other)
  *   agr_poll    AGR_OK: *out is filled and the ticket is spent;  AGR_EAGAIN: not decided yet (the ticket stays valid)
  *   agr_wait    the same, spinning until decided (what agr_ingest_ex / agr_complete do internally)
  * A ticket must be collected exactly once.  AGR_EINVAL on an engine created without AGR_CFG_COMBINE. */

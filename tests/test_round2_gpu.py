@@ -1,6 +1,7 @@
 """Round-2 behaviour through the C-ABI: malformed lengths, reserved-but-unfilled rows, log overflow, long outcome chains on
 one record inside one agr_complete batch (against oracle/model.py), the dedupe index after the ring has wrapped, and the
 single-request front end (lock-free ring + resident service kernel) under threads, in both id modes."""
+import os
 import threading
 
 import numpy as np
@@ -293,3 +294,17 @@ def test_reclaim_async_keeps_a_ring_running_one_step_behind(flags):
         assert get(bytes(ids_by_step[-1][7])) is not None        # the last step's records are alive
         assert get(bytes(ids_by_step[10][7])) is None            # long gone: expired, released, row reused
         assert len(eng.list(agent, K.AGR_LIST_PENDING, cap=1 << 14)) <= 4 * per
+
+
+def test_more_tickets_held_than_ring_slots_never_deadlocks():
+    """Callers that together hold MORE uncollected tickets than the request ring has slots (8 threads x 4096 in flight against
+    16384 slots): a submit that draws a slot whose answer nobody has collected must come back with AGR_EAGAIN instead of waiting
+    for that ticket's holder (who may be waiting for ours).  The run has to end, without errors, and make progress."""
+    import json
+    import subprocess
+    exe = os.path.join(os.path.dirname(A.build_host()), "bench_callers")
+    for threads, inflight in ((8, 4096), (12, 256), (8, 512)):
+        res = subprocess.run([exe, str(threads), "1.0", "0", "mint", "64", str(inflight)], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, (threads, inflight, res.stdout[-400:], res.stderr[-400:])
+        d = json.loads(res.stdout.strip().splitlines()[-1])
+        assert d["errors"] == 0 and d["round_trips"] > 0, d
