@@ -728,8 +728,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     } else {
         TRY(dev_alloc(h, &d.slab, (size_t)c.slab_rows * AGR_REC, false));
     }
-    TRY(dev_alloc(h, &d.state, c.slab_rows, true));
-    TRY(dev_alloc(h, &d.route, c.slab_rows, true));
+    TRY(dev_alloc(h, &d.state, c.slab_rows + 4, true));        // (+4: k3_mark reads these two four rows at a time)
+    TRY(dev_alloc(h, &d.route, c.slab_rows + 4, true));
     TRY(dev_alloc(h, &d.aux, c.slab_rows, true));
     TRY(dev_alloc(h, &d.cksum, c.slab_rows, true));
     TRY(dev_alloc(h, &d.table, c.table_slots, true));
@@ -1246,9 +1246,10 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     *total = 0;
     if (hi <= lo) return 0;
     agr_k3_params p{};
-    p.mode = mode; p.slot = slot; p.log = log; p.lo = lo; p.hi = hi;
+    p.mode = mode; p.slot = slot; p.log = log; p.lo = lo; p.hi = hi; p.lo_real = lo;
+    if (mode != K3_LOG_AGENT) p.lo = lo & ~3ull;               // k3_mark reads the row words four rows per lane (16-byte loads)
     p.groups = (mode == K3_TICK) ? std::max<uint32_t>(1, (uint32_t)h->agent_names.size()) : 1;
-    uint64_t items = hi - lo;
+    uint64_t items = hi - p.lo;
     uint64_t max_warps = std::max<uint64_t>(1, (4u << 20) / p.groups);
     uint64_t want = std::min<uint64_t>((uint64_t)h->sm_count * 128, (items + 1023) / 1024);  // several waves of 8-warp CTAs; the column scan runs over per-CTA rows
     p.nwarps = (uint32_t)std::max<uint64_t>(1, std::min(want, max_warps));
@@ -1284,7 +1285,7 @@ static int select_locked(agr_handle* h, int mode, uint32_t slot, const uint32_t*
     *total = h->h_small[0];
     if (mode == K3_TICK) {
         uint32_t m = h->h_small[1];
-        h->scan_lo = (m == AGR_RID_NONE) ? hi : std::max<uint64_t>(h->scan_lo, lo + m);
+        h->scan_lo = (m == AGR_RID_NONE) ? hi : std::max<uint64_t>(h->scan_lo, p.lo + m);
     }
     return 0;
 }

@@ -668,6 +668,44 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
         if (d.ring_rows && q >= d.ring_rows) q -= d.ring_rows;
         return q;
     };
+    // Row modes, aligned run (the host rounds `lo` down to a multiple of 4; ring sizes that are not one take the scalar path): a lane
+    // owns FOUR consecutive rows, so the row words arrive as two 16-byte loads per 128-row group instead of eight 4-byte ones;
+    // the groups of 512 rows are in flight at once.  The selection bits are put together from the lanes' nibbles (three xor-shuffles).
+    const bool vec = rows && ((pb | d.ring_rows | (uint32_t)p.per_warp) & 3u) == 0u;
+    if (vec) {
+        constexpr int NG = 4;
+        uint4 st_v[NG], rt_v[NG]; uint32_t q_v[NG];
+        for (unsigned long long k8 = b; k8 < e; k8 += 128u * NG) {
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const unsigned long long k = k8 + 128u * j + 4u * lane;
+                q_v[j] = prow_of(k);
+                const bool ok = k < e;                                // (e - b and hi need not be multiples of 4: k3_eval checks every row)
+                st_v[j] = ok ? __ldcs(reinterpret_cast<const uint4*>(d.state + q_v[j])) : make_uint4(0u, 0u, 0u, 0u);
+                rt_v[j] = ok ? __ldcs(reinterpret_cast<const uint4*>(d.route + q_v[j])) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const unsigned long long k0 = k8 + 128u * j;
+                if (k0 >= e) break;
+                const uint32_t st4[4] = {st_v[j].x, st_v[j].y, st_v[j].z, st_v[j].w}, rt4[4] = {rt_v[j].x, rt_v[j].y, rt_v[j].z, rt_v[j].w};
+                uint32_t nib = 0u;
+                if (__any_sync(FULL, ((st4[0] | st4[1] | st4[2] | st4[3]) & ST_INQ) != 0u)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const unsigned long long kk = k0 + 4u * lane + i;
+                        if (kk < p.lo_real || kk >= e) continue;
+                        const k3_item it = k3_eval(d, p, kk, q_v[j] + i, st4[i], rt4[i]);
+                        if (it.inq && (uint32_t)(kk - p.lo) < mininq) mininq = (uint32_t)(kk - p.lo);
+                        if (it.sel) { atomicAdd((SMEM ? srow : grow) + ((p.groups == 1) ? 0u : it.slot), 1u); nib |= 1u << i; }
+                    }
+                }
+                uint32_t v = nib << (4u * (lane & 7u));
+                v |= __shfl_xor_sync(FULL, v, 1); v |= __shfl_xor_sync(FULL, v, 2); v |= __shfl_xor_sync(FULL, v, 4);
+                if ((lane & 7) == 0) mask[((k0 - b) >> 5) + (lane >> 3)] = v;
+            }
+        }
+    } else {
     // the row words of eight steps (256 rows) are in flight at once
     constexpr int NS = 8;
     uint32_t st_c[NS], rt_c[NS], pr_c[NS];
@@ -687,13 +725,15 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
             const uint32_t st = st_c[j], rt = rt_c[j], pr = pr_c[j];
             uint32_t selbits = 0u;
             if (!rows || __any_sync(FULL, (st & ST_INQ) != 0u)) {                    // else: nothing pending in these 32 rows
-                const k3_item it = k3_eval(d, p, k0 + lane, pr, st, rt);
+                const bool in = k0 + lane >= p.lo_real;
+                const k3_item it = in ? k3_eval(d, p, k0 + lane, pr, st, rt) : k3_item{false, AGR_RID_NONE, RT_SLOT_NONE, false};
                 if (it.inq && (uint32_t)(k0 + lane - p.lo) < mininq) mininq = (uint32_t)(k0 + lane - p.lo);
                 if (it.sel) atomicAdd((SMEM ? srow : grow) + ((p.groups == 1) ? 0u : it.slot), 1u);   // counting needs no order
                 selbits = __ballot_sync(FULL, it.sel);
             }
             if (lane == 0) mask[(k0 - b) >> 5] = selbits;
         }
+    }
     }
     if (SMEM) {
         __syncwarp();
@@ -717,6 +757,7 @@ __global__ void __launch_bounds__(256) k3_mark(const agr_dev d, const agr_k3_par
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_params p) {
     extern __shared__ uint32_t s_rows[];
+    __shared__ uint16_t s_list[8][1024];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const bool live = w < p.nwarps;
@@ -730,7 +771,7 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
         for (uint32_t g = lane; g < p.groups; g += 32) {
             uint32_t base = p.cta_matrix[(size_t)blockIdx.x * p.groups + g];
             for (uint32_t k = 0; k < (threadIdx.x >> 5); ++k) base += s_rows[(size_t)k * p.groups + g];
-            cur[g] = base;
+            cur[g] = base + p.goff[g];                               // absolute output position of the warp's next item of group g
         }
         __syncwarp();
         srow = cur;
@@ -743,20 +784,35 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
     const uint32_t* mask = p.selmask + (size_t)w * (p.per_warp >> 5);
     const uint32_t pb = rows ? row_physical(d, b) : 0u;
     const uint32_t steps = (uint32_t)((e - b + 31u) >> 5);
+    // A block = 32 selection words = 1024 items.  The set bits are first expanded into a dense list of item offsets (shared memory,
+    // 2 KB per warp), so the rank / claim / store rounds below run on 32 SELECTED items each instead of on 32 items of which a
+    // quarter are selected — and the route word of the next round is in flight while this one is placed.
+    uint16_t* list = s_list[threadIdx.x >> 5];
+    auto fetch = [&](const uint32_t blk_first, const uint32_t i, uint32_t& rid, uint32_t& rt) {
+        const unsigned long long k = b + blk_first + list[i];
+        if (rows) { rid = pb + (uint32_t)(k - b); if (d.ring_rows && rid >= d.ring_rows) rid -= d.ring_rows; }
+        else rid = p.log[k];
+        rt = __ldg(&d.route[rid]);
+    };
     for (uint32_t s0 = 0; s0 < steps; s0 += 32) {
         const uint32_t mine = (s0 + lane < steps) ? mask[s0 + lane] : 0u;          // 32 steps' selection words in one load
-        uint32_t live = __ballot_sync(FULL, mine != 0u);
-        while (live) {
-            const int j = __ffs(live) - 1; live &= live - 1u;
-            const uint32_t bits = __shfl_sync(FULL, mine, j);
-            const unsigned long long k = b + ((unsigned long long)(s0 + j) << 5) + lane;
-            const bool sel = (bits >> lane) & 1u;
-            uint32_t rid = AGR_RID_NONE, slot = 0u;
-            if (sel) {
-                if (rows) { rid = pb + (uint32_t)(k - b); if (d.ring_rows && rid >= d.ring_rows) rid -= d.ring_rows; }
-                else rid = p.log[k];
-                slot = rt_slot(d.route[rid]);
-            }
+        if (!__any_sync(FULL, mine != 0u)) continue;
+        const uint32_t c = (uint32_t)__popc(mine);
+        uint32_t incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        {
+            uint32_t o = incl - c, m = mine;
+            while (m) { const int bit = __ffs(m) - 1; m &= m - 1u; list[o++] = (uint16_t)(lane * 32 + bit); }
+        }
+        __syncwarp();
+        uint32_t rid_n = AGR_RID_NONE, rt_n = 0u;
+        if ((uint32_t)lane < total) fetch(s0 << 5, lane, rid_n, rt_n);
+        for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+            const bool sel = i0 + lane < total;
+            const uint32_t rid = rid_n, slot = rt_slot(rt_n);
+            if (i0 + 32u + lane < total) fetch(s0 << 5, i0 + 32u + lane, rid_n, rt_n);
             const uint32_t g = (p.groups == 1) ? 0u : slot;
             const uint32_t key = sel ? g : (0x80000000u | (uint32_t)lane);
             const uint32_t peers = __match_any_sync(FULL, key);
@@ -766,10 +822,11 @@ __global__ void __launch_bounds__(256) k3_place(const agr_dev d, const agr_k3_pa
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd((SMEM ? srow : grow) + g, (uint32_t)__popc(peers));
                 base = __shfl_sync(peers, base, leader);
-                const uint32_t pos = p.goff[g] + base + __popc(peers & ((1u << lane) - 1u));
+                const uint32_t pos = (SMEM ? 0u : p.goff[g]) + base + __popc(peers & ((1u << lane) - 1u));
                 if (pos < p.cap) p.out_rid[pos] = rid;              // (the agent slot is one load away for whoever needs it: route[rid])
             }
         }
+        __syncwarp();                                                // the list is rewritten by the next block
     }
 }
 

@@ -85,7 +85,8 @@ struct agr_k3_params {
     int mode;
     uint32_t slot;             // agent for the single-agent modes
     const uint32_t* log;       // K3_LOG_AGENT: source log
-    unsigned long long lo, hi; // item range [lo, hi): rids or log positions
+    unsigned long long lo, hi; // item range [lo, hi): rids or log positions (row modes: lo rounded down to a multiple of 4)
+    unsigned long long lo_real; // first item that counts (items in [lo, lo_real) are skipped)
     uint32_t groups;           // matrix columns: max agent slot + 1 (TICK) or 1
     uint32_t nwarps;           // matrix rows
     uint32_t per_warp;         // items per warp chunk (multiple of 32)
