@@ -58,6 +58,8 @@ struct agr_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;        // H2D of chunk k+1 overlaps K1 of chunk k (agr_ingest pipeline)
     std::vector<cudaEvent_t> chunk_ev;
+    cudaStream_t d2h_stream = nullptr;         // verdicts / ids of chunk k go back while chunk k+1 comes in (PCIe is full duplex)
+    std::vector<cudaEvent_t> out_ev;
     agr_verdict* d_verdicts = nullptr;         // [max_batch], written by k1_post
     agr_verdict* h_verdicts = nullptr;         // pinned [max_batch]
     uint8_t* d_ids = nullptr;                  // [max_batch][16] Request.ID per record (agr_ingest_ex)
@@ -67,6 +69,7 @@ struct agr_handle {
     uint64_t tail = 0;        // ring: first logical row that has not been released
     uint32_t* d_log_scratch = nullptr; uint32_t* d_lc_chunks = nullptr;   // ring: log compaction
     uint64_t released_total = 0;
+    uint32_t* d_reclaim_scratch = nullptr;                        // k_first_live: {offset found, ticket}
     uint8_t* d_reclaim = nullptr; uint8_t* h_reclaim = nullptr;   // agr_reclaim's scan result (device scratch / pinned copy)
     cudaEvent_t reclaim_ev = nullptr; bool reclaim_pending = false; uint64_t reclaim_bound = 0;
     uint32_t* dupfix_base = nullptr; uint32_t batch_phase = 0;   // two sets of per-batch words, used alternately
@@ -713,6 +716,7 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     h->cfg = c;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     agr_dev& d = h->d;
     const bool varlen = (c.flags & AGR_CFG_VARLEN) != 0;
     if (varlen) {
@@ -792,6 +796,8 @@ static int create_impl(const agr_config* cfg_in, agr_handle* h) {
     TRY(host_alloc(h, &h->h_results, c.max_batch));
     TRY(host_alloc(h, &h->h_small, (size_t)64));
     TRY(dev_alloc(h, &h->d_reclaim, (size_t)64, true));
+    TRY(dev_alloc(h, &h->d_reclaim_scratch, (size_t)2, false));
+    { const uint32_t init[2] = {0xffffffffu, 0u}; CK(cudaMemcpyAsync(h->d_reclaim_scratch, init, 8, cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); }
     TRY(host_alloc(h, &h->h_reclaim, (size_t)64));
     TRY(dev_alloc(h, &h->d_ops, (size_t)16, false));
     TRY(dev_alloc(h, &h->d_hrid, (size_t)16, false));
@@ -827,6 +833,8 @@ void agr_destroy(agr_handle* h) {
     for (auto e : h->chunk_ev) cudaEventDestroy(e);
     if (h->reclaim_ev) cudaEventDestroy(h->reclaim_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    for (auto e : h->out_ev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1129,11 +1137,17 @@ static int ingest_ex_locked(agr_handle* h, const agr_record* recs, uint32_t n, a
         CK(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->chunk_ev[c], 0));
         TRY(launch_k1_locked(h, first + off, cn, out ? h->d_verdicts + off : nullptr, ids ? h->d_ids + (size_t)off * 16 : nullptr));
+        if (out || ids) {
+            // the chunk's read-backs (8 + 16 B per record) leave on their own stream as soon as its K1 is done
+            while (h->out_ev.size() <= c) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->out_ev.push_back(e); }
+            CK(cudaEventRecord(h->out_ev[c], h->stream));
+            CK(cudaStreamWaitEvent(h->d2h_stream, h->out_ev[c], 0));
+            if (out) CK(cudaMemcpyAsync((out_pinned ? out : h->h_verdicts) + off, h->d_verdicts + off, (size_t)cn * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (ids) CK(cudaMemcpyAsync((ids_pinned ? (uint8_t*)ids : h->h_ids) + (size_t)off * 16, h->d_ids + (size_t)off * 16, (size_t)cn * 16, cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
     }
-    // the read-backs are small (8 + 16 B per record): one copy each, after the last K1
-    if (out) CK(cudaMemcpyAsync(out_pinned ? out : h->h_verdicts, h->d_verdicts, (size_t)n * sizeof(agr_verdict), cudaMemcpyDeviceToHost, h->stream));
-    if (ids) CK(cudaMemcpyAsync(ids_pinned ? (uint8_t*)ids : h->h_ids, h->d_ids, (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (out || ids) CK(cudaStreamSynchronize(h->d2h_stream));
     if (out && !out_pinned) memcpy(out, h->h_verdicts, (size_t)n * sizeof(agr_verdict));
     if (ids && !ids_pinned) memcpy(ids, h->h_ids, (size_t)n * 16);
     return 0;
@@ -1884,8 +1898,8 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
     if (!h) return fail(AGR_EINVAL, "NULL argument");
     HLock lk(h);
     CK(cudaSetDevice(h->device));
-    unsigned long long* d_cnt = (unsigned long long*)(h->d.ctr + C_NCTR - 1);     // last counter slot as scratch
-    CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
+    unsigned long long* d_cnt = expired ? (unsigned long long*)(h->d.ctr + C_NCTR - 1) : nullptr;     // last counter slot as scratch
+    if (d_cnt) CK(cudaMemsetAsync(d_cnt, 0, 8, h->stream));
     sync_window(h);
     if ((!is_ring(h) || (h->cfg.flags & AGR_CFG_VARLEN)) && h->rows_used > h->sweep_clean) {
         // append-only slabs and variable-length engines: K1 does not keep the chunks' time bounds (k1_note_time); the chunks that
@@ -1918,15 +1932,12 @@ int agr_expire(agr_handle* h, uint64_t now, uint64_t ttl, uint64_t* expired) {
 struct reclaim_result { uint32_t off, pad; unsigned long long lens[2]; unsigned long long voff; };
 
 // enqueues the scan: first stored row behind the tail (k_first_live), the log lengths and — variable-length mode — the byte
-// offset of that row's record, packed by one tiny kernel and copied to pinned memory; nothing waits here
+// offset of that row's record, packed by the scan's last CTA straight into pinned memory; nothing waits here
 static int reclaim_scan_launch(agr_handle* h, uint64_t bound) {
     sync_window(h);
-    uint32_t* d_off = h->d_min_inq;                                            // 4-byte scratch
-    CK(cudaMemsetAsync(d_off, 0xff, 4, h->stream));
-    agr_launch_first_live(h->d, bound - h->tail, d_off, h->stream);
-    agr_launch_reclaim_pack(h->d, d_off, h->d_reclaim, h->stream);
+    // (the scan's two scratch words re-arm themselves, and its last CTA writes the result into the pinned buffer: one launch)
+    agr_launch_first_live(h->d, bound - h->tail, is_ring(h) && !(h->cfg.flags & AGR_CFG_VARLEN), h->d_reclaim_scratch, h->h_reclaim, h->stream);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_reclaim, h->d_reclaim, sizeof(reclaim_result), cudaMemcpyDeviceToHost, h->stream));
     if (!h->reclaim_ev) CK(cudaEventCreateWithFlags(&h->reclaim_ev, cudaEventDisableTiming));
     CK(cudaEventRecord(h->reclaim_ev, h->stream));
     h->reclaim_bound = bound;

@@ -59,6 +59,8 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
     if (threadIdx.x < WARPS * STAGES) mbar_init(smem_u32(&bars[threadIdx.x]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // k1_post is launched as a programmatic dependent: its CTAs may be scheduled as ours retire (it waits for this grid to complete)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
 
     uint32_t lc[K1_NLC + 1];
@@ -145,7 +147,12 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
         }
 #pragma unroll
         for (int q = 0; q < STAGES; ++q) if (s == q) tile_of[q] = next_tile;
-        if (valid) d.cksum[rid] = agr_cksum_pack(c0, c1);
+        if (valid) {
+            d.cksum[rid] = agr_cksum_pack(c0, c1);
+            // a ring sweeps every step: the row's last-SET time (= created_at, requests.go:106) goes into the word the sweep streams,
+            // so k_expire never has to fetch created_at out of the 512 B records (one 32 B sector per row)
+            if (d.cfg_flags & AGR_CFG_RING) d.mtime[rid] = pack64(h4.x, h4.y);
+        }
         k1_note_time(d, first_rid + tile * TILE_RECS, min(TILE_RECS, n - tile * TILE_RECS), valid ? pack64(h4.x, h4.y) : ~0ULL);
         // previous tile: its CAS has had a full tile to come back
         if (it) {                                                 // (warp-uniform: every lane has a previous tile or none has)

@@ -10,6 +10,23 @@
 // All arithmetic is integer / byte work bounded by HBM bandwidth; there is no tensor-core work on this path.
 #include "agr_device.cuh"
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be scheduled while its predecessor in the stream
+// is still draining, once every CTA of the predecessor has executed pdl_trigger() (or exited); it must not touch anything the
+// predecessor writes before pdl_wait() returns, which is when the predecessor has completed and its writes are visible.  Used
+// on the chain of short maintenance kernels of a ring step (TTL sweep -> release -> tail scan): their launch latencies overlap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // v0: each warp owns 32 consecutive records.  Pass 1: lane i loads the 96 B header of record i (six 16 B loads,
 // every fetched sector fully used) and runs the decision chain thread-per-record, so 32 index inserts are in
 // flight per warp.  Pass 2: the warp streams the 416 B payloads coalesced (lane l = 16 B chunk l) for the record
@@ -74,6 +91,7 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
             d.state[rid] = r.state;
             d.route[rid] = r.route;
             d.cksum[rid] = agr_cksum_pack(c0, c1);
+            if (d.cfg_flags & AGR_CFG_RING) d.mtime[rid] = pack64(h4.x, h4.y);          // (see agr_k1_tma.cu)
         }
     }
     k1_flush_counters(d, lc, s_ctr);
@@ -89,6 +107,8 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 //       later row of the same batch) is promoted to stored.
 __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts,
                                                uint4* __restrict__ ids, const uint32_t* __restrict__ marks) {
+    pdl_wait();                                     // (launched as a programmatic dependent of the K1 kernel: nothing before this line reads its output)
+    pdl_trigger();
     const uint32_t dupfix = __ldcg(d.dupfix);
     if (blockIdx.x == 0 && threadIdx.x < 4) d.dupfix_next[threadIdx.x] = 0;      // the previous batch is done with these words
     // nothing to do: no in-batch id races, no replay-flagged records to resolve, nobody asked for verdicts or ids
@@ -198,6 +218,8 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
                                                 const unsigned long long ttl, unsigned long long* __restrict__ expired) {
     __shared__ unsigned long long s_min[8];
     __shared__ uint32_t s_cnt;
+    pdl_trigger();
+    pdl_wait();
     const uint32_t c = blockIdx.x;
     const unsigned long long cm = d.cmin[c];
     if (cm == ~0ULL) return;
@@ -241,50 +263,74 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int w = 1; w < 8; ++w) if (s_min[w] < lmin) lmin = s_min[w];
-        if (s_cnt) atomicAdd(expired, (unsigned long long)s_cnt);
+        if (s_cnt && expired) atomicAdd(expired, (unsigned long long)s_cnt);
         d.cmin[c] = (lmin == 0ULL) ? 1ULL : lmin;               // exact now (~0: the chunk holds no stored row any more)
     }
 }
 void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
                        unsigned long long* expired, cudaStream_t st) {
-    if (rows) k_expire<<<(unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, rows, now, ttl, expired);
+    if (rows) launch_pdl(k_expire, (unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256u, st, d, rows, now, ttl, expired);
 }
 // ---- ring mode (AGR_CFG_RING): releasing rows at the tail
-// offset (from the tail) of the first row that still holds a stored record, among the `live` rows behind the tail.  Blocks
-// walk the window in order; a block that starts behind an offset already found has nothing to add and leaves at once.
-__global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsigned long long live, uint32_t* __restrict__ out_off) {
-    const unsigned long long b0 = (unsigned long long)blockIdx.x * AGR_CHUNK_ROWS;
-    if (*reinterpret_cast<volatile uint32_t*>(out_off) < b0) return;
-    uint32_t st[EXP_PER_THREAD];
+// offset (from the tail) of the first row that still holds a stored record, among the `live` rows behind the tail.
+// One CTA per PHYSICAL chunk of the ring (the chunks of the TTL sweep).  A chunk that lies behind an offset already found has
+// nothing to add; with use_cmin (fixed-stride ring: K1 and K2 keep the chunk bounds current) a chunk whose bound says "no stored
+// row" costs one 8-byte load — after a sweep that is every chunk up to the one the answer lies in.
+// The last CTA to finish packs what agr_reclaim needs on the host into one 32-byte record — the offset found, both log lengths
+// and (variable-length mode) the byte offset of the first live row's record — writes it straight into the pinned host buffer
+// `out`, and re-arms the two scratch words (offset = "none", ticket = 0) for the next scan: no memset, no copy, one launch.
+__global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsigned long long live, const uint32_t use_cmin,
+                                                    uint32_t* __restrict__ scratch /* [0] offset found, [1] ticket */,
+                                                    unsigned long long* __restrict__ out) {
+    __shared__ uint32_t s_last;
+    pdl_wait();
+    uint32_t* out_off = scratch;
+    const unsigned long long R = d.ring_rows, tp = d.tail_phys;
+    const unsigned long long p0 = (unsigned long long)blockIdx.x * AGR_CHUNK_ROWS;
+    const bool holds_tail = tp >= p0 && tp < p0 + AGR_CHUNK_ROWS;
+    const unsigned long long kmin = holds_tail ? 0ULL : (p0 + R - tp) % R;      // smallest offset of a row of this chunk
+    bool work = kmin < live && *reinterpret_cast<volatile uint32_t*>(out_off) >= kmin;
+    if (work && use_cmin && d.cmin[blockIdx.x] == ~0ULL) work = false;
+    if (work) {
+        uint32_t st[EXP_PER_THREAD];
+        unsigned long long kk[EXP_PER_THREAD];
 #pragma unroll
-    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
-        const unsigned long long k = b0 + threadIdx.x + q * 256u;
-        st[q] = k < live ? d.state[row_physical(d, d.tail + k)] : 0u;
+        for (uint32_t q = 0; q < EXP_PER_THREAD; ++q) {
+            const unsigned long long p = p0 + threadIdx.x + q * 256u;
+            kk[q] = (p >= tp) ? p - tp : p + R - tp;
+            st[q] = (p < R && kk[q] < live) ? d.state[p] : 0u;
+        }
+        uint32_t mine = 0xffffffffu;
+#pragma unroll
+        for (uint32_t q = 0; q < EXP_PER_THREAD; ++q)
+            if ((st[q] & ST_STORED) && (uint32_t)kk[q] < mine) mine = (uint32_t)kk[q];
+        mine = __reduce_min_sync(FULL, mine);
+        if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
     }
-    uint32_t mine = 0xffffffffu;
-#pragma unroll
-    for (uint32_t q = 0; q < EXP_PER_THREAD; ++q)
-        if ((st[q] & ST_STORED) && mine == 0xffffffffu) mine = (uint32_t)(b0 + threadIdx.x + q * 256u);
-    mine = __reduce_min_sync(FULL, mine);
-    if ((threadIdx.x & 31) == 0 && mine != 0xffffffffu) atomicMin(out_off, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(scratch + 1, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t o = *reinterpret_cast<volatile uint32_t*>(out_off);
+        out[1] = d.log_len[0]; out[2] = d.log_len[1];
+        out[3] = (d.voff && o != 0xffffffffu) ? d.voff[row_physical(d, d.tail + o)] : 0ULL;
+        out[0] = o;
+        scratch[0] = 0xffffffffu; scratch[1] = 0u;
+    }
 }
-// packs what agr_reclaim needs on the host into one 32-byte record: the offset found, both log lengths, and (variable-length
-// mode) the byte offset of the first live row's record
-__global__ void k_reclaim_pack(const agr_dev d, const uint32_t* __restrict__ off, unsigned long long* __restrict__ out) {
-    const uint32_t o = *off;
-    out[0] = o;
-    out[1] = d.log_len[0]; out[2] = d.log_len[1];
-    out[3] = (d.voff && o != 0xffffffffu) ? d.voff[row_physical(d, d.tail + o)] : 0ULL;
-}
-void agr_launch_reclaim_pack(const agr_dev& d, const uint32_t* off, void* out, cudaStream_t st) {
-    k_reclaim_pack<<<1, 1, 0, st>>>(d, off, (unsigned long long*)out);
-}
-void agr_launch_first_live(const agr_dev& d, unsigned long long live, uint32_t* out_off, cudaStream_t st) {
-    if (live) k_first_live<<<(unsigned)((live + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, live, out_off);
+void agr_launch_first_live(const agr_dev& d, unsigned long long live, bool use_cmin, uint32_t* scratch, void* out, cudaStream_t st) {
+    launch_pdl(k_first_live, (unsigned)((d.ring_rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256u, st, d, live, use_cmin ? 1u : 0u, scratch,
+               (unsigned long long*)out);
 }
 // rows tail .. tail + count go back to the pool: every per-row word reads "no record"
 __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uint32_t count, uint32_t* __restrict__ resp_len,
                                                       uint32_t* __restrict__ resp_hlen, uint32_t* __restrict__ err_len) {
+    pdl_trigger();
+    pdl_wait();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const uint32_t p = row_physical(d, d.tail + k);
@@ -292,7 +338,7 @@ __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uin
     resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;      // (the chunk's time bound stays a valid lower bound of what is left)
 }
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
-    if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
+    if (count) launch_pdl(k_release_rows, (count + 255u) / 256u, 256u, st, d, count, resp_len, resp_hlen, err_len);
 }
 // how far back from the byte slab's head (physical offset `head`) the oldest blob lies that a live row still refers to
 __global__ void __launch_bounds__(256) k_bytes_span(const agr_dev d, const unsigned long long head, const unsigned long long cap,
@@ -425,7 +471,7 @@ cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& 
 
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids,
                         const uint32_t* marks) {
-    if (n) k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, marks);
+    if (n) launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, marks);
 }
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
@@ -436,7 +482,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, d.marks);
+        launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, (const uint32_t*)d.marks);
         return;
     }
     constexpr int WARPS = 8;
@@ -447,7 +493,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
     if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, nullptr);
+    launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, (const uint32_t*)nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K2

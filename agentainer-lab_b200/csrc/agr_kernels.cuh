@@ -163,8 +163,7 @@ void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long 
                        unsigned long long* expired, cudaStream_t st);
 // ring mode: first live (STORED) row at or after the tail, as an offset from it (0xffffffff: none), then release of
 // `count` rows from the tail and stable compaction of a log (entries of released rows drop out)
-void agr_launch_first_live(const agr_dev& d, unsigned long long live, uint32_t* out_off, cudaStream_t st);
-void agr_launch_reclaim_pack(const agr_dev& d, const uint32_t* off, void* out /* 32 B */, cudaStream_t st);
+void agr_launch_first_live(const agr_dev& d, unsigned long long live, bool use_cmin, uint32_t* scratch, void* out_host, cudaStream_t st);
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st);
 void agr_launch_bytes_span(const agr_dev& d, unsigned long long head, unsigned long long cap, const unsigned long long* resp_off,
                            const uint32_t* resp_len, const unsigned long long* err_off, const uint32_t* err_len, unsigned long long* span,

@@ -322,7 +322,7 @@ def measure_sustained(A, K, torch, local_rank, variant, steps=48):
     synth = dict(seed=11, n_agents=256, agent_nanos0=nanos0)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local_rank))
     warm = 10
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(4)) for _ in range(steps)]
     released = 0
     for s in range(warm + steps):
         first = eng.reserve_rows(B)
@@ -330,18 +330,24 @@ def measure_sustained(A, K, torch, local_rank, variant, steps=48):
         if s >= warm:
             evs[s - warm][0].record(stream)
         eng.ingest_rows_async(first, B)
-        eng.expire((s + 1) * B, 4 * B, want_count=False)           # enqueue the TTL sweep ...
-        released += eng.reclaim_async()                             # ... release what the previous step's scan found, start the next scan
         if s >= warm:
             evs[s - warm][1].record(stream)
+        eng.expire((s + 1) * B, 4 * B, want_count=False)           # enqueue the TTL sweep ...
+        if s >= warm:
+            evs[s - warm][2].record(stream)
+        released += eng.reclaim_async()                             # ... release what the previous step's scan found, start the next scan
+        if s >= warm:
+            evs[s - warm][3].record(stream)
     eng.sync(); torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    ms = sum(e[0].elapsed_time(e[3]) for e in evs) / steps
+    parts = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / steps for k in range(3)]
     st = eng.stats()
     assert st["stored"] == (warm + steps) * B and st["rows_used"] == (warm + steps) * B, st
     assert st["rows_used"] - st["rows_tail"] <= R and released >= (warm + steps - 6) * B, (st, released)
     eng.close()
     return {"records_per_step": B, "ring_rows": R, "steps": steps, "laps": (warm + steps) * B / R, "ms_per_step": ms,
             "requests_per_s": B / (ms * 1e-3), "rows_released": released,
+            "ms_by_call": {"ingest (K1 + k1_post)": parts[0], "agr_expire": parts[1], "agr_reclaim_async": parts[2]},
             "what": "K1 + agr_expire (TTL sweep: per-chunk time bounds, only due chunks are read) + agr_reclaim_async (release of 1 M rows, one step behind, no host wait) per step, device time"}
 
 
