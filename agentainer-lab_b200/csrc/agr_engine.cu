@@ -141,7 +141,7 @@ struct agr_handle {
     agr_verdict* d_vback = nullptr;            // verdicts returned by owners, owner-major [max_batch]
     agr_verdict* d_vout = nullptr;             // caller-order verdicts [max_batch]
     // AGR_CFG_TIMING: CUDA-event pairs around the dominant K1 kernel, on the launching stream
-    std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0;
+    std::vector<cudaEvent_t> tev; uint64_t tev_next = 0, tev_read = 0, timing_calls = 0;
     cudaEvent_t op_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [0,1] last K2 group, [2,3] last K3 select group, [4,5] last K5 encode
     bool op_timed[3] = {false, false, false};
 };
@@ -991,7 +991,10 @@ static int launch_k1_locked(agr_handle* h, uint64_t first, uint32_t n, agr_verdi
     sync_window(h);
     flip_batch_words(h);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->cfg.flags & AGR_CFG_TIMING) {
+    // AGR_CFG_TIMING: events around the K1 kernel of every launch, or of every k-th one (k1_variant bits 16..23): an event record
+    // is a stream operation of its own between two kernels, and two of them per step cost a back-to-back loop a few microseconds
+    const uint32_t tstride = std::max<uint32_t>(1u, (h->cfg.k1_variant >> 16) & 0xffu);
+    if ((h->cfg.flags & AGR_CFG_TIMING) && (h->timing_calls++ % tstride) == 0) {
         if (h->tev.empty()) {
             h->tev.resize(2 * AGR_TIMING_RING);
             for (auto& e : h->tev) CK(cudaEventCreate(&e));
@@ -2373,6 +2376,7 @@ int agr_kernel_time(agr_handle* h, double* sum_ms, uint64_t* launches) {
         *sum_ms += ms; (*launches)++;
     }
     h->tev_read = h->tev_next;
+    h->timing_calls = 0;                       // the next launch is a timed one again (stride, k1_variant bits 16..23)
     return 0;
 }
 

@@ -275,7 +275,7 @@ def run_reference(args, wl, rank, world):
 def measure_resident(A, K, torch, dist, args, wl, rank, local_rank, extra_flags, steps, warmup):
     """Device-resident K1 measurement on a fresh engine: records pre-generated in the slab, `steps` timed launches."""
     B = wl["records"]
-    eng = A.Engine(device=local_rank, slab_rows=(warmup + steps) * B, max_agents=1024, max_batch=B, k1_variant=args.variant,
+    eng = A.Engine(device=local_rank, slab_rows=(warmup + steps) * B, max_agents=1024, max_batch=B, k1_variant=args.variant | (args.timing_stride << 16),
                    flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | extra_flags)
     nanos0 = 1700000000000000000 + rank * 10_000_000_000
     for k in range(wl["agents"]):
@@ -510,7 +510,7 @@ def run_ours(args, wl, rank, world, local_rank):
     e_steps, e_warm = min(S, args.e2e_steps), 1
     rows = max(args.rows, (W + S) * B + (e_warm + e_steps) * B + (B if world > 1 else 0) * 2)
     id_flags = K.AGR_CFG_MINT_IDS if args.id_mode == "mint" else 0
-    eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant,
+    eng = A.Engine(device=local_rank, slab_rows=rows, max_agents=1024, max_batch=B, k1_variant=args.variant | (args.timing_stride << 16),
                    flags=K.AGR_CFG_PERSISTENCE | K.AGR_CFG_TIMING | args.diag_flags | id_flags)
     nanos0 = 1700000000000000000 + rank * 10_000_000_000        # each rank (shard) owns its own agent ids
     for k in range(wl["agents"]):
@@ -702,8 +702,9 @@ def run_ours(args, wl, rank, world, local_rank):
                                                    if id_flags else " (caller-supplied random ids in a 32 B/slot dedupe index)")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src,
-                         "kernel": "k1_ingest", "kernel_ms": k_avg, "launches_timed": k_n, "algorithmic_bytes_per_record": ALG_BYTES_PER_RECORD,
-                         "peak_source": peak_src},
+                         "kernel": "k1_ingest", "kernel_ms": k_avg, "launches_timed": k_n, "launches_in_timed_region": S,
+                         "timing": f"CUDA events on the engine's stream around the K1 kernel of every {max(1, args.timing_stride)}-th launch of the timed region (an event pair per launch costs the back-to-back loop ~5 us a step)" if args.timing_stride > 1 else "CUDA events on the engine's stream around the K1 kernel of every launch of the timed region",
+                         "algorithmic_bytes_per_record": ALG_BYTES_PER_RECORD, "peak_source": peak_src},
             "e2e": {"value": world * B / (e_ms * 1e-3), "unit": "requests/s", "h2d_bytes_per_step": B * 512, "d2h_bytes_per_step": B * 24,
                     "steps": len(e_times), "ms_per_step": e_ms, "api": "agr_ingest_ex (pinned host records in; verdicts + Request.IDs out)",
                     "host_cpus_local_to_gpu": local_cpus},
@@ -911,6 +912,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "c5"])
     ap.add_argument("--variant", type=lambda x: int(x, 0), default=0)
+    ap.add_argument("--timing-stride", type=int, default=8, help="CUDA events around the K1 kernel of every k-th launch of the timed region (1 = every launch)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exchange", action="store_true")
