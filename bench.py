@@ -67,6 +67,23 @@ def k1_traffic(mode, variant):
         return None, "no committed ncu capture for this mode"
 
 
+def init_nccl_quietly(dist, torch, local_rank):
+    """NCCL prints its version banner to STDOUT when the first communicator comes up; the contract is ONE JSON line there, so
+    file descriptor 1 points at stderr while torch.distributed creates its communicator (eagerly: device_id is given)."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+
 def run_callers(local_rank, seconds=2.0):
     """e2e_callers: the reference's real call pattern (one request per call, server.go:493) through the C-ABI, measured by the
     C++ driver host/bench_callers in its own process: blocking agr_ingest_ex(n=1) + agr_complete(n=1) from T OS threads, and
@@ -403,7 +420,7 @@ def run_c4(args, rank, world, local_rank):
     from agentainer_lab_b200.sharding import owned_agents, make_rank_batch
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl_quietly(dist, torch, local_rank)
     else:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
         dist.init_process_group("gloo", rank=0, world_size=1)
@@ -501,7 +518,7 @@ def run_ours(args, wl, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl_quietly(dist, torch, local_rank)
     local_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     sampler = ClockSampler(local_rank)
@@ -771,7 +788,7 @@ def run_c5(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl_quietly(dist, torch, local_rank)
     local_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     n, na, W = 1 << 18, 256, max(3, args.warmup)
