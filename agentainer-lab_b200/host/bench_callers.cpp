@@ -92,7 +92,8 @@ int main(int argc, char** argv) {
                         o.kind = AGR_OUT_RESPONSE; o.http_status = 200; o.seq = n;
                         int rc2;
                         // AGR_EAGAIN: the slot drawn still holds somebody's uncollected answer; the next draw is another slot
-                        while ((rc2 = agr_submit_complete(h, &o, &f.t)) == AGR_EAGAIN) {}
+                        while ((rc2 = agr_submit_complete(h, &o, &f.t)) == AGR_EAGAIN && !stop.load(std::memory_order_relaxed)) {}
+                        if (rc2 == AGR_EAGAIN) break;                      // the run is over: this request stays forwarded-but-uncompleted
                         if (rc2 < 0) { bad++; stop.store(true); break; }
                         f.stage = 1;
                         push(f);

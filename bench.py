@@ -120,9 +120,14 @@ h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
 get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
 out = open(sys.argv[2], "w", buffering=1)
 print("max", N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), file=out)
+import os
+parent, t_end, k = int(sys.argv[3]), time.time() + 600.0, 0
 while True:
     print("%.6f" % time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), get_reasons(h), file=out)
     time.sleep(0.0002)
+    k += 1
+    if k % 512 == 0 and (os.getppid() != parent or time.time() > t_end):    # never outlive the bench (a killed parent cannot stop us)
+        break
 """
 
 
@@ -139,7 +144,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(self.index), self.path],
+            self.proc = subprocess.Popen([sys.executable, "-c", SAMPLER_SRC, str(self.index), self.path, str(os.getpid())],
                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

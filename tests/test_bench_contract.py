@@ -74,3 +74,40 @@ def test_gpu_arm_line():
     assert "sm_mhz" in d["clocks"] and isinstance(d["clocks"]["reasons"], list)
     for k in ("k2_complete", "k3_replay_scan", "k5_json", "sustained_ring"):
         assert k in d["secondary_kernels"]
+
+
+def test_nccl_banner_is_kept_off_stdout(tmp_path):
+    """N > 1: NCCL prints its version banner to file descriptor 1 when torch.distributed creates the communicator; bench.py
+    points fd 1 at stderr for that moment and restores it (ONE JSON line on stdout).  Checked with a stand-in for
+    torch.distributed in a child process whose stdout is a file."""
+    code = r'''
+import os, sys
+sys.path.insert(0, %r)
+import bench
+class Dist:
+    def init_process_group(self, backend, device_id=None):
+        os.write(1, b"NCCL version 0.0.0+test\n")          # what libnccl does: a raw write to fd 1
+    def barrier(self): pass
+class Cuda:
+    def synchronize(self): pass
+class Torch:
+    cuda = Cuda()
+    def device(self, *a): return None
+print("before")
+bench.init_nccl_quietly(Dist(), Torch(), 0)
+print("after")
+''' % ROOT
+    out, err = tmp_path / "out.txt", tmp_path / "err.txt"
+    with open(out, "w") as fo, open(err, "w") as fe:
+        res = subprocess.run([sys.executable, "-c", code], stdout=fo, stderr=fe, timeout=120, cwd=ROOT)
+    assert res.returncode == 0, err.read_text()
+    assert out.read_text().split() == ["before", "after"]
+    assert "NCCL version" in err.read_text()
+
+
+def test_clock_sampler_source_is_valid_and_self_terminating():
+    import ast
+    sys.path.insert(0, ROOT)
+    import bench
+    ast.parse(bench.SAMPLER_SRC)
+    assert "getppid" in bench.SAMPLER_SRC                           # a killed bench must not leave an NVML poller behind
