@@ -310,6 +310,7 @@ static inline void cpu_relax(uint32_t& spins) {
     else { sched_yield(); }
 }
 
+static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only);
 // stops the resident kernel; the caller holds h->mu, so no new batch can be published meanwhile
 static int svc_stop_locked(agr_handle* h) {
     svc_host* s = h->svc;
@@ -323,7 +324,16 @@ static int svc_stop_locked(agr_handle* h) {
     s->cyc[0] += (double)s->ctl->cyc_wait; s->cyc[1] += (double)s->ctl->cyc_load; s->cyc[2] += (double)s->ctl->cyc_work; s->cyc[3] += (double)s->ctl->cyc_publish;
     s->polls += s->ctl->heartbeat;
     if (e != cudaSuccess) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, std::string("service kernel: ") + cudaGetErrorString(e)); }
-    if (s->ctl->done_seq != s->seq) { s->fatal = AGR_ECUDA; return fail(AGR_ECUDA, "service kernel left with batches unprocessed"); }
+    if (s->ctl->done_seq != s->seq) {
+        // (cannot happen while the dispatcher runs: it stops the kernel after 2 ms without traffic, the kernel's own idle exit is 2 s)
+        // whoever waits for an operation of those batches gets an error instead of waiting for ever
+        for (uint64_t q = s->ctl->done_seq + 1; q <= s->seq; ++q) {
+            const svc_desc* dsc = s->desc + (q % SVC_DESCS);
+            if (dsc->seq == q) svc_fail_ops(s, dsc->from, dsc->from + dsc->count, AGR_ECUDA, false);
+        }
+        s->fatal = AGR_ECUDA;
+        return fail(AGR_ECUDA, "service kernel left with batches unprocessed");
+    }
     return 0;
 }
 static int svc_start_locked(agr_handle* h) {

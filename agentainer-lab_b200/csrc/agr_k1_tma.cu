@@ -59,8 +59,6 @@ k1_ingest_tma(const __grid_constant__ CUtensorMap tmap, const agr_dev d, const u
     if (threadIdx.x < K1_NLC) s_ctr[threadIdx.x] = 0;
     if (threadIdx.x < WARPS * STAGES) mbar_init(smem_u32(&bars[threadIdx.x]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // k1_post is launched as a programmatic dependent: its CTAs may be scheduled as ours retire (it waits for this grid to complete)
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
 
     uint32_t lc[K1_NLC + 1];

@@ -10,22 +10,6 @@
 // All arithmetic is integer / byte work bounded by HBM bandwidth; there is no tensor-core work on this path.
 #include "agr_device.cuh"
 
-// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may be scheduled while its predecessor in the stream
-// is still draining, once every CTA of the predecessor has executed pdl_trigger() (or exited); it must not touch anything the
-// predecessor writes before pdl_wait() returns, which is when the predecessor has completed and its writes are visible.  Used
-// on the chain of short maintenance kernels of a ring step (TTL sweep -> release -> tail scan): their launch latencies overlap.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
 
 // v0: each warp owns 32 consecutive records.  Pass 1: lane i loads the 96 B header of record i (six 16 B loads,
 // every fetched sector fully used) and runs the decision chain thread-per-record, so 32 index inserts are in
@@ -107,8 +91,6 @@ __global__ void __launch_bounds__(WARPS * 32) k1_ingest_v0(const agr_dev d, cons
 //       later row of the same batch) is promoted to stored.
 __global__ void __launch_bounds__(256) k1_post(const agr_dev d, const uint32_t first_rid, const uint32_t n, uint2* __restrict__ verdicts,
                                                uint4* __restrict__ ids, const uint32_t* __restrict__ marks) {
-    pdl_wait();                                     // (launched as a programmatic dependent of the K1 kernel: nothing before this line reads its output)
-    pdl_trigger();
     const uint32_t dupfix = __ldcg(d.dupfix);
     if (blockIdx.x == 0 && threadIdx.x < 4) d.dupfix_next[threadIdx.x] = 0;      // the previous batch is done with these words
     // nothing to do: no in-batch id races, no replay-flagged records to resolve, nobody asked for verdicts or ids
@@ -218,8 +200,6 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
                                                 const unsigned long long ttl, unsigned long long* __restrict__ expired) {
     __shared__ unsigned long long s_min[8];
     __shared__ uint32_t s_cnt;
-    pdl_trigger();
-    pdl_wait();
     const uint32_t c = blockIdx.x;
     const unsigned long long cm = d.cmin[c];
     if (cm == ~0ULL) return;
@@ -269,7 +249,7 @@ __global__ void __launch_bounds__(256) k_expire(const agr_dev d, const unsigned 
 }
 void agr_launch_expire(const agr_dev& d, unsigned long long rows, unsigned long long now, unsigned long long ttl,
                        unsigned long long* expired, cudaStream_t st) {
-    if (rows) launch_pdl(k_expire, (unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256u, st, d, rows, now, ttl, expired);
+    if (rows) k_expire<<<(unsigned)((rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, rows, now, ttl, expired);
 }
 // ---- ring mode (AGR_CFG_RING): releasing rows at the tail
 // offset (from the tail) of the first row that still holds a stored record, among the `live` rows behind the tail.
@@ -283,7 +263,6 @@ __global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsig
                                                     uint32_t* __restrict__ scratch /* [0] offset found, [1] ticket */,
                                                     unsigned long long* __restrict__ out) {
     __shared__ uint32_t s_last;
-    pdl_wait();
     uint32_t* out_off = scratch;
     const unsigned long long R = d.ring_rows, tp = d.tail_phys;
     const unsigned long long p0 = (unsigned long long)blockIdx.x * AGR_CHUNK_ROWS;
@@ -323,14 +302,12 @@ __global__ void __launch_bounds__(256) k_first_live(const agr_dev d, const unsig
     }
 }
 void agr_launch_first_live(const agr_dev& d, unsigned long long live, bool use_cmin, uint32_t* scratch, void* out, cudaStream_t st) {
-    launch_pdl(k_first_live, (unsigned)((d.ring_rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256u, st, d, live, use_cmin ? 1u : 0u, scratch,
-               (unsigned long long*)out);
+    k_first_live<<<(unsigned)((d.ring_rows + AGR_CHUNK_ROWS - 1) / AGR_CHUNK_ROWS), 256, 0, st>>>(d, live, use_cmin ? 1u : 0u, scratch,
+                                                                                                 (unsigned long long*)out);
 }
 // rows tail .. tail + count go back to the pool: every per-row word reads "no record"
 __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uint32_t count, uint32_t* __restrict__ resp_len,
                                                       uint32_t* __restrict__ resp_hlen, uint32_t* __restrict__ err_len) {
-    pdl_trigger();
-    pdl_wait();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const uint32_t p = row_physical(d, d.tail + k);
@@ -338,7 +315,7 @@ __global__ void __launch_bounds__(256) k_release_rows(const agr_dev d, const uin
     resp_len[p] = 0; resp_hlen[p] = 0; err_len[p] = 0;      // (the chunk's time bound stays a valid lower bound of what is left)
 }
 void agr_launch_release_rows(const agr_dev& d, uint32_t count, uint32_t* resp_len, uint32_t* resp_hlen, uint32_t* err_len, cudaStream_t st) {
-    if (count) launch_pdl(k_release_rows, (count + 255u) / 256u, 256u, st, d, count, resp_len, resp_hlen, err_len);
+    if (count) k_release_rows<<<(count + 255u) / 256u, 256, 0, st>>>(d, count, resp_len, resp_hlen, err_len);
 }
 // how far back from the byte slab's head (physical offset `head`) the oldest blob lies that a live row still refers to
 __global__ void __launch_bounds__(256) k_bytes_span(const agr_dev d, const unsigned long long head, const unsigned long long cap,
@@ -471,7 +448,7 @@ cudaError_t agr_launch_k1_tma(uint32_t variant, const void* map, const agr_dev& 
 
 void agr_launch_k1_post(const agr_dev& d, uint32_t first_rid, uint32_t n, int sm_count, cudaStream_t st, void* verdicts, void* ids,
                         const uint32_t* marks) {
-    if (n) launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, marks);
+    if (n) k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, marks);
 }
 
 void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t variant, const void* tmap, int sm_count,
@@ -482,7 +459,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
         agr_launch_k1_tma(variant & 0xfu, tmap, d, first_rid, n, (variant >> 8) & 0xffu, sm_count, st);
         if (ev1) cudaEventRecord(ev1, st);
         if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-        launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, (const uint32_t*)d.marks);
+        k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, d.marks);
         return;
     }
     constexpr int WARPS = 8;
@@ -493,7 +470,7 @@ void agr_launch_k1(const agr_dev& d, uint32_t first_rid, uint32_t n, uint32_t va
     k1_ingest_v0<WARPS><<<blocks, WARPS * 32, 0, st>>>(d, first_rid, n);
     if (ev1) cudaEventRecord(ev1, st);
     if ((d.cfg_flags & AGR_CFGI_SPLIT_INDEX) && !(d.cfg_flags & AGR_CFG_MINT_IDS)) k1_index<<<(n + 255u) / 256u, 256, 0, st>>>(d, first_rid, n);
-    launch_pdl(k1_post, k1_post_blocks(n, sm_count), 256u, st, d, first_rid, n, (uint2*)verdicts, (uint4*)ids, (const uint32_t*)nullptr);
+    k1_post<<<k1_post_blocks(n, sm_count), 256, 0, st>>>(d, first_rid, n, (uint2*)verdicts, (uint4*)ids, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K2
