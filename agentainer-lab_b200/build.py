@@ -11,7 +11,7 @@ LIBDIR = os.path.join(_HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIBNAME = "libagentainer_b200.so"
 SOURCES = ["agr_kernels.cu", "agr_k1_tma.cu", "agr_k1_var.cu", "agr_k4.cu", "agr_k5_json.cu", "agr_svc.cu", "agr_json_host.cpp", "agr_engine.cu"]
-HEADERS = ["agr_common.h", "agr_synth.h", "agr_kernels.cuh", "agr_device.cuh", "agr_svc.h", os.path.join("..", "..", "include", "agentainer_gpu.h")]
+HEADERS = ["agr_common.h", "agr_synth.h", "agr_kernels.cuh", "agr_device.cuh", "agr_svc.h", "agr_ring.hpp", os.path.join("..", "..", "include", "agentainer_gpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -30,6 +30,7 @@
 #include <sched.h>
 #include <time.h>
 #include <sys/prctl.h>
+#include "agr_ring.hpp"
 
 static_assert(sizeof(agr_record) == 512, "agr_record must be 512 B");
 static_assert(sizeof(agr_outcome) == 64, "agr_outcome must be 64 B");
@@ -305,10 +306,6 @@ struct svc_host {
     alignas(64) std::mutex smu; std::condition_variable scv;   // the dispatcher sleeps here when the ring has been empty for a while
 };
 
-static inline void cpu_relax(uint32_t& spins) {
-    if (++spins < 4096u) _mm_pause();
-    else { sched_yield(); }
-}
 
 static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only);
 // stops the resident kernel; the caller holds h->mu, so no new batch can be published meanwhile
@@ -372,9 +369,10 @@ struct HLock {
 static void svc_fail_ops(svc_host* s, uint64_t from, uint64_t to, int rc, bool records_only) {
     for (uint64_t a = from; a < to; ++a) {
         const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
-        const uint32_t kd = s->ready[slot].load(std::memory_order_relaxed) & 3u;
+        const uint32_t rw = s->ready[slot].load(std::memory_order_relaxed), kd = rw & 3u;
         const bool rec = kd == SVC_OP_RECORD;
-        if (kd == SVC_OP_SKIP || (records_only && !rec)) continue;                  // (a skipped slot has no waiter and keeps its old answer)
+        // (a skipped slot has no waiter and keeps its old answer; it may even have been published again for the NEXT lap already)
+        if ((rw >> 2) != (uint32_t)(a / SVC_SLOTS) + 1u || kd == SVC_OP_SKIP || (records_only && !rec)) continue;
         svc_res* r = s->res + slot;
         r->w[0] = rec ? 0u : (uint32_t)rc; r->w[1] = rec ? (uint32_t)rc : 0u; r->w[2] = 0;
         std::atomic_thread_fence(std::memory_order_release);
@@ -544,84 +542,8 @@ static void svc_destroy(agr_handle* h) {
     delete s;
 }
 
-// caller side: claim n slots, write the payloads, publish, wake the dispatcher if it sleeps.  Returns the first slot.
-// Slot reuse.  A caller that draws slot number a (lap = a / SVC_SLOTS of the ring) may overwrite the slot's payload and ready
-// word only when the op one lap earlier is completely over: the dispatcher has consumed its ready word, the GPU has answered it
-// and its caller has collected the answer (svc_release puts SVC_COLLECTED into the answer's tag).  The first two depend on
-// the dispatcher and the GPU alone and are waited for.  The third depends on ANOTHER CALLER — the holder of that ticket, who may
-// itself be inside a submit, waiting for one of our uncollected tickets — so it is never waited for beyond a short spin:
-// the slot is published as a no-op instead (the ring moves on, the uncollected answer stays intact) and the caller is told to
-// collect and come again (AGR_EAGAIN from agr_submit_*; the blocking calls, which hold no tickets, simply take the next slot).
-static bool svc_slot_free(svc_host* s, uint64_t a, uint32_t slot, uint32_t lap) {
-    if (!lap) return true;
-    const uint32_t prev = svc_tag(a - SVC_SLOTS);
-    // usual case: the previous lap's op was a real one and is over (its tag in the cell says all three at once — and the ready
-    // word, which sits in the dispatcher's cache, need not be read)
-    if ((s->res[slot].w[3] >> 16) == (prev | SVC_COLLECTED)) return true;
-    uint32_t w = 0;
-    while (s->scanned.load(std::memory_order_acquire) <= a - SVC_SLOTS) cpu_relax(w);     // its ready word has been consumed
-    const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
-    if ((rw & 3u) != SVC_OP_SKIP) {
-        w = 0;
-        while (((s->res[slot].w[3] >> 16) & 0x7fffu) != prev) cpu_relax(w);                // answered (GPU, or svc_fail_ops)
-    }
-    // the previous lap was a no-op: the cell holds an older answer (or none at all)
-    for (uint32_t k = 0; k < 2000u; ++k) {                                                   // ~0.1 ms of patience
-        const uint32_t t = s->res[slot].w[3] >> 16;
-        if (t == 0u || (t & SVC_COLLECTED)) return true;
-        _mm_pause();
-    }
-    return false;
-}
-// hands ONE operation over.  true: *abs is its slot (ticket); false: the slot it drew was not free (see above).
-static bool svc_submit_one(svc_host* s, uint32_t kind, const void* item, size_t item_bytes, uint64_t* abs) {
-    const uint64_t a = s->head.fetch_add(1, std::memory_order_relaxed);
-    const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
-    const bool ok = svc_slot_free(s, a, slot, lap);
-    if (ok) {
-        std::atomic_thread_fence(std::memory_order_acquire);
-        // streaming stores: the slot's lines were last written by another core a lap ago and are read next by the GPU (DMA),
-        // so pulling them into this core's cache first (read-for-ownership) would only cost a miss per line
-        __m128i* dst = reinterpret_cast<__m128i*>(s->payload + (size_t)slot * SVC_PAYLOAD);
-        const __m128i* src = reinterpret_cast<const __m128i*>(item);
-        for (size_t k = 0; k < item_bytes / 16; ++k) _mm_stream_si128(dst + k, _mm_loadu_si128(src + k));
-        _mm_sfence();
-    }
-    s->ready[slot].store(((lap + 1u) << 2) | (ok ? kind : (uint32_t)SVC_OP_SKIP), std::memory_order_release);
-    if (s->sleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(s->smu); s->scv.notify_one(); }
-    *abs = a;
-    return ok;
-}
-struct svc_answer { uint32_t w0, w1; uint64_t rid; };
-static inline bool svc_try(svc_host* s, uint64_t a, svc_answer* out) {
-    const svc_res* r = s->res + (a & (SVC_SLOTS - 1u));
-    const uint32_t w3 = r->w[3];
-    if ((w3 >> 16) != svc_tag(a)) return false;
-    std::atomic_thread_fence(std::memory_order_acquire);
-    out->w0 = r->w[0]; out->w1 = r->w[1]; out->rid = (uint64_t)r->w[2] | ((uint64_t)(w3 & 0xffffu) << 32);
-    return true;
-}
-// Blocking wait.  The first spin_cpus waiters spin (the answer is ~20 us away); waiters beyond that many would only burn the
-// process's CPU allowance against each other (a container with a CPU quota throttles ALL its threads once it is spent), so they
-// sleep in short naps instead.
-static inline void svc_wait(svc_host* s, uint64_t a, svc_answer* out) {
-    if (svc_try(s, a, out)) return;
-    const uint32_t me = s->waiters.fetch_add(1, std::memory_order_relaxed);
-    if (me < s->spin_cpus) {
-        uint32_t w = 0;
-        while (!svc_try(s, a, out)) cpu_relax(w);
-    } else {
-        static thread_local bool slack_set = false;
-        if (!slack_set) { prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); slack_set = true; }   // naps of tens of us, not the default +50 us
-        struct timespec ts = {0, 25000};
-        while (!svc_try(s, a, out)) nanosleep(&ts, nullptr);
-    }
-    s->waiters.fetch_sub(1, std::memory_order_relaxed);
-}
-static inline void svc_release(svc_host* s, uint64_t a) {       // everything of the answer (and of the payload) has been read
-    std::atomic_thread_fence(std::memory_order_release);
-    s->res[a & (SVC_SLOTS - 1u)].w[3] = (svc_tag(a) | SVC_COLLECTED) << 16;
-}
+// (the callers' side of the ring — svc_submit_one, svc_try, svc_wait, svc_release — is csrc/agr_ring.hpp: the same code runs against a
+// stand-in for the dispatcher and the GPU in tests/ring_sim.cpp, on the CPU)
 // Request.ID of the record in ring slot a: minted from its row, or the caller's own (still in the slot's payload)
 static inline void svc_request_id(agr_handle* h, uint64_t a, uint64_t rid, uint8_t id[16]) {
     if (h->cfg.flags & AGR_CFG_MINT_IDS) {
