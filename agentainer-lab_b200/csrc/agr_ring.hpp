@@ -19,6 +19,12 @@
 #include <sys/prctl.h>
 #include "agr_svc.h"
 
+// The answer cells are written by the GPU (one 16-byte PCIe store) and by host threads (svc_release, svc_fail_ops); their tag word
+// is the synchronising one.  Acquire / release accesses through the compiler's atomic builtins: plain MOVs on x86-64, and a form
+// ThreadSanitizer understands when this header runs against the CPU stand-in (tests/ring_sim.cpp).
+static inline uint32_t svc_tag_word(const svc_res* r) { return __atomic_load_n(&r->w[3], __ATOMIC_ACQUIRE); }
+static inline uint32_t svc_word(const svc_res* r, int k) { return __atomic_load_n(&r->w[k], __ATOMIC_RELAXED); }
+
 static inline void cpu_relax(uint32_t& spins) {
     if (++spins < 4096u) _mm_pause();
     else { sched_yield(); }
@@ -37,17 +43,17 @@ static bool svc_slot_free(H* s, uint64_t a, uint32_t slot, uint32_t lap) {
     const uint32_t prev = svc_tag(a - SVC_SLOTS);
     // usual case: the previous lap's op was a real one and is over (its tag in the cell says all three at once — and the ready
     // word, which sits in the dispatcher's cache, need not be read)
-    if ((s->res[slot].w[3] >> 16) == (prev | SVC_COLLECTED)) return true;
+    if ((svc_tag_word(&s->res[slot]) >> 16) == (prev | SVC_COLLECTED)) return true;
     uint32_t w = 0;
     while (s->scanned.load(std::memory_order_acquire) <= a - SVC_SLOTS) cpu_relax(w);     // its ready word has been consumed
     const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
     if ((rw & 3u) != SVC_OP_SKIP) {
         w = 0;
-        while (((s->res[slot].w[3] >> 16) & 0x7fffu) != prev) cpu_relax(w);                // answered (GPU, or svc_fail_ops)
+        while (((svc_tag_word(&s->res[slot]) >> 16) & 0x7fffu) != prev) cpu_relax(w);                // answered (GPU, or svc_fail_ops)
     }
     // the previous lap was a no-op: the cell holds an older answer (or none at all)
     for (uint32_t k = 0; k < 2000u; ++k) {                                                   // ~0.1 ms of patience
-        const uint32_t t = s->res[slot].w[3] >> 16;
+        const uint32_t t = svc_tag_word(&s->res[slot]) >> 16;
         if (t == 0u || (t & SVC_COLLECTED)) return true;
         _mm_pause();
     }
@@ -60,7 +66,6 @@ static bool svc_submit_one(H* s, uint32_t kind, const void* item, size_t item_by
     const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u)), lap = (uint32_t)(a / SVC_SLOTS);
     const bool ok = svc_slot_free(s, a, slot, lap);
     if (ok) {
-        std::atomic_thread_fence(std::memory_order_acquire);
         // streaming stores: the slot's lines were last written by another core a lap ago and are read next by the GPU (DMA),
         // so pulling them into this core's cache first (read-for-ownership) would only cost a miss per line
         __m128i* dst = reinterpret_cast<__m128i*>(s->payload + (size_t)slot * SVC_PAYLOAD);
@@ -77,10 +82,9 @@ struct svc_answer { uint32_t w0, w1; uint64_t rid; };
 template <class H>
 static inline bool svc_try(H* s, uint64_t a, svc_answer* out) {
     const svc_res* r = s->res + (a & (SVC_SLOTS - 1u));
-    const uint32_t w3 = r->w[3];
+    const uint32_t w3 = svc_tag_word(r);
     if ((w3 >> 16) != svc_tag(a)) return false;
-    std::atomic_thread_fence(std::memory_order_acquire);
-    out->w0 = r->w[0]; out->w1 = r->w[1]; out->rid = (uint64_t)r->w[2] | ((uint64_t)(w3 & 0xffffu) << 32);
+    out->w0 = svc_word(r, 0); out->w1 = svc_word(r, 1); out->rid = (uint64_t)svc_word(r, 2) | ((uint64_t)(w3 & 0xffffu) << 32);
     return true;
 }
 // Blocking wait.  The first spin_cpus waiters spin (the answer is ~20 us away); waiters beyond that many would only burn the
@@ -103,6 +107,5 @@ static inline void svc_wait(H* s, uint64_t a, svc_answer* out) {
 }
 template <class H>
 static inline void svc_release(H* s, uint64_t a) {       // everything of the answer (and of the payload) has been read
-    std::atomic_thread_fence(std::memory_order_release);
-    s->res[a & (SVC_SLOTS - 1u)].w[3] = (svc_tag(a) | SVC_COLLECTED) << 16;
+    __atomic_store_n(&s->res[a & (SVC_SLOTS - 1u)].w[3], (svc_tag(a) | SVC_COLLECTED) << 16, __ATOMIC_RELEASE);
 }

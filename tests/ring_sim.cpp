@@ -63,9 +63,9 @@ int main(int argc, char** argv) {
                 uint64_t token; memcpy(&token, S.payload + (size_t)slot * SVC_PAYLOAD, 8);
                 const uint64_t ans = mix(token ^ a);                                   // depends on the payload AND the slot number
                 svc_res* r = S.res + slot;
-                r->w[0] = (uint32_t)ans | 1u; r->w[1] = (uint32_t)(ans >> 32); r->w[2] = (uint32_t)kind;
-                std::atomic_thread_fence(std::memory_order_release);
-                r->w[3] = svc_tag(a) << 16;
+                __atomic_store_n(&r->w[0], (uint32_t)ans | 1u, __ATOMIC_RELAXED); __atomic_store_n(&r->w[1], (uint32_t)(ans >> 32), __ATOMIC_RELAXED);
+                __atomic_store_n(&r->w[2], (uint32_t)kind, __ATOMIC_RELAXED);
+                __atomic_store_n(&r->w[3], svc_tag(a) << 16, __ATOMIC_RELEASE);                 // (the kernel: one 16-byte store)
                 served++;
             }
         }

@@ -33,3 +33,19 @@ def test_ring_protocol_on_cpu(ring_sim, args):
     assert res.returncode == 0 and d["ok"] and d["wrong_answers"] == 0 and d["served"] == d["operations"], d
     if int(args[1]) * int(args[2]) > 16384:
         assert d["eagain"] > 0 and d["skipped_slots"] >= d["eagain"], d      # the oversubscribed runs really went through the no-op path
+
+
+def test_ring_protocol_under_thread_sanitizer(tmp_path):
+    """The same simulation built with -fsanitize=thread: the shipped caller-side code (acquire / release accesses on the answer
+    cells, release / acquire on the ready words, streaming stores behind an sfence) has no data race ThreadSanitizer can see."""
+    exe = str(tmp_path / "ring_sim_tsan")
+    res = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-o", exe, os.path.join(ROOT, "tests", "ring_sim.cpp")],
+                         capture_output=True, text=True, timeout=300)
+    if res.returncode != 0:
+        pytest.skip("no ThreadSanitizer runtime in this image: " + res.stderr[-200:])
+    assert "-Wtsan" not in res.stderr                       # (atomic_thread_fence is not modelled by TSAN: the header must not need it)
+    for args in (("1", "3", "512", "10000"), ("0", "8", "4096", "6000", "20")):
+        run = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+        assert "ThreadSanitizer" not in run.stderr, run.stderr[-2000:]
+        d = json.loads(run.stdout.strip().splitlines()[-1])
+        assert run.returncode == 0 and d["ok"], d
