@@ -391,15 +391,7 @@ static void svc_dispatcher(agr_handle* h) {
     uint32_t nrec = 0;
     uint32_t kinds[SVC_MAX_OPS / 16] = {0};
     while (!s->shutdown.load(std::memory_order_acquire)) {
-        while (to - s->taken < SVC_MAX_OPS) {
-            const uint32_t slot = (uint32_t)(to & (SVC_SLOTS - 1u));
-            const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
-            if ((rw >> 2) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
-            if ((rw & 3u) == SVC_OP_RECORD) { if (nrec == 128u) break; nrec++; }
-            kinds[(to - s->taken) >> 4] |= (rw & 3u) << (((to - s->taken) & 15u) * 2u);
-            to++;
-        }
-        if (to != s->scanned.load(std::memory_order_relaxed)) s->scanned.store(to, std::memory_order_release);
+        svc_scan(s, s->taken, &to, &nrec, kinds, 128u);           // (csrc/agr_ring.hpp: shared with the CPU simulation of the ring)
         const auto now = std::chrono::steady_clock::now();
         if (to == s->taken) {
             const auto idle = std::chrono::duration_cast<std::chrono::microseconds>(now - last_work).count();

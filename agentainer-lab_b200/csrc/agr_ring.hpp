@@ -109,3 +109,22 @@ template <class H>
 static inline void svc_release(H* s, uint64_t a) {       // everything of the answer (and of the payload) has been read
     __atomic_store_n(&s->res[a & (SVC_SLOTS - 1u)].w[3], (svc_tag(a) | SVC_COLLECTED) << 16, __ATOMIC_RELEASE);
 }
+
+// ---- the dispatcher's side of the ready words
+// Grows the contiguous published prefix [taken, *to) by whatever has been published since: at most SVC_MAX_OPS operations and
+// max_records records per batch.  A slot is looked at until it is published and never again (re-reading the callers' ready words
+// every iteration keeps pulling their cache lines away from the cores that write them), and an operation's kind is noted in
+// kinds[] (2 bits each, the batch descriptor's form) AT THAT MOMENT: a no-op slot may be published again, for the next lap, as soon
+// as `scanned` has passed it.  Publishes the new scan position.
+template <class H>
+static inline void svc_scan(H* s, const uint64_t taken, uint64_t* to, uint32_t* nrec, uint32_t* kinds, const uint32_t max_records) {
+    while (*to - taken < SVC_MAX_OPS) {
+        const uint32_t slot = (uint32_t)(*to & (SVC_SLOTS - 1u));
+        const uint32_t rw = s->ready[slot].load(std::memory_order_acquire);
+        if ((rw >> 2) != (uint32_t)(*to / SVC_SLOTS) + 1u) break;
+        if ((rw & 3u) == SVC_OP_RECORD) { if (*nrec == max_records) break; (*nrec)++; }
+        kinds[(*to - taken) >> 4] |= (rw & 3u) << (((*to - taken) & 15u) * 2u);
+        (*to)++;
+    }
+    if (*to != s->scanned.load(std::memory_order_relaxed)) s->scanned.store(*to, std::memory_order_release);
+}

@@ -44,21 +44,15 @@ int main(int argc, char** argv) {
     // up to SVC_MAX_OPS, answer every real operation with ONE 16-byte result whose last word carries the lap tag (like k_svc)
     std::thread service([&] {
         uint64_t to = 0;
-        uint8_t kinds[SVC_MAX_OPS];                                                    // captured at scan time, like the batch descriptor:
-        while (!quit.load(std::memory_order_acquire)) {                                // a no-op slot may be republished for the next lap
-            const uint64_t from = to;                                                  // as soon as `scanned` has passed it
-            while (to - from < SVC_MAX_OPS) {
-                const uint32_t rw = S.ready[to & (SVC_SLOTS - 1u)].load(std::memory_order_acquire);
-                if ((rw >> 2) != (uint32_t)(to / SVC_SLOTS) + 1u) break;
-                kinds[to - from] = (uint8_t)(rw & 3u);
-                to++;
-            }
+        while (!quit.load(std::memory_order_acquire)) {
+            const uint64_t from = to;
+            uint32_t nrec = 0, kinds[SVC_MAX_OPS / 16] = {0};
+            svc_scan(&S, from, &to, &nrec, kinds, 128u);                               // the dispatcher's own scan (agr_ring.hpp)
             if (to == from) { std::this_thread::yield(); continue; }
-            S.scanned.store(to, std::memory_order_release);
             if (delay_us) std::this_thread::sleep_for(std::chrono::microseconds(delay_us));     // the batch is "on the GPU"
             for (uint64_t a = from; a < to; ++a) {
                 const uint32_t slot = (uint32_t)(a & (SVC_SLOTS - 1u));
-                const uint32_t kind = kinds[a - from];
+                const uint32_t kind = (kinds[(a - from) >> 4] >> (((a - from) & 15u) * 2u)) & 3u;
                 if (kind == SVC_OP_SKIP) { skipped++; continue; }
                 uint64_t token; memcpy(&token, S.payload + (size_t)slot * SVC_PAYLOAD, 8);
                 const uint64_t ans = mix(token ^ a);                                   // depends on the payload AND the slot number
